@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — output frames/s of the CRFP hot path (CRFP_DSV.forward) on B200, per the driver contract.
+
+A "step" is one forward of one synthetic clip (per rank) through the drop-in module:
+  workload "R-lit"  : LR 180x320 (REDS *_sharp_BI frames, BASELINE.json configs[1]) through the x8 network
+                      -> 1440x2560, t frames (default 100)
+  workload "R-nat"  : LR 90x160 -> 720x1280 (the x8 network's native route to 1280x720)
+  workload "V7"     : LR 64x112, t=7 (configs[0], the reference's CPU-runnable case)
+`value`  = frames/s with the clip already resident in HBM (CUDA events, max over ranks).
+`e2e`    = frames/s through the public API from HOST buffers: pinned lrs + fovea patches + coords H2D, forward,
+           output frames D2H, all inside the timed region.
+`roofline` = the align kernel (DCNv2 @L1, the kernel BASELINE.json's metric names) timed alone through the C ABI.
+`cpu_baseline` / `--impl reference` = the oracle port of the reference's PyTorch path on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {"R-lit": (180, 320, 100), "R-nat": (90, 160, 100), "V7": (64, 112, 7)}
+METRIC = "output frames/sec"
+ALIGN_BYTES_PER_L1_PX = 1120  # (32 in + 144 offset + 72 mask + 32 out) fp32, SURVEY.md 8(d)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="crfp_b200", choices=["crfp_b200", "reference"])
+    ap.add_argument("--workload", default="R-lit", choices=list(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=0, help="override frames per clip")
+    ap.add_argument("--clips", type=int, default=1, help="clips per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_fps(h, w, frames, threads):
+    """The reference's PyTorch path (oracle port, bit-identical to the reference on CPU) on the host cores."""
+    import torch
+    from crfp_b200.synthetic import make_clip, make_state_dict
+    from oracle import crfp_oracle as O
+    torch.set_num_threads(threads)
+    sd = make_state_dict(seed=1)
+    lrs, fvs, mks, _ = make_clip(seed=2, n=1, t=frames, h=h, w=w, fv_size=96)
+    t0 = time.perf_counter()
+    out = O.crfp_dsv_forward(sd, lrs, fvs, mks)
+    dt = time.perf_counter() - t0
+    assert out.shape[1] == frames
+    return frames / dt, dt
+
+
+def run_reference(args):
+    """`--impl reference`: rank 0 times the CPU path on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    h, w, _ = WORKLOADS[args.workload]
+    frames = 2
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_reference_fps(h, w, frames, cores)
+    times = []
+    for _ in range(args.steps):
+        _, dt = cpu_reference_fps(h, w, frames, cores)
+        times.append(dt)
+    total = sum(times)
+    value = frames * args.steps / total
+    sample = f"{frames}-frame clip of {args.workload} (LR {h}x{w} -> {8 * h}x{8 * w}) per step, oracle port, torch CPU fp32"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: LR {h}x{w} -> {8 * h}x{8 * w} (x8 network), {frames} frames/step",
+                   "clips_per_gpu": 1},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def time_align_kernel(torch, h1, w1, reps=20):
+    """Average device time of the DCNv2 @L1 align kernel alone (C ABI), inputs > L2 so every launch is cold."""
+    import ctypes as C
+    from crfp_b200 import _lib as L
+    from crfp_b200.packing import pack_dcn
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(0)
+    nbuf = 3  # rotate buffers: 3 x (29 + 199) MB > 126 MB L2
+    xs = [torch.randn(1, h1, w1, 32, generator=g).to(dev) for _ in range(nbuf)]
+    oms = []
+    for _ in range(nbuf):
+        om = torch.empty(1, h1, w1, 216)
+        om[..., :144] = torch.randn(1, h1, w1, 144, generator=g) * 3.0
+        om[..., 144:] = torch.rand(1, h1, w1, 72, generator=g)
+        oms.append(om.to(dev))
+    wp, bp = pack_dcn((torch.randn(32, 32, 3, 3, generator=g) * 0.05).to(dev), torch.zeros(32).to(dev), 8)
+    out = torch.empty(1, h1, w1, 32, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def launch(i):
+        d = L.DcnDesc(n=1, h=h1, w=w1, c=32, cout=32, dg=8, shared_taps=0, x=xs[i % nbuf].data_ptr(), x_cstride=32,
+                      x_coffset=0, offset=oms[i % nbuf].data_ptr(), off_cstride=216, off_coffset=0,
+                      mask=oms[i % nbuf].data_ptr(), mask_cstride=216, mask_coffset=144, weight=wp.data_ptr(),
+                      bias=bp.data_ptr(), out=out.data_ptr(), out_cstride=32, out_coffset=0)
+        L.check(L.lib().crfp_dcn_v2_fwd(C.byref(d), st), "dcn_v2")
+
+    for i in range(3):
+        launch(i)
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for i, (a, b) in enumerate(evs):
+        a.record()
+        launch(i)
+        b.record()
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in evs)
+    return sum(ms) / len(ms)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from crfp_b200 import CRFP_DSV, _lib
+    from crfp_b200.synthetic import make_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    h, w, t = WORKLOADS[args.workload]
+    if args.frames:
+        t = args.frames
+    n = args.clips
+    H, W_ = 8 * h, 8 * w
+    fv = 96
+
+    model = CRFP_DSV("cuda", mid_channels=32).eval()
+    model.load_state_dict(make_state_dict(seed=1), strict=True)
+    model.to(dev)
+
+    # synthetic clip: smooth-ish LR frames, Gaussian gaze, random fovea patch; seeded per rank
+    g = torch.Generator(device="cpu").manual_seed(100 + rank)
+    coarse = torch.rand(n, t, 3, max(h // 8, 2), max(w // 8, 2), generator=g)
+    lrs_h = torch.nn.functional.interpolate(coarse.view(n * t, 3, *coarse.shape[-2:]), size=(h, w), mode="bicubic",
+                                            align_corners=False).view(n, t, 3, h, w)
+    lrs_h = (lrs_h + 0.05 * torch.rand(n, t, 3, h, w, generator=g)).clamp_(0, 1).contiguous().pin_memory()
+    patch_h = torch.rand(n, t, 3, fv, fv, generator=g).pin_memory()
+    gy = (torch.randn(n, t, generator=g) * 50 + H / 2).floor().long() - fv // 2
+    gx = (torch.randn(n, t, generator=g) * 50 + W_ / 2).floor().long() - fv // 2
+    coords = torch.stack([gy.clamp(0, H - fv), gx.clamp(0, W_ - fv)], -1)
+
+    def build_inputs():
+        lrs = lrs_h.to(dev, non_blocking=True)
+        patch = patch_h.to(dev, non_blocking=True)
+        fvs = torch.zeros(n, t, 3, H, W_, device=dev)
+        mks = torch.zeros(n, t, 1, H, W_, device=dev, dtype=torch.bool)
+        for b in range(n):
+            for i in range(t):
+                y, x = int(coords[b, i, 0]), int(coords[b, i, 1])
+                fvs[b, i, :, y:y + fv, x:x + fv] = patch[b, i]
+                mks[b, i, :, y:y + fv, x:x + fv] = True
+        return lrs, fvs, mks
+
+    lrs, fvs, mks = build_inputs()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput
+    for _ in range(args.warmup):
+        out = model(lrs, fvs, mks)
+    barrier()
+    _lib.lib().crfp_launch_count_reset()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = model(lrs, fvs, mks)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = int(_lib.lib().crfp_launch_count())
+    clocks = sampler.stop() if rank == 0 else None
+    assert torch.isfinite(out[:, -1]).all()
+    tms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    frames_total = world * n * t * args.steps
+    value = frames_total / (ms_max * 1e-3)
+
+    # ---------------- end-to-end through the public API from host buffers
+    e2e = None
+    if not args.no_e2e:
+        out_h = torch.empty(n, t, 3, H, W_, dtype=torch.float32).pin_memory()
+        coords_dev_free = coords  # coords stay on the host: forward_patch reads them as integers
+
+        def e2e_step():
+            o = model.forward_patch(lrs_h.to(dev, non_blocking=True), patch_h.to(dev, non_blocking=True), coords_dev_free)
+            out_h.copy_(o, non_blocking=True)
+
+        del fvs, mks
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        ems = torch.tensor([max(e0.elapsed_time(e1), wall)], device=dev)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": frames_total / (float(ems.item()) * 1e-3), "unit": "frames/s",
+               "h2d_bytes_per_step": int(lrs_h.numel() * 4 + patch_h.numel() * 4 + coords.numel() * 8),
+               "d2h_bytes_per_step": int(out_h.numel() * 4),
+               "api": "CRFP_DSV.forward_patch(lrs, fovea_patch, coords) -> frames copied to pinned host memory"}
+        del out_h
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the align kernel (timed alone, cold inputs)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    k_ms = time_align_kernel(torch, 2 * h, 2 * w)
+    alg_bytes = ALIGN_BYTES_PER_L1_PX * (2 * h) * (2 * w)
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    roofline = {"kernel": "dcn_l1_kernel (DCNv2 align @L1, C=32 dg=8)", "bound": "hbm", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_ms,
+                "timing": "kernel timed alone through crfp_dcn_v2_fwd, CUDA events, 3 rotating input sets > L2"}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        fr = 2
+        fps, dt = cpu_reference_fps(h, w, fr, cores)
+        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": f"{fr}-frame clip of {args.workload} (LR {h}x{w}), oracle port of the reference's PyTorch path, "
+                         f"torch CPU fp32, {dt:.1f} s"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: LR {h}x{w} -> {H}x{W_} (x8 network; BASELINE.json configs[1]), "
+                               f"{t}-frame clip, fovea 96x96, CRFP_DSV mid_channels=32",
+                   "clips_per_gpu": n, "frames_per_clip": t, "parallelism": f"clip-sharded x{world}, no collective",
+                   "l2": "per-step working set (>= 4 GB of HR planes) exceeds the 126 MB L2"},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

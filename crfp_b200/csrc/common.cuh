@@ -1,0 +1,155 @@
+// Shared helpers for libcrfp_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/crfp_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libcrfp_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace crfp {
+
+// ---- status / launch accounting (thread-local, no global mutable state shared between callers)
+void note_cuda_error(cudaError_t e);
+void count_launch();
+
+inline int check_launch() {
+  cudaError_t e = cudaPeekAtLastError();
+  count_launch();
+  if (e != cudaSuccess) {
+    note_cuda_error(e);
+    (void)cudaGetLastError();
+    return CRFP_ERR_CUDA;
+  }
+  return CRFP_OK;
+}
+
+#define CRFP_TRY(expr)          \
+  do {                          \
+    int _s = (expr);            \
+    if (_s != CRFP_OK) return _s; \
+  } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- internal conv description (superset of the public crfp_conv_desc)
+enum {
+  EPI_STD = 0,       // bias, act, residual, post_scale, NHWC segments / pixel shuffle
+  EPI_BLEND = 1,     // thin only: S = lrelu(m*v + (1-m)*S_old)       (model/CRFP.py:1674-1675)
+  EPI_OUT_NCHW = 2   // thin only: planar NCHW output + bilinear x8 base of the LR frame (model/CRFP.py:1678-1683)
+};
+
+struct ConvParams {
+  int n, h, w;
+  int nsrc;
+  const float* src[3];
+  int src_c[3], src_cstride[3], src_coffset[3], src_mode[3];
+  int qstart[4];     // first packed quad of each source; qstart[nsrc] = total real quads
+  int cin_packed;    // multiple of 8
+  int cout;          // real
+  int cout_packed;   // wide: multiple of 32; thin: 4
+  int act;
+  const float* weight;
+  const float* bias;
+  int out_mode, shuffle_r;
+  int ndst;
+  float* dst[2];
+  int dst_c[2], dst_cstride[2], dst_coffset[2];
+  const float* residual;
+  int res_cstride, res_coffset;
+  const float* flow;
+  int head_split;
+  float post_scale, head_mag;
+  // special epilogues (thin kernels)
+  int epi;
+  const uint8_t* mask;            // EPI_BLEND: bool (1,H,W) per clip
+  long long mask_clip_stride;
+  const float* blend_old;         // EPI_BLEND: NHWC 4ch tensor holding S_old
+  const float* fg;                // optional regional mask fp32 (1,H,W) per clip multiplied into every source
+  long long fg_clip_stride;
+  const float* base_lr4;          // EPI_OUT_NCHW: NHWC4 LR frame
+  long long base_clip_stride;
+  long long out_clip_stride;      // EPI_OUT_NCHW: floats between clips of the planar output
+  int out_planes;                 // EPI_OUT_NCHW: number of planes written (3)
+};
+
+int conv_params_from_desc(const crfp_conv_desc* d, ConvParams* p);
+int launch_conv_wide(const ConvParams& p, cudaStream_t st);
+int launch_conv_thin(const ConvParams& p, cudaStream_t st);
+int launch_conv(const ConvParams& p, cudaStream_t st);  // dispatch on cout
+int launch_flow_warp(const crfp_warp_desc& d, cudaStream_t st);
+int launch_dcn(const crfp_dcn_desc& d, cudaStream_t st);
+
+// ---- device helpers
+__device__ __forceinline__ float lrelu01(float v) { return v > 0.f ? v : 0.1f * v; }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == CRFP_ACT_LRELU) return lrelu01(v);
+  if (act == CRFP_ACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+
+// Packed-quad loader shared by the conv kernels: 4 consecutive packed input channels (quad `vq`) of the
+// channel-concatenated input at pixel (n, y, x); zero outside the image and in padding channels.
+__device__ __forceinline__ float4 load_quad(const ConvParams& P, int vq, int n, int y, int x) {
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (y < 0 || y >= P.h || x < 0 || x >= P.w) return r;
+  int s = 0;
+  if (P.nsrc > 1 && vq >= P.qstart[1]) s = 1;
+  if (P.nsrc > 2 && vq >= P.qstart[2]) s = 2;
+  if (vq >= P.qstart[P.nsrc]) return r;
+  const int lq = vq - P.qstart[s];
+  const float* base = P.src[s];
+  const int cs = P.src_cstride[s], co = P.src_coffset[s];
+  if (P.src_mode[s] == CRFP_SRC_UNSHUFFLE4) {
+    const int hc4 = P.src_c[s] >> 6;  // quads per HR pixel (HR channels / 4)
+    const int sub = lq / hc4, qq = lq - sub * hc4;
+    const int dy = sub >> 2, dx = sub & 3;
+    const size_t pix = ((size_t)n * (P.h * 4) + (y * 4 + dy)) * (size_t)(P.w * 4) + (x * 4 + dx);
+    return __ldg(reinterpret_cast<const float4*>(base + pix * cs + co + qq * 4));
+  }
+  const size_t pix = ((size_t)n * P.h + y) * (size_t)P.w + x;
+  const float* p = base + pix * cs + co + lq * 4;
+  const int rem = P.src_c[s] - lq * 4;
+  const bool vec_ok = ((cs | co) & 3) == 0;
+  if (vec_ok && (rem >= 4 || co + lq * 4 + 4 <= cs)) {
+    r = __ldg(reinterpret_cast<const float4*>(p));
+    if (rem < 4) {
+      if (rem < 3) r.z = 0.f;
+      if (rem < 2) r.y = 0.f;
+      r.w = 0.f;
+    }
+    return r;
+  }
+  r.x = __ldg(p);
+  if (rem > 1) r.y = __ldg(p + 1);
+  if (rem > 2) r.z = __ldg(p + 2);
+  if (rem > 3) r.w = __ldg(p + 3);
+  return r;
+}
+
+__device__ __forceinline__ float4 load_quad_fg(const ConvParams& P, int vq, int n, int y, int x) {
+  float4 v = load_quad(P, vq, n, y, x);
+  if (P.fg != nullptr && y >= 0 && y < P.h && x >= 0 && x < P.w) {
+    const float f = __ldg(P.fg + (size_t)n * P.fg_clip_stride + (size_t)y * P.w + x);
+    v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+  }
+  return v;
+}
+
+// nn.Upsample / F.interpolate bilinear, align_corners=False: source index and lerp weight
+__device__ __forceinline__ void bilin_src(int dst, float rscale, int size, int& i0, int& i1, float& l1) {
+  float s = rscale * ((float)dst + 0.5f) - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s;
+  if (i0 > size - 1) i0 = size - 1;
+  i1 = i0 + ((i0 < size - 1) ? 1 : 0);
+  l1 = s - (float)i0;
+}
+
+}  // namespace crfp

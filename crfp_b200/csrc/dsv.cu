@@ -1,0 +1,512 @@
+// CRFP_DSV composite entry points: the clip-level stage (flows + LR features) and one recurrent frame step.
+// Reference: /root/reference/model/CRFP.py:1483-1508 (compute_flow), 797-814 (FNet), 1510-1686 (forward).
+// Everything here is host-side sequencing of the library's own kernels on the caller's stream, inside the
+// caller's workspace; no allocation, no synchronisation.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace crfp {
+
+// ------------------------------------------------------------------------------------------------ layer table
+enum Layer {
+  L_FNET_E1_0, L_FNET_E1_2, L_FNET_E2_0, L_FNET_E2_2, L_FNET_E3_0, L_FNET_E3_2,
+  L_FNET_D1_0, L_FNET_D1_2, L_FNET_D2_0, L_FNET_D2_2, L_FNET_D3_0, L_FNET_D3_2,
+  L_FNET_F0, L_FNET_F2,
+  L_ENC_LR_0, L_ENC_LR_2,
+  L_UPSAMPLE, L_DOWNSAMPLE,
+  L_DCN0_B0, L_DCN0_B2, L_DCN0_HEADS, L_DCN0_DCN,
+  L_DCN1_B0, L_DCN1_B2, L_DCN1_FUSE, L_DCN1_HEADS, L_DCN1_DCN,
+  L_DCN2_B0, L_DCN2_B2, L_DCN2_FUSE, L_DCN2_HEADS, L_DCN2_DCN,
+  L_RES0_IN, L_RES0_IN_FIRST, L_RES0_C1, L_RES0_C2,
+  L_RES1_IN, L_RES1_IN_FIRST, L_RES1_C1, L_RES1_C2,
+  L_RES2_IN, L_RES2_IN_FIRST, L_RES2_C1, L_RES2_C2,
+  L_UPSAMPLE_POST,
+  L_DCN3_UP, L_DCN3_B0, L_DCN3_B2, L_DCN3_FUSE, L_DCN3_HEADS, L_DCN3_DCN,
+  L_RES3_IN, L_RES3_IN_FIRST, L_RES3_C1, L_RES3_C2,
+  L_ENC_HR_0, L_ENC_HR_2, L_TTTF, L_LAST,
+  L_COUNT
+};
+static_assert(L_COUNT <= CRFP_DSV_MAX_LAYERS, "layer table too large");
+
+#define CONV1(key, cin, cout) {key, nullptr, 0, 1, {cin, 0, 0}, {0, 0, 0}, cout, 0, 0, (cout) <= 4}
+static const crfp_layer_info kLayers[L_COUNT] = {
+    {"spynet.encoder1.0", nullptr, 0, 2, {3, 3, 0}, {0, 0, 0}, 32, 0, 0, 0},
+    CONV1("spynet.encoder1.2", 32, 32),
+    CONV1("spynet.encoder2.0", 32, 64), CONV1("spynet.encoder2.2", 64, 64),
+    CONV1("spynet.encoder3.0", 64, 128), CONV1("spynet.encoder3.2", 128, 128),
+    CONV1("spynet.decoder1.0", 128, 256), CONV1("spynet.decoder1.2", 256, 256),
+    CONV1("spynet.decoder2.0", 256, 128), CONV1("spynet.decoder2.2", 128, 128),
+    CONV1("spynet.decoder3.0", 128, 64), CONV1("spynet.decoder3.2", 64, 64),
+    CONV1("spynet.flow.0", 64, 32), CONV1("spynet.flow.2", 32, 2),
+    CONV1("encoder_lr.slice1.0", 3, 32), CONV1("encoder_lr.slice1.2", 32, 32),
+    CONV1("upsample.upsample_conv", 32, 96),
+    {"downsample.downsample_conv", nullptr, 0, 1, {64, 0, 0}, {CRFP_SRC_UNSHUFFLE4, 0, 0}, 32, 0, 0, 0},
+#define DCN_L1(k, fuse)                                                                        \
+    {"dcn_" #k ".dcn_block.0", nullptr, 0, 3, {32, 32, 2}, {0, 0, 0}, 32, 0, 0, 0},           \
+    CONV1("dcn_" #k ".dcn_block.2", 32, 32),                                                   \
+    fuse                                                                                       \
+    {"dcn_" #k ".dcn_offset", "dcn_" #k ".dcn_mask", 2, 1, {32, 0, 0}, {0, 0, 0}, 216, 0, 8, 0}, \
+    {"dcn_" #k ".dcn", nullptr, 1, 1, {32, 0, 0}, {0, 0, 0}, 32, 0, 8, 0},
+#define FUSE_L1(k) {"dcn_" #k ".conv_fuse", nullptr, 0, 2, {32, 32, 0}, {0, 0, 0}, 32, 0, 0, 0},
+    DCN_L1(0, )
+    DCN_L1(1, FUSE_L1(1))
+    DCN_L1(2, FUSE_L1(2))
+#define RES_L1(k)                                                                                       \
+    {"forward_resblocks_" #k ".main.0", nullptr, 0, 2, {32, 32, 0}, {0, 0, 0}, 32, 0, 0, 0},            \
+    {"forward_resblocks_" #k ".main.0", nullptr, 0, 1, {24, 0, 0}, {0, 0, 0}, 32, 0, 0, 0},             \
+    CONV1("forward_resblocks_" #k ".main.2.0.conv1", 32, 32),                                           \
+    CONV1("forward_resblocks_" #k ".main.2.0.conv2", 32, 32),
+    RES_L1(0) RES_L1(1) RES_L1(2)
+    CONV1("upsample_post.upsample_conv", 24, 64),
+    CONV1("dcn_3.upsample.upsample_conv", 32, 64),
+    {"dcn_3.dcn_block.0", nullptr, 0, 3, {4, 4, 2}, {0, 0, 0}, 4, 0, 0, 1},
+    CONV1("dcn_3.dcn_block.2", 4, 4),
+    {"dcn_3.conv_fuse", nullptr, 0, 2, {4, 4, 0}, {0, 0, 0}, 4, 0, 0, 1},
+    {"dcn_3.dcn_offset", "dcn_3.dcn_mask", 2, 1, {4, 0, 0}, {0, 0, 0}, 3, 0, 1, 1},
+    {"dcn_3.dcn", nullptr, 1, 1, {4, 0, 0}, {0, 0, 0}, 4, 0, 1, 1},
+    {"forward_resblocks_3.main.0", nullptr, 0, 2, {4, 4, 0}, {0, 0, 0}, 4, 0, 0, 1},
+    {"forward_resblocks_3.main.0", nullptr, 0, 1, {4, 0, 0}, {0, 0, 0}, 4, 0, 0, 1},
+    CONV1("forward_resblocks_3.main.2.0.conv1", 4, 4),
+    CONV1("forward_resblocks_3.main.2.0.conv2", 4, 4),
+    CONV1("encoder_hr.slice1.0", 6, 4), CONV1("encoder_hr.slice1.2", 4, 4),
+    {"conv_tttf", nullptr, 0, 2, {4, 4, 0}, {0, 0, 0}, 4, 0, 0, 1},
+    CONV1("conv_last", 4, 3),
+};
+
+// ------------------------------------------------------------------------------------------------ conv builder
+struct CB {
+  ConvParams p;
+  CB(int n, int h, int w) {
+    memset(&p, 0, sizeof(p));
+    p.n = n; p.h = h; p.w = w;
+    p.epi = EPI_STD; p.out_mode = CRFP_OUT_NHWC; p.post_scale = 1.f;
+  }
+  CB& src(const float* ptr, int c, int cs, int co = 0, int mode = CRFP_SRC_PLAIN) {
+    const int s = p.nsrc++;
+    p.src[s] = ptr; p.src_c[s] = c; p.src_cstride[s] = cs; p.src_coffset[s] = co; p.src_mode[s] = mode;
+    return *this;
+  }
+  CB& layer(const crfp_dsv_weights* w, int li) {
+    p.weight = w->layer[li].w; p.bias = w->layer[li].b; p.cout = kLayers[li].cout;
+    return *this;
+  }
+  CB& act(int a) { p.act = a; return *this; }
+  CB& dst(float* ptr, int c, int cs, int co = 0) {
+    const int s = p.ndst++;
+    p.dst[s] = ptr; p.dst_c[s] = c; p.dst_cstride[s] = cs; p.dst_coffset[s] = co;
+    return *this;
+  }
+  CB& shuffle(int r) { p.out_mode = CRFP_OUT_SHUFFLE; p.shuffle_r = r; return *this; }
+  CB& res(const float* ptr, int cs, int co = 0) { p.residual = ptr; p.res_cstride = cs; p.res_coffset = co; return *this; }
+  CB& scale(float s) { p.post_scale = s; return *this; }
+  CB& head(const float* flow, int split, float mag) {
+    p.act = CRFP_ACT_DCN_HEAD; p.flow = flow; p.head_split = split; p.head_mag = mag; return *this;
+  }
+  CB& fg(const float* ptr, long long clip_stride) { p.fg = ptr; p.fg_clip_stride = clip_stride; return *this; }
+  int run(cudaStream_t st) {
+    int q = 0;
+    for (int s = 0; s < p.nsrc; ++s) { p.qstart[s] = q; q += (p.src_c[s] + 3) / 4; }
+    for (int s = p.nsrc; s < 4; ++s) p.qstart[s] = q;
+    p.cin_packed = (q * 4 + 7) & ~7;
+    p.cout_packed = crfp_conv_cout_packed(p.cout);
+    if (!p.weight || !p.bias) return CRFP_ERR_NULL;
+    return launch_conv(p, st);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ small kernels
+// Fovea compositing (model/CRFP.py:1542-1547): hr_in[...,0:3] = fvs*m + up8(lr)*(1-m), hr_in[...,3:6] = up8(lr),
+// hr_in[...,6:8] = 0.  fvs planar NCHW, mask uint8, lr NHWC4.
+__global__ void __launch_bounds__(256) fovea_compose_kernel(int n, int H, int W, const float* __restrict__ fvs,
+                                                            long long fvs_cs, const uint8_t* __restrict__ mks,
+                                                            long long mks_cs, const float* __restrict__ lr4,
+                                                            long long lr4_cs, float* __restrict__ out) {
+  const long long total = (long long)n * H * W;
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const long long hw = (long long)H * W;
+  const int b = (int)(pix / hw);
+  const long long p = pix - (long long)b * hw;
+  const int y = (int)(p / W), x = (int)(p - (long long)y * W);
+  const int hl = H >> 3, wl = W >> 3;
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilin_src(y, 0.125f, hl, y0, y1, ly);
+  bilin_src(x, 0.125f, wl, x0, x1, lx);
+  const float* lb = lr4 + (size_t)b * lr4_cs;
+  const float4 p00 = __ldg(reinterpret_cast<const float4*>(lb + ((size_t)y0 * wl + x0) * 4));
+  const float4 p01 = __ldg(reinterpret_cast<const float4*>(lb + ((size_t)y0 * wl + x1) * 4));
+  const float4 p10 = __ldg(reinterpret_cast<const float4*>(lb + ((size_t)y1 * wl + x0) * 4));
+  const float4 p11 = __ldg(reinterpret_cast<const float4*>(lb + ((size_t)y1 * wl + x1) * 4));
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const float b0 = hy * (hx * p00.x + lx * p01.x) + ly * (hx * p10.x + lx * p11.x);
+  const float b1 = hy * (hx * p00.y + lx * p01.y) + ly * (hx * p10.y + lx * p11.y);
+  const float b2 = hy * (hx * p00.z + lx * p01.z) + ly * (hx * p10.z + lx * p11.z);
+  const float m = mks[(size_t)b * mks_cs + p] ? 1.f : 0.f;
+  const float* fb = fvs + (size_t)b * fvs_cs + p;
+  const float f0 = __ldg(fb), f1 = __ldg(fb + hw), f2 = __ldg(fb + 2 * hw);
+  float4* o = reinterpret_cast<float4*>(out + (size_t)pix * 8);
+  o[0] = make_float4(f0 * m + b0 * (1.f - m), f1 * m + b1 * (1.f - m), f2 * m + b2 * (1.f - m), b0);
+  o[1] = make_float4(b1, b2, 0.f, 0.f);
+}
+
+static int launch_compose(int n, int H, int W, const crfp_dsv_frame_desc* d, float* out, cudaStream_t st) {
+  const long long total = (long long)n * H * W;
+  fovea_compose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, H, W, d->fvs, d->fvs_clip_stride, d->mks,
+                                                                       d->mks_clip_stride, d->lr4, d->lr4_clip_stride,
+                                                                       out);
+  return check_launch();
+}
+
+// gather `n` strided images into a contiguous run (used to make per-frame slices of clip tensors dense)
+__global__ void __launch_bounds__(256) gather_images_kernel(int n, long long per_image, const float* __restrict__ in,
+                                                            long long in_stride, float* __restrict__ out) {
+  const long long total = (long long)n * per_image;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int b = (int)(idx / per_image);
+  out[idx] = __ldg(in + (size_t)b * in_stride + (idx - (long long)b * per_image));
+}
+
+static int gather_images(int n, long long per_image, const float* in, long long in_stride, float* out, cudaStream_t st) {
+  const long long total = (long long)n * per_image;
+  gather_images_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, per_image, in, in_stride, out);
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------------------ workspace carving
+struct Carver {
+  char* base;
+  size_t off;
+  explicit Carver(void* b) : base((char*)b), off(0) {}
+  float* take(size_t nfloats) {
+    float* p = base ? (float*)(base + off) : nullptr;
+    off += align_up(nfloats * sizeof(float), 256);
+    return p;
+  }
+};
+
+struct FNetWs {
+  float *a, *b, *flowtmp, *prev4;
+};
+static const int kPrepChunk = 8;  // images per FNet / encoder chunk
+
+static size_t carve_prepare(const crfp_dsv_shape* s, void* ws, FNetWs* f, float** enc_tmp) {
+  Carver c(ws);
+  const size_t hw = (size_t)s->h * s->w;
+  f->a = c.take(kPrepChunk * hw * 64);
+  f->b = c.take(kPrepChunk * hw * 64);
+  f->flowtmp = c.take(kPrepChunk * hw * 2);
+  f->prev4 = c.take((size_t)s->n * hw * 4);
+  *enc_tmp = c.take(kPrepChunk * hw * 32);
+  return c.off;
+}
+
+// FNet over `cnt` consecutive (cur, prev) NHWC4 image pairs -> flows (cnt, h, w, 2)   (model/CRFP.py:797-814)
+static int run_fnet(const crfp_dsv_weights* W, int cnt, int h, int w, const float* cur4, const float* prev4,
+                    const FNetWs& f, float* flows, cudaStream_t st) {
+  const int h2 = h / 2, w2 = w / 2, h4 = h2 / 2, w4 = w2 / 2, h8 = h4 / 2, w8 = w4 / 2;
+  if (h8 < 1 || w8 < 1) return CRFP_ERR_BAD_SHAPE;
+  float *A = f.a, *B = f.b;
+  CRFP_TRY(CB(cnt, h, w).src(cur4, 3, 4).src(prev4, 3, 4).layer(W, L_FNET_E1_0).act(CRFP_ACT_RELU).dst(A, 32, 32).run(st));
+  CRFP_TRY(CB(cnt, h, w).src(A, 32, 32).layer(W, L_FNET_E1_2).act(CRFP_ACT_RELU).dst(B, 32, 32).run(st));
+  CRFP_TRY(crfp_avgpool2(cnt, h, w, 32, B, A, st));
+  CRFP_TRY(CB(cnt, h2, w2).src(A, 32, 32).layer(W, L_FNET_E2_0).act(CRFP_ACT_RELU).dst(B, 64, 64).run(st));
+  CRFP_TRY(CB(cnt, h2, w2).src(B, 64, 64).layer(W, L_FNET_E2_2).act(CRFP_ACT_RELU).dst(A, 64, 64).run(st));
+  CRFP_TRY(crfp_avgpool2(cnt, h2, w2, 64, A, B, st));
+  CRFP_TRY(CB(cnt, h4, w4).src(B, 64, 64).layer(W, L_FNET_E3_0).act(CRFP_ACT_RELU).dst(A, 128, 128).run(st));
+  CRFP_TRY(CB(cnt, h4, w4).src(A, 128, 128).layer(W, L_FNET_E3_2).act(CRFP_ACT_RELU).dst(B, 128, 128).run(st));
+  CRFP_TRY(crfp_avgpool2(cnt, h4, w4, 128, B, A, st));
+  CRFP_TRY(CB(cnt, h8, w8).src(A, 128, 128).layer(W, L_FNET_D1_0).act(CRFP_ACT_RELU).dst(B, 256, 256).run(st));
+  CRFP_TRY(CB(cnt, h8, w8).src(B, 256, 256).layer(W, L_FNET_D1_2).act(CRFP_ACT_RELU).dst(A, 256, 256).run(st));
+  CRFP_TRY(crfp_resize_bilinear(cnt, h8, w8, 256, A, 2 * h8, 2 * w8, 0.5f, 0.5f, 1.f, B, st));
+  CRFP_TRY(CB(cnt, 2 * h8, 2 * w8).src(B, 256, 256).layer(W, L_FNET_D2_0).act(CRFP_ACT_RELU).dst(A, 128, 128).run(st));
+  CRFP_TRY(CB(cnt, 2 * h8, 2 * w8).src(A, 128, 128).layer(W, L_FNET_D2_2).act(CRFP_ACT_RELU).dst(B, 128, 128).run(st));
+  CRFP_TRY(crfp_resize_bilinear(cnt, 2 * h8, 2 * w8, 128, B, 4 * h8, 4 * w8, 0.5f, 0.5f, 1.f, A, st));
+  CRFP_TRY(CB(cnt, 4 * h8, 4 * w8).src(A, 128, 128).layer(W, L_FNET_D3_0).act(CRFP_ACT_RELU).dst(B, 64, 64).run(st));
+  CRFP_TRY(CB(cnt, 4 * h8, 4 * w8).src(B, 64, 64).layer(W, L_FNET_D3_2).act(CRFP_ACT_RELU).dst(A, 64, 64).run(st));
+  CRFP_TRY(crfp_resize_bilinear(cnt, 4 * h8, 4 * w8, 64, A, 8 * h8, 8 * w8, 0.5f, 0.5f, 1.f, B, st));
+  const int hf = 8 * h8, wf = 8 * w8;
+  CRFP_TRY(CB(cnt, hf, wf).src(B, 64, 64).layer(W, L_FNET_F0).act(CRFP_ACT_RELU).dst(A, 32, 32).run(st));
+  const bool same = (hf == h && wf == w);
+  float* fl = same ? flows : f.flowtmp;
+  CRFP_TRY(CB(cnt, hf, wf).src(A, 32, 32).layer(W, L_FNET_F2).act(CRFP_ACT_TANH256).dst(fl, 2, 2).run(st));
+  if (!same)
+    CRFP_TRY(crfp_resize_bilinear(cnt, hf, wf, 2, fl, h, w, (float)hf / (float)h, (float)wf / (float)w, 1.f, flows, st));
+  return CRFP_OK;
+}
+
+struct FrameWs {
+  // L1 (2h x 2w)
+  float *P, *P_w, *cur[3], *t1, *t2, *offf[2], *A, *r0, *r1, *prop, *flow_l1, *om, *fg_l1;
+  // HR (8h x 8w)
+  float *S0_w, *q, *po, *h1, *h2, *h3, *om3, *A3, *g0, *g1, *S_pre, *hr_in, *e1, *x_hr, *flow_hr;
+  // dense per-frame copies of strided clip slices
+  float *x_lr_d, *flow_d;
+};
+
+static size_t carve_frame(const crfp_dsv_shape* s, void* ws, FrameWs* f) {
+  Carver c(ws);
+  const size_t n = s->n, hw = (size_t)s->h * s->w;
+  const size_t l1 = n * hw * 4, hr = n * hw * 64;
+  f->P = c.take(l1 * 32); f->P_w = c.take(l1 * 32);
+  for (int k = 0; k < 3; ++k) f->cur[k] = c.take(l1 * 32);
+  f->t1 = c.take(l1 * 32); f->t2 = c.take(l1 * 32);
+  f->offf[0] = c.take(l1 * 32); f->offf[1] = c.take(l1 * 32);
+  f->A = c.take(l1 * 32); f->r0 = c.take(l1 * 32); f->r1 = c.take(l1 * 32);
+  f->prop = c.take(l1 * 24);
+  f->flow_l1 = c.take(l1 * 2);
+  f->om = c.take(l1 * 216);
+  f->fg_l1 = c.take(l1);
+  f->S0_w = c.take(hr * 4); f->q = c.take(hr * 4); f->po = c.take(hr * 4);
+  f->h1 = c.take(hr * 4); f->h2 = c.take(hr * 4); f->h3 = c.take(hr * 4);
+  f->om3 = c.take(hr * 4); f->A3 = c.take(hr * 4);
+  f->g0 = c.take(hr * 4); f->g1 = c.take(hr * 4); f->S_pre = c.take(hr * 4);
+  f->hr_in = c.take(hr * 8); f->e1 = c.take(hr * 4); f->x_hr = c.take(hr * 4);
+  f->flow_hr = c.take(hr * 2);
+  f->x_lr_d = c.take(n * hw * 32);
+  f->flow_d = c.take(n * hw * 2);
+  return c.off;
+}
+
+}  // namespace crfp
+
+using namespace crfp;
+
+extern "C" int crfp_dsv_num_layers(void) { return L_COUNT; }
+
+extern "C" int crfp_dsv_layer_info(int i, crfp_layer_info* info) {
+  if (!info) return CRFP_ERR_NULL;
+  if (i < 0 || i >= L_COUNT) return CRFP_ERR_BAD_SHAPE;
+  *info = kLayers[i];
+  return CRFP_OK;
+}
+
+extern "C" size_t crfp_sizeof_dsv_weights(void) { return sizeof(crfp_dsv_weights); }
+extern "C" size_t crfp_sizeof_dsv_frame_desc(void) { return sizeof(crfp_dsv_frame_desc); }
+
+static int check_shape(const crfp_dsv_shape* s) {
+  if (!s) return CRFP_ERR_NULL;
+  if (s->n <= 0 || s->t <= 0 || s->h < 8 || s->w < 8) return CRFP_ERR_BAD_SHAPE;
+  if (s->mid_channels != 32) return CRFP_ERR_UNSUPPORTED;
+  return CRFP_OK;
+}
+
+extern "C" size_t crfp_dsv_prepare_workspace(const crfp_dsv_shape* s) {
+  if (check_shape(s) != CRFP_OK) return 0;
+  FNetWs f; float* e;
+  return carve_prepare(s, nullptr, &f, &e);
+}
+
+extern "C" int crfp_dsv_prepare(const crfp_dsv_shape* s, const crfp_dsv_weights* W, const float* lrs,
+                                const float* prev_lr, float* lr4, float* x_lr, float* flows, void* workspace,
+                                size_t ws_bytes, crfp_stream stream) {
+  CRFP_TRY(check_shape(s));
+  if (!W || !lrs || !lr4 || !x_lr || !flows || !workspace) return CRFP_ERR_NULL;
+  if (W->nlayers != L_COUNT || W->mid_channels != 32) return CRFP_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  FNetWs f; float* enc_tmp;
+  if (carve_prepare(s, workspace, &f, &enc_tmp) > ws_bytes) return CRFP_ERR_WORKSPACE;
+  const int n = s->n, t = s->t, h = s->h, w = s->w;
+  const size_t hw = (size_t)h * w;
+  CRFP_TRY(crfp_nchw_to_nhwc(n * t, 3, h, w, lrs, (long long)(3 * hw), 4, lr4, st));
+  // encoder_lr over all n*t frames, in chunks                                    (model/LTE.py:34-51)
+  for (int i0 = 0; i0 < n * t; i0 += kPrepChunk) {
+    const int cnt = (n * t - i0 < kPrepChunk) ? (n * t - i0) : kPrepChunk;
+    CRFP_TRY(CB(cnt, h, w).src(lr4 + (size_t)i0 * hw * 4, 3, 4).layer(W, L_ENC_LR_0).act(CRFP_ACT_LRELU)
+                 .dst(enc_tmp, 32, 32).run(st));
+    CRFP_TRY(CB(cnt, h, w).src(enc_tmp, 32, 32).layer(W, L_ENC_LR_2).act(CRFP_ACT_LRELU)
+                 .dst(x_lr + (size_t)i0 * hw * 32, 32, 32).run(st));
+  }
+  // flows: frame i (cur) -> frame i-1 (prev), per clip so that pairs are consecutive images
+  if (prev_lr) CRFP_TRY(crfp_nchw_to_nhwc(n, 3, h, w, prev_lr, (long long)(3 * hw), 4, f.prev4, st));
+  for (int b = 0; b < n; ++b) {
+    if (prev_lr)
+      CRFP_TRY(run_fnet(W, 1, h, w, lr4 + (size_t)(b * t) * hw * 4, f.prev4 + (size_t)b * hw * 4, f,
+                        flows + (size_t)(b * t) * hw * 2, st));
+    for (int i0 = 1; i0 < t; i0 += kPrepChunk) {
+      const int cnt = (t - i0 < kPrepChunk) ? (t - i0) : kPrepChunk;
+      CRFP_TRY(run_fnet(W, cnt, h, w, lr4 + (size_t)(b * t + i0) * hw * 4, lr4 + (size_t)(b * t + i0 - 1) * hw * 4, f,
+                        flows + (size_t)(b * t + i0) * hw * 2, st));
+    }
+  }
+  return CRFP_OK;
+}
+
+extern "C" size_t crfp_dsv_frame_workspace(const crfp_dsv_shape* s) {
+  if (check_shape(s) != CRFP_OK) return 0;
+  FrameWs f;
+  return carve_frame(s, nullptr, &f);
+}
+
+extern "C" int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weights* W, void* workspace,
+                              size_t ws_bytes, crfp_stream stream) {
+  if (!d || !W || !workspace) return CRFP_ERR_NULL;
+  const crfp_dsv_shape* s = &d->shape;
+  CRFP_TRY(check_shape(s));
+  if (W->nlayers != L_COUNT || W->mid_channels != 32) return CRFP_ERR_BAD_SHAPE;
+  if (!d->lr4 || !d->x_lr || !d->fvs || !d->mks || !d->state_hr || !d->state_l1 || !d->out) return CRFP_ERR_NULL;
+  if (!d->first && !d->flow) return CRFP_ERR_NULL;
+  cudaStream_t st = (cudaStream_t)stream;
+  FrameWs f;
+  if (carve_frame(s, workspace, &f) > ws_bytes) return CRFP_ERR_WORKSPACE;
+  const int n = s->n, h = s->h, w = s->w;
+  const int h1 = 2 * h, w1 = 2 * w, H = 8 * h, Wd = 8 * w;
+  const size_t hw = (size_t)h * w;
+
+  // dense copies of this frame's LR features / flow (the clip tensors are (b, t, ...) so a frame is strided)
+  const float* x_lr = d->x_lr;
+  if (n > 1 && d->x_lr_clip_stride != (long long)(hw * 32)) {
+    CRFP_TRY(gather_images(n, (long long)hw * 32, d->x_lr, d->x_lr_clip_stride, f.x_lr_d, st));
+    x_lr = f.x_lr_d;
+  }
+
+  // feat_prop_lv0 = PixelShufflePack(x_lr): 32 -> 96 @LR, shuffle x2 -> 24ch @L1           (CRFP.py:1560)
+  float* prop_dst = d->first ? f.prop : f.cur[0];
+  const int prop_cs = d->first ? 24 : 32;
+  CRFP_TRY(CB(n, h, w).src(x_lr, 32, 32).layer(W, L_UPSAMPLE).shuffle(2).dst(prop_dst, 24, prop_cs).run(st));
+
+  const float* prop24 = nullptr;  // input of upsample_post
+  if (!d->first) {
+    const float* flow = d->flow;
+    if (n > 1 && d->flow_clip_stride != (long long)(hw * 2)) {
+      CRFP_TRY(gather_images(n, (long long)hw * 2, d->flow, d->flow_clip_stride, f.flow_d, st));
+      flow = f.flow_d;
+    }
+    // flow_lv3 = up2(flow)*2, flow_lv0 = up8(flow)*8                                        (CRFP.py:1565-1566)
+    CRFP_TRY(crfp_resize_bilinear(n, h, w, 2, flow, h1, w1, 0.5f, 0.5f, 2.f, f.flow_l1, st));
+    CRFP_TRY(crfp_resize_bilinear(n, h, w, 2, flow, H, Wd, 0.125f, 0.125f, 8.f, f.flow_hr, st));
+    // P = downsample(S0): pixel_unshuffle(4) + conv 64 -> 32                                (CRFP.py:1569)
+    CRFP_TRY(CB(n, h1, w1).src(d->state_hr, 64, 4, 0, CRFP_SRC_UNSHUFFLE4).layer(W, L_DOWNSAMPLE).dst(f.P, 32, 32).run(st));
+    // warps                                                                                 (CRFP.py:1570-1577)
+    crfp_warp_desc wd;
+    memset(&wd, 0, sizeof(wd));
+    wd.n = n; wd.h = h1; wd.w = w1; wd.c = 32; wd.x = f.P; wd.x_cstride = 32; wd.flow = f.flow_l1;
+    wd.out = f.P_w; wd.out_cstride = 32;
+    CRFP_TRY(launch_flow_warp(wd, st));
+    wd.h = H; wd.w = Wd; wd.c = 4; wd.x = d->state_hr; wd.x_cstride = 4; wd.flow = f.flow_hr;
+    wd.out = f.S0_w; wd.out_cstride = 4;
+    CRFP_TRY(launch_flow_warp(wd, st));
+    for (int k = 0; k < 3; ++k) {  // warped feat_lv{k} lands in channels 24..31 of level k's `cur`
+      wd.h = h1; wd.w = w1; wd.c = 8; wd.x = d->state_l1; wd.x_cstride = 24; wd.x_coffset = 8 * k; wd.flow = f.flow_l1;
+      wd.out = f.cur[k]; wd.out_cstride = 32; wd.out_coffset = 24;
+      CRFP_TRY(launch_flow_warp(wd, st));
+    }
+    const float* fg_l1 = nullptr;
+    if (d->fg) {  // streaming regional mask at L1: bilinear x0.25                            (CRFP_test.py:2299-2300)
+      if (n > 1 && d->fg_clip_stride != (long long)H * Wd) return CRFP_ERR_UNSUPPORTED;
+      CRFP_TRY(crfp_resize_bilinear(n, H, Wd, 1, d->fg, h1, w1, 4.f, 4.f, 1.f, f.fg_l1, st));
+      fg_l1 = f.fg_l1;
+    }
+    static const int lb0[3] = {L_DCN0_B0, L_DCN1_B0, L_DCN2_B0};
+    static const int lb2[3] = {L_DCN0_B2, L_DCN1_B2, L_DCN2_B2};
+    static const int lfu[3] = {-1, L_DCN1_FUSE, L_DCN2_FUSE};
+    static const int lhd[3] = {L_DCN0_HEADS, L_DCN1_HEADS, L_DCN2_HEADS};
+    static const int ldc[3] = {L_DCN0_DCN, L_DCN1_DCN, L_DCN2_DCN};
+    static const int lri[3] = {L_RES0_IN, L_RES1_IN, L_RES2_IN};
+    static const int lr1[3] = {L_RES0_C1, L_RES1_C1, L_RES2_C1};
+    static const int lr2[3] = {L_RES0_C2, L_RES1_C2, L_RES2_C2};
+    const float* offfeat = nullptr;
+    for (int k = 0; k < 3; ++k) {
+      float* cur = f.cur[k];
+      // DCN_module (CRFP.py:324-352)
+      CRFP_TRY(CB(n, h1, w1).src(cur, 32, 32).src(f.P_w, 32, 32).src(f.flow_l1, 2, 2).layer(W, lb0[k])
+                   .act(CRFP_ACT_LRELU).dst(f.t1, 32, 32).run(st));
+      float* z = f.offf[k & 1];
+      if (k == 0) {
+        CRFP_TRY(CB(n, h1, w1).src(f.t1, 32, 32).layer(W, lb2[k]).act(CRFP_ACT_LRELU).dst(z, 32, 32).run(st));
+      } else {
+        CRFP_TRY(CB(n, h1, w1).src(f.t1, 32, 32).layer(W, lb2[k]).act(CRFP_ACT_LRELU).dst(f.t2, 32, 32).run(st));
+        CRFP_TRY(CB(n, h1, w1).src(f.t2, 32, 32).src(offfeat, 32, 32).layer(W, lfu[k]).act(CRFP_ACT_LRELU)
+                     .dst(z, 32, 32).run(st));
+      }
+      offfeat = z;
+      CRFP_TRY(CB(n, h1, w1).src(z, 32, 32).layer(W, lhd[k]).head(f.flow_l1, 144, 10.f).dst(f.om, 216, 216).run(st));
+      crfp_dcn_desc dd;
+      memset(&dd, 0, sizeof(dd));
+      dd.n = n; dd.h = h1; dd.w = w1; dd.c = 32; dd.cout = 32; dd.dg = 8;
+      dd.x = f.P; dd.x_cstride = 32;
+      dd.offset = f.om; dd.off_cstride = 216; dd.off_coffset = 0;
+      dd.mask = f.om; dd.mask_cstride = 216; dd.mask_coffset = 144;
+      dd.weight = W->layer[ldc[k]].w; dd.bias = W->layer[ldc[k]].b;
+      dd.out = f.A; dd.out_cstride = 32;
+      CRFP_TRY(launch_dcn(dd, st));
+      // ResidualBlocksWithInputConv on cat(cur, A) (CRFP.py:1589-1596)
+      CB in(n, h1, w1);
+      in.src(cur, 32, 32).src(f.A, 32, 32).layer(W, lri[k]).act(CRFP_ACT_LRELU).dst(f.r0, 32, 32);
+      if (fg_l1 && k > 0) in.fg(fg_l1, (long long)h1 * w1);
+      CRFP_TRY(in.run(st));
+      CRFP_TRY(CB(n, h1, w1).src(f.r0, 32, 32).layer(W, lr1[k]).act(CRFP_ACT_RELU).dst(f.r1, 32, 32).run(st));
+      // split: first 24 channels propagate, last 8 become feat_lv{k} of the next frame
+      float* nxt = (k < 2) ? f.cur[k + 1] : f.prop;
+      const int nxt_cs = (k < 2) ? 32 : 24;
+      CRFP_TRY(CB(n, h1, w1).src(f.r1, 32, 32).layer(W, lr2[k]).res(f.r0, 32).dst(nxt, 24, nxt_cs)
+                   .dst(d->state_l1, 8, 24, 8 * k).run(st));
+    }
+    prop24 = f.prop;
+    // L3                                                                                    (CRFP.py:1625-1630)
+    CRFP_TRY(CB(n, h1, w1).src(prop24, 24, 24).layer(W, L_UPSAMPLE_POST).act(CRFP_ACT_LRELU).shuffle(4)
+                 .dst(f.q, 4, 4).run(st));
+    CRFP_TRY(CB(n, h1, w1).src(offfeat, 32, 32).layer(W, L_DCN3_UP).shuffle(4).scale(2.f).dst(f.po, 4, 4).run(st));
+    CRFP_TRY(CB(n, H, Wd).src(f.q, 4, 4).src(f.S0_w, 4, 4).src(f.flow_hr, 2, 2).layer(W, L_DCN3_B0).act(CRFP_ACT_LRELU)
+                 .dst(f.h1, 4, 4).run(st));
+    CRFP_TRY(CB(n, H, Wd).src(f.h1, 4, 4).layer(W, L_DCN3_B2).act(CRFP_ACT_LRELU).dst(f.h2, 4, 4).run(st));
+    CRFP_TRY(CB(n, H, Wd).src(f.h2, 4, 4).src(f.po, 4, 4).layer(W, L_DCN3_FUSE).act(CRFP_ACT_LRELU).dst(f.h3, 4, 4).run(st));
+    CRFP_TRY(CB(n, H, Wd).src(f.h3, 4, 4).layer(W, L_DCN3_HEADS).head(f.flow_hr, 2, 10.f).dst(f.om3, 4, 4).run(st));
+    crfp_dcn_desc dd;
+    memset(&dd, 0, sizeof(dd));
+    dd.n = n; dd.h = H; dd.w = Wd; dd.c = 4; dd.cout = 4; dd.dg = 1; dd.shared_taps = 1;
+    dd.x = d->state_hr; dd.x_cstride = 4;
+    dd.offset = f.om3; dd.off_cstride = 4; dd.off_coffset = 0;
+    dd.mask = f.om3; dd.mask_cstride = 4; dd.mask_coffset = 2;
+    dd.weight = W->layer[L_DCN3_DCN].w; dd.bias = W->layer[L_DCN3_DCN].b;
+    dd.out = f.A3; dd.out_cstride = 4;
+    CRFP_TRY(launch_dcn(dd, st));
+    CB in3(n, H, Wd);
+    in3.src(f.q, 4, 4).src(f.A3, 4, 4).layer(W, L_RES3_IN).act(CRFP_ACT_LRELU).dst(f.g0, 4, 4);
+    if (d->fg) in3.fg(d->fg, d->fg_clip_stride);
+    CRFP_TRY(in3.run(st));
+  } else {
+    // first frame: no alignment; cat([prop, zeros32, zeros8]) == only weight[:, :24] contributes (CRFP.py:1634-1670)
+    static const int lrf[3] = {L_RES0_IN_FIRST, L_RES1_IN_FIRST, L_RES2_IN_FIRST};
+    static const int lr1[3] = {L_RES0_C1, L_RES1_C1, L_RES2_C1};
+    static const int lr2[3] = {L_RES0_C2, L_RES1_C2, L_RES2_C2};
+    float* pa = f.prop;       // 24ch ping
+    float* pb = f.cur[0];     // reuse as 24ch pong (pixel stride 24)
+    for (int k = 0; k < 3; ++k) {
+      CRFP_TRY(CB(n, h1, w1).src(pa, 24, 24).layer(W, lrf[k]).act(CRFP_ACT_LRELU).dst(f.r0, 32, 32).run(st));
+      CRFP_TRY(CB(n, h1, w1).src(f.r0, 32, 32).layer(W, lr1[k]).act(CRFP_ACT_RELU).dst(f.r1, 32, 32).run(st));
+      CRFP_TRY(CB(n, h1, w1).src(f.r1, 32, 32).layer(W, lr2[k]).res(f.r0, 32).dst(pb, 24, 24)
+                   .dst(d->state_l1, 8, 24, 8 * k).run(st));
+      float* tmp = pa; pa = pb; pb = tmp;
+    }
+    prop24 = pa;
+    CRFP_TRY(CB(n, h1, w1).src(prop24, 24, 24).layer(W, L_UPSAMPLE_POST).act(CRFP_ACT_LRELU).shuffle(4)
+                 .dst(f.q, 4, 4).run(st));
+    CRFP_TRY(CB(n, H, Wd).src(f.q, 4, 4).layer(W, L_RES3_IN_FIRST).act(CRFP_ACT_LRELU).dst(f.g0, 4, 4).run(st));
+  }
+  CRFP_TRY(CB(n, H, Wd).src(f.g0, 4, 4).layer(W, L_RES3_C1).act(CRFP_ACT_RELU).dst(f.g1, 4, 4).run(st));
+  CRFP_TRY(CB(n, H, Wd).src(f.g1, 4, 4).layer(W, L_RES3_C2).res(f.g0, 4).dst(f.S_pre, 4, 4).run(st));
+
+  // fovea compositing + encoder_hr for this frame                                          (CRFP.py:1542-1547)
+  CRFP_TRY(launch_compose(n, H, Wd, d, f.hr_in, st));
+  CRFP_TRY(CB(n, H, Wd).src(f.hr_in, 6, 8).layer(W, L_ENC_HR_0).act(CRFP_ACT_LRELU).dst(f.e1, 4, 4).run(st));
+  CRFP_TRY(CB(n, H, Wd).src(f.e1, 4, 4).layer(W, L_ENC_HR_2).act(CRFP_ACT_LRELU).dst(f.x_hr, 4, 4).run(st));
+  // conv_tttf + blend + LeakyReLU -> new state                                             (CRFP.py:1672-1675)
+  {
+    CB b(n, H, Wd);
+    b.src(f.S_pre, 4, 4).src(f.x_hr, 4, 4).layer(W, L_TTTF).dst(d->state_hr, 4, 4);
+    b.p.epi = EPI_BLEND; b.p.mask = d->mks; b.p.mask_clip_stride = d->mks_clip_stride; b.p.blend_old = f.S_pre;
+    CRFP_TRY(b.run(st));
+  }
+  // out = conv_last(S) + up8(lr)                                                           (CRFP.py:1678-1683)
+  {
+    CB o(n, H, Wd);
+    o.src(d->state_hr, 4, 4).layer(W, L_LAST).dst(d->out, 3, 3);
+    o.p.epi = EPI_OUT_NCHW; o.p.base_lr4 = d->lr4; o.p.base_clip_stride = d->lr4_clip_stride;
+    o.p.out_clip_stride = d->out_clip_stride; o.p.out_planes = 3;
+    CRFP_TRY(o.run(st));
+  }
+  return CRFP_OK;
+}

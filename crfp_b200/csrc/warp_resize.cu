@@ -1,0 +1,200 @@
+// flow_warp (bilinear backward warp), bilinear resize, 2x2 average pool and NCHW<->NHWC layout kernels.
+// All are pure HBM-bandwidth kernels: NHWC float4 channel-quads, one thread per (pixel, quad), coalesced.
+//
+// flow_warp replaces /root/reference/model/CRFP.py:90-130 (meshgrid + normalise + F.grid_sample): the
+// sampling position is computed with the SAME fp32 operation sequence (no FMA contraction) so that the
+// integer corner indices agree bit for bit with the reference's CPU path:
+//   g  = 2.0f*(x + flow_x)/(W-1) - 1.0f                (CRFP.py:118-121)
+//   ix = ((g + 1.0f)/2)*(W-1)                          (ATen grid_sampler_unnormalize, align_corners=True)
+#include "common.cuh"
+
+namespace crfp {
+
+__device__ __forceinline__ float warp_coord(int i, float f, int size) {
+  const float denom = (float)((size - 1) > 1 ? (size - 1) : 1);
+  const float gf = __fadd_rn((float)i, f);
+  const float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, gf), denom), 1.0f);
+  return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), (float)(size - 1));
+}
+
+__global__ void __launch_bounds__(256) flow_warp_kernel(const crfp_warp_desc D) {
+  const int cq = D.c >> 2;
+  const long long total = (long long)D.n * D.h * D.w * cq;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int q = (int)(idx % cq);
+  const long long pix = idx / cq;
+  const int x = (int)(pix % D.w);
+  const int y = (int)((pix / D.w) % D.h);
+  const int n = (int)(pix / ((long long)D.w * D.h));
+  const float2 fl = __ldg(reinterpret_cast<const float2*>(D.flow + pix * 2));
+  float ix = warp_coord(x, fl.x, D.w);
+  float iy = warp_coord(y, fl.y, D.h);
+  if (D.border) {  // padding_mode='border': clip_coordinates
+    ix = fminf(fmaxf(ix, 0.f), (float)(D.w - 1));
+    iy = fminf(fmaxf(iy, 0.f), (float)(D.h - 1));
+  }
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+  // grid_sample weights: nw = (x1-ix)(y1-iy), ne = (ix-x0)(y1-iy), sw = (x1-ix)(iy-y0), se = (ix-x0)(iy-y0)
+  const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix;
+  const float wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
+  const float* base = D.x + (size_t)n * D.h * D.w * D.x_cstride + D.x_coffset + q * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool vx0 = (x0 >= 0 && x0 < D.w), vx1 = (x1 >= 0 && x1 < D.w);
+  const bool vy0 = (y0 >= 0 && y0 < D.h), vy1 = (y1 >= 0 && y1 < D.h);
+#define CRFP_ACC(vy, vx, yy, xx, wgt)                                                                  \
+  if ((vy) && (vx)) {                                                                                  \
+    const float4 t = __ldg(reinterpret_cast<const float4*>(base + ((size_t)(yy) * D.w + (xx)) * D.x_cstride)); \
+    const float w_ = (wgt);                                                                            \
+    acc.x += t.x * w_; acc.y += t.y * w_; acc.z += t.z * w_; acc.w += t.w * w_;                        \
+  }
+  CRFP_ACC(vy0, vx0, y0, x0, wx0 * wy0)
+  CRFP_ACC(vy0, vx1, y0, x1, wx1 * wy0)
+  CRFP_ACC(vy1, vx0, y1, x0, wx0 * wy1)
+  CRFP_ACC(vy1, vx1, y1, x1, wx1 * wy1)
+#undef CRFP_ACC
+  *reinterpret_cast<float4*>(D.out + (size_t)pix * D.out_cstride + D.out_coffset + q * 4) = acc;
+}
+
+__global__ void __launch_bounds__(256) flow_warp_indices_kernel(int n, int h, int w, const float* __restrict__ flow,
+                                                                int32_t* __restrict__ x0, int32_t* __restrict__ y0) {
+  const long long total = (long long)n * h * w;
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const int x = (int)(pix % w), y = (int)((pix / w) % h);
+  const float2 fl = __ldg(reinterpret_cast<const float2*>(flow + pix * 2));
+  x0[pix] = (int)floorf(warp_coord(x, fl.x, w));
+  y0[pix] = (int)floorf(warp_coord(y, fl.y, h));
+}
+
+// ---- bilinear resize (align_corners=False), NHWC, all channels of the pixel
+__global__ void __launch_bounds__(256) resize_bilinear_kernel(int n, int hin, int win, int c, const float* __restrict__ in,
+                                                              int hout, int wout, float rh, float rw, float mul,
+                                                              float* __restrict__ out) {
+  const long long total = (long long)n * hout * wout * c;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ch = (int)(idx % c);
+  const long long pix = idx / c;
+  const int x = (int)(pix % wout);
+  const int y = (int)((pix / wout) % hout);
+  const int b = (int)(pix / ((long long)wout * hout));
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilin_src(y, rh, hin, y0, y1, ly);
+  bilin_src(x, rw, win, x0, x1, lx);
+  const float* ib = in + (size_t)b * hin * win * c + ch;
+  const float v00 = __ldg(ib + ((size_t)y0 * win + x0) * c), v01 = __ldg(ib + ((size_t)y0 * win + x1) * c);
+  const float v10 = __ldg(ib + ((size_t)y1 * win + x0) * c), v11 = __ldg(ib + ((size_t)y1 * win + x1) * c);
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  out[idx] = (hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11)) * mul;
+}
+
+__global__ void __launch_bounds__(256) avgpool2_kernel(int n, int hin, int win, int c, const float* __restrict__ in,
+                                                       float* __restrict__ out) {
+  const int ho = hin >> 1, wo = win >> 1;
+  const long long total = (long long)n * ho * wo * c;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ch = (int)(idx % c);
+  const long long pix = idx / c;
+  const int x = (int)(pix % wo);
+  const int y = (int)((pix / wo) % ho);
+  const int b = (int)(pix / ((long long)wo * ho));
+  const float* ib = in + (((size_t)b * hin + 2 * y) * win + 2 * x) * c + ch;
+  const float s = (__ldg(ib) + __ldg(ib + c)) + (__ldg(ib + (size_t)win * c) + __ldg(ib + (size_t)win * c + c));
+  out[idx] = s * 0.25f;
+}
+
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(int n, int c, int h, int w, const float* __restrict__ in,
+                                                           long long in_image_stride, int cpad, float* __restrict__ out) {
+  const long long total = (long long)n * h * w;
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const long long hw = (long long)h * w;
+  const int b = (int)(pix / hw);
+  const long long p = pix - (long long)b * hw;
+  const float* ib = in + (size_t)b * in_image_stride + p;
+  float* ob = out + (size_t)pix * cpad;
+  for (int ch = 0; ch < cpad; ++ch) ob[ch] = (ch < c) ? __ldg(ib + (size_t)ch * hw) : 0.f;
+}
+
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(int n, int c, int h, int w, const float* __restrict__ in,
+                                                           int cs, int co, float* __restrict__ out,
+                                                           long long out_image_stride) {
+  const long long hw = (long long)h * w;
+  const long long total = (long long)n * hw * c;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long p = idx % hw;
+  const int ch = (int)((idx / hw) % c);
+  const int b = (int)(idx / (hw * c));
+  out[(size_t)b * out_image_stride + (size_t)ch * hw + p] = __ldg(in + ((size_t)b * hw + p) * cs + co + ch);
+}
+
+static inline unsigned grid1d(long long total) { return (unsigned)((total + 255) / 256); }
+
+int launch_flow_warp(const crfp_warp_desc& d, cudaStream_t st) {
+  if (d.c % 4 || ((d.x_cstride | d.x_coffset | d.out_cstride | d.out_coffset) & 3)) return CRFP_ERR_BAD_SHAPE;
+  const long long total = (long long)d.n * d.h * d.w * (d.c / 4);
+  if (total == 0) return CRFP_OK;
+  flow_warp_kernel<<<grid1d(total), 256, 0, st>>>(d);
+  return check_launch();
+}
+
+}  // namespace crfp
+
+using namespace crfp;
+
+extern "C" int crfp_flow_warp_fwd(const crfp_warp_desc* d, crfp_stream stream) {
+  if (!d || !d->x || !d->flow || !d->out) return CRFP_ERR_NULL;
+  if (d->n < 0 || d->h <= 0 || d->w <= 0 || d->c <= 0) return CRFP_ERR_BAD_SHAPE;
+  return launch_flow_warp(*d, (cudaStream_t)stream);
+}
+
+extern "C" int crfp_flow_warp_indices(int n, int h, int w, const float* flow, int32_t* x0, int32_t* y0,
+                                      crfp_stream stream) {
+  if (!flow || !x0 || !y0) return CRFP_ERR_NULL;
+  const long long total = (long long)n * h * w;
+  if (total <= 0) return CRFP_ERR_BAD_SHAPE;
+  flow_warp_indices_kernel<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(n, h, w, flow, x0, y0);
+  return check_launch();
+}
+
+extern "C" int crfp_resize_bilinear(int n, int hin, int win, int c, const float* in, int hout, int wout, float rscale_h,
+                                    float rscale_w, float mul, float* out, crfp_stream stream) {
+  if (!in || !out) return CRFP_ERR_NULL;
+  if (n <= 0 || hin <= 0 || win <= 0 || c <= 0 || hout <= 0 || wout <= 0) return CRFP_ERR_BAD_SHAPE;
+  const long long total = (long long)n * hout * wout * c;
+  resize_bilinear_kernel<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(n, hin, win, c, in, hout, wout, rscale_h,
+                                                                         rscale_w, mul, out);
+  return check_launch();
+}
+
+extern "C" int crfp_avgpool2(int n, int hin, int win, int c, const float* in, float* out, crfp_stream stream) {
+  if (!in || !out) return CRFP_ERR_NULL;
+  if (n <= 0 || hin < 2 || win < 2 || c <= 0) return CRFP_ERR_BAD_SHAPE;
+  const long long total = (long long)n * (hin / 2) * (win / 2) * c;
+  avgpool2_kernel<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(n, hin, win, c, in, out);
+  return check_launch();
+}
+
+extern "C" int crfp_nchw_to_nhwc(int n, int c, int h, int w, const float* in, long long in_image_stride, int cpad,
+                                 float* out, crfp_stream stream) {
+  if (!in || !out) return CRFP_ERR_NULL;
+  if (n <= 0 || c <= 0 || h <= 0 || w <= 0 || cpad < c) return CRFP_ERR_BAD_SHAPE;
+  nchw_to_nhwc_kernel<<<grid1d((long long)n * h * w), 256, 0, (cudaStream_t)stream>>>(n, c, h, w, in, in_image_stride,
+                                                                                    cpad, out);
+  return check_launch();
+}
+
+extern "C" int crfp_nhwc_to_nchw(int n, int c, int h, int w, const float* in, int in_cstride, int in_coffset,
+                                 float* out, long long out_image_stride, crfp_stream stream) {
+  if (!in || !out) return CRFP_ERR_NULL;
+  if (n <= 0 || c <= 0 || h <= 0 || w <= 0) return CRFP_ERR_BAD_SHAPE;
+  nhwc_to_nchw_kernel<<<grid1d((long long)n * h * w * c), 256, 0, (cudaStream_t)stream>>>(n, c, h, w, in, in_cstride,
+                                                                                        in_coffset, out,
+                                                                                        out_image_stride);
+  return check_launch();
+}

@@ -1,0 +1,270 @@
+"""nn.Module shells with the reference's API over libcrfp_b200.
+
+  CRFP_DSV          /root/reference/model/CRFP.py:1387-1706   forward(lrs, fvs, mks) -> (n,t,3,8h,8w)
+  MRCF_simple_v18   /root/reference/model/CRFP_test.py:2114-2478   stateful forward(lrs, fvs, mks, fgs) +
+                    clear_states(); identical state_dict (118 tensors)
+
+The shells own the parameters (same names, shapes and dtypes as the reference so checkpoints load with
+strict=True in both directions) and device buffers; every arithmetic op of the forward runs in the CUDA
+library through `crfp_dsv_prepare` / `crfp_dsv_frame`.  No CPU fallback: a missing library or a non-CUDA
+input raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .packing import pack_layer
+from .spec import crfp_dsv_param_shapes
+from .synthetic import fovea_rect
+
+
+class _Holder(nn.Module):
+    """Plain container so that parameter paths equal the reference's (`dcn_0.dcn_block.0.weight`, ...)."""
+
+
+class _DCNParams(nn.Module):
+    """Parameter holder for `dcn_k.dcn` (dcn_v2.DCNv2: weight (Co,Ci,3,3), bias (Co))."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.weight = nn.Parameter(torch.zeros(cout, cin, 3, 3))
+        self.bias = nn.Parameter(torch.zeros(cout))
+
+
+def _build_tree(root: nn.Module, shapes):
+    for key, shape in shapes.items():
+        if not key.endswith(".weight"):
+            continue
+        path = key[: -len(".weight")].split(".")
+        node = root
+        for comp in path[:-1]:
+            if comp not in node._modules:
+                node.add_module(comp, _Holder())
+            node = node._modules[comp]
+        cout, cin = shape[0], shape[1]
+        leaf = _DCNParams(cin, cout) if path[-1] == "dcn" else nn.Conv2d(cin, cout, 3, 1, 1, bias=True)
+        node.add_module(path[-1], leaf)
+
+
+def _kaiming_fan_in_(conv: nn.Conv2d, scale: float):
+    nn.init.kaiming_normal_(conv.weight, a=0, mode="fan_in", nonlinearity="relu")
+    conv.weight.data *= scale
+    nn.init.constant_(conv.bias, 0)
+
+
+class _CRFPBase(nn.Module):
+    def __init__(self, device, mid_channels=16, y_only=False, hr_dcn=True, offset_prop=True, spynet_pretrained=None):
+        super().__init__()
+        if mid_channels != 32:
+            raise L.CrfpError("crfp_b200 implements the shipped configuration mid_channels=32 (main.py:34)")
+        if y_only or not hr_dcn or not offset_prop:
+            raise L.CrfpError("crfp_b200 implements y_only=False, hr_dcn=True, offset_prop=True "
+                              "(the defaults every shipped script uses, option.py:58-63)")
+        self.device = device
+        self.mid_channels = mid_channels
+        self.last_channels = mid_channels // 8
+        self.dg_num, self.dk, self.max_residue_magnitude = 8, 3, 10
+        self.y_only, self.hr_dcn, self.offset_prop, self.split_ratio = y_only, hr_dcn, offset_prop, 3
+        _build_tree(self, crfp_dsv_param_shapes(mid_channels, y_only))
+        self._init_like_reference()
+        if spynet_pretrained is not None:
+            self.spynet.load_state_dict(torch.load(spynet_pretrained, map_location="cpu"))
+        self._packed = None       # (version key, device, blob tensors, DsvWeights)
+        self._ws = {}             # workspace cache keyed by shape
+        self.skip_outside_fovea = True
+
+    # ---- init policy of the reference (statistically identical, not RNG-stream identical)
+    def _init_like_reference(self):
+        for name, m in self.named_modules():
+            if isinstance(m, nn.Conv2d):
+                if name.endswith("upsample_conv") or name.endswith("downsample_conv"):
+                    _kaiming_fan_in_(m, 1.0)           # PixelShufflePack.init_weights, CRFP.py:182-185
+                elif ".main.2.0.conv" in name:
+                    _kaiming_fan_in_(m, 0.1)           # ResidualBlockNoBN.init_weights, CRFP.py:459-470
+                elif name.endswith("dcn_offset") or name.endswith("dcn_mask"):
+                    nn.init.zeros_(m.weight)           # DCN_module.init_dcn, CRFP.py:354-359
+                    nn.init.zeros_(m.bias)
+            elif isinstance(m, _DCNParams):            # conv_identify, CRFP.py:361-370
+                with torch.no_grad():
+                    m.weight.zero_()
+                    m.bias.zero_()
+                    for p in range(min(m.weight.shape[0], m.weight.shape[1])):
+                        m.weight[p, p, 1, 1] = 1.0
+
+    def init_weights(self, pretrained=None, strict=True):
+        """Same contract as the reference (CRFP.py:1688-1706)."""
+        if isinstance(pretrained, str):
+            saved = {k: v for k, v in torch.load(pretrained, map_location=self.device).items()}
+            sd = self.state_dict()
+            sd.update(saved)
+            self.load_state_dict(sd, strict=strict)
+        elif pretrained is not None:
+            raise TypeError(f'"pretrained" must be a str or None. But received {type(pretrained)}.')
+
+    # ---- packed weights (refreshed whenever a parameter changes or moves)
+    def _weights(self, device):
+        params = list(self.parameters())
+        key = (str(device), tuple((p.data_ptr(), p._version) for p in params))
+        if self._packed is not None and self._packed[0] == key:
+            return self._packed[2]
+        sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in self.state_dict().items()}
+        table = L.layer_table()
+        W = L.DsvWeights()
+        W.mid_channels, W.nlayers = self.mid_channels, len(table)
+        keep = []
+        for i, info in enumerate(table):
+            w, b = pack_layer(info, sd)
+            keep.append((w, b))
+            W.layer[i].w, W.layer[i].b = w.data_ptr(), b.data_ptr()
+        self._packed = (key, keep, W)
+        return W
+
+    def _buffers(self, n, t, h, w, device):
+        key = (n, t, h, w, str(device))
+        if key not in self._ws:
+            self._ws.clear()
+            lib = L.lib()
+            shp = L.DsvShape(n=n, t=t, h=h, w=w, mid_channels=self.mid_channels)
+            pw, fw = lib.crfp_dsv_prepare_workspace(C.byref(shp)), lib.crfp_dsv_frame_workspace(C.byref(shp))
+            if pw == 0 or fw == 0:
+                raise L.CrfpError(f"unsupported clip shape n={n} t={t} h={h} w={w}")
+            f32 = dict(device=device, dtype=torch.float32)
+            self._ws[key] = dict(
+                shape=shp,
+                ws=torch.empty(max(pw, fw), device=device, dtype=torch.uint8),
+                lr4=torch.empty(n * t * h * w * 4, **f32),
+                x_lr=torch.empty(n * t * h * w * self.mid_channels, **f32),
+                flows=torch.zeros(n * t * h * w * 2, **f32),
+                state_hr=torch.zeros(n * 64 * h * w * 4, **f32),
+                state_l1=torch.zeros(n * 4 * h * w * 24, **f32),
+            )
+        return self._ws[key]
+
+    @staticmethod
+    def _check_inputs(lrs, fvs, mks):
+        for name, t_ in (("lrs", lrs), ("fvs", fvs), ("mks", mks)):
+            if not (isinstance(t_, torch.Tensor) and t_.is_cuda):
+                raise L.CrfpError(f"{name} must be a CUDA tensor: crfp_b200 has no CPU fallback")
+        n, t, c, h, w = lrs.shape
+        if c != 3:
+            raise ValueError(f"lrs must have 3 channels, got {c}")
+        if tuple(fvs.shape) != (n, t, 3, 8 * h, 8 * w):
+            raise ValueError(f"fvs must be {(n, t, 3, 8 * h, 8 * w)}, got {tuple(fvs.shape)}")
+        if tuple(mks.shape) != (n, t, 1, 8 * h, 8 * w):
+            raise ValueError(f"mks must be {(n, t, 1, 8 * h, 8 * w)}, got {tuple(mks.shape)}")
+        lrs = lrs.to(torch.float32).contiguous()
+        fvs = fvs.to(torch.float32).contiguous()
+        mks = (mks != 0).to(torch.uint8).contiguous() if mks.dtype != torch.bool else mks.contiguous().view(torch.uint8)
+        return lrs, fvs, mks
+
+    def _run_frames(self, buf, W, lrs, fvs, mks, fgs, out, first_flags):
+        lib = L.lib()
+        n, t, _, h, w = lrs.shape
+        hw, HW = h * w, 64 * h * w
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        d = L.DsvFrameDesc()
+        d.shape = L.DsvShape(n=n, t=1, h=h, w=w, mid_channels=self.mid_channels)
+        d.skip_outside_fovea = int(self.skip_outside_fovea)
+        d.lr4_clip_stride, d.x_lr_clip_stride, d.flow_clip_stride = t * hw * 4, t * hw * self.mid_channels, t * hw * 2
+        d.fvs_clip_stride, d.mks_clip_stride, d.out_clip_stride = t * 3 * HW, t * HW, t * 3 * HW
+        d.state_hr, d.state_l1 = buf["state_hr"].data_ptr(), buf["state_l1"].data_ptr()
+        ws = buf["ws"]
+        for i in range(t):
+            d.first = int(first_flags[i])
+            d.lr4 = buf["lr4"].data_ptr() + i * hw * 4 * 4
+            d.x_lr = buf["x_lr"].data_ptr() + i * hw * self.mid_channels * 4
+            d.flow = buf["flows"].data_ptr() + i * hw * 2 * 4
+            d.fvs = fvs.data_ptr() + i * 3 * HW * 4
+            d.mks = mks.data_ptr() + i * HW
+            if fgs is not None:
+                d.fg, d.fg_clip_stride = fgs.data_ptr() + i * HW * 4, t * HW
+            d.out = out.data_ptr() + i * 3 * HW * 4
+            L.check(lib.crfp_dsv_frame(C.byref(d), C.byref(W), ws.data_ptr(), ws.numel(), st), f"dsv_frame[{i}]")
+
+
+class CRFP_DSV(_CRFPBase):
+    """Drop-in for `model.CRFP.CRFP_DSV` (the model main.py:34 builds)."""
+
+    def forward(self, lrs, fvs, mks):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise NotImplementedError("crfp_b200: the backward kernels are not implemented yet; call under "
+                                      "torch.no_grad() / model.eval() (SURVEY.md 8(f) rank 1)")
+        with torch.no_grad():
+            lrs, fvs, mks = self._check_inputs(lrs, fvs, mks)
+            n, t, _, h, w = lrs.shape
+            dev = lrs.device
+            with torch.cuda.device(dev):
+                L.check(L.lib().crfp_check_device(), "device check (sm_100 required)")
+                W = self._weights(dev)
+                buf = self._buffers(n, t, h, w, dev)
+                out = torch.empty(n, t, 3, 8 * h, 8 * w, device=dev, dtype=torch.float32)
+                st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+                shp = L.DsvShape(n=n, t=t, h=h, w=w, mid_channels=self.mid_channels)
+                L.check(L.lib().crfp_dsv_prepare(C.byref(shp), C.byref(W), lrs.data_ptr(), None, buf["lr4"].data_ptr(),
+                                                 buf["x_lr"].data_ptr(), buf["flows"].data_ptr(), buf["ws"].data_ptr(),
+                                                 buf["ws"].numel(), st), "dsv_prepare")
+                self._run_frames(buf, W, lrs, fvs, mks, None, out, [i == 0 for i in range(t)])
+            return out
+
+    def forward_patch(self, lrs, fovea_patch, coords):
+        """Convenience entry named by BASELINE.json: `fovea_patch` (n,t,3,FV,FV) pasted at integer top-left
+        `coords` (n,t,2) = [y, x] exactly as the data loader does (dataset/reds.py:196-201)."""
+        n, t, _, h, w = lrs.shape
+        fv = fovea_patch.shape[-1]
+        H, Wd = 8 * h, 8 * w
+        mks = fovea_rect(coords.cpu(), fv, H, Wd).to(lrs.device)
+        fvs = torch.zeros(n, t, 3, H, Wd, device=lrs.device, dtype=torch.float32)
+        cc = coords.cpu()
+        for b in range(n):
+            for i in range(t):
+                y, x = int(cc[b, i, 0]), int(cc[b, i, 1])
+                fvs[b, i, :, y:y + fv, x:x + fv] = fovea_patch[b, i]
+        return self.forward(lrs, fvs, mks)
+
+
+class MRCF_simple_v18(_CRFPBase):
+    """Drop-in for the streaming `model.CRFP_test.MRCF_simple_v18`: one (or a few) frames per call, recurrent
+    state kept on the module, `clear_states()` between clips."""
+
+    def __init__(self, device, mid_channels=16, y_only=False, hr_dcn=True, offset_prop=True, split_ratio=3,
+                 spynet_pretrained=None):
+        super().__init__(device, mid_channels, y_only, hr_dcn, offset_prop, spynet_pretrained)
+        if split_ratio != 3:
+            raise L.CrfpError("split_ratio=3 only")
+        self.pre_lr = None
+        self._has_state = False
+
+    def clear_states(self):
+        self.pre_lr = None
+        self._has_state = False
+
+    @torch.no_grad()
+    def forward(self, lrs, fvs, mks, fgs):
+        lrs, fvs, mks = self._check_inputs(lrs, fvs, mks)
+        n, t, _, h, w = lrs.shape
+        dev = lrs.device
+        fgs = fgs.to(device=dev, dtype=torch.float32).contiguous()
+        if tuple(fgs.shape) != (n, t, 1, 8 * h, 8 * w):
+            raise ValueError(f"fgs must be {(n, t, 1, 8 * h, 8 * w)}")
+        with torch.cuda.device(dev):
+            W = self._weights(dev)
+            buf = self._buffers(n, t, h, w, dev)
+            out = torch.empty(n, t, 3, 8 * h, 8 * w, device=dev, dtype=torch.float32)
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            shp = L.DsvShape(n=n, t=t, h=h, w=w, mid_channels=self.mid_channels)
+            # first frame of a stream is paired with the last frame of this call (CRFP_test.py:2232-2239); its
+            # flow is never used because that frame takes the no-alignment branch
+            prev = self.pre_lr if self.pre_lr is not None else lrs[:, -1].contiguous()
+            L.check(L.lib().crfp_dsv_prepare(C.byref(shp), C.byref(W), lrs.data_ptr(), prev.data_ptr(),
+                                             buf["lr4"].data_ptr(), buf["x_lr"].data_ptr(), buf["flows"].data_ptr(),
+                                             buf["ws"].data_ptr(), buf["ws"].numel(), st), "dsv_prepare")
+            self.pre_lr = lrs[:, -1].clone()
+            first = [(not self._has_state) and i == 0 for i in range(t)]
+            self._run_frames(buf, W, lrs, fvs, mks, fgs, out, first)
+            self._has_state = True
+        return out

@@ -1,0 +1,290 @@
+/*
+ * crfp_b200.h — C ABI of libcrfp_b200.so: the B200 (sm_100a) implementation of CRFP's recurrent
+ * cross-resolution propagation hot path (reference: eugenelet/CRFP, model/CRFP.py).
+ *
+ * Conventions
+ *   - plain C: device pointers + sizes, no torch types; every pointer is CALLER-OWNED device memory.
+ *   - every entry point is asynchronous on the given `cudaStream_t` (passed as void*), never
+ *     allocates, never synchronises, keeps no global mutable state, and returns 0 (CRFP_OK) or a
+ *     negative crfp_status; it never throws.
+ *   - activations are fp32 NHWC ("channels-last": a pixel's channels are contiguous); a tensor is
+ *     addressed as ptr[((n*H + y)*W + x)*cstride + coffset + c] so that channel slices of a wider
+ *     tensor can be read/written in place (this is how torch.cat / torch.chunk of the reference
+ *     disappear).  The user-facing NCHW tensors (lrs, fvs, mks, output) are read/written directly.
+ *   - conv weights are passed PACKED, see crfp_conv3x3_fwd.
+ *
+ * Reference interfaces replaced (file:line under /root/reference):
+ *   crfp_flow_warp_fwd        flow_warp(x, flow)                         model/CRFP.py:90-130
+ *   crfp_dcn_v2_fwd           dcn_v2.DCNv2.forward(input, offset, mask)  model/CRFP.py:318-320,350
+ *                             (= _ext.dcn_v2_forward of jinfagang/DCNv2_latest, README.md:26)
+ *   crfp_conv3x3_fwd          nn.Conv2d(3x3,s1,p1) + bias + LeakyReLU/ReLU + residual + torch.cat of
+ *                             the inputs + torch.chunk / F.pixel_shuffle / pixel_unshuffle of the
+ *                             output:  model/CRFP.py:154-193, 239-279, 28-42, 433-552, 303-317
+ *   crfp_resize_bilinear      nn.Upsample(bilinear, align_corners=False) model/CRFP.py:1471-1478,
+ *                             F.interpolate(size=) model/CRFP.py:808-812
+ *   crfp_avgpool2             nn.AvgPool2d(2,2)                          model/CRFP.py:755,762,769
+ *   crfp_dsv_prepare          CRFP_DSV.compute_flow + encoder_lr         model/CRFP.py:1483-1508,1540
+ *   crfp_dsv_frame            one iteration of the t-loop of CRFP_DSV.forward   model/CRFP.py:1555-1684
+ *                             incl. fovea compositing + encoder_hr (1542-1547) for that frame
+ */
+#ifndef CRFP_B200_H
+#define CRFP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRFP_ABI_VERSION 1
+
+typedef enum {
+  CRFP_OK = 0,
+  CRFP_ERR_BAD_SHAPE = -1,    /* inconsistent sizes / channel counts */
+  CRFP_ERR_UNSUPPORTED = -2,  /* valid request the library has no kernel for */
+  CRFP_ERR_WORKSPACE = -3,    /* workspace too small */
+  CRFP_ERR_CUDA = -4,         /* a CUDA runtime call or launch failed (see crfp_last_cuda_error) */
+  CRFP_ERR_NULL = -5          /* required pointer is NULL */
+} crfp_status;
+
+typedef void* crfp_stream; /* cudaStream_t */
+
+/* ------------------------------------------------------------------ misc */
+int crfp_abi_version(void);
+const char* crfp_status_string(int status);
+/* last cudaError_t seen by this thread inside the library, as text (thread-local) */
+const char* crfp_last_cuda_error(void);
+/* number of kernel launches issued by this library from the calling thread since the last reset */
+long long crfp_launch_count(void);
+void crfp_launch_count_reset(void);
+/* device properties check: 0 if the current device is sm_100 (B200), CRFP_ERR_UNSUPPORTED otherwise */
+int crfp_check_device(void);
+
+/* ------------------------------------------------------------------ activations / epilogues */
+enum {
+  CRFP_ACT_NONE = 0,
+  CRFP_ACT_LRELU = 1,     /* LeakyReLU(0.1) */
+  CRFP_ACT_RELU = 2,
+  CRFP_ACT_DCN_HEAD = 3,  /* channels [0, head_split): max_mag*tanh(v) + flow (even ch: flow y, odd ch: flow x);
+                             channels [head_split, cout): sigmoid(v)        (model/CRFP.py:337-340,349) */
+  CRFP_ACT_TANH256 = 4    /* tanh(v) * 256                                   (model/CRFP.py:807) */
+};
+
+enum { CRFP_SRC_PLAIN = 0, CRFP_SRC_UNSHUFFLE4 = 1 };
+enum { CRFP_OUT_NHWC = 0, CRFP_OUT_SHUFFLE = 1 };
+
+typedef struct {
+  const float* ptr; /* NHWC base of image 0 */
+  int32_t c;        /* channels taken from this source */
+  int32_t cstride;  /* floats per pixel of the underlying tensor */
+  int32_t coffset;  /* first channel taken */
+  int32_t mode;     /* CRFP_SRC_PLAIN, or CRFP_SRC_UNSHUFFLE4: the source is a (4h x 4w) plane with `c/16`
+                       channels read through pixel_unshuffle(4) (model/CRFP.py:28-42); packed channel order
+                       of such a source is (dy*4+dx)*(c/16) + ch, see crfp_conv_pack_index */
+} crfp_src;
+
+typedef struct {
+  float* ptr;      /* NHWC base of image 0 */
+  int32_t c;       /* number of output channels routed here (segments are consecutive) */
+  int32_t cstride;
+  int32_t coffset;
+  int32_t _pad;
+} crfp_dst;
+
+/*
+ * 3x3, stride 1, pad 1 convolution over the channel-concatenation of up to 3 NHWC sources.
+ *   packed input channel space: each source is padded up to a multiple of 4 channels, the total up to
+ *   a multiple of 8 (= cin_packed); packed output channels: cout padded up to a multiple of
+ *   crfp_conv_cout_pad(cout).  weight[(tap*cin_packed + ci)*cout_packed + co], tap = ky*3+kx, zero in
+ *   all padding; bias[cout_packed].
+ *   out_mode CRFP_OUT_NHWC: conv channel co goes to the dst segment that contains it.
+ *   out_mode CRFP_OUT_SHUFFLE: F.pixel_shuffle(r): conv channel o*r*r + dy*r + dx goes to pixel
+ *   (y*r+dy, x*r+dx), channel o of dst[0] (an (h*r x w*r) plane).
+ *   epilogue order: v = acc + bias; v = act(v); v += residual; v *= post_scale.
+ */
+typedef struct {
+  int32_t n, h, w;
+  int32_t nsrc;
+  crfp_src src[3];
+  int32_t cout;
+  int32_t act;
+  const float* weight;
+  const float* bias;
+  int32_t out_mode;
+  int32_t shuffle_r;
+  int32_t ndst;
+  int32_t head_split;   /* CRFP_ACT_DCN_HEAD only */
+  crfp_dst dst[2];
+  const float* residual; /* optional NHWC, added after the activation */
+  int32_t res_cstride;
+  int32_t res_coffset;
+  const float* flow;     /* CRFP_ACT_DCN_HEAD only: NHWC 2-channel flow (x, y) at the output resolution */
+  float post_scale;      /* 0 is treated as 1 */
+  float head_mag;        /* CRFP_ACT_DCN_HEAD: max_residue_magnitude (10) */
+} crfp_conv_desc;
+
+int crfp_conv3x3_fwd(const crfp_conv_desc* d, crfp_stream stream);
+/* packed sizes for a conv over sources with `c[i]` channels */
+int crfp_conv_cin_packed(int nsrc, const int32_t* c);
+int crfp_conv_cout_packed(int cout);
+size_t crfp_sizeof_conv_desc(void);
+
+/* ------------------------------------------------------------------ flow_warp */
+/*
+ * out[n,y,x,c] = bilinear(x_in[n,:,:,c], y + flow[n,y,x,1], x + flow[n,y,x,0]); corners outside the
+ * image contribute 0 (padding_mode='zeros', border=0) or are clamped (padding_mode='border', border=1);
+ * sampling positions are computed with the reference's fp32 op sequence (normalise to [-1,1], then
+ * grid_sample align_corners=True) so that floor() agrees bit for bit.
+ */
+typedef struct {
+  int32_t n, h, w, c;      /* c % 4 == 0 */
+  const float* x; int32_t x_cstride, x_coffset;
+  const float* flow;       /* NHWC, 2 channels (x, y) */
+  float* out; int32_t out_cstride, out_coffset;
+  int32_t border;
+  int32_t _pad;
+} crfp_warp_desc;
+int crfp_flow_warp_fwd(const crfp_warp_desc* d, crfp_stream stream);
+/* debug/parity: the integer corner indices (x0, y0) flow_warp uses at every pixel: int32 [n,h,w] each */
+int crfp_flow_warp_indices(int n, int h, int w, const float* flow, int32_t* x0, int32_t* y0, crfp_stream stream);
+size_t crfp_sizeof_warp_desc(void);
+
+/* ------------------------------------------------------------------ DCNv2 */
+/*
+ * Modulated deformable 3x3 convolution (stride 1, pad 1, dilation 1), DCNv2 semantics:
+ *   out[n,y,x,o] = b[o] + sum_{c,i,j} W[o,c,i,j] * m[n,y,x,g*9+t] * bilinear(in[n,:,:,c], py, px),
+ *   t = i*3+j, g = c / (C/dg), py = (y-1+i) + off[n,y,x,(g*9+t)*2], px = (x-1+j) + off[...+1].
+ * offset and mask are NHWC with their own pixel strides / channel offsets (so they may live in one fused
+ * "heads" tensor).  shared_taps=1: one (dy,dx) and one mask per deformable group shared by the 9 taps
+ * (the `repeat=True` HR module, model/CRFP.py:341-347): offset has 2*dg channels ordered [dy(g)..., dx(g)...]
+ * and mask dg channels.
+ * weight packed as [k][co] with k = (g*9+t)*(C/dg) + c_in_group, co padded to a multiple of 4; bias[co].
+ * Supported: (C=32, dg=8, cout=32) and (C=4, dg=1, cout=4).
+ */
+typedef struct {
+  int32_t n, h, w;
+  int32_t c, cout, dg;
+  int32_t shared_taps;
+  int32_t _pad;
+  const float* x; int32_t x_cstride, x_coffset;
+  const float* offset; int32_t off_cstride, off_coffset;
+  const float* mask; int32_t mask_cstride, mask_coffset;
+  const float* weight;
+  const float* bias;
+  float* out; int32_t out_cstride, out_coffset;
+} crfp_dcn_desc;
+int crfp_dcn_v2_fwd(const crfp_dcn_desc* d, crfp_stream stream);
+/* debug/parity: floor(py), floor(px) for every (pixel, group, tap): int32 [n,h,w,dg*9] each (non-shared form) */
+int crfp_dcn_v2_indices(const crfp_dcn_desc* d, int32_t* y0, int32_t* x0, crfp_stream stream);
+size_t crfp_sizeof_dcn_desc(void);
+
+/* ------------------------------------------------------------------ resampling / layout */
+/*
+ * Bilinear resize, align_corners=False, NHWC, c channels (all of the pixel: cstride == c):
+ * src = max((dst+0.5)*rscale - 0.5, 0).  rscale_{h,w} = 1/scale_factor for nn.Upsample(scale_factor=..)
+ * or in/out for F.interpolate(size=..); out = value * mul.
+ */
+int crfp_resize_bilinear(int n, int hin, int win, int c, const float* in, int hout, int wout, float rscale_h,
+                         float rscale_w, float mul, float* out, crfp_stream stream);
+int crfp_avgpool2(int n, int hin, int win, int c, const float* in, float* out, crfp_stream stream);
+/* NCHW (with an explicit image stride in floats) -> NHWC with cpad >= c channels (extra channels zero) */
+int crfp_nchw_to_nhwc(int n, int c, int h, int w, const float* in, long long in_image_stride, int cpad, float* out,
+                      crfp_stream stream);
+int crfp_nhwc_to_nchw(int n, int c, int h, int w, const float* in, int in_cstride, int in_coffset, float* out,
+                      long long out_image_stride, crfp_stream stream);
+
+/* ------------------------------------------------------------------ CRFP_DSV composite entry points */
+/* conv layers of CRFP_DSV in the order the library expects them in crfp_dsv_weights.layer[] */
+#define CRFP_DSV_MAX_LAYERS 72
+typedef struct {
+  const float* w; /* packed as the consuming kernel expects (see crfp_dsv_layer_info) */
+  const float* b;
+} crfp_layer;
+
+typedef struct {
+  int32_t mid_channels; /* 32 */
+  int32_t nlayers;      /* must equal crfp_dsv_num_layers() */
+  crfp_layer layer[CRFP_DSV_MAX_LAYERS];
+} crfp_dsv_weights;
+
+/*
+ * Static description of layer `i` so that the host can pack a state_dict without duplicating tables:
+ *   key      state_dict prefix ("dcn_0.dcn_block.0", ...), weight = key+".weight", bias = key+".bias"
+ *   kind     0 conv (crfp_conv3x3_fwd packing), 1 DCN (crfp_dcn_v2_fwd packing),
+ *            2 fused heads: conv packing of cat(key.weight, key2.weight) along cout (dcn_offset ++ dcn_mask)
+ *   nsrc/c   the channel split of the input concat (conv packing pads each source)
+ *   mode     per-source CRFP_SRC_*
+ *   ci_lo    first input channel of the ORIGINAL weight this packed layer consumes (first-frame variants
+ *            use only a slice of the input channels, model/CRFP.py:1637 and SURVEY.md App. A)
+ */
+typedef struct {
+  const char* key;
+  const char* key2;
+  int32_t kind;
+  int32_t nsrc;
+  int32_t c[3];
+  int32_t mode[3];
+  int32_t cout;
+  int32_t ci_lo;
+  int32_t dg;
+  int32_t thin; /* 1: consumed by the thin-channel kernels (cout <= 4): weight [9][cin_packed][4] */
+} crfp_layer_info;
+int crfp_dsv_num_layers(void);
+int crfp_dsv_layer_info(int i, crfp_layer_info* info);
+
+typedef struct {
+  int32_t n, t, h, w;     /* clip batch, frames in this call, LR size */
+  int32_t mid_channels;
+  int32_t _pad;
+} crfp_dsv_shape;
+
+/*
+ * Clip-level stage for frames [0, t) of `n` clips:
+ *   lrs      NCHW fp32 (n, t, 3, h, w) contiguous
+ *   prev_lr  optional NCHW (n, 3, h, w): frame preceding lrs[:,0] (streaming); NULL in clip mode
+ *   lr4      out: NHWC4 copy of lrs, image index b*t+i                       [n*t*h*w*4]
+ *   x_lr     out: encoder_lr features NHWC 32ch, image index b*t+i           [n*t*h*w*C]
+ *   flows    out: NHWC 2ch flow from frame i to frame i-1, image index b*t+i [n*t*h*w*2]; entry i=0 is
+ *            written only when prev_lr != NULL (otherwise left untouched)
+ */
+size_t crfp_dsv_prepare_workspace(const crfp_dsv_shape* s);
+int crfp_dsv_prepare(const crfp_dsv_shape* s, const crfp_dsv_weights* wts, const float* lrs, const float* prev_lr,
+                     float* lr4, float* x_lr, float* flows, void* workspace, size_t ws_bytes, crfp_stream stream);
+
+/*
+ * One recurrent step for `n` clips (model/CRFP.py:1555-1684).  All per-frame inputs are passed as the pointer
+ * to clip 0's frame plus the stride (in elements) between clips.
+ *   first        1: no previous state (i == 0 branch), state buffers are only written
+ *   lr4/x_lr/flow   this frame's slices of the crfp_dsv_prepare outputs (clip stride in floats)
+ *   fvs          NCHW fp32 (3, 8h, 8w) fovea frame; mks: bool/uint8 (1, 8h, 8w)
+ *   fg           optional uint8/float? NULL in clip mode (streaming regional mask, fp32 (1,8h,8w))
+ *   state_hr     in/out NHWC (n, 8h, 8w, 4): feat_prop_lv3 (S)
+ *   state_l1     in/out NHWC (n, 2h, 2w, 24): [feat_lv0 | feat_lv1 | feat_lv2]
+ *   out          NCHW fp32 (3, 8h, 8w) per clip
+ */
+typedef struct {
+  crfp_dsv_shape shape;   /* t ignored */
+  int32_t first;
+  int32_t skip_outside_fovea; /* 1: evaluate encoder_hr/conv_tttf only on tiles whose (dilated) mask is non-empty
+                                 (bit-identical) */
+  const float* lr4;   long long lr4_clip_stride;
+  const float* x_lr;  long long x_lr_clip_stride;
+  const float* flow;  long long flow_clip_stride;
+  const float* fvs;   long long fvs_clip_stride;
+  const uint8_t* mks; long long mks_clip_stride;
+  const float* fg;    long long fg_clip_stride;
+  float* state_hr;
+  float* state_l1;
+  float* out;         long long out_clip_stride;
+} crfp_dsv_frame_desc;
+size_t crfp_dsv_frame_workspace(const crfp_dsv_shape* s);
+int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weights* wts, void* workspace, size_t ws_bytes,
+                   crfp_stream stream);
+size_t crfp_sizeof_dsv_weights(void);
+size_t crfp_sizeof_dsv_frame_desc(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRFP_B200_H */

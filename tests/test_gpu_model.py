@@ -1,0 +1,124 @@
+"""GPU parity tests (-m gpu) of the drop-in modules against the oracle and the reference's golden outputs.
+Bar (BASELINE.json north_star): fp32 max-abs <= 1e-3 on the output tensor."""
+import os
+
+import pytest
+import torch
+
+from crfp_b200.synthetic import make_clip, make_state_dict
+from oracle import crfp_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return make_state_dict(seed=1)
+
+
+@pytest.fixture(scope="module")
+def model(sd):
+    from crfp_b200 import CRFP_DSV
+    m = CRFP_DSV("cuda", mid_channels=32).eval()
+    m.load_state_dict(sd, strict=True)
+    return m.cuda()
+
+
+def _run(model, lrs, fvs, mks):
+    out = model(lrs.cuda(), fvs.cuda(), mks.cuda())
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+@pytest.mark.parametrize("name", ["dsv_n1_t3_16x24", "dsv_n2_t2_18x20", "dsv_n1_t1_8x8"])
+def test_against_reference_golden(name, golden_dir, model):
+    fix = torch.load(os.path.join(golden_dir, name + ".pt"))
+    c = fix["case"]
+    lrs, fvs, mks, _ = make_clip(seed=c["seed"], n=c["n"], t=c["t"], h=c["h"], w=c["w"], fv_size=c["fv"])
+    out = _run(model, lrs, fvs, mks)
+    assert out.shape == fix["out"].shape
+    err = (out - fix["out"]).abs().max().item()
+    print(f"{name}: max-abs vs reference golden {err:.3e}")
+    assert err <= TOL
+
+
+@pytest.mark.parametrize("n,t,h,w,fv", [(1, 5, 32, 48, 96), (2, 3, 24, 40, 64), (1, 4, 45, 80, 96), (3, 2, 16, 16, 128)])
+def test_against_oracle(model, sd, n, t, h, w, fv):
+    lrs, fvs, mks, _ = make_clip(seed=21, n=n, t=t, h=h, w=w, fv_size=fv)
+    taps = []
+    ref = O.crfp_dsv_forward(sd, lrs, fvs, mks, taps=taps)
+    out = _run(model, lrs, fvs, mks)
+    errs = [(out[:, i] - ref[:, i]).abs().max().item() for i in range(t)]
+    print(f"n={n} t={t} {h}x{w}: per-frame max-abs {['%.2e' % e for e in errs]}")
+    assert max(errs) <= TOL
+
+
+def test_mask_variants_and_skip_flag(model, sd):
+    """Arbitrary boolean masks (quadrant, empty, full) and the exactness of the outside-fovea skip."""
+    n, t, h, w = 1, 3, 16, 24
+    lrs, fvs, mks, _ = make_clip(seed=5, n=n, t=t, h=h, w=w, fv_size=32)
+    mks[:, 0] = False                                  # no fovea at all in frame 0
+    mks[:, 1, :, : 4 * h, : 4 * w] = True              # a whole quadrant (DemoHscan, dataset/reds.py:197-198)
+    mks[:, 2] = True                                   # everything is fovea
+    fvs = torch.rand(n, t, 3, 8 * h, 8 * w, generator=torch.Generator().manual_seed(1)) * mks
+    ref = O.crfp_dsv_forward(sd, lrs, fvs, mks)
+    out = _run(model, lrs, fvs, mks)
+    assert (out - ref).abs().max().item() <= TOL
+    model.skip_outside_fovea = False
+    out2 = _run(model, lrs, fvs, mks)
+    model.skip_outside_fovea = True
+    assert torch.equal(out, out2)
+
+
+def test_patch_coords_entry_and_determinism(model, sd):
+    n, t, h, w, fv = 1, 2, 16, 24, 48
+    lrs, fvs, mks, fv_sp = make_clip(seed=9, n=n, t=t, h=h, w=w, fv_size=fv)
+    patch = torch.stack([torch.stack([fvs[b, i, :, fv_sp[b, i, 0]:fv_sp[b, i, 0] + fv, fv_sp[b, i, 1]:fv_sp[b, i, 1] + fv]
+                                      for i in range(t)]) for b in range(n)])
+    a = _run(model, lrs, fvs, mks)
+    b = model.forward_patch(lrs.cuda(), patch.cuda(), fv_sp).cpu()
+    assert torch.equal(a, b)                           # exact agreement on the integer fovea rectangle
+    assert torch.equal(a, _run(model, lrs, fvs, mks))  # bitwise deterministic
+
+
+def test_clip_batch_equals_single_clips(model):
+    """Clips are independent (the multi-GPU sharding unit): a batch of 3 equals three batch-1 runs bit for bit."""
+    lrs, fvs, mks, _ = make_clip(seed=13, n=3, t=3, h=16, w=24, fv_size=48)
+    full = _run(model, lrs, fvs, mks)
+    for b in range(3):
+        one = _run(model, lrs[b:b + 1], fvs[b:b + 1], mks[b:b + 1])
+        assert torch.equal(full[b:b + 1], one)
+
+
+def test_streaming_module_matches_reference_golden(golden_dir, sd):
+    from crfp_b200 import MRCF_simple_v18
+    fix = torch.load(os.path.join(golden_dir, "stream_n1_t3_16x24.pt"))
+    c = fix["case"]
+    lrs, fvs, mks, _ = make_clip(seed=c["seed"], n=c["n"], t=c["t"], h=c["h"], w=c["w"], fv_size=c["fv"])
+    fgs = torch.ones(c["n"], c["t"], 1, 8 * c["h"], 8 * c["w"])
+    fgs[..., : 4 * c["h"], :] = 0.0
+    fgs[:, 0] = 1.0
+    m = MRCF_simple_v18("cuda", mid_channels=32).eval()
+    m.load_state_dict(sd, strict=True)
+    m.cuda()
+    outs = [m(lrs[:, i:i + 1].cuda(), fvs[:, i:i + 1].cuda(), mks[:, i:i + 1].cuda(), fgs[:, i:i + 1].cuda()).cpu()
+            for i in range(c["t"])]
+    err = (torch.cat(outs, 1) - fix["out"]).abs().max().item()
+    print(f"streaming: max-abs vs reference golden {err:.3e}")
+    assert err <= TOL
+    m.clear_states()
+    again = m(lrs[:, :1].cuda(), fvs[:, :1].cuda(), mks[:, :1].cuda(), fgs[:, :1].cuda()).cpu()
+    assert torch.equal(again, outs[0])
+
+
+def test_reds_native_shape_long_clip_properties(model, sd):
+    """BASELINE config-2 shape (LR 90x160 -> 720x1280), t=12: finite, deterministic, and frame i only depends on
+    frames <= i (causality of the recurrence): a 12-frame run and an 8-frame run agree on the first 8 frames."""
+    lrs, fvs, mks, _ = make_clip(seed=3, n=1, t=12, h=90, w=160, fv_size=96)
+    out = _run(model, lrs, fvs, mks)
+    assert torch.isfinite(out).all()
+    out8 = _run(model, lrs[:, :8], fvs[:, :8], mks[:, :8])
+    assert torch.equal(out[:, :8], out8)
+    ref = O.crfp_dsv_forward(sd, lrs[:, :3], fvs[:, :3], mks[:, :3])
+    assert (out[:, :3] - ref).abs().max().item() <= TOL
