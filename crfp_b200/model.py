@@ -124,7 +124,7 @@ class _CRFPBase(nn.Module):
         self._packed = (key, keep, W)
         return W
 
-    def _buffers(self, n, t, h, w, device):
+    def _clip_buffers(self, n, t, h, w, device):
         key = (n, t, h, w, str(device))
         if key not in self._ws:
             self._ws.clear()
@@ -201,7 +201,7 @@ class CRFP_DSV(_CRFPBase):
             with torch.cuda.device(dev):
                 L.check(L.lib().crfp_check_device(), "device check (sm_100 required)")
                 W = self._weights(dev)
-                buf = self._buffers(n, t, h, w, dev)
+                buf = self._clip_buffers(n, t, h, w, dev)
                 out = torch.empty(n, t, 3, 8 * h, 8 * w, device=dev, dtype=torch.float32)
                 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
                 shp = L.DsvShape(n=n, t=t, h=h, w=w, mid_channels=self.mid_channels)
@@ -253,7 +253,7 @@ class MRCF_simple_v18(_CRFPBase):
             raise ValueError(f"fgs must be {(n, t, 1, 8 * h, 8 * w)}")
         with torch.cuda.device(dev):
             W = self._weights(dev)
-            buf = self._buffers(n, t, h, w, dev)
+            buf = self._clip_buffers(n, t, h, w, dev)
             out = torch.empty(n, t, 3, 8 * h, 8 * w, device=dev, dtype=torch.float32)
             st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
             shp = L.DsvShape(n=n, t=t, h=h, w=w, mid_channels=self.mid_channels)
