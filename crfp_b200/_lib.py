@@ -100,6 +100,7 @@ SYMBOLS = {
     "crfp_launch_count": (C.c_longlong, []),
     "crfp_launch_count_reset": (None, []),
     "crfp_check_device": (C.c_int, []),
+    "crfp_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "crfp_conv3x3_fwd": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "crfp_conv_cin_packed": (C.c_int, [C.c_int, C.POINTER(C.c_int32)]),
     "crfp_conv_cout_packed": (C.c_int, [C.c_int]),

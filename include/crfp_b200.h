@@ -61,6 +61,10 @@ void crfp_launch_count_reset(void);
 /* device properties check: 0 if the current device is sm_100 (B200), CRFP_ERR_UNSUPPORTED otherwise */
 int crfp_check_device(void);
 
+/* tcgen05 plumbing self-test: D[m][n] = sum_k A[m+shift][k]*B[n][k] (m<128) with bf16 A[rowsA][K], B[N][K]
+ * row-major in HBM, fp32 D[128][N]; exercises the shifted-window operand addressing of the conv kernels. */
+int crfp_selftest_umma(int rowsA, int K, int N, int shift, const void* A, const void* B, float* D, crfp_stream stream);
+
 /* ------------------------------------------------------------------ activations / epilogues */
 enum {
   CRFP_ACT_NONE = 0,
