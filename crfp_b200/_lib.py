@@ -16,6 +16,7 @@ CRFP_OK = 0
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_DCN_HEAD, ACT_TANH256 = 0, 1, 2, 3, 4
 SRC_PLAIN, SRC_UNSHUFFLE4 = 0, 1
 OUT_NHWC, OUT_SHUFFLE = 0, 1
+TC_OUT_BF16, TC_OUT_F32, TC_OUT_SHUFFLE_F32 = 0, 1, 2
 MAX_LAYERS = 72
 
 c_float_p = C.POINTER(C.c_float)
@@ -38,6 +39,21 @@ class ConvDesc(C.Structure):
                 ("weight", C.c_void_p), ("bias", C.c_void_p),
                 ("out_mode", C.c_int32), ("shuffle_r", C.c_int32), ("ndst", C.c_int32), ("head_split", C.c_int32),
                 ("dst", Dst * 2),
+                ("residual", C.c_void_p), ("res_cstride", C.c_int32), ("res_coffset", C.c_int32),
+                ("flow", C.c_void_p), ("post_scale", C.c_float), ("head_mag", C.c_float)]
+
+
+class TcSrc(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("c", C.c_int32), ("cstride", C.c_int32), ("coffset", C.c_int32), ("_pad", C.c_int32)]
+
+
+class ConvTcDesc(C.Structure):
+    _fields_ = [("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("nsrc", C.c_int32),
+                ("src", TcSrc * 3),
+                ("cout", C.c_int32), ("act", C.c_int32),
+                ("weight", C.c_void_p), ("bias", C.c_void_p),
+                ("out_kind", C.c_int32), ("shuffle_r", C.c_int32), ("ndst", C.c_int32), ("head_split", C.c_int32),
+                ("dst", TcSrc * 2),
                 ("residual", C.c_void_p), ("res_cstride", C.c_int32), ("res_coffset", C.c_int32),
                 ("flow", C.c_void_p), ("post_scale", C.c_float), ("head_mag", C.c_float)]
 
@@ -102,6 +118,9 @@ SYMBOLS = {
     "crfp_check_device": (C.c_int, []),
     "crfp_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "crfp_conv3x3_fwd": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "crfp_conv3x3_tc_fwd": (C.c_int, [C.POINTER(ConvTcDesc), C.c_void_p]),
+    "crfp_tc_cout_tile": (C.c_int, [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "crfp_sizeof_conv_tc_desc": (C.c_size_t, []),
     "crfp_conv_cin_packed": (C.c_int, [C.c_int, C.POINTER(C.c_int32)]),
     "crfp_conv_cout_packed": (C.c_int, [C.c_int]),
     "crfp_sizeof_conv_desc": (C.c_size_t, []),
@@ -148,7 +167,7 @@ def lib():
             fn = getattr(h, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        for struct, fn in ((ConvDesc, h.crfp_sizeof_conv_desc), (WarpDesc, h.crfp_sizeof_warp_desc),
+        for struct, fn in ((ConvDesc, h.crfp_sizeof_conv_desc), (ConvTcDesc, h.crfp_sizeof_conv_tc_desc), (WarpDesc, h.crfp_sizeof_warp_desc),
                            (DcnDesc, h.crfp_sizeof_dcn_desc), (DsvWeights, h.crfp_sizeof_dsv_weights),
                            (DsvFrameDesc, h.crfp_sizeof_dsv_frame_desc)):
             if C.sizeof(struct) != fn():

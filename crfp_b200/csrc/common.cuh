@@ -1,6 +1,8 @@
 // Shared helpers for libcrfp_b200 (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <string.h>
 #include <stdint.h>
 
 #include "../../include/crfp_b200.h"
@@ -75,6 +77,34 @@ struct ConvParams {
   long long out_clip_stride;      // EPI_OUT_NCHW: floats between clips of the planar output
   int out_planes;                 // EPI_OUT_NCHW: number of planes written (3)
 };
+
+// ---- tensor-core (tcgen05) conv description: bf16 NHWC sources, channel counts multiples of 8
+enum { TC_OUT_BF16 = 0, TC_OUT_F32 = 1, TC_OUT_SHUFFLE_F32 = 2 };
+
+struct TcParams {
+  int n, h, w;
+  int nsrc;
+  const __nv_bfloat16* src[3];
+  int src_c[3], src_cstride[3], src_coffset[3];
+  int kstart[3];          // first 8-channel chunk of each source
+  int kc_real, kc_total;  // chunks of 8 input channels; kc_total = kc_real rounded up to even (K step = 16)
+  int cout, nt, ntiles;   // nt = UMMA N (cout tile, multiple of 16, <= 128)
+  const __nv_bfloat16* weight;  // [ntiles][9][kc_total][nt][8]
+  const float* bias;            // [ntiles*nt]
+  int act;
+  int out_kind, shuffle_r;
+  int ndst;
+  void* dst[2];
+  int dst_c[2], dst_cstride[2], dst_coffset[2];
+  const __nv_bfloat16* residual;
+  int res_cstride, res_coffset;
+  const float* flow;
+  int head_split;
+  float head_mag, post_scale;
+  int rows_per_cta;
+};
+void tc_cout_tile(int cout, int* nt, int* ntiles);
+int launch_conv_tc(TcParams p, cudaStream_t st);
 
 int conv_params_from_desc(const crfp_conv_desc* d, ConvParams* p);
 int launch_conv_wide(const ConvParams& p, cudaStream_t st);

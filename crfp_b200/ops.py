@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
-from .packing import cin_packed, cout_packed, pack_conv, pack_dcn
+from .packing import cin_packed, cout_packed, pack_conv, pack_conv_tc, pack_dcn
 
 
 def _stream():
@@ -195,3 +195,46 @@ def avgpool2_nhwc(x):
     out = torch.empty(n, h // 2, w // 2, c, device=x.device, dtype=torch.float32)
     L.check(L.lib().crfp_avgpool2(n, h, w, c, x.data_ptr(), out.data_ptr(), _stream()), "avgpool2")
     return out
+
+
+def conv3x3_tc_nhwc(srcs, weight, bias, act=L.ACT_NONE, residual=None, out_kind=L.TC_OUT_BF16, shuffle_r=0,
+                    post_scale=1.0, split=None, flow=None, head_split=0, head_mag=10.0, c_real=None):
+    """Tensor-core (tcgen05) 3x3 conv over the channel concat of bf16 NHWC `srcs` (channel counts multiples of 8)
+    with an OIHW fp32 weight.  `c_real[i]` = how many channels of source i the reference weight really has
+    (the remaining channels of that source must be zero)."""
+    for s in srcs:
+        if not (s.is_cuda and s.dtype == torch.bfloat16):
+            raise L.CrfpError("conv3x3_tc_nhwc: sources must be CUDA bfloat16 NHWC")
+    srcs = [s.contiguous() for s in srcs]
+    n, h, w, _ = srcs[0].shape
+    c_real = c_real or [s.shape[-1] for s in srcs]
+    cout = weight.shape[0]
+    wp, bp = pack_conv_tc(weight, bias, c_real)
+    d = L.ConvTcDesc()
+    d.n, d.h, d.w, d.nsrc = n, h, w, len(srcs)
+    for i, s in enumerate(srcs):
+        d.src[i] = L.TcSrc(ptr=s.data_ptr(), c=s.shape[-1], cstride=s.shape[-1], coffset=0)
+    d.cout, d.act = cout, act
+    d.weight, d.bias = wp.data_ptr(), bp.data_ptr()
+    d.post_scale, d.head_mag, d.head_split = post_scale, head_mag, head_split
+    d.out_kind, d.shuffle_r = out_kind, shuffle_r
+    if flow is not None:
+        flow = _req(flow, "flow")
+        d.flow = flow.data_ptr()
+    if residual is not None:
+        residual = residual.contiguous()
+        d.residual, d.res_cstride, d.res_coffset = residual.data_ptr(), residual.shape[-1], 0
+    dev = srcs[0].device
+    if out_kind == L.TC_OUT_SHUFFLE_F32:
+        r = shuffle_r
+        outs = [torch.zeros(n, h * r, w * r, cout // (r * r), device=dev, dtype=torch.float32)]
+    elif out_kind == L.TC_OUT_F32:
+        outs = [torch.zeros(n, h, w, cout, device=dev, dtype=torch.float32)]
+    else:
+        parts = list(split) if split else [cout]
+        outs = [torch.zeros(n, h, w, c, device=dev, dtype=torch.bfloat16) for c in parts]
+    d.ndst = len(outs)
+    for i, o in enumerate(outs):
+        d.dst[i] = L.TcSrc(ptr=o.data_ptr(), c=o.shape[-1], cstride=o.shape[-1], coffset=0)
+    L.check(L.lib().crfp_conv3x3_tc_fwd(C.byref(d), _stream()), "conv3x3_tc")
+    return outs[0] if len(outs) == 1 else tuple(outs)

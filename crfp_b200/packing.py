@@ -72,6 +72,40 @@ def pack_dcn(weight: torch.Tensor, bias: torch.Tensor, dg: int):
     return out.contiguous(), b.contiguous()
 
 
+def tc_cout_tile(cout: int):
+    """(nt, ntiles) exactly as crfp_tc_cout_tile computes them."""
+    tiles = (cout + 127) // 128
+    per = (cout + tiles - 1) // tiles
+    return max(16, (per + 15) // 16 * 16), tiles
+
+
+def pack_conv_tc(weight: torch.Tensor, bias: torch.Tensor, c_list, ci_lo: int = 0):
+    """OIHW -> bf16 [ntiles][9][kc][nt][8] for crfp_conv3x3_tc_fwd (+ fp32 bias [ntiles*nt]).
+
+    `c_list` are the REAL channels each source contributes; every source occupies ceil(c/8) chunks of 8 (the
+    caller's buffers are zero in the padding channels), the chunk total is rounded up to even."""
+    cout = weight.shape[0]
+    nt, ntiles = tc_cout_tile(cout)
+    idx, base = [], ci_lo
+    for c in c_list:
+        idx.extend(range(base, base + c))
+        idx.extend([-1] * ((-c) % 8))
+        base += c
+    if (len(idx) // 8) % 2:
+        idx.extend([-1] * 8)
+    kc = len(idx) // 8
+    w = weight.detach().to(torch.float32)
+    sel = torch.tensor([i if i >= 0 else 0 for i in idx], device=w.device, dtype=torch.long)
+    valid = torch.tensor([1.0 if i >= 0 else 0.0 for i in idx], device=w.device)
+    wp = (w[:, sel] * valid.view(1, -1, 1, 1)).reshape(cout, kc, 8, 9)          # (o, kc, j, tap)
+    full = torch.zeros(ntiles * nt, kc, 8, 9, device=w.device)
+    full[:cout] = wp
+    out = full.view(ntiles, nt, kc, 8, 9).permute(0, 4, 2, 1, 3).contiguous()    # (tile, tap, kc, n, j)
+    b = torch.zeros(ntiles * nt, device=w.device, dtype=torch.float32)
+    b[:cout] = bias.detach().to(torch.float32)
+    return out.to(torch.bfloat16).contiguous(), b.contiguous()
+
+
 def pack_layer(info: dict, sd):
     """Pack one entry of the library's layer table (crfp_dsv_layer_info) from a state_dict."""
     w, b = sd[info["key"] + ".weight"], sd[info["key"] + ".bias"]

@@ -134,6 +134,50 @@ int crfp_conv_cin_packed(int nsrc, const int32_t* c);
 int crfp_conv_cout_packed(int cout);
 size_t crfp_sizeof_conv_desc(void);
 
+/* ------------------------------------------------------------------ tensor-core conv (bf16 storage) */
+/*
+ * Same convolution on the 5th-gen tensor cores (tcgen05.mma, fp32 accumulation in TMEM): sources are bf16 NHWC
+ * with channel counts / strides / offsets that are multiples of 8; the packed K space is the plain
+ * concatenation of the sources (padded to a multiple of 16 channels).
+ *   weight: bf16 [ntiles][9][kc][nt][8] with (nt, ntiles) = crfp_tc_cout_tile(cout), kc = K/8:
+ *           element = W[tile*nt + n][kc*8 + j][tap]; bias fp32 [ntiles*nt].
+ *   out_kind CRFP_TC_OUT_BF16: bf16 NHWC, up to 2 channel segments (multiples of 8);
+ *            CRFP_TC_OUT_F32: fp32 NHWC into dst[0]; CRFP_TC_OUT_SHUFFLE_F32: pixel_shuffle(r) into fp32 dst[0].
+ *   residual: optional bf16 NHWC.  act / head_* / post_scale as in crfp_conv_desc.
+ */
+enum { CRFP_TC_OUT_BF16 = 0, CRFP_TC_OUT_F32 = 1, CRFP_TC_OUT_SHUFFLE_F32 = 2 };
+typedef struct {
+  const void* ptr; /* bf16 NHWC */
+  int32_t c, cstride, coffset, _pad;
+} crfp_tc_src;
+typedef struct {
+  void* ptr;
+  int32_t c, cstride, coffset, _pad;
+} crfp_tc_dst;
+typedef struct {
+  int32_t n, h, w;
+  int32_t nsrc;
+  crfp_tc_src src[3];
+  int32_t cout;
+  int32_t act;
+  const void* weight;
+  const float* bias;
+  int32_t out_kind;
+  int32_t shuffle_r;
+  int32_t ndst;
+  int32_t head_split;
+  crfp_tc_dst dst[2];
+  const void* residual; /* bf16 NHWC */
+  int32_t res_cstride;
+  int32_t res_coffset;
+  const float* flow;
+  float post_scale;
+  float head_mag;
+} crfp_conv_tc_desc;
+int crfp_conv3x3_tc_fwd(const crfp_conv_tc_desc* d, crfp_stream stream);
+int crfp_tc_cout_tile(int cout, int32_t* nt, int32_t* ntiles);
+size_t crfp_sizeof_conv_tc_desc(void);
+
 /* ------------------------------------------------------------------ flow_warp */
 /*
  * out[n,y,x,c] = bilinear(x_in[n,:,:,c], y + flow[n,y,x,1], x + flow[n,y,x,0]); corners outside the

@@ -1,0 +1,81 @@
+"""GPU tests (-m gpu) of the tcgen05 tensor-core kernels (bf16 storage, fp32 accumulation) against a PyTorch
+fp32 reference evaluated on the SAME bf16-rounded operands: differences are accumulation order + the final
+bf16 rounding of the output (<= 2^-8 relative)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def nhwc_bf16(x):
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+
+
+def nchw(x):
+    return x.float().permute(0, 3, 1, 2).contiguous().cpu()
+
+
+def close_bf16(got, ref, extra=0.0):
+    tol = ref.abs() * 2.0 ** -7 + 2e-3 + extra
+    bad = (got - ref).abs() > tol
+    assert not bad.any(), f"max err {(got - ref).abs().max().item():.4e}, {int(bad.sum())} elements out of tolerance"
+
+
+@pytest.mark.parametrize("c_list,cout,hw,act", [
+    ([32], 32, (9, 128), 1), ([32], 32, (21, 300), 1), ([32, 32], 32, (12, 130), 1), ([32, 32, 8], 32, (10, 70), 1),
+    ([24], 64, (16, 140), 0), ([32], 216, (7, 200), 0), ([64], 96, (5, 64), 2)])
+def test_conv_tc(c_list, cout, hw, act):
+    from crfp_b200 import ops
+    g = _g(1)
+    h, w = hw
+    n = 2
+    srcs = [bf(torch.randn(n, c, h, w, generator=g)) for c in c_list]
+    wt = bf(torch.randn(cout, sum(c_list), 3, 3, generator=g) * (2.0 / (9 * sum(c_list))) ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.1
+    ref = F.conv2d(torch.cat(srcs, 1), wt, b, padding=1)
+    ref = F.leaky_relu(ref, 0.1) if act == 1 else F.relu(ref) if act == 2 else ref
+    got = nchw(ops.conv3x3_tc_nhwc([nhwc_bf16(s) for s in srcs], wt.cuda(), b.cuda(), act=act))
+    close_bf16(got, ref)
+
+
+def test_conv_tc_epilogues():
+    from crfp_b200 import _lib as L
+    from crfp_b200 import ops
+    g = _g(2)
+    n, h, w = 1, 11, 150
+    x = bf(torch.randn(n, 32, h, w, generator=g))
+    r = bf(torch.randn(n, 32, h, w, generator=g))
+    wt = bf(torch.randn(32, 32, 3, 3, generator=g) * 0.08)
+    b = torch.randn(32, generator=g) * 0.1
+    ref = F.conv2d(x, wt, b, padding=1) + r
+    a, c = ops.conv3x3_tc_nhwc([nhwc_bf16(x)], wt.cuda(), b.cuda(), residual=nhwc_bf16(r), split=(24, 8))
+    close_bf16(nchw(a), ref[:, :24])
+    close_bf16(nchw(c), ref[:, 24:])
+    # fp32 output + DCN heads epilogue
+    flow = torch.randn(n, 2, h, w, generator=g) * 3
+    w216 = bf(torch.randn(216, 32, 3, 3, generator=g) * 0.05)
+    b216 = torch.randn(216, generator=g) * 0.05
+    raw = F.conv2d(x, w216, b216, padding=1)
+    off = 10 * torch.tanh(raw[:, :144]) + flow.flip(1).repeat(1, 72, 1, 1)
+    msk = torch.sigmoid(raw[:, 144:])
+    got = nchw(ops.conv3x3_tc_nhwc([nhwc_bf16(x)], w216.cuda(), b216.cuda(), act=L.ACT_DCN_HEAD, out_kind=L.TC_OUT_F32,
+                                   flow=flow.permute(0, 2, 3, 1).contiguous().cuda(), head_split=144, head_mag=10.0))
+    assert (got[:, :144] - off).abs().max().item() < 2e-3
+    assert (got[:, 144:] - msk).abs().max().item() < 1e-4
+    # pixel shuffle x4 to fp32 with LeakyReLU and x2 scale (upsample_post / dcn_3.upsample)
+    x24 = bf(torch.randn(n, 24, h, w, generator=g))
+    w64 = bf(torch.randn(64, 24, 3, 3, generator=g) * 0.1)
+    b64 = torch.randn(64, generator=g) * 0.1
+    ref4 = F.leaky_relu(F.pixel_shuffle(F.conv2d(x24, w64, b64, padding=1), 4), 0.1) * 2.0
+    got4 = nchw(ops.conv3x3_tc_nhwc([nhwc_bf16(x24)], w64.cuda(), b64.cuda(), act=1, out_kind=L.TC_OUT_SHUFFLE_F32,
+                                    shuffle_r=4, post_scale=2.0))
+    assert (got4 - ref4).abs().max().item() < 1e-4
