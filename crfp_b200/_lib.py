@@ -17,6 +17,7 @@ ACT_NONE, ACT_LRELU, ACT_RELU, ACT_DCN_HEAD, ACT_TANH256 = 0, 1, 2, 3, 4
 SRC_PLAIN, SRC_UNSHUFFLE4 = 0, 1
 OUT_NHWC, OUT_SHUFFLE = 0, 1
 TC_OUT_BF16, TC_OUT_F32, TC_OUT_SHUFFLE_F32 = 0, 1, 2
+PREC_FP32, PREC_BF16, PREC_TC3 = 0, 1, 2
 MAX_LAYERS = 72
 
 c_float_p = C.POINTER(C.c_float)
@@ -58,6 +59,18 @@ class ConvTcDesc(C.Structure):
                 ("flow", C.c_void_p), ("post_scale", C.c_float), ("head_mag", C.c_float)]
 
 
+class ConvTc3Desc(C.Structure):
+    _fields_ = [("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("nsrc", C.c_int32),
+                ("src", TcSrc * 3),
+                ("cout", C.c_int32), ("act", C.c_int32),
+                ("weight_hi", C.c_void_p), ("weight_lo", C.c_void_p), ("bias", C.c_void_p),
+                ("extra", C.c_void_p), ("w_extra", C.c_void_p),
+                ("out_kind", C.c_int32), ("shuffle_r", C.c_int32), ("ndst", C.c_int32), ("head_split", C.c_int32),
+                ("dst", TcSrc * 2),
+                ("residual", C.c_void_p), ("res_cstride", C.c_int32), ("res_coffset", C.c_int32),
+                ("flow", C.c_void_p), ("post_scale", C.c_float), ("head_mag", C.c_float)]
+
+
 class WarpDesc(C.Structure):
     _fields_ = [("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
                 ("x", C.c_void_p), ("x_cstride", C.c_int32), ("x_coffset", C.c_int32),
@@ -81,14 +94,19 @@ class Layer(C.Structure):
     _fields_ = [("w", C.c_void_p), ("b", C.c_void_p)]
 
 
+class LayerTc(C.Structure):
+    _fields_ = [("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("b", C.c_void_p), ("w_extra", C.c_void_p)]
+
+
 class DsvWeights(C.Structure):
-    _fields_ = [("mid_channels", C.c_int32), ("nlayers", C.c_int32), ("layer", Layer * MAX_LAYERS)]
+    _fields_ = [("mid_channels", C.c_int32), ("nlayers", C.c_int32), ("precision", C.c_int32), ("_pad", C.c_int32),
+                ("layer", Layer * MAX_LAYERS), ("layer_tc", LayerTc * MAX_LAYERS)]
 
 
 class LayerInfo(C.Structure):
     _fields_ = [("key", C.c_char_p), ("key2", C.c_char_p), ("kind", C.c_int32), ("nsrc", C.c_int32),
                 ("c", C.c_int32 * 3), ("mode", C.c_int32 * 3), ("cout", C.c_int32), ("ci_lo", C.c_int32),
-                ("dg", C.c_int32), ("thin", C.c_int32)]
+                ("dg", C.c_int32), ("thin", C.c_int32), ("tc", C.c_int32), ("_pad", C.c_int32)]
 
 
 class DsvShape(C.Structure):
@@ -121,13 +139,19 @@ SYMBOLS = {
     "crfp_conv3x3_tc_fwd": (C.c_int, [C.POINTER(ConvTcDesc), C.c_void_p]),
     "crfp_tc_cout_tile": (C.c_int, [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "crfp_sizeof_conv_tc_desc": (C.c_size_t, []),
+    "crfp_conv3x3_tc3_fwd": (C.c_int, [C.POINTER(ConvTc3Desc), C.c_void_p]),
+    "crfp_tc3_cout_tile": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "crfp_sizeof_conv_tc3_desc": (C.c_size_t, []),
     "crfp_conv_cin_packed": (C.c_int, [C.c_int, C.POINTER(C.c_int32)]),
     "crfp_conv_cout_packed": (C.c_int, [C.c_int]),
     "crfp_sizeof_conv_desc": (C.c_size_t, []),
     "crfp_flow_warp_fwd": (C.c_int, [C.POINTER(WarpDesc), C.c_void_p]),
+    "crfp_flow_warp_bf16_fwd": (C.c_int, [C.POINTER(WarpDesc), C.c_void_p]),
     "crfp_flow_warp_indices": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "crfp_sizeof_warp_desc": (C.c_size_t, []),
     "crfp_dcn_v2_fwd": (C.c_int, [C.POINTER(DcnDesc), C.c_void_p]),
+    "crfp_dcn_v2_tc_fwd": (C.c_int, [C.POINTER(DcnDesc), C.c_void_p]),
+    "crfp_dcn_v2_tc3_fwd": (C.c_int, [C.POINTER(DcnDesc), C.c_void_p, C.c_void_p]),
     "crfp_dcn_v2_indices": (C.c_int, [C.POINTER(DcnDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "crfp_sizeof_dcn_desc": (C.c_size_t, []),
     "crfp_resize_bilinear": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float,
@@ -167,7 +191,7 @@ def lib():
             fn = getattr(h, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        for struct, fn in ((ConvDesc, h.crfp_sizeof_conv_desc), (ConvTcDesc, h.crfp_sizeof_conv_tc_desc), (WarpDesc, h.crfp_sizeof_warp_desc),
+        for struct, fn in ((ConvDesc, h.crfp_sizeof_conv_desc), (ConvTcDesc, h.crfp_sizeof_conv_tc_desc), (ConvTc3Desc, h.crfp_sizeof_conv_tc3_desc), (WarpDesc, h.crfp_sizeof_warp_desc),
                            (DcnDesc, h.crfp_sizeof_dcn_desc), (DsvWeights, h.crfp_sizeof_dsv_weights),
                            (DsvFrameDesc, h.crfp_sizeof_dsv_frame_desc)):
             if C.sizeof(struct) != fn():
@@ -194,5 +218,5 @@ def layer_table():
         check(h.crfp_dsv_layer_info(i, C.byref(info)), "layer_info")
         out.append(dict(key=info.key.decode(), key2=info.key2.decode() if info.key2 else None, kind=info.kind,
                         c=[info.c[j] for j in range(info.nsrc)], mode=[info.mode[j] for j in range(info.nsrc)],
-                        cout=info.cout, ci_lo=info.ci_lo, dg=info.dg, thin=info.thin))
+                        cout=info.cout, ci_lo=info.ci_lo, dg=info.dg, thin=info.thin, tc=info.tc))
     return out

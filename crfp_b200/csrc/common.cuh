@@ -76,6 +76,7 @@ struct ConvParams {
   long long base_clip_stride;
   long long out_clip_stride;      // EPI_OUT_NCHW: floats between clips of the planar output
   int out_planes;                 // EPI_OUT_NCHW: number of planes written (3)
+  int out_bf16;                   // wide kernel: destinations are bf16 (strides / offsets in bf16 elements)
 };
 
 // ---- tensor-core (tcgen05) conv description: bf16 NHWC sources, channel counts multiples of 8
@@ -106,12 +107,47 @@ struct TcParams {
 void tc_cout_tile(int cout, int* nt, int* ntiles);
 int launch_conv_tc(TcParams p, cudaStream_t st);
 
+// ---- fp32-accurate tensor-core conv (3 x bf16 split): fp32 NHWC sources, channel counts multiples of 8
+struct Tc3Params {
+  int n, h, w;
+  int nsrc;
+  const float* src[3];
+  int src_c[3], src_cstride[3], src_coffset[3];
+  int kstart[3];
+  int kc_real, kc_total;
+  int cout, nt, ntiles;
+  const __nv_bfloat16* weight_hi;  // [ntiles][9][kc_total][nt][8]
+  const __nv_bfloat16* weight_lo;
+  const float* bias;               // [ntiles*nt]
+  const float* extra;              // optional NHWC 2-channel fp32 source convolved in the epilogue (flow)
+  const float* w_extra;            // fp32 [9][2][ntiles*nt]
+  const float* fg;                 // optional regional mask (1,h,w) per clip multiplied into the sources
+  long long fg_clip_stride;
+  int act;
+  int out_kind, shuffle_r;
+  int ndst;
+  void* dst[2];
+  int dst_c[2], dst_cstride[2], dst_coffset[2];
+  const float* residual;
+  int res_cstride, res_coffset;
+  const float* flow;
+  int head_split;
+  float head_mag, post_scale;
+  int rows_per_cta;
+};
+int tc3_cout_tile(int cout, int kc_real, int* nt, int* ntiles);
+int launch_conv_tc3(Tc3Params p, cudaStream_t st);
+
 int conv_params_from_desc(const crfp_conv_desc* d, ConvParams* p);
 int launch_conv_wide(const ConvParams& p, cudaStream_t st);
 int launch_conv_thin(const ConvParams& p, cudaStream_t st);
 int launch_conv(const ConvParams& p, cudaStream_t st);  // dispatch on cout
 int launch_flow_warp(const crfp_warp_desc& d, cudaStream_t st);
 int launch_dcn(const crfp_dcn_desc& d, cudaStream_t st);
+int launch_dcn_tc(const crfp_dcn_desc& d, cudaStream_t st);
+int launch_dcn_tc3(const crfp_dcn_desc& d, const void* w_lo, cudaStream_t st);
+int launch_flow_warp_bf16(const crfp_warp_desc& d, cudaStream_t st);
+int launch_flow_up2_dual(int n, int h, int w, const float* flow, float* out_f32, void* out_bf8, cudaStream_t st);
 
 // ---- device helpers
 __device__ __forceinline__ float lrelu01(float v) { return v > 0.f ? v : 0.1f * v; }

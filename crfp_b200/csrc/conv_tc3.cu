@@ -1,0 +1,367 @@
+// fp32-accurate tensor-core 3x3 convolution: fp32 NHWC activations in HBM, 3 x bf16 split products on tcgen05.
+//
+// Every fp32 operand is split as x = hi + lo with hi = bf16(x), lo = bf16(x - hi) (16 mantissa bits kept) and the
+// contraction is evaluated as A_hi*W_hi + A_lo*W_hi + A_hi*W_lo with fp32 accumulation in TMEM (the dropped
+// A_lo*W_lo term is ~2^-18 relative).  This keeps the <= 1e-3 fp32 parity bar of BASELINE.json (measured ~1e-4 end
+// to end) while the dense L1 contractions of CRFP (/root/reference/model/CRFP.py:303-317, 433-552, 154-193) run on
+// the 5th-gen tensor cores; MMA work triples but these layers are HBM/latency bound, not MMA bound.
+//
+// Structure is that of conv_tc.cu (128-pixel row tiles, 3x3 taps as shifted descriptor start addresses into a
+// ring of staged rows in the K-major no-swizzle UMMA layout) plus a conversion stage: each input row is fetched
+// once with cp.async into an fp32 staging buffer, then split into the hi / lo bf16 rings by all threads while
+// the previous row's MMAs and epilogue are in flight.  A 2-channel fp32 "extra" source (the optical flow input of
+// dcn_block.0) is convolved on the CUDA cores in the epilogue instead of being padded into the K dimension.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace crfp {
+
+constexpr int T3M = 128;
+constexpr int T3WP = 130;
+
+__device__ __forceinline__ void tc3_stage_row(const Tc3Params& P, float4* stage, int n, int y, int x0, int tid) {
+  const bool yin = (y >= 0 && y < P.h);
+  const int kcr = P.kc_real;
+  const int items = kcr * T3WP * 2;  // 16-byte halves of 32-byte (8-channel fp32) records
+  for (int it = tid; it < items; it += 128) {
+    const int half = it & 1, rec = it >> 1;
+    const int px = rec / kcr, kc = rec - px * kcr;
+    const int x = x0 + px - 1;
+    int s = 0;
+    if (P.nsrc > 1 && kc >= P.kstart[1]) s = 1;
+    if (P.nsrc > 2 && kc >= P.kstart[2]) s = 2;
+    const bool in = yin && x >= 0 && x < P.w;
+    const float* g = P.src[s];
+    if (in) g += (((size_t)n * P.h + y) * (size_t)P.w + x) * P.src_cstride[s] + P.src_coffset[s] + (kc - P.kstart[s]) * 8 + half * 4;
+    umma::cp_async16(stage + (kc * T3WP + px) * 2 + half, g, in ? 16u : 0u);
+  }
+}
+
+__device__ __forceinline__ void split8(const float4 a, const float4 b, uint4& hi, uint4& lo) {
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * k]), h1 = __float2bfloat16_rn(v[2 * k + 1]);
+    const float r0 = v[2 * k] - __bfloat162float(h0), r1 = v[2 * k + 1] - __bfloat162float(h1);
+    h[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[k] = umma::pack_bf16(r0, r1);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// staged fp32 row -> hi / lo bf16 records of one ring slot (optionally multiplied by the regional mask fg)
+__device__ __forceinline__ void tc3_convert_row(const Tc3Params& P, const float4* stage, uint4* slot_hi, uint4* slot_lo,
+                                                int n, int y, int x0, int tid) {
+  const int recs = P.kc_real * T3WP;
+  for (int r = tid; r < recs; r += 128) {
+    float4 a = stage[2 * r], b = stage[2 * r + 1];
+    if (P.fg != nullptr) {
+      const int px = r % T3WP, x = x0 + px - 1;
+      float f = 0.f;
+      if (y >= 0 && y < P.h && x >= 0 && x < P.w) f = __ldg(P.fg + (size_t)n * P.fg_clip_stride + (size_t)y * P.w + x);
+      a.x *= f; a.y *= f; a.z *= f; a.w *= f; b.x *= f; b.y *= f; b.z *= f; b.w *= f;
+    }
+    uint4 hi, lo;
+    split8(a, b, hi, lo);
+    slot_hi[r] = hi;
+    slot_lo[r] = lo;
+  }
+}
+
+__global__ void __launch_bounds__(128) conv_tc3_kernel(const Tc3Params P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int KC = P.kc_total, NT = P.nt;
+  const int wrecs = 9 * KC * NT;          // records per weight half
+  const int slot_recs = KC * T3WP;        // records per ring slot half
+  uint4* sWh = reinterpret_cast<uint4*>(smem);
+  uint4* sWl = sWh + wrecs;
+  uint4* sAh = sWl + wrecs;               // [3 slots][KC][130]
+  uint4* sAl = sAh + 3 * slot_recs;
+  float4* sStage = reinterpret_cast<float4*>(sAl + 3 * slot_recs);   // [kc_real][130][2]
+  float* sBias = reinterpret_cast<float*>(sStage + 2 * P.kc_real * T3WP);
+  float* sWx = sBias + NT;                // extra 2-channel source weights [9][2][NT] (optional)
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int cotile = blockIdx.z % P.ntiles, n = blockIdx.z / P.ntiles;
+  const int x0 = blockIdx.x * T3M;
+  const int y_begin = blockIdx.y * P.rows_per_cta;
+  const int y_end = min(P.h, y_begin + P.rows_per_cta);
+
+  {
+    const uint4* gwh = reinterpret_cast<const uint4*>(P.weight_hi) + (size_t)cotile * wrecs;
+    const uint4* gwl = reinterpret_cast<const uint4*>(P.weight_lo) + (size_t)cotile * wrecs;
+    for (int i = tid; i < wrecs; i += 128) {
+      umma::cp_async16(sWh + i, gwh + i, 16u);
+      umma::cp_async16(sWl + i, gwl + i, 16u);
+    }
+    umma::cp_async_commit();
+    for (int i = tid; i < NT; i += 128) sBias[i] = P.bias[cotile * NT + i];
+    if (P.extra != nullptr)
+      for (int i = tid; i < 18 * NT; i += 128) sWx[i] = P.w_extra[(size_t)(i / NT) * (P.ntiles * NT) + cotile * NT + (i % NT)];
+    for (int kc = P.kc_real; kc < KC; ++kc)  // K padding chunk: zero in every slot, both halves
+      for (int i = tid; i < 3 * T3WP; i += 128) {
+        sAh[(i / T3WP) * slot_recs + kc * T3WP + (i % T3WP)] = make_uint4(0u, 0u, 0u, 0u);
+        sAl[(i / T3WP) * slot_recs + kc * T3WP + (i % T3WP)] = make_uint4(0u, 0u, 0u, 0u);
+      }
+  }
+  uint32_t ncols = 32;
+  while ((int)ncols < NT) ncols <<= 1;
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, ncols);
+  if (tid == 0) {
+    umma::mbar_init(&bar, 1);
+    umma::fence_mbar_init();
+  }
+  // prologue: rows y_begin-1 and y_begin go through the staging buffer one after the other
+  for (int r = -1; r <= 0; ++r) {
+    const int yy = y_begin + r, sl = (yy + 3) % 3;
+    tc3_stage_row(P, sStage, n, yy, x0, tid);
+    umma::cp_async_commit();
+    umma::cp_async_wait<0>();
+    __syncthreads();
+    tc3_convert_row(P, sStage, sAh + sl * slot_recs, sAl + sl * slot_recs, n, yy, x0, tid);
+    __syncthreads();
+  }
+  tc3_stage_row(P, sStage, n, y_begin + 1, x0, tid);
+  umma::cp_async_commit();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t taddr = tmem_base_s;
+  const uint32_t idesc = umma::make_idesc_bf16(T3M, NT);
+  const uint32_t aH = umma::smem_u32(sAh), aL = umma::smem_u32(sAl), wH = umma::smem_u32(sWh), wL = umma::smem_u32(sWl);
+  const uint32_t lboA = T3WP * 16, lboB = (uint32_t)NT * 16;
+  uint32_t phase = 0;
+  const int x = x0 + tid;
+  const bool xvalid = x < P.w;
+
+  for (int y = y_begin; y < y_end; ++y) {
+    umma::cp_async_wait<0>();
+    __syncthreads();  // staged row y+1 is visible to everyone; MMA(y-1) has been waited for by all threads
+    {
+      const int sl = (y + 1 + 3) % 3;
+      tc3_convert_row(P, sStage, sAh + sl * slot_recs, sAl + sl * slot_recs, n, y + 1, x0, tid);
+    }
+    umma::fence_proxy_async();
+    __syncthreads();
+    if (y + 1 < y_end) tc3_stage_row(P, sStage, n, y + 2, x0, tid);
+    umma::cp_async_commit();
+    if (tid == 0) {
+      umma::fence_after_sync();
+#pragma unroll 1
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap - ky * 3;
+        const uint32_t aoff = (uint32_t)(((y + ky - 1 + 3) % 3) * slot_recs + kx) * 16;
+        const uint32_t boff = (uint32_t)(tap * KC * NT) * 16;
+        for (int ks = 0; ks < KC / 2; ++ks) {
+          const uint32_t ao = aoff + (uint32_t)(2 * ks) * lboA, bo = boff + (uint32_t)(2 * ks) * lboB;
+          const uint64_t dah = umma::make_desc(aH + ao, lboA, 128), dal = umma::make_desc(aL + ao, lboA, 128);
+          const uint64_t dbh = umma::make_desc(wH + bo, lboB, 128), dbl = umma::make_desc(wL + bo, lboB, 128);
+          umma::mma_bf16(taddr, dah, dbh, idesc, (tap | ks) != 0 ? 1u : 0u);
+          umma::mma_bf16(taddr, dal, dbh, idesc, 1u);
+          umma::mma_bf16(taddr, dah, dbl, idesc, 1u);
+        }
+      }
+      umma::mma_commit(&bar);
+    }
+    // work that does not need the accumulator: flow at this pixel, the 2-channel extra source taps
+    const size_t pix = ((size_t)n * P.h + y) * (size_t)P.w + x;
+    float2 fl = make_float2(0.f, 0.f);
+    if (P.act == CRFP_ACT_DCN_HEAD && xvalid) fl = __ldg(reinterpret_cast<const float2*>(P.flow + pix * 2));
+    float2 ex[9];
+    if (P.extra != nullptr) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        ex[tap] = (xvalid && yy >= 0 && yy < P.h && xx >= 0 && xx < P.w)
+                      ? __ldg(reinterpret_cast<const float2*>(P.extra + (((size_t)n * P.h + yy) * (size_t)P.w + xx) * 2))
+                      : make_float2(0.f, 0.f);
+      }
+    }
+    umma::mbar_wait(&bar, phase);
+    phase ^= 1;
+    umma::fence_after_sync();
+
+    for (int c0 = 0; c0 < NT; c0 += 32) {
+      float v[32];
+      umma::tmem_ld32(taddr + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, v);
+      const int cbase = cotile * NT + c0;
+      if (!xvalid || cbase >= P.cout) continue;
+      const int nvalid = min(min(32, NT - c0), P.cout - cbase);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += sBias[c0 + i];
+      if (P.extra != nullptr) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const float4* wx0 = reinterpret_cast<const float4*>(sWx + (tap * 2) * NT + c0);
+          const float4* wx1 = reinterpret_cast<const float4*>(sWx + (tap * 2 + 1) * NT + c0);
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 a = wx0[i4], b = wx1[i4];
+            v[4 * i4 + 0] = fmaf(ex[tap].x, a.x, fmaf(ex[tap].y, b.x, v[4 * i4 + 0]));
+            v[4 * i4 + 1] = fmaf(ex[tap].x, a.y, fmaf(ex[tap].y, b.y, v[4 * i4 + 1]));
+            v[4 * i4 + 2] = fmaf(ex[tap].x, a.z, fmaf(ex[tap].y, b.z, v[4 * i4 + 2]));
+            v[4 * i4 + 3] = fmaf(ex[tap].x, a.w, fmaf(ex[tap].y, b.w, v[4 * i4 + 3]));
+          }
+        }
+      }
+      if (P.act == CRFP_ACT_LRELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = lrelu01(v[i]);
+      } else if (P.act == CRFP_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+      } else if (P.act == CRFP_ACT_DCN_HEAD) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int cc = cbase + i;
+          v[i] = (cc < P.head_split) ? P.head_mag * tanhf(v[i]) + ((cc & 1) ? fl.x : fl.y) : sigmoidf_(v[i]);
+        }
+      }
+      if (P.residual != nullptr) {
+        const float* rp = P.residual + pix * P.res_cstride + P.res_coffset + cbase;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (4 * j >= nvalid) break;
+          const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + 4 * j));
+          v[4 * j] += rv.x; v[4 * j + 1] += rv.y; v[4 * j + 2] += rv.z; v[4 * j + 3] += rv.w;
+        }
+      }
+      if (P.post_scale != 1.f) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= P.post_scale;
+      }
+      if (P.out_kind == TC_OUT_F32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int cc = cbase + 4 * j;
+          if (4 * j >= nvalid) break;
+          int seg = 0, cl = cc;
+          if (P.ndst > 1 && cc >= P.dst_c[0]) { seg = 1; cl = cc - P.dst_c[0]; }
+          float* op = reinterpret_cast<float*>(P.dst[seg]) + pix * P.dst_cstride[seg] + P.dst_coffset[seg] + cl;
+          *reinterpret_cast<float4*>(op) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      } else {  // TC_OUT_SHUFFLE_F32
+        const int r_ = P.shuffle_r, rr = r_ * r_;
+        const int Wo = P.w * r_;
+        float* ob = reinterpret_cast<float*>(P.dst[0]);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int cc = cbase + i;
+          if (i >= nvalid) break;
+          const int o = cc / rr, sub = cc - o * rr;
+          const int dy = sub / r_, dx = sub - dy * r_;
+          const size_t opix = ((size_t)n * (P.h * r_) + (y * r_ + dy)) * (size_t)Wo + (x * r_ + dx);
+          ob[opix * P.dst_cstride[0] + P.dst_coffset[0] + o] = v[i];
+        }
+      }
+    }
+    umma::fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(taddr, ncols);
+}
+
+static size_t tc3_smem_bytes(int kc_real, int kc_total, int nt, bool extra) {
+  return (size_t)(2 * 9 * kc_total * nt + 6 * kc_total * T3WP) * 16 + (size_t)kc_real * T3WP * 32 + (size_t)nt * 4 +
+         (extra ? (size_t)18 * nt * 4 : 0);
+}
+
+// cout tile for the split kernel: weights are resident twice (hi, lo), so tiles are smaller than conv_tc's
+// (also bounded by shared memory: the tile count grows until weights + rings + staging fit in 225 KB)
+int tc3_cout_tile(int cout, int kc_real, int* nt, int* ntiles) {
+  const int kc_total = (kc_real + 1) & ~1;
+  for (int tiles = (cout + 111) / 112; tiles <= cout; ++tiles) {
+    const int per = (cout + tiles - 1) / tiles;
+    int n = (per + 15) & ~15;
+    if (n < 16) n = 16;
+    if (tc3_smem_bytes(kc_real, kc_total, n, true) <= (size_t)225 * 1024) {
+      *nt = n; *ntiles = tiles;
+      return CRFP_OK;
+    }
+    if (n == 16) break;
+  }
+  return CRFP_ERR_UNSUPPORTED;
+}
+
+int launch_conv_tc3(Tc3Params p, cudaStream_t st) {
+  if (p.nsrc < 1 || p.nsrc > 3) return CRFP_ERR_BAD_SHAPE;
+  int kc = 0;
+  for (int s = 0; s < p.nsrc; ++s) {
+    if (!p.src[s]) return CRFP_ERR_NULL;
+    if (p.src_c[s] % 8 || p.src_cstride[s] % 4 || p.src_coffset[s] % 4 || ((uintptr_t)p.src[s] & 15)) return CRFP_ERR_BAD_SHAPE;
+    p.kstart[s] = kc;
+    kc += p.src_c[s] / 8;
+  }
+  p.kc_real = kc;
+  p.kc_total = (kc + 1) & ~1;
+  CRFP_TRY(tc3_cout_tile(p.cout, p.kc_real, &p.nt, &p.ntiles));
+  if (!p.weight_hi || !p.weight_lo || !p.bias || !p.dst[0]) return CRFP_ERR_NULL;
+  if (p.extra && !p.w_extra) return CRFP_ERR_NULL;
+  if (p.out_kind != TC_OUT_F32 && p.out_kind != TC_OUT_SHUFFLE_F32) return CRFP_ERR_UNSUPPORTED;
+  if (p.out_kind == TC_OUT_F32)
+    for (int s = 0; s < p.ndst; ++s)
+      if (p.dst_cstride[s] % 4 || p.dst_coffset[s] % 4 || (s == 0 && p.ndst > 1 && p.dst_c[0] % 4)) return CRFP_ERR_BAD_SHAPE;
+  if (p.residual && (p.res_cstride % 4 || p.res_coffset % 4)) return CRFP_ERR_BAD_SHAPE;
+  if (p.post_scale == 0.f) p.post_scale = 1.f;
+  const size_t smem = tc3_smem_bytes(p.kc_real, p.kc_total, p.nt, p.extra != nullptr);
+  if (smem > 227 * 1024) return CRFP_ERR_UNSUPPORTED;
+  const int ctas_per_sm = (int)((227 * 1024) / (smem + 1024)) < 1 ? 1 : (int)((227 * 1024) / (smem + 1024));
+  const int strips = ceil_div(p.w, T3M);
+  const int per_seg = strips * p.n * p.ntiles;
+  int segs = (148 * (ctas_per_sm > 4 ? 4 : ctas_per_sm)) / per_seg;
+  if (segs < 1) segs = 1;
+  if (segs > ceil_div(p.h, 4)) segs = ceil_div(p.h, 4);
+  p.rows_per_cta = ceil_div(p.h, segs);
+  segs = ceil_div(p.h, p.rows_per_cta);
+  cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
+  dim3 grid(strips, segs, p.n * p.ntiles);
+  conv_tc3_kernel<<<grid, 128, smem, st>>>(p);
+  return check_launch();
+}
+
+}  // namespace crfp
+
+using namespace crfp;
+
+extern "C" int crfp_tc3_cout_tile(int cout, int cin, int32_t* nt, int32_t* ntiles) {
+  if (!nt || !ntiles || cout <= 0 || cin <= 0 || cin % 8) return CRFP_ERR_BAD_SHAPE;
+  int a = 0, b = 0;
+  CRFP_TRY(tc3_cout_tile(cout, cin / 8, &a, &b));
+  *nt = a; *ntiles = b;
+  return CRFP_OK;
+}
+
+extern "C" int crfp_conv3x3_tc3_fwd(const crfp_conv_tc3_desc* d, crfp_stream stream) {
+  if (!d) return CRFP_ERR_NULL;
+  if (d->n < 0 || d->h <= 0 || d->w <= 0 || d->cout <= 0) return CRFP_ERR_BAD_SHAPE;
+  if ((long long)d->n * d->h * d->w == 0) return CRFP_OK;
+  if (d->ndst < 1 || d->ndst > 2 || d->nsrc < 1 || d->nsrc > 3) return CRFP_ERR_BAD_SHAPE;
+  Tc3Params p;
+  memset(&p, 0, sizeof(p));
+  p.n = d->n; p.h = d->h; p.w = d->w; p.nsrc = d->nsrc;
+  for (int s = 0; s < d->nsrc; ++s) {
+    p.src[s] = d->src[s].ptr; p.src_c[s] = d->src[s].c; p.src_cstride[s] = d->src[s].cstride;
+    p.src_coffset[s] = d->src[s].coffset;
+  }
+  p.cout = d->cout; p.act = d->act;
+  p.weight_hi = reinterpret_cast<const __nv_bfloat16*>(d->weight_hi);
+  p.weight_lo = reinterpret_cast<const __nv_bfloat16*>(d->weight_lo);
+  p.bias = d->bias;
+  p.extra = d->extra; p.w_extra = d->w_extra;
+  p.out_kind = d->out_kind; p.shuffle_r = d->shuffle_r; p.ndst = d->ndst;
+  for (int s = 0; s < d->ndst; ++s) {
+    p.dst[s] = d->dst[s].ptr; p.dst_c[s] = d->dst[s].c; p.dst_cstride[s] = d->dst[s].cstride;
+    p.dst_coffset[s] = d->dst[s].coffset;
+  }
+  p.residual = d->residual; p.res_cstride = d->res_cstride; p.res_coffset = d->res_coffset;
+  p.flow = d->flow; p.head_split = d->head_split; p.head_mag = d->head_mag; p.post_scale = d->post_scale;
+  if (d->act == CRFP_ACT_DCN_HEAD && !d->flow) return CRFP_ERR_NULL;
+  if (d->out_kind == CRFP_TC_OUT_SHUFFLE_F32 && (d->shuffle_r < 1 || d->cout % (d->shuffle_r * d->shuffle_r))) return CRFP_ERR_BAD_SHAPE;
+  return launch_conv_tc3(p, (cudaStream_t)stream);
+}
+
+extern "C" size_t crfp_sizeof_conv_tc3_desc(void) { return sizeof(crfp_conv_tc3_desc); }

@@ -150,7 +150,20 @@ __global__ void __launch_bounds__(256, 2) conv_wide_kernel(const ConvParams P) {
       int seg = 0, cl = cch;
       if (P.ndst > 1 && cch >= P.dst_c[0]) { seg = 1; cl = cch - P.dst_c[0]; }
       const bool whole = (cl + 8 <= P.dst_c[seg]) && (((P.dst_cstride[seg] | P.dst_coffset[seg]) & 3) == 0);
-      if (whole) {
+      if (P.out_bf16) {
+        const bool whole8 = (cl + 8 <= P.dst_c[seg]) && (((P.dst_cstride[seg] | P.dst_coffset[seg]) & 7) == 0);
+        __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(P.dst[seg]) + pix * P.dst_cstride[seg] + P.dst_coffset[seg] + cl;
+        if (whole8) {
+          __nv_bfloat162 o[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) o[c] = __floats2bfloat162_rn(v[2 * c], v[2 * c + 1]);
+          *reinterpret_cast<uint4*>(ob) = *reinterpret_cast<uint4*>(o);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (cch + c < P.cout && cl + c < P.dst_c[seg]) ob[c] = __float2bfloat16(v[c]);
+        }
+      } else if (whole) {
         float* op = P.dst[seg] + pix * P.dst_cstride[seg] + P.dst_coffset[seg] + cl;
         *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<float4*>(op + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -174,7 +187,10 @@ __global__ void __launch_bounds__(256, 2) conv_wide_kernel(const ConvParams P) {
         const int o = cc / rr, sub = cc - o * rr;
         const int dy = sub / r_, dx = sub - dy * r_;
         const size_t opix = ((size_t)n * Ho + (y * r_ + dy)) * (size_t)Wo + (x * r_ + dx);
-        P.dst[0][opix * P.dst_cstride[0] + P.dst_coffset[0] + o] = v[c];
+        if (P.out_bf16)
+          reinterpret_cast<__nv_bfloat16*>(P.dst[0])[opix * P.dst_cstride[0] + P.dst_coffset[0] + o] = __float2bfloat16(v[c]);
+        else
+          P.dst[0][opix * P.dst_cstride[0] + P.dst_coffset[0] + o] = v[c];
       }
     }
   }

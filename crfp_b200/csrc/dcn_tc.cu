@@ -1,0 +1,357 @@
+// DCNv2 align kernel on the tensor cores (bf16 storage): the modulated deformable im2col is gathered straight into
+// the UMMA A-operand tile in shared memory and contracted with tcgen05.mma — `columns` never exists in HBM.
+//
+// Reference: dcn_v2.DCNv2.forward (/root/reference/model/CRFP.py:318-320,350); SURVEY.md 8(a) a7.
+//   CTA = 16x8 output pixels (M = 128), 256 threads.
+//   gather   every (pixel, 8-wide K chunk) record = 2 (group,tap) samples x 4 channels: offsets/mask read as one
+//            float4 + one float2 (fp32, exact sampling positions), 4 bilinear corners x 8 B (4 bf16) per sample,
+//            fp32 lerp x mask -> 8 bf16 -> one 16-byte st.shared into A[kc][pixel] (K-major, no swizzle,
+//            LBO = 129*16 B so that consecutive-kc lanes hit distinct banks, SBO = 128 B)
+//   contract 18 x tcgen05.mma M128 N32 K16, B = W[32][288] bf16 resident in smem, fp32 accumulators in TMEM
+//   epilogue TMEM -> registers (+bias) -> bf16 NHWC, 64 B per pixel.
+// One CTA per SM on purpose: the gather's working set (tile + reach of the offsets) must stay in L1.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace crfp {
+
+constexpr int DTW = 16, DTH = 8;    // tile
+constexpr int DKC = 36;             // 288 / 8 K chunks
+constexpr int DAP = 129;            // records per kc row of A (128 + 1 pad)
+
+struct DcnTcParams {
+  int n, h, w;
+  const __nv_bfloat16* x; int x_cstride, x_coffset;       // bf16 NHWC, 32 channels used
+  const float* offset; int off_cstride, off_coffset;      // fp32: (dy,dx) per (g,t)
+  const float* mask; int mask_cstride, mask_coffset;      // fp32 per (g,t)
+  const __nv_bfloat16* weight;                            // [36][32][8] bf16, k = (g*9+t)*4+c
+  const float* bias;                                      // [32]
+  __nv_bfloat16* out; int out_cstride, out_coffset;
+};
+
+__device__ __forceinline__ void dcn_corner_w(float py, float px, int H, int W, int& y0, int& x0, float& w00, float& w01,
+                                             float& w10, float& w11) {
+  const float fy = floorf(py), fx = floorf(px);
+  y0 = (int)fy; x0 = (int)fx;
+  const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
+  const bool inside = (py > -1.f) && (py < (float)H) && (px > -1.f) && (px < (float)W);
+  const bool vy0 = inside && y0 >= 0, vy1 = inside && (y0 + 1 <= H - 1);
+  const bool vx0 = x0 >= 0, vx1 = (x0 + 1 <= W - 1);
+  w00 = (vy0 && vx0) ? hy * hx : 0.f;
+  w01 = (vy0 && vx1) ? hy * lx : 0.f;
+  w10 = (vy1 && vx0) ? ly * hx : 0.f;
+  w11 = (vy1 && vx1) ? ly * lx : 0.f;
+}
+
+__device__ __forceinline__ void acc4_bf16(float* a, const __nv_bfloat16* p, float wgt) {
+  const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+  const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+  a[0] += wgt * lo.x; a[1] += wgt * lo.y; a[2] += wgt * hi.x; a[3] += wgt * hi.y;
+}
+
+__device__ __forceinline__ void dcn_sample_bf16(const DcnTcParams& P, const __nv_bfloat16* img, int gt, int y, int x,
+                                                float dy, float dx, float m, float* v) {
+  const int g = gt / 9, t = gt - g * 9;
+  const int i = t / 3, j = t - i * 3;
+  int y0, x0;
+  float w00, w01, w10, w11;
+  dcn_corner_w((float)(y - 1 + i) + dy, (float)(x - 1 + j) + dx, P.h, P.w, y0, x0, w00, w01, w10, w11);
+  v[0] = v[1] = v[2] = v[3] = 0.f;
+  const __nv_bfloat16* p = img + ((long long)y0 * P.w + x0) * P.x_cstride + g * 4;
+  if (w00 != 0.f) acc4_bf16(v, p, w00);
+  if (w01 != 0.f) acc4_bf16(v, p + P.x_cstride, w01);
+  if (w10 != 0.f) acc4_bf16(v, p + (long long)P.w * P.x_cstride, w10);
+  if (w11 != 0.f) acc4_bf16(v, p + (long long)P.w * P.x_cstride + P.x_cstride, w11);
+  v[0] *= m; v[1] *= m; v[2] *= m; v[3] *= m;
+}
+
+__global__ void __launch_bounds__(256, 1) dcn_tc_kernel(const DcnTcParams P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[32];
+  uint4* sB = reinterpret_cast<uint4*>(smem);   // [36][32] records
+  uint4* sA = sB + DKC * 32;                     // [36][129] records
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tiles_x = (P.w + DTW - 1) / DTW;
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int n = blockIdx.y;
+  const int x0t = tx * DTW, y0t = ty * DTH;
+
+  for (int i = tid; i < DKC * 32; i += 256) umma::cp_async16(sB + i, reinterpret_cast<const uint4*>(P.weight) + i, 16u);
+  umma::cp_async_commit();
+  if (tid < 32) s_bias[tid] = P.bias[tid];
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 32);
+  if (tid == 0) {
+    umma::mbar_init(&bar, 1);
+    umma::fence_mbar_init();
+  }
+
+  // ---- gather: 128 px x 36 chunks = 4608 records, 18 per thread; consecutive lanes = consecutive kc of one pixel
+  const __nv_bfloat16* img = P.x + (size_t)n * P.h * P.w * P.x_cstride + P.x_coffset;
+#pragma unroll 2
+  for (int idx = tid; idx < 128 * DKC; idx += 256) {
+    const int m = idx / DKC, kc = idx - m * DKC;
+    const int y = y0t + (m >> 4), x = x0t + (m & 15);
+    uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+    if (y < P.h && x < P.w) {
+      const size_t pix = ((size_t)n * P.h + y) * (size_t)P.w + x;
+      const float4 off = __ldg(reinterpret_cast<const float4*>(P.offset + pix * P.off_cstride + P.off_coffset + kc * 4));
+      const float2 mk = __ldg(reinterpret_cast<const float2*>(P.mask + pix * P.mask_cstride + P.mask_coffset + kc * 2));
+      float v0[4], v1[4];
+      dcn_sample_bf16(P, img, 2 * kc, y, x, off.x, off.y, mk.x, v0);
+      dcn_sample_bf16(P, img, 2 * kc + 1, y, x, off.z, off.w, mk.y, v1);
+      rec.x = umma::pack_bf16(v0[0], v0[1]);
+      rec.y = umma::pack_bf16(v0[2], v0[3]);
+      rec.z = umma::pack_bf16(v1[0], v1[1]);
+      rec.w = umma::pack_bf16(v1[2], v1[3]);
+    }
+    sA[kc * DAP + m] = rec;
+  }
+  umma::cp_async_wait<0>();
+  umma::fence_proxy_async();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t taddr = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = umma::make_idesc_bf16(128, 32);
+    const uint32_t a0 = umma::smem_u32(sA), b0 = umma::smem_u32(sB);
+#pragma unroll 1
+    for (int ks = 0; ks < DKC / 2; ++ks) {
+      const uint64_t da = umma::make_desc(a0 + (uint32_t)(2 * ks) * (DAP * 16), DAP * 16, 128);
+      const uint64_t db = umma::make_desc(b0 + (uint32_t)(2 * ks) * (32 * 16), 32 * 16, 128);
+      umma::mma_bf16(taddr, da, db, idesc, ks != 0 ? 1u : 0u);
+    }
+    umma::mma_commit(&bar);
+  }
+  if (warp < 4) {
+    umma::mbar_wait(&bar, 0);
+    umma::fence_after_sync();
+    float v[32];
+    umma::tmem_ld32(taddr + ((uint32_t)(32 * warp) << 16), v);
+    const int m = tid;  // TMEM lane = pixel index in the tile
+    const int y = y0t + (m >> 4), x = x0t + (m & 15);
+    if (y < P.h && x < P.w) {
+      const size_t pix = ((size_t)n * P.h + y) * (size_t)P.w + x;
+      __nv_bfloat16* op = P.out + pix * P.out_cstride + P.out_coffset;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = umma::pack_bf16(v[8 * j + 0] + s_bias[8 * j + 0], v[8 * j + 1] + s_bias[8 * j + 1]);
+        o.y = umma::pack_bf16(v[8 * j + 2] + s_bias[8 * j + 2], v[8 * j + 3] + s_bias[8 * j + 3]);
+        o.z = umma::pack_bf16(v[8 * j + 4] + s_bias[8 * j + 4], v[8 * j + 5] + s_bias[8 * j + 5]);
+        o.w = umma::pack_bf16(v[8 * j + 6] + s_bias[8 * j + 6], v[8 * j + 7] + s_bias[8 * j + 7]);
+        *reinterpret_cast<uint4*>(op + 8 * j) = o;
+      }
+    }
+    umma::fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(taddr, 32);
+}
+
+// ------------------------------------------------------------------------------------------------ fp32-accurate variant
+// fp32 NHWC input / output; the modulated columns are split hi/lo into bf16 and contracted as
+// A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (fp32 TMEM accumulation).  K = 288 is processed in two halves of 144 so that
+// the hi+lo A tiles (2 x 37 KB) + hi+lo weights (37 KB) leave >= 110 KB of L1 for the gather's working set.
+constexpr int D3KH = 18;  // K chunks per half
+
+struct DcnTc3Params {
+  int n, h, w;
+  const float* x; int x_cstride, x_coffset;
+  const float* offset; int off_cstride, off_coffset;
+  const float* mask; int mask_cstride, mask_coffset;
+  const __nv_bfloat16* w_hi;  // [36][32][8]
+  const __nv_bfloat16* w_lo;
+  const float* bias;
+  float* out; int out_cstride, out_coffset;
+};
+
+__device__ __forceinline__ void dcn_sample_f32(const DcnTc3Params& P, const float* img, int gt, int y, int x, float dy,
+                                               float dx, float m, float* v) {
+  const int g = gt / 9, t = gt - g * 9;
+  const int i = t / 3, j = t - i * 3;
+  int y0, x0;
+  float w00, w01, w10, w11;
+  dcn_corner_w((float)(y - 1 + i) + dy, (float)(x - 1 + j) + dx, P.h, P.w, y0, x0, w00, w01, w10, w11);
+  v[0] = v[1] = v[2] = v[3] = 0.f;
+  const float* p = img + ((long long)y0 * P.w + x0) * P.x_cstride + g * 4;
+#define CRFP_C4(ptr, wgt)                                                  \
+  if ((wgt) != 0.f) {                                                      \
+    const float4 t4 = __ldg(reinterpret_cast<const float4*>(ptr));         \
+    v[0] += (wgt) * t4.x; v[1] += (wgt) * t4.y; v[2] += (wgt) * t4.z; v[3] += (wgt) * t4.w; \
+  }
+  CRFP_C4(p, w00)
+  CRFP_C4(p + P.x_cstride, w01)
+  CRFP_C4(p + (long long)P.w * P.x_cstride, w10)
+  CRFP_C4(p + (long long)P.w * P.x_cstride + P.x_cstride, w11)
+#undef CRFP_C4
+  v[0] *= m; v[1] *= m; v[2] *= m; v[3] *= m;
+}
+
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
+  hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  lo = umma::pack_bf16(a - __bfloat162float(h0), b - __bfloat162float(h1));
+}
+
+__global__ void __launch_bounds__(256, 1) dcn_tc3_kernel(const DcnTc3Params P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[32];
+  uint4* sBh = reinterpret_cast<uint4*>(smem);   // [36][32]
+  uint4* sBl = sBh + DKC * 32;
+  uint4* sAh = sBl + DKC * 32;                   // [18][129]
+  uint4* sAl = sAh + D3KH * DAP;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tiles_x = (P.w + DTW - 1) / DTW;
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int n = blockIdx.y;
+  const int x0t = tx * DTW, y0t = ty * DTH;
+
+  for (int i = tid; i < DKC * 32; i += 256) {
+    umma::cp_async16(sBh + i, reinterpret_cast<const uint4*>(P.w_hi) + i, 16u);
+    umma::cp_async16(sBl + i, reinterpret_cast<const uint4*>(P.w_lo) + i, 16u);
+  }
+  umma::cp_async_commit();
+  if (tid < 32) s_bias[tid] = P.bias[tid];
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 32);
+  if (tid == 0) {
+    umma::mbar_init(&bar, 1);
+    umma::fence_mbar_init();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t taddr = tmem_base_s;
+  const uint32_t idesc = umma::make_idesc_bf16(128, 32);
+  const float* img = P.x + (size_t)n * P.h * P.w * P.x_cstride + P.x_coffset;
+
+  for (int half = 0; half < 2; ++half) {
+    // ---- gather this half's 18 K chunks for the 128 pixels: 2304 records, 9 per thread
+#pragma unroll 2
+    for (int idx = tid; idx < 128 * D3KH; idx += 256) {
+      const int m = idx / D3KH, kl = idx - m * D3KH, kc = half * D3KH + kl;
+      const int y = y0t + (m >> 4), x = x0t + (m & 15);
+      uint4 rh = make_uint4(0u, 0u, 0u, 0u), rl = rh;
+      if (y < P.h && x < P.w) {
+        const size_t pix = ((size_t)n * P.h + y) * (size_t)P.w + x;
+        const float4 off = __ldg(reinterpret_cast<const float4*>(P.offset + pix * P.off_cstride + P.off_coffset + kc * 4));
+        const float2 mk = __ldg(reinterpret_cast<const float2*>(P.mask + pix * P.mask_cstride + P.mask_coffset + kc * 2));
+        float v0[4], v1[4];
+        dcn_sample_f32(P, img, 2 * kc, y, x, off.x, off.y, mk.x, v0);
+        dcn_sample_f32(P, img, 2 * kc + 1, y, x, off.z, off.w, mk.y, v1);
+        split_pair(v0[0], v0[1], rh.x, rl.x);
+        split_pair(v0[2], v0[3], rh.y, rl.y);
+        split_pair(v1[0], v1[1], rh.z, rl.z);
+        split_pair(v1[2], v1[3], rh.w, rl.w);
+      }
+      sAh[kl * DAP + m] = rh;
+      sAl[kl * DAP + m] = rl;
+    }
+    if (half == 0) umma::cp_async_wait<0>();
+    umma::fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      umma::fence_after_sync();
+      const uint32_t ah = umma::smem_u32(sAh), al = umma::smem_u32(sAl);
+      const uint32_t bh = umma::smem_u32(sBh) + (uint32_t)(half * D3KH) * (32 * 16);
+      const uint32_t bl = umma::smem_u32(sBl) + (uint32_t)(half * D3KH) * (32 * 16);
+#pragma unroll 1
+      for (int ks = 0; ks < D3KH / 2; ++ks) {
+        const uint32_t ao = (uint32_t)(2 * ks) * (DAP * 16), bo = (uint32_t)(2 * ks) * (32 * 16);
+        const uint64_t dah = umma::make_desc(ah + ao, DAP * 16, 128), dal = umma::make_desc(al + ao, DAP * 16, 128);
+        const uint64_t dbh = umma::make_desc(bh + bo, 32 * 16, 128), dbl = umma::make_desc(bl + bo, 32 * 16, 128);
+        umma::mma_bf16(taddr, dah, dbh, idesc, (half | ks) != 0 ? 1u : 0u);
+        umma::mma_bf16(taddr, dal, dbh, idesc, 1u);
+        umma::mma_bf16(taddr, dah, dbl, idesc, 1u);
+      }
+      umma::mma_commit(&bar);
+    }
+    // the A tiles are overwritten by the next half: everybody waits for this half's MMAs
+    umma::mbar_wait(&bar, (uint32_t)half);
+    umma::fence_after_sync();
+  }
+  if (warp < 4) {
+    float v[32];
+    umma::tmem_ld32(taddr + ((uint32_t)(32 * warp) << 16), v);
+    const int m = tid;
+    const int y = y0t + (m >> 4), x = x0t + (m & 15);
+    if (y < P.h && x < P.w) {
+      const size_t pix = ((size_t)n * P.h + y) * (size_t)P.w + x;
+      float* op = P.out + pix * P.out_cstride + P.out_coffset;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(op + 4 * j) = make_float4(v[4 * j] + s_bias[4 * j], v[4 * j + 1] + s_bias[4 * j + 1],
+                                                             v[4 * j + 2] + s_bias[4 * j + 2], v[4 * j + 3] + s_bias[4 * j + 3]);
+    }
+    umma::fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(taddr, 32);
+}
+
+int launch_dcn_tc3(const crfp_dcn_desc& d, const void* w_lo, cudaStream_t st) {
+  if ((long long)d.n * d.h * d.w == 0) return CRFP_OK;
+  if (!(d.c == 32 && d.dg == 8 && d.cout == 32 && !d.shared_taps)) return CRFP_ERR_UNSUPPORTED;
+  if (!w_lo) return CRFP_ERR_NULL;
+  if ((d.x_cstride | d.x_coffset | d.out_cstride | d.out_coffset) & 3) return CRFP_ERR_BAD_SHAPE;
+  if (((d.off_cstride | d.off_coffset) & 3) || ((d.mask_cstride | d.mask_coffset) & 1)) return CRFP_ERR_BAD_SHAPE;
+  DcnTc3Params p;
+  p.n = d.n; p.h = d.h; p.w = d.w;
+  p.x = d.x; p.x_cstride = d.x_cstride; p.x_coffset = d.x_coffset;
+  p.offset = d.offset; p.off_cstride = d.off_cstride; p.off_coffset = d.off_coffset;
+  p.mask = d.mask; p.mask_cstride = d.mask_cstride; p.mask_coffset = d.mask_coffset;
+  p.w_hi = reinterpret_cast<const __nv_bfloat16*>(d.weight); p.w_lo = reinterpret_cast<const __nv_bfloat16*>(w_lo);
+  p.bias = d.bias;
+  p.out = d.out; p.out_cstride = d.out_cstride; p.out_coffset = d.out_coffset;
+  const size_t smem = (size_t)(2 * DKC * 32 + 2 * D3KH * DAP) * 16;  // 36864 + 74304 = 111168 B
+  cudaError_t e = cudaFuncSetAttribute(dcn_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
+  dim3 grid(ceil_div(d.w, DTW) * ceil_div(d.h, DTH), d.n);
+  dcn_tc3_kernel<<<grid, 256, smem, st>>>(p);
+  return check_launch();
+}
+
+int launch_dcn_tc(const crfp_dcn_desc& d, cudaStream_t st) {
+  if ((long long)d.n * d.h * d.w == 0) return CRFP_OK;
+  if (!(d.c == 32 && d.dg == 8 && d.cout == 32 && !d.shared_taps)) return CRFP_ERR_UNSUPPORTED;
+  if ((d.x_cstride | d.x_coffset | d.out_cstride | d.out_coffset) & 7) return CRFP_ERR_BAD_SHAPE;
+  if (((d.off_cstride | d.off_coffset) & 3) || ((d.mask_cstride | d.mask_coffset) & 1)) return CRFP_ERR_BAD_SHAPE;
+  DcnTcParams p;
+  p.n = d.n; p.h = d.h; p.w = d.w;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(d.x); p.x_cstride = d.x_cstride; p.x_coffset = d.x_coffset;
+  p.offset = d.offset; p.off_cstride = d.off_cstride; p.off_coffset = d.off_coffset;
+  p.mask = d.mask; p.mask_cstride = d.mask_cstride; p.mask_coffset = d.mask_coffset;
+  p.weight = reinterpret_cast<const __nv_bfloat16*>(d.weight); p.bias = d.bias;
+  p.out = reinterpret_cast<__nv_bfloat16*>(d.out); p.out_cstride = d.out_cstride; p.out_coffset = d.out_coffset;
+  const size_t smem = (size_t)(DKC * 32 + DKC * DAP) * 16;  // 18432 + 74304 = 92736 B
+  cudaError_t e = cudaFuncSetAttribute(dcn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
+  dim3 grid(ceil_div(d.w, DTW) * ceil_div(d.h, DTH), d.n);
+  dcn_tc_kernel<<<grid, 256, smem, st>>>(p);
+  return check_launch();
+}
+
+}  // namespace crfp
+
+using namespace crfp;
+
+// bf16 variant of crfp_dcn_v2_fwd: x / out are bf16 NHWC, weight bf16 [36][32][8] (k = (g*9+t)*4+c), offset / mask /
+// bias fp32.  Same descriptor struct; pointers are reinterpreted.
+// fp32-accurate tensor-core variant: x / out fp32 NHWC; d->weight = hi part, weight_lo = lo part of the bf16 split of
+// the [36][32][8] packed weight (k = (g*9+t)*4+c).
+extern "C" int crfp_dcn_v2_tc3_fwd(const crfp_dcn_desc* d, const void* weight_lo, crfp_stream stream) {
+  if (!d || !d->x || !d->offset || !d->mask || !d->weight || !d->bias || !d->out || !weight_lo) return CRFP_ERR_NULL;
+  if (d->n < 0 || d->h <= 0 || d->w <= 0) return CRFP_ERR_BAD_SHAPE;
+  return launch_dcn_tc3(*d, weight_lo, (cudaStream_t)stream);
+}
+
+extern "C" int crfp_dcn_v2_tc_fwd(const crfp_dcn_desc* d, crfp_stream stream) {
+  if (!d || !d->x || !d->offset || !d->mask || !d->weight || !d->bias || !d->out) return CRFP_ERR_NULL;
+  if (d->n < 0 || d->h <= 0 || d->w <= 0) return CRFP_ERR_BAD_SHAPE;
+  return launch_dcn_tc(*d, (cudaStream_t)stream);
+}

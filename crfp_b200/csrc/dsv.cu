@@ -74,9 +74,32 @@ static const crfp_layer_info kLayers[L_COUNT] = {
     CONV1("conv_last", 4, 3),
 };
 
+// tensor-core packing kind per layer: 0 none, 1 conv_tc (pack_conv_tc over the same source split), 2 dcn_tc
+static int layer_tc_kind(int li) {
+  switch (li) {
+    case L_DCN0_B0: case L_DCN0_B2: case L_DCN0_HEADS:
+    case L_DCN1_B0: case L_DCN1_B2: case L_DCN1_FUSE: case L_DCN1_HEADS:
+    case L_DCN2_B0: case L_DCN2_B2: case L_DCN2_FUSE: case L_DCN2_HEADS:
+    case L_RES0_IN: case L_RES0_IN_FIRST: case L_RES0_C1: case L_RES0_C2:
+    case L_RES1_IN: case L_RES1_IN_FIRST: case L_RES1_C1: case L_RES1_C2:
+    case L_RES2_IN: case L_RES2_IN_FIRST: case L_RES2_C1: case L_RES2_C2:
+    case L_UPSAMPLE_POST: case L_DCN3_UP:
+      return 1;
+    case L_DCN0_DCN: case L_DCN1_DCN: case L_DCN2_DCN:
+      return 2;
+    case L_FNET_E1_2: case L_FNET_E2_0: case L_FNET_E2_2: case L_FNET_E3_0: case L_FNET_D3_2: case L_FNET_F0:
+    case L_ENC_LR_2: case L_UPSAMPLE:
+      return 3;
+    default:
+      return 0;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ conv builder
 struct CB {
   ConvParams p;
+  const crfp_dsv_weights* W_ = nullptr;
+  int li_ = -1;
   CB(int n, int h, int w) {
     memset(&p, 0, sizeof(p));
     p.n = n; p.h = h; p.w = w;
@@ -89,7 +112,48 @@ struct CB {
   }
   CB& layer(const crfp_dsv_weights* w, int li) {
     p.weight = w->layer[li].w; p.bias = w->layer[li].b; p.cout = kLayers[li].cout;
+    W_ = w; li_ = li;
     return *this;
+  }
+  // TC3 precision: the same layer on the tensor cores (3 x bf16 split) when it is eligible
+  bool tc3_eligible() const {
+    if (!W_ || li_ < 0 || W_->precision != CRFP_PREC_TC3 || !W_->layer_tc[li_].w_hi || !W_->layer_tc[li_].w_lo) return false;
+    if (p.epi != EPI_STD || p.out_bf16 || p.cout <= 4) return false;
+    int kc = 0;
+    for (int s = 0; s < p.nsrc; ++s) {
+      if (p.src_mode[s] != CRFP_SRC_PLAIN) return false;
+      if (p.src_c[s] % 8 == 0) { kc += p.src_c[s] / 8; continue; }
+      if (p.src_c[s] == 2 && s == p.nsrc - 1 && p.src_cstride[s] == 2 && p.src_coffset[s] == 0 && W_->layer_tc[li_].w_extra) continue;
+      return false;
+    }
+    return kc >= 1 && kc <= 8;
+  }
+  int run_tc3(cudaStream_t st) const {
+    Tc3Params t;
+    memset(&t, 0, sizeof(t));
+    t.n = p.n; t.h = p.h; t.w = p.w;
+    for (int s = 0; s < p.nsrc; ++s) {
+      if (p.src_c[s] % 8 == 0) {
+        const int k = t.nsrc++;
+        t.src[k] = p.src[s]; t.src_c[k] = p.src_c[s]; t.src_cstride[k] = p.src_cstride[s]; t.src_coffset[k] = p.src_coffset[s];
+      } else {
+        t.extra = p.src[s];
+        t.w_extra = W_->layer_tc[li_].w_extra;
+      }
+    }
+    t.cout = p.cout; t.act = p.act;
+    t.weight_hi = reinterpret_cast<const __nv_bfloat16*>(W_->layer_tc[li_].w_hi);
+    t.weight_lo = reinterpret_cast<const __nv_bfloat16*>(W_->layer_tc[li_].w_lo);
+    t.bias = W_->layer_tc[li_].b;
+    t.fg = p.fg; t.fg_clip_stride = p.fg_clip_stride;
+    t.out_kind = (p.out_mode == CRFP_OUT_SHUFFLE) ? TC_OUT_SHUFFLE_F32 : TC_OUT_F32;
+    t.shuffle_r = p.shuffle_r; t.ndst = p.ndst;
+    for (int s = 0; s < p.ndst; ++s) {
+      t.dst[s] = p.dst[s]; t.dst_c[s] = p.dst_c[s]; t.dst_cstride[s] = p.dst_cstride[s]; t.dst_coffset[s] = p.dst_coffset[s];
+    }
+    t.residual = p.residual; t.res_cstride = p.res_cstride; t.res_coffset = p.res_coffset;
+    t.flow = p.flow; t.head_split = p.head_split; t.head_mag = p.head_mag; t.post_scale = p.post_scale;
+    return launch_conv_tc3(t, st);
   }
   CB& act(int a) { p.act = a; return *this; }
   CB& dst(float* ptr, int c, int cs, int co = 0) {
@@ -110,9 +174,46 @@ struct CB {
     for (int s = p.nsrc; s < 4; ++s) p.qstart[s] = q;
     p.cin_packed = (q * 4 + 7) & ~7;
     p.cout_packed = crfp_conv_cout_packed(p.cout);
+    if (tc3_eligible()) return run_tc3(st);
     if (!p.weight || !p.bias) return CRFP_ERR_NULL;
     return launch_conv(p, st);
   }
+};
+
+// tensor-core conv builder (bf16 sources)
+struct TB {
+  TcParams p;
+  TB(int n, int h, int w) {
+    memset(&p, 0, sizeof(p));
+    p.n = n; p.h = h; p.w = w;
+    p.out_kind = TC_OUT_BF16; p.post_scale = 1.f;
+  }
+  TB& src(const void* ptr, int c, int cs, int co = 0) {
+    const int s = p.nsrc++;
+    p.src[s] = reinterpret_cast<const __nv_bfloat16*>(ptr); p.src_c[s] = c; p.src_cstride[s] = cs; p.src_coffset[s] = co;
+    return *this;
+  }
+  TB& layer(const crfp_dsv_weights* w, int li) {
+    p.weight = reinterpret_cast<const __nv_bfloat16*>(w->layer_tc[li].w_hi); p.bias = w->layer_tc[li].b;
+    p.cout = kLayers[li].cout;
+    return *this;
+  }
+  TB& act(int a) { p.act = a; return *this; }
+  TB& dst(void* ptr, int c, int cs, int co = 0) {
+    const int s = p.ndst++;
+    p.dst[s] = ptr; p.dst_c[s] = c; p.dst_cstride[s] = cs; p.dst_coffset[s] = co;
+    return *this;
+  }
+  TB& f32() { p.out_kind = TC_OUT_F32; return *this; }
+  TB& shuffle_f32(int r) { p.out_kind = TC_OUT_SHUFFLE_F32; p.shuffle_r = r; return *this; }
+  TB& res(const void* ptr, int cs, int co = 0) {
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(ptr); p.res_cstride = cs; p.res_coffset = co; return *this;
+  }
+  TB& scale(float s) { p.post_scale = s; return *this; }
+  TB& head(const float* flow, int split, float mag) {
+    p.act = CRFP_ACT_DCN_HEAD; p.flow = flow; p.head_split = split; p.head_mag = mag; return *this;
+  }
+  int run(cudaStream_t st) { return launch_conv_tc(p, st); }
 };
 
 // ------------------------------------------------------------------------------------------------ small kernels
@@ -239,7 +340,7 @@ static int run_fnet(const crfp_dsv_weights* W, int cnt, int h, int w, const floa
 
 struct FrameWs {
   // L1 (2h x 2w)
-  float *P, *P_w, *cur[3], *t1, *t2, *offf[2], *A, *r0, *r1, *prop, *flow_l1, *om, *fg_l1;
+  float *P, *P_w, *cur[3], *t1, *t2, *offf[2], *A, *r0, *r1, *prop, *flow_l1, *flow8, *om, *fg_l1;
   // HR (8h x 8w)
   float *S0_w, *q, *po, *h1, *h2, *h3, *om3, *A3, *g0, *g1, *S_pre, *hr_in, *e1, *x_hr, *flow_hr;
   // dense per-frame copies of strided clip slices
@@ -257,6 +358,7 @@ static size_t carve_frame(const crfp_dsv_shape* s, void* ws, FrameWs* f) {
   f->A = c.take(l1 * 32); f->r0 = c.take(l1 * 32); f->r1 = c.take(l1 * 32);
   f->prop = c.take(l1 * 24);
   f->flow_l1 = c.take(l1 * 2);
+  f->flow8 = c.take(l1 * 4);
   f->om = c.take(l1 * 216);
   f->fg_l1 = c.take(l1);
   f->S0_w = c.take(hr * 4); f->q = c.take(hr * 4); f->po = c.take(hr * 4);
@@ -270,6 +372,112 @@ static size_t carve_frame(const crfp_dsv_shape* s, void* ws, FrameWs* f) {
   return c.off;
 }
 
+
+// L1 stage in bf16 mode: every 2h x 2w layer on tcgen05 (conv_tc / dcn_tc), bf16 storage, fp32 accumulation.
+// Produces the same hand-off to the HR stage as the fp32 path: q, po (fp32 HR), S0_w, flow_hr, new state_l1 (bf16).
+static int frame_l1_bf16(const crfp_dsv_frame_desc* d, const crfp_dsv_weights* W, const FrameWs& f, const float* x_lr,
+                         cudaStream_t st) {
+  const crfp_dsv_shape* s = &d->shape;
+  const int n = s->n, h = s->h, w = s->w;
+  const int h1 = 2 * h, w1 = 2 * w, H = 8 * h, Wd = 8 * w;
+  const size_t hw = (size_t)h * w;
+  for (int li = 0; li < L_COUNT; ++li)
+    if ((layer_tc_kind(li) == 1 || layer_tc_kind(li) == 2) && (!W->layer_tc[li].w_hi || !W->layer_tc[li].b)) return CRFP_ERR_NULL;
+  // feat_prop_lv0 = PixelShufflePack(x_lr) (fp32 SIMT conv at LR resolution, bf16 store)   (CRFP.py:1560)
+  {
+    CB c(n, h, w);
+    c.src(x_lr, 32, 32).layer(W, L_UPSAMPLE).shuffle(2).dst(d->first ? f.prop : f.cur[0], 24, d->first ? 24 : 32);
+    c.p.out_bf16 = 1;
+    CRFP_TRY(c.run(st));
+  }
+  if (!d->first) {
+    const float* flow = d->flow;
+    if (n > 1 && d->flow_clip_stride != (long long)(hw * 2)) {
+      CRFP_TRY(gather_images(n, (long long)hw * 2, d->flow, d->flow_clip_stride, f.flow_d, st));
+      flow = f.flow_d;
+    }
+    CRFP_TRY(launch_flow_up2_dual(n, h, w, flow, f.flow_l1, f.flow8, st));
+    CRFP_TRY(crfp_resize_bilinear(n, h, w, 2, flow, H, Wd, 0.125f, 0.125f, 8.f, f.flow_hr, st));
+    {  // P = downsample(S0): fp32 HR state read through pixel_unshuffle(4), bf16 store         (CRFP.py:1569)
+      CB c(n, h1, w1);
+      c.src(d->state_hr, 64, 4, 0, CRFP_SRC_UNSHUFFLE4).layer(W, L_DOWNSAMPLE).dst(f.P, 32, 32);
+      c.p.out_bf16 = 1;
+      CRFP_TRY(c.run(st));
+    }
+    crfp_warp_desc wd;
+    memset(&wd, 0, sizeof(wd));
+    wd.n = n; wd.h = h1; wd.w = w1; wd.c = 32; wd.x = f.P; wd.x_cstride = 32; wd.flow = f.flow_l1;
+    wd.out = f.P_w; wd.out_cstride = 32;
+    CRFP_TRY(launch_flow_warp_bf16(wd, st));
+    wd.h = H; wd.w = Wd; wd.c = 4; wd.x = d->state_hr; wd.x_cstride = 4; wd.flow = f.flow_hr;
+    wd.out = f.S0_w; wd.out_cstride = 4;
+    CRFP_TRY(launch_flow_warp(wd, st));
+    for (int k = 0; k < 3; ++k) {
+      wd.h = h1; wd.w = w1; wd.c = 8; wd.x = d->state_l1; wd.x_cstride = 24; wd.x_coffset = 8 * k; wd.flow = f.flow_l1;
+      wd.out = f.cur[k]; wd.out_cstride = 32; wd.out_coffset = 24;
+      CRFP_TRY(launch_flow_warp_bf16(wd, st));
+    }
+    static const int lb0[3] = {L_DCN0_B0, L_DCN1_B0, L_DCN2_B0};
+    static const int lb2[3] = {L_DCN0_B2, L_DCN1_B2, L_DCN2_B2};
+    static const int lfu[3] = {-1, L_DCN1_FUSE, L_DCN2_FUSE};
+    static const int lhd[3] = {L_DCN0_HEADS, L_DCN1_HEADS, L_DCN2_HEADS};
+    static const int ldc[3] = {L_DCN0_DCN, L_DCN1_DCN, L_DCN2_DCN};
+    static const int lri[3] = {L_RES0_IN, L_RES1_IN, L_RES2_IN};
+    static const int lr1[3] = {L_RES0_C1, L_RES1_C1, L_RES2_C1};
+    static const int lr2[3] = {L_RES0_C2, L_RES1_C2, L_RES2_C2};
+    const float* offfeat = nullptr;
+    for (int k = 0; k < 3; ++k) {
+      float* cur = f.cur[k];
+      CRFP_TRY(TB(n, h1, w1).src(cur, 32, 32).src(f.P_w, 32, 32).src(f.flow8, 8, 8).layer(W, lb0[k]).act(CRFP_ACT_LRELU)
+                   .dst(f.t1, 32, 32).run(st));
+      float* z = f.offf[k & 1];
+      if (k == 0) {
+        CRFP_TRY(TB(n, h1, w1).src(f.t1, 32, 32).layer(W, lb2[k]).act(CRFP_ACT_LRELU).dst(z, 32, 32).run(st));
+      } else {
+        CRFP_TRY(TB(n, h1, w1).src(f.t1, 32, 32).layer(W, lb2[k]).act(CRFP_ACT_LRELU).dst(f.t2, 32, 32).run(st));
+        CRFP_TRY(TB(n, h1, w1).src(f.t2, 32, 32).src(offfeat, 32, 32).layer(W, lfu[k]).act(CRFP_ACT_LRELU)
+                     .dst(z, 32, 32).run(st));
+      }
+      offfeat = z;
+      CRFP_TRY(TB(n, h1, w1).src(z, 32, 32).layer(W, lhd[k]).head(f.flow_l1, 144, 10.f).f32().dst(f.om, 216, 216).run(st));
+      crfp_dcn_desc dd;
+      memset(&dd, 0, sizeof(dd));
+      dd.n = n; dd.h = h1; dd.w = w1; dd.c = 32; dd.cout = 32; dd.dg = 8;
+      dd.x = f.P; dd.x_cstride = 32;
+      dd.offset = f.om; dd.off_cstride = 216; dd.off_coffset = 0;
+      dd.mask = f.om; dd.mask_cstride = 216; dd.mask_coffset = 144;
+      dd.weight = reinterpret_cast<const float*>(W->layer_tc[ldc[k]].w_hi); dd.bias = W->layer_tc[ldc[k]].b;
+      dd.out = f.A; dd.out_cstride = 32;
+      CRFP_TRY(launch_dcn_tc(dd, st));
+      CRFP_TRY(TB(n, h1, w1).src(cur, 32, 32).src(f.A, 32, 32).layer(W, lri[k]).act(CRFP_ACT_LRELU).dst(f.r0, 32, 32).run(st));
+      CRFP_TRY(TB(n, h1, w1).src(f.r0, 32, 32).layer(W, lr1[k]).act(CRFP_ACT_RELU).dst(f.r1, 32, 32).run(st));
+      float* nxt = (k < 2) ? f.cur[k + 1] : f.prop;
+      const int nxt_cs = (k < 2) ? 32 : 24;
+      CRFP_TRY(TB(n, h1, w1).src(f.r1, 32, 32).layer(W, lr2[k]).res(f.r0, 32).dst(nxt, 24, nxt_cs)
+                   .dst(d->state_l1, 8, 24, 8 * k).run(st));
+    }
+    CRFP_TRY(TB(n, h1, w1).src(f.prop, 24, 24).layer(W, L_UPSAMPLE_POST).act(CRFP_ACT_LRELU).shuffle_f32(4)
+                 .dst(f.q, 4, 4).run(st));
+    CRFP_TRY(TB(n, h1, w1).src(offfeat, 32, 32).layer(W, L_DCN3_UP).shuffle_f32(4).scale(2.f).dst(f.po, 4, 4).run(st));
+  } else {
+    static const int lrf[3] = {L_RES0_IN_FIRST, L_RES1_IN_FIRST, L_RES2_IN_FIRST};
+    static const int lr1[3] = {L_RES0_C1, L_RES1_C1, L_RES2_C1};
+    static const int lr2[3] = {L_RES0_C2, L_RES1_C2, L_RES2_C2};
+    float* pa = f.prop;
+    float* pb = f.cur[0];
+    for (int k = 0; k < 3; ++k) {
+      CRFP_TRY(TB(n, h1, w1).src(pa, 24, 24).layer(W, lrf[k]).act(CRFP_ACT_LRELU).dst(f.r0, 32, 32).run(st));
+      CRFP_TRY(TB(n, h1, w1).src(f.r0, 32, 32).layer(W, lr1[k]).act(CRFP_ACT_RELU).dst(f.r1, 32, 32).run(st));
+      CRFP_TRY(TB(n, h1, w1).src(f.r1, 32, 32).layer(W, lr2[k]).res(f.r0, 32).dst(pb, 24, 24)
+                   .dst(d->state_l1, 8, 24, 8 * k).run(st));
+      float* tmp = pa; pa = pb; pb = tmp;
+    }
+    CRFP_TRY(TB(n, h1, w1).src(pa, 24, 24).layer(W, L_UPSAMPLE_POST).act(CRFP_ACT_LRELU).shuffle_f32(4)
+                 .dst(f.q, 4, 4).run(st));
+  }
+  return CRFP_OK;
+}
+
 }  // namespace crfp
 
 using namespace crfp;
@@ -280,6 +488,7 @@ extern "C" int crfp_dsv_layer_info(int i, crfp_layer_info* info) {
   if (!info) return CRFP_ERR_NULL;
   if (i < 0 || i >= L_COUNT) return CRFP_ERR_BAD_SHAPE;
   *info = kLayers[i];
+  info->tc = layer_tc_kind(i);
   return CRFP_OK;
 }
 
@@ -362,93 +571,124 @@ extern "C" int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weigh
     x_lr = f.x_lr_d;
   }
 
-  // feat_prop_lv0 = PixelShufflePack(x_lr): 32 -> 96 @LR, shuffle x2 -> 24ch @L1           (CRFP.py:1560)
-  float* prop_dst = d->first ? f.prop : f.cur[0];
-  const int prop_cs = d->first ? 24 : 32;
-  CRFP_TRY(CB(n, h, w).src(x_lr, 32, 32).layer(W, L_UPSAMPLE).shuffle(2).dst(prop_dst, 24, prop_cs).run(st));
+  if (W->precision == CRFP_PREC_BF16) {
+    if (d->fg) return CRFP_ERR_UNSUPPORTED;  // regional masking is only wired in the fp32 path
+    CRFP_TRY(frame_l1_bf16(d, W, f, x_lr, st));
+  } else {
+    // feat_prop_lv0 = PixelShufflePack(x_lr): 32 -> 96 @LR, shuffle x2 -> 24ch @L1           (CRFP.py:1560)
+    float* prop_dst = d->first ? f.prop : f.cur[0];
+    const int prop_cs = d->first ? 24 : 32;
+    CRFP_TRY(CB(n, h, w).src(x_lr, 32, 32).layer(W, L_UPSAMPLE).shuffle(2).dst(prop_dst, 24, prop_cs).run(st));
 
-  const float* prop24 = nullptr;  // input of upsample_post
-  if (!d->first) {
-    const float* flow = d->flow;
-    if (n > 1 && d->flow_clip_stride != (long long)(hw * 2)) {
-      CRFP_TRY(gather_images(n, (long long)hw * 2, d->flow, d->flow_clip_stride, f.flow_d, st));
-      flow = f.flow_d;
-    }
-    // flow_lv3 = up2(flow)*2, flow_lv0 = up8(flow)*8                                        (CRFP.py:1565-1566)
-    CRFP_TRY(crfp_resize_bilinear(n, h, w, 2, flow, h1, w1, 0.5f, 0.5f, 2.f, f.flow_l1, st));
-    CRFP_TRY(crfp_resize_bilinear(n, h, w, 2, flow, H, Wd, 0.125f, 0.125f, 8.f, f.flow_hr, st));
-    // P = downsample(S0): pixel_unshuffle(4) + conv 64 -> 32                                (CRFP.py:1569)
-    CRFP_TRY(CB(n, h1, w1).src(d->state_hr, 64, 4, 0, CRFP_SRC_UNSHUFFLE4).layer(W, L_DOWNSAMPLE).dst(f.P, 32, 32).run(st));
-    // warps                                                                                 (CRFP.py:1570-1577)
-    crfp_warp_desc wd;
-    memset(&wd, 0, sizeof(wd));
-    wd.n = n; wd.h = h1; wd.w = w1; wd.c = 32; wd.x = f.P; wd.x_cstride = 32; wd.flow = f.flow_l1;
-    wd.out = f.P_w; wd.out_cstride = 32;
-    CRFP_TRY(launch_flow_warp(wd, st));
-    wd.h = H; wd.w = Wd; wd.c = 4; wd.x = d->state_hr; wd.x_cstride = 4; wd.flow = f.flow_hr;
-    wd.out = f.S0_w; wd.out_cstride = 4;
-    CRFP_TRY(launch_flow_warp(wd, st));
-    for (int k = 0; k < 3; ++k) {  // warped feat_lv{k} lands in channels 24..31 of level k's `cur`
-      wd.h = h1; wd.w = w1; wd.c = 8; wd.x = d->state_l1; wd.x_cstride = 24; wd.x_coffset = 8 * k; wd.flow = f.flow_l1;
-      wd.out = f.cur[k]; wd.out_cstride = 32; wd.out_coffset = 24;
-      CRFP_TRY(launch_flow_warp(wd, st));
-    }
-    const float* fg_l1 = nullptr;
-    if (d->fg) {  // streaming regional mask at L1: bilinear x0.25                            (CRFP_test.py:2299-2300)
-      if (n > 1 && d->fg_clip_stride != (long long)H * Wd) return CRFP_ERR_UNSUPPORTED;
-      CRFP_TRY(crfp_resize_bilinear(n, H, Wd, 1, d->fg, h1, w1, 4.f, 4.f, 1.f, f.fg_l1, st));
-      fg_l1 = f.fg_l1;
-    }
-    static const int lb0[3] = {L_DCN0_B0, L_DCN1_B0, L_DCN2_B0};
-    static const int lb2[3] = {L_DCN0_B2, L_DCN1_B2, L_DCN2_B2};
-    static const int lfu[3] = {-1, L_DCN1_FUSE, L_DCN2_FUSE};
-    static const int lhd[3] = {L_DCN0_HEADS, L_DCN1_HEADS, L_DCN2_HEADS};
-    static const int ldc[3] = {L_DCN0_DCN, L_DCN1_DCN, L_DCN2_DCN};
-    static const int lri[3] = {L_RES0_IN, L_RES1_IN, L_RES2_IN};
-    static const int lr1[3] = {L_RES0_C1, L_RES1_C1, L_RES2_C1};
-    static const int lr2[3] = {L_RES0_C2, L_RES1_C2, L_RES2_C2};
-    const float* offfeat = nullptr;
-    for (int k = 0; k < 3; ++k) {
-      float* cur = f.cur[k];
-      // DCN_module (CRFP.py:324-352)
-      CRFP_TRY(CB(n, h1, w1).src(cur, 32, 32).src(f.P_w, 32, 32).src(f.flow_l1, 2, 2).layer(W, lb0[k])
-                   .act(CRFP_ACT_LRELU).dst(f.t1, 32, 32).run(st));
-      float* z = f.offf[k & 1];
-      if (k == 0) {
-        CRFP_TRY(CB(n, h1, w1).src(f.t1, 32, 32).layer(W, lb2[k]).act(CRFP_ACT_LRELU).dst(z, 32, 32).run(st));
-      } else {
-        CRFP_TRY(CB(n, h1, w1).src(f.t1, 32, 32).layer(W, lb2[k]).act(CRFP_ACT_LRELU).dst(f.t2, 32, 32).run(st));
-        CRFP_TRY(CB(n, h1, w1).src(f.t2, 32, 32).src(offfeat, 32, 32).layer(W, lfu[k]).act(CRFP_ACT_LRELU)
-                     .dst(z, 32, 32).run(st));
+    const float* prop24 = nullptr;  // input of upsample_post
+    if (!d->first) {
+      const float* flow = d->flow;
+      if (n > 1 && d->flow_clip_stride != (long long)(hw * 2)) {
+        CRFP_TRY(gather_images(n, (long long)hw * 2, d->flow, d->flow_clip_stride, f.flow_d, st));
+        flow = f.flow_d;
       }
-      offfeat = z;
-      CRFP_TRY(CB(n, h1, w1).src(z, 32, 32).layer(W, lhd[k]).head(f.flow_l1, 144, 10.f).dst(f.om, 216, 216).run(st));
-      crfp_dcn_desc dd;
-      memset(&dd, 0, sizeof(dd));
-      dd.n = n; dd.h = h1; dd.w = w1; dd.c = 32; dd.cout = 32; dd.dg = 8;
-      dd.x = f.P; dd.x_cstride = 32;
-      dd.offset = f.om; dd.off_cstride = 216; dd.off_coffset = 0;
-      dd.mask = f.om; dd.mask_cstride = 216; dd.mask_coffset = 144;
-      dd.weight = W->layer[ldc[k]].w; dd.bias = W->layer[ldc[k]].b;
-      dd.out = f.A; dd.out_cstride = 32;
-      CRFP_TRY(launch_dcn(dd, st));
-      // ResidualBlocksWithInputConv on cat(cur, A) (CRFP.py:1589-1596)
-      CB in(n, h1, w1);
-      in.src(cur, 32, 32).src(f.A, 32, 32).layer(W, lri[k]).act(CRFP_ACT_LRELU).dst(f.r0, 32, 32);
-      if (fg_l1 && k > 0) in.fg(fg_l1, (long long)h1 * w1);
-      CRFP_TRY(in.run(st));
-      CRFP_TRY(CB(n, h1, w1).src(f.r0, 32, 32).layer(W, lr1[k]).act(CRFP_ACT_RELU).dst(f.r1, 32, 32).run(st));
-      // split: first 24 channels propagate, last 8 become feat_lv{k} of the next frame
-      float* nxt = (k < 2) ? f.cur[k + 1] : f.prop;
-      const int nxt_cs = (k < 2) ? 32 : 24;
-      CRFP_TRY(CB(n, h1, w1).src(f.r1, 32, 32).layer(W, lr2[k]).res(f.r0, 32).dst(nxt, 24, nxt_cs)
-                   .dst(d->state_l1, 8, 24, 8 * k).run(st));
+      // flow_lv3 = up2(flow)*2, flow_lv0 = up8(flow)*8                                        (CRFP.py:1565-1566)
+      CRFP_TRY(crfp_resize_bilinear(n, h, w, 2, flow, h1, w1, 0.5f, 0.5f, 2.f, f.flow_l1, st));
+      CRFP_TRY(crfp_resize_bilinear(n, h, w, 2, flow, H, Wd, 0.125f, 0.125f, 8.f, f.flow_hr, st));
+      // P = downsample(S0): pixel_unshuffle(4) + conv 64 -> 32                                (CRFP.py:1569)
+      CRFP_TRY(CB(n, h1, w1).src(d->state_hr, 64, 4, 0, CRFP_SRC_UNSHUFFLE4).layer(W, L_DOWNSAMPLE).dst(f.P, 32, 32).run(st));
+      // warps                                                                                 (CRFP.py:1570-1577)
+      crfp_warp_desc wd;
+      memset(&wd, 0, sizeof(wd));
+      wd.n = n; wd.h = h1; wd.w = w1; wd.c = 32; wd.x = f.P; wd.x_cstride = 32; wd.flow = f.flow_l1;
+      wd.out = f.P_w; wd.out_cstride = 32;
+      CRFP_TRY(launch_flow_warp(wd, st));
+      wd.h = H; wd.w = Wd; wd.c = 4; wd.x = d->state_hr; wd.x_cstride = 4; wd.flow = f.flow_hr;
+      wd.out = f.S0_w; wd.out_cstride = 4;
+      CRFP_TRY(launch_flow_warp(wd, st));
+      for (int k = 0; k < 3; ++k) {  // warped feat_lv{k} lands in channels 24..31 of level k's `cur`
+        wd.h = h1; wd.w = w1; wd.c = 8; wd.x = d->state_l1; wd.x_cstride = 24; wd.x_coffset = 8 * k; wd.flow = f.flow_l1;
+        wd.out = f.cur[k]; wd.out_cstride = 32; wd.out_coffset = 24;
+        CRFP_TRY(launch_flow_warp(wd, st));
+      }
+      const float* fg_l1 = nullptr;
+      if (d->fg) {  // streaming regional mask at L1: bilinear x0.25                            (CRFP_test.py:2299-2300)
+        if (n > 1 && d->fg_clip_stride != (long long)H * Wd) return CRFP_ERR_UNSUPPORTED;
+        CRFP_TRY(crfp_resize_bilinear(n, H, Wd, 1, d->fg, h1, w1, 4.f, 4.f, 1.f, f.fg_l1, st));
+        fg_l1 = f.fg_l1;
+      }
+      static const int lb0[3] = {L_DCN0_B0, L_DCN1_B0, L_DCN2_B0};
+      static const int lb2[3] = {L_DCN0_B2, L_DCN1_B2, L_DCN2_B2};
+      static const int lfu[3] = {-1, L_DCN1_FUSE, L_DCN2_FUSE};
+      static const int lhd[3] = {L_DCN0_HEADS, L_DCN1_HEADS, L_DCN2_HEADS};
+      static const int ldc[3] = {L_DCN0_DCN, L_DCN1_DCN, L_DCN2_DCN};
+      static const int lri[3] = {L_RES0_IN, L_RES1_IN, L_RES2_IN};
+      static const int lr1[3] = {L_RES0_C1, L_RES1_C1, L_RES2_C1};
+      static const int lr2[3] = {L_RES0_C2, L_RES1_C2, L_RES2_C2};
+      const float* offfeat = nullptr;
+      for (int k = 0; k < 3; ++k) {
+        float* cur = f.cur[k];
+        // DCN_module (CRFP.py:324-352)
+        CRFP_TRY(CB(n, h1, w1).src(cur, 32, 32).src(f.P_w, 32, 32).src(f.flow_l1, 2, 2).layer(W, lb0[k])
+                     .act(CRFP_ACT_LRELU).dst(f.t1, 32, 32).run(st));
+        float* z = f.offf[k & 1];
+        if (k == 0) {
+          CRFP_TRY(CB(n, h1, w1).src(f.t1, 32, 32).layer(W, lb2[k]).act(CRFP_ACT_LRELU).dst(z, 32, 32).run(st));
+        } else {
+          CRFP_TRY(CB(n, h1, w1).src(f.t1, 32, 32).layer(W, lb2[k]).act(CRFP_ACT_LRELU).dst(f.t2, 32, 32).run(st));
+          CRFP_TRY(CB(n, h1, w1).src(f.t2, 32, 32).src(offfeat, 32, 32).layer(W, lfu[k]).act(CRFP_ACT_LRELU)
+                       .dst(z, 32, 32).run(st));
+        }
+        offfeat = z;
+        CRFP_TRY(CB(n, h1, w1).src(z, 32, 32).layer(W, lhd[k]).head(f.flow_l1, 144, 10.f).dst(f.om, 216, 216).run(st));
+        crfp_dcn_desc dd;
+        memset(&dd, 0, sizeof(dd));
+        dd.n = n; dd.h = h1; dd.w = w1; dd.c = 32; dd.cout = 32; dd.dg = 8;
+        dd.x = f.P; dd.x_cstride = 32;
+        dd.offset = f.om; dd.off_cstride = 216; dd.off_coffset = 0;
+        dd.mask = f.om; dd.mask_cstride = 216; dd.mask_coffset = 144;
+        dd.weight = W->layer[ldc[k]].w; dd.bias = W->layer[ldc[k]].b;
+        dd.out = f.A; dd.out_cstride = 32;
+        if (W->precision == CRFP_PREC_TC3 && W->layer_tc[ldc[k]].w_hi && W->layer_tc[ldc[k]].w_lo) {
+          dd.weight = reinterpret_cast<const float*>(W->layer_tc[ldc[k]].w_hi); dd.bias = W->layer_tc[ldc[k]].b;
+          CRFP_TRY(launch_dcn_tc3(dd, W->layer_tc[ldc[k]].w_lo, st));
+        } else {
+          CRFP_TRY(launch_dcn(dd, st));
+        }
+        // ResidualBlocksWithInputConv on cat(cur, A) (CRFP.py:1589-1596)
+        CB in(n, h1, w1);
+        in.src(cur, 32, 32).src(f.A, 32, 32).layer(W, lri[k]).act(CRFP_ACT_LRELU).dst(f.r0, 32, 32);
+        if (fg_l1 && k > 0) in.fg(fg_l1, (long long)h1 * w1);
+        CRFP_TRY(in.run(st));
+        CRFP_TRY(CB(n, h1, w1).src(f.r0, 32, 32).layer(W, lr1[k]).act(CRFP_ACT_RELU).dst(f.r1, 32, 32).run(st));
+        // split: first 24 channels propagate, last 8 become feat_lv{k} of the next frame
+        float* nxt = (k < 2) ? f.cur[k + 1] : f.prop;
+        const int nxt_cs = (k < 2) ? 32 : 24;
+        CRFP_TRY(CB(n, h1, w1).src(f.r1, 32, 32).layer(W, lr2[k]).res(f.r0, 32).dst(nxt, 24, nxt_cs)
+                     .dst(d->state_l1, 8, 24, 8 * k).run(st));
+      }
+      prop24 = f.prop;
+      // L3                                                                                    (CRFP.py:1625-1630)
+      CRFP_TRY(CB(n, h1, w1).src(prop24, 24, 24).layer(W, L_UPSAMPLE_POST).act(CRFP_ACT_LRELU).shuffle(4)
+                   .dst(f.q, 4, 4).run(st));
+      CRFP_TRY(CB(n, h1, w1).src(offfeat, 32, 32).layer(W, L_DCN3_UP).shuffle(4).scale(2.f).dst(f.po, 4, 4).run(st));
+    } else {
+      // first frame: no alignment; cat([prop, zeros32, zeros8]) == only weight[:, :24] contributes (CRFP.py:1634-1670)
+      static const int lrf[3] = {L_RES0_IN_FIRST, L_RES1_IN_FIRST, L_RES2_IN_FIRST};
+      static const int lr1[3] = {L_RES0_C1, L_RES1_C1, L_RES2_C1};
+      static const int lr2[3] = {L_RES0_C2, L_RES1_C2, L_RES2_C2};
+      float* pa = f.prop;       // 24ch ping
+      float* pb = f.cur[0];     // reuse as 24ch pong (pixel stride 24)
+      for (int k = 0; k < 3; ++k) {
+        CRFP_TRY(CB(n, h1, w1).src(pa, 24, 24).layer(W, lrf[k]).act(CRFP_ACT_LRELU).dst(f.r0, 32, 32).run(st));
+        CRFP_TRY(CB(n, h1, w1).src(f.r0, 32, 32).layer(W, lr1[k]).act(CRFP_ACT_RELU).dst(f.r1, 32, 32).run(st));
+        CRFP_TRY(CB(n, h1, w1).src(f.r1, 32, 32).layer(W, lr2[k]).res(f.r0, 32).dst(pb, 24, 24)
+                     .dst(d->state_l1, 8, 24, 8 * k).run(st));
+        float* tmp = pa; pa = pb; pb = tmp;
+      }
+      prop24 = pa;
+      CRFP_TRY(CB(n, h1, w1).src(prop24, 24, 24).layer(W, L_UPSAMPLE_POST).act(CRFP_ACT_LRELU).shuffle(4)
+                   .dst(f.q, 4, 4).run(st));
     }
-    prop24 = f.prop;
-    // L3                                                                                    (CRFP.py:1625-1630)
-    CRFP_TRY(CB(n, h1, w1).src(prop24, 24, 24).layer(W, L_UPSAMPLE_POST).act(CRFP_ACT_LRELU).shuffle(4)
-                 .dst(f.q, 4, 4).run(st));
-    CRFP_TRY(CB(n, h1, w1).src(offfeat, 32, 32).layer(W, L_DCN3_UP).shuffle(4).scale(2.f).dst(f.po, 4, 4).run(st));
+  }
+
+  // ---------------- HR stage (8h x 8w, 4 channels, fp32 in both precisions)
+  if (!d->first) {
     CRFP_TRY(CB(n, H, Wd).src(f.q, 4, 4).src(f.S0_w, 4, 4).src(f.flow_hr, 2, 2).layer(W, L_DCN3_B0).act(CRFP_ACT_LRELU)
                  .dst(f.h1, 4, 4).run(st));
     CRFP_TRY(CB(n, H, Wd).src(f.h1, 4, 4).layer(W, L_DCN3_B2).act(CRFP_ACT_LRELU).dst(f.h2, 4, 4).run(st));
@@ -468,22 +708,6 @@ extern "C" int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weigh
     if (d->fg) in3.fg(d->fg, d->fg_clip_stride);
     CRFP_TRY(in3.run(st));
   } else {
-    // first frame: no alignment; cat([prop, zeros32, zeros8]) == only weight[:, :24] contributes (CRFP.py:1634-1670)
-    static const int lrf[3] = {L_RES0_IN_FIRST, L_RES1_IN_FIRST, L_RES2_IN_FIRST};
-    static const int lr1[3] = {L_RES0_C1, L_RES1_C1, L_RES2_C1};
-    static const int lr2[3] = {L_RES0_C2, L_RES1_C2, L_RES2_C2};
-    float* pa = f.prop;       // 24ch ping
-    float* pb = f.cur[0];     // reuse as 24ch pong (pixel stride 24)
-    for (int k = 0; k < 3; ++k) {
-      CRFP_TRY(CB(n, h1, w1).src(pa, 24, 24).layer(W, lrf[k]).act(CRFP_ACT_LRELU).dst(f.r0, 32, 32).run(st));
-      CRFP_TRY(CB(n, h1, w1).src(f.r0, 32, 32).layer(W, lr1[k]).act(CRFP_ACT_RELU).dst(f.r1, 32, 32).run(st));
-      CRFP_TRY(CB(n, h1, w1).src(f.r1, 32, 32).layer(W, lr2[k]).res(f.r0, 32).dst(pb, 24, 24)
-                   .dst(d->state_l1, 8, 24, 8 * k).run(st));
-      float* tmp = pa; pa = pb; pb = tmp;
-    }
-    prop24 = pa;
-    CRFP_TRY(CB(n, h1, w1).src(prop24, 24, 24).layer(W, L_UPSAMPLE_POST).act(CRFP_ACT_LRELU).shuffle(4)
-                 .dst(f.q, 4, 4).run(st));
     CRFP_TRY(CB(n, H, Wd).src(f.q, 4, 4).layer(W, L_RES3_IN_FIRST).act(CRFP_ACT_LRELU).dst(f.g0, 4, 4).run(st));
   }
   CRFP_TRY(CB(n, H, Wd).src(f.g0, 4, 4).layer(W, L_RES3_C1).act(CRFP_ACT_RELU).dst(f.g1, 4, 4).run(st));

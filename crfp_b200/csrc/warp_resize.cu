@@ -133,7 +133,90 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(int n, int c, int h, 
   out[(size_t)b * out_image_stride + (size_t)ch * hw + p] = __ldg(in + ((size_t)b * hw + p) * cs + co + ch);
 }
 
+// ---- bf16 flow_warp: thread = (pixel, 8-channel chunk); fp32 positions / weights, bf16 storage
+__global__ void __launch_bounds__(256) flow_warp_bf16_kernel(const crfp_warp_desc D) {
+  const int cq = D.c >> 3;
+  const long long total = (long long)D.n * D.h * D.w * cq;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int q = (int)(idx % cq);
+  const long long pix = idx / cq;
+  const int x = (int)(pix % D.w);
+  const int y = (int)((pix / D.w) % D.h);
+  const int n = (int)(pix / ((long long)D.w * D.h));
+  const float2 fl = __ldg(reinterpret_cast<const float2*>(D.flow + pix * 2));
+  const float ix = warp_coord(x, fl.x, D.w), iy = warp_coord(y, fl.y, D.h);
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+  const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix;
+  const float wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
+  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(D.x) + (size_t)n * D.h * D.w * D.x_cstride + D.x_coffset + q * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const bool vx0 = (x0 >= 0 && x0 < D.w), vx1 = (x1 >= 0 && x1 < D.w);
+  const bool vy0 = (y0 >= 0 && y0 < D.h), vy1 = (y1 >= 0 && y1 < D.h);
+#define CRFP_ACC8(vy, vx, yy, xx, wgt)                                                                        \
+  if ((vy) && (vx)) {                                                                                         \
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)(yy) * D.w + (xx)) * D.x_cstride));   \
+    const __nv_bfloat162* t2 = reinterpret_cast<const __nv_bfloat162*>(&t);                                   \
+    const float w_ = (wgt);                                                                                   \
+    for (int k = 0; k < 4; ++k) {                                                                             \
+      const float2 f = __bfloat1622float2(t2[k]);                                                             \
+      acc[2 * k] += f.x * w_; acc[2 * k + 1] += f.y * w_;                                                     \
+    }                                                                                                         \
+  }
+  CRFP_ACC8(vy0, vx0, y0, x0, wx0 * wy0)
+  CRFP_ACC8(vy0, vx1, y0, x1, wx1 * wy0)
+  CRFP_ACC8(vy1, vx0, y1, x0, wx0 * wy1)
+  CRFP_ACC8(vy1, vx1, y1, x1, wx1 * wy1)
+#undef CRFP_ACC8
+  __nv_bfloat162 o[4];
+  for (int k = 0; k < 4; ++k) o[k] = __floats2bfloat162_rn(acc[2 * k], acc[2 * k + 1]);
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(D.out) + (size_t)pix * D.out_cstride + D.out_coffset + q * 8) =
+      *reinterpret_cast<uint4*>(o);
+}
+
+// flow_lv3 = up2(flow)*2 (model/CRFP.py:1565) written twice: fp32 NHWC2 (warps, DCN heads) and bf16 NHWC8
+// [fx, fy, 0 x6] (third source of the tensor-core dcn_block conv)
+__global__ void __launch_bounds__(256) flow_up2_dual_kernel(int n, int h, int w, const float* __restrict__ flow,
+                                                            float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf8) {
+  const int ho = 2 * h, wo = 2 * w;
+  const long long total = (long long)n * ho * wo;
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const int x = (int)(pix % wo), y = (int)((pix / wo) % ho);
+  const int b = (int)(pix / ((long long)wo * ho));
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilin_src(y, 0.5f, h, y0, y1, ly);
+  bilin_src(x, 0.5f, w, x0, x1, lx);
+  const float2* ib = reinterpret_cast<const float2*>(flow) + (size_t)b * h * w;
+  const float2 v00 = __ldg(ib + (size_t)y0 * w + x0), v01 = __ldg(ib + (size_t)y0 * w + x1);
+  const float2 v10 = __ldg(ib + (size_t)y1 * w + x0), v11 = __ldg(ib + (size_t)y1 * w + x1);
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const float fx = (hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x)) * 2.f;
+  const float fy = (hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y)) * 2.f;
+  reinterpret_cast<float2*>(out_f32)[pix] = make_float2(fx, fy);
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  __nv_bfloat162 p = __floats2bfloat162_rn(fx, fy);
+  o.x = *reinterpret_cast<uint32_t*>(&p);
+  reinterpret_cast<uint4*>(out_bf8)[pix] = o;
+}
+
 static inline unsigned grid1d(long long total) { return (unsigned)((total + 255) / 256); }
+
+int launch_flow_warp_bf16(const crfp_warp_desc& d, cudaStream_t st) {
+  if (d.c % 8 || ((d.x_cstride | d.x_coffset | d.out_cstride | d.out_coffset) & 7)) return CRFP_ERR_BAD_SHAPE;
+  const long long total = (long long)d.n * d.h * d.w * (d.c / 8);
+  if (total == 0) return CRFP_OK;
+  flow_warp_bf16_kernel<<<grid1d(total), 256, 0, st>>>(d);
+  return check_launch();
+}
+
+int launch_flow_up2_dual(int n, int h, int w, const float* flow, float* out_f32, void* out_bf8, cudaStream_t st) {
+  const long long total = (long long)n * 4 * h * w;
+  flow_up2_dual_kernel<<<grid1d(total), 256, 0, st>>>(n, h, w, flow, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf8));
+  return check_launch();
+}
 
 int launch_flow_warp(const crfp_warp_desc& d, cudaStream_t st) {
   if (d.c % 4 || ((d.x_cstride | d.x_coffset | d.out_cstride | d.out_coffset) & 3)) return CRFP_ERR_BAD_SHAPE;
@@ -151,6 +234,12 @@ extern "C" int crfp_flow_warp_fwd(const crfp_warp_desc* d, crfp_stream stream) {
   if (!d || !d->x || !d->flow || !d->out) return CRFP_ERR_NULL;
   if (d->n < 0 || d->h <= 0 || d->w <= 0 || d->c <= 0) return CRFP_ERR_BAD_SHAPE;
   return launch_flow_warp(*d, (cudaStream_t)stream);
+}
+
+extern "C" int crfp_flow_warp_bf16_fwd(const crfp_warp_desc* d, crfp_stream stream) {
+  if (!d || !d->x || !d->flow || !d->out) return CRFP_ERR_NULL;
+  if (d->n < 0 || d->h <= 0 || d->w <= 0 || d->c <= 0 || d->border) return CRFP_ERR_BAD_SHAPE;
+  return launch_flow_warp_bf16(*d, (cudaStream_t)stream);
 }
 
 extern "C" int crfp_flow_warp_indices(int n, int h, int w, const float* flow, int32_t* x0, int32_t* y0,

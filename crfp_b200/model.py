@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
-from .packing import pack_layer
+from .packing import pack_layer, pack_layer_tc3
 from .spec import crfp_dsv_param_shapes
 from .synthetic import fovea_rect
 
@@ -58,8 +58,13 @@ def _kaiming_fan_in_(conv: nn.Conv2d, scale: float):
 
 
 class _CRFPBase(nn.Module):
-    def __init__(self, device, mid_channels=16, y_only=False, hr_dcn=True, offset_prop=True, spynet_pretrained=None):
+    def __init__(self, device, mid_channels=16, y_only=False, hr_dcn=True, offset_prop=True, spynet_pretrained=None,
+                 precision="tc"):
         super().__init__()
+        if precision not in ("fp32", "tc"):
+            raise L.CrfpError("precision must be 'tc' (fp32 storage, tcgen05 3 x bf16 split contractions, fp32-grade) "
+                              "or 'fp32' (all-SIMT fp32 FFMA)")
+        self.precision = precision
         if mid_channels != 32:
             raise L.CrfpError("crfp_b200 implements the shipped configuration mid_channels=32 (main.py:34)")
         if y_only or not hr_dcn or not offset_prop:
@@ -109,18 +114,25 @@ class _CRFPBase(nn.Module):
     # ---- packed weights (refreshed whenever a parameter changes or moves)
     def _weights(self, device):
         params = list(self.parameters())
-        key = (str(device), tuple((p.data_ptr(), p._version) for p in params))
+        key = (str(device), self.precision, tuple((p.data_ptr(), p._version) for p in params))
         if self._packed is not None and self._packed[0] == key:
             return self._packed[2]
         sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in self.state_dict().items()}
         table = L.layer_table()
         W = L.DsvWeights()
         W.mid_channels, W.nlayers = self.mid_channels, len(table)
+        W.precision = L.PREC_TC3 if self.precision == "tc" else L.PREC_FP32
         keep = []
         for i, info in enumerate(table):
             w, b = pack_layer(info, sd)
             keep.append((w, b))
             W.layer[i].w, W.layer[i].b = w.data_ptr(), b.data_ptr()
+            if info["tc"] and self.precision == "tc":
+                hi, lo, bt, wx = pack_layer_tc3(info, sd)
+                keep.append((hi, lo, bt, wx))
+                W.layer_tc[i].w_hi, W.layer_tc[i].w_lo, W.layer_tc[i].b = hi.data_ptr(), lo.data_ptr(), bt.data_ptr()
+                if wx is not None:
+                    W.layer_tc[i].w_extra = wx.data_ptr()
         self._packed = (key, keep, W)
         return W
 
@@ -232,8 +244,8 @@ class MRCF_simple_v18(_CRFPBase):
     state kept on the module, `clear_states()` between clips."""
 
     def __init__(self, device, mid_channels=16, y_only=False, hr_dcn=True, offset_prop=True, split_ratio=3,
-                 spynet_pretrained=None):
-        super().__init__(device, mid_channels, y_only, hr_dcn, offset_prop, spynet_pretrained)
+                 spynet_pretrained=None, precision="tc"):
+        super().__init__(device, mid_channels, y_only, hr_dcn, offset_prop, spynet_pretrained, precision)
         if split_ratio != 3:
             raise L.CrfpError("split_ratio=3 only")
         self.pre_lr = None

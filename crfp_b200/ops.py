@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
-from .packing import cin_packed, cout_packed, pack_conv, pack_conv_tc, pack_dcn
+from .packing import cin_packed, cout_packed, pack_conv, pack_conv_tc, pack_conv_tc3, pack_dcn
 
 
 def _stream():
@@ -237,4 +237,45 @@ def conv3x3_tc_nhwc(srcs, weight, bias, act=L.ACT_NONE, residual=None, out_kind=
     for i, o in enumerate(outs):
         d.dst[i] = L.TcSrc(ptr=o.data_ptr(), c=o.shape[-1], cstride=o.shape[-1], coffset=0)
     L.check(L.lib().crfp_conv3x3_tc_fwd(C.byref(d), _stream()), "conv3x3_tc")
+    return outs[0] if len(outs) == 1 else tuple(outs)
+
+
+def conv3x3_tc3_nhwc(srcs, weight, bias, act=L.ACT_NONE, residual=None, shuffle_r=0, post_scale=1.0, split=None,
+                     flow=None, head_split=0, head_mag=10.0, extra=None):
+    """fp32-accurate tensor-core conv (3 x bf16 split) over the channel concat of fp32 NHWC `srcs` (+ optional
+    2-channel fp32 `extra` source whose weights are the trailing input channels of `weight`)."""
+    srcs = [_req(s, "src") for s in srcs]
+    n, h, w, _ = srcs[0].shape
+    c_list = [s.shape[-1] for s in srcs]
+    cout = weight.shape[0]
+    hi, lo, bp, wx = pack_conv_tc3(weight, bias, c_list, extra=0 if extra is None else extra.shape[-1])
+    d = L.ConvTc3Desc()
+    d.n, d.h, d.w, d.nsrc = n, h, w, len(srcs)
+    for i, s in enumerate(srcs):
+        d.src[i] = L.TcSrc(ptr=s.data_ptr(), c=s.shape[-1], cstride=s.shape[-1], coffset=0)
+    d.cout, d.act = cout, act
+    d.weight_hi, d.weight_lo, d.bias = hi.data_ptr(), lo.data_ptr(), bp.data_ptr()
+    if extra is not None:
+        extra = _req(extra, "extra")
+        d.extra, d.w_extra = extra.data_ptr(), wx.data_ptr()
+    d.post_scale, d.head_mag, d.head_split = post_scale, head_mag, head_split
+    if flow is not None:
+        flow = _req(flow, "flow")
+        d.flow = flow.data_ptr()
+    if residual is not None:
+        residual = _req(residual, "residual")
+        d.residual, d.res_cstride, d.res_coffset = residual.data_ptr(), residual.shape[-1], 0
+    dev = srcs[0].device
+    if shuffle_r:
+        r = shuffle_r
+        outs = [torch.zeros(n, h * r, w * r, cout // (r * r), device=dev, dtype=torch.float32)]
+        d.out_kind, d.shuffle_r = L.TC_OUT_SHUFFLE_F32, r
+    else:
+        parts = list(split) if split else [cout]
+        outs = [torch.zeros(n, h, w, c, device=dev, dtype=torch.float32) for c in parts]
+        d.out_kind = L.TC_OUT_F32
+    d.ndst = len(outs)
+    for i, o in enumerate(outs):
+        d.dst[i] = L.TcSrc(ptr=o.data_ptr(), c=o.shape[-1], cstride=o.shape[-1], coffset=0)
+    L.check(L.lib().crfp_conv3x3_tc3_fwd(C.byref(d), _stream()), "conv3x3_tc3")
     return outs[0] if len(outs) == 1 else tuple(outs)

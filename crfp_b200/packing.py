@@ -106,6 +106,103 @@ def pack_conv_tc(weight: torch.Tensor, bias: torch.Tensor, c_list, ci_lo: int = 
     return out.to(torch.bfloat16).contiguous(), b.contiguous()
 
 
+def _tc3_smem_bytes(kc_real, kc_total, nt):
+    return (2 * 9 * kc_total * nt + 6 * kc_total * 130) * 16 + kc_real * 130 * 32 + nt * 4 + 18 * nt * 4
+
+
+def tc3_cout_tile(cout: int, cin: int):
+    """(nt, ntiles) exactly as crfp_tc3_cout_tile computes them (None if cin is too large for the kernel)."""
+    kc_real = cin // 8
+    kc_total = kc_real + kc_real % 2
+    tiles = (cout + 111) // 112
+    while tiles <= cout:
+        per = (cout + tiles - 1) // tiles
+        nt = max(16, (per + 15) // 16 * 16)
+        if _tc3_smem_bytes(kc_real, kc_total, nt) <= 225 * 1024:
+            return nt, tiles
+        if nt == 16:
+            break
+        tiles += 1
+    return None
+
+
+def split_bf16(x: torch.Tensor):
+    """x (fp32) -> (hi, lo) bf16 with hi = bf16(x), lo = bf16(x - hi)."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.to(torch.float32)).to(torch.bfloat16)
+    return hi, lo
+
+
+def pack_conv_tc3(weight: torch.Tensor, bias: torch.Tensor, c_list, ci_lo: int = 0, extra: int = 0):
+    """OIHW fp32 -> (w_hi, w_lo bf16 [ntiles][9][kc][nt][8], bias fp32 [ntiles*nt], w_extra fp32 [9][extra][ntiles*nt])
+    for crfp_conv3x3_tc3_fwd.  `c_list`: channels of the tensor-core sources (multiples of 8); `extra`: trailing
+    input channels convolved on the CUDA cores (the 2 flow channels of dcn_block.0)."""
+    cout = weight.shape[0]
+    assert all(c % 8 == 0 for c in c_list)
+    k = sum(c_list)
+    tile = tc3_cout_tile(cout, k)
+    if tile is None:
+        raise ValueError(f"conv_tc3: {k} input channels do not fit the shared-memory rings (max 64)")
+    nt, ntiles = tile
+    kc = k // 8
+    kc += kc % 2
+    w = weight.detach().to(torch.float32)
+    wm = torch.zeros(ntiles * nt, kc * 8, 9, device=w.device)
+    wm[:cout, :k] = w[:, ci_lo:ci_lo + k].reshape(cout, k, 9)
+    packed = wm.view(ntiles, nt, kc, 8, 9).permute(0, 4, 2, 1, 3).contiguous()      # (tile, tap, kc, n, j)
+    hi, lo = split_bf16(packed)
+    b = torch.zeros(ntiles * nt, device=w.device, dtype=torch.float32)
+    b[:cout] = bias.detach().to(torch.float32)
+    wx = None
+    if extra:
+        wx = torch.zeros(9, extra, ntiles * nt, device=w.device, dtype=torch.float32)
+        wx[:, :, :cout] = w[:, ci_lo + k:ci_lo + k + extra].reshape(cout, extra, 9).permute(2, 1, 0)
+        wx = wx.contiguous()
+    return hi.contiguous(), lo.contiguous(), b.contiguous(), wx
+
+
+def pack_dcn_tc(weight: torch.Tensor, bias: torch.Tensor, dg: int):
+    """DCNv2 weight -> bf16 UMMA B operand [K/8][cout][8] (k = (g*9+t)*(C/dg)+c) + fp32 bias, for crfp_dcn_v2_tc_fwd."""
+    wk, b = pack_dcn(weight, bias, dg)                     # [K, cout]
+    k, cout = wk.shape
+    out = wk.view(k // 8, 8, cout).permute(0, 2, 1).contiguous()
+    return out.to(torch.bfloat16).contiguous(), b
+
+
+def pack_dcn_tc3(weight: torch.Tensor, bias: torch.Tensor, dg: int):
+    """DCNv2 weight -> (hi, lo) bf16 UMMA B operands [K/8][cout][8] + fp32 bias, for crfp_dcn_v2_tc3_fwd."""
+    wk, b = pack_dcn(weight, bias, dg)
+    k, cout = wk.shape
+    hi, lo = split_bf16(wk.view(k // 8, 8, cout).permute(0, 2, 1).contiguous())
+    return hi.contiguous(), lo.contiguous(), b
+
+
+def pack_layer_tc(info: dict, sd):
+    """bf16-storage tensor-core packing (experimental CRFP_PREC_BF16) of a layer with crfp_layer_info.tc in (1, 2)."""
+    w, b = sd[info["key"] + ".weight"], sd[info["key"] + ".bias"]
+    if info["tc"] == 2:
+        return pack_dcn_tc(w, b, info["dg"])
+    if info["kind"] == 2:
+        w = torch.cat([w, sd[info["key2"] + ".weight"]], dim=0)
+        b = torch.cat([b, sd[info["key2"] + ".bias"]], dim=0)
+    return pack_conv_tc(w, b, info["c"], info["ci_lo"])
+
+
+def pack_layer_tc3(info: dict, sd):
+    """CRFP_PREC_TC3 packing of a layer with crfp_layer_info.tc != 0: (w_hi, w_lo, bias, w_extra or None)."""
+    w, b = sd[info["key"] + ".weight"], sd[info["key"] + ".bias"]
+    if info["tc"] == 2:
+        hi, lo, bb = pack_dcn_tc3(w, b, info["dg"])
+        return hi, lo, bb, None
+    if info["kind"] == 2:
+        w = torch.cat([w, sd[info["key2"] + ".weight"]], dim=0)
+        b = torch.cat([b, sd[info["key2"] + ".bias"]], dim=0)
+    c_tc = [c for c in info["c"] if c % 8 == 0]
+    extra = info["c"][-1] if info["c"][-1] % 8 else 0
+    assert sum(c_tc) + extra == sum(info["c"]) and extra in (0, 2)
+    return pack_conv_tc3(w, b, c_tc, info["ci_lo"], extra)
+
+
 def pack_layer(info: dict, sd):
     """Pack one entry of the library's layer table (crfp_dsv_layer_info) from a state_dict."""
     w, b = sd[info["key"] + ".weight"], sd[info["key"] + ".bias"]

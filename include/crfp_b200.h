@@ -178,6 +178,48 @@ int crfp_conv3x3_tc_fwd(const crfp_conv_tc_desc* d, crfp_stream stream);
 int crfp_tc_cout_tile(int cout, int32_t* nt, int32_t* ntiles);
 size_t crfp_sizeof_conv_tc_desc(void);
 
+/*
+ * fp32-ACCURATE tensor-core conv: fp32 NHWC sources/outputs, operands split hi/lo into bf16 inside the kernel,
+ * A_hi*W_hi + A_lo*W_hi + A_hi*W_lo accumulated in fp32 TMEM (error ~2^-17 relative: keeps the fp32 parity bar).
+ *   sources: fp32 NHWC, channel counts multiples of 8 (strides/offsets multiples of 4)
+ *   weight_hi / weight_lo: bf16 [ntiles][9][kc][nt][8], (nt, ntiles) = crfp_tc3_cout_tile(cout, cin); bias fp32
+ *   extra / w_extra: optional 2-channel fp32 NHWC source (the flow input of dcn_block.0) convolved on the CUDA
+ *           cores in the epilogue with fp32 weights [9][2][ntiles*nt]
+ *   out_kind: CRFP_TC_OUT_F32 (up to 2 channel segments, multiples of 4) or CRFP_TC_OUT_SHUFFLE_F32.
+ */
+typedef struct {
+  const float* ptr;
+  int32_t c, cstride, coffset, _pad;
+} crfp_tc3_src;
+typedef struct {
+  int32_t n, h, w;
+  int32_t nsrc;
+  crfp_tc3_src src[3];
+  int32_t cout;
+  int32_t act;
+  const void* weight_hi;
+  const void* weight_lo;
+  const float* bias;
+  const float* extra;
+  const float* w_extra;
+  int32_t out_kind;
+  int32_t shuffle_r;
+  int32_t ndst;
+  int32_t head_split;
+  crfp_tc_dst dst[2];
+  const float* residual;
+  int32_t res_cstride;
+  int32_t res_coffset;
+  const float* flow;
+  float post_scale;
+  float head_mag;
+} crfp_conv_tc3_desc;
+int crfp_conv3x3_tc3_fwd(const crfp_conv_tc3_desc* d, crfp_stream stream);
+/* cout tiling for `cin` tensor-core input channels (multiple of 8); CRFP_ERR_UNSUPPORTED when cin is too large for
+ * the shared-memory resident rings (cin > 64) */
+int crfp_tc3_cout_tile(int cout, int cin, int32_t* nt, int32_t* ntiles);
+size_t crfp_sizeof_conv_tc3_desc(void);
+
 /* ------------------------------------------------------------------ flow_warp */
 /*
  * out[n,y,x,c] = bilinear(x_in[n,:,:,c], y + flow[n,y,x,1], x + flow[n,y,x,0]); corners outside the
@@ -194,6 +236,8 @@ typedef struct {
   int32_t _pad;
 } crfp_warp_desc;
 int crfp_flow_warp_fwd(const crfp_warp_desc* d, crfp_stream stream);
+/* same, x / out bf16 NHWC with c % 8 == 0 (zeros padding only) */
+int crfp_flow_warp_bf16_fwd(const crfp_warp_desc* d, crfp_stream stream);
 /* debug/parity: the integer corner indices (x0, y0) flow_warp uses at every pixel: int32 [n,h,w] each */
 int crfp_flow_warp_indices(int n, int h, int w, const float* flow, int32_t* x0, int32_t* y0, crfp_stream stream);
 size_t crfp_sizeof_warp_desc(void);
@@ -223,6 +267,12 @@ typedef struct {
   float* out; int32_t out_cstride, out_coffset;
 } crfp_dcn_desc;
 int crfp_dcn_v2_fwd(const crfp_dcn_desc* d, crfp_stream stream);
+/* tensor-core variant (C=32, dg=8, cout=32): x / out bf16 NHWC, weight bf16 [36][32][8] with k = (g*9+t)*4+c,
+ * offset / mask / bias fp32; the gather writes the UMMA A tile in shared memory, tcgen05.mma contracts it. */
+int crfp_dcn_v2_tc_fwd(const crfp_dcn_desc* d, crfp_stream stream);
+/* fp32-accurate tensor-core variant: x / out fp32 NHWC; d->weight and weight_lo are the hi / lo bf16 halves of the
+ * [36][32][8] packed weight; columns are split hi/lo in the kernel, 3 products accumulate in fp32 TMEM. */
+int crfp_dcn_v2_tc3_fwd(const crfp_dcn_desc* d, const void* weight_lo, crfp_stream stream);
 /* debug/parity: floor(py), floor(px) for every (pixel, group, tap): int32 [n,h,w,dg*9] each (non-shared form) */
 int crfp_dcn_v2_indices(const crfp_dcn_desc* d, int32_t* y0, int32_t* x0, crfp_stream stream);
 size_t crfp_sizeof_dcn_desc(void);
@@ -250,10 +300,24 @@ typedef struct {
   const float* b;
 } crfp_layer;
 
+enum { CRFP_PREC_FP32 = 0, CRFP_PREC_BF16 = 1, CRFP_PREC_TC3 = 2 };
+typedef struct {
+  const void* w_hi;     /* bf16 tensor-core packing (TC3: hi half of the split) */
+  const void* w_lo;     /* TC3: lo half (NULL in bf16 mode) */
+  const float* b;
+  const float* w_extra; /* TC3: fp32 [9][2][cout_packed] weights of a trailing 2-channel source, else NULL */
+} crfp_layer_tc;
 typedef struct {
   int32_t mid_channels; /* 32 */
   int32_t nlayers;      /* must equal crfp_dsv_num_layers() */
+  int32_t precision;    /* CRFP_PREC_FP32: every layer fp32 SIMT FFMA (parity <= 1e-3);
+                           CRFP_PREC_TC3 : fp32 storage, the dense layers (cin <= 64) and the L1 DCN contraction on
+                                           tcgen05 as 3 x bf16 split products with fp32 TMEM accumulation — fp32-grade
+                                           (parity <= 1e-3), the default of the Python shell;
+                           CRFP_PREC_BF16: experimental, L1 layers with bf16 STORAGE (not parity-certified) */
+  int32_t _pad;
   crfp_layer layer[CRFP_DSV_MAX_LAYERS];
+  crfp_layer_tc layer_tc[CRFP_DSV_MAX_LAYERS]; /* entries of layers with crfp_layer_info.tc != 0 (else all NULL) */
 } crfp_dsv_weights;
 
 /*
@@ -277,6 +341,11 @@ typedef struct {
   int32_t ci_lo;
   int32_t dg;
   int32_t thin; /* 1: consumed by the thin-channel kernels (cout <= 4): weight [9][cin_packed][4] */
+  int32_t tc;   /* tensor-core packing into crfp_dsv_weights.layer_tc[i]: 0 none; 1 conv (TC3: crfp_conv3x3_tc3_fwd
+                   packing of the sources with c % 8 == 0, a trailing 2-channel source becomes w_extra; BF16:
+                   crfp_conv3x3_tc_fwd packing); 2 DCN (crfp_dcn_v2_tc3_fwd / crfp_dcn_v2_tc_fwd packing);
+                   3 conv, TC3 only */
+  int32_t _pad;
 } crfp_layer_info;
 int crfp_dsv_num_layers(void);
 int crfp_dsv_layer_info(int i, crfp_layer_info* info);

@@ -17,10 +17,11 @@ def sd():
     return make_state_dict(seed=1)
 
 
-@pytest.fixture(scope="module")
-def model(sd):
+@pytest.fixture(scope="module", params=["tc", "fp32"])
+def model(request, sd):
+    """Both precisions must meet the fp32 bar: 'tc' = tcgen05 3 x bf16 split contractions (default), 'fp32' = SIMT."""
     from crfp_b200 import CRFP_DSV
-    m = CRFP_DSV("cuda", mid_channels=32).eval()
+    m = CRFP_DSV("cuda", mid_channels=32, precision=request.param).eval()
     m.load_state_dict(sd, strict=True)
     return m.cuda()
 
@@ -39,7 +40,7 @@ def test_against_reference_golden(name, golden_dir, model):
     out = _run(model, lrs, fvs, mks)
     assert out.shape == fix["out"].shape
     err = (out - fix["out"]).abs().max().item()
-    print(f"{name}: max-abs vs reference golden {err:.3e}")
+    print(f"{name} [{model.precision}]: max-abs vs reference golden {err:.3e}")
     assert err <= TOL
 
 
@@ -50,7 +51,7 @@ def test_against_oracle(model, sd, n, t, h, w, fv):
     ref = O.crfp_dsv_forward(sd, lrs, fvs, mks, taps=taps)
     out = _run(model, lrs, fvs, mks)
     errs = [(out[:, i] - ref[:, i]).abs().max().item() for i in range(t)]
-    print(f"n={n} t={t} {h}x{w}: per-frame max-abs {['%.2e' % e for e in errs]}")
+    print(f"[{model.precision}] n={n} t={t} {h}x{w}: per-frame max-abs {['%.2e' % e for e in errs]}")
     assert max(errs) <= TOL
 
 
@@ -91,7 +92,8 @@ def test_clip_batch_equals_single_clips(model):
         assert torch.equal(full[b:b + 1], one)
 
 
-def test_streaming_module_matches_reference_golden(golden_dir, sd):
+@pytest.mark.parametrize("precision", ["tc", "fp32"])
+def test_streaming_module_matches_reference_golden(golden_dir, sd, precision):
     from crfp_b200 import MRCF_simple_v18
     fix = torch.load(os.path.join(golden_dir, "stream_n1_t3_16x24.pt"))
     c = fix["case"]
@@ -99,7 +101,7 @@ def test_streaming_module_matches_reference_golden(golden_dir, sd):
     fgs = torch.ones(c["n"], c["t"], 1, 8 * c["h"], 8 * c["w"])
     fgs[..., : 4 * c["h"], :] = 0.0
     fgs[:, 0] = 1.0
-    m = MRCF_simple_v18("cuda", mid_channels=32).eval()
+    m = MRCF_simple_v18("cuda", mid_channels=32, precision=precision).eval()
     m.load_state_dict(sd, strict=True)
     m.cuda()
     outs = [m(lrs[:, i:i + 1].cuda(), fvs[:, i:i + 1].cuda(), mks[:, i:i + 1].cuda(), fgs[:, i:i + 1].cuda()).cpu()

@@ -79,3 +79,131 @@ def test_conv_tc_epilogues():
     got4 = nchw(ops.conv3x3_tc_nhwc([nhwc_bf16(x24)], w64.cuda(), b64.cuda(), act=1, out_kind=L.TC_OUT_SHUFFLE_F32,
                                     shuffle_r=4, post_scale=2.0))
     assert (got4 - ref4).abs().max().item() < 1e-4
+
+
+def test_flow_warp_bf16():
+    import ctypes as C
+    from crfp_b200 import _lib as L
+    from oracle import crfp_oracle as O
+    g = _g(3)
+    n, c, h, w = 2, 32, 20, 36
+    x = bf(torch.randn(n, c, h, w, generator=g))
+    flow = torch.randn(n, 2, h, w, generator=g) * 3
+    ref = O.flow_warp(x, flow)
+    xd = nhwc_bf16(x)
+    fd = flow.permute(0, 2, 3, 1).contiguous().cuda()
+    out = torch.zeros_like(xd)
+    d = L.WarpDesc(n=n, h=h, w=w, c=c, x=xd.data_ptr(), x_cstride=c, x_coffset=0, flow=fd.data_ptr(),
+                   out=out.data_ptr(), out_cstride=c, out_coffset=0, border=0)
+    L.check(L.lib().crfp_flow_warp_bf16_fwd(C.byref(d), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "warp bf16")
+    close_bf16(nchw(out), ref)
+
+
+def test_dcn_v2_tc():
+    import ctypes as C
+    from crfp_b200 import _lib as L
+    from crfp_b200.packing import pack_dcn_tc
+    from oracle import crfp_oracle as O
+    g = _g(4)
+    n, h, w = 2, 21, 37
+    x = bf(torch.randn(n, 32, h, w, generator=g))
+    off = torch.randn(n, 144, h, w, generator=g) * 4
+    off[0, :, :2] = 40.0
+    off[0, :, 2:4] = 0.0
+    msk = torch.rand(n, 72, h, w, generator=g)
+    wt = bf(torch.randn(32, 32, 3, 3, generator=g) * 0.05)
+    b = torch.randn(32, generator=g) * 0.05
+    ref = O.dcn_v2(x, off, msk, wt, b, 8)
+    xd = nhwc_bf16(x)
+    om = torch.cat([off, msk], 1).permute(0, 2, 3, 1).contiguous().cuda()       # fused heads tensor (216 ch fp32)
+    wp, bp = pack_dcn_tc(wt.cuda(), b.cuda(), 8)
+    out = torch.zeros(n, h, w, 32, device="cuda", dtype=torch.bfloat16)
+    d = L.DcnDesc(n=n, h=h, w=w, c=32, cout=32, dg=8, shared_taps=0, x=xd.data_ptr(), x_cstride=32, x_coffset=0,
+                  offset=om.data_ptr(), off_cstride=216, off_coffset=0, mask=om.data_ptr(), mask_cstride=216,
+                  mask_coffset=144, weight=wp.data_ptr(), bias=bp.data_ptr(), out=out.data_ptr(), out_cstride=32,
+                  out_coffset=0)
+    L.check(L.lib().crfp_dcn_v2_tc_fwd(C.byref(d), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "dcn tc")
+    # the modulated columns are rounded to bf16 before the contraction: ~2^-9 relative per term
+    close_bf16(nchw(out), ref, extra=4e-3)
+
+
+def test_dcn_v2_tc3_fp32_accuracy():
+    import ctypes as C
+    from crfp_b200 import _lib as L
+    from crfp_b200.packing import pack_dcn_tc3
+    from oracle import crfp_oracle as O
+    g = _g(5)
+    n, h, w = 2, 21, 37
+    x = torch.randn(n, 32, h, w, generator=g)
+    off = torch.randn(n, 144, h, w, generator=g) * 4
+    off[0, :, :2] = 40.0
+    off[0, :, 2:4] = 0.0
+    msk = torch.rand(n, 72, h, w, generator=g)
+    wt = torch.randn(32, 32, 3, 3, generator=g) * 0.05
+    b = torch.randn(32, generator=g) * 0.05
+    ref = O.dcn_v2(x, off, msk, wt, b, 8)
+    xd = x.permute(0, 2, 3, 1).contiguous().cuda()
+    om = torch.cat([off, msk], 1).permute(0, 2, 3, 1).contiguous().cuda()
+    hi, lo, bp = pack_dcn_tc3(wt.cuda(), b.cuda(), 8)
+    out = torch.zeros(n, h, w, 32, device="cuda")
+    d = L.DcnDesc(n=n, h=h, w=w, c=32, cout=32, dg=8, shared_taps=0, x=xd.data_ptr(), x_cstride=32, x_coffset=0,
+                  offset=om.data_ptr(), off_cstride=216, off_coffset=0, mask=om.data_ptr(), mask_cstride=216,
+                  mask_coffset=144, weight=hi.data_ptr(), bias=bp.data_ptr(), out=out.data_ptr(), out_cstride=32,
+                  out_coffset=0)
+    L.check(L.lib().crfp_dcn_v2_tc3_fwd(C.byref(d), lo.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "dcn tc3")
+    err = (nchw(out) - ref).abs().max().item()
+    print(f"dcn tc3 max-abs {err:.3e}")
+    assert err < 1e-4
+
+
+@pytest.mark.parametrize("c_list,cout,hw,act,extra", [
+    ([32], 32, (9, 128), 1, 0), ([32], 32, (21, 300), 1, 0), ([32, 32], 32, (12, 130), 1, 2), ([24], 64, (16, 140), 0, 0),
+    ([32], 216, (7, 200), 0, 0), ([64], 96, (5, 64), 2, 0), ([32, 32], 32, (6, 70), 1, 0), ([64], 128, (6, 20), 2, 0)])
+def test_conv_tc3_fp32_accuracy(c_list, cout, hw, act, extra):
+    """3 x bf16 split tensor-core conv on fp32 data: must be fp32-grade (<= 2e-4 abs on O(1) outputs)."""
+    from crfp_b200 import ops
+    g = _g(11)
+    h, w = hw
+    n = 2
+    srcs = [torch.randn(n, c, h, w, generator=g) for c in c_list]
+    ex = torch.randn(n, extra, h, w, generator=g) * 3 if extra else None
+    cin = sum(c_list) + extra
+    wt = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    allsrc = srcs + ([ex] if extra else [])
+    ref = F.conv2d(torch.cat(allsrc, 1), wt, b, padding=1)
+    ref = F.leaky_relu(ref, 0.1) if act == 1 else F.relu(ref) if act == 2 else ref
+    got = nchw(ops.conv3x3_tc3_nhwc([s.permute(0, 2, 3, 1).contiguous().cuda() for s in srcs], wt.cuda(), b.cuda(), act=act,
+                                    extra=None if ex is None else ex.permute(0, 2, 3, 1).contiguous().cuda()))
+    err = (got - ref).abs().max().item()
+    print(f"tc3 {c_list}->{cout}: max-abs {err:.3e}")
+    assert err < 2e-4
+
+
+def test_conv_tc3_epilogues():
+    from crfp_b200 import _lib as L
+    from crfp_b200 import ops
+    g = _g(12)
+    n, h, w = 1, 11, 150
+    f32 = lambda t: t.permute(0, 2, 3, 1).contiguous().cuda()
+    x = torch.randn(n, 32, h, w, generator=g)
+    r = torch.randn(n, 32, h, w, generator=g)
+    wt = torch.randn(32, 32, 3, 3, generator=g) * 0.08
+    b = torch.randn(32, generator=g) * 0.1
+    ref = F.conv2d(x, wt, b, padding=1) + r
+    a, c = ops.conv3x3_tc3_nhwc([f32(x)], wt.cuda(), b.cuda(), residual=f32(r), split=(24, 8))
+    assert (nchw(a) - ref[:, :24]).abs().max().item() < 2e-4 and (nchw(c) - ref[:, 24:]).abs().max().item() < 2e-4
+    flow = torch.randn(n, 2, h, w, generator=g) * 3
+    w216 = torch.randn(216, 32, 3, 3, generator=g) * 0.05
+    b216 = torch.randn(216, generator=g) * 0.05
+    raw = F.conv2d(x, w216, b216, padding=1)
+    off = 10 * torch.tanh(raw[:, :144]) + flow.flip(1).repeat(1, 72, 1, 1)
+    msk = torch.sigmoid(raw[:, 144:])
+    got = nchw(ops.conv3x3_tc3_nhwc([f32(x)], w216.cuda(), b216.cuda(), act=L.ACT_DCN_HEAD, flow=f32(flow), head_split=144))
+    assert (got[:, :144] - off).abs().max().item() < 1e-3 and (got[:, 144:] - msk).abs().max().item() < 1e-4
+    x24 = torch.randn(n, 24, h, w, generator=g)
+    w64 = torch.randn(64, 24, 3, 3, generator=g) * 0.1
+    b64 = torch.randn(64, generator=g) * 0.1
+    ref4 = F.leaky_relu(F.pixel_shuffle(F.conv2d(x24, w64, b64, padding=1), 4), 0.1) * 2.0
+    got4 = nchw(ops.conv3x3_tc3_nhwc([f32(x24)], w64.cuda(), b64.cuda(), act=1, shuffle_r=4, post_scale=2.0))
+    assert (got4 - ref4).abs().max().item() < 2e-4
