@@ -39,8 +39,8 @@ def parse():
     ap.add_argument("--workload", default="R-lit", choices=list(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="override frames per clip")
     ap.add_argument("--clips", type=int, default=1, help="clips per GPU per step")
-    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
-                    help="f32: all-SIMT fp32 path; bf16: L1 layers on tcgen05 with bf16 storage")
+    ap.add_argument("--precision", default="tc", choices=["tc", "fp32"],
+                    help="tc: fp32 storage, tcgen05 3 x bf16 split contractions (fp32-grade, default); fp32: all-SIMT FFMA")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -194,7 +194,7 @@ def main():
     H, W_ = 8 * h, 8 * w
     fv = 96
 
-    model = CRFP_DSV("cuda", mid_channels=32, precision="bf16" if args.dtype == "bf16" else "fp32").eval()
+    model = CRFP_DSV("cuda", mid_channels=32, precision=args.precision).eval()
     model.load_state_dict(make_state_dict(seed=1), strict=True)
     model.to(dev)
 
@@ -317,9 +317,12 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: LR {h}x{w} -> {H}x{W_} (x8 network; BASELINE.json configs[1]), "
                                f"{t}-frame clip, fovea 96x96, CRFP_DSV mid_channels=32",
+                   "precision": ("fp32 storage; dense contractions as 3 x bf16 split products on tcgen05 with fp32 TMEM "
+                                 "accumulation (parity <= 1e-3 vs the fp32 reference)") if args.precision == "tc"
+                   else "fp32 SIMT FFMA everywhere",
                    "clips_per_gpu": n, "frames_per_clip": t, "parallelism": f"clip-sharded x{world}, no collective",
                    "l2": "per-step working set (>= 4 GB of HR planes) exceeds the 126 MB L2"},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

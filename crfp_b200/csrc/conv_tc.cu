@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const TcParams P) {
   {  // weights slab of this cout tile + bias
     const uint4* gw = reinterpret_cast<const uint4*>(P.weight) + (size_t)cotile * 9 * KC * NT;
     for (int i = tid; i < 9 * KC * NT; i += 128) umma::cp_async16(sW + i, gw + i, 16u);
-    for (int i = tid; i < NT; i += 128) sBias[i] = P.bias[cotile * NT + i];
+    for (int i = tid; i < ((NT + 31) & ~31); i += 128) sBias[i] = (i < NT) ? P.bias[cotile * NT + i] : 0.f;
     // K padding chunks (never loaded) must be finite: zero them once in every slot
     for (int kc = P.kc_real; kc < KC; ++kc)
       for (int i = tid; i < 4 * TCWP; i += 128)
@@ -234,7 +234,7 @@ int launch_conv_tc(TcParams p, cudaStream_t st) {
   if (segs > ceil_div(p.h, 4)) segs = ceil_div(p.h, 4);
   p.rows_per_cta = ceil_div(p.h, segs);
   segs = ceil_div(p.h, p.rows_per_cta);
-  const size_t smem = (size_t)(9 * p.kc_total * p.nt + 4 * p.kc_total * TCWP) * 16 + (size_t)p.nt * 4;
+  const size_t smem = (size_t)(9 * p.kc_total * p.nt + 4 * p.kc_total * TCWP) * 16 + (size_t)((p.nt + 31) & ~31) * 4;
   if (smem > 227 * 1024) return CRFP_ERR_UNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }

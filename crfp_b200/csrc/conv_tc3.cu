@@ -19,21 +19,27 @@ namespace crfp {
 constexpr int T3M = 128;
 constexpr int T3WP = 130;
 
+// Stage one input row (tile + halo) of every source into the fp32 staging buffer, laid out [px][kc_real] 32-byte
+// records = the global NHWC order, so a dense source row is copied as a flat run of 16-byte cp.async pieces.
 __device__ __forceinline__ void tc3_stage_row(const Tc3Params& P, float4* stage, int n, int y, int x0, int tid) {
   const bool yin = (y >= 0 && y < P.h);
   const int kcr = P.kc_real;
-  const int items = kcr * T3WP * 2;  // 16-byte halves of 32-byte (8-channel fp32) records
-  for (int it = tid; it < items; it += 128) {
-    const int half = it & 1, rec = it >> 1;
-    const int px = rec / kcr, kc = rec - px * kcr;
-    const int x = x0 + px - 1;
-    int s = 0;
-    if (P.nsrc > 1 && kc >= P.kstart[1]) s = 1;
-    if (P.nsrc > 2 && kc >= P.kstart[2]) s = 2;
-    const bool in = yin && x >= 0 && x < P.w;
-    const float* g = P.src[s];
-    if (in) g += (((size_t)n * P.h + y) * (size_t)P.w + x) * P.src_cstride[s] + P.src_coffset[s] + (kc - P.kstart[s]) * 8 + half * 4;
-    umma::cp_async16(stage + (kc * T3WP + px) * 2 + half, g, in ? 16u : 0u);
+#pragma unroll 1
+  for (int s = 0; s < P.nsrc; ++s) {
+    const int q = P.src_c[s] >> 2;                 // 16-byte pieces per pixel of this source
+    const int items = T3WP * q;
+    const float* rowp = P.src[s] + (((size_t)n * P.h + (yin ? y : 0)) * (size_t)P.w) * P.src_cstride[s] + P.src_coffset[s];
+    float4* st = stage + P.kstart[s] * 2;          // first piece of this source inside a pixel's staging record
+    int px = tid / q, j = tid - px * q;            // one division per source per row
+    const int dpx = 128 / q, dj = 128 - dpx * q;
+    for (int it = tid; it < items; it += 128) {
+      const int x = x0 + px - 1;
+      const bool in = yin && x >= 0 && x < P.w;
+      const float* g = in ? rowp + (size_t)x * P.src_cstride[s] + j * 4 : P.src[s];
+      umma::cp_async16(st + px * (kcr * 2 + 1) + j, g, in ? 16u : 0u);
+      px += dpx; j += dj;
+      if (j >= q) { j -= q; ++px; }
+    }
   }
 }
 
@@ -42,31 +48,76 @@ __device__ __forceinline__ void split8(const float4 a, const float4 b, uint4& hi
   uint32_t h[4], l[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * k]), h1 = __float2bfloat16_rn(v[2 * k + 1]);
-    const float r0 = v[2 * k] - __bfloat162float(h0), r1 = v[2 * k + 1] - __bfloat162float(h1);
-    h[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[k] = umma::pack_bf16(r0, r1);
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+    const float2 hf = __bfloat1622float2(hh);
+    h[k] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[k] = umma::pack_bf16(v[2 * k] - hf.x, v[2 * k + 1] - hf.y);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// staged fp32 row -> hi / lo bf16 records of one ring slot (optionally multiplied by the regional mask fg)
+// staged fp32 row [px][kc] -> hi / lo bf16 records [kc][px] of one ring slot (optionally x regional mask fg)
 __device__ __forceinline__ void tc3_convert_row(const Tc3Params& P, const float4* stage, uint4* slot_hi, uint4* slot_lo,
                                                 int n, int y, int x0, int tid) {
-  const int recs = P.kc_real * T3WP;
-  for (int r = tid; r < recs; r += 128) {
-    float4 a = stage[2 * r], b = stage[2 * r + 1];
+  const int kcr = P.kc_real;
+#pragma unroll 1
+  for (int px = tid; px < T3WP; px += 128) {
+    float f = 1.f;
     if (P.fg != nullptr) {
-      const int px = r % T3WP, x = x0 + px - 1;
-      float f = 0.f;
-      if (y >= 0 && y < P.h && x >= 0 && x < P.w) f = __ldg(P.fg + (size_t)n * P.fg_clip_stride + (size_t)y * P.w + x);
-      a.x *= f; a.y *= f; a.z *= f; a.w *= f; b.x *= f; b.y *= f; b.z *= f; b.w *= f;
+      const int x = x0 + px - 1;
+      f = (y >= 0 && y < P.h && x >= 0 && x < P.w) ? __ldg(P.fg + (size_t)n * P.fg_clip_stride + (size_t)y * P.w + x) : 0.f;
     }
-    uint4 hi, lo;
-    split8(a, b, hi, lo);
-    slot_hi[r] = hi;
-    slot_lo[r] = lo;
+    const float4* sp = stage + px * (kcr * 2 + 1);   // +1: odd pitch keeps the LDS.128 conflict-free
+    for (int kc = 0; kc < kcr; ++kc) {
+      float4 a = sp[2 * kc], b = sp[2 * kc + 1];
+      if (P.fg != nullptr) { a.x *= f; a.y *= f; a.z *= f; a.w *= f; b.x *= f; b.y *= f; b.z *= f; b.w *= f; }
+      uint4 hi, lo;
+      split8(a, b, hi, lo);
+      slot_hi[kc * T3WP + px] = hi;
+      slot_lo[kc * T3WP + px] = lo;
+    }
+  }
+}
+
+// One output row: 9 taps x KC/2 K-steps x 3 split products.  All operand offsets are compile-time multiples of the
+// runtime slot bases / NT, so each tcgen05.mma costs a couple of integer adds on the single issuing thread.
+template <int KC>
+__device__ __forceinline__ void tc3_issue_row(uint64_t dAh, uint64_t dAl, uint64_t dBh, uint64_t dBl, uint32_t s0, uint32_t s1,
+                                              uint32_t s2, uint32_t NT, uint32_t idesc, uint32_t taddr) {
+  const uint32_t ahl = (uint32_t)dAh, ahh = (uint32_t)(dAh >> 32), all_ = (uint32_t)dAl, alh = (uint32_t)(dAl >> 32);
+  const uint32_t bhl = (uint32_t)dBh, bhh = (uint32_t)(dBh >> 32), bll = (uint32_t)dBl, blh = (uint32_t)(dBl >> 32);
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int ky = tap / 3, kx = tap % 3;
+    const uint32_t arow = (ky == 0 ? s0 : ky == 1 ? s1 : s2) + kx;
+#pragma unroll
+    for (int ks = 0; ks < KC / 2; ++ks) {
+      const uint32_t a = arow + 2 * ks * T3WP, b = (uint32_t)(tap * KC + 2 * ks) * NT;
+      const uint64_t dah = umma::desc_advance(ahl, ahh, a), dal = umma::desc_advance(all_, alh, a);
+      const uint64_t dbh = umma::desc_advance(bhl, bhh, b), dbl = umma::desc_advance(bll, blh, b);
+      umma::mma_bf16(taddr, dah, dbh, idesc, (tap | ks) != 0 ? 1u : 0u);
+      umma::mma_bf16(taddr, dal, dbh, idesc, 1u);
+      umma::mma_bf16(taddr, dah, dbl, idesc, 1u);
+    }
+  }
+}
+
+__device__ __noinline__ void tc3_issue_row_generic(uint64_t dAh, uint64_t dAl, uint64_t dBh, uint64_t dBl, uint32_t s0,
+                                                   uint32_t s1, uint32_t s2, uint32_t NT, int KC, uint32_t idesc, uint32_t taddr) {
+  const uint32_t ahl = (uint32_t)dAh, ahh = (uint32_t)(dAh >> 32), all_ = (uint32_t)dAl, alh = (uint32_t)(dAl >> 32);
+  const uint32_t bhl = (uint32_t)dBh, bhh = (uint32_t)(dBh >> 32), bll = (uint32_t)dBl, blh = (uint32_t)(dBl >> 32);
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const int ky = tap / 3, kx = tap - ky * 3;
+    uint32_t a = (ky == 0 ? s0 : ky == 1 ? s1 : s2) + kx, b = (uint32_t)(tap * KC) * NT;
+    for (int ks = 0; ks < KC / 2; ++ks, a += 2 * T3WP, b += 2 * NT) {
+      const uint64_t dah = umma::desc_advance(ahl, ahh, a), dal = umma::desc_advance(all_, alh, a);
+      const uint64_t dbh = umma::desc_advance(bhl, bhh, b), dbl = umma::desc_advance(bll, blh, b);
+      umma::mma_bf16(taddr, dah, dbh, idesc, (tap | ks) != 0 ? 1u : 0u);
+      umma::mma_bf16(taddr, dal, dbh, idesc, 1u);
+      umma::mma_bf16(taddr, dah, dbl, idesc, 1u);
+    }
   }
 }
 
@@ -82,8 +133,8 @@ __global__ void __launch_bounds__(128) conv_tc3_kernel(const Tc3Params P) {
   uint4* sAh = sWl + wrecs;               // [3 slots][KC][130]
   uint4* sAl = sAh + 3 * slot_recs;
   float4* sStage = reinterpret_cast<float4*>(sAl + 3 * slot_recs);   // [kc_real][130][2]
-  float* sBias = reinterpret_cast<float*>(sStage + 2 * P.kc_real * T3WP);
-  float* sWx = sBias + NT;                // extra 2-channel source weights [9][2][NT] (optional)
+  float* sBias = reinterpret_cast<float*>(sStage + (2 * P.kc_real + 1) * T3WP);
+  float* sWx = sBias + ((NT + 31) & ~31);   // extra 2-channel source weights [9][2][NT] (optional); bias padded to 32
   const int tid = threadIdx.x, warp = tid >> 5;
   const int cotile = blockIdx.z % P.ntiles, n = blockIdx.z / P.ntiles;
   const int x0 = blockIdx.x * T3M;
@@ -98,7 +149,7 @@ __global__ void __launch_bounds__(128) conv_tc3_kernel(const Tc3Params P) {
       umma::cp_async16(sWl + i, gwl + i, 16u);
     }
     umma::cp_async_commit();
-    for (int i = tid; i < NT; i += 128) sBias[i] = P.bias[cotile * NT + i];
+    for (int i = tid; i < ((NT + 31) & ~31); i += 128) sBias[i] = (i < NT) ? P.bias[cotile * NT + i] : 0.f;
     if (P.extra != nullptr)
       for (int i = tid; i < 18 * NT; i += 128) sWx[i] = P.w_extra[(size_t)(i / NT) * (P.ntiles * NT) + cotile * NT + (i % NT)];
     for (int kc = P.kc_real; kc < KC; ++kc)  // K padding chunk: zero in every slot, both halves
@@ -131,8 +182,9 @@ __global__ void __launch_bounds__(128) conv_tc3_kernel(const Tc3Params P) {
   umma::fence_after_sync();
   const uint32_t taddr = tmem_base_s;
   const uint32_t idesc = umma::make_idesc_bf16(T3M, NT);
-  const uint32_t aH = umma::smem_u32(sAh), aL = umma::smem_u32(sAl), wH = umma::smem_u32(sWh), wL = umma::smem_u32(sWl);
-  const uint32_t lboA = T3WP * 16, lboB = (uint32_t)NT * 16;
+  // base descriptors (record 0 of each operand region); the issue loop only advances their start addresses
+  const uint64_t dAh = umma::make_desc(umma::smem_u32(sAh), T3WP * 16, 128), dAl = umma::make_desc(umma::smem_u32(sAl), T3WP * 16, 128);
+  const uint64_t dBh = umma::make_desc(umma::smem_u32(sWh), (uint32_t)NT * 16, 128), dBl = umma::make_desc(umma::smem_u32(sWl), (uint32_t)NT * 16, 128);
   uint32_t phase = 0;
   const int x = x0 + tid;
   const bool xvalid = x < P.w;
@@ -150,20 +202,14 @@ __global__ void __launch_bounds__(128) conv_tc3_kernel(const Tc3Params P) {
     umma::cp_async_commit();
     if (tid == 0) {
       umma::fence_after_sync();
-#pragma unroll 1
-      for (int tap = 0; tap < 9; ++tap) {
-        const int ky = tap / 3, kx = tap - ky * 3;
-        const uint32_t aoff = (uint32_t)(((y + ky - 1 + 3) % 3) * slot_recs + kx) * 16;
-        const uint32_t boff = (uint32_t)(tap * KC * NT) * 16;
-        for (int ks = 0; ks < KC / 2; ++ks) {
-          const uint32_t ao = aoff + (uint32_t)(2 * ks) * lboA, bo = boff + (uint32_t)(2 * ks) * lboB;
-          const uint64_t dah = umma::make_desc(aH + ao, lboA, 128), dal = umma::make_desc(aL + ao, lboA, 128);
-          const uint64_t dbh = umma::make_desc(wH + bo, lboB, 128), dbl = umma::make_desc(wL + bo, lboB, 128);
-          umma::mma_bf16(taddr, dah, dbh, idesc, (tap | ks) != 0 ? 1u : 0u);
-          umma::mma_bf16(taddr, dal, dbh, idesc, 1u);
-          umma::mma_bf16(taddr, dah, dbl, idesc, 1u);
-        }
-      }
+      const uint32_t s0 = (uint32_t)(((y - 1 + 3) % 3) * slot_recs), s1 = (uint32_t)(((y + 3) % 3) * slot_recs),
+                     s2 = (uint32_t)(((y + 1 + 3) % 3) * slot_recs);
+      if (KC == 4)
+        tc3_issue_row<4>(dAh, dAl, dBh, dBl, s0, s1, s2, (uint32_t)NT, idesc, taddr);
+      else if (KC == 8)
+        tc3_issue_row<8>(dAh, dAl, dBh, dBl, s0, s1, s2, (uint32_t)NT, idesc, taddr);
+      else
+        tc3_issue_row_generic(dAh, dAl, dBh, dBl, s0, s1, s2, (uint32_t)NT, KC, idesc, taddr);
       umma::mma_commit(&bar);
     }
     // work that does not need the accumulator: flow at this pixel, the 2-channel extra source taps
@@ -265,8 +311,8 @@ __global__ void __launch_bounds__(128) conv_tc3_kernel(const Tc3Params P) {
 }
 
 static size_t tc3_smem_bytes(int kc_real, int kc_total, int nt, bool extra) {
-  return (size_t)(2 * 9 * kc_total * nt + 6 * kc_total * T3WP) * 16 + (size_t)kc_real * T3WP * 32 + (size_t)nt * 4 +
-         (extra ? (size_t)18 * nt * 4 : 0);
+  return (size_t)(2 * 9 * kc_total * nt + 6 * kc_total * T3WP) * 16 + (size_t)(2 * kc_real + 1) * T3WP * 16 +
+         (size_t)((nt + 31) & ~31) * 4 + (extra ? (size_t)(18 * nt + 32) * 4 : 0);
 }
 
 // cout tile for the split kernel: weights are resident twice (hi, lo), so tiles are smaller than conv_tc's

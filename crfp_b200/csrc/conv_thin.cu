@@ -10,38 +10,9 @@
 
 namespace crfp {
 
-__global__ void __launch_bounds__(256) conv_thin_kernel(const ConvParams P) {
-  extern __shared__ __align__(16) float s_w[];  // [9][cin_packed][4]
-  const int nw4 = 9 * P.cin_packed;
-  for (int i = threadIdx.x + threadIdx.y * blockDim.x; i < nw4; i += blockDim.x * blockDim.y)
-    reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(P.weight) + i);
-  __syncthreads();
-
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  const int n = blockIdx.z;
-  if (x >= P.w || y >= P.h) return;
-
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  const int nq = P.cin_packed >> 2;
-#pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int yy = y + ky - 1, xx = x + kx - 1;
-      const float4* wt = reinterpret_cast<const float4*>(s_w) + (size_t)(ky * 3 + kx) * P.cin_packed;
-      for (int q = 0; q < nq; ++q) {
-        const float4 v = load_quad_fg(P, q, n, yy, xx);
-        const float4 w0 = wt[q * 4 + 0], w1 = wt[q * 4 + 1], w2 = wt[q * 4 + 2], w3 = wt[q * 4 + 3];
-        a0 = fmaf(v.x, w0.x, a0); a1 = fmaf(v.x, w0.y, a1); a2 = fmaf(v.x, w0.z, a2); a3 = fmaf(v.x, w0.w, a3);
-        a0 = fmaf(v.y, w1.x, a0); a1 = fmaf(v.y, w1.y, a1); a2 = fmaf(v.y, w1.z, a2); a3 = fmaf(v.y, w1.w, a3);
-        a0 = fmaf(v.z, w2.x, a0); a1 = fmaf(v.z, w2.y, a1); a2 = fmaf(v.z, w2.z, a2); a3 = fmaf(v.z, w2.w, a3);
-        a0 = fmaf(v.w, w3.x, a0); a1 = fmaf(v.w, w3.y, a1); a2 = fmaf(v.w, w3.z, a2); a3 = fmaf(v.w, w3.w, a3);
-      }
-    }
-  }
-  const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias));
-  float v[4] = {a0 + b.x, a1 + b.y, a2 + b.z, a3 + b.w};
+// Shared epilogue of the thin kernels for one output pixel (v = conv + bias, 4 channels).
+__device__ __forceinline__ void thin_epilogue(const ConvParams& P, int n, int y, int x, float e0, float e1, float e2, float e3) {
+  float v[4] = {e0, e1, e2, e3};
   const size_t pix = ((size_t)n * P.h + y) * (size_t)P.w + x;
 
   if (P.epi == EPI_BLEND) {
@@ -113,10 +84,120 @@ __global__ void __launch_bounds__(256) conv_thin_kernel(const ConvParams P) {
   }
 }
 
+__global__ void __launch_bounds__(256) conv_thin_kernel(const ConvParams P) {
+  extern __shared__ __align__(16) float s_w[];  // [9][cin_packed][4]
+  const int nw4 = 9 * P.cin_packed;
+  for (int i = threadIdx.x + threadIdx.y * blockDim.x; i < nw4; i += blockDim.x * blockDim.y)
+    reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(P.weight) + i);
+  __syncthreads();
+
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int n = blockIdx.z;
+  if (x >= P.w || y >= P.h) return;
+
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const int nq = P.cin_packed >> 2;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int yy = y + ky - 1, xx = x + kx - 1;
+      const float4* wt = reinterpret_cast<const float4*>(s_w) + (size_t)(ky * 3 + kx) * P.cin_packed;
+      for (int q = 0; q < nq; ++q) {
+        const float4 v = load_quad_fg(P, q, n, yy, xx);
+        const float4 w0 = wt[q * 4 + 0], w1 = wt[q * 4 + 1], w2 = wt[q * 4 + 2], w3 = wt[q * 4 + 3];
+        a0 = fmaf(v.x, w0.x, a0); a1 = fmaf(v.x, w0.y, a1); a2 = fmaf(v.x, w0.z, a2); a3 = fmaf(v.x, w0.w, a3);
+        a0 = fmaf(v.y, w1.x, a0); a1 = fmaf(v.y, w1.y, a1); a2 = fmaf(v.y, w1.z, a2); a3 = fmaf(v.y, w1.w, a3);
+        a0 = fmaf(v.z, w2.x, a0); a1 = fmaf(v.z, w2.y, a1); a2 = fmaf(v.z, w2.z, a2); a3 = fmaf(v.z, w2.w, a3);
+        a0 = fmaf(v.w, w3.x, a0); a1 = fmaf(v.w, w3.y, a1); a2 = fmaf(v.w, w3.z, a2); a3 = fmaf(v.w, w3.w, a3);
+      }
+    }
+  }
+  const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias));
+  thin_epilogue(P, n, y, x, a0 + b.x, a1 + b.y, a2 + b.z, a3 + b.w);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// v2 for the HR planes (<= 3 input quads): CTA = 32x32 output pixels, 256 threads, each thread owns a 4-pixel COLUMN
+// strip (x = lane, 4 consecutive rows) x 4 output channels.  The (34x34) halo tile of every input quad is staged once
+// in shared memory (coalesced float4 loads, zero padding / regional mask applied by the loader); per (quad, kx) a
+// thread reads its 6-row column (conflict-free LDS.128, reused by the 3 ky taps) and 12 broadcast weight float4s.
+// 16 accumulators, ~54 LDS.128 per 576 FFMA: FFMA bound (the 4-channel convs are ~2x over their HBM time in fp32).
+template <int NQ>
+__global__ void __launch_bounds__(256) conv_thin4_kernel(const ConvParams P) {
+  constexpr int TS = 32, HS = TS + 2, PITCH = HS + 1;
+  extern __shared__ __align__(16) float smem_t4[];
+  float4* s_in = reinterpret_cast<float4*>(smem_t4);            // [NQ][34][35]
+  float4* s_w = s_in + NQ * HS * PITCH;                         // [9][cin_packed]
+  const int tid = threadIdx.x + threadIdx.y * 32;
+  const int n = blockIdx.z;
+  const int x0 = blockIdx.x * TS, y0 = blockIdx.y * TS;
+  for (int i = tid; i < 9 * P.cin_packed; i += 256) s_w[i] = __ldg(reinterpret_cast<const float4*>(P.weight) + i);
+  for (int i = tid; i < NQ * HS * HS; i += 256) {
+    const int q = i / (HS * HS), r = i - q * (HS * HS);
+    const int py = r / HS, px = r - py * HS;
+    s_in[(q * HS + py) * PITCH + px] = load_quad_fg(P, q, n, y0 + py - 1, x0 + px - 1);
+  }
+  __syncthreads();
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      float4 col[6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) col[r] = s_in[(q * HS + 4 * ty + r) * PITCH + tx + kx];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const float4* wt = s_w + (ky * 3 + kx) * P.cin_packed + q * 4;
+        const float4 w0 = wt[0], w1 = wt[1], w2 = wt[2], w3 = wt[3];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float4 v = col[r + ky];
+          acc[r][0] = fmaf(v.x, w0.x, fmaf(v.y, w1.x, fmaf(v.z, w2.x, fmaf(v.w, w3.x, acc[r][0]))));
+          acc[r][1] = fmaf(v.x, w0.y, fmaf(v.y, w1.y, fmaf(v.z, w2.y, fmaf(v.w, w3.y, acc[r][1]))));
+          acc[r][2] = fmaf(v.x, w0.z, fmaf(v.y, w1.z, fmaf(v.z, w2.z, fmaf(v.w, w3.z, acc[r][2]))));
+          acc[r][3] = fmaf(v.x, w0.w, fmaf(v.y, w1.w, fmaf(v.z, w2.w, fmaf(v.w, w3.w, acc[r][3]))));
+        }
+      }
+    }
+  }
+  const int x = x0 + tx;
+  if (x >= P.w) return;
+  const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias));
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int y = y0 + 4 * ty + r;
+    if (y >= P.h) break;
+    thin_epilogue(P, n, y, x, acc[r][0] + b.x, acc[r][1] + b.y, acc[r][2] + b.z, acc[r][3] + b.w);
+  }
+}
+
 int launch_conv_thin(const ConvParams& p, cudaStream_t st) {
   if (p.cout > 4 || p.cout_packed != 4) return CRFP_ERR_BAD_SHAPE;
   if (p.out_mode != CRFP_OUT_NHWC && p.epi == EPI_STD) return CRFP_ERR_UNSUPPORTED;
   dim3 block(32, 8);
+  const int nq = p.qstart[p.nsrc];   // real input quads
+  if (nq >= 1 && nq <= 3 && (long long)p.h * p.w >= 32 * 32) {
+    dim3 grid(ceil_div(p.w, 32), ceil_div(p.h, 32), p.n);
+    const size_t smem4 = ((size_t)nq * 34 * 35 + 9 * p.cin_packed) * 16;
+    if (nq == 1) {
+      conv_thin4_kernel<1><<<grid, block, smem4, st>>>(p);
+    } else if (nq == 2) {
+      cudaFuncSetAttribute(conv_thin4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+      conv_thin4_kernel<2><<<grid, block, smem4, st>>>(p);
+    } else {
+      cudaFuncSetAttribute(conv_thin4_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+      conv_thin4_kernel<3><<<grid, block, smem4, st>>>(p);
+    }
+    return check_launch();
+  }
   dim3 grid(ceil_div(p.w, 32), ceil_div(p.h, 8), p.n);
   const size_t smem = (size_t)9 * p.cin_packed * 4 * sizeof(float);
   if (smem > 48 * 1024) return CRFP_ERR_UNSUPPORTED;

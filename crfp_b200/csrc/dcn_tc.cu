@@ -257,14 +257,15 @@ __global__ void __launch_bounds__(256, 1) dcn_tc3_kernel(const DcnTc3Params P) {
     __syncthreads();
     if (tid == 0) {
       umma::fence_after_sync();
-      const uint32_t ah = umma::smem_u32(sAh), al = umma::smem_u32(sAl);
-      const uint32_t bh = umma::smem_u32(sBh) + (uint32_t)(half * D3KH) * (32 * 16);
-      const uint32_t bl = umma::smem_u32(sBl) + (uint32_t)(half * D3KH) * (32 * 16);
-#pragma unroll 1
+      const uint64_t dAh = umma::make_desc(umma::smem_u32(sAh), DAP * 16, 128), dAl = umma::make_desc(umma::smem_u32(sAl), DAP * 16, 128);
+      const uint64_t dBh = umma::make_desc(umma::smem_u32(sBh) + (uint32_t)(half * D3KH) * (32 * 16), 32 * 16, 128);
+      const uint64_t dBl = umma::make_desc(umma::smem_u32(sBl) + (uint32_t)(half * D3KH) * (32 * 16), 32 * 16, 128);
+      const uint32_t ahl = (uint32_t)dAh, ahh = (uint32_t)(dAh >> 32), all_ = (uint32_t)dAl, alh = (uint32_t)(dAl >> 32);
+      const uint32_t bhl = (uint32_t)dBh, bhh = (uint32_t)(dBh >> 32), bll = (uint32_t)dBl, blh = (uint32_t)(dBl >> 32);
+#pragma unroll
       for (int ks = 0; ks < D3KH / 2; ++ks) {
-        const uint32_t ao = (uint32_t)(2 * ks) * (DAP * 16), bo = (uint32_t)(2 * ks) * (32 * 16);
-        const uint64_t dah = umma::make_desc(ah + ao, DAP * 16, 128), dal = umma::make_desc(al + ao, DAP * 16, 128);
-        const uint64_t dbh = umma::make_desc(bh + bo, 32 * 16, 128), dbl = umma::make_desc(bl + bo, 32 * 16, 128);
+        const uint64_t dah = umma::desc_advance(ahl, ahh, 2 * ks * DAP), dal = umma::desc_advance(all_, alh, 2 * ks * DAP);
+        const uint64_t dbh = umma::desc_advance(bhl, bhh, 2 * ks * 32), dbl = umma::desc_advance(bll, blh, 2 * ks * 32);
         umma::mma_bf16(taddr, dah, dbh, idesc, (half | ks) != 0 ? 1u : 0u);
         umma::mma_bf16(taddr, dal, dbh, idesc, 1u);
         umma::mma_bf16(taddr, dah, dbl, idesc, 1u);

@@ -27,6 +27,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;                // layout_type (bits 61..63) = 0: SWIZZLE_NONE
 }
 
+// A descriptor whose start address is `recs` 16-byte records past the one encoded in (lo0, hi): only the low word
+// changes (start-address field, 16-byte units), so the MMA issue loop is one integer add per operand.
+__device__ __forceinline__ uint64_t desc_advance(uint32_t lo0, uint32_t hi, uint32_t recs) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo0 + recs), "r"(hi));
+  return d;
+}
+
 // ---- instruction descriptor for kind::f16, BF16 x BF16 -> F32, both operands K-major
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4)                      // c_format = F32

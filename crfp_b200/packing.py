@@ -107,7 +107,7 @@ def pack_conv_tc(weight: torch.Tensor, bias: torch.Tensor, c_list, ci_lo: int = 
 
 
 def _tc3_smem_bytes(kc_real, kc_total, nt):
-    return (2 * 9 * kc_total * nt + 6 * kc_total * 130) * 16 + kc_real * 130 * 32 + nt * 4 + 18 * nt * 4
+    return (2 * 9 * kc_total * nt + 6 * kc_total * 130) * 16 + (2 * kc_real + 1) * 130 * 16 + (nt + 31) // 32 * 32 * 4 + (18 * nt + 32) * 4
 
 
 def tc3_cout_tile(cout: int, cin: int):

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for DT in bf16 f32; do
-timeout 600 python bench.py --workload R-lit --frames 20 --steps 3 --warmup 3 --dtype $DT --no-cpu-baseline --no-e2e > gpurun_out/quick_$DT.log 2>&1
+for DT in tc fp32; do
+timeout 600 python bench.py --workload R-lit --frames 20 --steps 3 --warmup 3 --precision $DT --no-cpu-baseline --no-e2e > gpurun_out/quick_$DT.log 2>&1
 python - <<PY
 import json
 try:
@@ -11,5 +11,5 @@ except Exception as e:
     print('$DT failed', e); print(open('gpurun_out/quick_$DT.log').read()[-1500:])
 PY
 done
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bf16.csv python bench.py --workload R-lit --frames 3 --steps 1 --warmup 1 --dtype bf16 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launch_bf16.log 2>&1
-wc -l gpurun_out/launches_bf16.csv
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_tc.csv python bench.py --workload R-lit --frames 3 --steps 1 --warmup 1 --precision tc --no-cpu-baseline --no-e2e > gpurun_out/ncu_launch_tc.log 2>&1
+wc -l gpurun_out/launches_tc.csv
