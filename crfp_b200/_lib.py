@@ -135,11 +135,13 @@ SYMBOLS = {
     "crfp_launch_count_reset": (None, []),
     "crfp_check_device": (C.c_int, []),
     "crfp_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crfp_selftest_umma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "crfp_conv3x3_fwd": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "crfp_conv3x3_tc_fwd": (C.c_int, [C.POINTER(ConvTcDesc), C.c_void_p]),
     "crfp_tc_cout_tile": (C.c_int, [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "crfp_sizeof_conv_tc_desc": (C.c_size_t, []),
     "crfp_conv3x3_tc3_fwd": (C.c_int, [C.POINTER(ConvTc3Desc), C.c_void_p]),
+    "crfp_conv3x3_tc3_trace": (C.c_int, [C.POINTER(ConvTc3Desc), C.c_void_p, C.c_void_p]),
     "crfp_tc3_cout_tile": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "crfp_sizeof_conv_tc3_desc": (C.c_size_t, []),
     "crfp_conv_cin_packed": (C.c_int, [C.c_int, C.POINTER(C.c_int32)]),

@@ -84,7 +84,7 @@ __device__ __forceinline__ void tc3_convert_row(const Tc3Params& P, const float4
 // runtime slot bases / NT, so each tcgen05.mma costs a couple of integer adds on the single issuing thread.
 template <int KC>
 __device__ __forceinline__ void tc3_issue_row(uint64_t dAh, uint64_t dAl, uint64_t dBh, uint64_t dBl, uint32_t s0, uint32_t s1,
-                                              uint32_t s2, uint32_t NT, uint32_t idesc, uint32_t taddr) {
+                                              uint32_t s2, uint32_t NT, uint32_t idesc, uint32_t taddr, uint32_t leader) {
   const uint32_t ahl = (uint32_t)dAh, ahh = (uint32_t)(dAh >> 32), all_ = (uint32_t)dAl, alh = (uint32_t)(dAl >> 32);
   const uint32_t bhl = (uint32_t)dBh, bhh = (uint32_t)(dBh >> 32), bll = (uint32_t)dBl, blh = (uint32_t)(dBl >> 32);
 #pragma unroll
@@ -104,7 +104,7 @@ __device__ __forceinline__ void tc3_issue_row(uint64_t dAh, uint64_t dAl, uint64
 }
 
 __device__ __noinline__ void tc3_issue_row_generic(uint64_t dAh, uint64_t dAl, uint64_t dBh, uint64_t dBl, uint32_t s0,
-                                                   uint32_t s1, uint32_t s2, uint32_t NT, int KC, uint32_t idesc, uint32_t taddr) {
+                                                   uint32_t s1, uint32_t s2, uint32_t NT, int KC, uint32_t idesc, uint32_t taddr, uint32_t leader) {
   const uint32_t ahl = (uint32_t)dAh, ahh = (uint32_t)(dAh >> 32), all_ = (uint32_t)dAl, alh = (uint32_t)(dAl >> 32);
   const uint32_t bhl = (uint32_t)dBh, bhh = (uint32_t)(dBh >> 32), bll = (uint32_t)dBl, blh = (uint32_t)(dBl >> 32);
 #pragma unroll 1
@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(128) conv_tc3_kernel(const Tc3Params P) {
   const int KC = P.kc_total, NT = P.nt;
   const int wrecs = 9 * KC * NT;          // records per weight half
   const int slot_recs = KC * T3WP;        // records per ring slot half
+  const long long t_start = clock64();
   uint4* sWh = reinterpret_cast<uint4*>(smem);
   uint4* sWl = sWh + wrecs;
   uint4* sAh = sWl + wrecs;               // [3 slots][KC][130]
@@ -135,7 +136,8 @@ __global__ void __launch_bounds__(128) conv_tc3_kernel(const Tc3Params P) {
   float4* sStage = reinterpret_cast<float4*>(sAl + 3 * slot_recs);   // [kc_real][130][2]
   float* sBias = reinterpret_cast<float*>(sStage + (2 * P.kc_real + 1) * T3WP);
   float* sWx = sBias + ((NT + 31) & ~31);   // extra 2-channel source weights [9][2][NT] (optional); bias padded to 32
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform (keeps the MMA issue path uniform)
   const int cotile = blockIdx.z % P.ntiles, n = blockIdx.z / P.ntiles;
   const int x0 = blockIdx.x * T3M;
   const int y_begin = blockIdx.y * P.rows_per_cta;
@@ -189,27 +191,35 @@ __global__ void __launch_bounds__(128) conv_tc3_kernel(const Tc3Params P) {
   const int x = x0 + tid;
   const bool xvalid = x < P.w;
 
+  const bool trace = (P.dbg != nullptr) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
+  if (trace) { P.dbg[0] = t_start; P.dbg[1] = clock64(); }
   for (int y = y_begin; y < y_end; ++y) {
+    long long* tr = trace ? P.dbg + 8 * (y - y_begin + 1) : nullptr;
+    if (tr) tr[0] = clock64();
     umma::cp_async_wait<0>();
     __syncthreads();  // staged row y+1 is visible to everyone; MMA(y-1) has been waited for by all threads
+    if (tr) tr[1] = clock64();
     {
       const int sl = (y + 1 + 3) % 3;
       tc3_convert_row(P, sStage, sAh + sl * slot_recs, sAl + sl * slot_recs, n, y + 1, x0, tid);
     }
     umma::fence_proxy_async();
     __syncthreads();
+    if (tr) tr[2] = clock64();
     if (y + 1 < y_end) tc3_stage_row(P, sStage, n, y + 2, x0, tid);
     umma::cp_async_commit();
-    if (tid == 0) {
+    if (tr) tr[3] = clock64();
+    if (warp == 0 && umma::elect_one()) {   // warp-uniform branch + elect.sync: one thread, uniform datapath
       umma::fence_after_sync();
+      const uint32_t leader = 1u;
       const uint32_t s0 = (uint32_t)(((y - 1 + 3) % 3) * slot_recs), s1 = (uint32_t)(((y + 3) % 3) * slot_recs),
                      s2 = (uint32_t)(((y + 1 + 3) % 3) * slot_recs);
       if (KC == 4)
-        tc3_issue_row<4>(dAh, dAl, dBh, dBl, s0, s1, s2, (uint32_t)NT, idesc, taddr);
+        tc3_issue_row<4>(dAh, dAl, dBh, dBl, s0, s1, s2, (uint32_t)NT, idesc, taddr, leader);
       else if (KC == 8)
-        tc3_issue_row<8>(dAh, dAl, dBh, dBl, s0, s1, s2, (uint32_t)NT, idesc, taddr);
+        tc3_issue_row<8>(dAh, dAl, dBh, dBl, s0, s1, s2, (uint32_t)NT, idesc, taddr, leader);
       else
-        tc3_issue_row_generic(dAh, dAl, dBh, dBl, s0, s1, s2, (uint32_t)NT, KC, idesc, taddr);
+        tc3_issue_row_generic(dAh, dAl, dBh, dBl, s0, s1, s2, (uint32_t)NT, KC, idesc, taddr, leader);
       umma::mma_commit(&bar);
     }
     // work that does not need the accumulator: flow at this pixel, the 2-channel extra source taps
@@ -226,9 +236,11 @@ __global__ void __launch_bounds__(128) conv_tc3_kernel(const Tc3Params P) {
                       : make_float2(0.f, 0.f);
       }
     }
+    if (tr) tr[4] = clock64();
     umma::mbar_wait(&bar, phase);
     phase ^= 1;
     umma::fence_after_sync();
+    if (tr) tr[5] = clock64();
 
     for (int c0 = 0; c0 < NT; c0 += 32) {
       float v[32];
@@ -305,6 +317,7 @@ __global__ void __launch_bounds__(128) conv_tc3_kernel(const Tc3Params P) {
       }
     }
     umma::fence_before_sync();
+    if (tr) tr[6] = clock64();
   }
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(taddr, ncols);
@@ -381,7 +394,7 @@ extern "C" int crfp_tc3_cout_tile(int cout, int cin, int32_t* nt, int32_t* ntile
   return CRFP_OK;
 }
 
-extern "C" int crfp_conv3x3_tc3_fwd(const crfp_conv_tc3_desc* d, crfp_stream stream) {
+static int tc3_fwd_impl(const crfp_conv_tc3_desc* d, long long* trace, crfp_stream stream) {
   if (!d) return CRFP_ERR_NULL;
   if (d->n < 0 || d->h <= 0 || d->w <= 0 || d->cout <= 0) return CRFP_ERR_BAD_SHAPE;
   if ((long long)d->n * d->h * d->w == 0) return CRFP_OK;
@@ -407,7 +420,17 @@ extern "C" int crfp_conv3x3_tc3_fwd(const crfp_conv_tc3_desc* d, crfp_stream str
   p.flow = d->flow; p.head_split = d->head_split; p.head_mag = d->head_mag; p.post_scale = d->post_scale;
   if (d->act == CRFP_ACT_DCN_HEAD && !d->flow) return CRFP_ERR_NULL;
   if (d->out_kind == CRFP_TC_OUT_SHUFFLE_F32 && (d->shuffle_r < 1 || d->cout % (d->shuffle_r * d->shuffle_r))) return CRFP_ERR_BAD_SHAPE;
+  p.dbg = trace;
   return launch_conv_tc3(p, (cudaStream_t)stream);
 }
+
+extern "C" int crfp_conv3x3_tc3_fwd(const crfp_conv_tc3_desc* d, crfp_stream stream) { return tc3_fwd_impl(d, nullptr, stream); }
+extern "C" int crfp_conv3x3_tc3_trace(const crfp_conv_tc3_desc* d, long long* trace, crfp_stream stream) {
+  if (!trace) return CRFP_ERR_NULL;
+  return tc3_fwd_impl(d, trace, stream);
+}
+
+// profiling aid: same as crfp_conv3x3_tc3_fwd plus a per-phase clock64 trace of CTA (0,0,0) into `trace` (device int64
+// [rows_per_cta+1][8]: row r+1 = {loop top, row staged, converted+synced, next row issued, MMAs issued, MMAs done, epilogue done})
 
 extern "C" size_t crfp_sizeof_conv_tc3_desc(void) { return sizeof(crfp_conv_tc3_desc); }

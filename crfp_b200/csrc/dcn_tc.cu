@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(256, 1) dcn_tc3_kernel(const DcnTc3Params P) {
   uint4* sBl = sBh + DKC * 32;
   uint4* sAh = sBl + DKC * 32;                   // [18][129]
   uint4* sAl = sAh + D3KH * DAP;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int tiles_x = (P.w + DTW - 1) / DTW;
   const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
   const int n = blockIdx.y;
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(256, 1) dcn_tc3_kernel(const DcnTc3Params P) {
     if (half == 0) umma::cp_async_wait<0>();
     umma::fence_proxy_async();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && umma::elect_one()) {
       umma::fence_after_sync();
       const uint64_t dAh = umma::make_desc(umma::smem_u32(sAh), DAP * 16, 128), dAl = umma::make_desc(umma::smem_u32(sAl), DAP * 16, 128);
       const uint64_t dBh = umma::make_desc(umma::smem_u32(sBh) + (uint32_t)(half * D3KH) * (32 * 16), 32 * 16, 128);

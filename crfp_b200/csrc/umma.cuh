@@ -30,9 +30,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 // A descriptor whose start address is `recs` 16-byte records past the one encoded in (lo0, hi): only the low word
 // changes (start-address field, 16-byte units), so the MMA issue loop is one integer add per operand.
 __device__ __forceinline__ uint64_t desc_advance(uint32_t lo0, uint32_t hi, uint32_t recs) {
-  uint64_t d;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo0 + recs), "r"(hi));
-  return d;
+  return ((uint64_t)hi << 32) | (uint64_t)(lo0 + recs);   // plain integer ops: stays in the uniform datapath
 }
 
 // ---- instruction descriptor for kind::f16, BF16 x BF16 -> F32, both operands K-major
@@ -69,6 +67,42 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Warp-uniform issue: the WHOLE warp executes the call with warp-uniform operands (so the compiler keeps the
+// descriptors in uniform registers — no per-MMA R2UR traffic) and only the lane with `leader != 0` issues.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 r;\n\t"
+      "elect.sync r|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void mma_bf16_lead(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_lead(uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(leader)
       : "memory");
 }
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed

@@ -73,3 +73,54 @@ extern "C" int crfp_selftest_umma(int rowsA, int K, int N, int shift, const void
                                                               K, N, shift);
   return check_launch();
 }
+
+// ---- micro-benchmark: cycles per tcgen05.mma (M128 x N x K16, bf16, no-swizzle K-major operands) issued back to
+// back by one thread with precomputed descriptors; used to size the conv kernels' tiles.
+namespace crfp {
+__global__ void __launch_bounds__(128) umma_rate_kernel(int N, int reps, long long* out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint4* s = reinterpret_cast<uint4*>(smem);
+  for (int i = tid; i < (2 * 136 + 2 * 256) ; i += 128) s[i] = make_uint4(0u, 0u, 0u, 0u);
+  uint32_t ncols = 32;
+  while ((int)ncols < N) ncols <<= 1;
+  if (warp == 0) umma::tmem_alloc(&tmem_base, ncols);
+  if (tid == 0) { umma::mbar_init(&bar, 1); umma::fence_mbar_init(); }
+  umma::fence_proxy_async();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t taddr = tmem_base;
+  long long t0 = 0, t1 = 0;
+  if (tid == 0) {
+    const uint32_t idesc = umma::make_idesc_bf16(128, N);
+    const uint64_t da0 = umma::make_desc(umma::smem_u32(s), 136 * 16, 128);
+    const uint64_t da1 = umma::make_desc(umma::smem_u32(s) + 16, 136 * 16, 128);
+    const uint64_t db = umma::make_desc(umma::smem_u32(s + 2 * 136), (uint32_t)N * 16, 128);
+    t0 = clock64();
+    for (int r = 0; r < reps; r += 2) {
+      umma::mma_bf16(taddr, da0, db, idesc, 1u);
+      umma::mma_bf16(taddr, da1, db, idesc, 1u);
+    }
+    umma::mma_commit(&bar);
+  }
+  umma::mbar_wait(&bar, 0);
+  if (tid == 0) {
+    t1 = clock64();
+    out[blockIdx.x] = t1 - t0;
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(taddr, ncols);
+}
+}  // namespace crfp
+
+extern "C" int crfp_selftest_umma_rate(int N, int reps, int ctas, long long* cycles_out, crfp_stream stream) {
+  using namespace crfp;
+  if (!cycles_out || N % 16 || N < 16 || N > 256 || reps < 2 || ctas < 1) return CRFP_ERR_BAD_SHAPE;
+  const size_t smem = (size_t)(2 * 136 + 2 * 256) * 16;
+  umma_rate_kernel<<<ctas, 128, smem, (cudaStream_t)stream>>>(N, reps, cycles_out);
+  return check_launch();
+}

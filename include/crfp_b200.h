@@ -65,6 +65,10 @@ int crfp_check_device(void);
  * row-major in HBM, fp32 D[128][N]; exercises the shifted-window operand addressing of the conv kernels. */
 int crfp_selftest_umma(int rowsA, int K, int N, int shift, const void* A, const void* B, float* D, crfp_stream stream);
 
+/* micro-benchmark: `ctas` CTAs each issue `reps` back-to-back tcgen05.mma (M128 x N x K16 bf16) from one thread;
+ * cycles_out[cta] = SM cycles from first issue to completion (device buffer of `ctas` int64). */
+int crfp_selftest_umma_rate(int N, int reps, int ctas, long long* cycles_out, crfp_stream stream);
+
 /* ------------------------------------------------------------------ activations / epilogues */
 enum {
   CRFP_ACT_NONE = 0,
@@ -215,6 +219,9 @@ typedef struct {
   float head_mag;
 } crfp_conv_tc3_desc;
 int crfp_conv3x3_tc3_fwd(const crfp_conv_tc3_desc* d, crfp_stream stream);
+/* profiling aid: same launch + a clock64 trace of CTA (0,0,0): trace[0..1] = kernel start / loop start, then per row
+ * trace[8*(r+1) + k], k = loop top, row staged, converted, next row issued, MMAs issued, MMAs done, epilogue done */
+int crfp_conv3x3_tc3_trace(const crfp_conv_tc3_desc* d, long long* trace, crfp_stream stream);
 /* cout tiling for `cin` tensor-core input channels (multiple of 8); CRFP_ERR_UNSUPPORTED when cin is too large for
  * the shared-memory resident rings (cin > 64) */
 int crfp_tc3_cout_tile(int cout, int cin, int32_t* nt, int32_t* ntiles);
