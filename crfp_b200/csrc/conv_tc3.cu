@@ -11,6 +11,8 @@
 // once with cp.async into an fp32 staging buffer, then split into the hi / lo bf16 rings by all threads while
 // the previous row's MMAs and epilogue are in flight.  A 2-channel fp32 "extra" source (the optical flow input of
 // dcn_block.0) is convolved on the CUDA cores in the epilogue instead of being padded into the K dimension.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -119,6 +121,80 @@ __device__ __noinline__ void tc3_issue_row_generic(uint64_t dAh, uint64_t dAl, u
       umma::mma_bf16(taddr, dah, dbl, idesc, 1u);
     }
   }
+}
+
+// Epilogue of one 32-channel chunk of one pixel: bias, 2-channel extra source, activation / DCN head, residual,
+// post-scale, store (fp32 NHWC segments or pixel shuffle).  Shared by both kernel variants.
+__device__ __forceinline__ void tc3_epilogue_chunk(const Tc3Params& P, float* v, const float* sBiasC, const float* sWxC,
+                                                   const float2* ex, float2 fl, int NT, int cbase, int nvalid, int n, int y,
+                                                   int x, size_t pix) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += sBiasC[i];
+      if (sWxC != nullptr) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const float4* wx0 = reinterpret_cast<const float4*>(sWxC + (tap * 2) * NT);
+          const float4* wx1 = reinterpret_cast<const float4*>(sWxC + (tap * 2 + 1) * NT);
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 a = wx0[i4], b = wx1[i4];
+            v[4 * i4 + 0] = fmaf(ex[tap].x, a.x, fmaf(ex[tap].y, b.x, v[4 * i4 + 0]));
+            v[4 * i4 + 1] = fmaf(ex[tap].x, a.y, fmaf(ex[tap].y, b.y, v[4 * i4 + 1]));
+            v[4 * i4 + 2] = fmaf(ex[tap].x, a.z, fmaf(ex[tap].y, b.z, v[4 * i4 + 2]));
+            v[4 * i4 + 3] = fmaf(ex[tap].x, a.w, fmaf(ex[tap].y, b.w, v[4 * i4 + 3]));
+          }
+        }
+      }
+      if (P.act == CRFP_ACT_LRELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = lrelu01(v[i]);
+      } else if (P.act == CRFP_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+      } else if (P.act == CRFP_ACT_DCN_HEAD) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int cc = cbase + i;
+          v[i] = (cc < P.head_split) ? P.head_mag * tanhf(v[i]) + ((cc & 1) ? fl.x : fl.y) : sigmoidf_(v[i]);
+        }
+      }
+      if (P.residual != nullptr) {
+        const float* rp = P.residual + pix * P.res_cstride + P.res_coffset + cbase;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (4 * j >= nvalid) break;
+          const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + 4 * j));
+          v[4 * j] += rv.x; v[4 * j + 1] += rv.y; v[4 * j + 2] += rv.z; v[4 * j + 3] += rv.w;
+        }
+      }
+      if (P.post_scale != 1.f) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= P.post_scale;
+      }
+      if (P.out_kind == TC_OUT_F32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int cc = cbase + 4 * j;
+          if (4 * j >= nvalid) break;
+          int seg = 0, cl = cc;
+          if (P.ndst > 1 && cc >= P.dst_c[0]) { seg = 1; cl = cc - P.dst_c[0]; }
+          float* op = reinterpret_cast<float*>(P.dst[seg]) + pix * P.dst_cstride[seg] + P.dst_coffset[seg] + cl;
+          *reinterpret_cast<float4*>(op) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      } else {  // TC_OUT_SHUFFLE_F32
+        const int r_ = P.shuffle_r, rr = r_ * r_;
+        const int Wo = P.w * r_;
+        float* ob = reinterpret_cast<float*>(P.dst[0]);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int cc = cbase + i;
+          if (i >= nvalid) break;
+          const int o = cc / rr, sub = cc - o * rr;
+          const int dy = sub / r_, dx = sub - dy * r_;
+          const size_t opix = ((size_t)n * (P.h * r_) + (y * r_ + dy)) * (size_t)Wo + (x * r_ + dx);
+          ob[opix * P.dst_cstride[0] + P.dst_coffset[0] + o] = v[i];
+        }
+      }
 }
 
 __global__ void __launch_bounds__(128) conv_tc3_kernel(const Tc3Params P) {
@@ -248,79 +324,201 @@ __global__ void __launch_bounds__(128) conv_tc3_kernel(const Tc3Params P) {
       const int cbase = cotile * NT + c0;
       if (!xvalid || cbase >= P.cout) continue;
       const int nvalid = min(min(32, NT - c0), P.cout - cbase);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] += sBias[c0 + i];
-      if (P.extra != nullptr) {
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const float4* wx0 = reinterpret_cast<const float4*>(sWx + (tap * 2) * NT + c0);
-          const float4* wx1 = reinterpret_cast<const float4*>(sWx + (tap * 2 + 1) * NT + c0);
-#pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 a = wx0[i4], b = wx1[i4];
-            v[4 * i4 + 0] = fmaf(ex[tap].x, a.x, fmaf(ex[tap].y, b.x, v[4 * i4 + 0]));
-            v[4 * i4 + 1] = fmaf(ex[tap].x, a.y, fmaf(ex[tap].y, b.y, v[4 * i4 + 1]));
-            v[4 * i4 + 2] = fmaf(ex[tap].x, a.z, fmaf(ex[tap].y, b.z, v[4 * i4 + 2]));
-            v[4 * i4 + 3] = fmaf(ex[tap].x, a.w, fmaf(ex[tap].y, b.w, v[4 * i4 + 3]));
-          }
-        }
-      }
-      if (P.act == CRFP_ACT_LRELU) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = lrelu01(v[i]);
-      } else if (P.act == CRFP_ACT_RELU) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-      } else if (P.act == CRFP_ACT_DCN_HEAD) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int cc = cbase + i;
-          v[i] = (cc < P.head_split) ? P.head_mag * tanhf(v[i]) + ((cc & 1) ? fl.x : fl.y) : sigmoidf_(v[i]);
-        }
-      }
-      if (P.residual != nullptr) {
-        const float* rp = P.residual + pix * P.res_cstride + P.res_coffset + cbase;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (4 * j >= nvalid) break;
-          const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + 4 * j));
-          v[4 * j] += rv.x; v[4 * j + 1] += rv.y; v[4 * j + 2] += rv.z; v[4 * j + 3] += rv.w;
-        }
-      }
-      if (P.post_scale != 1.f) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= P.post_scale;
-      }
-      if (P.out_kind == TC_OUT_F32) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int cc = cbase + 4 * j;
-          if (4 * j >= nvalid) break;
-          int seg = 0, cl = cc;
-          if (P.ndst > 1 && cc >= P.dst_c[0]) { seg = 1; cl = cc - P.dst_c[0]; }
-          float* op = reinterpret_cast<float*>(P.dst[seg]) + pix * P.dst_cstride[seg] + P.dst_coffset[seg] + cl;
-          *reinterpret_cast<float4*>(op) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-      } else {  // TC_OUT_SHUFFLE_F32
-        const int r_ = P.shuffle_r, rr = r_ * r_;
-        const int Wo = P.w * r_;
-        float* ob = reinterpret_cast<float*>(P.dst[0]);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int cc = cbase + i;
-          if (i >= nvalid) break;
-          const int o = cc / rr, sub = cc - o * rr;
-          const int dy = sub / r_, dx = sub - dy * r_;
-          const size_t opix = ((size_t)n * (P.h * r_) + (y * r_ + dy)) * (size_t)Wo + (x * r_ + dx);
-          ob[opix * P.dst_cstride[0] + P.dst_coffset[0] + o] = v[i];
-        }
-      }
+      tc3_epilogue_chunk(P, v, sBias + c0, P.extra != nullptr ? sWx + c0 : nullptr, ex, fl, NT, cbase, nvalid, n, y, x, pix);
     }
     umma::fence_before_sync();
     if (tr) tr[6] = clock64();
   }
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(taddr, ncols);
+}
+
+
+// =====================================================================================================================
+// Warp-specialised, software-pipelined variant (default): 384 threads = 4 epilogue warps (TMEM lanes 0..127) + 1 MMA
+// warp + 7 producer warps.  Producers load fp32 rows straight from global (coalesced LDG.128), split them hi/lo and
+// store them into a 4-slot ring of UMMA operand rows; the MMA warp issues each output row's 9 x KC/2 x 3 tcgen05.mma
+// into one of two TMEM accumulators; the epilogue warps drain the other accumulator.  Stages meet only through
+// mbarriers: full[slot] (producers -> MMA), acc_full[buf] (tcgen05.commit -> epilogue and, as "rows <= v are
+// consumed", -> producers), acc_empty[buf] (epilogue -> MMA).  All three stages of consecutive rows overlap.
+constexpr int WS_EPI = 128, WS_NPROD = 224, WS_THREADS = 384, WS_SLOTS = 4;
+
+__device__ __forceinline__ void ws_produce_row(const Tc3Params& P, uint4* hi, uint4* lo, int n, int y, int x0, int ptid) {
+  const bool yin = (y >= 0 && y < P.h);
+#pragma unroll 1
+  for (int s = 0; s < P.nsrc; ++s) {
+    const int cps = P.src_c[s] >> 3;  // 8-channel records per pixel of this source
+    const int nrec = T3WP * cps;
+    const float* rowp = P.src[s] + (((size_t)n * P.h + (yin ? y : 0)) * (size_t)P.w) * P.src_cstride[s] + P.src_coffset[s];
+    const int kbase = P.kstart[s] * T3WP;
+#pragma unroll 1
+    for (int base = ptid; base < nrec; base += 3 * WS_NPROD) {
+      float4 a[3], b[3];
+      int dst[3];
+      float f[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int id = base + k * WS_NPROD;
+        dst[k] = -1;
+        a[k] = b[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        f[k] = 1.f;
+        if (id < nrec) {
+          const int px = id / cps, j = id - px * cps;
+          const int x = x0 + px - 1;
+          dst[k] = kbase + j * T3WP + px;
+          if (yin && x >= 0 && x < P.w) {
+            const float4* g = reinterpret_cast<const float4*>(rowp + (size_t)x * P.src_cstride[s] + j * 8);
+            a[k] = __ldg(g);
+            b[k] = __ldg(g + 1);
+            if (P.fg != nullptr) f[k] = __ldg(P.fg + (size_t)n * P.fg_clip_stride + (size_t)y * P.w + x);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (dst[k] < 0) continue;
+        if (P.fg != nullptr) {
+          a[k].x *= f[k]; a[k].y *= f[k]; a[k].z *= f[k]; a[k].w *= f[k];
+          b[k].x *= f[k]; b[k].y *= f[k]; b[k].z *= f[k]; b[k].w *= f[k];
+        }
+        uint4 h, l;
+        split8(a[k], b[k], h, l);
+        hi[dst[k]] = h;
+        lo[dst[k]] = l;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Params P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t full_bar[WS_SLOTS], accf_bar[2], acce_bar[2];
+  __shared__ uint32_t tmem_base_s;
+  const int KC = P.kc_total, NT = P.nt;
+  const int wrecs = 9 * KC * NT;
+  const int slot_recs = KC * T3WP;
+  uint4* sWh = reinterpret_cast<uint4*>(smem);
+  uint4* sWl = sWh + wrecs;
+  uint4* sAh = sWl + wrecs;                 // [4 slots][KC][130]
+  uint4* sAl = sAh + WS_SLOTS * slot_recs;
+  float* sBias = reinterpret_cast<float*>(sAl + WS_SLOTS * slot_recs);
+  float* sWx = sBias + ((NT + 31) & ~31);
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int cotile = blockIdx.z % P.ntiles, n = blockIdx.z / P.ntiles;
+  const int x0 = blockIdx.x * T3M;
+  const int y_begin = blockIdx.y * P.rows_per_cta;
+  const int y_end = min(P.h, y_begin + P.rows_per_cta);
+  const int rows_out = y_end - y_begin;
+
+  {
+    const uint4* gwh = reinterpret_cast<const uint4*>(P.weight_hi) + (size_t)cotile * wrecs;
+    const uint4* gwl = reinterpret_cast<const uint4*>(P.weight_lo) + (size_t)cotile * wrecs;
+    for (int i = tid; i < wrecs; i += WS_THREADS) {
+      umma::cp_async16(sWh + i, gwh + i, 16u);
+      umma::cp_async16(sWl + i, gwl + i, 16u);
+    }
+    umma::cp_async_commit();
+    for (int i = tid; i < ((NT + 31) & ~31); i += WS_THREADS) sBias[i] = (i < NT) ? P.bias[cotile * NT + i] : 0.f;
+    if (P.extra != nullptr)
+      for (int i = tid; i < 18 * NT; i += WS_THREADS) sWx[i] = P.w_extra[(size_t)(i / NT) * (P.ntiles * NT) + cotile * NT + (i % NT)];
+    for (int kc = P.kc_real; kc < KC; ++kc)
+      for (int i = tid; i < WS_SLOTS * T3WP; i += WS_THREADS) {
+        sAh[(i / T3WP) * slot_recs + kc * T3WP + (i % T3WP)] = make_uint4(0u, 0u, 0u, 0u);
+        sAl[(i / T3WP) * slot_recs + kc * T3WP + (i % T3WP)] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    umma::cp_async_wait<0>();
+  }
+  uint32_t ncols = 32;
+  while ((int)ncols < NT) ncols <<= 1;
+  if (warp == 4) umma::tmem_alloc(&tmem_base_s, 2 * ncols);
+  if (tid == 0) {
+    for (int i = 0; i < WS_SLOTS; ++i) umma::mbar_init(&full_bar[i], WS_NPROD);
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&accf_bar[i], 1); umma::mbar_init(&acce_bar[i], WS_EPI); }
+    umma::fence_mbar_init();
+  }
+  umma::fence_proxy_async();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t taddr = tmem_base_s;
+
+  if (warp >= 5) {
+    // ------------------------------------------------------------------ producers
+    const int ptid = tid - 160;
+    for (int u = 0; u < rows_out + 2; ++u) {
+      const int slot = u & (WS_SLOTS - 1);
+      if (u >= WS_SLOTS) umma::mbar_wait_safe(&accf_bar[(u - 4) & 1], (uint32_t)(((u - 4) >> 1) & 1));
+      ws_produce_row(P, sAh + slot * slot_recs, sAl + slot * slot_recs, n, y_begin - 1 + u, x0, ptid);
+      umma::fence_proxy_async();
+      umma::mbar_arrive(&full_bar[slot]);
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma::make_idesc_bf16(T3M, NT);
+    const uint64_t dAh = umma::make_desc(umma::smem_u32(sAh), T3WP * 16, 128), dAl = umma::make_desc(umma::smem_u32(sAl), T3WP * 16, 128);
+    const uint64_t dBh = umma::make_desc(umma::smem_u32(sWh), (uint32_t)NT * 16, 128), dBl = umma::make_desc(umma::smem_u32(sWl), (uint32_t)NT * 16, 128);
+    for (int v = 0; v < rows_out; ++v) {
+      if (v == 0) {
+        umma::mbar_wait_safe(&full_bar[0], 0u);
+        umma::mbar_wait_safe(&full_bar[1], 0u);
+      }
+      const int u2 = v + 2, b = v & 1;
+      umma::mbar_wait_safe(&full_bar[u2 & 3], (uint32_t)((u2 >> 2) & 1));
+      umma::mbar_wait_safe(&acce_bar[b], (uint32_t)(((v >> 1) & 1) ^ 1));
+      umma::fence_after_sync();
+      if (umma::elect_one()) {
+        const uint32_t s0 = (uint32_t)((v & 3) * slot_recs), s1 = (uint32_t)(((v + 1) & 3) * slot_recs),
+                       s2 = (uint32_t)(((v + 2) & 3) * slot_recs);
+        const uint32_t acc = taddr + (uint32_t)b * ncols;
+        if (KC == 4)
+          tc3_issue_row<4>(dAh, dAl, dBh, dBl, s0, s1, s2, (uint32_t)NT, idesc, acc, 1u);
+        else if (KC == 8)
+          tc3_issue_row<8>(dAh, dAl, dBh, dBl, s0, s1, s2, (uint32_t)NT, idesc, acc, 1u);
+        else
+          tc3_issue_row_generic(dAh, dAl, dBh, dBl, s0, s1, s2, (uint32_t)NT, KC, idesc, acc, 1u);
+        umma::mma_commit(&accf_bar[b]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (thread = pixel = TMEM lane)
+    const int x = x0 + tid;
+    const bool xvalid = x < P.w;
+    for (int v = 0; v < rows_out; ++v) {
+      const int y = y_begin + v, b = v & 1;
+      const size_t pix = ((size_t)n * P.h + y) * (size_t)P.w + x;
+      float2 fl = make_float2(0.f, 0.f);
+      if (P.act == CRFP_ACT_DCN_HEAD && xvalid) fl = __ldg(reinterpret_cast<const float2*>(P.flow + pix * 2));
+      float2 ex[9];
+      if (P.extra != nullptr) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+          ex[tap] = (xvalid && yy >= 0 && yy < P.h && xx >= 0 && xx < P.w)
+                        ? __ldg(reinterpret_cast<const float2*>(P.extra + (((size_t)n * P.h + yy) * (size_t)P.w + xx) * 2))
+                        : make_float2(0.f, 0.f);
+        }
+      }
+      umma::mbar_wait_safe(&accf_bar[b], (uint32_t)((v >> 1) & 1));
+      umma::fence_after_sync();
+      for (int c0 = 0; c0 < NT; c0 += 32) {
+        float vv[32];
+        umma::tmem_ld32(taddr + ((uint32_t)(32 * warp) << 16) + (uint32_t)b * ncols + (uint32_t)c0, vv);
+        if (c0 + 32 >= NT) {  // last chunk is in registers: the accumulator can be overwritten
+          umma::fence_before_sync();
+          umma::mbar_arrive(&acce_bar[b]);
+        }
+        const int cbase = cotile * NT + c0;
+        if (!xvalid || cbase >= P.cout) continue;
+        const int nvalid = min(min(32, NT - c0), P.cout - cbase);
+        tc3_epilogue_chunk(P, vv, sBias + c0, P.extra != nullptr ? sWx + c0 : nullptr, ex, fl, NT, cbase, nvalid, n, y, x, pix);
+      }
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 4) umma::tmem_dealloc(taddr, 2 * ncols);
 }
 
 static size_t tc3_smem_bytes(int kc_real, int kc_total, int nt, bool extra) {
@@ -365,11 +563,28 @@ int launch_conv_tc3(Tc3Params p, cudaStream_t st) {
       if (p.dst_cstride[s] % 4 || p.dst_coffset[s] % 4 || (s == 0 && p.ndst > 1 && p.dst_c[0] % 4)) return CRFP_ERR_BAD_SHAPE;
   if (p.residual && (p.res_cstride % 4 || p.res_coffset % 4)) return CRFP_ERR_BAD_SHAPE;
   if (p.post_scale == 0.f) p.post_scale = 1.f;
+  const int strips = ceil_div(p.w, T3M);
+  const int per_seg = strips * p.n * p.ntiles;
+  static const bool use_v1 = (getenv("CRFP_TC3_V1") != nullptr);   // A/B switch: the non-specialised kernel
+  if (!use_v1) {
+    // warp-specialised pipeline: one CTA per SM, one wave
+    const size_t smem = (size_t)(2 * 9 * p.kc_total * p.nt + 2 * WS_SLOTS * p.kc_total * T3WP) * 16 +
+                        (size_t)((p.nt + 31) & ~31) * 4 + (p.extra ? (size_t)(18 * p.nt + 32) * 4 : 0);
+    if (smem > 227 * 1024) return CRFP_ERR_UNSUPPORTED;
+    int segs = 148 / per_seg;
+    if (segs < 1) segs = 1;
+    if (segs > ceil_div(p.h, 4)) segs = ceil_div(p.h, 4);
+    p.rows_per_cta = ceil_div(p.h, segs);
+    segs = ceil_div(p.h, p.rows_per_cta);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc3_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
+    dim3 grid(strips, segs, p.n * p.ntiles);
+    conv_tc3_ws_kernel<<<grid, WS_THREADS, smem, st>>>(p);
+    return check_launch();
+  }
   const size_t smem = tc3_smem_bytes(p.kc_real, p.kc_total, p.nt, p.extra != nullptr);
   if (smem > 227 * 1024) return CRFP_ERR_UNSUPPORTED;
   const int ctas_per_sm = (int)((227 * 1024) / (smem + 1024)) < 1 ? 1 : (int)((227 * 1024) / (smem + 1024));
-  const int strips = ceil_div(p.w, T3M);
-  const int per_seg = strips * p.n * p.ntiles;
   int segs = (148 * (ctas_per_sm > 4 ? 4 : ctas_per_sm)) / per_seg;
   if (segs < 1) segs = 1;
   if (segs > ceil_div(p.h, 4)) segs = ceil_div(p.h, 4);
