@@ -153,7 +153,7 @@ SYMBOLS = {
     "crfp_sizeof_warp_desc": (C.c_size_t, []),
     "crfp_dcn_v2_fwd": (C.c_int, [C.POINTER(DcnDesc), C.c_void_p]),
     "crfp_dcn_v2_tc_fwd": (C.c_int, [C.POINTER(DcnDesc), C.c_void_p]),
-    "crfp_dcn_v2_tc3_fwd": (C.c_int, [C.POINTER(DcnDesc), C.c_void_p, C.c_void_p]),
+    "crfp_dcn_v2_tc3_fwd": (C.c_int, [C.POINTER(DcnDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "crfp_dcn_v2_indices": (C.c_int, [C.POINTER(DcnDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "crfp_sizeof_dcn_desc": (C.c_size_t, []),
     "crfp_resize_bilinear": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float,

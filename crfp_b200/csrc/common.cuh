@@ -146,7 +146,7 @@ int launch_conv(const ConvParams& p, cudaStream_t st);  // dispatch on cout
 int launch_flow_warp(const crfp_warp_desc& d, cudaStream_t st);
 int launch_dcn(const crfp_dcn_desc& d, cudaStream_t st);
 int launch_dcn_tc(const crfp_dcn_desc& d, cudaStream_t st);
-int launch_dcn_tc3(const crfp_dcn_desc& d, const void* w_lo, cudaStream_t st);
+int launch_dcn_tc3(const crfp_dcn_desc& d, const void* w_lo, const float* flow_hint, cudaStream_t st);
 int launch_flow_warp_bf16(const crfp_warp_desc& d, cudaStream_t st);
 int launch_flow_up2_dual(int n, int h, int w, const float* flow, float* out_f32, void* out_bf8, cudaStream_t st);
 
@@ -160,6 +160,9 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+// MUFU-based versions for the tensor-core epilogues (abs error ~1e-7, far inside the parity budget)
+__device__ __forceinline__ float fast_sigmoid(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+__device__ __forceinline__ float fast_tanh(float v) { return 1.f - __fdividef(2.f, __expf(2.f * v) + 1.f); }
 
 // Packed-quad loader shared by the conv kernels: 4 consecutive packed input channels (quad `vq`) of the
 // channel-concatenated input at pixel (n, y, x); zero outside the image and in padding channels.

@@ -155,7 +155,7 @@ __device__ __forceinline__ void tc3_epilogue_chunk(const Tc3Params& P, float* v,
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int cc = cbase + i;
-          v[i] = (cc < P.head_split) ? P.head_mag * tanhf(v[i]) + ((cc & 1) ? fl.x : fl.y) : sigmoidf_(v[i]);
+          v[i] = (cc < P.head_split) ? P.head_mag * fast_tanh(v[i]) + ((cc & 1) ? fl.x : fl.y) : fast_sigmoid(v[i]);
         }
       }
       if (P.residual != nullptr) {

@@ -167,6 +167,7 @@ struct DcnTc3Params {
   const __nv_bfloat16* w_lo;
   const float* bias;
   float* out; int out_cstride, out_coffset;
+  const float* flow_hint;     // optional NHWC 2-channel flow: centres the shared-memory sampling window
 };
 
 __device__ __forceinline__ void dcn_sample_f32(const DcnTc3Params& P, const float* img, int gt, int y, int x, float dy,
@@ -197,7 +198,59 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   lo = umma::pack_bf16(a - __bfloat162float(h0), b - __bfloat162float(h1));
 }
 
-__global__ void __launch_bounds__(256, 1) dcn_tc3_kernel(const DcnTc3Params P) {
+// Shared-memory sampling window: for each K half (4 deformable groups = 64 B of every input pixel) the
+// (16+2R) x (8+2R) neighbourhood of the tile, shifted by the rounded optical flow at the tile centre, is staged once
+// with cp.async (zero filled outside the image).  Samples whose 2x2 footprint lies inside the window are gathered
+// with LDS.128; the rest (large residual offsets) fall back to global loads — always correct, never assumed.
+constexpr int DWR = 10;
+constexpr int DWW = DTW + 2 * DWR, DWH = DTH + 2 * DWR;   // 36 x 28 pixels
+
+__device__ __forceinline__ void dcn_load_window(const DcnTc3Params& P, float4* sWin, int n, int wy0, int wx0, int half, int tid) {
+  const float* img = P.x + (size_t)n * P.h * P.w * P.x_cstride + P.x_coffset + half * 16;
+  for (int i = tid; i < DWH * DWW * 4; i += blockDim.x) {
+    const int gl = i & 3, pix = i >> 2;
+    const int py = pix / DWW, px = pix - py * DWW;
+    const int gy = wy0 + py, gx = wx0 + px;
+    const bool in = gy >= 0 && gy < P.h && gx >= 0 && gx < P.w;
+    const float* g = in ? img + ((size_t)gy * P.w + gx) * P.x_cstride + gl * 4 : P.x;
+    umma::cp_async16(sWin + i, g, in ? 16u : 0u);
+  }
+}
+
+__device__ __forceinline__ void dcn_sample_win(const DcnTc3Params& P, const float* img, const float4* sWin, int wy0, int wx0,
+                                               int half, int gt, int y, int x, float dy, float dx, float m, float* v) {
+  const int g = gt / 9, t = gt - g * 9;
+  const int i = t / 3, j = t - i * 3;
+  int y0, x0;
+  float w00, w01, w10, w11;
+  dcn_corner_w((float)(y - 1 + i) + dy, (float)(x - 1 + j) + dx, P.h, P.w, y0, x0, w00, w01, w10, w11);
+  const int wy = y0 - wy0, wx = x0 - wx0;
+  if (wy >= 0 && wy + 1 < DWH && wx >= 0 && wx + 1 < DWW) {
+    const float4* p = sWin + (wy * DWW + wx) * 4 + (g - 4 * half);
+    const float4 c00 = p[0], c01 = p[4], c10 = p[DWW * 4], c11 = p[DWW * 4 + 4];
+    v[0] = (w00 * c00.x + w01 * c01.x + w10 * c10.x + w11 * c11.x) * m;
+    v[1] = (w00 * c00.y + w01 * c01.y + w10 * c10.y + w11 * c11.y) * m;
+    v[2] = (w00 * c00.z + w01 * c01.z + w10 * c10.z + w11 * c11.z) * m;
+    v[3] = (w00 * c00.w + w01 * c01.w + w10 * c10.w + w11 * c11.w) * m;
+    return;
+  }
+  // outside the staged window: global gather
+  v[0] = v[1] = v[2] = v[3] = 0.f;
+  const float* p = img + ((long long)y0 * P.w + x0) * P.x_cstride + g * 4;
+#define CRFP_C4(ptr, wgt)                                                  \
+  if ((wgt) != 0.f) {                                                      \
+    const float4 t4 = __ldg(reinterpret_cast<const float4*>(ptr));         \
+    v[0] += (wgt) * t4.x; v[1] += (wgt) * t4.y; v[2] += (wgt) * t4.z; v[3] += (wgt) * t4.w; \
+  }
+  CRFP_C4(p, w00)
+  CRFP_C4(p + P.x_cstride, w01)
+  CRFP_C4(p + (long long)P.w * P.x_cstride, w10)
+  CRFP_C4(p + (long long)P.w * P.x_cstride + P.x_cstride, w11)
+#undef CRFP_C4
+  v[0] *= m; v[1] *= m; v[2] *= m; v[3] *= m;
+}
+
+__global__ void __launch_bounds__(512, 1) dcn_tc3_kernel(const DcnTc3Params P) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -206,6 +259,7 @@ __global__ void __launch_bounds__(256, 1) dcn_tc3_kernel(const DcnTc3Params P) {
   uint4* sBl = sBh + DKC * 32;
   uint4* sAh = sBl + DKC * 32;                   // [18][129]
   uint4* sAl = sAh + D3KH * DAP;
+  float4* sWin = reinterpret_cast<float4*>(sAl + D3KH * DAP);   // [28][36][4]
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int tiles_x = (P.w + DTW - 1) / DTW;
@@ -213,10 +267,20 @@ __global__ void __launch_bounds__(256, 1) dcn_tc3_kernel(const DcnTc3Params P) {
   const int n = blockIdx.y;
   const int x0t = tx * DTW, y0t = ty * DTH;
 
-  for (int i = tid; i < DKC * 32; i += 256) {
+  // window origin: tile - reach, shifted by the rounded flow at the tile centre (the offsets are flow + residual)
+  int wy0 = y0t - DWR, wx0 = x0t - DWR;
+  if (P.flow_hint != nullptr) {
+    const int cy = min(y0t + DTH / 2, P.h - 1), cx = min(x0t + DTW / 2, P.w - 1);
+    const float2 fl = __ldg(reinterpret_cast<const float2*>(P.flow_hint + (((size_t)n * P.h + cy) * (size_t)P.w + cx) * 2));
+    wy0 += (int)rintf(fminf(fmaxf(fl.y, -4096.f), 4096.f));
+    wx0 += (int)rintf(fminf(fmaxf(fl.x, -4096.f), 4096.f));
+  }
+
+  for (int i = tid; i < DKC * 32; i += 512) {
     umma::cp_async16(sBh + i, reinterpret_cast<const uint4*>(P.w_hi) + i, 16u);
     umma::cp_async16(sBl + i, reinterpret_cast<const uint4*>(P.w_lo) + i, 16u);
   }
+  dcn_load_window(P, sWin, n, wy0, wx0, 0, tid);
   umma::cp_async_commit();
   if (tid < 32) s_bias[tid] = P.bias[tid];
   if (warp == 0) umma::tmem_alloc(&tmem_base_s, 32);
@@ -232,19 +296,36 @@ __global__ void __launch_bounds__(256, 1) dcn_tc3_kernel(const DcnTc3Params P) {
   const float* img = P.x + (size_t)n * P.h * P.w * P.x_cstride + P.x_coffset;
 
   for (int half = 0; half < 2; ++half) {
-    // ---- gather this half's 18 K chunks for the 128 pixels: 2304 records, 9 per thread
-#pragma unroll 2
-    for (int idx = tid; idx < 128 * D3KH; idx += 256) {
+    umma::cp_async_wait<0>();
+    __syncthreads();   // this half's window (and, first time, the weights) have landed for everyone
+    // ---- gather this half's 18 K chunks for the 128 pixels: 2304 records, <= 5 per thread (16 warps).  All offset / mask loads
+    //      (the long-latency HBM stream) are issued up front, then the samples are taken from the window.
+    float4 offs[5];
+    float2 mks[5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      const int idx = tid + r * 512;
+      const int m = idx / D3KH, kl = idx - m * D3KH, kc = half * D3KH + kl;
+      const int y = y0t + (m >> 4), x = x0t + (m & 15);
+      offs[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      mks[r] = make_float2(0.f, 0.f);
+      if (idx < 128 * D3KH && y < P.h && x < P.w) {
+        const size_t pix = ((size_t)n * P.h + y) * (size_t)P.w + x;
+        offs[r] = __ldg(reinterpret_cast<const float4*>(P.offset + pix * P.off_cstride + P.off_coffset + kc * 4));
+        mks[r] = __ldg(reinterpret_cast<const float2*>(P.mask + pix * P.mask_cstride + P.mask_coffset + kc * 2));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      const int idx = tid + r * 512;
+      if (idx >= 128 * D3KH) break;
       const int m = idx / D3KH, kl = idx - m * D3KH, kc = half * D3KH + kl;
       const int y = y0t + (m >> 4), x = x0t + (m & 15);
       uint4 rh = make_uint4(0u, 0u, 0u, 0u), rl = rh;
       if (y < P.h && x < P.w) {
-        const size_t pix = ((size_t)n * P.h + y) * (size_t)P.w + x;
-        const float4 off = __ldg(reinterpret_cast<const float4*>(P.offset + pix * P.off_cstride + P.off_coffset + kc * 4));
-        const float2 mk = __ldg(reinterpret_cast<const float2*>(P.mask + pix * P.mask_cstride + P.mask_coffset + kc * 2));
         float v0[4], v1[4];
-        dcn_sample_f32(P, img, 2 * kc, y, x, off.x, off.y, mk.x, v0);
-        dcn_sample_f32(P, img, 2 * kc + 1, y, x, off.z, off.w, mk.y, v1);
+        dcn_sample_win(P, img, sWin, wy0, wx0, half, 2 * kc, y, x, offs[r].x, offs[r].y, mks[r].x, v0);
+        dcn_sample_win(P, img, sWin, wy0, wx0, half, 2 * kc + 1, y, x, offs[r].z, offs[r].w, mks[r].y, v1);
         split_pair(v0[0], v0[1], rh.x, rl.x);
         split_pair(v0[2], v0[3], rh.y, rl.y);
         split_pair(v1[0], v1[1], rh.z, rl.z);
@@ -253,9 +334,12 @@ __global__ void __launch_bounds__(256, 1) dcn_tc3_kernel(const DcnTc3Params P) {
       sAh[kl * DAP + m] = rh;
       sAl[kl * DAP + m] = rl;
     }
-    if (half == 0) umma::cp_async_wait<0>();
     umma::fence_proxy_async();
-    __syncthreads();
+    __syncthreads();   // A tiles complete; the window buffer is free again
+    if (half == 0) {
+      dcn_load_window(P, sWin, n, wy0, wx0, 1, tid);   // overlaps with the MMAs below
+      umma::cp_async_commit();
+    }
     if (warp == 0 && umma::elect_one()) {
       umma::fence_after_sync();
       const uint64_t dAh = umma::make_desc(umma::smem_u32(sAh), DAP * 16, 128), dAl = umma::make_desc(umma::smem_u32(sAl), DAP * 16, 128);
@@ -296,7 +380,7 @@ __global__ void __launch_bounds__(256, 1) dcn_tc3_kernel(const DcnTc3Params P) {
   if (warp == 0) umma::tmem_dealloc(taddr, 32);
 }
 
-int launch_dcn_tc3(const crfp_dcn_desc& d, const void* w_lo, cudaStream_t st) {
+int launch_dcn_tc3(const crfp_dcn_desc& d, const void* w_lo, const float* flow_hint, cudaStream_t st) {
   if ((long long)d.n * d.h * d.w == 0) return CRFP_OK;
   if (!(d.c == 32 && d.dg == 8 && d.cout == 32 && !d.shared_taps)) return CRFP_ERR_UNSUPPORTED;
   if (!w_lo) return CRFP_ERR_NULL;
@@ -310,11 +394,12 @@ int launch_dcn_tc3(const crfp_dcn_desc& d, const void* w_lo, cudaStream_t st) {
   p.w_hi = reinterpret_cast<const __nv_bfloat16*>(d.weight); p.w_lo = reinterpret_cast<const __nv_bfloat16*>(w_lo);
   p.bias = d.bias;
   p.out = d.out; p.out_cstride = d.out_cstride; p.out_coffset = d.out_coffset;
-  const size_t smem = (size_t)(2 * DKC * 32 + 2 * D3KH * DAP) * 16;  // 36864 + 74304 = 111168 B
+  p.flow_hint = flow_hint;
+  const size_t smem = (size_t)(2 * DKC * 32 + 2 * D3KH * DAP + DWH * DWW * 4) * 16;  // 36864 + 74304 + 64512 B
   cudaError_t e = cudaFuncSetAttribute(dcn_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
   dim3 grid(ceil_div(d.w, DTW) * ceil_div(d.h, DTH), d.n);
-  dcn_tc3_kernel<<<grid, 256, smem, st>>>(p);
+  dcn_tc3_kernel<<<grid, 512, smem, st>>>(p);
   return check_launch();
 }
 
@@ -346,10 +431,10 @@ using namespace crfp;
 // bias fp32.  Same descriptor struct; pointers are reinterpreted.
 // fp32-accurate tensor-core variant: x / out fp32 NHWC; d->weight = hi part, weight_lo = lo part of the bf16 split of
 // the [36][32][8] packed weight (k = (g*9+t)*4+c).
-extern "C" int crfp_dcn_v2_tc3_fwd(const crfp_dcn_desc* d, const void* weight_lo, crfp_stream stream) {
+extern "C" int crfp_dcn_v2_tc3_fwd(const crfp_dcn_desc* d, const void* weight_lo, const float* flow_hint, crfp_stream stream) {
   if (!d || !d->x || !d->offset || !d->mask || !d->weight || !d->bias || !d->out || !weight_lo) return CRFP_ERR_NULL;
   if (d->n < 0 || d->h <= 0 || d->w <= 0) return CRFP_ERR_BAD_SHAPE;
-  return launch_dcn_tc3(*d, weight_lo, (cudaStream_t)stream);
+  return launch_dcn_tc3(*d, weight_lo, flow_hint, (cudaStream_t)stream);
 }
 
 extern "C" int crfp_dcn_v2_tc_fwd(const crfp_dcn_desc* d, crfp_stream stream) {

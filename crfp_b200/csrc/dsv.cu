@@ -646,7 +646,7 @@ extern "C" int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weigh
         dd.out = f.A; dd.out_cstride = 32;
         if (W->precision == CRFP_PREC_TC3 && W->layer_tc[ldc[k]].w_hi && W->layer_tc[ldc[k]].w_lo) {
           dd.weight = reinterpret_cast<const float*>(W->layer_tc[ldc[k]].w_hi); dd.bias = W->layer_tc[ldc[k]].b;
-          CRFP_TRY(launch_dcn_tc3(dd, W->layer_tc[ldc[k]].w_lo, st));
+          CRFP_TRY(launch_dcn_tc3(dd, W->layer_tc[ldc[k]].w_lo, f.flow_l1, st));
         } else {
           CRFP_TRY(launch_dcn(dd, st));
         }

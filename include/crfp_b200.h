@@ -278,8 +278,10 @@ int crfp_dcn_v2_fwd(const crfp_dcn_desc* d, crfp_stream stream);
  * offset / mask / bias fp32; the gather writes the UMMA A tile in shared memory, tcgen05.mma contracts it. */
 int crfp_dcn_v2_tc_fwd(const crfp_dcn_desc* d, crfp_stream stream);
 /* fp32-accurate tensor-core variant: x / out fp32 NHWC; d->weight and weight_lo are the hi / lo bf16 halves of the
- * [36][32][8] packed weight; columns are split hi/lo in the kernel, 3 products accumulate in fp32 TMEM. */
-int crfp_dcn_v2_tc3_fwd(const crfp_dcn_desc* d, const void* weight_lo, crfp_stream stream);
+ * [36][32][8] packed weight; columns are split hi/lo in the kernel, 3 products accumulate in fp32 TMEM.
+ * flow_hint (optional, NHWC 2-channel flow at this resolution) centres the shared-memory sampling window of each tile;
+ * it only affects speed (samples outside the window are gathered from global memory). */
+int crfp_dcn_v2_tc3_fwd(const crfp_dcn_desc* d, const void* weight_lo, const float* flow_hint, crfp_stream stream);
 /* debug/parity: floor(py), floor(px) for every (pixel, group, tap): int32 [n,h,w,dg*9] each (non-shared form) */
 int crfp_dcn_v2_indices(const crfp_dcn_desc* d, int32_t* y0, int32_t* x0, crfp_stream stream);
 size_t crfp_sizeof_dcn_desc(void);

@@ -150,10 +150,18 @@ def test_dcn_v2_tc3_fp32_accuracy():
                   offset=om.data_ptr(), off_cstride=216, off_coffset=0, mask=om.data_ptr(), mask_cstride=216,
                   mask_coffset=144, weight=hi.data_ptr(), bias=bp.data_ptr(), out=out.data_ptr(), out_cstride=32,
                   out_coffset=0)
-    L.check(L.lib().crfp_dcn_v2_tc3_fwd(C.byref(d), lo.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "dcn tc3")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    L.check(L.lib().crfp_dcn_v2_tc3_fwd(C.byref(d), lo.data_ptr(), None, st), "dcn tc3")
     err = (nchw(out) - ref).abs().max().item()
     print(f"dcn tc3 max-abs {err:.3e}")
     assert err < 1e-4
+    # the flow hint only moves the shared-memory sampling window: any hint (good, zero, wild) gives the same result
+    for scale in (0.0, 3.0, 60.0):
+        hint = (torch.randn(n, h, w, 2, generator=g) * scale).cuda()
+        out2 = torch.zeros_like(out)
+        d.out = out2.data_ptr()
+        L.check(L.lib().crfp_dcn_v2_tc3_fwd(C.byref(d), lo.data_ptr(), hint.data_ptr(), st), "dcn tc3 hint")
+        assert (nchw(out2) - ref).abs().max().item() < 1e-4
 
 
 @pytest.mark.parametrize("c_list,cout,hw,act,extra", [
