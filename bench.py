@@ -129,33 +129,8 @@ def run_reference(args):
     }))
 
 
-def time_align_kernel(torch, h1, w1, reps=20):
-    """Average device time of the DCNv2 @L1 align kernel alone (C ABI), inputs > L2 so every launch is cold."""
-    import ctypes as C
-    from crfp_b200 import _lib as L
-    from crfp_b200.packing import pack_dcn
-    dev = torch.device("cuda")
-    g = torch.Generator(device="cpu").manual_seed(0)
-    nbuf = 3  # rotate buffers: 3 x (29 + 199) MB > 126 MB L2
-    xs = [torch.randn(1, h1, w1, 32, generator=g).to(dev) for _ in range(nbuf)]
-    oms = []
-    for _ in range(nbuf):
-        om = torch.empty(1, h1, w1, 216)
-        om[..., :144] = torch.randn(1, h1, w1, 144, generator=g) * 3.0
-        om[..., 144:] = torch.rand(1, h1, w1, 72, generator=g)
-        oms.append(om.to(dev))
-    wp, bp = pack_dcn((torch.randn(32, 32, 3, 3, generator=g) * 0.05).to(dev), torch.zeros(32).to(dev), 8)
-    out = torch.empty(1, h1, w1, 32, device=dev)
-    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-    def launch(i):
-        d = L.DcnDesc(n=1, h=h1, w=w1, c=32, cout=32, dg=8, shared_taps=0, x=xs[i % nbuf].data_ptr(), x_cstride=32,
-                      x_coffset=0, offset=oms[i % nbuf].data_ptr(), off_cstride=216, off_coffset=0,
-                      mask=oms[i % nbuf].data_ptr(), mask_cstride=216, mask_coffset=144, weight=wp.data_ptr(),
-                      bias=bp.data_ptr(), out=out.data_ptr(), out_cstride=32, out_coffset=0)
-        L.check(L.lib().crfp_dcn_v2_fwd(C.byref(d), st), "dcn_v2")
-
-    for i in range(3):
+def _events_avg_ms(torch, launch, reps, warm=3):
+    for i in range(warm):
         launch(i)
     torch.cuda.synchronize()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
@@ -164,8 +139,105 @@ def time_align_kernel(torch, h1, w1, reps=20):
         launch(i)
         b.record()
     torch.cuda.synchronize()
-    ms = sorted(a.elapsed_time(b) for a, b in evs)
+    ms = [a.elapsed_time(b) for a, b in evs]
     return sum(ms) / len(ms)
+
+
+def time_align_kernel(torch, h1, w1, precision, reps=12):
+    """Average device time of the DCNv2 @L1 align kernel alone (C ABI), 3 rotating input sets > L2 (cold launches)."""
+    import ctypes as C
+    from crfp_b200 import _lib as L
+    from crfp_b200.packing import pack_dcn, pack_dcn_tc3
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(0)
+    nbuf = 3  # 3 x (29 + 199) MB > 126 MB L2
+    xs = [torch.randn(1, h1, w1, 32, generator=g).to(dev) for _ in range(nbuf)]
+    oms, flows = [], []
+    for _ in range(nbuf):
+        fl = torch.randn(1, h1, w1, 2, generator=g) * 2.0
+        om = torch.empty(1, h1, w1, 216)
+        om[..., :144] = torch.tanh(torch.randn(1, h1, w1, 144, generator=g)) * 10.0 * 0.35 + fl.flip(-1).repeat(1, 1, 1, 72)
+        om[..., 144:] = torch.rand(1, h1, w1, 72, generator=g)
+        oms.append(om.to(dev)); flows.append(fl.to(dev))
+    wt = (torch.randn(32, 32, 3, 3, generator=g) * 0.05).to(dev)
+    out = torch.empty(1, h1, w1, 32, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if precision == "tc":
+        hi, lo, bp = pack_dcn_tc3(wt, torch.zeros(32, device=dev), 8)
+        wptr = hi.data_ptr()
+    else:
+        wp, bp = pack_dcn(wt, torch.zeros(32, device=dev), 8)
+        wptr = wp.data_ptr()
+
+    def launch(i):
+        k = i % nbuf
+        d = L.DcnDesc(n=1, h=h1, w=w1, c=32, cout=32, dg=8, shared_taps=0, x=xs[k].data_ptr(), x_cstride=32,
+                      x_coffset=0, offset=oms[k].data_ptr(), off_cstride=216, off_coffset=0,
+                      mask=oms[k].data_ptr(), mask_cstride=216, mask_coffset=144, weight=wptr,
+                      bias=bp.data_ptr(), out=out.data_ptr(), out_cstride=32, out_coffset=0)
+        if precision == "tc":
+            L.check(L.lib().crfp_dcn_v2_tc3_fwd(C.byref(d), lo.data_ptr(), flows[k].data_ptr(), st), "dcn_v2_tc3")
+        else:
+            L.check(L.lib().crfp_dcn_v2_fwd(C.byref(d), st), "dcn_v2")
+
+    return _events_avg_ms(torch, launch, reps)
+
+
+def time_conv_mix(torch, h1, w1, reps=4):
+    """The per-frame mix of tensor-core conv launches (conv_tc3_ws_kernel, the dominant kernel of the step): every L1
+    layer shape of one steady-state frame through crfp_conv3x3_tc3_fwd.  Returns (avg ms per launch, launches,
+    algorithmic bytes per launch = unique fp32 operands in + out, useful fp32 FLOP per launch)."""
+    import ctypes as C
+    from crfp_b200 import _lib as L
+    from crfp_b200.packing import pack_conv_tc3
+    dev = torch.device("cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # (source channels, extra flow channels, cout, count per frame, output kind)
+    layers = [([32, 32], 2, 32, 3, "nhwc"), ([32], 0, 32, 9, "nhwc"), ([32, 32], 0, 32, 5, "nhwc"),
+              ([32], 0, 216, 3, "nhwc"), ([24], 0, 64, 1, "shuffle4"), ([32], 0, 64, 1, "shuffle4")]
+    bufs = [torch.randn(1, h1, w1, 32, device=dev) for _ in range(5)]   # 5 x 29.5 MB planes, rotated: > L2 together
+    buf24 = torch.randn(1, h1, w1, 24, device=dev)
+    flow = torch.randn(1, h1, w1, 2, device=dev)
+    out216 = torch.empty(1, h1, w1, 216, device=dev)
+    out_hr = torch.empty(1, 4 * h1, 4 * w1, 4, device=dev)
+    descs, keep = [], []
+    px = h1 * w1
+    tot_bytes = tot_flop = 0
+    rot = 0
+    for srcs, extra, cout, count, kind in layers:
+        cin = sum(srcs) + extra
+        w = torch.randn(cout, cin, 3, 3, device=dev) * 0.05
+        hi, lo, bp, wx = pack_conv_tc3(w, torch.zeros(cout, device=dev), srcs, extra=extra)
+        keep.append((hi, lo, bp, wx))
+        for _ in range(count):
+            d = L.ConvTc3Desc()
+            d.n, d.h, d.w, d.nsrc = 1, h1, w1, len(srcs)
+            for i, c in enumerate(srcs):
+                t = buf24 if c == 24 else bufs[(rot + i) % 5]
+                d.src[i] = L.TcSrc(ptr=t.data_ptr(), c=c, cstride=t.shape[-1], coffset=0)
+            d.cout, d.act = cout, 1
+            d.weight_hi, d.weight_lo, d.bias = hi.data_ptr(), lo.data_ptr(), bp.data_ptr()
+            if extra:
+                d.extra, d.w_extra = flow.data_ptr(), wx.data_ptr()
+            d.post_scale, d.ndst = 1.0, 1
+            if kind == "shuffle4":
+                d.out_kind, d.shuffle_r = L.TC_OUT_SHUFFLE_F32, 4
+                d.dst[0] = L.TcSrc(ptr=out_hr.data_ptr(), c=4, cstride=4, coffset=0)
+            else:
+                o = out216 if cout == 216 else bufs[(rot + 3) % 5]
+                d.out_kind = L.TC_OUT_F32
+                d.dst[0] = L.TcSrc(ptr=o.data_ptr(), c=cout, cstride=o.shape[-1], coffset=0)
+            descs.append(d)
+            rot += 1
+            tot_bytes += (cin + cout) * 4 * px
+            tot_flop += 2 * 9 * cin * cout * px
+
+    def launch(_):
+        for d in descs:
+            L.check(L.lib().crfp_conv3x3_tc3_fwd(C.byref(d), st), "conv_tc3")
+
+    ms = _events_avg_ms(torch, launch, reps, warm=2)
+    return ms / len(descs), len(descs), tot_bytes / len(descs), tot_flop / len(descs)
 
 
 def main():
@@ -297,13 +369,29 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    k_ms = time_align_kernel(torch, 2 * h, 2 * w)
+    bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
+    a_ms = time_align_kernel(torch, 2 * h, 2 * w, args.precision)
     alg_bytes = ALIGN_BYTES_PER_L1_PX * (2 * h) * (2 * w)
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"kernel": "dcn_l1_kernel (DCNv2 align @L1, C=32 dg=8)", "bound": "hbm", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_ms,
-                "timing": "kernel timed alone through crfp_dcn_v2_fwd, CUDA events, 3 rotating input sets > L2"}
+    a_ach = alg_bytes / (a_ms * 1e-3) / 1e9
+    align = {"kernel": ("dcn_tc3_kernel" if args.precision == "tc" else "dcn_l1_kernel") + " (DCNv2 align @L1, C=32 dg=8)",
+             "bound": "hbm", "achieved": a_ach, "peak": peak, "unit": "GB/s", "frac": a_ach / peak, "traffic": None,
+             "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": a_ms,
+             "timing": "kernel timed alone through the C ABI, CUDA events, 3 rotating input sets > L2"}
+    if args.precision == "tc":
+        c_ms, c_n, c_bytes, c_flop = time_conv_mix(torch, 2 * h, 2 * w)
+        c_ach = c_bytes / (c_ms * 1e-3) / 1e9
+        roofline = {"kernel": "conv_tc3_ws_kernel (tcgen05 3x3 implicit-GEMM conv, the per-frame mix of its %d L1 launches)" % c_n,
+                    "bound": "hbm", "achieved": c_ach, "peak": peak, "unit": "GB/s", "frac": c_ach / peak, "traffic": None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": c_bytes, "avg_launch_ms": c_ms,
+                    "tensor": {"useful_fp32_tflops": c_flop / (c_ms * 1e-3) / 1e12,
+                               "issued_bf16_tflops": 3 * c_flop / (c_ms * 1e-3) / 1e12, "bf16_peak_tflops": bf16_peak,
+                               "frac_of_bf16_peak": 3 * c_flop / (c_ms * 1e-3) / 1e12 / bf16_peak},
+                    "timing": "all L1 conv launches of one steady-state frame replayed back to back through "
+                              "crfp_conv3x3_tc3_fwd, CUDA events, rotating 29.5 MB planes + 199 MB heads output (> L2)",
+                    "align_kernel": align}
+    else:
+        roofline = dict(align)
+        roofline["peak_source"] = peak_src
 
     cpu = None
     if not args.no_cpu_baseline:
