@@ -77,6 +77,14 @@ struct ConvParams {
   long long out_clip_stride;      // EPI_OUT_NCHW: floats between clips of the planar output
   int out_planes;                 // EPI_OUT_NCHW: number of planes written (3)
   int out_bf16;                   // wide kernel: destinations are bf16 (strides / offsets in bf16 elements)
+  // fast per-quad addressing for the thin kernels (filled by launch_conv_thin): kind 0 = aligned float4,
+  // 1 = aligned float2 (+2 zero channels), 2 = generic (load_quad)
+  const float* qptr[3];
+  int qcs[3], qkind[3];
+  // fovea tile skipping (thin4 kernels, 32x32 tiles): flags[n][tiles_y][tiles_x] != 0 where the conv is needed;
+  // tile_mode 1: untouched tiles are skipped; 2 (EPI_BLEND): untouched tiles get S = lrelu(S_old) without the conv
+  const uint8_t* tile_flags;
+  int tiles_x, tiles_y, tile_mode;
 };
 
 // ---- tensor-core (tcgen05) conv description: bf16 NHWC sources, channel counts multiples of 8

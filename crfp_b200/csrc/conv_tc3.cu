@@ -485,6 +485,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
     // ------------------------------------------------------------------ epilogue warps (thread = pixel = TMEM lane)
     const int x = x0 + tid;
     const bool xvalid = x < P.w;
+    const bool shuffle4_fast = P.out_kind == TC_OUT_SHUFFLE_F32 && P.shuffle_r == 4 && NT == 64 && P.cout == 64 &&
+                               P.dst_cstride[0] == 4 && P.dst_coffset[0] == 0 && P.residual == nullptr &&
+                               P.extra == nullptr && (P.act == CRFP_ACT_NONE || P.act == CRFP_ACT_LRELU);
     for (int v = 0; v < rows_out; ++v) {
       const int y = y_begin + v, b = v & 1;
       const size_t pix = ((size_t)n * P.h + y) * (size_t)P.w + x;
@@ -502,6 +505,33 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
       }
       umma::mbar_wait_safe(&accf_bar[b], (uint32_t)((v >> 1) & 1));
       umma::fence_after_sync();
+      if (shuffle4_fast) {
+        // PixelShufflePack x4 with 64 conv channels -> 4-channel HR plane: hold all 64 values, then every (dy) row of
+        // the 4x4 sub-pixel block is 4 consecutive float4 = 64 contiguous bytes per thread, 2 KB per warp.
+        float v0[32], v1[32];
+        umma::tmem_ld32(taddr + ((uint32_t)(32 * warp) << 16) + (uint32_t)b * ncols, v0);
+        umma::tmem_ld32(taddr + ((uint32_t)(32 * warp) << 16) + (uint32_t)b * ncols + 32u, v1);
+        umma::fence_before_sync();
+        umma::mbar_arrive(&acce_bar[b]);
+        if (!xvalid) continue;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          v0[i] += sBias[i];
+          v1[i] += sBias[32 + i];
+          if (P.act == CRFP_ACT_LRELU) { v0[i] = lrelu01(v0[i]); v1[i] = lrelu01(v1[i]); }
+          v0[i] *= P.post_scale;
+          v1[i] *= P.post_scale;
+        }
+        float* ob = reinterpret_cast<float*>(P.dst[0]);
+        const int Wo = P.w * 4;
+#pragma unroll
+        for (int dy = 0; dy < 4; ++dy) {
+          float4* op = reinterpret_cast<float4*>(ob + (((size_t)n * (P.h * 4) + (y * 4 + dy)) * (size_t)Wo + (size_t)x * 4) * 4);
+#pragma unroll
+          for (int dx = 0; dx < 4; ++dx) op[dx] = make_float4(v0[dy * 4 + dx], v0[16 + dy * 4 + dx], v1[dy * 4 + dx], v1[16 + dy * 4 + dx]);
+        }
+        continue;
+      }
       for (int c0 = 0; c0 < NT; c0 += 32) {
         float vv[32];
         umma::tmem_ld32(taddr + ((uint32_t)(32 * warp) << 16) + (uint32_t)b * ncols + (uint32_t)c0, vv);

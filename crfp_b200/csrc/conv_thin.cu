@@ -16,13 +16,14 @@ __device__ __forceinline__ void thin_epilogue(const ConvParams& P, int n, int y,
   const size_t pix = ((size_t)n * P.h + y) * (size_t)P.w + x;
 
   if (P.epi == EPI_BLEND) {
-    const float m = P.mask[(size_t)n * P.mask_clip_stride + (size_t)y * P.w + x] ? 1.f : 0.f;
+    // m*F + (1-m)*S with m in {0,1}: a select (identical for finite operands, immune to values the mask discards)
+    const bool m = P.mask[(size_t)n * P.mask_clip_stride + (size_t)y * P.w + x] != 0;
     const float4 so = __ldg(reinterpret_cast<const float4*>(P.blend_old + pix * 4));
     float4 o;
-    o.x = lrelu01(m * v[0] + (1.f - m) * so.x);
-    o.y = lrelu01(m * v[1] + (1.f - m) * so.y);
-    o.z = lrelu01(m * v[2] + (1.f - m) * so.z);
-    o.w = lrelu01(m * v[3] + (1.f - m) * so.w);
+    o.x = lrelu01(m ? v[0] : so.x);
+    o.y = lrelu01(m ? v[1] : so.y);
+    o.z = lrelu01(m ? v[2] : so.z);
+    o.w = lrelu01(m ? v[3] : so.w);
     *reinterpret_cast<float4*>(P.dst[0] + pix * 4) = o;
     return;
   }
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(256) conv_thin_kernel(const ConvParams P) {
 // thread reads its 6-row column (conflict-free LDS.128, reused by the 3 ky taps) and 12 broadcast weight float4s.
 // 16 accumulators, ~54 LDS.128 per 576 FFMA: FFMA bound (the 4-channel convs are ~2x over their HBM time in fp32).
 template <int NQ>
-__global__ void __launch_bounds__(256) conv_thin4_kernel(const ConvParams P) {
+__global__ void __launch_bounds__(256, 3) conv_thin4_kernel(const ConvParams P) {
   constexpr int TS = 32, HS = TS + 2, PITCH = HS + 1;
   extern __shared__ __align__(16) float smem_t4[];
   float4* s_in = reinterpret_cast<float4*>(smem_t4);            // [NQ][34][35]
@@ -133,11 +134,43 @@ __global__ void __launch_bounds__(256) conv_thin4_kernel(const ConvParams P) {
   const int tid = threadIdx.x + threadIdx.y * 32;
   const int n = blockIdx.z;
   const int x0 = blockIdx.x * TS, y0 = blockIdx.y * TS;
+  if (P.tile_flags != nullptr && P.tile_flags[((size_t)n * P.tiles_y + blockIdx.y) * P.tiles_x + blockIdx.x] == 0) {
+    // tile outside the (dilated) fovea: the conv result would be multiplied by a zero mask
+    if (P.tile_mode == 2) {
+      const int x = x0 + threadIdx.x;
+      for (int r = 0; r < 4; ++r) {
+        const int y = y0 + 4 * threadIdx.y + r;
+        if (x < P.w && y < P.h) {
+          const size_t pix = ((size_t)n * P.h + y) * (size_t)P.w + x;
+          const float4 so = __ldg(reinterpret_cast<const float4*>(P.blend_old + pix * 4));
+          *reinterpret_cast<float4*>(P.dst[0] + pix * 4) = make_float4(lrelu01(so.x), lrelu01(so.y), lrelu01(so.z), lrelu01(so.w));
+        }
+      }
+    }
+    return;
+  }
   for (int i = tid; i < 9 * P.cin_packed; i += 256) s_w[i] = __ldg(reinterpret_cast<const float4*>(P.weight) + i);
-  for (int i = tid; i < NQ * HS * HS; i += 256) {
-    const int q = i / (HS * HS), r = i - q * (HS * HS);
-    const int py = r / HS, px = r - py * HS;
-    s_in[(q * HS + py) * PITCH + px] = load_quad_fg(P, q, n, y0 + py - 1, x0 + px - 1);
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int kind = (P.fg != nullptr) ? 2 : P.qkind[q];
+    const float* base = P.qptr[q] + (size_t)n * P.h * P.w * P.qcs[q];
+    for (int r = tid; r < HS * HS; r += 256) {
+      const int py = r / HS, px = r - py * HS;
+      const int y = y0 + py - 1, x = x0 + px - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kind == 2) {
+        v = load_quad_fg(P, q, n, y, x);
+      } else if (y >= 0 && y < P.h && x >= 0 && x < P.w) {
+        const float* g = base + ((size_t)y * P.w + x) * P.qcs[q];
+        if (kind == 0) {
+          v = __ldg(reinterpret_cast<const float4*>(g));
+        } else {
+          const float2 t = __ldg(reinterpret_cast<const float2*>(g));
+          v.x = t.x; v.y = t.y;
+        }
+      }
+      s_in[(q * HS + py) * PITCH + px] = v;
+    }
   }
   __syncthreads();
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -179,12 +212,30 @@ __global__ void __launch_bounds__(256) conv_thin4_kernel(const ConvParams P) {
   }
 }
 
-int launch_conv_thin(const ConvParams& p, cudaStream_t st) {
+int launch_conv_thin(const ConvParams& p_in, cudaStream_t st) {
+  ConvParams p = p_in;
   if (p.cout > 4 || p.cout_packed != 4) return CRFP_ERR_BAD_SHAPE;
+  {  // per-quad fast addressing
+    const int nqr = p.qstart[p.nsrc];
+    for (int q = 0; q < 3; ++q) { p.qptr[q] = p.src[0]; p.qcs[q] = p.src_cstride[0]; p.qkind[q] = 2; }
+    for (int q = 0; q < nqr && q < 3; ++q) {
+      int s = 0;
+      if (p.nsrc > 1 && q >= p.qstart[1]) s = 1;
+      if (p.nsrc > 2 && q >= p.qstart[2]) s = 2;
+      const int lc = (q - p.qstart[s]) * 4, rem = p.src_c[s] - lc;
+      const float* ptr = p.src[s] + p.src_coffset[s] + lc;
+      p.qptr[q] = ptr; p.qcs[q] = p.src_cstride[s];
+      if (p.src_mode[s] != CRFP_SRC_PLAIN) continue;
+      const bool phys4 = (p.src_coffset[s] + lc + 4 <= p.src_cstride[s]);   // 4 floats physically present
+      if ((rem >= 4 || (phys4 && rem == 4)) && ((uintptr_t)ptr & 15) == 0 && (p.src_cstride[s] & 3) == 0) p.qkind[q] = 0;
+      else if (rem == 2 && ((uintptr_t)ptr & 7) == 0 && (p.src_cstride[s] & 1) == 0) p.qkind[q] = 1;
+    }
+  }
   if (p.out_mode != CRFP_OUT_NHWC && p.epi == EPI_STD) return CRFP_ERR_UNSUPPORTED;
   dim3 block(32, 8);
   const int nq = p.qstart[p.nsrc];   // real input quads
-  if (nq >= 1 && nq <= 3 && (long long)p.h * p.w >= 32 * 32) {
+  if (p.tile_flags != nullptr && !(nq >= 1 && nq <= 3)) return CRFP_ERR_UNSUPPORTED;
+  if (nq >= 1 && nq <= 3 && ((long long)p.h * p.w >= 32 * 32 || p.tile_flags != nullptr)) {
     dim3 grid(ceil_div(p.w, 32), ceil_div(p.h, 32), p.n);
     const size_t smem4 = ((size_t)nq * 34 * 35 + 9 * p.cin_packed) * 16;
     if (nq == 1) {

@@ -222,7 +222,8 @@ struct TB {
 __global__ void __launch_bounds__(256) fovea_compose_kernel(int n, int H, int W, const float* __restrict__ fvs,
                                                             long long fvs_cs, const uint8_t* __restrict__ mks,
                                                             long long mks_cs, const float* __restrict__ lr4,
-                                                            long long lr4_cs, float* __restrict__ out) {
+                                                            long long lr4_cs, float* __restrict__ out,
+                                                            const uint8_t* __restrict__ flags, int tiles_x, int tiles_y) {
   const long long total = (long long)n * H * W;
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= total) return;
@@ -230,6 +231,7 @@ __global__ void __launch_bounds__(256) fovea_compose_kernel(int n, int H, int W,
   const int b = (int)(pix / hw);
   const long long p = pix - (long long)b * hw;
   const int y = (int)(p / W), x = (int)(p - (long long)y * W);
+  if (flags != nullptr && flags[((size_t)b * tiles_y + (y >> 5)) * tiles_x + (x >> 5)] == 0) return;
   const int hl = H >> 3, wl = W >> 3;
   int y0, y1, x0, x1;
   float ly, lx;
@@ -252,11 +254,30 @@ __global__ void __launch_bounds__(256) fovea_compose_kernel(int n, int H, int W,
   o[1] = make_float4(b1, b2, 0.f, 0.f);
 }
 
-static int launch_compose(int n, int H, int W, const crfp_dsv_frame_desc* d, float* out, cudaStream_t st) {
+// flags[n][ty][tx] = any(mask) over the 32x32 tile dilated by one tile on every side (covers the 3-pixel receptive
+// field of encoder_hr.0 -> encoder_hr.2 -> conv_tttf around every mask pixel)
+__global__ void __launch_bounds__(256) fovea_tile_flags_kernel(int H, int W, const uint8_t* __restrict__ mks, long long mks_cs,
+                                                               int tiles_x, int tiles_y, uint8_t* __restrict__ flags) {
+  const int tx = blockIdx.x, ty = blockIdx.y, b = blockIdx.z;
+  const int x_lo = max(0, tx * 32 - 32), x_hi = min(W, tx * 32 + 64);
+  const int y_lo = max(0, ty * 32 - 32), y_hi = min(H, ty * 32 + 64);
+  const int wdt = x_hi - x_lo, cnt = wdt * (y_hi - y_lo);
+  const uint8_t* mb = mks + (size_t)b * mks_cs;
+  int any = 0;
+  for (int i = threadIdx.x; i < cnt; i += 256) {
+    const int yy = y_lo + i / wdt, xx = x_lo + i % wdt;
+    any |= mb[(size_t)yy * W + xx];
+  }
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) flags[((size_t)b * tiles_y + ty) * tiles_x + tx] = any ? 1 : 0;
+}
+
+static int launch_compose(int n, int H, int W, const crfp_dsv_frame_desc* d, float* out, const uint8_t* flags, int tiles_x,
+                          int tiles_y, cudaStream_t st) {
   const long long total = (long long)n * H * W;
   fovea_compose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, H, W, d->fvs, d->fvs_clip_stride, d->mks,
                                                                        d->mks_clip_stride, d->lr4, d->lr4_clip_stride,
-                                                                       out);
+                                                                       out, flags, tiles_x, tiles_y);
   return check_launch();
 }
 
@@ -342,7 +363,7 @@ struct FrameWs {
   // L1 (2h x 2w)
   float *P, *P_w, *cur[3], *t1, *t2, *offf[2], *A, *r0, *r1, *prop, *flow_l1, *flow8, *om, *fg_l1;
   // HR (8h x 8w)
-  float *S0_w, *q, *po, *h1, *h2, *h3, *om3, *A3, *g0, *g1, *S_pre, *hr_in, *e1, *x_hr, *flow_hr;
+  float *S0_w, *q, *po, *h1, *h2, *h3, *om3, *A3, *g0, *g1, *S_pre, *hr_in, *e1, *x_hr, *flow_hr, *tile_flags;
   // dense per-frame copies of strided clip slices
   float *x_lr_d, *flow_d;
 };
@@ -367,6 +388,7 @@ static size_t carve_frame(const crfp_dsv_shape* s, void* ws, FrameWs* f) {
   f->g0 = c.take(hr * 4); f->g1 = c.take(hr * 4); f->S_pre = c.take(hr * 4);
   f->hr_in = c.take(hr * 8); f->e1 = c.take(hr * 4); f->x_hr = c.take(hr * 4);
   f->flow_hr = c.take(hr * 2);
+  f->tile_flags = c.take(n * (size_t)((s->h * 8 + 31) / 32) * ((s->w * 8 + 31) / 32) / 4 + 64);
   f->x_lr_d = c.take(n * hw * 32);
   f->flow_d = c.take(n * hw * 2);
   return c.off;
@@ -714,14 +736,33 @@ extern "C" int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weigh
   CRFP_TRY(CB(n, H, Wd).src(f.g1, 4, 4).layer(W, L_RES3_C2).res(f.g0, 4).dst(f.S_pre, 4, 4).run(st));
 
   // fovea compositing + encoder_hr for this frame                                          (CRFP.py:1542-1547)
-  CRFP_TRY(launch_compose(n, H, Wd, d, f.hr_in, st));
-  CRFP_TRY(CB(n, H, Wd).src(f.hr_in, 6, 8).layer(W, L_ENC_HR_0).act(CRFP_ACT_LRELU).dst(f.e1, 4, 4).run(st));
-  CRFP_TRY(CB(n, H, Wd).src(f.e1, 4, 4).layer(W, L_ENC_HR_2).act(CRFP_ACT_LRELU).dst(f.x_hr, 4, 4).run(st));
+  // Outside the mask the blend keeps S (0*F + 1*S): encoder_hr and conv_tttf are only CONSUMED within 3 pixels of a
+  // mask pixel, so tiles whose one-tile-dilated neighbourhood holds no mask pixel skip them (bit-identical output).
+  const int tiles_x = (Wd + 31) / 32, tiles_y = (H + 31) / 32;
+  const uint8_t* flags = nullptr;
+  if (d->skip_outside_fovea) {
+    uint8_t* fl = reinterpret_cast<uint8_t*>(f.tile_flags);
+    fovea_tile_flags_kernel<<<dim3(tiles_x, tiles_y, n), 256, 0, st>>>(H, Wd, d->mks, d->mks_clip_stride, tiles_x, tiles_y, fl);
+    CRFP_TRY(check_launch());
+    flags = fl;
+  }
+  CRFP_TRY(launch_compose(n, H, Wd, d, f.hr_in, flags, tiles_x, tiles_y, st));
+  {
+    CB e0(n, H, Wd);
+    e0.src(f.hr_in, 6, 8).layer(W, L_ENC_HR_0).act(CRFP_ACT_LRELU).dst(f.e1, 4, 4);
+    e0.p.tile_flags = flags; e0.p.tiles_x = tiles_x; e0.p.tiles_y = tiles_y; e0.p.tile_mode = 1;
+    CRFP_TRY(e0.run(st));
+    CB e2(n, H, Wd);
+    e2.src(f.e1, 4, 4).layer(W, L_ENC_HR_2).act(CRFP_ACT_LRELU).dst(f.x_hr, 4, 4);
+    e2.p.tile_flags = flags; e2.p.tiles_x = tiles_x; e2.p.tiles_y = tiles_y; e2.p.tile_mode = 1;
+    CRFP_TRY(e2.run(st));
+  }
   // conv_tttf + blend + LeakyReLU -> new state                                             (CRFP.py:1672-1675)
   {
     CB b(n, H, Wd);
     b.src(f.S_pre, 4, 4).src(f.x_hr, 4, 4).layer(W, L_TTTF).dst(d->state_hr, 4, 4);
     b.p.epi = EPI_BLEND; b.p.mask = d->mks; b.p.mask_clip_stride = d->mks_clip_stride; b.p.blend_old = f.S_pre;
+    b.p.tile_flags = flags; b.p.tiles_x = tiles_x; b.p.tiles_y = tiles_y; b.p.tile_mode = 2;
     CRFP_TRY(b.run(st));
   }
   // out = conv_last(S) + up8(lr)                                                           (CRFP.py:1678-1683)
