@@ -121,6 +121,7 @@ struct Tc3Params {
   int nsrc;
   const float* src[3];
   int src_c[3], src_cstride[3], src_coffset[3];
+  int src_mode[3];        // CRFP_SRC_PLAIN or CRFP_SRC_UNSHUFFLE4 (dense 4-channel (4h x 4w) plane, c = 64)
   int kstart[3];
   int kc_real, kc_total;
   int cout, nt, ntiles;

@@ -349,7 +349,9 @@ __device__ __forceinline__ void ws_produce_row(const Tc3Params& P, uint4* hi, ui
   for (int s = 0; s < P.nsrc; ++s) {
     const int cps = P.src_c[s] >> 3;  // 8-channel records per pixel of this source
     const int nrec = T3WP * cps;
-    const float* rowp = P.src[s] + (((size_t)n * P.h + (yin ? y : 0)) * (size_t)P.w) * P.src_cstride[s] + P.src_coffset[s];
+    const bool unsh = (P.src_mode[s] == CRFP_SRC_UNSHUFFLE4);   // pixel_unshuffle(4) of a dense 4-channel HR plane
+    const float* rowp = unsh ? P.src[s] + ((size_t)n * (P.h * 4) + (size_t)(yin ? y : 0) * 4) * (size_t)(P.w * 4) * 4
+                             : P.src[s] + (((size_t)n * P.h + (yin ? y : 0)) * (size_t)P.w) * P.src_cstride[s] + P.src_coffset[s];
     const int kbase = P.kstart[s] * T3WP;
 #pragma unroll 1
     for (int base = ptid; base < nrec; base += 3 * WS_NPROD) {
@@ -367,7 +369,9 @@ __device__ __forceinline__ void ws_produce_row(const Tc3Params& P, uint4* hi, ui
           const int x = x0 + px - 1;
           dst[k] = kbase + j * T3WP + px;
           if (yin && x >= 0 && x < P.w) {
-            const float4* g = reinterpret_cast<const float4*>(rowp + (size_t)x * P.src_cstride[s] + j * 8);
+            // unshuffle: record j = HR row 4y + j/2, HR pixels 4x + 2*(j%2) and +1 (8 contiguous floats)
+            const float4* g = unsh ? reinterpret_cast<const float4*>(rowp + ((size_t)(j >> 1) * (P.w * 4) + (size_t)x * 4 + (j & 1) * 2) * 4)
+                                   : reinterpret_cast<const float4*>(rowp + (size_t)x * P.src_cstride[s] + j * 8);
             a[k] = __ldg(g);
             b[k] = __ldg(g + 1);
             if (P.fg != nullptr) f[k] = __ldg(P.fg + (size_t)n * P.fg_clip_stride + (size_t)y * P.w + x);
@@ -579,6 +583,7 @@ int launch_conv_tc3(Tc3Params p, cudaStream_t st) {
   for (int s = 0; s < p.nsrc; ++s) {
     if (!p.src[s]) return CRFP_ERR_NULL;
     if (p.src_c[s] % 8 || p.src_cstride[s] % 4 || p.src_coffset[s] % 4 || ((uintptr_t)p.src[s] & 15)) return CRFP_ERR_BAD_SHAPE;
+    if (p.src_mode[s] == CRFP_SRC_UNSHUFFLE4 && (p.src_c[s] != 64 || p.src_cstride[s] != 4 || p.src_coffset[s] != 0)) return CRFP_ERR_UNSUPPORTED;
     p.kstart[s] = kc;
     kc += p.src_c[s] / 8;
   }
@@ -596,6 +601,8 @@ int launch_conv_tc3(Tc3Params p, cudaStream_t st) {
   const int strips = ceil_div(p.w, T3M);
   const int per_seg = strips * p.n * p.ntiles;
   static const bool use_v1 = (getenv("CRFP_TC3_V1") != nullptr);   // A/B switch: the non-specialised kernel
+  for (int s = 0; s < p.nsrc; ++s)
+    if (use_v1 && p.src_mode[s] != CRFP_SRC_PLAIN) return CRFP_ERR_UNSUPPORTED;
   if (!use_v1) {
     // warp-specialised pipeline: one CTA per SM, one wave
     const size_t smem = (size_t)(2 * 9 * p.kc_total * p.nt + 2 * WS_SLOTS * p.kc_total * T3WP) * 16 +
@@ -649,7 +656,7 @@ static int tc3_fwd_impl(const crfp_conv_tc3_desc* d, long long* trace, crfp_stre
   p.n = d->n; p.h = d->h; p.w = d->w; p.nsrc = d->nsrc;
   for (int s = 0; s < d->nsrc; ++s) {
     p.src[s] = d->src[s].ptr; p.src_c[s] = d->src[s].c; p.src_cstride[s] = d->src[s].cstride;
-    p.src_coffset[s] = d->src[s].coffset;
+    p.src_coffset[s] = d->src[s].coffset; p.src_mode[s] = d->src[s]._pad;   /* crfp_tc3_src.mode */
   }
   p.cout = d->cout; p.act = d->act;
   p.weight_hi = reinterpret_cast<const __nv_bfloat16*>(d->weight_hi);

@@ -88,7 +88,7 @@ static int layer_tc_kind(int li) {
     case L_DCN0_DCN: case L_DCN1_DCN: case L_DCN2_DCN:
       return 2;
     case L_FNET_E1_2: case L_FNET_E2_0: case L_FNET_E2_2: case L_FNET_E3_0: case L_FNET_D3_2: case L_FNET_F0:
-    case L_ENC_LR_2: case L_UPSAMPLE:
+    case L_ENC_LR_2: case L_UPSAMPLE: case L_DOWNSAMPLE:
       return 3;
     default:
       return 0;
@@ -121,7 +121,11 @@ struct CB {
     if (p.epi != EPI_STD || p.out_bf16 || p.cout <= 4) return false;
     int kc = 0;
     for (int s = 0; s < p.nsrc; ++s) {
-      if (p.src_mode[s] != CRFP_SRC_PLAIN) return false;
+      if (p.src_mode[s] == CRFP_SRC_UNSHUFFLE4) {
+        if (p.src_c[s] != 64 || p.src_cstride[s] != 4 || p.src_coffset[s] != 0) return false;
+      } else if (p.src_mode[s] != CRFP_SRC_PLAIN) {
+        return false;
+      }
       if (p.src_c[s] % 8 == 0) { kc += p.src_c[s] / 8; continue; }
       if (p.src_c[s] == 2 && s == p.nsrc - 1 && p.src_cstride[s] == 2 && p.src_coffset[s] == 0 && W_->layer_tc[li_].w_extra) continue;
       return false;
@@ -136,6 +140,7 @@ struct CB {
       if (p.src_c[s] % 8 == 0) {
         const int k = t.nsrc++;
         t.src[k] = p.src[s]; t.src_c[k] = p.src_c[s]; t.src_cstride[k] = p.src_cstride[s]; t.src_coffset[k] = p.src_coffset[s];
+        t.src_mode[k] = p.src_mode[s];
       } else {
         t.extra = p.src[s];
         t.w_extra = W_->layer_tc[li_].w_extra;

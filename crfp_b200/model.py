@@ -174,8 +174,17 @@ class _CRFPBase(nn.Module):
         mks = (mks != 0).to(torch.uint8).contiguous() if mks.dtype != torch.bool else mks.contiguous().view(torch.uint8)
         return lrs, fvs, mks
 
-    def _run_frames(self, buf, W, lrs, fvs, mks, fgs, out, first_flags):
+    def _run_frames(self, buf, W, lrs, fvs, mks, fgs, out, first_flags, out_host=None):
+        """Frame loop.  `out_host` (pinned CPU tensor shaped like `out`): every finished frame is copied to the host on a
+        side stream while the next frames are computed (device->host traffic overlaps the recurrence)."""
         lib = L.lib()
+        copy_stream = None
+        if out_host is not None:
+            if tuple(out_host.shape) != tuple(out.shape) or out_host.dtype != out.dtype or not out_host.is_pinned():
+                raise ValueError("out_host must be a pinned CPU tensor with the output's shape and dtype")
+            if getattr(self, "_copy_stream", None) is None or self._copy_stream.device != out.device:
+                self._copy_stream = torch.cuda.Stream(device=out.device)
+            copy_stream = self._copy_stream
         n, t, _, h, w = lrs.shape
         hw, HW = h * w, 64 * h * w
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -197,12 +206,22 @@ class _CRFPBase(nn.Module):
                 d.fg, d.fg_clip_stride = fgs.data_ptr() + i * HW * 4, t * HW
             d.out = out.data_ptr() + i * 3 * HW * 4
             L.check(lib.crfp_dsv_frame(C.byref(d), C.byref(W), ws.data_ptr(), ws.numel(), st), f"dsv_frame[{i}]")
+            if copy_stream is not None:
+                ev = torch.cuda.Event()
+                ev.record()
+                copy_stream.wait_event(ev)
+                with torch.cuda.stream(copy_stream):
+                    out_host[:, i].copy_(out[:, i], non_blocking=True)
+        if copy_stream is not None:
+            torch.cuda.current_stream().wait_stream(copy_stream)
 
 
 class CRFP_DSV(_CRFPBase):
     """Drop-in for `model.CRFP.CRFP_DSV` (the model main.py:34 builds)."""
 
-    def forward(self, lrs, fvs, mks):
+    def forward(self, lrs, fvs, mks, out_host=None):
+        """Reference signature `forward(lrs, fvs, mks)`; the optional `out_host` (pinned CPU tensor) additionally
+        streams every finished frame to the host while the recurrence continues."""
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
             raise NotImplementedError("crfp_b200: the backward kernels are not implemented yet; call under "
                                       "torch.no_grad() / model.eval() (SURVEY.md 8(f) rank 1)")
@@ -220,10 +239,10 @@ class CRFP_DSV(_CRFPBase):
                 L.check(L.lib().crfp_dsv_prepare(C.byref(shp), C.byref(W), lrs.data_ptr(), None, buf["lr4"].data_ptr(),
                                                  buf["x_lr"].data_ptr(), buf["flows"].data_ptr(), buf["ws"].data_ptr(),
                                                  buf["ws"].numel(), st), "dsv_prepare")
-                self._run_frames(buf, W, lrs, fvs, mks, None, out, [i == 0 for i in range(t)])
+                self._run_frames(buf, W, lrs, fvs, mks, None, out, [i == 0 for i in range(t)], out_host)
             return out
 
-    def forward_patch(self, lrs, fovea_patch, coords):
+    def forward_patch(self, lrs, fovea_patch, coords, out_host=None):
         """Convenience entry named by BASELINE.json: `fovea_patch` (n,t,3,FV,FV) pasted at integer top-left
         `coords` (n,t,2) = [y, x] exactly as the data loader does (dataset/reds.py:196-201)."""
         n, t, _, h, w = lrs.shape
@@ -236,7 +255,7 @@ class CRFP_DSV(_CRFPBase):
             for i in range(t):
                 y, x = int(cc[b, i, 0]), int(cc[b, i, 1])
                 fvs[b, i, :, y:y + fv, x:x + fv] = fovea_patch[b, i]
-        return self.forward(lrs, fvs, mks)
+        return self.forward(lrs, fvs, mks, out_host=out_host)
 
 
 class MRCF_simple_v18(_CRFPBase):

@@ -133,7 +133,7 @@ def split_bf16(x: torch.Tensor):
     return hi, lo
 
 
-def pack_conv_tc3(weight: torch.Tensor, bias: torch.Tensor, c_list, ci_lo: int = 0, extra: int = 0):
+def pack_conv_tc3(weight: torch.Tensor, bias: torch.Tensor, c_list, ci_lo: int = 0, extra: int = 0, modes=None):
     """OIHW fp32 -> (w_hi, w_lo bf16 [ntiles][9][kc][nt][8], bias fp32 [ntiles*nt], w_extra fp32 [9][extra][ntiles*nt])
     for crfp_conv3x3_tc3_fwd.  `c_list`: channels of the tensor-core sources (multiples of 8); `extra`: trailing
     input channels convolved on the CUDA cores (the 2 flow channels of dcn_block.0)."""
@@ -148,7 +148,9 @@ def pack_conv_tc3(weight: torch.Tensor, bias: torch.Tensor, c_list, ci_lo: int =
     kc += kc % 2
     w = weight.detach().to(torch.float32)
     wm = torch.zeros(ntiles * nt, kc * 8, 9, device=w.device)
-    wm[:cout, :k] = w[:, ci_lo:ci_lo + k].reshape(cout, k, 9)
+    idx = input_index_map(c_list, modes, ci_lo)[:k]           # packed K index -> original input channel
+    assert all(i >= 0 for i in idx)
+    wm[:cout, :k] = w[:, torch.tensor(idx, device=w.device)].reshape(cout, k, 9)
     packed = wm.view(ntiles, nt, kc, 8, 9).permute(0, 4, 2, 1, 3).contiguous()      # (tile, tap, kc, n, j)
     hi, lo = split_bf16(packed)
     b = torch.zeros(ntiles * nt, device=w.device, dtype=torch.float32)
@@ -200,7 +202,8 @@ def pack_layer_tc3(info: dict, sd):
     c_tc = [c for c in info["c"] if c % 8 == 0]
     extra = info["c"][-1] if info["c"][-1] % 8 else 0
     assert sum(c_tc) + extra == sum(info["c"]) and extra in (0, 2)
-    return pack_conv_tc3(w, b, c_tc, info["ci_lo"], extra)
+    m_tc = [m for c, m in zip(info["c"], info["mode"]) if c % 8 == 0]
+    return pack_conv_tc3(w, b, c_tc, info["ci_lo"], extra, m_tc)
 
 
 def pack_layer(info: dict, sd):

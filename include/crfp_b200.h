@@ -193,7 +193,9 @@ size_t crfp_sizeof_conv_tc_desc(void);
  */
 typedef struct {
   const float* ptr;
-  int32_t c, cstride, coffset, _pad;
+  int32_t c, cstride, coffset;
+  int32_t _pad; /* = mode: CRFP_SRC_PLAIN, or CRFP_SRC_UNSHUFFLE4 (dense 4-channel (4h x 4w) plane read through
+                   pixel_unshuffle(4): c = 64, cstride = 4, coffset = 0; packed channel order (dy*4+dx)*4 + ch) */
 } crfp_tc3_src;
 typedef struct {
   int32_t n, h, w;

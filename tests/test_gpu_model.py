@@ -83,6 +83,15 @@ def test_patch_coords_entry_and_determinism(model, sd):
     assert torch.equal(a, _run(model, lrs, fvs, mks))  # bitwise deterministic
 
 
+def test_out_host_streaming_copy(model):
+    lrs, fvs, mks, _ = make_clip(seed=17, n=2, t=3, h=16, w=24, fv_size=48)
+    ref = _run(model, lrs, fvs, mks)
+    host = torch.empty(ref.shape, dtype=torch.float32).pin_memory()
+    out = model(lrs.cuda(), fvs.cuda(), mks.cuda(), out_host=host)
+    torch.cuda.synchronize()
+    assert torch.equal(host, ref) and torch.equal(out.cpu(), ref)
+
+
 def test_clip_batch_equals_single_clips(model):
     """Clips are independent (the multi-GPU sharding unit): a batch of 3 equals three batch-1 runs bit for bit."""
     lrs, fvs, mks, _ = make_clip(seed=13, n=3, t=3, h=16, w=24, fv_size=48)

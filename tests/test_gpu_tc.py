@@ -215,3 +215,28 @@ def test_conv_tc3_epilogues():
     ref4 = F.leaky_relu(F.pixel_shuffle(F.conv2d(x24, w64, b64, padding=1), 4), 0.1) * 2.0
     got4 = nchw(ops.conv3x3_tc3_nhwc([f32(x24)], w64.cuda(), b64.cuda(), act=1, shuffle_r=4, post_scale=2.0))
     assert (got4 - ref4).abs().max().item() < 2e-4
+
+
+def test_conv_tc3_unshuffle_source():
+    """PixelUnShufflePack_v2 (pixel_unshuffle(4) + conv 64->32, CRFP.py:239-279) read straight from the 4-channel HR plane."""
+    import ctypes as C
+    from crfp_b200 import _lib as L
+    from crfp_b200.packing import pack_conv_tc3
+    g = _g(21)
+    n, h, w = 2, 13, 70
+    s_hr = torch.randn(n, 4, 4 * h, 4 * w, generator=g)
+    wt = torch.randn(32, 64, 3, 3, generator=g) * 0.06
+    b = torch.randn(32, generator=g) * 0.1
+    ref = F.conv2d(F.pixel_unshuffle(s_hr, 4), wt, b, padding=1)
+    x = s_hr.permute(0, 2, 3, 1).contiguous().cuda()
+    hi, lo, bp, _ = pack_conv_tc3(wt.cuda(), b.cuda(), [64], modes=[1])
+    out = torch.zeros(n, h, w, 32, device="cuda")
+    d = L.ConvTc3Desc()
+    d.n, d.h, d.w, d.nsrc = n, h, w, 1
+    d.src[0] = L.TcSrc(ptr=x.data_ptr(), c=64, cstride=4, coffset=0, _pad=1)
+    d.cout, d.act = 32, 0
+    d.weight_hi, d.weight_lo, d.bias = hi.data_ptr(), lo.data_ptr(), bp.data_ptr()
+    d.post_scale, d.out_kind, d.ndst = 1.0, L.TC_OUT_F32, 1
+    d.dst[0] = L.TcSrc(ptr=out.data_ptr(), c=32, cstride=32, coffset=0)
+    L.check(L.lib().crfp_conv3x3_tc3_fwd(C.byref(d), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "tc3 unshuffle")
+    assert (nchw(out) - ref).abs().max().item() < 2e-4
