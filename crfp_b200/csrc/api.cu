@@ -1,4 +1,5 @@
 // C-ABI plumbing: status strings, launch accounting, device check, public conv entry point.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -9,6 +10,10 @@ static thread_local cudaError_t g_last_err = cudaSuccess;
 static thread_local long long g_launches = 0;
 
 void note_cuda_error(cudaError_t e) { g_last_err = e; }
+bool pdl_enabled() {
+  static const bool on = (getenv("CRFP_NO_PDL") == nullptr);
+  return on;
+}
 void count_launch() { ++g_launches; }
 
 static int pad4(int c) { return (c + 3) & ~3; }

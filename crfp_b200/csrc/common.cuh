@@ -35,6 +35,22 @@ inline int check_launch() {
   } while (0)
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- programmatic dependent launch (PDL): every kernel of the frame chain is launched with
+// programmaticStreamSerialization so that its launch latency, CTA scheduling and constant-only prologue (weights ->
+// smem, TMEM allocation, mbarrier init) overlap the tail of the previous kernel; pdl_wait() (griddepcontrol.wait)
+// precedes the first access to any activation.  CRFP_NO_PDL=1 in the environment disables the attribute (A/B).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ---- internal conv description (superset of the public crfp_conv_desc)
@@ -160,6 +176,8 @@ int launch_flow_warp_bf16(const crfp_warp_desc& d, cudaStream_t st);
 int launch_flow_up2_dual(int n, int h, int w, const float* flow, float* out_f32, void* out_bf8, cudaStream_t st);
 
 // ---- device helpers
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ float lrelu01(float v) { return v > 0.f ? v : 0.1f * v; }
 
 __device__ __forceinline__ float apply_act(float v, int act) {

@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const TcParams P) {
   const int y_end = min(P.h, y_begin + P.rows_per_cta);
   const int slot_recs = KC * TCWP;
 
+  pdl_trigger();
   {  // weights slab of this cout tile + bias
     const uint4* gw = reinterpret_cast<const uint4*>(P.weight) + (size_t)cotile * 9 * KC * NT;
     for (int i = tid; i < 9 * KC * NT; i += 128) umma::cp_async16(sW + i, gw + i, 16u);
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const TcParams P) {
     umma::mbar_init(&bar, 1);
     umma::fence_mbar_init();
   }
+  pdl_wait();
   for (int r = -1; r <= 1; ++r) {
     tc_load_row(P, sA + ((y_begin + r) & 3) * slot_recs, n, y_begin + r, x0, tid);
     umma::cp_async_commit();
@@ -239,7 +241,7 @@ int launch_conv_tc(TcParams p, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
   dim3 grid(strips, segs, p.n * p.ntiles);
-  conv_tc_kernel<<<grid, 128, smem, st>>>(p);
+  launch_k(conv_tc_kernel, dim3(grid), dim3(128), (size_t)(smem), st, p);
   return check_launch();
 }
 

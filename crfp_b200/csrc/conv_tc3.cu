@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(128) conv_tc3_kernel(const Tc3Params P) {
   const int wrecs = 9 * KC * NT;          // records per weight half
   const int slot_recs = KC * T3WP;        // records per ring slot half
   const long long t_start = clock64();
+  pdl_trigger();
   uint4* sWh = reinterpret_cast<uint4*>(smem);
   uint4* sWl = sWh + wrecs;
   uint4* sAh = sWl + wrecs;               // [3 slots][KC][130]
@@ -243,6 +244,7 @@ __global__ void __launch_bounds__(128) conv_tc3_kernel(const Tc3Params P) {
     umma::mbar_init(&bar, 1);
     umma::fence_mbar_init();
   }
+  pdl_wait();
   // prologue: rows y_begin-1 and y_begin go through the staging buffer one after the other
   for (int r = -1; r <= 0; ++r) {
     const int yy = y_begin + r, sl = (yy + 3) % 3;
@@ -415,6 +417,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
   const int y_end = min(P.h, y_begin + P.rows_per_cta);
   const int rows_out = y_end - y_begin;
 
+  pdl_trigger();   // constant-only prologue below overlaps the previous kernel's tail (PDL)
   {
     const uint4* gwh = reinterpret_cast<const uint4*>(P.weight_hi) + (size_t)cotile * wrecs;
     const uint4* gwl = reinterpret_cast<const uint4*>(P.weight_lo) + (size_t)cotile * wrecs;
@@ -446,6 +449,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t taddr = tmem_base_s;
+  pdl_wait();      // activations (sources, residual, flow, destinations) are only touched from here on
 
   if (warp >= 5) {
     // ------------------------------------------------------------------ producers
@@ -616,7 +620,7 @@ int launch_conv_tc3(Tc3Params p, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc3_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
     dim3 grid(strips, segs, p.n * p.ntiles);
-    conv_tc3_ws_kernel<<<grid, WS_THREADS, smem, st>>>(p);
+    launch_k(conv_tc3_ws_kernel, dim3(grid), dim3(WS_THREADS), (size_t)(smem), st, p);
     return check_launch();
   }
   const size_t smem = tc3_smem_bytes(p.kc_real, p.kc_total, p.nt, p.extra != nullptr);
@@ -630,7 +634,7 @@ int launch_conv_tc3(Tc3Params p, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
   dim3 grid(strips, segs, p.n * p.ntiles);
-  conv_tc3_kernel<<<grid, 128, smem, st>>>(p);
+  launch_k(conv_tc3_kernel, dim3(grid), dim3(128), (size_t)(smem), st, p);
   return check_launch();
 }
 

@@ -87,9 +87,11 @@ __device__ __forceinline__ void thin_epilogue(const ConvParams& P, int n, int y,
 
 __global__ void __launch_bounds__(256) conv_thin_kernel(const ConvParams P) {
   extern __shared__ __align__(16) float s_w[];  // [9][cin_packed][4]
+  pdl_trigger();
   const int nw4 = 9 * P.cin_packed;
   for (int i = threadIdx.x + threadIdx.y * blockDim.x; i < nw4; i += blockDim.x * blockDim.y)
     reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(P.weight) + i);
+  pdl_wait();
   __syncthreads();
 
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -134,6 +136,8 @@ __global__ void __launch_bounds__(256, 3) conv_thin4_kernel(const ConvParams P) 
   const int tid = threadIdx.x + threadIdx.y * 32;
   const int n = blockIdx.z;
   const int x0 = blockIdx.x * TS, y0 = blockIdx.y * TS;
+  pdl_trigger();
+  pdl_wait();
   if (P.tile_flags != nullptr && P.tile_flags[((size_t)n * P.tiles_y + blockIdx.y) * P.tiles_x + blockIdx.x] == 0) {
     // tile outside the (dilated) fovea: the conv result would be multiplied by a zero mask
     if (P.tile_mode == 2) {
@@ -239,20 +243,20 @@ int launch_conv_thin(const ConvParams& p_in, cudaStream_t st) {
     dim3 grid(ceil_div(p.w, 32), ceil_div(p.h, 32), p.n);
     const size_t smem4 = ((size_t)nq * 34 * 35 + 9 * p.cin_packed) * 16;
     if (nq == 1) {
-      conv_thin4_kernel<1><<<grid, block, smem4, st>>>(p);
+      launch_k(conv_thin4_kernel<1>, dim3(grid), dim3(block), (size_t)(smem4), st, p);
     } else if (nq == 2) {
       cudaFuncSetAttribute(conv_thin4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
-      conv_thin4_kernel<2><<<grid, block, smem4, st>>>(p);
+      launch_k(conv_thin4_kernel<2>, dim3(grid), dim3(block), (size_t)(smem4), st, p);
     } else {
       cudaFuncSetAttribute(conv_thin4_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
-      conv_thin4_kernel<3><<<grid, block, smem4, st>>>(p);
+      launch_k(conv_thin4_kernel<3>, dim3(grid), dim3(block), (size_t)(smem4), st, p);
     }
     return check_launch();
   }
   dim3 grid(ceil_div(p.w, 32), ceil_div(p.h, 8), p.n);
   const size_t smem = (size_t)9 * p.cin_packed * 4 * sizeof(float);
   if (smem > 48 * 1024) return CRFP_ERR_UNSUPPORTED;
-  conv_thin_kernel<<<grid, block, smem, st>>>(p);
+  launch_k(conv_thin_kernel, dim3(grid), dim3(block), (size_t)(smem), st, p);
   return check_launch();
 }
 

@@ -27,6 +27,8 @@ struct WideSmem {
 
 template <int RPT>
 __global__ void __launch_bounds__(256, 2) conv_wide_kernel(const ConvParams P) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int TH = 2 * RPT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WideSmem<RPT>& S = *reinterpret_cast<WideSmem<RPT>*>(smem_raw);
@@ -209,7 +211,7 @@ int launch_conv_wide(const ConvParams& p, cudaStream_t st) {
       cudaFuncSetAttribute(conv_wide_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       attr8 = true;
     }
-    conv_wide_kernel<8><<<grid, 256, smem, st>>>(p);
+    launch_k(conv_wide_kernel<8>, dim3(grid), dim3(256), (size_t)(smem), st, p);
   } else {
     dim3 grid(ceil_div(p.w, TW), ceil_div(p.h, 8), p.n * co_tiles);
     size_t smem = sizeof(WideSmem<4>);
@@ -218,7 +220,7 @@ int launch_conv_wide(const ConvParams& p, cudaStream_t st) {
       cudaFuncSetAttribute(conv_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       attr4 = true;
     }
-    conv_wide_kernel<4><<<grid, 256, smem, st>>>(p);
+    launch_k(conv_wide_kernel<4>, dim3(grid), dim3(256), (size_t)(smem), st, p);
   }
   return check_launch();
 }

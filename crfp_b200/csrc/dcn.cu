@@ -68,8 +68,10 @@ __global__ void __launch_bounds__(256, 2) dcn_l1_kernel(const crfp_dcn_desc D) {
   const int n = blockIdx.y;
   const int x0 = tx * DT, y0 = ty * DT;
 
+  pdl_trigger();
   for (int i = tid; i < DK * DCO / 4; i += 256)
     reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(D.weight) + i);
+  pdl_wait();
 
   // ---- phase 1: gather.  64 px * 72 (group,tap) samples, 18 rounds of 256 threads
   const float* img = D.x + (size_t)n * D.h * D.w * D.x_cstride + D.x_coffset;
@@ -152,8 +154,10 @@ __global__ void __launch_bounds__(256) dcn_hr_kernel(const crfp_dcn_desc D) {
   __shared__ float4 s_w[36];  // [k = t*4 + c][co 0..3]
   __shared__ float4 s_b;
   const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+  pdl_trigger();
   if (tid < 36) s_w[tid] = __ldg(reinterpret_cast<const float4*>(D.weight) + tid);
   if (tid == 36) s_b = __ldg(reinterpret_cast<const float4*>(D.bias));
+  pdl_wait();
   __syncthreads();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -211,13 +215,13 @@ int launch_dcn(const crfp_dcn_desc& d, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(dcn_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
     dim3 grid(ceil_div(d.w, DT) * ceil_div(d.h, DT), d.n);
-    dcn_l1_kernel<<<grid, 256, smem, st>>>(d);
+    launch_k(dcn_l1_kernel, dim3(grid), dim3(256), (size_t)(smem), st, d);
     return check_launch();
   }
   if (d.c == 4 && d.dg == 1 && d.cout == 4) {
     if ((d.x_cstride | d.x_coffset | d.out_cstride | d.out_coffset) & 3) return CRFP_ERR_BAD_SHAPE;
     dim3 block(32, 8), grid(ceil_div(d.w, 32), ceil_div(d.h, 8), d.n);
-    dcn_hr_kernel<<<grid, block, 0, st>>>(d);
+    launch_k(dcn_hr_kernel, dim3(grid), dim3(block), (size_t)(0), st, d);
     return check_launch();
   }
   return CRFP_ERR_UNSUPPORTED;

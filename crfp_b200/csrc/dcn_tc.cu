@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(256, 1) dcn_tc_kernel(const DcnTcParams P) {
   const int n = blockIdx.y;
   const int x0t = tx * DTW, y0t = ty * DTH;
 
+  pdl_trigger();
   for (int i = tid; i < DKC * 32; i += 256) umma::cp_async16(sB + i, reinterpret_cast<const uint4*>(P.weight) + i, 16u);
   umma::cp_async_commit();
   if (tid < 32) s_bias[tid] = P.bias[tid];
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(256, 1) dcn_tc_kernel(const DcnTcParams P) {
     umma::fence_mbar_init();
   }
 
+  pdl_wait();
   // ---- gather: 128 px x 36 chunks = 4608 records, 18 per thread; consecutive lanes = consecutive kc of one pixel
   const __nv_bfloat16* img = P.x + (size_t)n * P.h * P.w * P.x_cstride + P.x_coffset;
 #pragma unroll 2
@@ -267,6 +269,19 @@ __global__ void __launch_bounds__(512, 1) dcn_tc3_kernel(const DcnTc3Params P) {
   const int n = blockIdx.y;
   const int x0t = tx * DTW, y0t = ty * DTH;
 
+  // constant-only prologue (overlaps the previous kernel under PDL): weights -> smem, bias, TMEM, barrier
+  pdl_trigger();
+  for (int i = tid; i < DKC * 32; i += 512) {
+    umma::cp_async16(sBh + i, reinterpret_cast<const uint4*>(P.w_hi) + i, 16u);
+    umma::cp_async16(sBl + i, reinterpret_cast<const uint4*>(P.w_lo) + i, 16u);
+  }
+  if (tid < 32) s_bias[tid] = P.bias[tid];
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 32);
+  if (tid == 0) {
+    umma::mbar_init(&bar, 1);
+    umma::fence_mbar_init();
+  }
+  pdl_wait();
   // window origin: tile - reach, shifted by the rounded flow at the tile centre (the offsets are flow + residual)
   int wy0 = y0t - DWR, wx0 = x0t - DWR;
   if (P.flow_hint != nullptr) {
@@ -275,19 +290,8 @@ __global__ void __launch_bounds__(512, 1) dcn_tc3_kernel(const DcnTc3Params P) {
     wy0 += (int)rintf(fminf(fmaxf(fl.y, -4096.f), 4096.f));
     wx0 += (int)rintf(fminf(fmaxf(fl.x, -4096.f), 4096.f));
   }
-
-  for (int i = tid; i < DKC * 32; i += 512) {
-    umma::cp_async16(sBh + i, reinterpret_cast<const uint4*>(P.w_hi) + i, 16u);
-    umma::cp_async16(sBl + i, reinterpret_cast<const uint4*>(P.w_lo) + i, 16u);
-  }
   dcn_load_window(P, sWin, n, wy0, wx0, 0, tid);
   umma::cp_async_commit();
-  if (tid < 32) s_bias[tid] = P.bias[tid];
-  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 32);
-  if (tid == 0) {
-    umma::mbar_init(&bar, 1);
-    umma::fence_mbar_init();
-  }
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
@@ -399,7 +403,7 @@ int launch_dcn_tc3(const crfp_dcn_desc& d, const void* w_lo, const float* flow_h
   cudaError_t e = cudaFuncSetAttribute(dcn_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
   dim3 grid(ceil_div(d.w, DTW) * ceil_div(d.h, DTH), d.n);
-  dcn_tc3_kernel<<<grid, 512, smem, st>>>(p);
+  launch_k(dcn_tc3_kernel, dim3(grid), dim3(512), (size_t)(smem), st, p);
   return check_launch();
 }
 
@@ -419,7 +423,7 @@ int launch_dcn_tc(const crfp_dcn_desc& d, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(dcn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
   dim3 grid(ceil_div(d.w, DTW) * ceil_div(d.h, DTH), d.n);
-  dcn_tc_kernel<<<grid, 256, smem, st>>>(p);
+  launch_k(dcn_tc_kernel, dim3(grid), dim3(256), (size_t)(smem), st, p);
   return check_launch();
 }
 

@@ -229,6 +229,8 @@ __global__ void __launch_bounds__(256) fovea_compose_kernel(int n, int H, int W,
                                                             long long mks_cs, const float* __restrict__ lr4,
                                                             long long lr4_cs, float* __restrict__ out,
                                                             const uint8_t* __restrict__ flags, int tiles_x, int tiles_y) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)n * H * W;
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= total) return;
@@ -263,6 +265,8 @@ __global__ void __launch_bounds__(256) fovea_compose_kernel(int n, int H, int W,
 // field of encoder_hr.0 -> encoder_hr.2 -> conv_tttf around every mask pixel)
 __global__ void __launch_bounds__(256) fovea_tile_flags_kernel(int H, int W, const uint8_t* __restrict__ mks, long long mks_cs,
                                                                int tiles_x, int tiles_y, uint8_t* __restrict__ flags) {
+  pdl_trigger();
+  pdl_wait();
   const int tx = blockIdx.x, ty = blockIdx.y, b = blockIdx.z;
   const int x_lo = max(0, tx * 32 - 32), x_hi = min(W, tx * 32 + 64);
   const int y_lo = max(0, ty * 32 - 32), y_hi = min(H, ty * 32 + 64);
@@ -280,7 +284,7 @@ __global__ void __launch_bounds__(256) fovea_tile_flags_kernel(int H, int W, con
 static int launch_compose(int n, int H, int W, const crfp_dsv_frame_desc* d, float* out, const uint8_t* flags, int tiles_x,
                           int tiles_y, cudaStream_t st) {
   const long long total = (long long)n * H * W;
-  fovea_compose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, H, W, d->fvs, d->fvs_clip_stride, d->mks,
+  launch_k(fovea_compose_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), st, n, H, W, d->fvs, d->fvs_clip_stride, d->mks,
                                                                        d->mks_clip_stride, d->lr4, d->lr4_clip_stride,
                                                                        out, flags, tiles_x, tiles_y);
   return check_launch();
@@ -289,6 +293,8 @@ static int launch_compose(int n, int H, int W, const crfp_dsv_frame_desc* d, flo
 // gather `n` strided images into a contiguous run (used to make per-frame slices of clip tensors dense)
 __global__ void __launch_bounds__(256) gather_images_kernel(int n, long long per_image, const float* __restrict__ in,
                                                             long long in_stride, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)n * per_image;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(256) gather_images_kernel(int n, long long per
 
 static int gather_images(int n, long long per_image, const float* in, long long in_stride, float* out, cudaStream_t st) {
   const long long total = (long long)n * per_image;
-  gather_images_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, per_image, in, in_stride, out);
+  launch_k(gather_images_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), st, n, per_image, in, in_stride, out);
   return check_launch();
 }
 
@@ -747,7 +753,7 @@ extern "C" int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weigh
   const uint8_t* flags = nullptr;
   if (d->skip_outside_fovea) {
     uint8_t* fl = reinterpret_cast<uint8_t*>(f.tile_flags);
-    fovea_tile_flags_kernel<<<dim3(tiles_x, tiles_y, n), 256, 0, st>>>(H, Wd, d->mks, d->mks_clip_stride, tiles_x, tiles_y, fl);
+    launch_k(fovea_tile_flags_kernel, dim3(dim3(tiles_x, tiles_y, n)), dim3(256), (size_t)(0), st, H, Wd, d->mks, d->mks_clip_stride, tiles_x, tiles_y, fl);
     CRFP_TRY(check_launch());
     flags = fl;
   }

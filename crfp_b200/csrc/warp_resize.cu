@@ -18,6 +18,8 @@ __device__ __forceinline__ float warp_coord(int i, float f, int size) {
 }
 
 __global__ void __launch_bounds__(256) flow_warp_kernel(const crfp_warp_desc D) {
+  pdl_trigger();
+  pdl_wait();
   const int cq = D.c >> 2;
   const long long total = (long long)D.n * D.h * D.w * cq;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,6 +61,8 @@ __global__ void __launch_bounds__(256) flow_warp_kernel(const crfp_warp_desc D) 
 
 __global__ void __launch_bounds__(256) flow_warp_indices_kernel(int n, int h, int w, const float* __restrict__ flow,
                                                                 int32_t* __restrict__ x0, int32_t* __restrict__ y0) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)n * h * w;
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= total) return;
@@ -72,6 +76,8 @@ __global__ void __launch_bounds__(256) flow_warp_indices_kernel(int n, int h, in
 __global__ void __launch_bounds__(256) resize_bilinear_kernel(int n, int hin, int win, int c, const float* __restrict__ in,
                                                               int hout, int wout, float rh, float rw, float mul,
                                                               float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)n * hout * wout * c;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -93,6 +99,8 @@ __global__ void __launch_bounds__(256) resize_bilinear_kernel(int n, int hin, in
 
 __global__ void __launch_bounds__(256) avgpool2_kernel(int n, int hin, int win, int c, const float* __restrict__ in,
                                                        float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int ho = hin >> 1, wo = win >> 1;
   const long long total = (long long)n * ho * wo * c;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -109,6 +117,8 @@ __global__ void __launch_bounds__(256) avgpool2_kernel(int n, int hin, int win, 
 
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(int n, int c, int h, int w, const float* __restrict__ in,
                                                            long long in_image_stride, int cpad, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)n * h * w;
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= total) return;
@@ -123,6 +133,8 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(int n, int c, int h, 
 __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(int n, int c, int h, int w, const float* __restrict__ in,
                                                            int cs, int co, float* __restrict__ out,
                                                            long long out_image_stride) {
+  pdl_trigger();
+  pdl_wait();
   const long long hw = (long long)h * w;
   const long long total = (long long)n * hw * c;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -135,6 +147,8 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(int n, int c, int h, 
 
 // ---- bf16 flow_warp: thread = (pixel, 8-channel chunk); fp32 positions / weights, bf16 storage
 __global__ void __launch_bounds__(256) flow_warp_bf16_kernel(const crfp_warp_desc D) {
+  pdl_trigger();
+  pdl_wait();
   const int cq = D.c >> 3;
   const long long total = (long long)D.n * D.h * D.w * cq;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -179,6 +193,8 @@ __global__ void __launch_bounds__(256) flow_warp_bf16_kernel(const crfp_warp_des
 // [fx, fy, 0 x6] (third source of the tensor-core dcn_block conv)
 __global__ void __launch_bounds__(256) flow_up2_dual_kernel(int n, int h, int w, const float* __restrict__ flow,
                                                             float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf8) {
+  pdl_trigger();
+  pdl_wait();
   const int ho = 2 * h, wo = 2 * w;
   const long long total = (long long)n * ho * wo;
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,13 +224,13 @@ int launch_flow_warp_bf16(const crfp_warp_desc& d, cudaStream_t st) {
   if (d.c % 8 || ((d.x_cstride | d.x_coffset | d.out_cstride | d.out_coffset) & 7)) return CRFP_ERR_BAD_SHAPE;
   const long long total = (long long)d.n * d.h * d.w * (d.c / 8);
   if (total == 0) return CRFP_OK;
-  flow_warp_bf16_kernel<<<grid1d(total), 256, 0, st>>>(d);
+  launch_k(flow_warp_bf16_kernel, dim3(grid1d(total)), dim3(256), (size_t)(0), st, d);
   return check_launch();
 }
 
 int launch_flow_up2_dual(int n, int h, int w, const float* flow, float* out_f32, void* out_bf8, cudaStream_t st) {
   const long long total = (long long)n * 4 * h * w;
-  flow_up2_dual_kernel<<<grid1d(total), 256, 0, st>>>(n, h, w, flow, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf8));
+  launch_k(flow_up2_dual_kernel, dim3(grid1d(total)), dim3(256), (size_t)(0), st, n, h, w, flow, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf8));
   return check_launch();
 }
 
@@ -222,7 +238,7 @@ int launch_flow_warp(const crfp_warp_desc& d, cudaStream_t st) {
   if (d.c % 4 || ((d.x_cstride | d.x_coffset | d.out_cstride | d.out_coffset) & 3)) return CRFP_ERR_BAD_SHAPE;
   const long long total = (long long)d.n * d.h * d.w * (d.c / 4);
   if (total == 0) return CRFP_OK;
-  flow_warp_kernel<<<grid1d(total), 256, 0, st>>>(d);
+  launch_k(flow_warp_kernel, dim3(grid1d(total)), dim3(256), (size_t)(0), st, d);
   return check_launch();
 }
 
@@ -256,7 +272,7 @@ extern "C" int crfp_resize_bilinear(int n, int hin, int win, int c, const float*
   if (!in || !out) return CRFP_ERR_NULL;
   if (n <= 0 || hin <= 0 || win <= 0 || c <= 0 || hout <= 0 || wout <= 0) return CRFP_ERR_BAD_SHAPE;
   const long long total = (long long)n * hout * wout * c;
-  resize_bilinear_kernel<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(n, hin, win, c, in, hout, wout, rscale_h,
+  launch_k(resize_bilinear_kernel, dim3(grid1d(total)), dim3(256), (size_t)(0), (cudaStream_t)stream, n, hin, win, c, in, hout, wout, rscale_h,
                                                                          rscale_w, mul, out);
   return check_launch();
 }
@@ -265,7 +281,7 @@ extern "C" int crfp_avgpool2(int n, int hin, int win, int c, const float* in, fl
   if (!in || !out) return CRFP_ERR_NULL;
   if (n <= 0 || hin < 2 || win < 2 || c <= 0) return CRFP_ERR_BAD_SHAPE;
   const long long total = (long long)n * (hin / 2) * (win / 2) * c;
-  avgpool2_kernel<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(n, hin, win, c, in, out);
+  launch_k(avgpool2_kernel, dim3(grid1d(total)), dim3(256), (size_t)(0), (cudaStream_t)stream, n, hin, win, c, in, out);
   return check_launch();
 }
 
@@ -273,7 +289,7 @@ extern "C" int crfp_nchw_to_nhwc(int n, int c, int h, int w, const float* in, lo
                                  float* out, crfp_stream stream) {
   if (!in || !out) return CRFP_ERR_NULL;
   if (n <= 0 || c <= 0 || h <= 0 || w <= 0 || cpad < c) return CRFP_ERR_BAD_SHAPE;
-  nchw_to_nhwc_kernel<<<grid1d((long long)n * h * w), 256, 0, (cudaStream_t)stream>>>(n, c, h, w, in, in_image_stride,
+  launch_k(nchw_to_nhwc_kernel, dim3(grid1d((long long)n * h * w)), dim3(256), (size_t)(0), (cudaStream_t)stream, n, c, h, w, in, in_image_stride,
                                                                                     cpad, out);
   return check_launch();
 }
@@ -282,7 +298,7 @@ extern "C" int crfp_nhwc_to_nchw(int n, int c, int h, int w, const float* in, in
                                  float* out, long long out_image_stride, crfp_stream stream) {
   if (!in || !out) return CRFP_ERR_NULL;
   if (n <= 0 || c <= 0 || h <= 0 || w <= 0) return CRFP_ERR_BAD_SHAPE;
-  nhwc_to_nchw_kernel<<<grid1d((long long)n * h * w * c), 256, 0, (cudaStream_t)stream>>>(n, c, h, w, in, in_cstride,
+  launch_k(nhwc_to_nchw_kernel, dim3(grid1d((long long)n * h * w * c)), dim3(256), (size_t)(0), (cudaStream_t)stream, n, c, h, w, in, in_cstride,
                                                                                         in_coffset, out,
                                                                                         out_image_stride);
   return check_launch();
