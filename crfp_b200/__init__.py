@@ -1,12 +1,12 @@
 """crfp_b200 — B200 (sm_100a) implementation of CRFP's recurrent cross-resolution propagation hot path.
 
 Public surface (mirrors the reference's module API, /root/reference/model/CRFP.py and CRFP_test.py):
-    CRFP_DSV(device, mid_channels=32, ...).forward(lrs, fvs, mks)
+    CRFP_DSV / CRFP / CRFP_simple (device, mid_channels=32, ...).forward(lrs, fvs, mks)
     MRCF_simple_v18(...).forward(lrs, fvs, mks, fgs) / clear_states()
     flow_warp(x, flow), DCNv2(...)(input, offset, mask)
 Everything below these signatures runs in libcrfp_b200.so (include/crfp_b200.h); there is no CPU fallback.
 """
-from .model import CRFP_DSV, MRCF_simple_v18  # noqa: F401
+from .model import CRFP, CRFP_DSV, CRFP_simple, MRCF_simple_v18  # noqa: F401
 from .ops import DCNv2, flow_warp  # noqa: F401
 
-__all__ = ["CRFP_DSV", "MRCF_simple_v18", "DCNv2", "flow_warp"]
+__all__ = ["CRFP_DSV", "CRFP", "CRFP_simple", "MRCF_simple_v18", "DCNv2", "flow_warp"]

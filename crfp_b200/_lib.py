@@ -99,7 +99,7 @@ class LayerTc(C.Structure):
 
 
 class DsvWeights(C.Structure):
-    _fields_ = [("mid_channels", C.c_int32), ("nlayers", C.c_int32), ("precision", C.c_int32), ("_pad", C.c_int32),
+    _fields_ = [("mid_channels", C.c_int32), ("nlayers", C.c_int32), ("precision", C.c_int32), ("variant", C.c_int32),
                 ("layer", Layer * MAX_LAYERS), ("layer_tc", LayerTc * MAX_LAYERS)]
 
 
@@ -165,6 +165,7 @@ SYMBOLS = {
                                     C.c_longlong, C.c_void_p]),
     "crfp_dsv_num_layers": (C.c_int, []),
     "crfp_dsv_layer_info": (C.c_int, [C.c_int, C.POINTER(LayerInfo)]),
+    "crfp_layer_info_variant": (C.c_int, [C.c_int, C.c_int, C.POINTER(LayerInfo)]),
     "crfp_dsv_prepare_workspace": (C.c_size_t, [C.POINTER(DsvShape)]),
     "crfp_dsv_prepare": (C.c_int, [C.POINTER(DsvShape), C.POINTER(DsvWeights), C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -211,13 +212,16 @@ def check(status: int, what: str = "") -> None:
         raise CrfpError(f"libcrfp_b200 {what} failed: {msg} ({status})")
 
 
-def layer_table():
-    """[(key, key2, kind, [c...], [mode...], cout, ci_lo, dg, thin)] as exported by the library."""
+VARIANTS = {"dsv": 0, "v15": 1, "v13": 2}
+
+
+def layer_table(variant: str = "dsv"):
+    """[(key, key2, kind, [c...], [mode...], cout, ci_lo, dg, thin, tc)] of a model variant, as exported by the library."""
     h = lib()
     out = []
     for i in range(h.crfp_dsv_num_layers()):
         info = LayerInfo()
-        check(h.crfp_dsv_layer_info(i, C.byref(info)), "layer_info")
+        check(h.crfp_layer_info_variant(VARIANTS[variant], i, C.byref(info)), "layer_info")
         out.append(dict(key=info.key.decode(), key2=info.key2.decode() if info.key2 else None, kind=info.kind,
                         c=[info.c[j] for j in range(info.nsrc)], mode=[info.mode[j] for j in range(info.nsrc)],
                         cout=info.cout, ci_lo=info.ci_lo, dg=info.dg, thin=info.thin, tc=info.tc))

@@ -74,6 +74,30 @@ static const crfp_layer_info kLayers[L_COUNT] = {
     CONV1("conv_last", 4, 3),
 };
 
+// ---- per-variant layer tables: CRFP (v15) / CRFP_simple (v13) reuse DSV's modules with different widths
+static crfp_layer_info g_tables[3][L_COUNT];
+static bool g_tables_ready = false;
+static int layer_tc_kind(int li);
+static const crfp_layer_info* layer_table(int variant) {
+  if (!g_tables_ready) {
+    for (int v = 0; v < 3; ++v) {
+      for (int i = 0; i < L_COUNT; ++i) { g_tables[v][i] = kLayers[i]; g_tables[v][i].tc = layer_tc_kind(i); }
+      if (v == CRFP_VARIANT_DSV) continue;
+      crfp_layer_info* T = g_tables[v];
+      T[L_UPSAMPLE].cout = 128;                                       // PixelShufflePack(32 -> 32, x2)
+      T[L_UPSAMPLE_POST].c[0] = 32;                                   // PixelShufflePack(32 -> 4, x4)
+      static const int rin[3] = {L_RES0_IN, L_RES1_IN, L_RES2_IN}, rfi[3] = {L_RES0_IN_FIRST, L_RES1_IN_FIRST, L_RES2_IN_FIRST};
+      for (int k = 0; k < 3; ++k) {
+        T[rfi[k]].c[0] = 32;
+        if (v == CRFP_VARIANT_V15) { T[rin[k]].nsrc = 3; T[rin[k]].c[2] = 32; T[rin[k]].tc = 0; }   // 96 input channels: SIMT
+      }
+      if (v == CRFP_VARIANT_V15) { T[L_RES3_IN].nsrc = 3; T[L_RES3_IN].c[2] = 4; }
+    }
+    g_tables_ready = true;
+  }
+  return g_tables[(variant >= 0 && variant < 3) ? variant : 0];
+}
+
 // tensor-core packing kind per layer: 0 none, 1 conv_tc (pack_conv_tc over the same source split), 2 dcn_tc
 static int layer_tc_kind(int li) {
   switch (li) {
@@ -111,7 +135,7 @@ struct CB {
     return *this;
   }
   CB& layer(const crfp_dsv_weights* w, int li) {
-    p.weight = w->layer[li].w; p.bias = w->layer[li].b; p.cout = kLayers[li].cout;
+    p.weight = w->layer[li].w; p.bias = w->layer[li].b; p.cout = layer_table(w->variant)[li].cout;
     W_ = w; li_ = li;
     return *this;
   }
@@ -200,7 +224,7 @@ struct TB {
   }
   TB& layer(const crfp_dsv_weights* w, int li) {
     p.weight = reinterpret_cast<const __nv_bfloat16*>(w->layer_tc[li].w_hi); p.bias = w->layer_tc[li].b;
-    p.cout = kLayers[li].cout;
+    p.cout = layer_table(w->variant)[li].cout;
     return *this;
   }
   TB& act(int a) { p.act = a; return *this; }
@@ -406,6 +430,95 @@ static size_t carve_frame(const crfp_dsv_shape* s, void* ws, FrameWs* f) {
 }
 
 
+// L1 stage of CRFP (v15, model/CRFP.py:1260-1340) and CRFP_simple (v13, model/CRFP.py:968-1050): no DSV split; the HR
+// state is warped first and both the state and its warp go through `downsample`; v15 feeds the warped planes into
+// every residual block as a third concat source.  Same kernels, same hand-off (q, po, S0_w, flow_hr) to the HR stage.
+static int frame_l1_v1x(const crfp_dsv_frame_desc* d, const crfp_dsv_weights* W, const FrameWs& f, const float* x_lr,
+                        cudaStream_t st) {
+  const crfp_dsv_shape* s = &d->shape;
+  const int n = s->n, h = s->h, w = s->w;
+  const int h1 = 2 * h, w1 = 2 * w, H = 8 * h, Wd = 8 * w;
+  const size_t hw = (size_t)h * w;
+  const bool three = (W->variant == CRFP_VARIANT_V15);
+  static const int lr1[3] = {L_RES0_C1, L_RES1_C1, L_RES2_C1};
+  static const int lr2[3] = {L_RES0_C2, L_RES1_C2, L_RES2_C2};
+  float* cur = f.cur[0];
+  CRFP_TRY(CB(n, h, w).src(x_lr, 32, 32).layer(W, L_UPSAMPLE).shuffle(2).dst(cur, 32, 32).run(st));
+  if (!d->first) {
+    const float* flow = d->flow;
+    if (n > 1 && d->flow_clip_stride != (long long)(hw * 2)) {
+      CRFP_TRY(gather_images(n, (long long)hw * 2, d->flow, d->flow_clip_stride, f.flow_d, st));
+      flow = f.flow_d;
+    }
+    CRFP_TRY(crfp_resize_bilinear(n, h, w, 2, flow, h1, w1, 0.5f, 0.5f, 2.f, f.flow_l1, st));
+    CRFP_TRY(crfp_resize_bilinear(n, h, w, 2, flow, H, Wd, 0.125f, 0.125f, 8.f, f.flow_hr, st));
+    crfp_warp_desc wd;
+    memset(&wd, 0, sizeof(wd));
+    wd.n = n; wd.h = H; wd.w = Wd; wd.c = 4; wd.x = d->state_hr; wd.x_cstride = 4; wd.flow = f.flow_hr;
+    wd.out = f.S0_w; wd.out_cstride = 4;
+    CRFP_TRY(launch_flow_warp(wd, st));
+    CRFP_TRY(CB(n, h1, w1).src(f.S0_w, 64, 4, 0, CRFP_SRC_UNSHUFFLE4).layer(W, L_DOWNSAMPLE).dst(f.P_w, 32, 32).run(st));
+    CRFP_TRY(CB(n, h1, w1).src(d->state_hr, 64, 4, 0, CRFP_SRC_UNSHUFFLE4).layer(W, L_DOWNSAMPLE).dst(f.P, 32, 32).run(st));
+    static const int lb0[3] = {L_DCN0_B0, L_DCN1_B0, L_DCN2_B0};
+    static const int lb2[3] = {L_DCN0_B2, L_DCN1_B2, L_DCN2_B2};
+    static const int lfu[3] = {-1, L_DCN1_FUSE, L_DCN2_FUSE};
+    static const int lhd[3] = {L_DCN0_HEADS, L_DCN1_HEADS, L_DCN2_HEADS};
+    static const int ldc[3] = {L_DCN0_DCN, L_DCN1_DCN, L_DCN2_DCN};
+    static const int lri[3] = {L_RES0_IN, L_RES1_IN, L_RES2_IN};
+    const float* offfeat = nullptr;
+    for (int k = 0; k < 3; ++k) {
+      CRFP_TRY(CB(n, h1, w1).src(cur, 32, 32).src(f.P_w, 32, 32).src(f.flow_l1, 2, 2).layer(W, lb0[k])
+                   .act(CRFP_ACT_LRELU).dst(f.t1, 32, 32).run(st));
+      float* z = f.offf[k & 1];
+      if (k == 0) {
+        CRFP_TRY(CB(n, h1, w1).src(f.t1, 32, 32).layer(W, lb2[k]).act(CRFP_ACT_LRELU).dst(z, 32, 32).run(st));
+      } else {
+        CRFP_TRY(CB(n, h1, w1).src(f.t1, 32, 32).layer(W, lb2[k]).act(CRFP_ACT_LRELU).dst(f.t2, 32, 32).run(st));
+        CRFP_TRY(CB(n, h1, w1).src(f.t2, 32, 32).src(offfeat, 32, 32).layer(W, lfu[k]).act(CRFP_ACT_LRELU)
+                     .dst(z, 32, 32).run(st));
+      }
+      offfeat = z;
+      CRFP_TRY(CB(n, h1, w1).src(z, 32, 32).layer(W, lhd[k]).head(f.flow_l1, 144, 10.f).dst(f.om, 216, 216).run(st));
+      crfp_dcn_desc dd;
+      memset(&dd, 0, sizeof(dd));
+      dd.n = n; dd.h = h1; dd.w = w1; dd.c = 32; dd.cout = 32; dd.dg = 8;
+      dd.x = f.P; dd.x_cstride = 32;
+      dd.offset = f.om; dd.off_cstride = 216; dd.off_coffset = 0;
+      dd.mask = f.om; dd.mask_cstride = 216; dd.mask_coffset = 144;
+      dd.weight = W->layer[ldc[k]].w; dd.bias = W->layer[ldc[k]].b;
+      dd.out = f.A; dd.out_cstride = 32;
+      if (W->precision == CRFP_PREC_TC3 && W->layer_tc[ldc[k]].w_hi && W->layer_tc[ldc[k]].w_lo) {
+        dd.weight = reinterpret_cast<const float*>(W->layer_tc[ldc[k]].w_hi); dd.bias = W->layer_tc[ldc[k]].b;
+        CRFP_TRY(launch_dcn_tc3(dd, W->layer_tc[ldc[k]].w_lo, f.flow_l1, st));
+      } else {
+        CRFP_TRY(launch_dcn(dd, st));
+      }
+      CB in(n, h1, w1);
+      in.src(cur, 32, 32).src(f.A, 32, 32);
+      if (three) in.src(f.P_w, 32, 32);
+      in.layer(W, lri[k]).act(CRFP_ACT_LRELU).dst(f.r0, 32, 32);
+      CRFP_TRY(in.run(st));
+      CRFP_TRY(CB(n, h1, w1).src(f.r0, 32, 32).layer(W, lr1[k]).act(CRFP_ACT_RELU).dst(f.r1, 32, 32).run(st));
+      float* nxt = f.cur[(k + 1) % 3];
+      CRFP_TRY(CB(n, h1, w1).src(f.r1, 32, 32).layer(W, lr2[k]).res(f.r0, 32).dst(nxt, 32, 32).run(st));
+      cur = nxt;
+    }
+    CRFP_TRY(CB(n, h1, w1).src(cur, 32, 32).layer(W, L_UPSAMPLE_POST).act(CRFP_ACT_LRELU).shuffle(4).dst(f.q, 4, 4).run(st));
+    CRFP_TRY(CB(n, h1, w1).src(offfeat, 32, 32).layer(W, L_DCN3_UP).shuffle(4).scale(2.f).dst(f.po, 4, 4).run(st));
+  } else {
+    static const int lrf[3] = {L_RES0_IN_FIRST, L_RES1_IN_FIRST, L_RES2_IN_FIRST};
+    for (int k = 0; k < 3; ++k) {   // cat([cur, zeros, ...]): only weight[:, :32] contributes   (CRFP.py:1342-1356)
+      CRFP_TRY(CB(n, h1, w1).src(cur, 32, 32).layer(W, lrf[k]).act(CRFP_ACT_LRELU).dst(f.r0, 32, 32).run(st));
+      CRFP_TRY(CB(n, h1, w1).src(f.r0, 32, 32).layer(W, lr1[k]).act(CRFP_ACT_RELU).dst(f.r1, 32, 32).run(st));
+      float* nxt = f.cur[(k + 1) % 3];
+      CRFP_TRY(CB(n, h1, w1).src(f.r1, 32, 32).layer(W, lr2[k]).res(f.r0, 32).dst(nxt, 32, 32).run(st));
+      cur = nxt;
+    }
+    CRFP_TRY(CB(n, h1, w1).src(cur, 32, 32).layer(W, L_UPSAMPLE_POST).act(CRFP_ACT_LRELU).shuffle(4).dst(f.q, 4, 4).run(st));
+  }
+  return CRFP_OK;
+}
+
 // L1 stage in bf16 mode: every 2h x 2w layer on tcgen05 (conv_tc / dcn_tc), bf16 storage, fp32 accumulation.
 // Produces the same hand-off to the HR stage as the fp32 path: q, po (fp32 HR), S0_w, flow_hr, new state_l1 (bf16).
 static int frame_l1_bf16(const crfp_dsv_frame_desc* d, const crfp_dsv_weights* W, const FrameWs& f, const float* x_lr,
@@ -520,8 +633,14 @@ extern "C" int crfp_dsv_num_layers(void) { return L_COUNT; }
 extern "C" int crfp_dsv_layer_info(int i, crfp_layer_info* info) {
   if (!info) return CRFP_ERR_NULL;
   if (i < 0 || i >= L_COUNT) return CRFP_ERR_BAD_SHAPE;
-  *info = kLayers[i];
-  info->tc = layer_tc_kind(i);
+  *info = layer_table(CRFP_VARIANT_DSV)[i];
+  return CRFP_OK;
+}
+
+extern "C" int crfp_layer_info_variant(int variant, int i, crfp_layer_info* info) {
+  if (!info) return CRFP_ERR_NULL;
+  if (i < 0 || i >= L_COUNT || variant < 0 || variant > 2) return CRFP_ERR_BAD_SHAPE;
+  *info = layer_table(variant)[i];
   return CRFP_OK;
 }
 
@@ -604,7 +723,11 @@ extern "C" int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weigh
     x_lr = f.x_lr_d;
   }
 
-  if (W->precision == CRFP_PREC_BF16) {
+  if (W->variant != CRFP_VARIANT_DSV) {
+    if (W->variant != CRFP_VARIANT_V15 && W->variant != CRFP_VARIANT_V13) return CRFP_ERR_UNSUPPORTED;
+    if (d->fg || W->precision == CRFP_PREC_BF16) return CRFP_ERR_UNSUPPORTED;
+    CRFP_TRY(frame_l1_v1x(d, W, f, x_lr, st));
+  } else if (W->precision == CRFP_PREC_BF16) {
     if (d->fg) return CRFP_ERR_UNSUPPORTED;  // regional masking is only wired in the fp32 path
     CRFP_TRY(frame_l1_bf16(d, W, f, x_lr, st));
   } else {
@@ -737,7 +860,9 @@ extern "C" int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weigh
     dd.out = f.A3; dd.out_cstride = 4;
     CRFP_TRY(launch_dcn(dd, st));
     CB in3(n, H, Wd);
-    in3.src(f.q, 4, 4).src(f.A3, 4, 4).layer(W, L_RES3_IN).act(CRFP_ACT_LRELU).dst(f.g0, 4, 4);
+    in3.src(f.q, 4, 4).src(f.A3, 4, 4);
+    if (W->variant == CRFP_VARIANT_V15) in3.src(f.S0_w, 4, 4);   // cat([q, A3, warped state]) (CRFP.py:1332)
+    in3.layer(W, L_RES3_IN).act(CRFP_ACT_LRELU).dst(f.g0, 4, 4);
     if (d->fg) in3.fg(d->fg, d->fg_clip_stride);
     CRFP_TRY(in3.run(st));
   } else {

@@ -19,7 +19,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from .packing import pack_layer, pack_layer_tc3
-from .spec import crfp_dsv_param_shapes
+from .spec import crfp_param_shapes
 from .synthetic import fovea_rect
 
 
@@ -58,6 +58,8 @@ def _kaiming_fan_in_(conv: nn.Conv2d, scale: float):
 
 
 class _CRFPBase(nn.Module):
+    VARIANT = "dsv"
+
     def __init__(self, device, mid_channels=16, y_only=False, hr_dcn=True, offset_prop=True, spynet_pretrained=None,
                  precision="tc"):
         super().__init__()
@@ -75,7 +77,7 @@ class _CRFPBase(nn.Module):
         self.last_channels = mid_channels // 8
         self.dg_num, self.dk, self.max_residue_magnitude = 8, 3, 10
         self.y_only, self.hr_dcn, self.offset_prop, self.split_ratio = y_only, hr_dcn, offset_prop, 3
-        _build_tree(self, crfp_dsv_param_shapes(mid_channels, y_only))
+        _build_tree(self, crfp_param_shapes(self.VARIANT, mid_channels, y_only))
         self._init_like_reference()
         if spynet_pretrained is not None:
             self.spynet.load_state_dict(torch.load(spynet_pretrained, map_location="cpu"))
@@ -118,10 +120,11 @@ class _CRFPBase(nn.Module):
         if self._packed is not None and self._packed[0] == key:
             return self._packed[2]
         sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in self.state_dict().items()}
-        table = L.layer_table()
+        table = L.layer_table(self.VARIANT)
         W = L.DsvWeights()
         W.mid_channels, W.nlayers = self.mid_channels, len(table)
         W.precision = L.PREC_TC3 if self.precision == "tc" else L.PREC_FP32
+        W.variant = L.VARIANTS[self.VARIANT]
         keep = []
         for i, info in enumerate(table):
             w, b = pack_layer(info, sd)
@@ -256,6 +259,16 @@ class CRFP_DSV(_CRFPBase):
                 y, x = int(cc[b, i, 0]), int(cc[b, i, 1])
                 fvs[b, i, :, y:y + fv, x:x + fv] = fovea_patch[b, i]
         return self.forward(lrs, fvs, mks, out_host=out_host)
+
+
+class CRFP(CRFP_DSV):
+    """Drop-in for `model.CRFP.CRFP` ("v15", CRFP.py:1101-1385): 3-way concat, HR state warped before down-sampling."""
+    VARIANT = "v15"
+
+
+class CRFP_simple(CRFP_DSV):
+    """Drop-in for `model.CRFP.CRFP_simple` ("v13", CRFP.py:816-1099)."""
+    VARIANT = "v13"
 
 
 class MRCF_simple_v18(_CRFPBase):

@@ -47,6 +47,45 @@ def dcn_module_param_shapes(prefix, C, dg, repeat, pre_offset, pixelshuffle):
     return d
 
 
+VARIANTS = ("dsv", "v15", "v13")   # CRFP_DSV (v18), CRFP (v15), CRFP_simple (v13)
+
+
+def crfp_param_shapes(variant="dsv", mid_channels=32, y_only=False):
+    """Parameters of CRFP_DSV (CRFP.py:1388-1481), CRFP (CRFP.py:1102-1221) or CRFP_simple (CRFP.py:817-936) with
+    hr_dcn=True, offset_prop=True, in module order.  The three share every module name; they differ in
+    forward_resblocks_k.main.0 input width, upsample / upsample_post widths (DSV's 24/8 channel split)."""
+    if variant == "dsv":
+        return crfp_dsv_param_shapes(mid_channels, y_only)
+    if variant not in ("v15", "v13"):
+        raise ValueError(variant)
+    C = mid_channels
+    c = C // 8
+    k_in = 3 if variant == "v15" else 2
+    d = OrderedDict()
+    d.update(fnet_param_shapes())
+    d.update(dcn_module_param_shapes("dcn_0.", C, 8, False, False, False))
+    d.update(dcn_module_param_shapes("dcn_1.", C, 8, False, True, False))
+    d.update(dcn_module_param_shapes("dcn_2.", C, 8, False, True, False))
+    d.update(dcn_module_param_shapes("dcn_3.", c, 1, True, True, True))
+    _conv(d, "encoder_lr.slice1.0", C, 3)
+    _conv(d, "encoder_lr.slice1.2", C, C)
+    _conv(d, "encoder_hr.slice1.0", c, 6)
+    _conv(d, "encoder_hr.slice1.2", c, c)
+    _conv(d, "conv_tttf", c, 2 * c)
+    for k in range(3):
+        _conv(d, f"forward_resblocks_{k}.main.0", C, k_in * C)
+        _conv(d, f"forward_resblocks_{k}.main.2.0.conv1", C, C)
+        _conv(d, f"forward_resblocks_{k}.main.2.0.conv2", C, C)
+    _conv(d, "forward_resblocks_3.main.0", c, k_in * c)
+    _conv(d, "forward_resblocks_3.main.2.0.conv1", c, c)
+    _conv(d, "forward_resblocks_3.main.2.0.conv2", c, c)
+    _conv(d, "downsample.downsample_conv", C, c * 16)
+    _conv(d, "upsample.upsample_conv", C * 4, C)
+    _conv(d, "upsample_post.upsample_conv", c * 16, C)
+    _conv(d, "conv_last", 1 if y_only else 3, c)
+    return d
+
+
 def crfp_dsv_param_shapes(mid_channels=32, y_only=False):
     """All parameters of CRFP_DSV(hr_dcn=True, offset_prop=True) in module order."""
     C = mid_channels

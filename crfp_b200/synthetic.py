@@ -23,7 +23,7 @@ from collections import OrderedDict
 import torch
 import torch.nn.functional as F
 
-from .spec import crfp_dsv_param_shapes
+from .spec import crfp_param_shapes
 
 
 def _key_seed(seed: int, key: str) -> int:
@@ -31,7 +31,7 @@ def _key_seed(seed: int, key: str) -> int:
 
 
 def make_state_dict(seed: int = 1, mid_channels: int = 32, y_only: bool = False,
-                    flow_gain: float = 0.05) -> "OrderedDict[str, torch.Tensor]":
+                    flow_gain: float = 0.05, variant: str = "dsv") -> "OrderedDict[str, torch.Tensor]":
     """Random fp32 state_dict with the reference's 118 keys and shapes.
 
     conv weights ~ N(0, (g*sqrt(2/fan_in))^2); residual-block convs use g=0.1
@@ -40,7 +40,7 @@ def make_state_dict(seed: int = 1, mid_channels: int = 32, y_only: bool = False,
     `flow_gain` so that tanh(.)*256 gives flows of a few LR pixels.
     """
     sd = OrderedDict()
-    for key, shape in crfp_dsv_param_shapes(mid_channels, y_only).items():
+    for key, shape in crfp_param_shapes(variant, mid_channels, y_only).items():
         g = torch.Generator(device="cpu")
         g.manual_seed(_key_seed(seed, key))
         if key.endswith(".bias"):

@@ -312,6 +312,9 @@ typedef struct {
 } crfp_layer;
 
 enum { CRFP_PREC_FP32 = 0, CRFP_PREC_BF16 = 1, CRFP_PREC_TC3 = 2 };
+/* model variants sharing every kernel and parameter name (model/CRFP.py): CRFP_DSV :1387 (24/8 split state),
+ * CRFP :1101 (3-way concat, HR state warped before down-sampling), CRFP_simple :816 (2-way concat) */
+enum { CRFP_VARIANT_DSV = 0, CRFP_VARIANT_V15 = 1, CRFP_VARIANT_V13 = 2 };
 typedef struct {
   const void* w_hi;     /* bf16 tensor-core packing (TC3: hi half of the split) */
   const void* w_lo;     /* TC3: lo half (NULL in bf16 mode) */
@@ -326,7 +329,7 @@ typedef struct {
                                            tcgen05 as 3 x bf16 split products with fp32 TMEM accumulation — fp32-grade
                                            (parity <= 1e-3), the default of the Python shell;
                            CRFP_PREC_BF16: experimental, L1 layers with bf16 STORAGE (not parity-certified) */
-  int32_t _pad;
+  int32_t variant;      /* CRFP_VARIANT_DSV (CRFP_DSV, v18), CRFP_VARIANT_V15 (CRFP), CRFP_VARIANT_V13 (CRFP_simple) */
   crfp_layer layer[CRFP_DSV_MAX_LAYERS];
   crfp_layer_tc layer_tc[CRFP_DSV_MAX_LAYERS]; /* entries of layers with crfp_layer_info.tc != 0 (else all NULL) */
 } crfp_dsv_weights;
@@ -359,13 +362,14 @@ typedef struct {
   int32_t _pad;
 } crfp_layer_info;
 int crfp_dsv_num_layers(void);
-int crfp_dsv_layer_info(int i, crfp_layer_info* info);
+int crfp_dsv_layer_info(int i, crfp_layer_info* info);               /* CRFP_VARIANT_DSV */
+int crfp_layer_info_variant(int variant, int i, crfp_layer_info* info);
 
 typedef struct {
   int32_t n, t, h, w;     /* clip batch, frames in this call, LR size */
   int32_t mid_channels;
   int32_t _pad;
-} crfp_dsv_shape;
+} crfp_dsv_shape;           /* (the model variant travels in crfp_dsv_weights.variant) */
 
 /*
  * Clip-level stage for frames [0, t) of `n` clips:

@@ -14,6 +14,8 @@ state_dict so that it needs neither `/root/reference` nor `dcn_v2`):
   ResidualBlocksWithInputConv /root/reference/model/CRFP.py:433-552
   FNet.forward                /root/reference/model/CRFP.py:797-814
   CRFP_DSV.forward            /root/reference/model/CRFP.py:1510-1686
+  CRFP.forward (v15)          /root/reference/model/CRFP.py:1223-1368
+  CRFP_simple.forward (v13)   /root/reference/model/CRFP.py:938-1080
   LTE_simple_lr / _hr_single  /root/reference/model/LTE.py:34-51, 100-117
   MRCF_simple_v18 (streaming) /root/reference/model/CRFP_test.py:2214-2478
 
@@ -272,6 +274,66 @@ def frame_step(sd, C, state, x_lr_cur, x_hr_cur, mk_cur, lr_cur, flow, *, fg_lv0
     if taps is not None:
         taps.update(S=S, out=out)
     return out, (S, feat_lv0, feat_lv1, feat_lv2)
+
+
+def frame_step_v1x(sd, C, variant, state, x_lr_cur, x_hr_cur, mk_cur, lr_cur, flow, *, naive_dcn=False):
+    """One loop iteration of CRFP.forward (v15, CRFP.py:1260-1368) / CRFP_simple.forward (v13, CRFP.py:968-1080).
+    No DSV split; the HR state is warped first and both the state and its warp are downsampled; v15 additionally
+    feeds the warped planes into every residual block (3-way concat)."""
+    three = (variant == "v15")
+    prop = pixel_shuffle_pack(x_lr_cur, sd, "upsample", 2)          # 32 ch @L1
+    n = lr_cur.shape[0]
+    h, w = lr_cur.shape[-2:]
+    c = C // 8
+    if state is not None:
+        S0 = state
+        flow_lv3 = up_bilinear(flow, 2) * 2.0
+        flow_lv0 = up_bilinear(flow, 8) * 8.0
+        S0_w = flow_warp(S0, flow_lv0)
+        P_w = conv3x3(F.pixel_unshuffle(S0_w, 4), sd, "downsample.downsample_conv")
+        P = conv3x3(F.pixel_unshuffle(S0, 4), sd, "downsample.downsample_conv")
+        offfeat = None
+        cur = prop
+        for k in range(3):
+            A, offfeat = dcn_module(sd, f"dcn_{k}", cur, P, P_w, flow_lv3, offfeat, dg=8, naive=naive_dcn)
+            y = torch.cat([cur, A, P_w], dim=1) if three else torch.cat([cur, A], dim=1)
+            cur = res_blocks_with_input_conv(y, sd, f"forward_resblocks_{k}")
+        q = lrelu(pixel_shuffle_pack(cur, sd, "upsample_post", 4))
+        A3, _ = dcn_module(sd, "dcn_3", q, S0, S0_w, flow_lv0, offfeat, dg=1, repeat=True, pixelshuffle=True,
+                           naive=naive_dcn)
+        y = torch.cat([q, A3, S0_w], dim=1) if three else torch.cat([q, A3], dim=1)
+        S = res_blocks_with_input_conv(y, sd, "forward_resblocks_3")
+    else:
+        z1 = lr_cur.new_zeros(n, C, 2 * h, 2 * w)
+        z3 = lr_cur.new_zeros(n, c, 8 * h, 8 * w)
+        cur = prop
+        for k in range(3):
+            y = torch.cat([cur, z1, z1], dim=1) if three else torch.cat([cur, z1], dim=1)
+            cur = res_blocks_with_input_conv(y, sd, f"forward_resblocks_{k}")
+        q = lrelu(pixel_shuffle_pack(cur, sd, "upsample_post", 4))
+        y = torch.cat([q, z3, z3], dim=1) if three else torch.cat([q, z3], dim=1)
+        S = res_blocks_with_input_conv(y, sd, "forward_resblocks_3")
+    Fz = conv3x3(torch.cat([S, x_hr_cur], dim=1), sd, "conv_tttf")
+    mkf = mk_cur.float()
+    S = lrelu(mkf * Fz + (1 - mkf) * S)
+    out = conv3x3(S, sd, "conv_last") + up_bilinear(lr_cur, 8)
+    return out, S
+
+
+@torch.no_grad()
+def crfp_forward(sd, lrs, fvs, mks, variant="dsv", mid_channels=32, naive_dcn=False):
+    """forward(lrs, fvs, mks) of CRFP_DSV ("dsv"), CRFP ("v15") or CRFP_simple ("v13")."""
+    if variant == "dsv":
+        return crfp_dsv_forward(sd, lrs, fvs, mks, mid_channels, naive_dcn)
+    n, t, c, h, w = lrs.shape
+    flows = compute_flow(sd, lrs) if t > 1 else None
+    x_lr, x_hr = encoders(sd, lrs, fvs, mks)
+    state, outs = None, []
+    for i in range(t):
+        out, state = frame_step_v1x(sd, mid_channels, variant, state, x_lr[:, i], x_hr[:, i], mks[:, i], lrs[:, i],
+                                    flows[:, i - 1] if i > 0 else None, naive_dcn=naive_dcn)
+        outs.append(out)
+    return torch.stack(outs, dim=1)
 
 
 def encoders(sd, lrs, fvs, mks):

@@ -111,6 +111,22 @@ def main():
                 tp["dcn0_mask"].mean()))
         torch.save(fix, os.path.join(out_dir, name + ".pt"))
 
+    # sibling models: CRFP (v15) and CRFP_simple (v13)
+    for variant, cls in (("v15", CRFP.CRFP), ("v13", CRFP.CRFP_simple)):
+        sdv = make_state_dict(seed=1, variant=variant)
+        refv = build_ref_model(cls, sdv)
+        name, n, t, h, w, fv = f"{variant}_n1_t3_16x24", 1, 3, 16, 24, 48
+        lrs, fvs, mks, fv_sp = make_clip(seed=21, n=n, t=t, h=h, w=w, fv_size=fv)
+        with torch.no_grad():
+            y_ref = refv(lrs.clone(), fvs.clone(), mks.clone())
+        y_or = O.crfp_forward(sdv, lrs, fvs, mks, variant=variant)
+        d = (y_ref - y_or).abs().max().item()
+        print(f"{name}: ref vs oracle max-abs {d:.3e}; out range [{y_ref.min():.3f},{y_ref.max():.3f}]")
+        assert d <= 1e-6, "oracle restatement deviates from the reference"
+        torch.save({"case": dict(n=n, t=t, h=h, w=w, fv=fv, seed=21, weight_seed=1, variant=variant),
+                    "weights_sum": float(sum(v.double().sum() for v in sdv.values())),
+                    "lrs_sum": float(lrs.double().sum()), "out": y_ref.contiguous()}, os.path.join(out_dir, name + ".pt"))
+
     # streaming model: same state_dict, frame by frame, with a regional fg mask
     name, n, t, h, w, fv = "stream_n1_t3_16x24", 1, 3, 16, 24, 48
     lrs, fvs, mks, fv_sp = make_clip(seed=11, n=n, t=t, h=h, w=w, fv_size=fv)

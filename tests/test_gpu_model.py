@@ -133,3 +133,26 @@ def test_reds_native_shape_long_clip_properties(model, sd):
     assert torch.equal(out[:, :8], out8)
     ref = O.crfp_dsv_forward(sd, lrs[:, :3], fvs[:, :3], mks[:, :3])
     assert (out[:, :3] - ref).abs().max().item() <= TOL
+
+
+@pytest.mark.parametrize("variant,precision", [("v15", "tc"), ("v15", "fp32"), ("v13", "tc"), ("v13", "fp32")])
+def test_sibling_models_against_reference_golden(golden_dir, variant, precision):
+    """CRFP (v15) and CRFP_simple (v13): same kernels, different wiring."""
+    import crfp_b200
+    fix = torch.load(os.path.join(golden_dir, f"{variant}_n1_t3_16x24.pt"))
+    c = fix["case"]
+    sdv = make_state_dict(seed=1, variant=variant)
+    assert abs(float(sum(v.double().sum() for v in sdv.values())) - fix["weights_sum"]) < 1e-6
+    cls = crfp_b200.CRFP if variant == "v15" else crfp_b200.CRFP_simple
+    m = cls("cuda", mid_channels=32, precision=precision).eval()
+    m.load_state_dict(sdv, strict=True)
+    m.cuda()
+    lrs, fvs, mks, _ = make_clip(seed=c["seed"], n=c["n"], t=c["t"], h=c["h"], w=c["w"], fv_size=c["fv"])
+    out = m(lrs.cuda(), fvs.cuda(), mks.cuda()).cpu()
+    err = (out - fix["out"]).abs().max().item()
+    print(f"{variant} [{precision}]: max-abs vs reference golden {err:.3e}")
+    assert err <= TOL
+    # a second, larger clip against the live oracle
+    lrs, fvs, mks, _ = make_clip(seed=23, n=2, t=3, h=24, w=40, fv_size=64)
+    ref = O.crfp_forward(sdv, lrs, fvs, mks, variant=variant)
+    assert (m(lrs.cuda(), fvs.cuda(), mks.cuda()).cpu() - ref).abs().max().item() <= TOL

@@ -96,6 +96,17 @@ def test_state_dict_contract():
     assert torch.equal(m.dcn_1.dcn.weight[:, :, 1, 1], torch.eye(32))
 
 
+def test_sibling_state_dict_contracts():
+    from crfp_b200 import CRFP, CRFP_simple
+    from crfp_b200.spec import crfp_param_shapes
+    for cls, variant, nparam in ((CRFP, "v15", 2326000), (CRFP_simple, "v13", 2298208)):   # SURVEY.md section 2 [probe]
+        shapes = crfp_param_shapes(variant, 32)
+        m = cls("cuda", mid_channels=32)
+        assert list(m.state_dict().keys()) == list(shapes.keys()) and len(shapes) == 118
+        assert sum(p.numel() for p in m.parameters()) == nparam
+        m.load_state_dict(make_state_dict(1, variant=variant), strict=True)
+
+
 def test_module_errors_loudly_without_cuda_inputs():
     from crfp_b200 import CRFP_DSV
     from crfp_b200._lib import CrfpError
@@ -135,6 +146,13 @@ def test_c_abi_exports_every_declared_symbol(built_lib):
 def test_layer_table_matches_state_dict(built_lib):
     from crfp_b200 import _lib
     shapes = crfp_dsv_param_shapes(32)
+    for variant in ("v15", "v13"):          # sibling tables pack too
+        from crfp_b200.spec import crfp_param_shapes
+        sdv = make_state_dict(1, variant=variant)
+        for info in _lib.layer_table(variant):
+            w, b = packing.pack_layer(info, sdv)
+            if info["tc"]:
+                packing.pack_layer_tc3(info, sdv)
     table = _lib.layer_table()
     used = set()
     sd = make_state_dict(1)

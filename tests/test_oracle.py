@@ -89,3 +89,13 @@ def test_flow_warp_indices_reproduce_grid_sample():
     assert (out - ref).abs().max().item() < 1e-5
     # at zero flow some columns do NOT land on the integer pixel: the reason index parity needs the exact op order
     assert (x0[0, 0, : w // 2] != torch.arange(w // 2)).any() or True
+
+
+@pytest.mark.parametrize("variant", ["v15", "v13"])
+def test_sibling_oracles_match_reference_golden(golden_dir, variant):
+    fix = torch.load(os.path.join(golden_dir, f"{variant}_n1_t3_16x24.pt"))
+    c = fix["case"]
+    sdv = make_state_dict(seed=1, variant=variant)
+    lrs, fvs, mks, _ = make_clip(seed=c["seed"], n=c["n"], t=c["t"], h=c["h"], w=c["w"], fv_size=c["fv"])
+    out = O.crfp_forward(sdv, lrs, fvs, mks, variant=variant)
+    assert (out - fix["out"]).abs().max().item() <= 1e-5
