@@ -36,3 +36,41 @@ def _worker(rank, world, port, n_clips):
 
 def test_shard_and_gather_world2_gloo():
     mp.spawn(_worker, args=(2, 29533, 5), nprocs=2, join=True)
+
+
+def test_tile_plan_partitions_frame():
+    from crfp_b200.tiling import tile_plan
+    for h, w, gy, gx, halo in [(180, 320, 2, 4, 32), (64, 96, 2, 2, 24), (45, 80, 3, 3, 0), (16, 16, 1, 1, 8)]:
+        plan = tile_plan(h, w, gy, gx, halo)
+        cover = torch.zeros(h, w, dtype=torch.int32)
+        for (y0, y1, x0, x1), (ey0, ey1, ex0, ex1) in plan:
+            cover[y0:y1, x0:x1] += 1
+            assert 0 <= ey0 <= y0 < y1 <= ey1 <= h and 0 <= ex0 <= x0 < x1 <= ex1 <= w
+            assert y0 - ey0 == min(halo, y0) and ey1 - y1 == min(halo, h - y1)
+            assert x0 - ex0 == min(halo, x0) and ex1 - x1 == min(halo, w - x1)
+        assert torch.all(cover == 1)
+
+
+def _tile_worker(rank, world, port):
+    """The per-frame exchange step of the tiled runner: after it every rank holds every tile's interior state."""
+    from crfp_b200.tiling import TiledClipRunner, tile_plan
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        h, w = 12, 20
+        plan = tile_plan(h, w, 2, 3, 4)
+        truth_hr = torch.arange(8 * h * 8 * w * 4, dtype=torch.float32).view(1, 8 * h, 8 * w, 4)
+        truth_l1 = torch.arange(2 * h * 2 * w * 24, dtype=torch.float32).view(1, 2 * h, 2 * w, 24) * 0.5
+        hr, l1 = torch.full_like(truth_hr, -1.0), torch.full_like(truth_l1, -1.0)     # stale everywhere ...
+        for k, ((y0, y1, x0, x1), _) in enumerate(plan):
+            if k % world == rank:                                                      # ... except my own interiors
+                hr[:, 8 * y0:8 * y1, 8 * x0:8 * x1] = truth_hr[:, 8 * y0:8 * y1, 8 * x0:8 * x1]
+                l1[:, 2 * y0:2 * y1, 2 * x0:2 * x1] = truth_l1[:, 2 * y0:2 * y1, 2 * x0:2 * x1]
+        TiledClipRunner(None, grid=(2, 3), halo=4)._allgather_interiors(hr, l1, plan, world, rank)
+        assert torch.equal(hr, truth_hr) and torch.equal(l1, truth_l1)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_tile_state_exchange_world2_gloo():
+    mp.spawn(_tile_worker, args=(2, 29537), nprocs=2, join=True)
