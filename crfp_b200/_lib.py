@@ -133,6 +133,7 @@ SYMBOLS = {
     "crfp_last_cuda_error": (C.c_char_p, []),
     "crfp_launch_count": (C.c_longlong, []),
     "crfp_launch_count_reset": (None, []),
+    "crfp_launch_count_add": (None, [C.c_longlong]),
     "crfp_check_device": (C.c_int, []),
     "crfp_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "crfp_selftest_umma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

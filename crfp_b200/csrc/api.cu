@@ -93,6 +93,7 @@ extern "C" const char* crfp_status_string(int s) {
 extern "C" const char* crfp_last_cuda_error(void) { return cudaGetErrorString(g_last_err); }
 extern "C" long long crfp_launch_count(void) { return g_launches; }
 extern "C" void crfp_launch_count_reset(void) { g_launches = 0; }
+extern "C" void crfp_launch_count_add(long long n) { g_launches += n; }
 
 extern "C" int crfp_check_device(void) {
   int dev = 0;

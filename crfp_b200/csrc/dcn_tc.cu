@@ -255,8 +255,16 @@ __device__ __forceinline__ void dcn_sample_win(const DcnTc3Params& P, const floa
   v[0] *= m; v[1] *= m; v[2] *= m; v[3] *= m;
 }
 
+constexpr int WQC = 10;                       // K chunks per quarter stage (9 real + 1 zero)
+constexpr int WNW = 2;                        // window ring depth
+constexpr int WSAMP = 384;                    // sampler threads
+constexpr int WWR = 12;                       // reach: 10 (max |residual offset|) + 1 (tap) + 1 (bilinear corner)
+constexpr int WWW = DTW + 2 * WWR, WWH = DTH + 2 * WWR;   // 40 x 32 pixels
+constexpr int WWIN_FLOATS = WWH * WWW * 8;    // 10240 floats = 40 KB per window
+constexpr int WA_RECS = WQC * DAP;            // uint4 records of one A stage (hi or lo)
+
 // window variant for the persistent kernel: the window holds 8 channels (the 2 deformable groups of K quarter `q`) per
-// pixel, [28][36][8] floats as written by the TMA tile load; `gtr` = (group, tap) index relative to the quarter (0..17)
+// pixel, [32][40][8] floats as written by the TMA tile load; `gtr` = (group, tap) index relative to the quarter (0..17)
 __device__ __forceinline__ void dcn_sample_win8(const DcnTc3Params& P, const float* img, const float4* sWin, int wy0, int wx0,
                                                 int q, int gtr, int y, int x, float dy, float dx, float m, float* v) {
   const int gl = gtr / 9, t = gtr - gl * 9;
@@ -265,9 +273,9 @@ __device__ __forceinline__ void dcn_sample_win8(const DcnTc3Params& P, const flo
   float w00, w01, w10, w11;
   dcn_corner_w((float)(y - 1 + i) + dy, (float)(x - 1 + j) + dx, P.h, P.w, y0, x0, w00, w01, w10, w11);
   const int wy = y0 - wy0, wx = x0 - wx0;
-  if (wy >= 0 && wy + 1 < DWH && wx >= 0 && wx + 1 < DWW) {
-    const float4* p = sWin + (wy * DWW + wx) * 2 + gl;
-    const float4 c00 = p[0], c01 = p[2], c10 = p[DWW * 2], c11 = p[DWW * 2 + 2];
+  if (wy >= 0 && wy + 1 < WWH && wx >= 0 && wx + 1 < WWW) {
+    const float4* p = sWin + (wy * WWW + wx) * 2 + gl;
+    const float4 c00 = p[0], c01 = p[2], c10 = p[WWW * 2], c11 = p[WWW * 2 + 2];
     v[0] = (w00 * c00.x + w01 * c01.x + w10 * c10.x + w11 * c11.x) * m;
     v[1] = (w00 * c00.y + w01 * c01.y + w10 * c10.y + w11 * c11.y) * m;
     v[2] = (w00 * c00.z + w01 * c01.z + w10 * c10.z + w11 * c11.z) * m;
@@ -427,28 +435,22 @@ __global__ void __launch_bounds__(512, 1) dcn_tc3_kernel(const DcnTc3Params P) {
 //   * one CTA per SM, each walking tiles blockIdx.x, +gridDim.x, ...; the weights are loaded once per CTA;
 //   * K = 288 is cut into 4 quarters = 2 deformable groups = 8 input channels each (9 real K chunks + 1 zero chunk so
 //     that a quarter is 5 K16 steps);
-//   * the sampling window of a quarter (28 x 36 pixels x 8 channels, 32 KB) is fetched by ONE TMA tensor-tile load
-//     (cp.async.bulk.tensor.4d, zero fill outside the image) into a ring of 3 buffers, 3 quarters ahead;
+//   * the sampling window of a quarter (32 x 40 pixels x 8 channels, 40 KB) is fetched by ONE TMA tensor-tile load
+//     (cp.async.bulk.tensor.4d, zero fill outside the image) into a ring of 2 buffers, 2 quarters ahead;
 //   * 12 sampler warps gather + modulate + split into a ring of 2 A stages (the next quarter's offsets / masks are
 //     already in registers when a quarter starts);
 //   * warp 0 issues the 15 tcgen05.mma of a full stage, commits the stage back to the samplers, then re-arms the
 //     window ring; after the 4th quarter warps 0-3 read the accumulator from TMEM and store the tile.
-// mbarriers: win_full[3] (TMA bytes), a_full[2] (384 sampler arrivals), a_empty[2] / acc_full (tcgen05.commit).
+// mbarriers: win_full[2] (TMA bytes), a_full[2] (384 sampler arrivals), a_empty[2] / acc_full (tcgen05.commit).
 // "Window slot free" needs no barrier of its own: a_full[k] completes only after every sampler has finished
 // reading the window of quarter k.
-constexpr int WQC = 10;                       // K chunks per quarter stage (9 real + 1 zero)
-constexpr int WNW = 3;                        // window ring depth
-constexpr int WSAMP = 384;                    // sampler threads
-constexpr int WWIN_FLOATS = DWH * DWW * 8;    // 8064 floats = 32256 B per window
-constexpr int WA_RECS = WQC * DAP;            // uint4 records of one A stage (hi or lo)
-
 __global__ void __launch_bounds__(512, 1) dcn_tc3_ws_kernel(const DcnTc3Params P, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t win_full[WNW], a_full[2], a_empty[2], acc_full;
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[32];
   __shared__ int2 s_org[WNW];
-  float* sWin = reinterpret_cast<float*>(smem);                              // [3][28][36][8]
+  float* sWin = reinterpret_cast<float*>(smem);                              // [2][32][40][8]
   uint4* sBh = reinterpret_cast<uint4*>(smem + WNW * WWIN_FLOATS * 4);       // [4][10][32]
   uint4* sBl = sBh + 4 * WQC * 32;
   uint4* sAh = sBl + 4 * WQC * 32;                                           // [2][10][129]
@@ -502,7 +504,7 @@ __global__ void __launch_bounds__(512, 1) dcn_tc3_ws_kernel(const DcnTc3Params P
       const int n = tile / tiles_img, tr = tile - n * tiles_img;
       const int ty = tr / tiles_x, tx = tr - ty * tiles_x;
       const int y0t = ty * DTH, x0t = tx * DTW;
-      int wy0 = y0t - DWR, wx0 = x0t - DWR;
+      int wy0 = y0t - WWR, wx0 = x0t - WWR;
       if (P.flow_hint != nullptr) {
         const int cy = min(y0t + DTH / 2, P.h - 1), cx = min(x0t + DTW / 2, P.w - 1);
         const float2 fl = __ldg(reinterpret_cast<const float2*>(P.flow_hint + (((size_t)n * P.h + cy) * (size_t)P.w + cx) * 2));
@@ -660,7 +662,7 @@ static int sm_count() {
   return n;
 }
 
-// x viewed as a 4-D tensor {channel, x, y, image}; one box = 8 channels x 36 x 28 pixels of one image
+// x viewed as a 4-D tensor {channel, x, y, image}; one box = 8 channels x 40 x 32 pixels of one image
 static int launch_dcn_tc3_ws(const DcnTc3Params& p, cudaStream_t st) {
   tmap_encode_fn enc = tmap_encoder();
   if (!enc) return CRFP_ERR_UNSUPPORTED;
@@ -669,12 +671,12 @@ static int launch_dcn_tc3_ws(const DcnTc3Params& p, cudaStream_t st) {
   CUtensorMap tmap;
   const cuuint64_t gdim[4] = {32, (cuuint64_t)p.w, (cuuint64_t)p.h, (cuuint64_t)p.n};
   const cuuint64_t gstr[3] = {(cuuint64_t)p.x_cstride * 4, (cuuint64_t)p.w * p.x_cstride * 4, (cuuint64_t)p.h * p.w * p.x_cstride * 4};
-  const cuuint32_t box[4] = {8, DWW, DWH, 1};
+  const cuuint32_t box[4] = {8, WWW, WWH, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return CRFP_ERR_UNSUPPORTED;
-  const size_t smem = (size_t)WNW * WWIN_FLOATS * 4 + (size_t)(2 * 4 * WQC * 32 + 2 * 2 * WA_RECS) * 16;   // 96768 + 40960 + 82560
+  const size_t smem = (size_t)WNW * WWIN_FLOATS * 4 + (size_t)(2 * 4 * WQC * 32 + 2 * 2 * WA_RECS) * 16;   // 81920 + 40960 + 82560
   cudaError_t e = cudaFuncSetAttribute(dcn_tc3_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
   const int total = ceil_div(p.w, DTW) * ceil_div(p.h, DTH) * p.n;

@@ -11,8 +11,10 @@ input raises.
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -84,6 +86,11 @@ class _CRFPBase(nn.Module):
         self._packed = None       # (version key, device, blob tensors, DsvWeights)
         self._ws = {}             # workspace cache keyed by shape
         self.skip_outside_fovea = True
+        # CUDA graphs: a clip forward is ~60 launches per frame; the second call on the same input buffers captures
+        # the whole clip into one graph and later calls replay it (one launch per clip: immune to host jitter)
+        self.use_graphs = os.environ.get("CRFP_NO_GRAPHS") is None
+        self._graphs = collections.OrderedDict()   # key -> dict(graph, out, launches)
+        self._seen_key = None
 
     # ---- init policy of the reference (statistically identical, not RNG-stream identical)
     def _init_like_reference(self):
@@ -137,12 +144,14 @@ class _CRFPBase(nn.Module):
                 if wx is not None:
                     W.layer_tc[i].w_extra = wx.data_ptr()
         self._packed = (key, keep, W)
+        self._graphs.clear()      # captured graphs point at the previous packed weights
         return W
 
     def _clip_buffers(self, n, t, h, w, device):
         key = (n, t, h, w, str(device))
         if key not in self._ws:
             self._ws.clear()
+            self._graphs.clear()  # captured graphs point at the previous clip buffers
             lib = L.lib()
             shp = L.DsvShape(n=n, t=t, h=h, w=w, mid_channels=self.mid_channels)
             pw, fw = lib.crfp_dsv_prepare_workspace(C.byref(shp)), lib.crfp_dsv_frame_workspace(C.byref(shp))
@@ -236,14 +245,56 @@ class CRFP_DSV(_CRFPBase):
                 L.check(L.lib().crfp_check_device(), "device check (sm_100 required)")
                 W = self._weights(dev)
                 buf = self._clip_buffers(n, t, h, w, dev)
+
+                def run(out):
+                    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+                    shp = L.DsvShape(n=n, t=t, h=h, w=w, mid_channels=self.mid_channels)
+                    L.check(L.lib().crfp_dsv_prepare(C.byref(shp), C.byref(W), lrs.data_ptr(), None, buf["lr4"].data_ptr(),
+                                                     buf["x_lr"].data_ptr(), buf["flows"].data_ptr(), buf["ws"].data_ptr(),
+                                                     buf["ws"].numel(), st), "dsv_prepare")
+                    self._run_frames(buf, W, lrs, fvs, mks, None, out, [i == 0 for i in range(t)], out_host)
+
+                key = (n, t, h, w, str(dev), lrs.data_ptr(), fvs.data_ptr(), mks.data_ptr(),
+                       0 if out_host is None else out_host.data_ptr(), bool(self.skip_outside_fovea))
+                if self.use_graphs and not torch.cuda.is_current_stream_capturing():
+                    entry = self._graphs.get(key)
+                    if entry is None and self._seen_key == key:
+                        entry = self._capture(key, run, (n, t, 3, 8 * h, 8 * w), dev)
+                    self._seen_key = key
+                    if entry is not None:
+                        self._graphs.move_to_end(key)
+                        entry["graph"].replay()
+                        L.lib().crfp_launch_count_add(entry["launches"])
+                        return entry["out"]
                 out = torch.empty(n, t, 3, 8 * h, 8 * w, device=dev, dtype=torch.float32)
-                st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-                shp = L.DsvShape(n=n, t=t, h=h, w=w, mid_channels=self.mid_channels)
-                L.check(L.lib().crfp_dsv_prepare(C.byref(shp), C.byref(W), lrs.data_ptr(), None, buf["lr4"].data_ptr(),
-                                                 buf["x_lr"].data_ptr(), buf["flows"].data_ptr(), buf["ws"].data_ptr(),
-                                                 buf["ws"].numel(), st), "dsv_prepare")
-                self._run_frames(buf, W, lrs, fvs, mks, None, out, [i == 0 for i in range(t)], out_host)
+                run(out)
             return out
+
+    def _capture(self, key, run, out_shape, dev):
+        """Capture one whole-clip forward (prepare + every frame, incl. the streaming device->host copies) into a CUDA
+        graph.  The entry owns its output tensor: replays on the same input buffers return that same tensor,
+        overwritten by the next replay (`use_graphs = False` or CRFP_NO_GRAPHS=1 restores one fresh tensor per call).
+        Returns None (and switches graphs off) if the capture fails for any reason."""
+        lib = L.lib()
+        out = torch.empty(*out_shape, device=dev, dtype=torch.float32)
+        try:
+            torch.cuda.synchronize(dev)
+            before = lib.crfp_launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run(out)
+            launches = lib.crfp_launch_count() - before
+            lib.crfp_launch_count_add(-launches)        # captured, not launched
+        except Exception as e:  # noqa: BLE001
+            import warnings
+            warnings.warn(f"crfp_b200: CUDA graph capture failed ({e}); continuing without graphs")
+            self.use_graphs = False
+            return None
+        while len(self._graphs) >= 3:
+            self._graphs.popitem(last=False)
+        entry = dict(graph=g, out=out, launches=launches)
+        self._graphs[key] = entry
+        return entry
 
     def forward_patch(self, lrs, fovea_patch, coords, out_host=None):
         """Convenience entry named by BASELINE.json: `fovea_patch` (n,t,3,FV,FV) pasted at integer top-left

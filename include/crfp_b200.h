@@ -58,6 +58,9 @@ const char* crfp_last_cuda_error(void);
 /* number of kernel launches issued by this library from the calling thread since the last reset */
 long long crfp_launch_count(void);
 void crfp_launch_count_reset(void);
+/* accounting hook for callers that capture this library's launches into a CUDA graph: a capture enqueues nothing
+ * (add -n), every replay of the graph launches its n kernels (add +n) */
+void crfp_launch_count_add(long long n);
 /* device properties check: 0 if the current device is sm_100 (B200), CRFP_ERR_UNSUPPORTED otherwise */
 int crfp_check_device(void);
 

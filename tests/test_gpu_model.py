@@ -156,3 +156,46 @@ def test_sibling_models_against_reference_golden(golden_dir, variant, precision)
     lrs, fvs, mks, _ = make_clip(seed=23, n=2, t=3, h=24, w=40, fv_size=64)
     ref = O.crfp_forward(sdv, lrs, fvs, mks, variant=variant)
     assert (m(lrs.cuda(), fvs.cuda(), mks.cuda()).cpu() - ref).abs().max().item() <= TOL
+
+
+def test_cuda_graph_replay_matches_eager(sd):
+    """The whole-clip CUDA graph (captured on the second call with the same input buffers) must reproduce the eager
+    forward bit for bit, count its launches, follow in-place input updates and stream frames to the host."""
+    from crfp_b200 import CRFP_DSV, _lib
+    m = CRFP_DSV("cuda", mid_channels=32).eval()
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    lrs, fvs, mks, _ = make_clip(seed=33, n=1, t=4, h=24, w=40, fv_size=64)
+    lrs, fvs, mks = lrs.cuda(), fvs.cuda(), mks.cuda()
+    m.use_graphs = False
+    _lib.lib().crfp_launch_count_reset()
+    eager = m(lrs, fvs, mks).clone()
+    n_eager = _lib.lib().crfp_launch_count()
+    m.use_graphs = True
+    o1 = m(lrs, fvs, mks)                 # first sighting: eager
+    assert len(m._graphs) == 0
+    o2 = m(lrs, fvs, mks)                 # second sighting: capture + replay
+    assert len(m._graphs) == 1 and m.use_graphs
+    _lib.lib().crfp_launch_count_reset()
+    o3 = m(lrs, fvs, mks)                 # replay
+    assert _lib.lib().crfp_launch_count() == n_eager > 0
+    torch.cuda.synchronize()
+    assert o3 is o2 and torch.equal(o1, eager) and torch.equal(o3, eager)
+    # the graph reads the buffers, not a snapshot of their contents
+    lrs2, fvs2, mks2, _ = make_clip(seed=34, n=1, t=4, h=24, w=40, fv_size=64)
+    lrs.copy_(lrs2.cuda()); fvs.copy_(fvs2.cuda()); mks.copy_(mks2.cuda())
+    o4 = m(lrs, fvs, mks).clone()
+    m.use_graphs = False
+    assert torch.equal(o4, m(lrs, fvs, mks))
+    # streaming device->host copies inside the graph
+    m.use_graphs = True
+    host = torch.empty(o4.shape, dtype=torch.float32).pin_memory()
+    for _ in range(3):
+        host.zero_()
+        m(lrs, fvs, mks, out_host=host)
+        torch.cuda.synchronize()
+        assert torch.equal(host, o4.cpu())
+    # new weights invalidate the graphs
+    m.load_state_dict(make_state_dict(seed=2), strict=True)
+    o5 = m(lrs, fvs, mks)
+    assert not torch.equal(o5, o4)
