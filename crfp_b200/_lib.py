@@ -160,6 +160,8 @@ SYMBOLS = {
     "crfp_resize_bilinear": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float,
                                        C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "crfp_avgpool2": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crfp_fovea_paste": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                   C.c_void_p]),
     "crfp_nchw_to_nhwc": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p,
                                     C.c_void_p]),
     "crfp_nhwc_to_nchw": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,

@@ -242,6 +242,22 @@ int launch_flow_warp(const crfp_warp_desc& d, cudaStream_t st) {
   return check_launch();
 }
 
+// ---- fovea paste: what the data loader does on the host (fvs[:, y:y+fv, x:x+fv] = patch, mks[...] = 1) for all
+// frames of a clip in one launch; `clear` = zero the rectangles instead (the previous call's positions)
+__global__ void fovea_paste_kernel(const float* __restrict__ patch, const int32_t* __restrict__ coords, int fv, int H, int W,
+                                   float* __restrict__ fvs, uint8_t* __restrict__ mks, int clear) {
+  const int f = blockIdx.y;   // frame index over n * t
+  const int y0 = min(max(coords[2 * f], 0), H - fv), x0 = min(max(coords[2 * f + 1], 0), W - fv);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < fv * fv; i += gridDim.x * blockDim.x) {
+    const int dy = i / fv, dx = i - dy * fv;
+    const size_t o = (size_t)(y0 + dy) * W + (x0 + dx);
+    mks[(size_t)f * H * W + o] = clear ? 0 : 1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      fvs[((size_t)f * 3 + c) * H * W + o] = clear ? 0.f : patch[((size_t)f * 3 + c) * fv * fv + i];
+  }
+}
+
 }  // namespace crfp
 
 using namespace crfp;
@@ -274,6 +290,17 @@ extern "C" int crfp_resize_bilinear(int n, int hin, int win, int c, const float*
   const long long total = (long long)n * hout * wout * c;
   launch_k(resize_bilinear_kernel, dim3(grid1d(total)), dim3(256), (size_t)(0), (cudaStream_t)stream, n, hin, win, c, in, hout, wout, rscale_h,
                                                                          rscale_w, mul, out);
+  return check_launch();
+}
+
+extern "C" int crfp_fovea_paste(const float* patch, const int32_t* coords, int frames, int fv, int H, int W, float* fvs,
+                                uint8_t* mks, int clear, crfp_stream stream) {
+  if (!coords || !fvs || !mks || (!clear && !patch)) return CRFP_ERR_NULL;
+  if (frames < 0 || fv <= 0 || fv > H || fv > W) return CRFP_ERR_BAD_SHAPE;
+  if (frames == 0) return CRFP_OK;
+  int bx = (fv * fv + 255) / 256;
+  if (bx > 64) bx = 64;
+  launch_k(fovea_paste_kernel, dim3(bx, frames), dim3(256), (size_t)(0), (cudaStream_t)stream, patch, coords, fv, H, W, fvs, mks, clear);
   return check_launch();
 }
 

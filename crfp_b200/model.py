@@ -234,41 +234,51 @@ class CRFP_DSV(_CRFPBase):
     def forward(self, lrs, fvs, mks, out_host=None):
         """Reference signature `forward(lrs, fvs, mks)`; the optional `out_host` (pinned CPU tensor) additionally
         streams every finished frame to the host while the recurrence continues."""
+        self._check_mode()
+        with torch.no_grad():
+            lrs, fvs, mks = self._check_inputs(lrs, fvs, mks)
+            key = ("clip", lrs.data_ptr(), fvs.data_ptr(), mks.data_ptr())
+            return self._forward_clip(key, lrs, fvs, mks, out_host, None)
+
+    def _check_mode(self):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
             raise NotImplementedError("crfp_b200: the backward kernels are not implemented yet; call under "
                                       "torch.no_grad() / model.eval() (SURVEY.md 8(f) rank 1)")
-        with torch.no_grad():
-            lrs, fvs, mks = self._check_inputs(lrs, fvs, mks)
-            n, t, _, h, w = lrs.shape
-            dev = lrs.device
-            with torch.cuda.device(dev):
-                L.check(L.lib().crfp_check_device(), "device check (sm_100 required)")
-                W = self._weights(dev)
-                buf = self._clip_buffers(n, t, h, w, dev)
 
-                def run(out):
-                    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-                    shp = L.DsvShape(n=n, t=t, h=h, w=w, mid_channels=self.mid_channels)
-                    L.check(L.lib().crfp_dsv_prepare(C.byref(shp), C.byref(W), lrs.data_ptr(), None, buf["lr4"].data_ptr(),
-                                                     buf["x_lr"].data_ptr(), buf["flows"].data_ptr(), buf["ws"].data_ptr(),
-                                                     buf["ws"].numel(), st), "dsv_prepare")
-                    self._run_frames(buf, W, lrs, fvs, mks, None, out, [i == 0 for i in range(t)], out_host)
+    def _forward_clip(self, key, lrs, fvs, mks, out_host, pre):
+        """prepare + frame loop, eagerly or as a replay of the captured whole-clip graph.  `pre(stream)` = extra work
+        at the head of the clip (the fovea paste of forward_patch)."""
+        n, t, _, h, w = lrs.shape
+        dev = lrs.device
+        with torch.cuda.device(dev):
+            L.check(L.lib().crfp_check_device(), "device check (sm_100 required)")
+            W = self._weights(dev)
+            buf = self._clip_buffers(n, t, h, w, dev)
 
-                key = (n, t, h, w, str(dev), lrs.data_ptr(), fvs.data_ptr(), mks.data_ptr(),
-                       0 if out_host is None else out_host.data_ptr(), bool(self.skip_outside_fovea))
-                if self.use_graphs and not torch.cuda.is_current_stream_capturing():
-                    entry = self._graphs.get(key)
-                    if entry is None and self._seen_key == key:
-                        entry = self._capture(key, run, (n, t, 3, 8 * h, 8 * w), dev)
-                    self._seen_key = key
-                    if entry is not None:
-                        self._graphs.move_to_end(key)
-                        entry["graph"].replay()
-                        L.lib().crfp_launch_count_add(entry["launches"])
-                        return entry["out"]
-                out = torch.empty(n, t, 3, 8 * h, 8 * w, device=dev, dtype=torch.float32)
-                run(out)
-            return out
+            def run(out):
+                st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+                if pre is not None:
+                    pre(st)
+                shp = L.DsvShape(n=n, t=t, h=h, w=w, mid_channels=self.mid_channels)
+                L.check(L.lib().crfp_dsv_prepare(C.byref(shp), C.byref(W), lrs.data_ptr(), None, buf["lr4"].data_ptr(),
+                                                 buf["x_lr"].data_ptr(), buf["flows"].data_ptr(), buf["ws"].data_ptr(),
+                                                 buf["ws"].numel(), st), "dsv_prepare")
+                self._run_frames(buf, W, lrs, fvs, mks, None, out, [i == 0 for i in range(t)], out_host)
+
+            key = key + (n, t, h, w, str(dev), 0 if out_host is None else out_host.data_ptr(), bool(self.skip_outside_fovea))
+            if self.use_graphs and not torch.cuda.is_current_stream_capturing():
+                entry = self._graphs.get(key)
+                if entry is None and self._seen_key == key:
+                    entry = self._capture(key, run, (n, t, 3, 8 * h, 8 * w), dev)
+                self._seen_key = key
+                if entry is not None:
+                    self._graphs.move_to_end(key)
+                    entry["graph"].replay()
+                    L.lib().crfp_launch_count_add(entry["launches"])
+                    return entry["out"]
+            out = torch.empty(n, t, 3, 8 * h, 8 * w, device=dev, dtype=torch.float32)
+            run(out)
+        return out
 
     def _capture(self, key, run, out_shape, dev):
         """Capture one whole-clip forward (prepare + every frame, incl. the streaming device->host copies) into a CUDA
@@ -298,18 +308,44 @@ class CRFP_DSV(_CRFPBase):
 
     def forward_patch(self, lrs, fovea_patch, coords, out_host=None):
         """Convenience entry named by BASELINE.json: `fovea_patch` (n,t,3,FV,FV) pasted at integer top-left
-        `coords` (n,t,2) = [y, x] exactly as the data loader does (dataset/reds.py:196-201)."""
-        n, t, _, h, w = lrs.shape
-        fv = fovea_patch.shape[-1]
-        H, Wd = 8 * h, 8 * w
-        mks = fovea_rect(coords.cpu(), fv, H, Wd).to(lrs.device)
-        fvs = torch.zeros(n, t, 3, H, Wd, device=lrs.device, dtype=torch.float32)
-        cc = coords.cpu()
-        for b in range(n):
-            for i in range(t):
-                y, x = int(cc[b, i, 0]), int(cc[b, i, 1])
-                fvs[b, i, :, y:y + fv, x:x + fv] = fovea_patch[b, i]
-        return self.forward(lrs, fvs, mks, out_host=out_host)
+        `coords` (n,t,2) = [y, x] exactly as the data loader does (dataset/reds.py:196-201) — on the device, into
+        persistent full-frame fvs / mks buffers (only the previous call's rectangles are cleared)."""
+        self._check_mode()
+        with torch.no_grad():
+            if not (isinstance(lrs, torch.Tensor) and lrs.is_cuda and isinstance(fovea_patch, torch.Tensor) and fovea_patch.is_cuda):
+                raise L.CrfpError("lrs and fovea_patch must be CUDA tensors: crfp_b200 has no CPU fallback")
+            n, t, c, h, w = lrs.shape
+            fv = fovea_patch.shape[-1]
+            H, Wd = 8 * h, 8 * w
+            if c != 3 or tuple(fovea_patch.shape) != (n, t, 3, fv, fv) or fv > min(H, Wd):
+                raise ValueError(f"lrs must be (n,t,3,h,w) and fovea_patch (n,t,3,fv,fv) with fv <= {min(H, Wd)}")
+            if tuple(coords.shape) != (n, t, 2):
+                raise ValueError(f"coords must be {(n, t, 2)}")
+            cc = coords.detach().to("cpu", torch.int64)
+            if int(cc.min()) < 0 or int(cc[..., 0].max()) > H - fv or int(cc[..., 1].max()) > Wd - fv:
+                raise ValueError("fovea patch outside the frame")
+            dev = lrs.device
+            lrs = lrs.to(torch.float32).contiguous()
+            patch = fovea_patch.to(torch.float32).contiguous()
+            pk = (n, t, h, w, fv, str(dev))
+            if getattr(self, "_patch_buf", None) is None or self._patch_buf[0] != pk:
+                self._graphs.clear()
+                self._patch_buf = (pk, dict(fvs=torch.zeros(n, t, 3, H, Wd, device=dev),
+                                            mks=torch.zeros(n, t, 1, H, Wd, device=dev, dtype=torch.uint8),
+                                            coords=torch.zeros(n, t, 2, device=dev, dtype=torch.int32),
+                                            prev=torch.zeros(n, t, 2, device=dev, dtype=torch.int32)))
+            pb = self._patch_buf[1]
+            pb["coords"].copy_(cc.to(torch.int32))          # outside the graph: a host -> device copy of n*t*8 bytes
+            lib = L.lib()
+
+            def pre(st):
+                args = (n * t, fv, H, Wd, pb["fvs"].data_ptr(), pb["mks"].data_ptr())
+                L.check(lib.crfp_fovea_paste(None, pb["prev"].data_ptr(), *args, 1, st), "fovea clear")
+                L.check(lib.crfp_fovea_paste(patch.data_ptr(), pb["coords"].data_ptr(), *args, 0, st), "fovea paste")
+                pb["prev"].copy_(pb["coords"])
+
+            key = ("patch", lrs.data_ptr(), patch.data_ptr(), fv)
+            return self._forward_clip(key, lrs, pb["fvs"], pb["mks"], out_host, pre)
 
 
 class CRFP(CRFP_DSV):

@@ -300,6 +300,14 @@ size_t crfp_sizeof_dcn_desc(void);
 int crfp_resize_bilinear(int n, int hin, int win, int c, const float* in, int hout, int wout, float rscale_h,
                          float rscale_w, float mul, float* out, crfp_stream stream);
 int crfp_avgpool2(int n, int hin, int win, int c, const float* in, float* out, crfp_stream stream);
+/*
+ * Fovea paste = the data loader's `ref[:, y:y+fv, x:x+fv] = patch; ref_sp[...] = 1` (dataset/reds.py:196-201) on the
+ * device for `frames` = n*t frames at once: patch [frames][3][fv][fv], coords int32 [frames][2] = (y, x) top-left in
+ * HR pixels (clamped to the frame), fvs [frames][3][H][W], mks [frames][H][W] (bytes).  clear != 0 zeroes the
+ * rectangles instead (used with the previous call's coords so that persistent fvs / mks buffers stay exact).
+ */
+int crfp_fovea_paste(const float* patch, const int32_t* coords, int frames, int fv, int H, int W, float* fvs,
+                     uint8_t* mks, int clear, crfp_stream stream);
 /* NCHW (with an explicit image stride in floats) -> NHWC with cpad >= c channels (extra channels zero) */
 int crfp_nchw_to_nhwc(int n, int c, int h, int w, const float* in, long long in_image_stride, int cpad, float* out,
                       crfp_stream stream);

@@ -199,3 +199,37 @@ def test_cuda_graph_replay_matches_eager(sd):
     m.load_state_dict(make_state_dict(seed=2), strict=True)
     o5 = m(lrs, fvs, mks)
     assert not torch.equal(o5, o4)
+
+
+def test_forward_patch_device_paste(sd):
+    """forward_patch (device-side fovea paste into persistent buffers, previous rectangles cleared, graph replay from
+    the second call on) == forward on host-assembled fvs / mks, for changing gaze positions."""
+    from crfp_b200 import CRFP_DSV
+    from crfp_b200.synthetic import fovea_rect
+    m = CRFP_DSV("cuda", mid_channels=32).eval()
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    n, t, h, w, fv = 2, 3, 16, 24, 48
+    H, W = 8 * h, 8 * w
+    g = torch.Generator().manual_seed(5)
+    lrs = torch.rand(n, t, 3, h, w, generator=g).cuda()
+    patch = torch.rand(n, t, 3, fv, fv, generator=g).cuda()
+    for trial in range(4):
+        coords = torch.stack([torch.randint(0, H - fv + 1, (n, t), generator=g), torch.randint(0, W - fv + 1, (n, t), generator=g)], -1)
+        if trial == 3:
+            patch.copy_(torch.rand(n, t, 3, fv, fv, generator=g))
+        fvs = torch.zeros(n, t, 3, H, W)
+        for b in range(n):
+            for i in range(t):
+                y, x = int(coords[b, i, 0]), int(coords[b, i, 1])
+                fvs[b, i, :, y:y + fv, x:x + fv] = patch[b, i].cpu()
+        mks = fovea_rect(coords, fv, H, W)
+        m.use_graphs = False
+        ref = m(lrs, fvs.cuda(), mks.cuda()).clone()
+        m.use_graphs = True
+        out = m.forward_patch(lrs, patch, coords)
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref), f"trial {trial}"
+    assert len(m._graphs) >= 1
+    with pytest.raises(ValueError):
+        m.forward_patch(lrs, patch, coords + 10_000)
