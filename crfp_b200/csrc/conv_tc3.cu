@@ -127,7 +127,7 @@ __device__ __noinline__ void tc3_issue_row_generic(uint64_t dAh, uint64_t dAl, u
 // post-scale, store (fp32 NHWC segments or pixel shuffle).  Shared by both kernel variants.
 __device__ __forceinline__ void tc3_epilogue_chunk(const Tc3Params& P, float* v, const float* sBiasC, const float* sWxC,
                                                    const float2* ex, float2 fl, int NT, int cbase, int nvalid, int n, int y,
-                                                   int x, size_t pix) {
+                                                   int x, size_t pix, const float4* rpre = nullptr) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] += sBiasC[i];
       if (sWxC != nullptr) {
@@ -158,7 +158,12 @@ __device__ __forceinline__ void tc3_epilogue_chunk(const Tc3Params& P, float* v,
           v[i] = (cc < P.head_split) ? P.head_mag * fast_tanh(v[i]) + ((cc & 1) ? fl.x : fl.y) : fast_sigmoid(v[i]);
         }
       }
-      if (P.residual != nullptr) {
+      if (rpre != nullptr) {   // residual of this chunk already in registers (loaded while the MMAs were running)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[4 * j] += rpre[j].x; v[4 * j + 1] += rpre[j].y; v[4 * j + 2] += rpre[j].z; v[4 * j + 3] += rpre[j].w;
+        }
+      } else if (P.residual != nullptr) {
         const float* rp = P.residual + pix * P.res_cstride + P.res_coffset + cbase;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -345,53 +350,89 @@ __global__ void __launch_bounds__(128) conv_tc3_kernel(const Tc3Params P) {
 // consumed", -> producers), acc_empty[buf] (epilogue -> MMA).  All three stages of consecutive rows overlap.
 constexpr int WS_EPI = 128, WS_NPROD = 224, WS_THREADS = 384, WS_SLOTS = 4;
 
-__device__ __forceinline__ void ws_produce_row(const Tc3Params& P, uint4* hi, uint4* lo, int n, int y, int x0, int ptid) {
-  const bool yin = (y >= 0 && y < P.h);
-#pragma unroll 1
-  for (int s = 0; s < P.nsrc; ++s) {
-    const int cps = P.src_c[s] >> 3;  // 8-channel records per pixel of this source
-    const int nrec = T3WP * cps;
-    const bool unsh = (P.src_mode[s] == CRFP_SRC_UNSHUFFLE4);   // pixel_unshuffle(4) of a dense 4-channel HR plane
-    const float* rowp = unsh ? P.src[s] + ((size_t)n * (P.h * 4) + (size_t)(yin ? y : 0) * 4) * (size_t)(P.w * 4) * 4
-                             : P.src[s] + (((size_t)n * P.h + (yin ? y : 0)) * (size_t)P.w) * P.src_cstride[s] + P.src_coffset[s];
-    const int kbase = P.kstart[s] * T3WP;
-#pragma unroll 1
-    for (int base = ptid; base < nrec; base += 3 * WS_NPROD) {
-      float4 a[3], b[3];
-      int dst[3];
-      float f[3];
+// Producer loop with register prefetch.  Every producer thread owns up to RPT fixed records of a row (record = 8
+// channels of one pixel of one source; same (source, pixel, channel group) for every row, so all addressing is hoisted
+// out of the row loop).  The loads of row u+D are issued before row u is split and stored: D+1 rows of HBM latency
+// overlap with the conversion and with the wait for a free ring slot.
+template <int RPT, int D>
+__device__ __forceinline__ void ws_producer_loop(const Tc3Params& P, uint4* sAh, uint4* sAl, int slot_recs, int n, int y_begin,
+                                                 int rows_out, int x0, int ptid, uint64_t* full_bar, uint64_t* accf_bar,
+                                                 long long* tr) {
+  const float* rp[RPT];
+  int rstride[RPT], dst[RPT];
+  const int nrec_total = T3WP * P.kc_real;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const int id = base + k * WS_NPROD;
-        dst[k] = -1;
-        a[k] = b[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        f[k] = 1.f;
-        if (id < nrec) {
-          const int px = id / cps, j = id - px * cps;
-          const int x = x0 + px - 1;
-          dst[k] = kbase + j * T3WP + px;
-          if (yin && x >= 0 && x < P.w) {
-            // unshuffle: record j = HR row 4y + j/2, HR pixels 4x + 2*(j%2) and +1 (8 contiguous floats)
-            const float4* g = unsh ? reinterpret_cast<const float4*>(rowp + ((size_t)(j >> 1) * (P.w * 4) + (size_t)x * 4 + (j & 1) * 2) * 4)
-                                   : reinterpret_cast<const float4*>(rowp + (size_t)x * P.src_cstride[s] + j * 8);
-            a[k] = __ldg(g);
-            b[k] = __ldg(g + 1);
-            if (P.fg != nullptr) f[k] = __ldg(P.fg + (size_t)n * P.fg_clip_stride + (size_t)y * P.w + x);
-          }
+  for (int k = 0; k < RPT; ++k) {
+    const int id = ptid + k * WS_NPROD;
+    rp[k] = nullptr; rstride[k] = 0; dst[k] = -1;
+    if (id < nrec_total) {
+      int s = 0, local = id;
+      while (s + 1 < P.nsrc && local >= T3WP * (P.src_c[s] >> 3)) { local -= T3WP * (P.src_c[s] >> 3); ++s; }
+      const int cps = P.src_c[s] >> 3;
+      const int px = local / cps, j = local - px * cps;
+      const int x = x0 + px - 1;
+      dst[k] = (P.kstart[s] + j) * T3WP + px;
+      if (x >= 0 && x < P.w) {
+        if (P.src_mode[s] == CRFP_SRC_UNSHUFFLE4) {
+          // pixel_unshuffle(4) of a dense 4-channel HR plane: record j = HR row 4y + j/2, HR pixels 4x + 2*(j%2), +1
+          rp[k] = P.src[s] + ((size_t)n * (P.h * 4) * (size_t)(P.w * 4) + (size_t)(j >> 1) * (P.w * 4) + (size_t)x * 4 + (j & 1) * 2) * 4;
+          rstride[k] = 4 * (P.w * 4) * 4;
+        } else {
+          rp[k] = P.src[s] + ((size_t)n * P.h * P.w + x) * (size_t)P.src_cstride[s] + P.src_coffset[s] + j * 8;
+          rstride[k] = P.w * P.src_cstride[s];
         }
       }
+    }
+  }
+  float4 ra[D + 1][RPT], rb[D + 1][RPT];
+  float rf[D + 1][RPT];
+  auto load_row = [&](int y, float4* a, float4* b, float* f) {
+    const bool yin = (y >= 0 && y < P.h);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (dst[k] < 0) continue;
-        if (P.fg != nullptr) {
-          a[k].x *= f[k]; a[k].y *= f[k]; a[k].z *= f[k]; a[k].w *= f[k];
-          b[k].x *= f[k]; b[k].y *= f[k]; b[k].z *= f[k]; b[k].w *= f[k];
-        }
-        uint4 h, l;
-        split8(a[k], b[k], h, l);
-        hi[dst[k]] = h;
-        lo[dst[k]] = l;
+    for (int k = 0; k < RPT; ++k) {
+      a[k] = b[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      f[k] = 1.f;
+      if (yin && rp[k] != nullptr) {
+        const float4* g = reinterpret_cast<const float4*>(rp[k] + (long long)y * rstride[k]);
+        a[k] = __ldg(g);
+        b[k] = __ldg(g + 1);
+        if (P.fg != nullptr) f[k] = __ldg(P.fg + (size_t)n * P.fg_clip_stride + (size_t)y * P.w + (x0 + dst[k] % T3WP - 1));
       }
+    }
+  };
+  const int nrows = rows_out + 2;
+#pragma unroll
+  for (int d = 0; d < D; ++d)
+    if (d < nrows) load_row(y_begin - 1 + d, ra[d], rb[d], rf[d]);
+  for (int u = 0; u < nrows; ++u) {
+    const int slot = u & (WS_SLOTS - 1);
+    if (u + D < nrows) load_row(y_begin - 1 + u + D, ra[D], rb[D], rf[D]);
+    if (tr && u < 60) tr[u * 4 + 0] = clock64();
+    if (u >= WS_SLOTS) umma::mbar_wait_safe(&accf_bar[(u - 4) & 1], (uint32_t)(((u - 4) >> 1) & 1));
+    if (tr && u < 60) tr[u * 4 + 1] = clock64();
+    uint4* hi = sAh + slot * slot_recs;
+    uint4* lo = sAl + slot * slot_recs;
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      if (dst[k] < 0) continue;
+      float4 a = ra[0][k], b = rb[0][k];
+      if (P.fg != nullptr) {
+        const float f = rf[0][k];
+        a.x *= f; a.y *= f; a.z *= f; a.w *= f;
+        b.x *= f; b.y *= f; b.z *= f; b.w *= f;
+      }
+      uint4 h, l;
+      split8(a, b, h, l);
+      hi[dst[k]] = h;
+      lo[dst[k]] = l;
+    }
+    umma::fence_proxy_async();
+    umma::mbar_arrive(&full_bar[slot]);
+    if (tr && u < 60) tr[u * 4 + 2] = clock64();
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) { ra[d][k] = ra[d + 1][k]; rb[d][k] = rb[d + 1][k]; rf[d][k] = rf[d + 1][k]; }
     }
   }
 }
@@ -416,6 +457,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
   const int y_begin = blockIdx.y * P.rows_per_cta;
   const int y_end = min(P.h, y_begin + P.rows_per_cta);
   const int rows_out = y_end - y_begin;
+  // profiling aid (crfp_conv3x3_tc3_trace): clock64 stamps of one interior CTA, per role and row
+  const bool trace_cta = P.dbg != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == gridDim.y / 2 && blockIdx.z == 0;
+  if (trace_cta && tid == 0) P.dbg[0] = clock64();
 
   pdl_trigger();   // constant-only prologue below overlaps the previous kernel's tail (PDL)
   {
@@ -450,30 +494,33 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
   umma::fence_after_sync();
   const uint32_t taddr = tmem_base_s;
   pdl_wait();      // activations (sources, residual, flow, destinations) are only touched from here on
+  if (trace_cta && tid == 0) P.dbg[1] = clock64();
 
   if (warp >= 5) {
     // ------------------------------------------------------------------ producers
     const int ptid = tid - 160;
-    for (int u = 0; u < rows_out + 2; ++u) {
-      const int slot = u & (WS_SLOTS - 1);
-      if (u >= WS_SLOTS) umma::mbar_wait_safe(&accf_bar[(u - 4) & 1], (uint32_t)(((u - 4) >> 1) & 1));
-      ws_produce_row(P, sAh + slot * slot_recs, sAl + slot * slot_recs, n, y_begin - 1 + u, x0, ptid);
-      umma::fence_proxy_async();
-      umma::mbar_arrive(&full_bar[slot]);
-    }
+    long long* tr = (trace_cta && ptid == 0) ? P.dbg + 1024 : nullptr;        // ws trace, role 1: producers
+    if (P.kc_real <= 4)
+      ws_producer_loop<3, 2>(P, sAh, sAl, slot_recs, n, y_begin, rows_out, x0, ptid, full_bar, accf_bar, tr);
+    else
+      ws_producer_loop<5, 1>(P, sAh, sAl, slot_recs, n, y_begin, rows_out, x0, ptid, full_bar, accf_bar, tr);
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = umma::make_idesc_bf16(T3M, NT);
     const uint64_t dAh = umma::make_desc(umma::smem_u32(sAh), T3WP * 16, 128), dAl = umma::make_desc(umma::smem_u32(sAl), T3WP * 16, 128);
     const uint64_t dBh = umma::make_desc(umma::smem_u32(sWh), (uint32_t)NT * 16, 128), dBl = umma::make_desc(umma::smem_u32(sWl), (uint32_t)NT * 16, 128);
+    long long* tr = (trace_cta && (tid & 31) == 0) ? P.dbg + 2048 : nullptr;  // role 2: MMA issuer
     for (int v = 0; v < rows_out; ++v) {
       if (v == 0) {
         umma::mbar_wait_safe(&full_bar[0], 0u);
         umma::mbar_wait_safe(&full_bar[1], 0u);
       }
       const int u2 = v + 2, b = v & 1;
+      if (tr && v < 60) tr[v * 4 + 0] = clock64();
       umma::mbar_wait_safe(&full_bar[u2 & 3], (uint32_t)((u2 >> 2) & 1));
+      if (tr && v < 60) tr[v * 4 + 1] = clock64();
       umma::mbar_wait_safe(&acce_bar[b], (uint32_t)(((v >> 1) & 1) ^ 1));
+      if (tr && v < 60) tr[v * 4 + 2] = clock64();
       umma::fence_after_sync();
       if (umma::elect_one()) {
         const uint32_t s0 = (uint32_t)((v & 3) * slot_recs), s1 = (uint32_t)(((v + 1) & 3) * slot_recs),
@@ -488,9 +535,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
         umma::mma_commit(&accf_bar[b]);
       }
       __syncwarp();
+      if (tr && v < 60) tr[v * 4 + 3] = clock64();
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps (thread = pixel = TMEM lane)
+    long long* tr = (trace_cta && tid == 0) ? P.dbg + 3072 : nullptr;         // role 3: epilogue
     const int x = x0 + tid;
     const bool xvalid = x < P.w;
     const bool shuffle4_fast = P.out_kind == TC_OUT_SHUFFLE_F32 && P.shuffle_r == 4 && NT == 64 && P.cout == 64 &&
@@ -511,7 +560,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
                         : make_float2(0.f, 0.f);
         }
       }
+      float4 rpre[8];
+      const bool use_rpre = P.residual != nullptr && xvalid && NT >= 32 && cotile * NT + 32 <= P.cout;
+      if (use_rpre) {   // the residual of the first 32-channel chunk is fetched while the MMAs of this row run
+        const float* rpp = P.residual + pix * P.res_cstride + P.res_coffset + cotile * NT;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rpre[j] = __ldg(reinterpret_cast<const float4*>(rpp + 4 * j));
+      }
+      if (tr && v < 60) tr[v * 4 + 0] = clock64();
       umma::mbar_wait_safe(&accf_bar[b], (uint32_t)((v >> 1) & 1));
+      if (tr && v < 60) tr[v * 4 + 1] = clock64();
       umma::fence_after_sync();
       if (shuffle4_fast) {
         // PixelShufflePack x4 with 64 conv channels -> 4-channel HR plane: hold all 64 values, then every (dy) row of
@@ -550,8 +608,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
         const int cbase = cotile * NT + c0;
         if (!xvalid || cbase >= P.cout) continue;
         const int nvalid = min(min(32, NT - c0), P.cout - cbase);
-        tc3_epilogue_chunk(P, vv, sBias + c0, P.extra != nullptr ? sWx + c0 : nullptr, ex, fl, NT, cbase, nvalid, n, y, x, pix);
+        tc3_epilogue_chunk(P, vv, sBias + c0, P.extra != nullptr ? sWx + c0 : nullptr, ex, fl, NT, cbase, nvalid, n, y, x, pix,
+                           (c0 == 0 && use_rpre) ? rpre : nullptr);
       }
+      if (tr && v < 60) tr[v * 4 + 2] = clock64();
     }
   }
   umma::fence_before_sync();
