@@ -306,10 +306,10 @@ def main():
         torch.cuda.synchronize()
 
     def host_decouple():
-        """A ~30 ms spin kernel ahead of the start event: the host enqueues the whole timed region while the GPU is
-        still spinning, so a host stall (this pool's VMs page memory in lazily: 50-150 ms hiccups) cannot starve the
-        GPU inside the timed region.  The spin itself ends before the start event fires."""
-        torch.cuda._sleep(int(0.03 * 1.9e9))
+        """A device spin kernel ahead of the start event: the host enqueues the whole timed region (K graph launches)
+        while the GPU is still spinning, so a host stall (this pool's VMs page memory in lazily: 50-150 ms hiccups
+        were measured) cannot starve the GPU inside the timed region.  The spin ends before the start event fires."""
+        torch.cuda._sleep(int(min(1.0, 0.2 + 0.01 * args.steps) * 1.9e9))
 
     # ---------------- device-resident throughput
     sampler = ClockSampler(local)

@@ -10,9 +10,14 @@ static thread_local cudaError_t g_last_err = cudaSuccess;
 static thread_local long long g_launches = 0;
 
 void note_cuda_error(cudaError_t e) { g_last_err = e; }
-bool pdl_enabled() {
-  static const bool on = (getenv("CRFP_NO_PDL") == nullptr);
-  return on;
+bool pdl_enabled(bool persistent) {
+  static const int mode = [] {   // 0 none, 1 persistent tensor-core kernels only, 2 all
+    if (getenv("CRFP_NO_PDL") != nullptr) return 0;
+    const char* m = getenv("CRFP_PDL");
+    if (m == nullptr) return 1;
+    return !strcmp(m, "all") ? 2 : !strcmp(m, "none") ? 0 : 1;
+  }();
+  return mode == 2 || (mode == 1 && persistent);
 }
 void count_launch() { ++g_launches; }
 

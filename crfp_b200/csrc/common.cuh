@@ -36,20 +36,31 @@ inline int check_launch() {
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-// ---- programmatic dependent launch (PDL): every kernel of the frame chain is launched with
-// programmaticStreamSerialization so that its launch latency, CTA scheduling and constant-only prologue (weights ->
-// smem, TMEM allocation, mbarrier init) overlap the tail of the previous kernel; pdl_wait() (griddepcontrol.wait)
-// precedes the first access to any activation.  CRFP_NO_PDL=1 in the environment disables the attribute (A/B).
-bool pdl_enabled();
-template <typename... KArgs, typename... Args>
-inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+// ---- programmatic dependent launch (PDL): a kernel launched with programmaticStreamSerialization may start while
+// its predecessor is still running; its launch latency, CTA scheduling and constant-only prologue (weights -> smem,
+// TMEM allocation, mbarrier init) then overlap the predecessor's tail.  pdl_wait() (griddepcontrol.wait) precedes
+// the first access to any activation.
+// CRFP_PDL = all | ws | none (default ws): measured in the whole-frame chain, early launch pays between the persistent
+// one-CTA-per-SM tensor-core kernels (their weight / TMEM / barrier prologue hides behind the previous kernel's tail)
+// and costs ~3 % when the multi-wave SIMT kernels are launched early as well.
+bool pdl_enabled(bool persistent);
+template <bool PERSISTENT, typename... KArgs, typename... Args>
+inline void launch_k_impl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled(PERSISTENT) ? 1 : 0;
   (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  launch_k_impl<false>(kernel, grid, block, smem, st, static_cast<Args&&>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline void launch_k_ws(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  launch_k_impl<true>(kernel, grid, block, smem, st, static_cast<Args&&>(args)...);
 }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

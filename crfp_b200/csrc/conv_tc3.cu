@@ -342,13 +342,14 @@ __global__ void __launch_bounds__(128) conv_tc3_kernel(const Tc3Params P) {
 
 
 // =====================================================================================================================
-// Warp-specialised, software-pipelined variant (default): 384 threads = 4 epilogue warps (TMEM lanes 0..127) + 1 MMA
-// warp + 7 producer warps.  Producers load fp32 rows straight from global (coalesced LDG.128), split them hi/lo and
-// store them into a 4-slot ring of UMMA operand rows; the MMA warp issues each output row's 9 x KC/2 x 3 tcgen05.mma
-// into one of two TMEM accumulators; the epilogue warps drain the other accumulator.  Stages meet only through
+// Warp-specialised, software-pipelined variant (default): 384 threads = 4 epilogue warps (TMEM lanes 0..127) + 2 MMA
+// warps (even / odd output rows) + 6 producer warps.  Producers load fp32 rows straight from global (coalesced
+// LDG.128, one or more rows ahead in registers), split them hi/lo and store them into a 4-slot ring of UMMA operand
+// rows; an MMA warp issues its output row's 9 x KC/2 x 3 tcgen05.mma into its TMEM accumulator; the epilogue warps
+// drain the other accumulator.  Stages meet only through
 // mbarriers: full[slot] (producers -> MMA), acc_full[buf] (tcgen05.commit -> epilogue and, as "rows <= v are
 // consumed", -> producers), acc_empty[buf] (epilogue -> MMA).  All three stages of consecutive rows overlap.
-constexpr int WS_EPI = 128, WS_NPROD = 224, WS_THREADS = 384, WS_SLOTS = 4;
+constexpr int WS_EPI = 128, WS_NPROD = 192, WS_THREADS = 384, WS_SLOTS = 4;
 
 // Producer loop with register prefetch.  Every producer thread owns up to RPT fixed records of a row (record = 8
 // channels of one pixel of one source; same (source, pixel, channel group) for every row, so all addressing is hoisted
@@ -496,27 +497,27 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
   pdl_wait();      // activations (sources, residual, flow, destinations) are only touched from here on
   if (trace_cta && tid == 0) P.dbg[1] = clock64();
 
-  if (warp >= 5) {
+  if (warp >= 6) {
     // ------------------------------------------------------------------ producers
-    const int ptid = tid - 160;
+    const int ptid = tid - 192;
     long long* tr = (trace_cta && ptid == 0) ? P.dbg + 1024 : nullptr;        // ws trace, role 1: producers
     if (P.kc_real <= 4)
       ws_producer_loop<3, 2>(P, sAh, sAl, slot_recs, n, y_begin, rows_out, x0, ptid, full_bar, accf_bar, tr);
     else
-      ws_producer_loop<5, 1>(P, sAh, sAl, slot_recs, n, y_begin, rows_out, x0, ptid, full_bar, accf_bar, tr);
-  } else if (warp == 4) {
-    // ------------------------------------------------------------------ MMA issuer
+      ws_producer_loop<6, 0>(P, sAh, sAl, slot_recs, n, y_begin, rows_out, x0, ptid, full_bar, accf_bar, tr);
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ MMA issuers: warp 4 = even rows (accumulator
+    // 0), warp 5 = odd rows (accumulator 1).  While one warp is blocked feeding the tensor pipe, the other one has
+    // already passed the barriers of the next row, so the pipe never drains between rows.
     const uint32_t idesc = umma::make_idesc_bf16(T3M, NT);
     const uint64_t dAh = umma::make_desc(umma::smem_u32(sAh), T3WP * 16, 128), dAl = umma::make_desc(umma::smem_u32(sAl), T3WP * 16, 128);
     const uint64_t dBh = umma::make_desc(umma::smem_u32(sWh), (uint32_t)NT * 16, 128), dBl = umma::make_desc(umma::smem_u32(sWl), (uint32_t)NT * 16, 128);
-    long long* tr = (trace_cta && (tid & 31) == 0) ? P.dbg + 2048 : nullptr;  // role 2: MMA issuer
-    for (int v = 0; v < rows_out; ++v) {
-      if (v == 0) {
-        umma::mbar_wait_safe(&full_bar[0], 0u);
-        umma::mbar_wait_safe(&full_bar[1], 0u);
-      }
+    long long* tr = (trace_cta && (tid & 31) == 0) ? P.dbg + 2048 : nullptr;  // role 2: MMA issuers
+    for (int v = warp - 4; v < rows_out; v += 2) {
       const int u2 = v + 2, b = v & 1;
       if (tr && v < 60) tr[v * 4 + 0] = clock64();
+      umma::mbar_wait_safe(&full_bar[v & 3], (uint32_t)((v >> 2) & 1));
+      umma::mbar_wait_safe(&full_bar[(v + 1) & 3], (uint32_t)(((v + 1) >> 2) & 1));
       umma::mbar_wait_safe(&full_bar[u2 & 3], (uint32_t)((u2 >> 2) & 1));
       if (tr && v < 60) tr[v * 4 + 1] = clock64();
       umma::mbar_wait_safe(&acce_bar[b], (uint32_t)(((v >> 1) & 1) ^ 1));
@@ -680,7 +681,7 @@ int launch_conv_tc3(Tc3Params p, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc3_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
     dim3 grid(strips, segs, p.n * p.ntiles);
-    launch_k(conv_tc3_ws_kernel, dim3(grid), dim3(WS_THREADS), (size_t)(smem), st, p);
+    launch_k_ws(conv_tc3_ws_kernel, dim3(grid), dim3(WS_THREADS), (size_t)(smem), st, p);
     return check_launch();
   }
   const size_t smem = tc3_smem_bytes(p.kc_real, p.kc_total, p.nt, p.extra != nullptr);

@@ -681,7 +681,7 @@ static int launch_dcn_tc3_ws(const DcnTc3Params& p, cudaStream_t st) {
   if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
   const int total = ceil_div(p.w, DTW) * ceil_div(p.h, DTH) * p.n;
   const int grid = total < sm_count() ? total : sm_count();
-  launch_k(dcn_tc3_ws_kernel, dim3(grid), dim3(512), smem, st, p, tmap);
+  launch_k_ws(dcn_tc3_ws_kernel, dim3(grid), dim3(512), smem, st, p, tmap);
   return check_launch();
 }
 
