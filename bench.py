@@ -220,6 +220,8 @@ def time_conv_mix(torch, h1, w1, reps=4):
                 t = buf24 if c == 24 else bufs[(rot + i) % 5]
                 d.src[i] = L.TcSrc(ptr=t.data_ptr(), c=c, cstride=t.shape[-1], coffset=0)
             d.cout, d.act = cout, 1
+            if cout == 216:   # the fused offset + mask heads: 10 * tanh + flow on 144 channels, sigmoid on 72
+                d.act, d.flow, d.head_split, d.head_mag = L.ACT_DCN_HEAD, flow.data_ptr(), 144, 10.0
             d.weight_hi, d.weight_lo, d.bias = hi.data_ptr(), lo.data_ptr(), bp.data_ptr()
             if extra:
                 d.extra, d.w_extra = flow.data_ptr(), wx.data_ptr()
