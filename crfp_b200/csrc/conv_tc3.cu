@@ -123,6 +123,17 @@ __device__ __noinline__ void tc3_issue_row_generic(uint64_t dAh, uint64_t dAl, u
   }
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Epilogue of one 32-channel chunk of one pixel: bias, 2-channel extra source, activation / DCN head, residual,
 // post-scale, store (fp32 NHWC segments or pixel shuffle).  Shared by both kernel variants.
 __device__ __forceinline__ void tc3_epilogue_chunk(const Tc3Params& P, float* v, const float* sBiasC, const float* sWxC,
@@ -152,15 +163,26 @@ __device__ __forceinline__ void tc3_epilogue_chunk(const Tc3Params& P, float* v,
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
       } else if (P.act == CRFP_ACT_DCN_HEAD) {
-        // offsets: mag * tanh(v) + flow;  masks: sigmoid(v).  Both are 1 - k / (exp(k v) + 1) (k = 2 / 1): one branch-free
-        // formula, so that the 32 channels' MUFU chains overlap instead of being serialised by per-channel branches
+        // offsets: mag * tanh(v) + flow = (mag + flow) - 2 mag / (exp(2v) + 1);  masks: sigmoid(v) = 1 - 1 / (exp(v) + 1).
+        // Raw ex2 / rcp MUFU ops (5 instructions per channel, no branches, 32 independent chains per chunk); chunks
+        // never straddle the offset / mask boundary in the fused head layout (144 | 72, chunk bases multiples of 16).
+        if (cbase + 32 <= P.head_split && !(cbase & 1)) {
+          const float m2 = -2.f * P.head_mag, by = P.head_mag + fl.y, bx = P.head_mag + fl.x;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int cc = cbase + i;
-          const bool off = cc < P.head_split;
-          const float k = off ? 2.f : 1.f;
-          const float t = 1.f - __fdividef(k, __expf(k * v[i]) + 1.f);
-          v[i] = off ? fmaf(P.head_mag, t, (cc & 1) ? fl.x : fl.y) : t;
+          for (int i = 0; i < 32; ++i)
+            v[i] = fmaf(m2, rcp_approx(ex2_approx(v[i] * 2.885390081777927f) + 1.f), (i & 1) ? bx : by);
+        } else if (cbase >= P.head_split) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 1.f - rcp_approx(ex2_approx(v[i] * 1.4426950408889634f) + 1.f);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int cc = cbase + i;
+            const bool off = cc < P.head_split;
+            const float k = off ? 2.f : 1.f;
+            const float t = 1.f - k * rcp_approx(ex2_approx(k * 1.4426950408889634f * v[i]) + 1.f);
+            v[i] = off ? fmaf(P.head_mag, t, (cc & 1) ? fl.x : fl.y) : t;
+          }
         }
       }
       if (rpre != nullptr) {   // residual of this chunk already in registers (loaded while the MMAs were running)
@@ -606,7 +628,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
       }
       for (int c0 = 0; c0 < NT; c0 += 32) {
         float vv[32];
+        if (tr && v == 8) tr[256 + (c0 >> 5) * 4 + 0] = clock64();
         umma::tmem_ld32(taddr + ((uint32_t)(32 * warp) << 16) + (uint32_t)b * ncols + (uint32_t)c0, vv);
+        if (tr && v == 8) tr[256 + (c0 >> 5) * 4 + 1] = clock64();
         if (tr && v < 60 && c0 == 0) tr[v * 4 + 3] = clock64();
         if (c0 + 32 >= NT) {  // last chunk is in registers: the accumulator can be overwritten
           umma::fence_before_sync();
@@ -617,6 +641,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
         const int nvalid = min(min(32, NT - c0), P.cout - cbase);
         tc3_epilogue_chunk(P, vv, sBias + c0, P.extra != nullptr ? sWx + c0 : nullptr, ex, fl, NT, cbase, nvalid, n, y, x, pix,
                            (c0 == 0 && use_rpre) ? rpre : nullptr);
+        if (tr && v == 8) tr[256 + (c0 >> 5) * 4 + 2] = clock64();
       }
       if (tr && v < 60) tr[v * 4 + 2] = clock64();
     }

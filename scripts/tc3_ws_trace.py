@@ -23,6 +23,9 @@ def run(cin_list, cout, H=360, W=640, act=1, residual=False, rows=8):
     d.dst[0] = L.TcSrc(ptr=out.data_ptr(), c=cout, cstride=cout, coffset=0)
     if residual:
         d.residual, d.res_cstride, d.res_coffset = res.data_ptr(), cout, 0
+    flow = torch.randn(1, H, W, 2, device='cuda')
+    if act == 3:
+        d.flow, d.head_split, d.head_mag = flow.data_ptr(), 144, 10.0
     flush = torch.empty(64 * 1024 * 1024, device='cuda')
     for _ in range(3):
         L.check(h.crfp_conv3x3_tc3_fwd(C.byref(d), st))
@@ -44,6 +47,11 @@ def run(cin_list, cout, H=360, W=640, act=1, residual=False, rows=8):
     last = 0
     for i in range(rows + 2):
         print(f"  row {i:2d} | prod: top {r(P[i,0]):6d} waited {r(P[i,1]):6d} done {r(P[i,2]):6d} | mma: top {r(M[i,0]):6d} full {r(M[i,1]):6d} acce {r(M[i,2]):6d} issued {r(M[i,3]):6d} | epi: top {r(E[i,0]):6d} accf {r(E[i,1]):6d} ld {r(E[i,3]):6d} done {r(E[i,2]):6d}")
-    nrow = int((E[:, 2] != 0).sum())
+    X = t[3072 + 256:3072 + 256 + 16].view(4, 4)
+    print("  row 8 chunks (before ld, after ld, after chunk):", [[r(X[c, k]) for k in range(3)] for c in range(4)])
+    nrow = int((E[:60, 2] != 0).sum())
     print(f"  rows {nrow}; last epilogue done at {r(E[nrow-1,2])} cycles -> {r(E[nrow-1,2]) / nrow:.0f} cycles/row")
-run([32], 32); run([32], 32, residual=True); run([32, 32], 32); run([32], 216, act=0)
+import os
+if os.environ.get('HEADS'): run([32], 216, act=3, rows=12)
+else:
+    run([32], 32); run([32], 32, residual=True); run([32, 32], 32); run([32], 216, act=0)
