@@ -203,7 +203,22 @@ __device__ __forceinline__ void tc3_epilogue_chunk(const Tc3Params& P, float* v,
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] *= P.post_scale;
       }
-      if (P.out_kind == TC_OUT_F32) {
+      if (P.out_kind == TC_OUT_F32 && (P.ndst == 1 || cbase >= P.dst_c[0] || cbase + nvalid <= P.dst_c[0])) {
+        // the whole chunk lands in one destination segment (always, for this network's layouts): one pointer
+        // computation, then stores at constant offsets
+        const bool s1 = P.ndst > 1 && cbase >= P.dst_c[0];
+        float* op = reinterpret_cast<float*>(s1 ? P.dst[1] : P.dst[0]) + pix * (size_t)(s1 ? P.dst_cstride[1] : P.dst_cstride[0]) +
+                    (s1 ? P.dst_coffset[1] + cbase - P.dst_c[0] : P.dst_coffset[0] + cbase);
+        if (nvalid == 32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(op + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (4 * j < nvalid) *reinterpret_cast<float4*>(op + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      } else if (P.out_kind == TC_OUT_F32) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int cc = cbase + 4 * j;
@@ -628,9 +643,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
       }
       for (int c0 = 0; c0 < NT; c0 += 32) {
         float vv[32];
-        if (tr && v == 8) tr[256 + (c0 >> 5) * 4 + 0] = clock64();
         umma::tmem_ld32(taddr + ((uint32_t)(32 * warp) << 16) + (uint32_t)b * ncols + (uint32_t)c0, vv);
-        if (tr && v == 8) tr[256 + (c0 >> 5) * 4 + 1] = clock64();
         if (tr && v < 60 && c0 == 0) tr[v * 4 + 3] = clock64();
         if (c0 + 32 >= NT) {  // last chunk is in registers: the accumulator can be overwritten
           umma::fence_before_sync();
@@ -641,7 +654,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
         const int nvalid = min(min(32, NT - c0), P.cout - cbase);
         tc3_epilogue_chunk(P, vv, sBias + c0, P.extra != nullptr ? sWx + c0 : nullptr, ex, fl, NT, cbase, nvalid, n, y, x, pix,
                            (c0 == 0 && use_rpre) ? rpre : nullptr);
-        if (tr && v == 8) tr[256 + (c0 >> 5) * 4 + 2] = clock64();
       }
       if (tr && v < 60) tr[v * 4 + 2] = clock64();
     }

@@ -47,8 +47,6 @@ def run(cin_list, cout, H=360, W=640, act=1, residual=False, rows=8):
     last = 0
     for i in range(rows + 2):
         print(f"  row {i:2d} | prod: top {r(P[i,0]):6d} waited {r(P[i,1]):6d} done {r(P[i,2]):6d} | mma: top {r(M[i,0]):6d} full {r(M[i,1]):6d} acce {r(M[i,2]):6d} issued {r(M[i,3]):6d} | epi: top {r(E[i,0]):6d} accf {r(E[i,1]):6d} ld {r(E[i,3]):6d} done {r(E[i,2]):6d}")
-    X = t[3072 + 256:3072 + 256 + 16].view(4, 4)
-    print("  row 8 chunks (before ld, after ld, after chunk):", [[r(X[c, k]) for k in range(3)] for c in range(4)])
     nrow = int((E[:60, 2] != 0).sum())
     print(f"  rows {nrow}; last epilogue done at {r(E[nrow-1,2])} cycles -> {r(E[nrow-1,2]) / nrow:.0f} cycles/row")
 import os
