@@ -53,10 +53,11 @@ __device__ __forceinline__ void thin_epilogue(const ConvParams& P, int n, int y,
     const float2 fl = __ldg(reinterpret_cast<const float2*>(P.flow + pix * 2));
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      if (c < P.head_split)
-        v[c] = P.head_mag * tanhf(v[c]) + ((c & 1) ? fl.x : fl.y);
-      else
-        v[c] = sigmoidf_(v[c]);
+      // same branch-free formulation as the tensor-core heads: 1 - k / (exp(k v) + 1), k = 2 (tanh) / 1 (sigmoid)
+      const bool off = c < P.head_split;
+      const float k = off ? 2.f : 1.f;
+      const float t = 1.f - __fdividef(k, __expf(k * v[c]) + 1.f);
+      v[c] = off ? fmaf(P.head_mag, t, (c & 1) ? fl.x : fl.y) : t;
     }
   } else if (P.act == CRFP_ACT_TANH256) {
 #pragma unroll

@@ -286,23 +286,49 @@ __global__ void __launch_bounds__(256) fovea_compose_kernel(int n, int H, int W,
 }
 
 // flags[n][ty][tx] = any(mask) over the 32x32 tile dilated by one tile on every side (covers the 3-pixel receptive
-// field of encoder_hr.0 -> encoder_hr.2 -> conv_tttf around every mask pixel)
-__global__ void __launch_bounds__(256) fovea_tile_flags_kernel(int H, int W, const uint8_t* __restrict__ mks, long long mks_cs,
-                                                               int tiles_x, int tiles_y, uint8_t* __restrict__ flags) {
+// field of encoder_hr.0 -> encoder_hr.2 -> conv_tttf around every mask pixel).  Two tiny passes: per-tile any() with
+// 8-byte loads (one block per tile row), then a 3x3 dilation over the tile grid.
+__global__ void __launch_bounds__(256) fovea_tile_any_kernel(int H, int W, const uint8_t* __restrict__ mks, long long mks_cs,
+                                                             int tiles_x, int tiles_y, uint8_t* __restrict__ any) {
+  extern __shared__ int s_any[];
   pdl_trigger();
   pdl_wait();
-  const int tx = blockIdx.x, ty = blockIdx.y, b = blockIdx.z;
-  const int x_lo = max(0, tx * 32 - 32), x_hi = min(W, tx * 32 + 64);
-  const int y_lo = max(0, ty * 32 - 32), y_hi = min(H, ty * 32 + 64);
-  const int wdt = x_hi - x_lo, cnt = wdt * (y_hi - y_lo);
-  const uint8_t* mb = mks + (size_t)b * mks_cs;
-  int any = 0;
-  for (int i = threadIdx.x; i < cnt; i += 256) {
-    const int yy = y_lo + i / wdt, xx = x_lo + i % wdt;
-    any |= mb[(size_t)yy * W + xx];
+  const int ty = blockIdx.x, b = blockIdx.y;
+  for (int i = threadIdx.x; i < tiles_x; i += 256) s_any[i] = 0;
+  __syncthreads();
+  const int y_lo = ty * 32, rows = min(32, H - y_lo);
+  const uint8_t* mb = mks + (size_t)b * mks_cs + (size_t)y_lo * W;
+  if ((W & 7) == 0 && (((uintptr_t)mb) & 7) == 0) {
+    const int ppr = W >> 3;                    // 8-byte pieces per row
+    for (int i = threadIdx.x; i < rows * ppr; i += 256) {
+      const int r = i / ppr, p = i - r * ppr;
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(mb + (size_t)r * W) + p);
+      if (v.x | v.y) s_any[p >> 2] = 1;
+    }
+  } else {
+    for (int i = threadIdx.x; i < rows * W; i += 256) {
+      const int r = i / W, x = i - r * W;
+      if (mb[(size_t)r * W + x]) s_any[x >> 5] = 1;
+    }
   }
-  any = __syncthreads_or(any);
-  if (threadIdx.x == 0) flags[((size_t)b * tiles_y + ty) * tiles_x + tx] = any ? 1 : 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < tiles_x; i += 256) any[((size_t)b * tiles_y + ty) * tiles_x + i] = s_any[i] ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) fovea_tile_dilate_kernel(int tiles_x, int tiles_y, int n, const uint8_t* __restrict__ any,
+                                                                uint8_t* __restrict__ flags) {
+  pdl_trigger();
+  pdl_wait();
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= tiles_x * tiles_y * n) return;
+  const int tx = i % tiles_x, ty = (i / tiles_x) % tiles_y, b = i / (tiles_x * tiles_y);
+  int f = 0;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int yy = ty + dy, xx = tx + dx;
+      if (yy >= 0 && yy < tiles_y && xx >= 0 && xx < tiles_x) f |= any[((size_t)b * tiles_y + yy) * tiles_x + xx];
+    }
+  flags[i] = f ? 1 : 0;
 }
 
 static int launch_compose(int n, int H, int W, const crfp_dsv_frame_desc* d, float* out, const uint8_t* flags, int tiles_x,
@@ -423,7 +449,7 @@ static size_t carve_frame(const crfp_dsv_shape* s, void* ws, FrameWs* f) {
   f->g0 = c.take(hr * 4); f->g1 = c.take(hr * 4); f->S_pre = c.take(hr * 4);
   f->hr_in = c.take(hr * 8); f->e1 = c.take(hr * 4); f->x_hr = c.take(hr * 4);
   f->flow_hr = c.take(hr * 2);
-  f->tile_flags = c.take(n * (size_t)((s->h * 8 + 31) / 32) * ((s->w * 8 + 31) / 32) / 4 + 64);
+  f->tile_flags = c.take(2 * (n * (size_t)((s->h * 8 + 31) / 32) * ((s->w * 8 + 31) / 32) / 4 + 64));   // flags + raw any()
   f->x_lr_d = c.take(n * hw * 32);
   f->flow_d = c.take(n * hw * 2);
   return c.off;
@@ -878,7 +904,10 @@ extern "C" int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weigh
   const uint8_t* flags = nullptr;
   if (d->skip_outside_fovea) {
     uint8_t* fl = reinterpret_cast<uint8_t*>(f.tile_flags);
-    launch_k(fovea_tile_flags_kernel, dim3(dim3(tiles_x, tiles_y, n)), dim3(256), (size_t)(0), st, H, Wd, d->mks, d->mks_clip_stride, tiles_x, tiles_y, fl);
+    uint8_t* any = fl + (((size_t)n * tiles_x * tiles_y + 255) & ~(size_t)255);
+    launch_k(fovea_tile_any_kernel, dim3(tiles_y, n), dim3(256), (size_t)tiles_x * sizeof(int), st, H, Wd, d->mks, d->mks_clip_stride, tiles_x, tiles_y, any);
+    CRFP_TRY(check_launch());
+    launch_k(fovea_tile_dilate_kernel, dim3((n * tiles_x * tiles_y + 255) / 256), dim3(256), (size_t)0, st, tiles_x, tiles_y, n, (const uint8_t*)any, fl);
     CRFP_TRY(check_launch());
     flags = fl;
   }
