@@ -6,6 +6,8 @@
 //   EPI_STD      bias + LeakyReLU/ReLU/tanh*256/DCN-head + residual + post_scale
 //   EPI_BLEND    conv_tttf + fovea blend + LeakyReLU:  S = lrelu(m*F + (1-m)*S)      (model/CRFP.py:1672-1675)
 //   EPI_OUT_NCHW conv_last + bilinear x8 base of the LR frame, planar NCHW store     (model/CRFP.py:1678-1683)
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace crfp {
@@ -128,9 +130,10 @@ __global__ void __launch_bounds__(256) conv_thin_kernel(const ConvParams P) {
 // in shared memory (coalesced float4 loads, zero padding / regional mask applied by the loader); per (quad, kx) a
 // thread reads its 6-row column (conflict-free LDS.128, reused by the 3 ky taps) and 12 broadcast weight float4s.
 // 16 accumulators, ~54 LDS.128 per 576 FFMA: FFMA bound (the 4-channel convs are ~2x over their HBM time in fp32).
-template <int NQ>
-__global__ void __launch_bounds__(256, 3) conv_thin4_kernel(const ConvParams P) {
-  constexpr int TS = 32, HS = TS + 2, PITCH = HS + 1;
+// ROWS = rows per thread (4: 256 threads / CTA, 8: 128 threads / CTA with twice the FFMA per shared-memory load).
+template <int NQ, int ROWS>
+__global__ void __launch_bounds__(1024 / ROWS, ROWS == 4 ? 3 : 4) conv_thin4_kernel(const ConvParams P) {
+  constexpr int TS = 32, HS = TS + 2, PITCH = HS + 1, NT = 1024 / ROWS;
   extern __shared__ __align__(16) float smem_t4[];
   float4* s_in = reinterpret_cast<float4*>(smem_t4);            // [NQ][34][35]
   float4* s_w = s_in + NQ * HS * PITCH;                         // [9][cin_packed]
@@ -143,8 +146,8 @@ __global__ void __launch_bounds__(256, 3) conv_thin4_kernel(const ConvParams P) 
     // tile outside the (dilated) fovea: the conv result would be multiplied by a zero mask
     if (P.tile_mode == 2) {
       const int x = x0 + threadIdx.x;
-      for (int r = 0; r < 4; ++r) {
-        const int y = y0 + 4 * threadIdx.y + r;
+      for (int r = 0; r < ROWS; ++r) {
+        const int y = y0 + ROWS * threadIdx.y + r;
         if (x < P.w && y < P.h) {
           const size_t pix = ((size_t)n * P.h + y) * (size_t)P.w + x;
           const float4 so = __ldg(reinterpret_cast<const float4*>(P.blend_old + pix * 4));
@@ -154,12 +157,12 @@ __global__ void __launch_bounds__(256, 3) conv_thin4_kernel(const ConvParams P) 
     }
     return;
   }
-  for (int i = tid; i < 9 * P.cin_packed; i += 256) s_w[i] = __ldg(reinterpret_cast<const float4*>(P.weight) + i);
+  for (int i = tid; i < 9 * P.cin_packed; i += NT) s_w[i] = __ldg(reinterpret_cast<const float4*>(P.weight) + i);
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     const int kind = (P.fg != nullptr) ? 2 : P.qkind[q];
     const float* base = P.qptr[q] + (size_t)n * P.h * P.w * P.qcs[q];
-    for (int r = tid; r < HS * HS; r += 256) {
+    for (int r = tid; r < HS * HS; r += NT) {
       const int py = r / HS, px = r - py * HS;
       const int y = y0 + py - 1, x = x0 + px - 1;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -179,24 +182,24 @@ __global__ void __launch_bounds__(256, 3) conv_thin4_kernel(const ConvParams P) 
   }
   __syncthreads();
   const int tx = threadIdx.x, ty = threadIdx.y;
-  float acc[4][4];
+  float acc[ROWS][4];
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int r = 0; r < ROWS; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
-      float4 col[6];
+      float4 col[ROWS + 2];
 #pragma unroll
-      for (int r = 0; r < 6; ++r) col[r] = s_in[(q * HS + 4 * ty + r) * PITCH + tx + kx];
+      for (int r = 0; r < ROWS + 2; ++r) col[r] = s_in[(q * HS + ROWS * ty + r) * PITCH + tx + kx];
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const float4* wt = s_w + (ky * 3 + kx) * P.cin_packed + q * 4;
         const float4 w0 = wt[0], w1 = wt[1], w2 = wt[2], w3 = wt[3];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < ROWS; ++r) {
           const float4 v = col[r + ky];
           acc[r][0] = fmaf(v.x, w0.x, fmaf(v.y, w1.x, fmaf(v.z, w2.x, fmaf(v.w, w3.x, acc[r][0]))));
           acc[r][1] = fmaf(v.x, w0.y, fmaf(v.y, w1.y, fmaf(v.z, w2.y, fmaf(v.w, w3.y, acc[r][1]))));
@@ -210,8 +213,8 @@ __global__ void __launch_bounds__(256, 3) conv_thin4_kernel(const ConvParams P) 
   if (x >= P.w) return;
   const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias));
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int y = y0 + 4 * ty + r;
+  for (int r = 0; r < ROWS; ++r) {
+    const int y = y0 + ROWS * ty + r;
     if (y >= P.h) break;
     thin_epilogue(P, n, y, x, acc[r][0] + b.x, acc[r][1] + b.y, acc[r][2] + b.z, acc[r][3] + b.w);
   }
@@ -243,15 +246,18 @@ int launch_conv_thin(const ConvParams& p_in, cudaStream_t st) {
   if (nq >= 1 && nq <= 3 && ((long long)p.h * p.w >= 32 * 32 || p.tile_flags != nullptr)) {
     dim3 grid(ceil_div(p.w, 32), ceil_div(p.h, 32), p.n);
     const size_t smem4 = ((size_t)nq * 34 * 35 + 9 * p.cin_packed) * 16;
-    if (nq == 1) {
-      launch_k(conv_thin4_kernel<1>, dim3(grid), dim3(block), (size_t)(smem4), st, p);
-    } else if (nq == 2) {
-      cudaFuncSetAttribute(conv_thin4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
-      launch_k(conv_thin4_kernel<2>, dim3(grid), dim3(block), (size_t)(smem4), st, p);
+    static const int rows = getenv("CRFP_THIN_ROWS") ? atoi(getenv("CRFP_THIN_ROWS")) : 4;   // 8 measured 7 % slower end to end
+#define CRFP_THIN4(NQ_, R_)                                                                                        \
+  do {                                                                                                             \
+    cudaFuncSetAttribute(conv_thin4_kernel<NQ_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);     \
+    launch_k(conv_thin4_kernel<NQ_, R_>, dim3(grid), dim3(32, 32 / R_), (size_t)(smem4), st, p);                   \
+  } while (0)
+    if (rows == 4) {
+      if (nq == 1) CRFP_THIN4(1, 4); else if (nq == 2) CRFP_THIN4(2, 4); else CRFP_THIN4(3, 4);
     } else {
-      cudaFuncSetAttribute(conv_thin4_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
-      launch_k(conv_thin4_kernel<3>, dim3(grid), dim3(block), (size_t)(smem4), st, p);
+      if (nq == 1) CRFP_THIN4(1, 8); else if (nq == 2) CRFP_THIN4(2, 8); else CRFP_THIN4(3, 8);
     }
+#undef CRFP_THIN4
     return check_launch();
   }
   dim3 grid(ceil_div(p.w, 32), ceil_div(p.h, 8), p.n);
