@@ -89,7 +89,8 @@ class _CRFPBase(nn.Module):
         # CUDA graphs: a clip forward is ~60 launches per frame; the second call on the same input buffers captures
         # the whole clip into one graph and later calls replay it (one launch per clip: immune to host jitter)
         self.use_graphs = os.environ.get("CRFP_NO_GRAPHS") is None
-        self._graphs = collections.OrderedDict()   # key -> dict(graph, out, launches)
+        self.graph_frames = 20                     # frames per captured graph
+        self._graphs = collections.OrderedDict()   # key -> dict(graphs, out, launches)
         self._seen_key = None
 
     # ---- init policy of the reference (statistically identical, not RNG-stream identical)
@@ -186,7 +187,7 @@ class _CRFPBase(nn.Module):
         mks = (mks != 0).to(torch.uint8).contiguous() if mks.dtype != torch.bool else mks.contiguous().view(torch.uint8)
         return lrs, fvs, mks
 
-    def _run_frames(self, buf, W, lrs, fvs, mks, fgs, out, first_flags, out_host=None):
+    def _run_frames(self, buf, W, lrs, fvs, mks, fgs, out, first_flags, out_host=None, frames=None):
         """Frame loop.  `out_host` (pinned CPU tensor shaped like `out`): every finished frame is copied to the host on a
         side stream while the next frames are computed (device->host traffic overlaps the recurrence)."""
         lib = L.lib()
@@ -207,7 +208,7 @@ class _CRFPBase(nn.Module):
         d.fvs_clip_stride, d.mks_clip_stride, d.out_clip_stride = t * 3 * HW, t * HW, t * 3 * HW
         d.state_hr, d.state_l1 = buf["state_hr"].data_ptr(), buf["state_l1"].data_ptr()
         ws = buf["ws"]
-        for i in range(t):
+        for i in (range(t) if frames is None else frames):
             d.first = int(first_flags[i])
             d.lr4 = buf["lr4"].data_ptr() + i * hw * 4 * 4
             d.x_lr = buf["x_lr"].data_ptr() + i * hw * self.mid_channels * 4
@@ -255,44 +256,52 @@ class CRFP_DSV(_CRFPBase):
             W = self._weights(dev)
             buf = self._clip_buffers(n, t, h, w, dev)
 
-            def run(out):
+            def run(out, part=None):
+                """part None: the whole clip; part k: frames [k*G, (k+1)*G) (+ the clip-level work when k == 0)."""
                 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-                if pre is not None:
-                    pre(st)
-                shp = L.DsvShape(n=n, t=t, h=h, w=w, mid_channels=self.mid_channels)
-                L.check(L.lib().crfp_dsv_prepare(C.byref(shp), C.byref(W), lrs.data_ptr(), None, buf["lr4"].data_ptr(),
-                                                 buf["x_lr"].data_ptr(), buf["flows"].data_ptr(), buf["ws"].data_ptr(),
-                                                 buf["ws"].numel(), st), "dsv_prepare")
-                self._run_frames(buf, W, lrs, fvs, mks, None, out, [i == 0 for i in range(t)], out_host)
+                if part is None or part == 0:
+                    if pre is not None:
+                        pre(st)
+                    shp = L.DsvShape(n=n, t=t, h=h, w=w, mid_channels=self.mid_channels)
+                    L.check(L.lib().crfp_dsv_prepare(C.byref(shp), C.byref(W), lrs.data_ptr(), None, buf["lr4"].data_ptr(),
+                                                     buf["x_lr"].data_ptr(), buf["flows"].data_ptr(), buf["ws"].data_ptr(),
+                                                     buf["ws"].numel(), st), "dsv_prepare")
+                frames = None if part is None else range(part * self.graph_frames, min(t, (part + 1) * self.graph_frames))
+                self._run_frames(buf, W, lrs, fvs, mks, None, out, [i == 0 for i in range(t)], out_host, frames)
 
             key = key + (n, t, h, w, str(dev), 0 if out_host is None else out_host.data_ptr(), bool(self.skip_outside_fovea))
             if self.use_graphs and not torch.cuda.is_current_stream_capturing():
                 entry = self._graphs.get(key)
                 if entry is None and self._seen_key == key:
-                    entry = self._capture(key, run, (n, t, 3, 8 * h, 8 * w), dev)
+                    entry = self._capture(key, run, (n, t, 3, 8 * h, 8 * w), dev, (t + self.graph_frames - 1) // self.graph_frames)
                 self._seen_key = key
                 if entry is not None:
                     self._graphs.move_to_end(key)
-                    entry["graph"].replay()
+                    for g in entry["graphs"]:
+                        g.replay()
                     L.lib().crfp_launch_count_add(entry["launches"])
                     return entry["out"]
             out = torch.empty(n, t, 3, 8 * h, 8 * w, device=dev, dtype=torch.float32)
             run(out)
         return out
 
-    def _capture(self, key, run, out_shape, dev):
-        """Capture one whole-clip forward (prepare + every frame, incl. the streaming device->host copies) into a CUDA
-        graph.  The entry owns its output tensor: replays on the same input buffers return that same tensor,
-        overwritten by the next replay (`use_graphs = False` or CRFP_NO_GRAPHS=1 restores one fresh tensor per call).
-        Returns None (and switches graphs off) if the capture fails for any reason."""
+    def _capture(self, key, run, out_shape, dev, parts):
+        """Capture one whole-clip forward (prepare + every frame, incl. the streaming device->host copies) into CUDA
+        graphs of `graph_frames` frames each: the next graph is launched while the previous one executes, so only
+        the first graph's launch latency is exposed.  The entry owns its output tensor: replays on the same input
+        buffers return that same tensor, overwritten by the next replay (`use_graphs = False` or CRFP_NO_GRAPHS=1
+        restores one fresh tensor per call).  Returns None (and switches graphs off) if the capture fails."""
         lib = L.lib()
         out = torch.empty(*out_shape, device=dev, dtype=torch.float32)
+        graphs = []
         try:
             torch.cuda.synchronize(dev)
             before = lib.crfp_launch_count()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                run(out)
+            for k in range(parts):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    run(out, k)
+                graphs.append(g)
             launches = lib.crfp_launch_count() - before
             lib.crfp_launch_count_add(-launches)        # captured, not launched
         except Exception as e:  # noqa: BLE001
@@ -302,7 +311,7 @@ class CRFP_DSV(_CRFPBase):
             return None
         while len(self._graphs) >= 3:
             self._graphs.popitem(last=False)
-        entry = dict(graph=g, out=out, launches=launches)
+        entry = dict(graphs=graphs, out=out, launches=launches)
         self._graphs[key] = entry
         return entry
 
@@ -335,7 +344,21 @@ class CRFP_DSV(_CRFPBase):
                                             coords=torch.zeros(n, t, 2, device=dev, dtype=torch.int32),
                                             prev=torch.zeros(n, t, 2, device=dev, dtype=torch.int32)))
             pb = self._patch_buf[1]
-            pb["coords"].copy_(cc.to(torch.int32))          # outside the graph: a host -> device copy of n*t*8 bytes
+            # outside the graph: host -> device copy of n*t*8 bytes through a small ring of pinned staging buffers, so
+            # the call never blocks on the stream (the host may run several steps ahead of the device)
+            if "stage" not in pb:
+                pb["stage"] = [torch.empty(n, t, 2, dtype=torch.int32).pin_memory() for _ in range(4)]
+                pb["stage_ev"] = [None] * 4
+                pb["stage_i"] = 0
+            k = pb["stage_i"]
+            pb["stage_i"] = (k + 1) % 4
+            if pb["stage_ev"][k] is not None:
+                pb["stage_ev"][k].synchronize()
+            pb["stage"][k].copy_(cc)
+            pb["coords"].copy_(pb["stage"][k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            pb["stage_ev"][k] = ev
             lib = L.lib()
 
             def pre(st):

@@ -172,10 +172,11 @@ def test_cuda_graph_replay_matches_eager(sd):
     eager = m(lrs, fvs, mks).clone()
     n_eager = _lib.lib().crfp_launch_count()
     m.use_graphs = True
+    m.graph_frames = 3                    # 4 frames -> two chained graphs
     o1 = m(lrs, fvs, mks)                 # first sighting: eager
     assert len(m._graphs) == 0
     o2 = m(lrs, fvs, mks)                 # second sighting: capture + replay
-    assert len(m._graphs) == 1 and m.use_graphs
+    assert len(m._graphs) == 1 and m.use_graphs and len(next(iter(m._graphs.values()))["graphs"]) == 2
     _lib.lib().crfp_launch_count_reset()
     o3 = m(lrs, fvs, mks)                 # replay
     assert _lib.lib().crfp_launch_count() == n_eager > 0
