@@ -395,14 +395,19 @@ def main():
     alg_bytes = ALIGN_BYTES_PER_L1_PX * (2 * h) * (2 * w)
     a_ach = alg_bytes / (a_ms * 1e-3) / 1e9
     align = {"kernel": ("dcn_tc3_kernel" if args.precision == "tc" else "dcn_l1_kernel") + " (DCNv2 align @L1, C=32 dg=8)",
-             "bound": "hbm", "achieved": a_ach, "peak": peak, "unit": "GB/s", "frac": a_ach / peak, "traffic": None,
+             "bound": "hbm", "achieved": a_ach, "peak": peak, "unit": "GB/s", "frac": a_ach / peak,
+             "traffic": (247.1e6 if (args.workload == "R-lit" and args.precision == "tc") else None),
+             "traffic_source": "dram__bytes_read+write per launch, ncu, profiles/r01/v3_dram_R-lit.csv (R-lit only)",
              "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": a_ms,
              "timing": "kernel timed alone through the C ABI, CUDA events, 3 rotating input sets > L2"}
     if args.precision == "tc":
         c_ms, c_n, c_bytes, c_flop = time_conv_mix(torch, 2 * h, 2 * w)
         c_ach = c_bytes / (c_ms * 1e-3) / 1e9
         roofline = {"kernel": "conv_tc3_ws_kernel (tcgen05 3x3 implicit-GEMM conv, the per-frame mix of its %d L1 launches)" % c_n,
-                    "bound": "hbm", "achieved": c_ach, "peak": peak, "unit": "GB/s", "frac": c_ach / peak, "traffic": None,
+                    "bound": "hbm", "achieved": c_ach, "peak": peak, "unit": "GB/s", "frac": c_ach / peak,
+                    "traffic": (64.3e6 if args.workload == "R-lit" else None),
+                    "traffic_source": "dram__bytes_read+write, mean over the 23 L1 conv launches of one steady-state frame, "
+                                      "ncu, profiles/r01/v3_dram_R-lit.csv (R-lit only; below the algorithmic bytes: L2 reuse)",
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": c_bytes, "avg_launch_ms": c_ms,
                     "tensor": {"useful_fp32_tflops": c_flop / (c_ms * 1e-3) / 1e12,
                                "issued_bf16_tflops": 3 * c_flop / (c_ms * 1e-3) / 1e12, "bf16_peak_tflops": bf16_peak,

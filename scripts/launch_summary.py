@@ -6,6 +6,7 @@ def main(path, tail=0):
     agg = collections.defaultdict(lambda: [0, 0.0]); order = []
     for row in csv.DictReader(lines):
         name = re.sub(r'\(.*', '', row['Kernel Name'])
+        if 'spin_kernel' in name: continue   # the bench's host-decoupling spin, not part of a step
         v = float(row['Metric Value'].replace(',', '')); u = row['Metric Unit']
         v = v / 1e3 if u == 'ns' else v * 1e3 if u == 'ms' else v * 1e6 if u == 's' else v
         agg[name][0] += 1; agg[name][1] += v; order.append((name, row['Grid Size'], v))
