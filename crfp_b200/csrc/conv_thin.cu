@@ -220,6 +220,135 @@ __global__ void __launch_bounds__(1024 / ROWS, ROWS == 4 ? 3 : 4) conv_thin4_ker
   }
 }
 
+__device__ __forceinline__ void umma_cp16(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void umma_cp8(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+// tile outside the (dilated) fovea: nothing to compute; tile_mode 2 (blend layer) still has to carry the old state
+// through the LeakyReLU of the blend (S <- lrelu(0*F + 1*S))
+__device__ __forceinline__ void thin4_skip_tile(const ConvParams& P, int tile, int per_img, int tiles_x) {
+  if (P.tile_mode != 2) return;
+  const int n = tile / per_img, tr = tile - n * per_img;
+  const int y0 = (tr / tiles_x) * 32, x = (tr % tiles_x) * 32 + threadIdx.x;
+  for (int r = 0; r < 4; ++r) {
+    const int y = y0 + 4 * threadIdx.y + r;
+    if (x < P.w && y < P.h) {
+      const size_t pix = ((size_t)n * P.h + y) * (size_t)P.w + x;
+      const float4 so = __ldg(reinterpret_cast<const float4*>(P.blend_old + pix * 4));
+      *reinterpret_cast<float4*>(P.dst[0] + pix * 4) = make_float4(lrelu01(so.x), lrelu01(so.y), lrelu01(so.z), lrelu01(so.w));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// v3: persistent + double buffered.  Same per-thread arithmetic as conv_thin4_kernel<NQ, 4>, but a CTA walks tiles
+// blockIdx.x, +gridDim.x, ... and the (34x34) halo tile of the NEXT tile is fetched with cp.async (zero fill outside
+// the image) into the other half of a 2-stage shared-memory ring while the current tile is being convolved, so the
+// load latency of a tile is hidden behind the FFMAs of the previous one instead of behind other CTAs.
+// Sources must be plain 4-channel (kind 0) or 2-channel (kind 1: 8-byte cp.async, upper half of the quad stays zero).
+template <int NQ>
+__global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) conv_thin4p_kernel(const ConvParams P) {
+  constexpr int TS = 32, HS = TS + 2, PITCH = HS + 1, STAGE = NQ * HS * PITCH;
+  extern __shared__ __align__(16) float smem_t4[];
+  float4* s_in = reinterpret_cast<float4*>(smem_t4);            // [2][NQ][34][35]
+  float4* s_w = s_in + 2 * STAGE;                               // [9][cin_packed]
+  const int tid = threadIdx.x + threadIdx.y * 32;
+  const int tiles_x = (P.w + TS - 1) / TS, tiles_y = (P.h + TS - 1) / TS;
+  const int per_img = tiles_x * tiles_y, total = per_img * P.n;
+  pdl_trigger();
+  for (int i = tid; i < 2 * STAGE; i += 256) s_in[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // pad column + kind-1 upper halves
+  for (int i = tid; i < 9 * P.cin_packed; i += 256) s_w[i] = __ldg(reinterpret_cast<const float4*>(P.weight) + i);
+  pdl_wait();
+  __syncthreads();
+
+  auto tile_live = [&](int tile) {   // tiles outside the (dilated) fovea are skipped
+    return P.tile_flags == nullptr || P.tile_flags[tile] != 0;   // flags are [n][tiles_y][tiles_x] = tile index order
+  };
+  auto prefetch = [&](int tile, int stage) {
+    const int n = tile / per_img, tr = tile - n * per_img;
+    const int y0 = (tr / tiles_x) * TS, x0 = (tr % tiles_x) * TS;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const float* base = P.qptr[q] + (size_t)n * P.h * P.w * P.qcs[q];
+      const int kind = P.qkind[q];
+      for (int r = tid; r < HS * HS; r += 256) {
+        const int py = r / HS, px = r - py * HS;
+        const int y = y0 + py - 1, x = x0 + px - 1;
+        const bool in = y >= 0 && y < P.h && x >= 0 && x < P.w;
+        const float* g = in ? base + ((size_t)y * P.w + x) * P.qcs[q] : base;
+        float4* dst = s_in + stage * STAGE + (q * HS + py) * PITCH + px;
+        if (kind == 0) umma_cp16(dst, g, in ? 16u : 0u);
+        else umma_cp8(dst, g, in ? 8u : 0u);
+      }
+    }
+  };
+
+  int tile = blockIdx.x;
+  while (tile < total && !tile_live(tile)) {   // leading skipped tiles
+    thin4_skip_tile(P, tile, per_img, tiles_x);
+    tile += gridDim.x;
+  }
+  if (tile < total) prefetch(tile, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  int stage = 0;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const float4 bias = __ldg(reinterpret_cast<const float4*>(P.bias));
+  while (tile < total) {
+    int next = tile + gridDim.x;
+    while (next < total && !tile_live(next)) {
+      thin4_skip_tile(P, next, per_img, tiles_x);
+      next += gridDim.x;
+    }
+    if (next < total) prefetch(next, stage ^ 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    const float4* sb = s_in + stage * STAGE;
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        float4 col[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) col[r] = sb[(q * HS + 4 * ty + r) * PITCH + tx + kx];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const float4* wt = s_w + (ky * 3 + kx) * P.cin_packed + q * 4;
+          const float4 w0 = wt[0], w1 = wt[1], w2 = wt[2], w3 = wt[3];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const float4 v = col[r + ky];
+            acc[r][0] = fmaf(v.x, w0.x, fmaf(v.y, w1.x, fmaf(v.z, w2.x, fmaf(v.w, w3.x, acc[r][0]))));
+            acc[r][1] = fmaf(v.x, w0.y, fmaf(v.y, w1.y, fmaf(v.z, w2.y, fmaf(v.w, w3.y, acc[r][1]))));
+            acc[r][2] = fmaf(v.x, w0.z, fmaf(v.y, w1.z, fmaf(v.z, w2.z, fmaf(v.w, w3.z, acc[r][2]))));
+            acc[r][3] = fmaf(v.x, w0.w, fmaf(v.y, w1.w, fmaf(v.z, w2.w, fmaf(v.w, w3.w, acc[r][3]))));
+          }
+        }
+      }
+    }
+    const int n = tile / per_img, tr = tile - n * per_img;
+    const int y0 = (tr / tiles_x) * TS, x = (tr % tiles_x) * TS + tx;
+    if (x < P.w) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int y = y0 + 4 * ty + r;
+        if (y < P.h) thin_epilogue(P, n, y, x, acc[r][0] + bias.x, acc[r][1] + bias.y, acc[r][2] + bias.z, acc[r][3] + bias.w);
+      }
+    }
+    __syncthreads();   // everybody is done with this stage before the next prefetch overwrites it
+    tile = next;
+    stage ^= 1;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 int launch_conv_thin(const ConvParams& p_in, cudaStream_t st) {
   ConvParams p = p_in;
   if (p.cout > 4 || p.cout_packed != 4) return CRFP_ERR_BAD_SHAPE;
@@ -247,6 +376,25 @@ int launch_conv_thin(const ConvParams& p_in, cudaStream_t st) {
     dim3 grid(ceil_div(p.w, 32), ceil_div(p.h, 32), p.n);
     const size_t smem4 = ((size_t)nq * 34 * 35 + 9 * p.cin_packed) * 16;
     static const int rows = getenv("CRFP_THIN_ROWS") ? atoi(getenv("CRFP_THIN_ROWS")) : 4;   // 8 measured 7 % slower end to end
+    static const bool persistent = getenv("CRFP_THIN_V2") == nullptr;   // A/B switch back to one CTA per tile
+    bool plain = p.fg == nullptr;
+    for (int q = 0; q < nq; ++q) plain = plain && (p.qkind[q] == 0 || p.qkind[q] == 1);
+    if (persistent && plain) {
+      const size_t smemp = ((size_t)2 * nq * 34 * 35 + 9 * p.cin_packed) * 16;
+      const int total = grid.x * grid.y * grid.z;
+      int sms = 148;
+      { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+      const int ctas = sms * (nq == 1 ? 3 : 2);
+      dim3 pgrid(total < ctas ? total : ctas);
+#define CRFP_THIN4P(NQ_)                                                                                       \
+  do {                                                                                                         \
+    cudaFuncSetAttribute(conv_thin4p_kernel<NQ_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp);    \
+    launch_k(conv_thin4p_kernel<NQ_>, dim3(pgrid), dim3(32, 8), (size_t)(smemp), st, p);                       \
+  } while (0)
+      if (nq == 1) CRFP_THIN4P(1); else if (nq == 2) CRFP_THIN4P(2); else CRFP_THIN4P(3);
+#undef CRFP_THIN4P
+      return check_launch();
+    }
 #define CRFP_THIN4(NQ_, R_)                                                                                        \
   do {                                                                                                             \
     cudaFuncSetAttribute(conv_thin4_kernel<NQ_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);     \
