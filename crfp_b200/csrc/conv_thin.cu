@@ -306,11 +306,11 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) conv_thin4p_kernel(const
     asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncthreads();
     const float4* sb = s_in + stage * STAGE;
-    float acc[4][4];
+    // packed fp32 FMAs (FFMA2, sm_100): a scalar 3-register FFMA issues every other cycle per scheduler, the 2-wide form
+    // retires two per issue; accumulators are (co 0,1) / (co 2,3) pairs, the input value is duplicated into a pair
+    float2 acc[4][2];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    for (int r = 0; r < 4; ++r) acc[r][0] = acc[r][1] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
 #pragma unroll
@@ -325,10 +325,11 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) conv_thin4p_kernel(const
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             const float4 v = col[r + ky];
-            acc[r][0] = fmaf(v.x, w0.x, fmaf(v.y, w1.x, fmaf(v.z, w2.x, fmaf(v.w, w3.x, acc[r][0]))));
-            acc[r][1] = fmaf(v.x, w0.y, fmaf(v.y, w1.y, fmaf(v.z, w2.y, fmaf(v.w, w3.y, acc[r][1]))));
-            acc[r][2] = fmaf(v.x, w0.z, fmaf(v.y, w1.z, fmaf(v.z, w2.z, fmaf(v.w, w3.z, acc[r][2]))));
-            acc[r][3] = fmaf(v.x, w0.w, fmaf(v.y, w1.w, fmaf(v.z, w2.w, fmaf(v.w, w3.w, acc[r][3]))));
+            const float2 vx = make_float2(v.x, v.x), vy = make_float2(v.y, v.y), vz = make_float2(v.z, v.z), vw = make_float2(v.w, v.w);
+            acc[r][0] = __ffma2_rn(vx, make_float2(w0.x, w0.y), __ffma2_rn(vy, make_float2(w1.x, w1.y),
+                        __ffma2_rn(vz, make_float2(w2.x, w2.y), __ffma2_rn(vw, make_float2(w3.x, w3.y), acc[r][0]))));
+            acc[r][1] = __ffma2_rn(vx, make_float2(w0.z, w0.w), __ffma2_rn(vy, make_float2(w1.z, w1.w),
+                        __ffma2_rn(vz, make_float2(w2.z, w2.w), __ffma2_rn(vw, make_float2(w3.z, w3.w), acc[r][1]))));
           }
         }
       }
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) conv_thin4p_kernel(const
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int y = y0 + 4 * ty + r;
-        if (y < P.h) thin_epilogue(P, n, y, x, acc[r][0] + bias.x, acc[r][1] + bias.y, acc[r][2] + bias.z, acc[r][3] + bias.w);
+        if (y < P.h) thin_epilogue(P, n, y, x, acc[r][0].x + bias.x, acc[r][0].y + bias.y, acc[r][1].x + bias.z, acc[r][1].y + bias.w);
       }
     }
     __syncthreads();   // everybody is done with this stage before the next prefetch overwrites it
