@@ -42,11 +42,12 @@ __global__ void __launch_bounds__(256, 2) conv_wide_kernel(const ConvParams P) {
   const int co_base = (blockIdx.z - n * co_tiles) * CO_T;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
 
-  float acc[RPT][8];
+  // accumulators as channel pairs: packed fp32 FMAs (FFMA2, sm_100) with the input value as the broadcast operand
+  float2 acc2[RPT][4];
 #pragma unroll
   for (int r = 0; r < RPT; ++r)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+    for (int c = 0; c < 4; ++c) acc2[r][c] = make_float2(0.f, 0.f);
 
   const int nchunks = P.cin_packed / CI_CH;
   for (int ch = 0; ch < nchunks; ++ch) {
@@ -84,15 +85,11 @@ __global__ void __launch_bounds__(256, 2) conv_wide_kernel(const ConvParams P) {
           const float4 w1 = *reinterpret_cast<const float4*>(&S.w[ky * 3 + kx][ci][cg * 8 + 4]);
 #pragma unroll
           for (int r = 0; r < RPT; ++r) {
-            const float a = col[r + ky];
-            acc[r][0] = fmaf(a, w0.x, acc[r][0]);
-            acc[r][1] = fmaf(a, w0.y, acc[r][1]);
-            acc[r][2] = fmaf(a, w0.z, acc[r][2]);
-            acc[r][3] = fmaf(a, w0.w, acc[r][3]);
-            acc[r][4] = fmaf(a, w1.x, acc[r][4]);
-            acc[r][5] = fmaf(a, w1.y, acc[r][5]);
-            acc[r][6] = fmaf(a, w1.z, acc[r][6]);
-            acc[r][7] = fmaf(a, w1.w, acc[r][7]);
+            const float2 a = make_float2(col[r + ky], col[r + ky]);
+            acc2[r][0] = __ffma2_rn(a, make_float2(w0.x, w0.y), acc2[r][0]);
+            acc2[r][1] = __ffma2_rn(a, make_float2(w0.z, w0.w), acc2[r][1]);
+            acc2[r][2] = __ffma2_rn(a, make_float2(w1.x, w1.y), acc2[r][2]);
+            acc2[r][3] = __ffma2_rn(a, make_float2(w1.z, w1.w), acc2[r][3]);
           }
         }
       }
@@ -119,7 +116,7 @@ __global__ void __launch_bounds__(256, 2) conv_wide_kernel(const ConvParams P) {
     const size_t pix = ((size_t)n * P.h + y) * (size_t)P.w + x;
     float v[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) v[c] = acc[r][c] + bias[c];
+    for (int c = 0; c < 8; ++c) v[c] = ((c & 1) ? acc2[r][c >> 1].y : acc2[r][c >> 1].x) + bias[c];
     if (P.act == CRFP_ACT_DCN_HEAD) {
       const float2 fl = __ldg(reinterpret_cast<const float2*>(P.flow + pix * 2));
 #pragma unroll
