@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) dcn_hr_kernel(const crfp_dcn_desc D) {
   const float* img = D.x + (size_t)n * D.h * D.w * D.x_cstride + D.x_coffset;
   float dys = 0.f, dxs = 0.f, ms = 0.f;
   if (D.shared_taps) { dys = __ldg(offp); dxs = __ldg(offp + 1); ms = __ldg(mp); }
-  float4 acc = s_b;
+  float2 a01 = make_float2(s_b.x, s_b.y), a23 = make_float2(s_b.z, s_b.w);   // packed fp32 FMAs (FFMA2)
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
     const int i = t / 3, j = t - i * 3;
@@ -179,12 +179,13 @@ __global__ void __launch_bounds__(256) dcn_hr_kernel(const crfp_dcn_desc D) {
     float4 v = dcn_sample4(img, D.x_cstride, D.w, c);
     v.x *= m; v.y *= m; v.z *= m; v.w *= m;
     const float4 w0 = s_w[t * 4 + 0], w1 = s_w[t * 4 + 1], w2 = s_w[t * 4 + 2], w3 = s_w[t * 4 + 3];
-    acc.x += v.x * w0.x + v.y * w1.x + v.z * w2.x + v.w * w3.x;
-    acc.y += v.x * w0.y + v.y * w1.y + v.z * w2.y + v.w * w3.y;
-    acc.z += v.x * w0.z + v.y * w1.z + v.z * w2.z + v.w * w3.z;
-    acc.w += v.x * w0.w + v.y * w1.w + v.z * w2.w + v.w * w3.w;
+    const float2 vx = make_float2(v.x, v.x), vy = make_float2(v.y, v.y), vz = make_float2(v.z, v.z), vw = make_float2(v.w, v.w);
+    a01 = __ffma2_rn(vx, make_float2(w0.x, w0.y), __ffma2_rn(vy, make_float2(w1.x, w1.y),
+          __ffma2_rn(vz, make_float2(w2.x, w2.y), __ffma2_rn(vw, make_float2(w3.x, w3.y), a01))));
+    a23 = __ffma2_rn(vx, make_float2(w0.z, w0.w), __ffma2_rn(vy, make_float2(w1.z, w1.w),
+          __ffma2_rn(vz, make_float2(w2.z, w2.w), __ffma2_rn(vw, make_float2(w3.z, w3.w), a23))));
   }
-  *reinterpret_cast<float4*>(D.out + pix * D.out_cstride + D.out_coffset) = acc;
+  *reinterpret_cast<float4*>(D.out + pix * D.out_cstride + D.out_coffset) = make_float4(a01.x, a01.y, a23.x, a23.y);
 }
 
 __global__ void __launch_bounds__(256) dcn_indices_kernel(const crfp_dcn_desc D, int32_t* __restrict__ y0o,

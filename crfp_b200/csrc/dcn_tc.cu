@@ -276,10 +276,15 @@ __device__ __forceinline__ void dcn_sample_win8(const DcnTc3Params& P, const flo
   if (wy >= 0 && wy + 1 < WWH && wx >= 0 && wx + 1 < WWW) {
     const float4* p = sWin + (wy * WWW + wx) * 2 + gl;
     const float4 c00 = p[0], c01 = p[2], c10 = p[WWW * 2], c11 = p[WWW * 2 + 2];
-    v[0] = (w00 * c00.x + w01 * c01.x + w10 * c10.x + w11 * c11.x) * m;
-    v[1] = (w00 * c00.y + w01 * c01.y + w10 * c10.y + w11 * c11.y) * m;
-    v[2] = (w00 * c00.z + w01 * c01.z + w10 * c10.z + w11 * c11.z) * m;
-    v[3] = (w00 * c00.w + w01 * c01.w + w10 * c10.w + w11 * c11.w) * m;
+    // packed fp32 FMAs (FFMA2): channel pairs (0,1) / (2,3), corner weight as the broadcast operand
+    const float2 k00 = make_float2(w00, w00), k01 = make_float2(w01, w01), k10 = make_float2(w10, w10), k11 = make_float2(w11, w11);
+    const float2 mm = make_float2(m, m), z = make_float2(0.f, 0.f);
+    float2 a = __ffma2_rn(k00, make_float2(c00.x, c00.y), z), b = __ffma2_rn(k00, make_float2(c00.z, c00.w), z);
+    a = __ffma2_rn(k01, make_float2(c01.x, c01.y), a); b = __ffma2_rn(k01, make_float2(c01.z, c01.w), b);
+    a = __ffma2_rn(k10, make_float2(c10.x, c10.y), a); b = __ffma2_rn(k10, make_float2(c10.z, c10.w), b);
+    a = __ffma2_rn(k11, make_float2(c11.x, c11.y), a); b = __ffma2_rn(k11, make_float2(c11.z, c11.w), b);
+    a = __ffma2_rn(a, mm, z); b = __ffma2_rn(b, mm, z);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
     return;
   }
   // outside the staged window: global gather
