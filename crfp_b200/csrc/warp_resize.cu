@@ -97,6 +97,40 @@ __global__ void __launch_bounds__(256) resize_bilinear_kernel(int n, int hin, in
   out[idx] = (hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11)) * mul;
 }
 
+// vectorised variants: one thread = VEC consecutive channels of one output pixel (float2 for the 2-channel flows,
+// float4 for feature maps); same arithmetic per channel as the scalar kernel
+template <typename VT>
+__global__ void __launch_bounds__(256) resize_bilinear_vec_kernel(int n, int hin, int win, int cv, const VT* __restrict__ in,
+                                                                  int hout, int wout, float rh, float rw, float mul,
+                                                                  VT* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const long long total = (long long)n * hout * wout * cv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ch = (int)(idx % cv);
+  const long long pix = idx / cv;
+  const int x = (int)(pix % wout);
+  const int y = (int)((pix / wout) % hout);
+  const int b = (int)(pix / ((long long)wout * hout));
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilin_src(y, rh, hin, y0, y1, ly);
+  bilin_src(x, rw, win, x0, x1, lx);
+  const VT* ib = in + (size_t)b * hin * win * cv + ch;
+  const VT v00 = __ldg(ib + ((size_t)y0 * win + x0) * cv), v01 = __ldg(ib + ((size_t)y0 * win + x1) * cv);
+  const VT v10 = __ldg(ib + ((size_t)y1 * win + x0) * cv), v11 = __ldg(ib + ((size_t)y1 * win + x1) * cv);
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  VT o;
+  o.x = (hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x)) * mul;
+  o.y = (hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y)) * mul;
+  if constexpr (sizeof(VT) == 16) {
+    o.z = (hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z)) * mul;
+    o.w = (hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w)) * mul;
+  }
+  out[idx] = o;
+}
+
 __global__ void __launch_bounds__(256) avgpool2_kernel(int n, int hin, int win, int c, const float* __restrict__ in,
                                                        float* __restrict__ out) {
   pdl_trigger();
@@ -288,6 +322,16 @@ extern "C" int crfp_resize_bilinear(int n, int hin, int win, int c, const float*
   if (!in || !out) return CRFP_ERR_NULL;
   if (n <= 0 || hin <= 0 || win <= 0 || c <= 0 || hout <= 0 || wout <= 0) return CRFP_ERR_BAD_SHAPE;
   const long long total = (long long)n * hout * wout * c;
+  if (c % 4 == 0 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
+    launch_k(resize_bilinear_vec_kernel<float4>, dim3(grid1d(total / 4)), dim3(256), (size_t)(0), (cudaStream_t)stream, n, hin, win, c / 4,
+             reinterpret_cast<const float4*>(in), hout, wout, rscale_h, rscale_w, mul, reinterpret_cast<float4*>(out));
+    return check_launch();
+  }
+  if (c % 2 == 0 && (((uintptr_t)in | (uintptr_t)out) & 7) == 0) {
+    launch_k(resize_bilinear_vec_kernel<float2>, dim3(grid1d(total / 2)), dim3(256), (size_t)(0), (cudaStream_t)stream, n, hin, win, c / 2,
+             reinterpret_cast<const float2*>(in), hout, wout, rscale_h, rscale_w, mul, reinterpret_cast<float2*>(out));
+    return check_launch();
+  }
   launch_k(resize_bilinear_kernel, dim3(grid1d(total)), dim3(256), (size_t)(0), (cudaStream_t)stream, n, hin, win, c, in, hout, wout, rscale_h,
                                                                          rscale_w, mul, out);
   return check_launch();
