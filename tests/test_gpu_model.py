@@ -236,3 +236,32 @@ def test_forward_patch_device_paste(sd):
     assert len(m._graphs) >= 1
     with pytest.raises(ValueError):
         m.forward_patch(lrs, patch, coords + 10_000)
+
+
+def test_reds_literal_full_size_properties(sd):
+    """BASELINE configs[1] at full size (LR 180x320 -> 1440x2560), t=4, through size-independent properties: finite,
+    tc and fp32 precisions agree within the fp32 bar, the fovea tile skip is bit-identical to the full computation,
+    graph replay is bit-identical to eager execution, and the recurrence is causal."""
+    from crfp_b200 import CRFP_DSV
+    lrs, fvs, mks, _ = make_clip(seed=11, n=1, t=4, h=180, w=320, fv_size=96)
+    lrs, fvs, mks = lrs.cuda(), fvs.cuda(), mks.cuda()
+    outs = {}
+    for prec in ("tc", "fp32"):
+        m = CRFP_DSV("cuda", mid_channels=32, precision=prec).eval()
+        m.load_state_dict(sd, strict=True)
+        m = m.cuda()
+        m.use_graphs = False
+        outs[prec] = m(lrs, fvs, mks).clone()
+        assert torch.isfinite(outs[prec]).all()
+        if prec == "tc":
+            m.skip_outside_fovea = False
+            assert torch.equal(m(lrs, fvs, mks), outs[prec])            # exact tile skip
+            m.skip_outside_fovea = True
+            assert torch.equal(m(lrs[:, :2], fvs[:, :2], mks[:, :2]), outs[prec][:, :2])   # causality
+            m.use_graphs = True
+            m(lrs, fvs, mks)
+            assert torch.equal(m(lrs, fvs, mks), outs[prec]) and len(m._graphs) == 1       # graph replay
+        del m
+    err = (outs["tc"] - outs["fp32"]).abs().max().item()
+    print(f"R-lit full size: tc vs fp32 max-abs {err:.3e}")
+    assert err <= TOL
