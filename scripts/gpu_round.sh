@@ -23,6 +23,6 @@ cap() {  # kernel regex, skip, count, keep-report
 }
 cap conv_tc3_ws_kernel 100 8
 cap dcn_tc3_ws_kernel 4 2 keep
-cap conv_thin4_kernel 30 6
+cap conv_thin4p_kernel 30 6
 cap dcn_hr_kernel 2 1
 ls -la gpurun_out | grep ${TAG}; du -sh gpurun_out
