@@ -383,8 +383,11 @@ int launch_conv_thin(const ConvParams& p_in, cudaStream_t st) {
     if (persistent && plain) {
       const size_t smemp = ((size_t)2 * nq * 34 * 35 + 9 * p.cin_packed) * 16;
       const int total = grid.x * grid.y * grid.z;
-      int sms = 148;
-      { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+      static const int sms = [] {   // one process per GPU: the SM count of the current device is queried once
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        return v;
+      }();
       const int ctas = sms * (nq == 1 ? 3 : 2);
       dim3 pgrid(total < ctas ? total : ctas);
 #define CRFP_THIN4P(NQ_)                                                                                       \
