@@ -170,6 +170,7 @@ struct Tc3Params {
   int head_split;
   float head_mag, post_scale;
   int rows_per_cta;
+  int ncat;         // ws kernel: hi | lo weights as one 64-wide B operand (2 MMAs per K step)
   long long* dbg;   // optional per-phase clock64 trace of CTA (0,0,0): [row][8] (debug / profiling only)
 };
 int tc3_cout_tile(int cout, int kc_real, int* nt, int* ntiles);

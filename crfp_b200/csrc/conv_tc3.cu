@@ -105,6 +105,30 @@ __device__ __forceinline__ void tc3_issue_row(uint64_t dAh, uint64_t dAl, uint64
   }
 }
 
+// N-concatenated form (cout tile of 32): the hi and lo halves of the weights sit side by side as ONE 64-wide B operand
+// ([tap][kc][hi 32 | lo 32]), so A_hi x [W_hi | W_lo] is a single N = 64 MMA (columns 0..31 and 32..63 of the
+// accumulator) and A_lo x W_hi an N = 32 MMA into columns 0..31: 2 instead of 3 MMAs per K step (the MMA cost here is
+// dominated by streaming the 4 KB A operand, 45 / 48 cycles for N = 32 / 64).  The epilogue adds the two halves.
+template <int KC>
+__device__ __forceinline__ void tc3_issue_row_cat(uint64_t dAh, uint64_t dAl, uint64_t dB, uint32_t s0, uint32_t s1, uint32_t s2,
+                                                  uint32_t idesc64, uint32_t idesc32, uint32_t taddr) {
+  const uint32_t ahl = (uint32_t)dAh, ahh = (uint32_t)(dAh >> 32), all_ = (uint32_t)dAl, alh = (uint32_t)(dAl >> 32);
+  const uint32_t bl = (uint32_t)dB, bh = (uint32_t)(dB >> 32);
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int ky = tap / 3, kx = tap % 3;
+    const uint32_t arow = (ky == 0 ? s0 : ky == 1 ? s1 : s2) + kx;
+#pragma unroll
+    for (int ks = 0; ks < KC / 2; ++ks) {
+      const uint32_t a = arow + 2 * ks * T3WP, b = (uint32_t)(tap * KC + 2 * ks) * 64;
+      const uint64_t dah = umma::desc_advance(ahl, ahh, a), dal = umma::desc_advance(all_, alh, a);
+      const uint64_t db = umma::desc_advance(bl, bh, b);
+      umma::mma_bf16(taddr, dah, db, idesc64, (tap | ks) != 0 ? 1u : 0u);
+      umma::mma_bf16(taddr, dal, db, idesc32, 1u);
+    }
+  }
+}
+
 __device__ __noinline__ void tc3_issue_row_generic(uint64_t dAh, uint64_t dAl, uint64_t dBh, uint64_t dBl, uint32_t s0,
                                                    uint32_t s1, uint32_t s2, uint32_t NT, int KC, uint32_t idesc, uint32_t taddr, uint32_t leader) {
   const uint32_t ahl = (uint32_t)dAh, ahh = (uint32_t)(dAh >> 32), all_ = (uint32_t)dAl, alh = (uint32_t)(dAl >> 32);
@@ -508,9 +532,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
   {
     const uint4* gwh = reinterpret_cast<const uint4*>(P.weight_hi) + (size_t)cotile * wrecs;
     const uint4* gwl = reinterpret_cast<const uint4*>(P.weight_lo) + (size_t)cotile * wrecs;
-    for (int i = tid; i < wrecs; i += WS_THREADS) {
-      umma::cp_async16(sWh + i, gwh + i, 16u);
-      umma::cp_async16(sWl + i, gwl + i, 16u);
+    if (P.ncat) {   // [tap][kc][hi NT | lo NT] (NT = 32)
+      for (int i = tid; i < wrecs; i += WS_THREADS) {
+        const int blk = i / NT, r = i - blk * NT;
+        umma::cp_async16(sWh + blk * 2 * NT + r, gwh + i, 16u);
+        umma::cp_async16(sWh + blk * 2 * NT + NT + r, gwl + i, 16u);
+      }
+    } else {
+      for (int i = tid; i < wrecs; i += WS_THREADS) {
+        umma::cp_async16(sWh + i, gwh + i, 16u);
+        umma::cp_async16(sWl + i, gwl + i, 16u);
+      }
     }
     umma::cp_async_commit();
     for (int i = tid; i < ((NT + 31) & ~31); i += WS_THREADS) sBias[i] = (i < NT) ? P.bias[cotile * NT + i] : 0.f;
@@ -524,7 +556,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
     umma::cp_async_wait<0>();
   }
   uint32_t ncols = 32;
-  while ((int)ncols < NT) ncols <<= 1;
+  while ((int)ncols < NT * (P.ncat ? 2 : 1)) ncols <<= 1;
   if (warp == 4) umma::tmem_alloc(&tmem_base_s, 2 * ncols);
   if (tid == 0) {
     for (int i = 0; i < WS_SLOTS; ++i) umma::mbar_init(&full_bar[i], WS_NPROD);
@@ -569,7 +601,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
         const uint32_t s0 = (uint32_t)((v & 3) * slot_recs), s1 = (uint32_t)(((v + 1) & 3) * slot_recs),
                        s2 = (uint32_t)(((v + 2) & 3) * slot_recs);
         const uint32_t acc = taddr + (uint32_t)b * ncols;
-        if (KC == 4)
+        if (P.ncat)
+          tc3_issue_row_cat<8>(dAh, dAl, umma::make_desc(umma::smem_u32(sWh), 64 * 16, 128), s0, s1, s2,
+                               umma::make_idesc_bf16(T3M, 64), idesc, acc);
+        else if (KC == 4)
           tc3_issue_row<4>(dAh, dAl, dBh, dBl, s0, s1, s2, (uint32_t)NT, idesc, acc, 1u);
         else if (KC == 8)
           tc3_issue_row<8>(dAh, dAl, dBh, dBl, s0, s1, s2, (uint32_t)NT, idesc, acc, 1u);
@@ -644,6 +679,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
       for (int c0 = 0; c0 < NT; c0 += 32) {
         float vv[32];
         umma::tmem_ld32(taddr + ((uint32_t)(32 * warp) << 16) + (uint32_t)b * ncols + (uint32_t)c0, vv);
+        if (P.ncat) {   // columns 32..63 hold A_hi x W_lo
+          float v2[32];
+          umma::tmem_ld32(taddr + ((uint32_t)(32 * warp) << 16) + (uint32_t)b * ncols + 32u, v2);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) vv[i] += v2[i];
+        }
         if (tr && v < 60 && c0 == 0) tr[v * 4 + 3] = clock64();
         if (c0 + 32 >= NT) {  // last chunk is in registers: the accumulator can be overwritten
           umma::fence_before_sync();
@@ -716,6 +757,8 @@ int launch_conv_tc3(Tc3Params p, cudaStream_t st) {
     const size_t smem = (size_t)(2 * 9 * p.kc_total * p.nt + 2 * WS_SLOTS * p.kc_total * T3WP) * 16 +
                         (size_t)((p.nt + 31) & ~31) * 4 + (p.extra ? (size_t)(18 * p.nt + 32) * 4 : 0);
     if (smem > 227 * 1024) return CRFP_ERR_UNSUPPORTED;
+    static const bool no_cat = (getenv("CRFP_TC3_NOCAT") != nullptr);
+    p.ncat = (!no_cat && p.kc_total == 8 && p.nt == 32 && p.out_kind == TC_OUT_F32) ? 1 : 0;
     int segs = 148 / per_seg;
     if (segs < 1) segs = 1;
     if (segs > ceil_div(p.h, 4)) segs = ceil_div(p.h, 4);
