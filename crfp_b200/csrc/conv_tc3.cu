@@ -601,8 +601,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
         const uint32_t s0 = (uint32_t)((v & 3) * slot_recs), s1 = (uint32_t)(((v + 1) & 3) * slot_recs),
                        s2 = (uint32_t)(((v + 2) & 3) * slot_recs);
         const uint32_t acc = taddr + (uint32_t)b * ncols;
-        if (P.ncat)
+        if (P.ncat && KC == 8)
           tc3_issue_row_cat<8>(dAh, dAl, umma::make_desc(umma::smem_u32(sWh), 64 * 16, 128), s0, s1, s2,
+                               umma::make_idesc_bf16(T3M, 64), idesc, acc);
+        else if (P.ncat)
+          tc3_issue_row_cat<4>(dAh, dAl, umma::make_desc(umma::smem_u32(sWh), 64 * 16, 128), s0, s1, s2,
                                umma::make_idesc_bf16(T3M, 64), idesc, acc);
         else if (KC == 4)
           tc3_issue_row<4>(dAh, dAl, dBh, dBl, s0, s1, s2, (uint32_t)NT, idesc, acc, 1u);
@@ -758,7 +761,8 @@ int launch_conv_tc3(Tc3Params p, cudaStream_t st) {
                         (size_t)((p.nt + 31) & ~31) * 4 + (p.extra ? (size_t)(18 * p.nt + 32) * 4 : 0);
     if (smem > 227 * 1024) return CRFP_ERR_UNSUPPORTED;
     static const bool no_cat = (getenv("CRFP_TC3_NOCAT") != nullptr);
-    p.ncat = (!no_cat && p.kc_total == 8 && p.nt == 32 && p.out_kind == TC_OUT_F32) ? 1 : 0;
+    static const bool cat4 = (getenv("CRFP_TC3_NOCAT4") == nullptr);   // also for the 32-channel layers (+0.5 %)
+    p.ncat = (!no_cat && (p.kc_total == 8 || (cat4 && p.kc_total == 4)) && p.nt == 32 && p.out_kind == TC_OUT_F32) ? 1 : 0;
     int segs = 148 / per_seg;
     if (segs < 1) segs = 1;
     if (segs > ceil_div(p.h, 4)) segs = ceil_div(p.h, 4);
