@@ -266,6 +266,14 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) conv_thin4p_kernel(const
   auto tile_live = [&](int tile) {   // tiles outside the (dilated) fovea are skipped
     return P.tile_flags == nullptr || P.tile_flags[tile] != 0;   // flags are [n][tiles_y][tiles_x] = tile index order
   };
+  // halo slots of this thread (the same five (py, px) positions for every tile): hoisted out of the tile loop
+  constexpr int NSLOT = (HS * HS + 255) / 256;
+  int slot_yx[NSLOT];
+#pragma unroll
+  for (int k = 0; k < NSLOT; ++k) {
+    const int r = tid + k * 256;
+    slot_yx[k] = (r < HS * HS) ? (((r / HS) << 8) | (r % HS)) : -1;
+  }
   auto prefetch = [&](int tile, int stage) {
     const int n = tile / per_img, tr = tile - n * per_img;
     const int y0 = (tr / tiles_x) * TS, x0 = (tr % tiles_x) * TS;
@@ -273,8 +281,10 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) conv_thin4p_kernel(const
     for (int q = 0; q < NQ; ++q) {
       const float* base = P.qptr[q] + (size_t)n * P.h * P.w * P.qcs[q];
       const int kind = P.qkind[q];
-      for (int r = tid; r < HS * HS; r += 256) {
-        const int py = r / HS, px = r - py * HS;
+#pragma unroll
+      for (int k = 0; k < NSLOT; ++k) {
+        if (slot_yx[k] < 0) continue;
+        const int py = slot_yx[k] >> 8, px = slot_yx[k] & 255;
         const int y = y0 + py - 1, x = x0 + px - 1;
         const bool in = y >= 0 && y < P.h && x >= 0 && x < P.w;
         const float* g = in ? base + ((size_t)y * P.w + x) * P.qcs[q] : base;
