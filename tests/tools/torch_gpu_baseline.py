@@ -2,7 +2,7 @@
 deform_conv2d) moved to CUDA, TF32 off and on.  Informational ("the real reference GPU kernel to beat")."""
 import os, sys, time
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from crfp_b200.synthetic import make_clip, make_state_dict
 from oracle import crfp_oracle as O
 h, w, t = 180, 320, int(os.environ.get("FRAMES", "6"))
