@@ -263,5 +263,9 @@ def test_reds_literal_full_size_properties(sd):
             assert torch.equal(m(lrs, fvs, mks), outs[prec]) and len(m._graphs) == 1       # graph replay
         del m
     err = (outs["tc"] - outs["fp32"]).abs().max().item()
-    print(f"R-lit full size: tc vs fp32 max-abs {err:.3e}")
-    assert err <= TOL
+    # the 0.05 dB criterion of BASELINE.json, PSNR as the reference computes it, against a fixed pseudo ground truth
+    from crfp_b200.metrics import psnr
+    gt = torch.rand(outs["tc"].shape[1:], generator=torch.Generator().manual_seed(3)).cuda()
+    dpsnr = abs(float(psnr(outs["tc"][0].clamp(0, 1), gt)) - float(psnr(outs["fp32"][0].clamp(0, 1), gt)))
+    print(f"R-lit full size: tc vs fp32 max-abs {err:.3e}, delta PSNR {dpsnr:.2e} dB")
+    assert err <= TOL and dpsnr <= 0.05

@@ -174,3 +174,20 @@ def test_layer_table_matches_state_dict(built_lib):
     assert built_lib.crfp_dsv_prepare_workspace(ctypes.byref(shp)) > 0
     bad = _lib.DsvShape(n=1, t=5, h=4, w=160, mid_channels=32)
     assert built_lib.crfp_dsv_frame_workspace(ctypes.byref(bad)) == 0
+
+
+def test_psnr_matches_reference_formula():
+    """crfp_b200.metrics.psnr == the reference's psnr_cuda (utils.py:165-184) on masked / unmasked / identical inputs."""
+    import math
+    import torch
+    from crfp_b200.metrics import psnr
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.rand(2, 3, 8, 10, generator=g), torch.rand(2, 3, 8, 10, generator=g)
+    mse = ((a - b) ** 2).mean().item()
+    assert abs(float(psnr(a, b)) - (-20 * math.log10(math.sqrt(mse)))) < 1e-5
+    m = (torch.rand(2, 1, 8, 10, generator=g) > 0.5).float()
+    mse_m = (((a - b) ** 2) * m).sum().item() / (m.sum().item() * 3)
+    assert abs(float(psnr(a, b, m)) - (-20 * math.log10(math.sqrt(mse_m)))) < 1e-5
+    per = psnr(a, b, batch_avg=True)
+    assert per.shape == (2,) and abs(float(per[0]) - (-20 * math.log10(math.sqrt(((a[0] - b[0]) ** 2).mean().item())))) < 1e-5
+    assert math.isfinite(float(psnr(a, a))) and float(psnr(a, a)) > 60
