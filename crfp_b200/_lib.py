@@ -90,6 +90,14 @@ class DcnDesc(C.Structure):
                 ("out", C.c_void_p), ("out_cstride", C.c_int32), ("out_coffset", C.c_int32)]
 
 
+class DcnBwdDesc(C.Structure):
+    _fields_ = [("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("c", C.c_int32), ("cout", C.c_int32), ("dg", C.c_int32),
+                ("x", C.c_void_p), ("offset", C.c_void_p), ("mask", C.c_void_p), ("weight", C.c_void_p),
+                ("dout", C.c_void_p), ("dx", C.c_void_p), ("doffset", C.c_void_p), ("dmask", C.c_void_p),
+                ("dweight", C.c_void_p), ("dbias", C.c_void_p), ("col", C.c_void_p)]
+
+
 class Layer(C.Structure):
     _fields_ = [("w", C.c_void_p), ("b", C.c_void_p)]
 
@@ -176,7 +184,22 @@ SYMBOLS = {
     "crfp_dsv_frame": (C.c_int, [C.POINTER(DsvFrameDesc), C.POINTER(DsvWeights), C.c_void_p, C.c_size_t, C.c_void_p]),
     "crfp_sizeof_dsv_weights": (C.c_size_t, []),
     "crfp_sizeof_dsv_frame_desc": (C.c_size_t, []),
+    # training: backward kernels, loss, optimiser (bwd.cu)
+    "crfp_act_bwd": (C.c_int, [C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crfp_conv3x3_bwd_data": (C.c_int, [C.c_int] * 5 + [C.c_void_p] * 4),
+    "crfp_conv3x3_bwd_weight": (C.c_int, [C.c_int] * 5 + [C.c_void_p] * 5),
+    "crfp_dcn_v2_bwd": (C.c_int, [C.POINTER(DcnBwdDesc), C.c_void_p]),
+    "crfp_sizeof_dcn_bwd_desc": (C.c_size_t, []),
+    "crfp_flow_warp_bwd": (C.c_int, [C.c_int] * 4 + [C.c_void_p] * 6),
+    "crfp_resize_bilinear_bwd": (C.c_int, [C.c_int] * 6 + [C.c_float] * 3 + [C.c_void_p] * 3),
+    "crfp_avgpool2_bwd": (C.c_int, [C.c_int] * 4 + [C.c_void_p] * 3),
+    "crfp_charbonnier_fwd_bwd": (C.c_int, [C.c_longlong, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                           C.c_void_p]),
+    "crfp_adam_step": (C.c_int, [C.c_longlong] + [C.c_void_p] * 4 + [C.c_float] * 5 + [C.c_void_p]),
 }
+
+# the training entry points alone: also exported by the host-emulation build the CPU tests use (tests/tools/hostemu)
+TRAIN_SYMBOLS = [k for k in SYMBOLS if "_bwd" in k or k == "crfp_adam_step"]
 
 _lib = None
 
@@ -198,7 +221,7 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         for struct, fn in ((ConvDesc, h.crfp_sizeof_conv_desc), (ConvTcDesc, h.crfp_sizeof_conv_tc_desc), (ConvTc3Desc, h.crfp_sizeof_conv_tc3_desc), (WarpDesc, h.crfp_sizeof_warp_desc),
-                           (DcnDesc, h.crfp_sizeof_dcn_desc), (DsvWeights, h.crfp_sizeof_dsv_weights),
+                           (DcnDesc, h.crfp_sizeof_dcn_desc), (DcnBwdDesc, h.crfp_sizeof_dcn_bwd_desc), (DsvWeights, h.crfp_sizeof_dsv_weights),
                            (DsvFrameDesc, h.crfp_sizeof_dsv_frame_desc)):
             if C.sizeof(struct) != fn():
                 raise CrfpError(f"ABI mismatch: sizeof({struct.__name__}) python {C.sizeof(struct)} != C {fn()}")

@@ -1,0 +1,304 @@
+"""torch.autograd bindings of the training kernels: every Function's forward AND backward run in libcrfp_b200.so.
+
+The reference trains through ATen/cuDNN autograd and `dcn_v2`'s own backward (`loss.backward()`,
+/root/reference/trainer.py:246-250).  Here torch.autograd is only the tape (it records which op consumed which
+tensor across the t-frame recurrence, i.e. BPTT); the arithmetic of each node is a hand-written kernel behind the C ABI:
+
+  Conv3x3Fn     crfp_conv3x3_fwd  | crfp_act_bwd, crfp_conv3x3_bwd_data, crfp_conv3x3_bwd_weight   (nn.Conv2d + act)
+  DCNv2Fn       crfp_dcn_v2_fwd   | crfp_dcn_v2_bwd                        (dcn_v2.DCNv2, model/CRFP.py:350)
+  FlowWarpFn    crfp_flow_warp_fwd| crfp_flow_warp_bwd                     (flow_warp, model/CRFP.py:90-130)
+  ResizeFn      crfp_resize_bilinear | crfp_resize_bilinear_bwd            (nn.Upsample / F.interpolate, bilinear)
+  AvgPool2Fn    crfp_avgpool2     | crfp_avgpool2_bwd                      (nn.AvgPool2d(2,2))
+  CharbonnierFn crfp_charbonnier_fwd_bwd                                   (loss/loss.py:116-124)
+
+All tensors are dense fp32 NHWC.  `KernelSet` is the only place that touches the library: the product instance
+(`CUDA`) requires CUDA tensors and raises otherwise — there is no CPU implementation in this package.  (The CPU test
+suite injects its own kernel set built from a host emulation of bwd.cu, see tests/tools/hostemu.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+ACT_NONE, ACT_LRELU, ACT_RELU = L.ACT_NONE, L.ACT_LRELU, L.ACT_RELU
+
+
+class KernelSet:
+    """Forward primitives + the C-ABI handle whose crfp_*_bwd entry points the Functions below call."""
+
+    name = "cuda"
+
+    def lib(self):
+        return L.lib()
+
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def req(self, t: torch.Tensor, what: str) -> torch.Tensor:
+        if not (isinstance(t, torch.Tensor) and t.is_cuda):
+            raise L.CrfpError(f"{what} must be a CUDA tensor (libcrfp_b200 has no CPU path)")
+        if t.dtype != torch.float32:
+            raise L.CrfpError(f"{what} must be float32, got {t.dtype}")
+        return t.contiguous()
+
+    # ---- forward primitives (GPU-verified SIMT fp32 kernels of the inference library)
+    def conv3x3(self, srcs, weight, bias, act):
+        from . import ops
+        return ops.conv3x3_nhwc(srcs, weight, bias, act=act)
+
+    def dcn_v2(self, x, offset, mask, weight, bias, dg):
+        from . import ops
+        from .packing import pack_dcn
+        wp, bp = pack_dcn(weight, bias, dg)
+        return ops.dcn_v2_nhwc(x, offset, mask, wp, bp, dg, weight.shape[0])
+
+    def flow_warp(self, x, flow):
+        from . import ops
+        return ops.flow_warp_nhwc(x, flow)
+
+    def resize(self, x, hout, wout, rh, rw, mul):
+        from . import ops
+        return ops.resize_bilinear_nhwc(x, hout, wout, rh, rw, mul)
+
+    def avgpool2(self, x):
+        from . import ops
+        return ops.avgpool2_nhwc(x)
+
+    def to_nhwc(self, x):
+        from . import ops
+        return ops.to_nhwc(x)
+
+
+CUDA = KernelSet()
+
+
+def _chk(K, status, what):
+    if status != 0:
+        if K is CUDA:
+            L.check(status, what)
+        raise L.CrfpError(f"{what} failed with status {status}")
+
+
+# ----------------------------------------------------------------------------------------------- conv3x3 (+bias+act)
+class Conv3x3Fn(torch.autograd.Function):
+    """act(conv3x3(cat(srcs, -1), weight) + bias); weight OIHW (the reference's nn.Conv2d parameter)."""
+
+    @staticmethod
+    def forward(ctx, K, act, weight, bias, *srcs):
+        srcs = [K.req(s.detach(), "conv source") for s in srcs]
+        out = K.conv3x3(srcs, weight.detach(), bias.detach(), act)
+        ctx.K, ctx.act, ctx.c_list = K, act, [s.shape[-1] for s in srcs]
+        ctx.save_for_backward(weight, out if act != ACT_NONE else None, *srcs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        K, act = ctx.K, ctx.act
+        weight, out, *srcs = ctx.saved_tensors
+        lib, st = K.lib(), K.stream()
+        dy = K.req(dy, "grad_output")
+        n, h, w, cout = dy.shape
+        cin = sum(ctx.c_list)
+        if act != ACT_NONE:
+            g = torch.empty_like(dy)
+            _chk(K, lib.crfp_act_bwd(dy.numel(), act, dy.data_ptr(), out.data_ptr(), g.data_ptr(), st), "act_bwd")
+        else:
+            g = dy
+        need_w, need_b = ctx.needs_input_grad[2], ctx.needs_input_grad[3]
+        need_x = any(ctx.needs_input_grad[4:])
+        dW = db = None
+        dxs = [None] * len(srcs)
+        if need_x:
+            w_t = weight.detach().permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous()      # [tap][co][ci]
+            dx = torch.empty(n, h, w, cin, device=dy.device, dtype=torch.float32)
+            _chk(K, lib.crfp_conv3x3_bwd_data(n, h, w, cin, cout, g.data_ptr(), w_t.data_ptr(), dx.data_ptr(), st),
+                 "conv3x3_bwd_data")
+            off = 0
+            for i, c in enumerate(ctx.c_list):
+                if ctx.needs_input_grad[4 + i]:
+                    dxs[i] = dx[..., off:off + c]
+                off += c
+        if need_w or need_b:
+            x = srcs[0] if len(srcs) == 1 else torch.cat(srcs, dim=-1)
+            dw = torch.zeros(9, cin, cout, device=dy.device, dtype=torch.float32)
+            dbt = torch.zeros(cout, device=dy.device, dtype=torch.float32)
+            _chk(K, lib.crfp_conv3x3_bwd_weight(n, h, w, cin, cout, x.data_ptr(), g.data_ptr(), dw.data_ptr(),
+                                                dbt.data_ptr(), st), "conv3x3_bwd_weight")
+            if need_w:
+                dW = dw.permute(2, 1, 0).reshape(cout, cin, 3, 3)
+            if need_b:
+                db = dbt
+        return (None, None, dW, db, *dxs)
+
+
+def conv3x3(K, weight, bias, srcs, act=ACT_NONE):
+    return Conv3x3Fn.apply(K, act, weight, bias, *srcs)
+
+
+# ----------------------------------------------------------------------------------------------- DCNv2
+class DCNv2Fn(torch.autograd.Function):
+    """dcn_v2.DCNv2.forward(input, offset, mask) in NHWC: offset (n,h,w,dg*18), mask (n,h,w,dg*9); weight OIHW."""
+
+    @staticmethod
+    def forward(ctx, K, dg, x, offset, mask, weight, bias):
+        x, offset, mask = K.req(x.detach(), "input"), K.req(offset.detach(), "offset"), K.req(mask.detach(), "mask")
+        if offset.shape[-1] != dg * 18 or mask.shape[-1] != dg * 9 or x.shape[-1] % dg:
+            raise L.CrfpError("DCNv2: offset/mask channel count does not match deformable_groups")
+        out = K.dcn_v2(x, offset, mask, weight.detach(), bias.detach(), dg)
+        ctx.K, ctx.dg = K, dg
+        ctx.save_for_backward(x, offset, mask, weight)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        K, dg = ctx.K, ctx.dg
+        x, offset, mask, weight = ctx.saved_tensors
+        dout = K.req(dout, "grad_output")
+        n, h, w, c = x.shape
+        cout = weight.shape[0]
+        cpg, kk = c // dg, 9 * c
+        dev = x.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        wk = weight.detach().reshape(cout, dg, cpg, 9).permute(1, 3, 2, 0).reshape(kk, cout).contiguous()  # [k][co]
+        dx = torch.zeros(n, h, w, c, **f32)
+        doff = torch.empty(n, h, w, dg * 18, **f32)
+        dmask = torch.empty(n, h, w, dg * 9, **f32)
+        dwk = torch.zeros(kk, cout, **f32)
+        dbias = torch.zeros(cout, **f32)
+        col = torch.empty(n * h * w, kk, **f32)
+        d = L.DcnBwdDesc(n=n, h=h, w=w, c=c, cout=cout, dg=dg, x=x.data_ptr(), offset=offset.data_ptr(),
+                         mask=mask.data_ptr(), weight=wk.data_ptr(), dout=dout.data_ptr(), dx=dx.data_ptr(),
+                         doffset=doff.data_ptr(), dmask=dmask.data_ptr(), dweight=dwk.data_ptr(),
+                         dbias=dbias.data_ptr(), col=col.data_ptr())
+        _chk(K, K.lib().crfp_dcn_v2_bwd(C.byref(d), K.stream()), "dcn_v2_bwd")
+        dW = dwk.view(dg, 9, cpg, cout).permute(3, 0, 2, 1).reshape(cout, c, 3, 3)
+        ng = ctx.needs_input_grad
+        return (None, None, dx if ng[2] else None, doff if ng[3] else None, dmask if ng[4] else None,
+                dW if ng[5] else None, dbias if ng[6] else None)
+
+
+def dcn_v2(K, x, offset, mask, weight, bias, dg):
+    return DCNv2Fn.apply(K, dg, x, offset, mask, weight, bias)
+
+
+# ----------------------------------------------------------------------------------------------- flow_warp
+class FlowWarpFn(torch.autograd.Function):
+    """flow_warp(x, flow) (model/CRFP.py:90-130), x (n,h,w,c) with c % 4 == 0, flow (n,h,w,2) = (dx, dy)."""
+
+    @staticmethod
+    def forward(ctx, K, x, flow):
+        x, flow = K.req(x.detach(), "x"), K.req(flow.detach(), "flow")
+        if tuple(flow.shape) != (*x.shape[:3], 2):
+            raise ValueError(f"The spatial sizes of input ({tuple(x.shape[1:3])}) and flow ({tuple(flow.shape[1:3])}) "
+                             "are not the same.")
+        ctx.K = K
+        ctx.save_for_backward(x, flow)
+        return K.flow_warp(x, flow)
+
+    @staticmethod
+    def backward(ctx, dy):
+        K = ctx.K
+        x, flow = ctx.saved_tensors
+        dy = K.req(dy, "grad_output")
+        n, h, w, c = x.shape
+        need_x, need_f = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        if not (need_x or need_f):
+            return None, None, None
+        dx = torch.zeros_like(x) if need_x else None
+        df = torch.empty_like(flow) if need_f else None
+        _chk(K, K.lib().crfp_flow_warp_bwd(n, h, w, c, x.data_ptr(), flow.data_ptr(), dy.data_ptr(),
+                                           dx.data_ptr() if need_x else None, df.data_ptr() if need_f else None,
+                                           K.stream()), "flow_warp_bwd")
+        return None, dx, df
+
+
+def flow_warp(K, x, flow):
+    return FlowWarpFn.apply(K, x, flow)
+
+
+# ----------------------------------------------------------------------------------------------- resize / pool
+class ResizeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, K, x, hout, wout, rh, rw, mul):
+        x = K.req(x.detach(), "x")
+        ctx.K, ctx.args, ctx.in_shape = K, (hout, wout, rh, rw, mul), tuple(x.shape)
+        return K.resize(x, hout, wout, rh, rw, mul)
+
+    @staticmethod
+    def backward(ctx, dy):
+        K = ctx.K
+        if not ctx.needs_input_grad[1]:
+            return (None,) * 7
+        dy = K.req(dy, "grad_output")
+        n, hin, win, c = ctx.in_shape
+        hout, wout, rh, rw, mul = ctx.args
+        dx = torch.zeros(n, hin, win, c, device=dy.device, dtype=torch.float32)
+        _chk(K, K.lib().crfp_resize_bilinear_bwd(n, hin, win, c, hout, wout, rh, rw, mul, dy.data_ptr(), dx.data_ptr(),
+                                                 K.stream()), "resize_bilinear_bwd")
+        return (None, dx, None, None, None, None, None)
+
+
+def up_bilinear(K, x, scale, mul=1.0):
+    """nn.Upsample(scale_factor=scale, mode='bilinear', align_corners=False)(x) * mul."""
+    n, h, w, c = x.shape
+    return ResizeFn.apply(K, x, int(h * scale), int(w * scale), 1.0 / scale, 1.0 / scale, float(mul))
+
+
+def resize_to(K, x, hout, wout):
+    """F.interpolate(x, size=(hout, wout), mode='bilinear', align_corners=False)."""
+    n, h, w, c = x.shape
+    if (h, w) == (hout, wout):
+        return x
+    return ResizeFn.apply(K, x, hout, wout, h / hout, w / wout, 1.0)
+
+
+class AvgPool2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, K, x):
+        x = K.req(x.detach(), "x")
+        ctx.K, ctx.in_shape = K, tuple(x.shape)
+        return K.avgpool2(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        K = ctx.K
+        dy = K.req(dy, "grad_output")
+        n, hin, win, c = ctx.in_shape
+        dx = torch.empty(n, hin, win, c, device=dy.device, dtype=torch.float32)
+        _chk(K, K.lib().crfp_avgpool2_bwd(n, hin, win, c, dy.data_ptr(), dx.data_ptr(), K.stream()), "avgpool2_bwd")
+        return None, dx
+
+
+def avgpool2(K, x):
+    return AvgPool2Fn.apply(K, x)
+
+
+# ----------------------------------------------------------------------------------------------- loss
+class CharbonnierFn(torch.autograd.Function):
+    """CharbonnierLoss(loss_weight, reduction='mean', eps)(pred, target) (loss/loss.py:116-176): one kernel computes the
+    loss sum and d loss / d pred."""
+
+    @staticmethod
+    def forward(ctx, K, pred, target, eps, loss_weight):
+        p, t = K.req(pred.detach(), "pred"), K.req(target.detach(), "target")
+        if p.shape != t.shape:
+            raise ValueError("pred and target must have the same shape")
+        count = p.numel()
+        loss_sum = torch.zeros(1, device=p.device, dtype=torch.float32)
+        dpred = torch.empty_like(p)
+        _chk(K, K.lib().crfp_charbonnier_fwd_bwd(count, p.data_ptr(), t.data_ptr(), eps, loss_weight / count,
+                                                 loss_sum.data_ptr(), dpred.data_ptr(), K.stream()), "charbonnier")
+        ctx.save_for_backward(dpred)
+        return (loss_sum * (loss_weight / count)).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dpred,) = ctx.saved_tensors
+        return None, dpred * g, None, None, None
+
+
+def charbonnier_loss(K, pred, target, eps=1e-12, loss_weight=1.0):
+    return CharbonnierFn.apply(K, pred, target, float(eps), float(loss_weight))

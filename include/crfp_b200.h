@@ -26,6 +26,7 @@
  *   crfp_dsv_prepare          CRFP_DSV.compute_flow + encoder_lr         model/CRFP.py:1483-1508,1540
  *   crfp_dsv_frame            one iteration of the t-loop of CRFP_DSV.forward   model/CRFP.py:1555-1684
  *                             incl. fovea compositing + encoder_hr (1542-1547) for that frame
+ *   crfp_*_bwd, crfp_charbonnier_fwd_bwd, crfp_adam_step   loss.backward() + optimizer.step()   trainer.py:246-250
  */
 #ifndef CRFP_B200_H
 #define CRFP_B200_H
@@ -426,6 +427,63 @@ int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weights* wts, vo
                    crfp_stream stream);
 size_t crfp_sizeof_dsv_weights(void);
 size_t crfp_sizeof_dsv_frame_desc(void);
+
+/* ------------------------------------------------------------------ training: backward kernels, loss, optimiser */
+/*
+ * Gradients the reference obtains from `loss.backward()` (trainer.py:246-250) through ATen / cuDNN autograd and
+ * `_ext.dcn_v2_backward(input, weight, bias, offset, mask, grad_output, ...)` of jinfagang/DCNv2_latest (README.md:26).
+ * All tensors here are DENSE fp32 NHWC (pixel stride == channel count).  Outputs documented as "accumulated" are +=
+ * (zero-fill them once per step); the others are overwritten.
+ */
+/* g = dy * act'(v), act in {CRFP_ACT_LRELU, CRFP_ACT_RELU}; the sign of v is taken from the saved forward output */
+int crfp_act_bwd(long long count, int act, const float* dy, const float* out, float* g, crfp_stream stream);
+/* nn.Conv2d(3x3,s1,p1) backward-data: dx[n,h,w,cin] from g[n,h,w,cout]; weight_t = [tap][cout][cin], tap = ky*3+kx */
+int crfp_conv3x3_bwd_data(int n, int h, int w, int cin, int cout, const float* g, const float* weight_t, float* dx,
+                          crfp_stream stream);
+/* backward-weight: dw[tap][cin][cout] (accumulated), db[cout] (accumulated, may be NULL) from x[n,h,w,cin], g[n,h,w,cout] */
+int crfp_conv3x3_bwd_weight(int n, int h, int w, int cin, int cout, const float* x, const float* g, float* dw, float* db,
+                            crfp_stream stream);
+/*
+ * DCNv2 backward (= dcn_v2_backward): non-shared layout only (offset dg*18, mask dg*9 channels per pixel).
+ *   weight   [K][cout], K = 9*c, k = (g*9+t)*(c/dg) + c_in_group (crfp_dcn_v2_fwd packing with cout % 4 == 0)
+ *   dx       [n,h,w,c]      accumulated (atomic scatter)
+ *   doffset  [n,h,w,dg*18], dmask [n,h,w,dg*9]   overwritten
+ *   dweight  [K][cout]      accumulated;  dbias [cout] accumulated (may be NULL)
+ *   col      workspace [n*h*w][K] floats: the modulated columns, rebuilt here and contracted with dout
+ */
+typedef struct {
+  int32_t n, h, w;
+  int32_t c, cout, dg;
+  const float* x;
+  const float* offset;
+  const float* mask;
+  const float* weight;
+  const float* dout;
+  float* dx;
+  float* doffset;
+  float* dmask;
+  float* dweight;
+  float* dbias;
+  float* col;
+} crfp_dcn_bwd_desc;
+int crfp_dcn_v2_bwd(const crfp_dcn_bwd_desc* d, crfp_stream stream);
+size_t crfp_sizeof_dcn_bwd_desc(void);
+/* flow_warp backward (zeros padding): dx [n,h,w,c] accumulated (may be NULL), dflow [n,h,w,2] overwritten (may be NULL) */
+int crfp_flow_warp_bwd(int n, int h, int w, int c, const float* x, const float* flow, const float* dy, float* dx,
+                       float* dflow, crfp_stream stream);
+/* crfp_resize_bilinear backward: dx [n,hin,win,c] accumulated from dy [n,hout,wout,c] */
+int crfp_resize_bilinear_bwd(int n, int hin, int win, int c, int hout, int wout, float rscale_h, float rscale_w, float mul,
+                             const float* dy, float* dx, crfp_stream stream);
+/* crfp_avgpool2 backward: dx [n,hin,win,c] overwritten from dy [n,hin/2,win/2,c] */
+int crfp_avgpool2_bwd(int n, int hin, int win, int c, const float* dy, float* dx, crfp_stream stream);
+/* Charbonnier loss (loss/loss.py:116-124): *loss_sum += sum sqrt((pred-target)^2 + eps) (divide by count for the mean);
+ * dpred (may be NULL) = grad_scale * (pred-target)/sqrt(.) — grad_scale = loss_weight / count for reduction='mean' */
+int crfp_charbonnier_fwd_bwd(long long count, const float* pred, const float* target, float eps, float grad_scale,
+                             float* loss_sum, float* dpred, crfp_stream stream);
+/* one torch.optim.Adam update (trainer.py:149: no weight decay / amsgrad) over a flat parameter range:
+ * step_size = lr / (1 - beta1^t), bc2_sqrt = sqrt(1 - beta2^t) */
+int crfp_adam_step(long long count, float* p, const float* g, float* m, float* v, float beta1, float beta2, float eps,
+                   float step_size, float bc2_sqrt, crfp_stream stream);
 
 #ifdef __cplusplus
 }

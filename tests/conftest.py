@@ -6,6 +6,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+TOOLS = os.path.join(ROOT, "tests", "tools")   # test-only helpers (hostemu: host emulation of the backward kernels)
+if TOOLS not in sys.path:
+    sys.path.insert(0, TOOLS)
 
 
 def pytest_configure(config):
