@@ -235,16 +235,26 @@ class CRFP_DSV(_CRFPBase):
     def forward(self, lrs, fvs, mks, out_host=None):
         """Reference signature `forward(lrs, fvs, mks)`; the optional `out_host` (pinned CPU tensor) additionally
         streams every finished frame to the host while the recurrence continues."""
-        self._check_mode()
+        if self._wants_grad():
+            # training: node-by-node forward over the autograd kernel pairs (crfp_b200/training.py); the fused
+            # whole-frame inference kernels keep no intermediates to differentiate through
+            if self.VARIANT != "dsv":
+                raise NotImplementedError("crfp_b200: the training forward is implemented for CRFP_DSV only")
+            from .training import forward_train
+            lrs, fvs, mks = self._check_inputs(lrs, fvs, mks)
+            return forward_train(self, lrs, fvs, mks)
         with torch.no_grad():
             lrs, fvs, mks = self._check_inputs(lrs, fvs, mks)
             key = ("clip", lrs.data_ptr(), fvs.data_ptr(), mks.data_ptr())
             return self._forward_clip(key, lrs, fvs, mks, out_host, None)
 
+    def _wants_grad(self):
+        return torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters())
+
     def _check_mode(self):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("crfp_b200: the backward kernels are not implemented yet; call under "
-                                      "torch.no_grad() / model.eval() (SURVEY.md 8(f) rank 1)")
+        if self._wants_grad():
+            raise NotImplementedError("crfp_b200: this entry point is inference-only; call under torch.no_grad() / "
+                                      "model.eval(), or use forward(lrs, fvs, mks) for training")
 
     def _forward_clip(self, key, lrs, fvs, mks, out_host, pre):
         """prepare + frame loop, eagerly or as a replay of the captured whole-clip graph.  `pre(stream)` = extra work

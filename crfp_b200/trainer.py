@@ -1,0 +1,118 @@
+"""One training iteration of the reference's `Trainer.train_basicvsr` loop (/root/reference/trainer.py:206-293) on the
+B200 kernels: forward with autograd over `crfp_b200.training`, Charbonnier loss, backward, ONE fused gradient
+all-reduce across ranks, Adam with two parameter groups on a cosine schedule.
+
+  groups      main parameters lr_rate (2e-4, train.sh:12) / `spynet.*` (the FNet) lr_rate_flow (2.5e-5, train.sh:13)
+              trainer.py:132-149; Adam betas (0.9, 0.999), eps 1e-12 (option.py:70-74)
+  schedule    cosine annealing from the base lr to 1e-7 over 600 000 iterations, no restarts (trainer.py:120-128,
+              604-622, annealing_cos :70-83), applied BEFORE each iteration (before_train_iter)
+  freeze      FNet parameters do not train during the first 5 000 iterations (trainer.py:223-229)
+  loss        rec_w * CharbonnierLoss()(sr.view(B*N,C,H,W), hr.view(B*N,C,H,W))   (trainer.py:233-246)
+
+Parameters, gradients and both Adam moments live in FLAT fp32 buffers ([main | spynet], 2 284 352 elements = 9.14 MB
+each): every `p.data` / `p.grad` is a view into them, so the multi-GPU gradient exchange is a single NCCL all-reduce
+of one bucket and the optimiser is one `crfp_adam_step` launch per group.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import autograd as A
+from .training import forward_train
+
+
+def annealing_cos(start, end, factor, weight=1.0):
+    """trainer.py:70-83."""
+    cos_out = math.cos(math.pi * factor) + 1
+    return end + 0.5 * weight * (start - end) * cos_out
+
+
+class Trainer:
+    def __init__(self, model, lr_rate=2e-4, lr_rate_flow=2.5e-5, beta1=0.9, beta2=0.999, eps=1e-12, rec_w=1.0,
+                 period=600000, min_lr=1e-7, freeze_flow_iters=5000, process_group=None, kernels=None):
+        self.model = model
+        self.K = kernels or A.CUDA
+        self.betas, self.eps, self.rec_w = (beta1, beta2), eps, rec_w
+        self.period, self.min_lr, self.freeze_flow_iters = period, min_lr, freeze_flow_iters
+        self.base_lr = [lr_rate, lr_rate_flow]
+        self.cur_iter = 0
+        self.pg = process_group
+        named = list(model.named_parameters())
+        groups = [[(k, p) for k, p in named if "spynet" not in k], [(k, p) for k, p in named if "spynet" in k]]
+        total = sum(p.numel() for _, p in named)
+        dev = named[0][1].device
+        self.flat_p = torch.empty(total, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_m = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_v = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.ranges, self.group_steps = [], [0, 0]
+        off = 0
+        for grp in groups:
+            start = off
+            for _, p in grp:
+                n = p.numel()
+                self.flat_p[off:off + n].copy_(p.data.reshape(-1))
+                p.data = self.flat_p[off:off + n].view_as(p)
+                p.grad = self.flat_g[off:off + n].view_as(p)
+                off += n
+            self.ranges.append((start, off))
+        self.group_params = [[p for _, p in grp] for grp in groups]
+        self.lr = list(self.base_lr)
+
+    # ---- trainer.py:604-622
+    def get_lr(self, base_lr):
+        alpha = min(self.cur_iter / self.period, 1)
+        return annealing_cos(base_lr, self.min_lr, alpha, 1.0)
+
+    def _set_flow_trainable(self):
+        train_flow = self.cur_iter >= self.freeze_flow_iters
+        for p in self.group_params[1]:
+            p.requires_grad_(train_flow)
+        return train_flow
+
+    def step(self, lrs, fvs, mks, hr):
+        """One iteration on this rank's clips: lrs (n,t,3,h,w), fvs (n,t,3,8h,8w), mks (n,t,1,8h,8w) bool,
+        hr (n,t,3,8h,8w).  Returns the (detached) loss tensor of this rank."""
+        K, model = self.K, self.model
+        model.train()
+        train_flow = self._set_flow_trainable()
+        self.lr = [self.get_lr(b) for b in self.base_lr]            # before_train_iter
+        sr = forward_train(model, lrs, fvs, mks, K)
+        b, n, c, h, w = sr.shape
+        loss = A.charbonnier_loss(K, sr.reshape(b * n, c, h, w), hr.reshape(b * n, c, h, w).to(torch.float32), 1e-12,
+                                  self.rec_w)
+        self.flat_g.zero_()                                          # optimizer.zero_grad()
+        for grp in self.group_params:                                # keep every .grad a view of the flat bucket
+            for p in grp:
+                if p.grad is None:
+                    raise RuntimeError("a parameter lost its flat gradient view")
+        loss.backward()
+        if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            ws = torch.distributed.get_world_size(self.pg)
+            if ws > 1:                                               # ONE all-reduce of the 9.14 MB bucket
+                torch.distributed.all_reduce(self.flat_g, group=self.pg)
+                self.flat_g.mul_(1.0 / ws)
+        self._adam(train_flow)
+        self.cur_iter += 1
+        model._packed = None                                         # inference-side packed weights are stale now
+        if hasattr(model, "_graphs"):
+            model._graphs.clear()
+        return loss.detach()
+
+    def _adam(self, train_flow):
+        lib, st = self.K.lib(), self.K.stream()
+        b1, b2 = self.betas
+        for gi, (lo, hi) in enumerate(self.ranges):
+            if gi == 1 and not train_flow:                           # params without grad are skipped by torch's Adam
+                continue
+            self.group_steps[gi] += 1
+            t = self.group_steps[gi]
+            step_size = self.lr[gi] / (1 - b1 ** t)
+            bc2_sqrt = math.sqrt(1 - b2 ** t)
+            rc = lib.crfp_adam_step(hi - lo, self.flat_p[lo:hi].data_ptr(), self.flat_g[lo:hi].data_ptr(),
+                                    self.flat_m[lo:hi].data_ptr(), self.flat_v[lo:hi].data_ptr(), b1, b2, self.eps,
+                                    step_size, bc2_sqrt, st)
+            if rc != 0:
+                raise RuntimeError(f"crfp_adam_step failed with status {rc}")
