@@ -41,14 +41,28 @@ def input_index_map(c_list, modes=None, ci_lo: int = 0):
     return idx
 
 
+_INDEX_CACHE = {}
+
+
+def _conv_index_tensors(c_list, modes, ci_lo, device):
+    """(gather index, validity mask) of input_index_map on `device`, built once per layer signature: the training
+    step re-packs every layer's weights every iteration and must not pay a host->device copy each time."""
+    key = (c_list, modes, ci_lo, str(device))
+    hit = _INDEX_CACHE.get(key)
+    if hit is None:
+        idx = input_index_map(list(c_list), list(modes) if modes else None, ci_lo)
+        sel = torch.tensor([i if i >= 0 else 0 for i in idx], device=device, dtype=torch.long)
+        valid = torch.tensor([1.0 if i >= 0 else 0.0 for i in idx], device=device)
+        hit = _INDEX_CACHE[key] = (sel, valid)
+    return hit
+
+
 def pack_conv(weight: torch.Tensor, bias: torch.Tensor, c_list, modes=None, ci_lo: int = 0):
     """OIHW (cout, cin, 3, 3) + bias -> ([9, cin_packed, cout_packed], [cout_packed]) fp32 contiguous."""
     cout = weight.shape[0]
     cp, op = cin_packed(c_list), cout_packed(cout)
-    idx = input_index_map(c_list, modes, ci_lo)
     w = weight.detach().to(torch.float32)
-    sel = torch.tensor([i if i >= 0 else 0 for i in idx], device=w.device, dtype=torch.long)
-    valid = torch.tensor([1.0 if i >= 0 else 0.0 for i in idx], device=w.device)
+    sel, valid = _conv_index_tensors(tuple(c_list), tuple(modes) if modes else None, ci_lo, w.device)
     wp = w[:, sel] * valid.view(1, -1, 1, 1)                    # (cout, cin_packed, 3, 3)
     wp = wp.permute(2, 3, 1, 0).reshape(9, cp, cout)            # (tap, ci, co)
     out = torch.zeros(9, cp, op, device=w.device, dtype=torch.float32)

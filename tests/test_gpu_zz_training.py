@@ -192,7 +192,7 @@ def test_model_gradients_match_the_oracle(A, n, t, h, w):
     loss = A.charbonnier_loss(A.CUDA, sr.reshape(n * t, 3, 8 * h, 8 * w), hr.cuda().reshape(n * t, 3, 8 * h, 8 * w))
     loss.backward()
     torch.cuda.synchronize()
-    assert L.lib().crfp_launch_count() > 100
+    assert L.lib().crfp_launch_count() > 40      # forward launches of this thread (autograd runs the backward in its own)
     sdg = {k: v.clone().requires_grad_() for k, v in sd.items()}
     ref = _oracle_forward_with_grad(sdg, lrs, fvs, mks)
     assert (sr.detach().cpu() - ref.detach()).abs().max().item() < 1e-3
