@@ -127,3 +127,34 @@ def test_trainer_step_matches_torch_adam_on_the_oracle():
         assert (params[k].detach() - sd[k]).abs().max().item() > 0, f"{k} did not train"
     assert tr.group_steps == [3, 2]
     assert losses[2] < losses[0]
+
+
+def _ddp_worker(rank, world, port, out_dir):
+    """world_size 2 over gloo: each rank trains on its own clip; ONE all-reduce of the flat gradient bucket."""
+    import os
+    import sys
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sd, model, lrs, fvs, mks, hr = _setup(5, 2, 2, 8, 8)
+        tr = Trainer(model, freeze_flow_iters=0, kernels=hostemu.HostEmuKernelSet())
+        sl = slice(rank, rank + 1)
+        loss = tr.step(lrs[sl], fvs[sl], mks[sl], hr[sl])
+        torch.save({"p": tr.flat_p.clone(), "g": tr.flat_g.clone(), "loss": loss}, os.path.join(out_dir, f"r{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_step_equals_the_single_process_step_on_both_clips(tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_ddp_worker, args=(2, 29541, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (torch.load(tmp_path / f"r{r}.pt") for r in (0, 1))
+    assert torch.equal(r0["p"], r1["p"]) and torch.equal(r0["g"], r1["g"])       # replicas stay identical
+    sd, model, lrs, fvs, mks, hr = _setup(5, 2, 2, 8, 8)
+    tr = Trainer(model, freeze_flow_iters=0, kernels=K)
+    loss = tr.step(lrs, fvs, mks, hr)                                              # both clips in one process
+    assert abs(loss.item() - 0.5 * (r0["loss"].item() + r1["loss"].item())) < 1e-6
+    gn = tr.flat_g.norm().item()
+    assert (tr.flat_g - r0["g"]).norm().item() < 1e-4 * gn                         # mean of per-rank grads == batch grad
