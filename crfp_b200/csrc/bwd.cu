@@ -63,13 +63,52 @@ __global__ void __launch_bounds__(256) conv3x3_bwd_data_kernel(int n, int h, int
   dx[idx] = acc;
 }
 
+// Register-tiled variant for cin % 4 == 0 and cout % 4 == 0: one thread per (pixel, 4 input channels); per 4 output
+// channels it issues 1 LDG.128 of g (warp broadcast) + 4 LDG.128 of weights (coalesced over ci) for 16 FMAs.
+__global__ void __launch_bounds__(256) conv3x3_bwd_data_v4_kernel(int n, int h, int w, int cin, int cout,
+                                                                  const float* __restrict__ g,
+                                                                  const float* __restrict__ wt_t, float* __restrict__ dx) {
+  const int cq = cin >> 2;
+  const long long total = (long long)n * h * w * cq;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ci = (int)(idx % cq) * 4;
+  const long long pix = idx / cq;
+  const int x = (int)(pix % w);
+  const int y = (int)((pix / w) % h);
+  const long long b = pix / ((long long)w * h);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yo = y + 1 - ky;
+    if (yo < 0 || yo >= h) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xo = x + 1 - kx;
+      if (xo < 0 || xo >= w) continue;
+      const float* gp = g + ((b * h + yo) * w + xo) * cout;
+      const float* wp = wt_t + (long long)(ky * 3 + kx) * cout * cin + ci;
+      for (int co = 0; co < cout; co += 4) {
+        const float4 gv = *reinterpret_cast<const float4*>(gp + co);
+        const float4 w0 = *reinterpret_cast<const float4*>(wp + (long long)co * cin);
+        const float4 w1 = *reinterpret_cast<const float4*>(wp + (long long)(co + 1) * cin);
+        const float4 w2 = *reinterpret_cast<const float4*>(wp + (long long)(co + 2) * cin);
+        const float4 w3 = *reinterpret_cast<const float4*>(wp + (long long)(co + 3) * cin);
+        acc.x += gv.x * w0.x + gv.y * w1.x + gv.z * w2.x + gv.w * w3.x;
+        acc.y += gv.x * w0.y + gv.y * w1.y + gv.z * w2.y + gv.w * w3.y;
+        acc.z += gv.x * w0.z + gv.y * w1.z + gv.z * w2.z + gv.w * w3.z;
+        acc.w += gv.x * w0.w + gv.y * w1.w + gv.z * w2.w + gv.w * w3.w;
+      }
+    }
+  }
+  *reinterpret_cast<float4*>(dx + pix * cin + ci) = acc;
+}
+
 // ------------------------------------------------------------------------------------------------ 3x3 conv, weights
 // dw[tap][ci][co] += sum_p x[p + shift(tap)][ci] * g[p][co];  db[co] += sum_p g[p][co].
 // One thread per weight element (co fastest: g loads coalesced, x loads warp-broadcast) and per block of image rows;
 // partial sums meet in dw through atomicAdd.  taps == 1 is the plain (pixels x cin)^T (pixels x cout) product used for
 // the DCN weight gradient (x = the modulated column buffer).
 __global__ void __launch_bounds__(128) conv_bwd_weight_kernel(int rows, int h, int w, int cin, int cout, int taps,
-                                                              int rows_per_block, const float* __restrict__ x,
+                                                              int rows_per_block, int xsegs, const float* __restrict__ x,
                                                               const float* __restrict__ g, float* __restrict__ dw,
                                                               float* __restrict__ db) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -79,35 +118,110 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_kernel(int rows, int h, i
   const int tap = e / (cout * cin);
   const int ky = (taps == 9) ? tap / 3 : 1, kx = (taps == 9) ? tap % 3 : 1;
   const bool do_bias = (db != nullptr) && ci == 0 && tap == ((taps == 9) ? 4 : 0);
-  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  // blockIdx.y = (row block, column segment): rows [r0, r1), columns [c0, c1)
+  const long long r0 = (long long)(blockIdx.y / xsegs) * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
+  const int wseg = (w + xsegs - 1) / xsegs;
+  const int c0 = (int)(blockIdx.y % xsegs) * wseg;
+  const int c1 = (c0 + wseg < w) ? c0 + wseg : w;
+  const int xlo = (kx == 0 && c0 == 0) ? 1 : c0, xhi = (kx == 2 && c1 == w) ? w - 1 : c1;
   float acc = 0.f, gsum = 0.f;
   for (long long r = r0; r < r1; ++r) {
     const int y = (int)(r % h);
     const int yi = y + ky - 1;
     const float* gp = g + r * w * cout + co;
     if (do_bias)
-      for (int xx = 0; xx < w; ++xx) gsum += gp[(long long)xx * cout];
+      for (int xx = c0; xx < c1; ++xx) gsum += gp[(long long)xx * cout];
     if (yi < 0 || yi >= h) continue;
     const float* xp = x + (r + (ky - 1)) * w * cin + ci;
-    const int xlo = (kx == 0) ? 1 : 0, xhi = (kx == 2) ? w - 1 : w;
     for (int xx = xlo; xx < xhi; ++xx) acc += gp[(long long)xx * cout] * xp[(long long)(xx + kx - 1) * cin];
   }
   atomicAdd(dw + e, acc);
   if (do_bias) atomicAdd(db + co, gsum);
 }
 
+// Register-tiled variant for cin % 4 == 0 and cout % 4 == 0: one thread per (tap, 4 ci, 4 co) block of dw; per pixel
+// 2 LDG.128 (x: warp broadcast over the co blocks, g: coalesced) feed 16 FMAs.
+__global__ void __launch_bounds__(128) conv_bwd_weight_v4_kernel(int rows, int h, int w, int cin, int cout, int taps,
+                                                                 int rows_per_block, int xsegs, const float* __restrict__ x,
+                                                                 const float* __restrict__ g, float* __restrict__ dw,
+                                                                 float* __restrict__ db) {
+  const int cq = cin >> 2, oq = cout >> 2;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= taps * cq * oq) return;
+  const int co = (e % oq) * 4;
+  const int ci = ((e / oq) % cq) * 4;
+  const int tap = e / (oq * cq);
+  const int ky = (taps == 9) ? tap / 3 : 1, kx = (taps == 9) ? tap % 3 : 1;
+  const bool do_bias = (db != nullptr) && ci == 0 && tap == ((taps == 9) ? 4 : 0);
+  const long long r0 = (long long)(blockIdx.y / xsegs) * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  const int wseg = (w + xsegs - 1) / xsegs;
+  const int c0 = (int)(blockIdx.y % xsegs) * wseg;
+  const int c1 = (c0 + wseg < w) ? c0 + wseg : w;
+  float acc[4][4];
+  for (int a = 0; a < 4; ++a)
+    for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+  float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int xlo = (kx == 0 && c0 == 0) ? 1 : c0, xhi = (kx == 2 && c1 == w) ? w - 1 : c1;
+  for (long long r = r0; r < r1; ++r) {
+    const int y = (int)(r % h);
+    const int yi = y + ky - 1;
+    const float* gp = g + r * w * cout + co;
+    if (do_bias)
+      for (int xx = c0; xx < c1; ++xx) {
+        const float4 gv = *reinterpret_cast<const float4*>(gp + (long long)xx * cout);
+        gsum.x += gv.x; gsum.y += gv.y; gsum.z += gv.z; gsum.w += gv.w;
+      }
+    if (yi < 0 || yi >= h) continue;
+    const float* xp = x + (r + (ky - 1)) * w * cin + ci;
+    for (int xx = xlo; xx < xhi; ++xx) {
+      const float4 gv = *reinterpret_cast<const float4*>(gp + (long long)xx * cout);
+      const float4 xv = *reinterpret_cast<const float4*>(xp + (long long)(xx + kx - 1) * cin);
+      acc[0][0] += xv.x * gv.x; acc[0][1] += xv.x * gv.y; acc[0][2] += xv.x * gv.z; acc[0][3] += xv.x * gv.w;
+      acc[1][0] += xv.y * gv.x; acc[1][1] += xv.y * gv.y; acc[1][2] += xv.y * gv.z; acc[1][3] += xv.y * gv.w;
+      acc[2][0] += xv.z * gv.x; acc[2][1] += xv.z * gv.y; acc[2][2] += xv.z * gv.z; acc[2][3] += xv.z * gv.w;
+      acc[3][0] += xv.w * gv.x; acc[3][1] += xv.w * gv.y; acc[3][2] += xv.w * gv.z; acc[3][3] += xv.w * gv.w;
+    }
+  }
+  float* d = dw + ((long long)tap * cin + ci) * cout + co;
+  for (int a = 0; a < 4; ++a)
+    for (int c = 0; c < 4; ++c) atomicAdd(d + (long long)a * cout + c, acc[a][c]);
+  if (do_bias) {
+    atomicAdd(db + co, gsum.x); atomicAdd(db + co + 1, gsum.y); atomicAdd(db + co + 2, gsum.z); atomicAdd(db + co + 3, gsum.w);
+  }
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 static int launch_bwd_weight(long long rows, int h, int w, int cin, int cout, int taps, const float* x, const float* g,
                              float* dw, float* db, cudaStream_t st) {
-  const int elems = taps * cin * cout;
+  const bool v4 = (cin % 4 == 0) && (cout % 4 == 0) && aligned16(x) && aligned16(g);
+  const int elems = v4 ? taps * (cin / 4) * (cout / 4) : taps * cin * cout;
   const unsigned gx = blocks_for(elems, 128);
   long long target_y = 8192 / gx;
   if (target_y < 1) target_y = 1;
   long long rpb = (rows + target_y - 1) / target_y;
   if (rpb < 1) rpb = 1;
-  const unsigned gy = (unsigned)((rows + rpb - 1) / rpb);
-  CRFP_LAUNCH(conv_bwd_weight_kernel, dim3(gx, gy), dim3(128), st, (int)rows, h, w, cin, cout, taps, (int)rpb, x, g, dw, db);
+  unsigned gy = (unsigned)((rows + rpb - 1) / rpb);
+  // few weight elements (the 4-channel HR layers): also split every row into column segments of >= 32 pixels so that
+  // the grid still fills the 148 SMs
+  int xsegs = 1;
+  if (rpb == 1 && (long long)gy * gx < 4096) {
+    xsegs = (int)(4096 / ((long long)gy * gx));
+    if (xsegs > w / 32) xsegs = w / 32;
+    if (xsegs < 1) xsegs = 1;
+    if ((long long)gy * xsegs > 65535) xsegs = (int)(65535 / gy);
+  }
+  gy *= (unsigned)xsegs;
+  if (v4)
+    CRFP_LAUNCH(conv_bwd_weight_v4_kernel, dim3(gx, gy), dim3(128), st, (int)rows, h, w, cin, cout, taps, (int)rpb, xsegs, x, g,
+                dw, db);
+  else
+    CRFP_LAUNCH(conv_bwd_weight_kernel, dim3(gx, gy), dim3(128), st, (int)rows, h, w, cin, cout, taps, (int)rpb, xsegs, x, g, dw,
+                db);
   return check_launch();
 }
 
@@ -330,6 +444,12 @@ extern "C" int crfp_conv3x3_bwd_data(int n, int h, int w, int cin, int cout, con
   if (n < 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0) return CRFP_ERR_BAD_SHAPE;
   if (n == 0) return CRFP_OK;
   if (!g || !weight_t || !dx) return CRFP_ERR_NULL;
+  if (cin % 4 == 0 && cout % 4 == 0 && aligned16(g) && aligned16(weight_t) && aligned16(dx)) {
+    const long long total4 = (long long)n * h * w * (cin / 4);
+    CRFP_LAUNCH(conv3x3_bwd_data_v4_kernel, dim3(blocks_for(total4, 256)), dim3(256), (cudaStream_t)stream, n, h, w, cin, cout,
+                g, weight_t, dx);
+    return check_launch();
+  }
   const long long total = (long long)n * h * w * cin;
   CRFP_LAUNCH(conv3x3_bwd_data_kernel, dim3(blocks_for(total, 256)), dim3(256), (cudaStream_t)stream, n, h, w, cin, cout, g,
               weight_t, dx);
