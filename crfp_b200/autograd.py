@@ -45,15 +45,27 @@ class KernelSet:
         return t.contiguous()
 
     # ---- forward primitives (GPU-verified SIMT fp32 kernels of the inference library)
-    def conv3x3(self, srcs, weight, bias, act):
+    # `cache` (a dict owned by the caller, valid while the weights do not change — one training step): the packed
+    # weight layouts are built once per layer and step instead of once per frame
+    def conv3x3(self, srcs, weight, bias, act, cache=None):
         from . import ops
-        return ops.conv3x3_nhwc(srcs, weight, bias, act=act)
+        from .packing import pack_conv
+        packed = None
+        if cache is not None:
+            packed = cache.get("fwd")
+            if packed is None:
+                packed = cache["fwd"] = pack_conv(weight, bias, [s.shape[-1] for s in srcs])
+        return ops.conv3x3_nhwc(srcs, weight, bias, act=act, packed=packed)
 
-    def dcn_v2(self, x, offset, mask, weight, bias, dg):
+    def dcn_v2(self, x, offset, mask, weight, bias, dg, cache=None):
         from . import ops
         from .packing import pack_dcn
-        wp, bp = pack_dcn(weight, bias, dg)
-        return ops.dcn_v2_nhwc(x, offset, mask, wp, bp, dg, weight.shape[0])
+        packed = cache.get("fwd") if cache is not None else None
+        if packed is None:
+            packed = pack_dcn(weight, bias, dg)
+            if cache is not None:
+                cache["fwd"] = packed
+        return ops.dcn_v2_nhwc(x, offset, mask, packed[0], packed[1], dg, weight.shape[0])
 
     def flow_warp(self, x, flow):
         from . import ops
@@ -87,10 +99,10 @@ class Conv3x3Fn(torch.autograd.Function):
     """act(conv3x3(cat(srcs, -1), weight) + bias); weight OIHW (the reference's nn.Conv2d parameter)."""
 
     @staticmethod
-    def forward(ctx, K, act, weight, bias, *srcs):
+    def forward(ctx, K, act, cache, weight, bias, *srcs):
         srcs = [K.req(s.detach(), "conv source") for s in srcs]
-        out = K.conv3x3(srcs, weight.detach(), bias.detach(), act)
-        ctx.K, ctx.act, ctx.c_list = K, act, [s.shape[-1] for s in srcs]
+        out = K.conv3x3(srcs, weight.detach(), bias.detach(), act, cache)
+        ctx.K, ctx.act, ctx.c_list, ctx.cache = K, act, [s.shape[-1] for s in srcs], cache
         ctx.save_for_backward(weight, out if act != ACT_NONE else None, *srcs)
         return out
 
@@ -107,18 +119,22 @@ class Conv3x3Fn(torch.autograd.Function):
             _chk(K, lib.crfp_act_bwd(dy.numel(), act, dy.data_ptr(), out.data_ptr(), g.data_ptr(), st), "act_bwd")
         else:
             g = dy
-        need_w, need_b = ctx.needs_input_grad[2], ctx.needs_input_grad[3]
-        need_x = any(ctx.needs_input_grad[4:])
+        need_w, need_b = ctx.needs_input_grad[3], ctx.needs_input_grad[4]
+        need_x = any(ctx.needs_input_grad[5:])
         dW = db = None
         dxs = [None] * len(srcs)
         if need_x:
-            w_t = weight.detach().permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous()      # [tap][co][ci]
+            w_t = ctx.cache.get("w_t") if ctx.cache is not None else None
+            if w_t is None:
+                w_t = weight.detach().permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous()  # [tap][co][ci]
+                if ctx.cache is not None:
+                    ctx.cache["w_t"] = w_t
             dx = torch.empty(n, h, w, cin, device=dy.device, dtype=torch.float32)
             _chk(K, lib.crfp_conv3x3_bwd_data(n, h, w, cin, cout, g.data_ptr(), w_t.data_ptr(), dx.data_ptr(), st),
                  "conv3x3_bwd_data")
             off = 0
             for i, c in enumerate(ctx.c_list):
-                if ctx.needs_input_grad[4 + i]:
+                if ctx.needs_input_grad[5 + i]:
                     dxs[i] = dx[..., off:off + c]
                 off += c
         if need_w or need_b:
@@ -131,11 +147,12 @@ class Conv3x3Fn(torch.autograd.Function):
                 dW = dw.permute(2, 1, 0).reshape(cout, cin, 3, 3)
             if need_b:
                 db = dbt
-        return (None, None, dW, db, *dxs)
+        return (None, None, None, dW, db, *dxs)
 
 
-def conv3x3(K, weight, bias, srcs, act=ACT_NONE):
-    return Conv3x3Fn.apply(K, act, weight, bias, *srcs)
+def conv3x3(K, weight, bias, srcs, act=ACT_NONE, cache=None):
+    """`cache`: optional dict reused for every call with the SAME weight tensor values (packed layouts live there)."""
+    return Conv3x3Fn.apply(K, act, cache, weight, bias, *srcs)
 
 
 # ----------------------------------------------------------------------------------------------- DCNv2
@@ -143,12 +160,12 @@ class DCNv2Fn(torch.autograd.Function):
     """dcn_v2.DCNv2.forward(input, offset, mask) in NHWC: offset (n,h,w,dg*18), mask (n,h,w,dg*9); weight OIHW."""
 
     @staticmethod
-    def forward(ctx, K, dg, x, offset, mask, weight, bias):
+    def forward(ctx, K, dg, cache, x, offset, mask, weight, bias):
         x, offset, mask = K.req(x.detach(), "input"), K.req(offset.detach(), "offset"), K.req(mask.detach(), "mask")
         if offset.shape[-1] != dg * 18 or mask.shape[-1] != dg * 9 or x.shape[-1] % dg:
             raise L.CrfpError("DCNv2: offset/mask channel count does not match deformable_groups")
-        out = K.dcn_v2(x, offset, mask, weight.detach(), bias.detach(), dg)
-        ctx.K, ctx.dg = K, dg
+        out = K.dcn_v2(x, offset, mask, weight.detach(), bias.detach(), dg, cache)
+        ctx.K, ctx.dg, ctx.cache = K, dg, cache
         ctx.save_for_backward(x, offset, mask, weight)
         return out
 
@@ -162,7 +179,11 @@ class DCNv2Fn(torch.autograd.Function):
         cpg, kk = c // dg, 9 * c
         dev = x.device
         f32 = dict(device=dev, dtype=torch.float32)
-        wk = weight.detach().reshape(cout, dg, cpg, 9).permute(1, 3, 2, 0).reshape(kk, cout).contiguous()  # [k][co]
+        wk = ctx.cache.get("wk") if ctx.cache is not None else None
+        if wk is None:
+            wk = weight.detach().reshape(cout, dg, cpg, 9).permute(1, 3, 2, 0).reshape(kk, cout).contiguous()  # [k][co]
+            if ctx.cache is not None:
+                ctx.cache["wk"] = wk
         dx = torch.zeros(n, h, w, c, **f32)
         doff = torch.empty(n, h, w, dg * 18, **f32)
         dmask = torch.empty(n, h, w, dg * 9, **f32)
@@ -176,12 +197,12 @@ class DCNv2Fn(torch.autograd.Function):
         _chk(K, K.lib().crfp_dcn_v2_bwd(C.byref(d), K.stream()), "dcn_v2_bwd")
         dW = dwk.view(dg, 9, cpg, cout).permute(3, 0, 2, 1).reshape(cout, c, 3, 3)
         ng = ctx.needs_input_grad
-        return (None, None, dx if ng[2] else None, doff if ng[3] else None, dmask if ng[4] else None,
-                dW if ng[5] else None, dbias if ng[6] else None)
+        return (None, None, None, dx if ng[3] else None, doff if ng[4] else None, dmask if ng[5] else None,
+                dW if ng[6] else None, dbias if ng[7] else None)
 
 
-def dcn_v2(K, x, offset, mask, weight, bias, dg):
-    return DCNv2Fn.apply(K, dg, x, offset, mask, weight, bias)
+def dcn_v2(K, x, offset, mask, weight, bias, dg, cache=None):
+    return DCNv2Fn.apply(K, dg, cache, x, offset, mask, weight, bias)
 
 
 # ----------------------------------------------------------------------------------------------- flow_warp

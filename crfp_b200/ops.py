@@ -135,7 +135,7 @@ class DCNv2(nn.Module):
 
 
 def conv3x3_nhwc(srcs, weight, bias, act=L.ACT_NONE, residual=None, shuffle_r=0, post_scale=1.0, split=None,
-                 flow=None, head_split=0, head_mag=10.0, modes=None):
+                 flow=None, head_split=0, head_mag=10.0, modes=None, packed=None):
     """3x3 conv over the channel concat of NHWC `srcs` with an OIHW weight; returns NHWC output(s).
 
     split=(c0, c1): route the first c0 output channels to one tensor and the next c1 to another.
@@ -149,7 +149,7 @@ def conv3x3_nhwc(srcs, weight, bias, act=L.ACT_NONE, residual=None, shuffle_r=0,
         c_list.append(s.shape[-1] * 16 if m == L.SRC_UNSHUFFLE4 else s.shape[-1])
     h, w = (srcs[0].shape[1], srcs[0].shape[2]) if modes[0] == 0 else (srcs[0].shape[1] // 4, srcs[0].shape[2] // 4)
     cout = weight.shape[0]
-    wp, bp = pack_conv(weight, bias, c_list, modes)
+    wp, bp = packed if packed is not None else pack_conv(weight, bias, c_list, modes)   # `packed`: a caller-side cache
     assert wp.shape[1] == cin_packed(c_list) and wp.shape[2] == cout_packed(cout)
     d = L.ConvDesc()
     d.n, d.h, d.w, d.nsrc = n, h, w, len(srcs)

@@ -40,15 +40,27 @@ class _Net:
         self.K = K
         self.C = model.mid_channels
         self.max_mag = float(model.max_residue_magnitude)
+        # per-step caches (this object lives for ONE forward/backward, during which the weights are constant): packed
+        # weight layouts per layer, and the concatenated head weights (one torch.cat node per step, not per frame)
+        self._cache = {}
+        self._cat = {}
+
+    def _layer_cache(self, key, srcs):
+        return self._cache.setdefault((key, tuple(s.shape[-1] for s in srcs)), {})
 
     def conv(self, name, srcs, act=A.ACT_NONE):
-        return A.conv3x3(self.K, self.p[name + ".weight"], self.p[name + ".bias"], list(srcs), act)
+        srcs = list(srcs)
+        return A.conv3x3(self.K, self.p[name + ".weight"], self.p[name + ".bias"], srcs, act, self._layer_cache(name, srcs))
 
     def conv_cat(self, names, srcs, act=A.ACT_NONE):
         """one conv over the concatenated output channels of several reference convs sharing an input"""
-        w = torch.cat([self.p[n + ".weight"] for n in names], dim=0)
-        b = torch.cat([self.p[n + ".bias"] for n in names], dim=0)
-        return A.conv3x3(self.K, w, b, list(srcs), act)
+        key = tuple(names)
+        if key not in self._cat:
+            self._cat[key] = (torch.cat([self.p[n + ".weight"] for n in names], dim=0),
+                              torch.cat([self.p[n + ".bias"] for n in names], dim=0))
+        w, b = self._cat[key]
+        srcs = list(srcs)
+        return A.conv3x3(self.K, w, b, srcs, act, self._layer_cache(key, srcs))
 
     # ---- ResidualBlocksWithInputConv (model/CRFP.py:433-552): conv+LReLU, then x + conv2(relu(conv1(x)))
     def res_blocks(self, name, srcs):
@@ -74,7 +86,8 @@ class _Net:
             mask = mask.repeat(1, 1, 1, 9)
         else:
             offset = offset + fyx.repeat(1, 1, 1, offset.shape[-1] // 2)
-        out = A.dcn_v2(self.K, pre_x, offset, mask, self.p[name + ".dcn.weight"], self.p[name + ".dcn.bias"], dg)
+        out = A.dcn_v2(self.K, pre_x, offset, mask, self.p[name + ".dcn.weight"], self.p[name + ".dcn.bias"], dg,
+                       self._cache.setdefault((name + ".dcn", dg), {}))
         return out, z
 
     # ---- FNet.forward (model/CRFP.py:797-814) on pairs (x1, x2) NHWC 3-channel

@@ -72,14 +72,14 @@ class HostEmuKernelSet:
     def _nhwc(x):
         return x.permute(0, 2, 3, 1).contiguous()
 
-    def conv3x3(self, srcs, weight, bias, act):
+    def conv3x3(self, srcs, weight, bias, act, cache=None):
         import torch
         import torch.nn.functional as F
         y = F.conv2d(self._nchw(torch.cat(list(srcs), dim=-1)), weight, bias, padding=1)
         y = F.leaky_relu(y, 0.1) if act == 1 else F.relu(y) if act == 2 else y
         return self._nhwc(y)
 
-    def dcn_v2(self, x, offset, mask, weight, bias, dg):
+    def dcn_v2(self, x, offset, mask, weight, bias, dg, cache=None):
         from oracle import crfp_oracle as O
         return self._nhwc(O.dcn_v2(self._nchw(x), self._nchw(offset), self._nchw(mask), weight, bias, dg))
 
