@@ -95,7 +95,7 @@ class DcnBwdDesc(C.Structure):
                 ("c", C.c_int32), ("cout", C.c_int32), ("dg", C.c_int32),
                 ("x", C.c_void_p), ("offset", C.c_void_p), ("mask", C.c_void_p), ("weight", C.c_void_p),
                 ("dout", C.c_void_p), ("dx", C.c_void_p), ("doffset", C.c_void_p), ("dmask", C.c_void_p),
-                ("dweight", C.c_void_p), ("dbias", C.c_void_p), ("col", C.c_void_p)]
+                ("dweight", C.c_void_p), ("dbias", C.c_void_p), ("col", C.c_void_p), ("weight_t", C.c_void_p)]
 
 
 class Layer(C.Structure):
@@ -186,8 +186,8 @@ SYMBOLS = {
     "crfp_sizeof_dsv_frame_desc": (C.c_size_t, []),
     # training: backward kernels, loss, optimiser (bwd.cu)
     "crfp_act_bwd": (C.c_int, [C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "crfp_conv3x3_bwd_data": (C.c_int, [C.c_int] * 5 + [C.c_void_p] * 4),
-    "crfp_conv3x3_bwd_weight": (C.c_int, [C.c_int] * 5 + [C.c_void_p] * 5),
+    "crfp_conv3x3_bwd_data": (C.c_int, [C.c_int] * 7 + [C.c_void_p] * 4),
+    "crfp_conv3x3_bwd_weight": (C.c_int, [C.c_int] * 7 + [C.c_void_p] * 5),
     "crfp_dcn_v2_bwd": (C.c_int, [C.POINTER(DcnBwdDesc), C.c_void_p]),
     "crfp_sizeof_dcn_bwd_desc": (C.c_size_t, []),
     "crfp_flow_warp_bwd": (C.c_int, [C.c_int] * 4 + [C.c_void_p] * 6),

@@ -129,20 +129,22 @@ class Conv3x3Fn(torch.autograd.Function):
                 w_t = weight.detach().permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous()  # [tap][co][ci]
                 if ctx.cache is not None:
                     ctx.cache["w_t"] = w_t
-            dx = torch.empty(n, h, w, cin, device=dy.device, dtype=torch.float32)
-            _chk(K, lib.crfp_conv3x3_bwd_data(n, h, w, cin, cout, g.data_ptr(), w_t.data_ptr(), dx.data_ptr(), st),
-                 "conv3x3_bwd_data")
             off = 0
-            for i, c in enumerate(ctx.c_list):
+            for i, c in enumerate(ctx.c_list):      # one launch per source of the concat: dense per-source gradients
                 if ctx.needs_input_grad[5 + i]:
-                    dxs[i] = dx[..., off:off + c]
+                    dxs[i] = torch.empty(n, h, w, c, device=dy.device, dtype=torch.float32)
+                    _chk(K, lib.crfp_conv3x3_bwd_data(n, h, w, c, cout, cin, off, g.data_ptr(), w_t.data_ptr(),
+                                                      dxs[i].data_ptr(), st), "conv3x3_bwd_data")
                 off += c
         if need_w or need_b:
-            x = srcs[0] if len(srcs) == 1 else torch.cat(srcs, dim=-1)
             dw = torch.zeros(9, cin, cout, device=dy.device, dtype=torch.float32)
             dbt = torch.zeros(cout, device=dy.device, dtype=torch.float32)
-            _chk(K, lib.crfp_conv3x3_bwd_weight(n, h, w, cin, cout, x.data_ptr(), g.data_ptr(), dw.data_ptr(),
-                                                dbt.data_ptr(), st), "conv3x3_bwd_weight")
+            off = 0
+            for i, c in enumerate(ctx.c_list):
+                _chk(K, lib.crfp_conv3x3_bwd_weight(n, h, w, c, cout, cin, off, srcs[i].data_ptr(), g.data_ptr(),
+                                                    dw.data_ptr(), dbt.data_ptr() if i == 0 else None, st),
+                     "conv3x3_bwd_weight")
+                off += c
             if need_w:
                 dW = dw.permute(2, 1, 0).reshape(cout, cin, 3, 3)
             if need_b:
@@ -182,8 +184,10 @@ class DCNv2Fn(torch.autograd.Function):
         wk = ctx.cache.get("wk") if ctx.cache is not None else None
         if wk is None:
             wk = weight.detach().reshape(cout, dg, cpg, 9).permute(1, 3, 2, 0).reshape(kk, cout).contiguous()  # [k][co]
+            wk = (wk, wk.t().contiguous())                                                                      # + [co][k]
             if ctx.cache is not None:
                 ctx.cache["wk"] = wk
+        wk, wk_t = wk
         dx = torch.zeros(n, h, w, c, **f32)
         doff = torch.empty(n, h, w, dg * 18, **f32)
         dmask = torch.empty(n, h, w, dg * 9, **f32)
@@ -193,7 +197,7 @@ class DCNv2Fn(torch.autograd.Function):
         d = L.DcnBwdDesc(n=n, h=h, w=w, c=c, cout=cout, dg=dg, x=x.data_ptr(), offset=offset.data_ptr(),
                          mask=mask.data_ptr(), weight=wk.data_ptr(), dout=dout.data_ptr(), dx=dx.data_ptr(),
                          doffset=doff.data_ptr(), dmask=dmask.data_ptr(), dweight=dwk.data_ptr(),
-                         dbias=dbias.data_ptr(), col=col.data_ptr())
+                         dbias=dbias.data_ptr(), col=col.data_ptr(), weight_t=wk_t.data_ptr())
         _chk(K, K.lib().crfp_dcn_v2_bwd(C.byref(d), K.stream()), "dcn_v2_bwd")
         dW = dwk.view(dg, 9, cpg, cout).permute(3, 0, 2, 1).reshape(cout, c, 3, 3)
         ng = ctx.needs_input_grad

@@ -35,10 +35,11 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(long long count, int act, 
 }
 
 // ------------------------------------------------------------------------------------------------ 3x3 conv, data
-// dx[b,y,x,ci] = sum_{ky,kx,co} g[b, y+1-ky, x+1-kx, co] * W[co,ci,ky,kx];  wt_t = [tap][co][ci] (ci fastest, so
-// that the threads of one pixel read consecutive weights; g[.., co] is a warp-wide broadcast).
-__global__ void __launch_bounds__(256) conv3x3_bwd_data_kernel(int n, int h, int w, int cin, int cout,
-                                                               const float* __restrict__ g,
+// dx[b,y,x,ci] = sum_{ky,kx,co} g[b, y+1-ky, x+1-kx, co] * W[co,cin_off+ci,ky,kx];  wt_t = [tap][co][cin_total] (ci
+// fastest, so that the threads of one pixel read consecutive weights; g[.., co] is a warp-wide broadcast).  One call
+// produces the gradient of ONE source of the forward's channel concat (channels [cin_off, cin_off+cin) of the weight).
+__global__ void __launch_bounds__(256) conv3x3_bwd_data_kernel(int n, int h, int w, int cin, int cout, int cin_total,
+                                                               int cin_off, const float* __restrict__ g,
                                                                const float* __restrict__ wt_t, float* __restrict__ dx) {
   const long long total = (long long)n * h * w * cin;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -56,8 +57,9 @@ __global__ void __launch_bounds__(256) conv3x3_bwd_data_kernel(int n, int h, int
       const int xo = x + 1 - kx;
       if (xo < 0 || xo >= w) continue;
       const float* gp = g + ((b * h + yo) * w + xo) * cout;
-      const float* wp = wt_t + (long long)(ky * 3 + kx) * cout * cin + ci;
-      for (int co = 0; co < cout; ++co) acc += gp[co] * wp[(long long)co * cin];
+      const float* wp = wt_t + (long long)(ky * 3 + kx) * cout * cin_total + cin_off + ci;
+#pragma unroll 4
+      for (int co = 0; co < cout; ++co) acc += gp[co] * wp[(long long)co * cin_total];
     }
   }
   dx[idx] = acc;
@@ -65,8 +67,8 @@ __global__ void __launch_bounds__(256) conv3x3_bwd_data_kernel(int n, int h, int
 
 // Register-tiled variant for cin % 4 == 0 and cout % 4 == 0: one thread per (pixel, 4 input channels); per 4 output
 // channels it issues 1 LDG.128 of g (warp broadcast) + 4 LDG.128 of weights (coalesced over ci) for 16 FMAs.
-__global__ void __launch_bounds__(256) conv3x3_bwd_data_v4_kernel(int n, int h, int w, int cin, int cout,
-                                                                  const float* __restrict__ g,
+__global__ void __launch_bounds__(256) conv3x3_bwd_data_v4_kernel(int n, int h, int w, int cin, int cout, int cin_total,
+                                                                  int cin_off, const float* __restrict__ g,
                                                                   const float* __restrict__ wt_t, float* __restrict__ dx) {
   const int cq = cin >> 2;
   const long long total = (long long)n * h * w * cq;
@@ -85,13 +87,14 @@ __global__ void __launch_bounds__(256) conv3x3_bwd_data_v4_kernel(int n, int h, 
       const int xo = x + 1 - kx;
       if (xo < 0 || xo >= w) continue;
       const float* gp = g + ((b * h + yo) * w + xo) * cout;
-      const float* wp = wt_t + (long long)(ky * 3 + kx) * cout * cin + ci;
+      const float* wp = wt_t + (long long)(ky * 3 + kx) * cout * cin_total + cin_off + ci;
+#pragma unroll 2
       for (int co = 0; co < cout; co += 4) {
         const float4 gv = *reinterpret_cast<const float4*>(gp + co);
-        const float4 w0 = *reinterpret_cast<const float4*>(wp + (long long)co * cin);
-        const float4 w1 = *reinterpret_cast<const float4*>(wp + (long long)(co + 1) * cin);
-        const float4 w2 = *reinterpret_cast<const float4*>(wp + (long long)(co + 2) * cin);
-        const float4 w3 = *reinterpret_cast<const float4*>(wp + (long long)(co + 3) * cin);
+        const float4 w0 = *reinterpret_cast<const float4*>(wp + (long long)co * cin_total);
+        const float4 w1 = *reinterpret_cast<const float4*>(wp + (long long)(co + 1) * cin_total);
+        const float4 w2 = *reinterpret_cast<const float4*>(wp + (long long)(co + 2) * cin_total);
+        const float4 w3 = *reinterpret_cast<const float4*>(wp + (long long)(co + 3) * cin_total);
         acc.x += gv.x * w0.x + gv.y * w1.x + gv.z * w2.x + gv.w * w3.x;
         acc.y += gv.x * w0.y + gv.y * w1.y + gv.z * w2.y + gv.w * w3.y;
         acc.z += gv.x * w0.z + gv.y * w1.z + gv.z * w2.z + gv.w * w3.z;
@@ -103,12 +106,14 @@ __global__ void __launch_bounds__(256) conv3x3_bwd_data_v4_kernel(int n, int h, 
 }
 
 // ------------------------------------------------------------------------------------------------ 3x3 conv, weights
-// dw[tap][ci][co] += sum_p x[p + shift(tap)][ci] * g[p][co];  db[co] += sum_p g[p][co].
+// dw[tap][cin_off + ci][co] += sum_p x[p + shift(tap)][ci] * g[p][co];  db[co] += sum_p g[p][co]  (dw = [tap][cin_total]
+// [cout]; one call handles ONE source of the forward's channel concat, so the concat is never materialised).
 // One thread per weight element (co fastest: g loads coalesced, x loads warp-broadcast) and per block of image rows;
 // partial sums meet in dw through atomicAdd.  taps == 1 is the plain (pixels x cin)^T (pixels x cout) product used for
 // the DCN weight gradient (x = the modulated column buffer).
 __global__ void __launch_bounds__(128) conv_bwd_weight_kernel(int rows, int h, int w, int cin, int cout, int taps,
-                                                              int rows_per_block, int xsegs, const float* __restrict__ x,
+                                                              int cin_total, int cin_off, int rows_per_block, int xsegs,
+                                                              const float* __restrict__ x,
                                                               const float* __restrict__ g, float* __restrict__ dw,
                                                               float* __restrict__ db) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -135,16 +140,18 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_kernel(int rows, int h, i
       for (int xx = c0; xx < c1; ++xx) gsum += gp[(long long)xx * cout];
     if (yi < 0 || yi >= h) continue;
     const float* xp = x + (r + (ky - 1)) * w * cin + ci;
+#pragma unroll 4
     for (int xx = xlo; xx < xhi; ++xx) acc += gp[(long long)xx * cout] * xp[(long long)(xx + kx - 1) * cin];
   }
-  atomicAdd(dw + e, acc);
+  atomicAdd(dw + ((long long)tap * cin_total + cin_off + ci) * cout + co, acc);
   if (do_bias) atomicAdd(db + co, gsum);
 }
 
 // Register-tiled variant for cin % 4 == 0 and cout % 4 == 0: one thread per (tap, 4 ci, 4 co) block of dw; per pixel
 // 2 LDG.128 (x: warp broadcast over the co blocks, g: coalesced) feed 16 FMAs.
 __global__ void __launch_bounds__(128) conv_bwd_weight_v4_kernel(int rows, int h, int w, int cin, int cout, int taps,
-                                                                 int rows_per_block, int xsegs, const float* __restrict__ x,
+                                                                 int cin_total, int cin_off, int rows_per_block, int xsegs,
+                                                                 const float* __restrict__ x,
                                                                  const float* __restrict__ g, float* __restrict__ dw,
                                                                  float* __restrict__ db) {
   const int cq = cin >> 2, oq = cout >> 2;
@@ -177,6 +184,7 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_v4_kernel(int rows, int h
       }
     if (yi < 0 || yi >= h) continue;
     const float* xp = x + (r + (ky - 1)) * w * cin + ci;
+#pragma unroll 4
     for (int xx = xlo; xx < xhi; ++xx) {
       const float4 gv = *reinterpret_cast<const float4*>(gp + (long long)xx * cout);
       const float4 xv = *reinterpret_cast<const float4*>(xp + (long long)(xx + kx - 1) * cin);
@@ -186,7 +194,7 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_v4_kernel(int rows, int h
       acc[3][0] += xv.w * gv.x; acc[3][1] += xv.w * gv.y; acc[3][2] += xv.w * gv.z; acc[3][3] += xv.w * gv.w;
     }
   }
-  float* d = dw + ((long long)tap * cin + ci) * cout + co;
+  float* d = dw + ((long long)tap * cin_total + cin_off + ci) * cout + co;
   for (int a = 0; a < 4; ++a)
     for (int c = 0; c < 4; ++c) atomicAdd(d + (long long)a * cout + c, acc[a][c]);
   if (do_bias) {
@@ -196,9 +204,9 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_v4_kernel(int rows, int h
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-static int launch_bwd_weight(long long rows, int h, int w, int cin, int cout, int taps, const float* x, const float* g,
-                             float* dw, float* db, cudaStream_t st) {
-  const bool v4 = (cin % 4 == 0) && (cout % 4 == 0) && aligned16(x) && aligned16(g);
+static int launch_bwd_weight(long long rows, int h, int w, int cin, int cout, int taps, int cin_total, int cin_off,
+                             const float* x, const float* g, float* dw, float* db, cudaStream_t st) {
+  const bool v4 = (cin % 4 == 0) && (cout % 4 == 0) && aligned16(x) && aligned16(g);   // (dw is only touched by atomics)
   const int elems = v4 ? taps * (cin / 4) * (cout / 4) : taps * cin * cout;
   const unsigned gx = blocks_for(elems, 128);
   long long target_y = 8192 / gx;
@@ -217,11 +225,11 @@ static int launch_bwd_weight(long long rows, int h, int w, int cin, int cout, in
   }
   gy *= (unsigned)xsegs;
   if (v4)
-    CRFP_LAUNCH(conv_bwd_weight_v4_kernel, dim3(gx, gy), dim3(128), st, (int)rows, h, w, cin, cout, taps, (int)rpb, xsegs, x, g,
-                dw, db);
+    CRFP_LAUNCH(conv_bwd_weight_v4_kernel, dim3(gx, gy), dim3(128), st, (int)rows, h, w, cin, cout, taps, cin_total, cin_off,
+                (int)rpb, xsegs, x, g, dw, db);
   else
-    CRFP_LAUNCH(conv_bwd_weight_kernel, dim3(gx, gy), dim3(128), st, (int)rows, h, w, cin, cout, taps, (int)rpb, xsegs, x, g, dw,
-                db);
+    CRFP_LAUNCH(conv_bwd_weight_kernel, dim3(gx, gy), dim3(128), st, (int)rows, h, w, cin, cout, taps, cin_total, cin_off,
+                (int)rpb, xsegs, x, g, dw, db);
   return check_launch();
 }
 
@@ -282,6 +290,79 @@ __global__ void __launch_bounds__(128) dcn_bwd_sample_kernel(const crfp_dcn_bwd_
     if (ok10) atomicAdd(D.dx + p10 + ch, gm * ly * hx);
     if (ok11) atomicAdd(D.dx + p11 + ch, gm * ly * lx);
   }
+  D.doffset[pix * gts * 2 + gt * 2] = m * sdy;
+  D.doffset[pix * gts * 2 + gt * 2 + 1] = m * sdx;
+  D.dmask[pix * gts + gt] = sdm;
+}
+
+// Vector variant for C/dg == 4 and cout % 4 == 0 (both CRFP configurations: C=32/dg=8 and C=4/dg=1): the group's 4
+// channels travel as one float4 — corner loads, the column store and the dx scatter (one 16-byte vector atomic per
+// corner instead of 4 scalar ones) — and gcol comes from the TRANSPOSED weight weight_t[co][K]: the lanes of a warp
+// hold consecutive (group, tap) slots, so `weight_t + co*K + gt*4` is one coalesced LDG.128 per output channel (the
+// [K][cout] layout made every lane walk its own 128-byte rows: 32 wavefronts per load, measured 0.95 ms per launch).
+__global__ void __launch_bounds__(128) dcn_bwd_sample_v4_kernel(const crfp_dcn_bwd_desc D) {
+  const int gts = D.dg * 9;
+  const long long total = (long long)D.n * D.h * D.w * gts;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int gt = (int)(idx % gts);
+  const long long pix = idx / gts;
+  const int x = (int)(pix % D.w);
+  const int y = (int)((pix / D.w) % D.h);
+  const long long b = pix / ((long long)D.w * D.h);
+  const int t = gt % 9, g = gt / 9, i = t / 3, j = t - i * 3;
+  const int K = gts * 4;
+  const float oy = D.offset[pix * gts * 2 + gt * 2], ox = D.offset[pix * gts * 2 + gt * 2 + 1];
+  const float m = D.mask[pix * gts + gt];
+  const float py = (float)(y - 1 + i) + oy, px = (float)(x - 1 + j) + ox;
+  const float fy = floorf(py), fx = floorf(px);
+  const int y0 = (int)fy, x0 = (int)fx;
+  const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
+  const bool inside = (py > -1.f) && (py < (float)D.h) && (px > -1.f) && (px < (float)D.w);
+  const bool vy0 = inside && y0 >= 0, vy1 = inside && (y0 + 1 <= D.h - 1);
+  const bool vx0 = x0 >= 0, vx1 = (x0 + 1 <= D.w - 1);
+  const bool ok00 = vy0 && vx0, ok01 = vy0 && vx1, ok10 = vy1 && vx0, ok11 = vy1 && vx1;
+  const long long img = b * D.h * D.w;
+  const int ch = g * 4;
+  const long long p00 = (img + (long long)y0 * D.w + x0) * D.c + ch, p01 = p00 + D.c;
+  const long long p10 = p00 + (long long)D.w * D.c, p11 = p10 + D.c;
+  const float* dout = D.dout + pix * D.cout;
+  const float* wt = D.weight_t + gt * 4;
+  float4 gc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+  for (int co = 0; co < D.cout; co += 4) {
+    const float4 dv = *reinterpret_cast<const float4*>(dout + co);
+    const float4 w0 = *reinterpret_cast<const float4*>(wt + (long long)co * K);
+    const float4 w1 = *reinterpret_cast<const float4*>(wt + (long long)(co + 1) * K);
+    const float4 w2 = *reinterpret_cast<const float4*>(wt + (long long)(co + 2) * K);
+    const float4 w3 = *reinterpret_cast<const float4*>(wt + (long long)(co + 3) * K);
+    gc.x += w0.x * dv.x + w1.x * dv.y + w2.x * dv.z + w3.x * dv.w;
+    gc.y += w0.y * dv.x + w1.y * dv.y + w2.y * dv.z + w3.y * dv.w;
+    gc.z += w0.z * dv.x + w1.z * dv.y + w2.z * dv.z + w3.z * dv.w;
+    gc.w += w0.w * dv.x + w1.w * dv.y + w2.w * dv.z + w3.w * dv.w;
+  }
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 v00 = ok00 ? *reinterpret_cast<const float4*>(D.x + p00) : z4;
+  const float4 v01 = ok01 ? *reinterpret_cast<const float4*>(D.x + p01) : z4;
+  const float4 v10 = ok10 ? *reinterpret_cast<const float4*>(D.x + p10) : z4;
+  const float4 v11 = ok11 ? *reinterpret_cast<const float4*>(D.x + p11) : z4;
+  const float w00 = hy * hx, w01 = hy * lx, w10 = ly * hx, w11 = ly * lx;
+  float4 val;
+  val.x = w00 * v00.x + w01 * v01.x + w10 * v10.x + w11 * v11.x;
+  val.y = w00 * v00.y + w01 * v01.y + w10 * v10.y + w11 * v11.y;
+  val.z = w00 * v00.z + w01 * v01.z + w10 * v10.z + w11 * v11.z;
+  val.w = w00 * v00.w + w01 * v01.w + w10 * v10.w + w11 * v11.w;
+  *reinterpret_cast<float4*>(D.col + pix * K + gt * 4) = make_float4(m * val.x, m * val.y, m * val.z, m * val.w);
+  const float sdm = gc.x * val.x + gc.y * val.y + gc.z * val.z + gc.w * val.w;
+  const float sdy = gc.x * (hx * (v10.x - v00.x) + lx * (v11.x - v01.x)) + gc.y * (hx * (v10.y - v00.y) + lx * (v11.y - v01.y)) +
+                    gc.z * (hx * (v10.z - v00.z) + lx * (v11.z - v01.z)) + gc.w * (hx * (v10.w - v00.w) + lx * (v11.w - v01.w));
+  const float sdx = gc.x * (hy * (v01.x - v00.x) + ly * (v11.x - v10.x)) + gc.y * (hy * (v01.y - v00.y) + ly * (v11.y - v10.y)) +
+                    gc.z * (hy * (v01.z - v00.z) + ly * (v11.z - v10.z)) + gc.w * (hy * (v01.w - v00.w) + ly * (v11.w - v10.w));
+  const float4 gm = make_float4(gc.x * m, gc.y * m, gc.z * m, gc.w * m);
+  if (ok00) atomicAdd(reinterpret_cast<float4*>(D.dx + p00), make_float4(gm.x * w00, gm.y * w00, gm.z * w00, gm.w * w00));
+  if (ok01) atomicAdd(reinterpret_cast<float4*>(D.dx + p01), make_float4(gm.x * w01, gm.y * w01, gm.z * w01, gm.w * w01));
+  if (ok10) atomicAdd(reinterpret_cast<float4*>(D.dx + p10), make_float4(gm.x * w10, gm.y * w10, gm.z * w10, gm.w * w10));
+  if (ok11) atomicAdd(reinterpret_cast<float4*>(D.dx + p11), make_float4(gm.x * w11, gm.y * w11, gm.z * w11, gm.w * w11));
   D.doffset[pix * gts * 2 + gt * 2] = m * sdy;
   D.doffset[pix * gts * 2 + gt * 2 + 1] = m * sdx;
   D.dmask[pix * gts + gt] = sdm;
@@ -439,29 +520,30 @@ extern "C" int crfp_act_bwd(long long count, int act, const float* dy, const flo
   return check_launch();
 }
 
-extern "C" int crfp_conv3x3_bwd_data(int n, int h, int w, int cin, int cout, const float* g, const float* weight_t,
-                                     float* dx, crfp_stream stream) {
-  if (n < 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0) return CRFP_ERR_BAD_SHAPE;
+extern "C" int crfp_conv3x3_bwd_data(int n, int h, int w, int cin, int cout, int cin_total, int cin_off, const float* g,
+                                     const float* weight_t, float* dx, crfp_stream stream) {
+  if (n < 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || cin_off < 0 || cin_off + cin > cin_total) return CRFP_ERR_BAD_SHAPE;
   if (n == 0) return CRFP_OK;
   if (!g || !weight_t || !dx) return CRFP_ERR_NULL;
-  if (cin % 4 == 0 && cout % 4 == 0 && aligned16(g) && aligned16(weight_t) && aligned16(dx)) {
+  if (cin % 4 == 0 && cout % 4 == 0 && cin_total % 4 == 0 && cin_off % 4 == 0 && aligned16(g) && aligned16(weight_t) &&
+      aligned16(dx)) {
     const long long total4 = (long long)n * h * w * (cin / 4);
     CRFP_LAUNCH(conv3x3_bwd_data_v4_kernel, dim3(blocks_for(total4, 256)), dim3(256), (cudaStream_t)stream, n, h, w, cin, cout,
-                g, weight_t, dx);
+                cin_total, cin_off, g, weight_t, dx);
     return check_launch();
   }
   const long long total = (long long)n * h * w * cin;
-  CRFP_LAUNCH(conv3x3_bwd_data_kernel, dim3(blocks_for(total, 256)), dim3(256), (cudaStream_t)stream, n, h, w, cin, cout, g,
-              weight_t, dx);
+  CRFP_LAUNCH(conv3x3_bwd_data_kernel, dim3(blocks_for(total, 256)), dim3(256), (cudaStream_t)stream, n, h, w, cin, cout,
+              cin_total, cin_off, g, weight_t, dx);
   return check_launch();
 }
 
-extern "C" int crfp_conv3x3_bwd_weight(int n, int h, int w, int cin, int cout, const float* x, const float* g, float* dw,
-                                       float* db, crfp_stream stream) {
-  if (n < 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0) return CRFP_ERR_BAD_SHAPE;
+extern "C" int crfp_conv3x3_bwd_weight(int n, int h, int w, int cin, int cout, int cin_total, int cin_off, const float* x,
+                                       const float* g, float* dw, float* db, crfp_stream stream) {
+  if (n < 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || cin_off < 0 || cin_off + cin > cin_total) return CRFP_ERR_BAD_SHAPE;
   if (n == 0) return CRFP_OK;
   if (!x || !g || !dw) return CRFP_ERR_NULL;
-  return launch_bwd_weight((long long)n * h, h, w, cin, cout, 9, x, g, dw, db, (cudaStream_t)stream);
+  return launch_bwd_weight((long long)n * h, h, w, cin, cout, 9, cin_total, cin_off, x, g, dw, db, (cudaStream_t)stream);
 }
 
 extern "C" int crfp_dcn_v2_bwd(const crfp_dcn_bwd_desc* d, crfp_stream stream) {
@@ -472,11 +554,16 @@ extern "C" int crfp_dcn_v2_bwd(const crfp_dcn_bwd_desc* d, crfp_stream stream) {
   if (!d->x || !d->offset || !d->mask || !d->weight || !d->dout || !d->dx || !d->doffset || !d->dmask || !d->col || !d->dweight)
     return CRFP_ERR_NULL;
   const long long total = (long long)d->n * d->h * d->w * d->dg * 9;
-  CRFP_LAUNCH(dcn_bwd_sample_kernel, dim3(blocks_for(total, 128)), dim3(128), (cudaStream_t)stream, *d);
+  const bool v4 = d->weight_t != nullptr && d->c == 4 * d->dg && d->cout % 4 == 0 && aligned16(d->x) && aligned16(d->dx) &&
+                  aligned16(d->dout) && aligned16(d->col) && aligned16(d->weight_t);
+  if (v4)
+    CRFP_LAUNCH(dcn_bwd_sample_v4_kernel, dim3(blocks_for(total, 128)), dim3(128), (cudaStream_t)stream, *d);
+  else
+    CRFP_LAUNCH(dcn_bwd_sample_kernel, dim3(blocks_for(total, 128)), dim3(128), (cudaStream_t)stream, *d);
   CRFP_TRY(check_launch());
   // dweight[k][co] += col^T dout, dbias[co] += sum dout
-  return launch_bwd_weight((long long)d->n * d->h, d->h, d->w, 9 * d->c, d->cout, 1, d->col, d->dout, d->dweight, d->dbias,
-                           (cudaStream_t)stream);
+  return launch_bwd_weight((long long)d->n * d->h, d->h, d->w, 9 * d->c, d->cout, 1, 9 * d->c, 0, d->col, d->dout, d->dweight,
+                           d->dbias, (cudaStream_t)stream);
 }
 
 extern "C" int crfp_flow_warp_bwd(int n, int h, int w, int c, const float* x, const float* flow, const float* dy,

@@ -31,8 +31,14 @@ def annealing_cos(start, end, factor, weight=1.0):
 
 class Trainer:
     def __init__(self, model, lr_rate=2e-4, lr_rate_flow=2.5e-5, beta1=0.9, beta2=0.999, eps=1e-12, rec_w=1.0,
-                 period=600000, min_lr=1e-7, freeze_flow_iters=5000, process_group=None, kernels=None):
+                 period=600000, min_lr=1e-7, freeze_flow_iters=5000, process_group=None, kernels=None, use_graphs=False):
         self.model = model
+        # use_graphs: capture forward + loss + backward of a step into ONE CUDA graph (per input shape and FNet-freeze
+        # phase; captured on the third step of a kind, after two eager ones) and replay it afterwards: a step is
+        # ~2 000 small launches plus the autograd tape, i.e. host-bound when launched eagerly.  The gradient
+        # all-reduce and the two Adam launches stay outside the graph (their scalars change every iteration).
+        self.use_graphs = use_graphs
+        self._graphs, self._seen = {}, {}
         self.K = kernels or A.CUDA
         self.betas, self.eps, self.rec_w = (beta1, beta2), eps, rec_w
         self.period, self.min_lr, self.freeze_flow_iters = period, min_lr, freeze_flow_iters
@@ -75,20 +81,15 @@ class Trainer:
     def step(self, lrs, fvs, mks, hr):
         """One iteration on this rank's clips: lrs (n,t,3,h,w), fvs (n,t,3,8h,8w), mks (n,t,1,8h,8w) bool,
         hr (n,t,3,8h,8w).  Returns the (detached) loss tensor of this rank."""
-        K, model = self.K, self.model
+        model = self.model
         model.train()
         train_flow = self._set_flow_trainable()
         self.lr = [self.get_lr(b) for b in self.base_lr]            # before_train_iter
-        sr = forward_train(model, lrs, fvs, mks, K)
-        b, n, c, h, w = sr.shape
-        loss = A.charbonnier_loss(K, sr.reshape(b * n, c, h, w), hr.reshape(b * n, c, h, w).to(torch.float32), 1e-12,
-                                  self.rec_w)
-        self.flat_g.zero_()                                          # optimizer.zero_grad()
         for grp in self.group_params:                                # keep every .grad a view of the flat bucket
             for p in grp:
                 if p.grad is None:
                     raise RuntimeError("a parameter lost its flat gradient view")
-        loss.backward()
+        loss = self._fwd_bwd_graphed(lrs, fvs, mks, hr, train_flow) if self.use_graphs else self._fwd_bwd(lrs, fvs, mks, hr)
         if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             ws = torch.distributed.get_world_size(self.pg)
             if ws > 1:                                               # ONE all-reduce of the 9.14 MB bucket
@@ -99,7 +100,42 @@ class Trainer:
         model._packed = None                                         # inference-side packed weights are stale now
         if hasattr(model, "_graphs"):
             model._graphs.clear()
+        return loss
+
+    def _fwd_bwd(self, lrs, fvs, mks, hr):
+        K = self.K
+        sr = forward_train(self.model, lrs, fvs, mks, K)
+        b, n, c, h, w = sr.shape
+        loss = A.charbonnier_loss(K, sr.reshape(b * n, c, h, w), hr.reshape(b * n, c, h, w).to(torch.float32), 1e-12,
+                                  self.rec_w)
+        self.flat_g.zero_()                                          # optimizer.zero_grad()
+        loss.backward()
         return loss.detach()
+
+    def _fwd_bwd_graphed(self, lrs, fvs, mks, hr, train_flow):
+        batch = (lrs, fvs, mks, hr)
+        key = (tuple((tuple(t_.shape), t_.dtype) for t_ in batch), str(lrs.device), train_flow)
+        entry = self._graphs.get(key)
+        if entry is None:
+            self._seen[key] = self._seen.get(key, 0) + 1
+            if self._seen[key] < 3:                                  # eager warm-ups (allocator, packing caches, autotune-free)
+                return self._fwd_bwd(*batch)
+            try:
+                static = [t_.detach().clone() for t_ in batch]
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    loss = self._fwd_bwd(*static)
+                entry = self._graphs[key] = dict(graph=g, static=static, loss=loss)
+            except Exception as e:  # noqa: BLE001
+                import warnings
+                warnings.warn(f"crfp_b200.Trainer: CUDA graph capture failed ({e}); continuing without graphs")
+                self.use_graphs = False
+                return self._fwd_bwd(*batch)
+        for dst, src in zip(entry["static"], batch):
+            dst.copy_(src, non_blocking=True)
+        entry["graph"].replay()
+        return entry["loss"].clone()
 
     def _adam(self, train_flow):
         lib, st = self.K.lib(), self.K.stream()

@@ -437,12 +437,15 @@ size_t crfp_sizeof_dsv_frame_desc(void);
  */
 /* g = dy * act'(v), act in {CRFP_ACT_LRELU, CRFP_ACT_RELU}; the sign of v is taken from the saved forward output */
 int crfp_act_bwd(long long count, int act, const float* dy, const float* out, float* g, crfp_stream stream);
-/* nn.Conv2d(3x3,s1,p1) backward-data: dx[n,h,w,cin] from g[n,h,w,cout]; weight_t = [tap][cout][cin], tap = ky*3+kx */
-int crfp_conv3x3_bwd_data(int n, int h, int w, int cin, int cout, const float* g, const float* weight_t, float* dx,
-                          crfp_stream stream);
-/* backward-weight: dw[tap][cin][cout] (accumulated), db[cout] (accumulated, may be NULL) from x[n,h,w,cin], g[n,h,w,cout] */
-int crfp_conv3x3_bwd_weight(int n, int h, int w, int cin, int cout, const float* x, const float* g, float* dw, float* db,
-                            crfp_stream stream);
+/* nn.Conv2d(3x3,s1,p1) backward for ONE source of the forward's channel concat (the concat is never materialised):
+ * the source owns input channels [cin_off, cin_off + cin) of the layer's cin_total.
+ * backward-data: dx[n,h,w,cin] (dense, overwritten) from g[n,h,w,cout]; weight_t = [tap][cout][cin_total], tap = ky*3+kx */
+int crfp_conv3x3_bwd_data(int n, int h, int w, int cin, int cout, int cin_total, int cin_off, const float* g,
+                          const float* weight_t, float* dx, crfp_stream stream);
+/* backward-weight: rows [cin_off, cin_off+cin) of dw[tap][cin_total][cout] (accumulated) from x[n,h,w,cin] (dense) and
+ * g[n,h,w,cout]; db[cout] (accumulated; pass it with one source only, NULL otherwise) */
+int crfp_conv3x3_bwd_weight(int n, int h, int w, int cin, int cout, int cin_total, int cin_off, const float* x,
+                            const float* g, float* dw, float* db, crfp_stream stream);
 /*
  * DCNv2 backward (= dcn_v2_backward): non-shared layout only (offset dg*18, mask dg*9 channels per pixel).
  *   weight   [K][cout], K = 9*c, k = (g*9+t)*(c/dg) + c_in_group (crfp_dcn_v2_fwd packing with cout % 4 == 0)
@@ -450,6 +453,7 @@ int crfp_conv3x3_bwd_weight(int n, int h, int w, int cin, int cout, const float*
  *   doffset  [n,h,w,dg*18], dmask [n,h,w,dg*9]   overwritten
  *   dweight  [K][cout]      accumulated;  dbias [cout] accumulated (may be NULL)
  *   col      workspace [n*h*w][K] floats: the modulated columns, rebuilt here and contracted with dout
+ *   weight_t optional [cout][K] transpose of `weight`: enables the vector kernel when c == 4*dg and cout % 4 == 0
  */
 typedef struct {
   int32_t n, h, w;
@@ -465,6 +469,7 @@ typedef struct {
   float* dweight;
   float* dbias;
   float* col;
+  const float* weight_t;
 } crfp_dcn_bwd_desc;
 int crfp_dcn_v2_bwd(const crfp_dcn_bwd_desc* d, crfp_stream stream);
 size_t crfp_sizeof_dcn_bwd_desc(void);

@@ -34,8 +34,9 @@ def test_emulation_exports_every_training_symbol():
         assert hasattr(h, name)
     assert len(L.TRAIN_SYMBOLS) == 10
     # argument validation returns a status, never crashes
-    assert h.crfp_conv3x3_bwd_data(1, 0, 4, 4, 4, None, None, None, None) == -1
-    assert h.crfp_conv3x3_bwd_data(1, 4, 4, 4, 4, None, None, None, None) == -5
+    assert h.crfp_conv3x3_bwd_data(1, 0, 4, 4, 4, 4, 0, None, None, None, None) == -1
+    assert h.crfp_conv3x3_bwd_data(1, 4, 4, 4, 4, 6, 4, None, None, None, None) == -1      # slice outside cin_total
+    assert h.crfp_conv3x3_bwd_data(1, 4, 4, 4, 4, 4, 0, None, None, None, None) == -5
     assert h.crfp_act_bwd(4, 0, None, None, None, None) == -2
     assert h.crfp_dcn_v2_bwd(None, None) == -5
     d = L.DcnBwdDesc(n=1, h=4, w=4, c=6, cout=4, dg=4)

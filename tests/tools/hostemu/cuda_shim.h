@@ -29,6 +29,9 @@ static inline float4 make_float4(float x, float y, float z, float w) { float4 r;
 static thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 static inline float atomicAdd(float* p, float v) { const float o = *p; *p = o + v; return o; }
+static inline float4 atomicAdd(float4* p, float4 v) {  // sm_90+ vector atomic (red.global.add.v4.f32)
+  const float4 o = *p; p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w; return o;
+}
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
