@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--shape", default="v7", choices=["v7", "crop", "tiny"])
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--graphs", action="store_true", help="replay forward+backward from one captured CUDA graph per step")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -39,7 +40,9 @@ def main():
     model = CRFP_DSV("cuda", mid_channels=32)
     model.load_state_dict(make_state_dict(seed=1), strict=True)
     model.cuda()
-    tr = Trainer(model, freeze_flow_iters=0)          # FNet trains from the first step: the full backward is timed
+    tr = Trainer(model, freeze_flow_iters=0, use_graphs=args.graphs)   # FNet trains from step 0: the full backward is timed
+    if args.graphs:
+        args.warmup = max(args.warmup, 4)             # two eager steps, the capture, one replay
     lrs, fvs, mks, _ = make_clip(seed=2 + rank, n=n, t=t, h=h, w=w, fv_size=fv)
     hr = torch.rand(n, t, 3, 8 * h, 8 * w, generator=torch.Generator().manual_seed(3 + rank))
     batch = (lrs.cuda(), fvs.cuda(), mks.cuda(), hr.cuda())
@@ -66,7 +69,8 @@ def main():
             "metric": "training frames/sec (forward + backward + all-reduce + Adam)",
             "value": world * n * t * args.steps / sec, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms.item() / args.steps, "higher_is_better": True, "scaling": "weak",
-            "dtype": "fp32", "data": "synthetic", "gpu_launches": int(_lib.lib().crfp_launch_count()),
+            "dtype": "fp32", "data": "synthetic", "cuda_graph": bool(args.graphs and tr.use_graphs and tr._graphs),
+            "gpu_launches": int(_lib.lib().crfp_launch_count()),
             "config": {"workload": f"{args.shape}: n={n} clips/GPU, t={t}, LR {h}x{w} -> {8 * h}x{8 * w}, FV {fv}",
                        "params": int(tr.flat_p.numel()), "grad_bucket_bytes": int(tr.flat_g.numel() * 4)},
             "loss_first_last": [losses[0], losses[-1]],
