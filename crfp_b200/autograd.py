@@ -18,6 +18,7 @@ suite injects its own kernel set built from a host emulation of bwd.cu, see test
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -30,6 +31,9 @@ class KernelSet:
     """Forward primitives + the C-ABI handle whose crfp_*_bwd entry points the Functions below call."""
 
     name = "cuda"
+    # backward-data through the tiled forward conv kernel (default) or the direct gather kernel crfp_conv3x3_bwd_data
+    # (CRFP_DGRAD=direct; kept for A/B and for shapes the forward kernel would not take)
+    dgrad_as_conv = os.environ.get("CRFP_DGRAD", "conv") != "direct"
 
     def lib(self):
         return L.lib()
@@ -124,18 +128,33 @@ class Conv3x3Fn(torch.autograd.Function):
         dW = db = None
         dxs = [None] * len(srcs)
         if need_x:
-            w_t = ctx.cache.get("w_t") if ctx.cache is not None else None
-            if w_t is None:
-                w_t = weight.detach().permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous()  # [tap][co][ci]
-                if ctx.cache is not None:
-                    ctx.cache["w_t"] = w_t
+            cache = ctx.cache if ctx.cache is not None else {}
             off = 0
-            for i, c in enumerate(ctx.c_list):      # one launch per source of the concat: dense per-source gradients
-                if ctx.needs_input_grad[5 + i]:
-                    dxs[i] = torch.empty(n, h, w, c, device=dy.device, dtype=torch.float32)
-                    _chk(K, lib.crfp_conv3x3_bwd_data(n, h, w, c, cout, cin, off, g.data_ptr(), w_t.data_ptr(),
-                                                      dxs[i].data_ptr(), st), "conv3x3_bwd_data")
-                off += c
+            if K.dgrad_as_conv:
+                # backward-data of a 3x3/s1/p1 conv IS a 3x3/s1/p1 conv of g with the transposed, 180-degree-rotated
+                # kernel: dx[ci] = sum_co conv(g[co], W[co,ci,2-ky,2-kx]).  Running it through the library's tiled
+                # forward conv kernel (shared-memory tiles, ~40 % of the FFMA peak) replaced the one-thread-per-
+                # (pixel, 4 ci) gather kernel, which sat on the L1 load pipe (ncu: 156 us per 32-channel L1 layer).
+                w2 = cache.get("w2")
+                if w2 is None:
+                    w2 = cache["w2"] = weight.detach().transpose(0, 1).flip(2, 3).contiguous()   # (cin, cout, 3, 3)
+                for i, c in enumerate(ctx.c_list):  # one launch per source of the concat: dense per-source gradients
+                    if ctx.needs_input_grad[5 + i]:
+                        sub = cache.setdefault(("dgrad", i), {})
+                        if "zb" not in sub:
+                            sub["zb"] = torch.zeros(c, device=dy.device, dtype=torch.float32)
+                        dxs[i] = K.conv3x3([g], w2[off:off + c], sub["zb"], ACT_NONE, sub)
+                    off += c
+            else:
+                w_t = cache.get("w_t")
+                if w_t is None:
+                    w_t = cache["w_t"] = weight.detach().permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous()  # [tap][co][ci]
+                for i, c in enumerate(ctx.c_list):
+                    if ctx.needs_input_grad[5 + i]:
+                        dxs[i] = torch.empty(n, h, w, c, device=dy.device, dtype=torch.float32)
+                        _chk(K, lib.crfp_conv3x3_bwd_data(n, h, w, c, cout, cin, off, g.data_ptr(), w_t.data_ptr(),
+                                                          dxs[i].data_ptr(), st), "conv3x3_bwd_data")
+                    off += c
         if need_w or need_b:
             dw = torch.zeros(9, cin, cout, device=dy.device, dtype=torch.float32)
             dbt = torch.zeros(cout, device=dy.device, dtype=torch.float32)

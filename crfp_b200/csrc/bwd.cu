@@ -111,13 +111,19 @@ __global__ void __launch_bounds__(256) conv3x3_bwd_data_v4_kernel(int n, int h, 
 // One thread per weight element (co fastest: g loads coalesced, x loads warp-broadcast) and per block of image rows;
 // partial sums meet in dw through atomicAdd.  taps == 1 is the plain (pixels x cin)^T (pixels x cout) product used for
 // the DCN weight gradient (x = the modulated column buffer).
-__global__ void __launch_bounds__(128) conv_bwd_weight_kernel(int rows, int h, int w, int cin, int cout, int taps,
+//
+// Thread mapping (host-chosen): plain — blockDim covers up to 512 weight elements, blockIdx.x the rest, so that ONE CTA
+// reads a pixel chunk for as many elements as possible (the chunk then comes from L2 once and from L1 afterwards);
+// pixel lanes (few elements, the 4-channel HR layers: `lanes` > 1) — the CTA holds `lanes` copies of the `epad`-padded
+// element set and copy `pl` takes every lanes-th pixel, so that the CTA's threads are not mostly idle.
+__global__ void __launch_bounds__(512) conv_bwd_weight_kernel(int rows, int h, int w, int cin, int cout, int taps,
                                                               int cin_total, int cin_off, int rows_per_block, int xsegs,
-                                                              const float* __restrict__ x,
+                                                              int lanes, int epad, const float* __restrict__ x,
                                                               const float* __restrict__ g, float* __restrict__ dw,
                                                               float* __restrict__ db) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= taps * cin * cout) return;
+  const int e = (lanes > 1) ? (int)(threadIdx.x % epad) : (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const int pl = (lanes > 1) ? (int)(threadIdx.x / epad) : 0;
+  if (e >= taps * cin * cout || pl >= lanes) return;
   const int co = e % cout;
   const int ci = (e / cout) % cin;
   const int tap = e / (cout * cin);
@@ -137,11 +143,11 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_kernel(int rows, int h, i
     const int yi = y + ky - 1;
     const float* gp = g + r * w * cout + co;
     if (do_bias)
-      for (int xx = c0; xx < c1; ++xx) gsum += gp[(long long)xx * cout];
+      for (int xx = c0 + pl; xx < c1; xx += lanes) gsum += gp[(long long)xx * cout];
     if (yi < 0 || yi >= h) continue;
     const float* xp = x + (r + (ky - 1)) * w * cin + ci;
 #pragma unroll 4
-    for (int xx = xlo; xx < xhi; ++xx) acc += gp[(long long)xx * cout] * xp[(long long)(xx + kx - 1) * cin];
+    for (int xx = xlo + pl; xx < xhi; xx += lanes) acc += gp[(long long)xx * cout] * xp[(long long)(xx + kx - 1) * cin];
   }
   atomicAdd(dw + ((long long)tap * cin_total + cin_off + ci) * cout + co, acc);
   if (do_bias) atomicAdd(db + co, gsum);
@@ -149,14 +155,15 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_kernel(int rows, int h, i
 
 // Register-tiled variant for cin % 4 == 0 and cout % 4 == 0: one thread per (tap, 4 ci, 4 co) block of dw; per pixel
 // 2 LDG.128 (x: warp broadcast over the co blocks, g: coalesced) feed 16 FMAs.
-__global__ void __launch_bounds__(128) conv_bwd_weight_v4_kernel(int rows, int h, int w, int cin, int cout, int taps,
+__global__ void __launch_bounds__(512) conv_bwd_weight_v4_kernel(int rows, int h, int w, int cin, int cout, int taps,
                                                                  int cin_total, int cin_off, int rows_per_block, int xsegs,
-                                                                 const float* __restrict__ x,
+                                                                 int lanes, int epad, const float* __restrict__ x,
                                                                  const float* __restrict__ g, float* __restrict__ dw,
                                                                  float* __restrict__ db) {
   const int cq = cin >> 2, oq = cout >> 2;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= taps * cq * oq) return;
+  const int e = (lanes > 1) ? (int)(threadIdx.x % epad) : (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const int pl = (lanes > 1) ? (int)(threadIdx.x / epad) : 0;
+  if (e >= taps * cq * oq || pl >= lanes) return;
   const int co = (e % oq) * 4;
   const int ci = ((e / oq) % cq) * 4;
   const int tap = e / (oq * cq);
@@ -178,14 +185,14 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_v4_kernel(int rows, int h
     const int yi = y + ky - 1;
     const float* gp = g + r * w * cout + co;
     if (do_bias)
-      for (int xx = c0; xx < c1; ++xx) {
+      for (int xx = c0 + pl; xx < c1; xx += lanes) {
         const float4 gv = *reinterpret_cast<const float4*>(gp + (long long)xx * cout);
         gsum.x += gv.x; gsum.y += gv.y; gsum.z += gv.z; gsum.w += gv.w;
       }
     if (yi < 0 || yi >= h) continue;
     const float* xp = x + (r + (ky - 1)) * w * cin + ci;
 #pragma unroll 4
-    for (int xx = xlo; xx < xhi; ++xx) {
+    for (int xx = xlo + pl; xx < xhi; xx += lanes) {
       const float4 gv = *reinterpret_cast<const float4*>(gp + (long long)xx * cout);
       const float4 xv = *reinterpret_cast<const float4*>(xp + (long long)(xx + kx - 1) * cin);
       acc[0][0] += xv.x * gv.x; acc[0][1] += xv.x * gv.y; acc[0][2] += xv.x * gv.z; acc[0][3] += xv.x * gv.w;
@@ -208,28 +215,41 @@ static int launch_bwd_weight(long long rows, int h, int w, int cin, int cout, in
                              const float* x, const float* g, float* dw, float* db, cudaStream_t st) {
   const bool v4 = (cin % 4 == 0) && (cout % 4 == 0) && aligned16(x) && aligned16(g);   // (dw is only touched by atomics)
   const int elems = v4 ? taps * (cin / 4) * (cout / 4) : taps * cin * cout;
-  const unsigned gx = blocks_for(elems, 128);
-  long long target_y = 8192 / gx;
+  // thread mapping, see the kernel comment
+  int lanes = 1, epad = 0, bd;
+  unsigned gx;
+  if (elems <= 64) {
+    epad = 16;
+    while (epad < elems) epad *= 2;
+    lanes = 128 / epad;
+    bd = 128;
+    gx = 1;
+  } else {
+    gx = (unsigned)((elems + 511) / 512);
+    bd = (int)((elems + gx - 1) / gx);
+    bd = (bd + 31) / 32 * 32;
+  }
+  long long target_y = 4096 / gx;
   if (target_y < 1) target_y = 1;
   long long rpb = (rows + target_y - 1) / target_y;
   if (rpb < 1) rpb = 1;
   unsigned gy = (unsigned)((rows + rpb - 1) / rpb);
-  // few weight elements (the 4-channel HR layers): also split every row into column segments of >= 32 pixels so that
-  // the grid still fills the 148 SMs
+  // few CTAs per row block: also split every row into column segments (>= 32 pixels per pixel lane) so that the grid
+  // still fills the 148 SMs
   int xsegs = 1;
-  if (rpb == 1 && (long long)gy * gx < 4096) {
-    xsegs = (int)(4096 / ((long long)gy * gx));
-    if (xsegs > w / 32) xsegs = w / 32;
+  if (rpb == 1 && (long long)gy * gx < 2048) {
+    xsegs = (int)(2048 / ((long long)gy * gx));
+    if (xsegs > w / (32 * lanes)) xsegs = w / (32 * lanes);
     if (xsegs < 1) xsegs = 1;
     if ((long long)gy * xsegs > 65535) xsegs = (int)(65535 / gy);
   }
   gy *= (unsigned)xsegs;
   if (v4)
-    CRFP_LAUNCH(conv_bwd_weight_v4_kernel, dim3(gx, gy), dim3(128), st, (int)rows, h, w, cin, cout, taps, cin_total, cin_off,
-                (int)rpb, xsegs, x, g, dw, db);
+    CRFP_LAUNCH(conv_bwd_weight_v4_kernel, dim3(gx, gy), dim3(bd), st, (int)rows, h, w, cin, cout, taps, cin_total, cin_off,
+                (int)rpb, xsegs, lanes, epad, x, g, dw, db);
   else
-    CRFP_LAUNCH(conv_bwd_weight_kernel, dim3(gx, gy), dim3(128), st, (int)rows, h, w, cin, cout, taps, cin_total, cin_off,
-                (int)rpb, xsegs, x, g, dw, db);
+    CRFP_LAUNCH(conv_bwd_weight_kernel, dim3(gx, gy), dim3(bd), st, (int)rows, h, w, cin, cout, taps, cin_total, cin_off,
+                (int)rpb, xsegs, lanes, epad, x, g, dw, db);
   return check_launch();
 }
 

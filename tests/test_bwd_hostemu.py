@@ -14,6 +14,7 @@ from crfp_b200 import autograd as A
 from oracle import crfp_oracle as O
 
 K = hostemu.HostEmuKernelSet()
+K_DIRECT = hostemu.HostEmuKernelSet(dgrad_as_conv=False)
 
 
 def _g(seed):
@@ -47,7 +48,11 @@ def test_emulation_exports_every_training_symbol():
                                                 ([4, 4], 4, (11, 9), 0), ([6], 4, (6, 7), 1), ([4], 3, (5, 5), 0),
                                                 ([24, 32, 8], 32, (6, 6), 1), ([8], 12, (1, 5), 0),
                                                 ([4, 4], 4, (3, 100), 1), ([6], 4, (3, 70), 0)])   # wide rows: column-segmented wgrad
-def test_conv3x3_grads(c_list, cout, hw, act):
+@pytest.mark.parametrize("direct", [False, True])
+def test_conv3x3_grads(c_list, cout, hw, act, direct):
+    """direct=False: backward-data as a forward conv with the rotated / transposed kernel (the product default);
+    direct=True: the gather kernels crfp_conv3x3_bwd_data (A/B path)."""
+    K = K_DIRECT if direct else globals()["K"]
     g = _g(1)
     h, w = hw
     srcs = [torch.randn(2, c, h, w, generator=g, requires_grad=True) for c in c_list]

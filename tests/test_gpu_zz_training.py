@@ -41,7 +41,12 @@ def nchw(x):
 @pytest.mark.parametrize("c_list,cout,hw,act", [([32], 32, (19, 33), 1), ([32, 32, 2], 32, (17, 20), 1), ([3, 3], 32, (16, 24), 2),
                                                 ([4, 4], 4, (37, 45), 0), ([6], 4, (20, 28), 1), ([4], 3, (15, 15), 0),
                                                 ([24, 32, 8], 32, (12, 12), 1), ([32], 216, (10, 14), 0), ([128], 256, (4, 6), 2)])
-def test_conv3x3_grads(A, c_list, cout, hw, act):
+@pytest.mark.parametrize("direct", [False, True])
+def test_conv3x3_grads(A, c_list, cout, hw, act, direct):
+    """direct=False: backward-data through the tiled forward conv kernel with the rotated / transposed weights (default);
+    direct=True: the gather kernels behind crfp_conv3x3_bwd_data (CRFP_DGRAD=direct)."""
+    K = A.KernelSet()
+    K.dgrad_as_conv = not direct
     g = _g(1)
     h, w = hw
     srcs = [torch.randn(2, c, h, w, generator=g, requires_grad=True) for c in c_list]
@@ -53,7 +58,7 @@ def test_conv3x3_grads(A, c_list, cout, hw, act):
     rg = torch.autograd.grad(ref, [wt, b, *srcs], dy)
     s2 = [nhwc(s).requires_grad_() for s in srcs]
     w2, b2 = wt.detach().cuda().requires_grad_(), b.detach().cuda().requires_grad_()
-    out = A.conv3x3(A.CUDA, w2, b2, s2, act)
+    out = A.conv3x3(K, w2, b2, s2, act)
     assert (nchw(out) - ref.detach()).abs().max().item() < 1e-4
     got = torch.autograd.grad(out, [w2, b2, *s2], nhwc(dy))
     tol_w = 1e-5 * rg[0].abs().max().item() + 2e-4       # sums over n*h*w pixels, atomics in arbitrary order

@@ -53,6 +53,9 @@ class HostEmuKernelSet:
 
     name = "hostemu"
 
+    def __init__(self, dgrad_as_conv=True):
+        self.dgrad_as_conv = dgrad_as_conv      # False: exercise the direct crfp_conv3x3_bwd_data kernels
+
     def lib(self):
         return lib()
 
