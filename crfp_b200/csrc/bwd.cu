@@ -229,20 +229,24 @@ static int launch_bwd_weight(long long rows, int h, int w, int cin, int cout, in
     bd = (int)((elems + gx - 1) / gx);
     bd = (bd + 31) / 32 * 32;
   }
-  long long target_y = 4096 / gx;
-  if (target_y < 1) target_y = 1;
-  long long rpb = (rows + target_y - 1) / target_y;
-  if (rpb < 1) rpb = 1;
-  unsigned gy = (unsigned)((rows + rpb - 1) / rpb);
-  // few CTAs per row block: also split every row into column segments (>= 32 pixels per pixel lane) so that the grid
-  // still fills the 148 SMs
+  // How many pixel chunks (= CTAs per element block)?  Every chunk ends in one atomicAdd per weight element, and ncu
+  // showed the launch time tracking the atomic count (~1e11 atomics/s device-wide, ~1 per 3 clocks on one cache line):
+  // use just enough chunks to put ~160 k threads in flight, and for the 4-channel layers (a few cache lines of dw) at
+  // most 512 partial sums per element.
+  long long chunks = 160000 / ((long long)gx * bd);
+  if ((long long)taps * cin * cout <= 1024 && chunks * lanes > 512) chunks = 512 / lanes;
+  if (chunks < 1) chunks = 1;
+  long long rpb = 1;
   int xsegs = 1;
-  if (rpb == 1 && (long long)gy * gx < 2048) {
-    xsegs = (int)(2048 / ((long long)gy * gx));
+  if (chunks <= rows) {
+    rpb = (rows + chunks - 1) / chunks;
+  } else {                       // more chunks than rows: split every row into column segments of >= 32 pixels per lane
+    xsegs = (int)(chunks / rows);
     if (xsegs > w / (32 * lanes)) xsegs = w / (32 * lanes);
     if (xsegs < 1) xsegs = 1;
-    if ((long long)gy * xsegs > 65535) xsegs = (int)(65535 / gy);
   }
+  unsigned gy = (unsigned)((rows + rpb - 1) / rpb);
+  if ((long long)gy * xsegs > 65535) xsegs = (int)(65535 / gy);
   gy *= (unsigned)xsegs;
   if (v4)
     CRFP_LAUNCH(conv_bwd_weight_v4_kernel, dim3(gx, gy), dim3(bd), st, (int)rows, h, w, cin, cout, taps, cin_total, cin_off,

@@ -47,7 +47,8 @@ def test_emulation_exports_every_training_symbol():
 @pytest.mark.parametrize("c_list,cout,hw,act", [([32], 32, (9, 13), 1), ([32, 32, 2], 32, (7, 10), 1), ([3, 3], 16, (8, 8), 2),
                                                 ([4, 4], 4, (11, 9), 0), ([6], 4, (6, 7), 1), ([4], 3, (5, 5), 0),
                                                 ([24, 32, 8], 32, (6, 6), 1), ([8], 12, (1, 5), 0),
-                                                ([4, 4], 4, (3, 100), 1), ([6], 4, (3, 70), 0)])   # wide rows: column-segmented wgrad
+                                                ([4, 4], 4, (3, 100), 1), ([6], 4, (3, 70), 0),   # wide rows: column-segmented wgrad
+                                                ([64], 64, (40, 8), 0)])                         # several rows per wgrad chunk
 @pytest.mark.parametrize("direct", [False, True])
 def test_conv3x3_grads(c_list, cout, hw, act, direct):
     """direct=False: backward-data as a forward conv with the rotated / transposed kernel (the product default);
