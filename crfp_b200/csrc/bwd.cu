@@ -12,6 +12,7 @@
 //
 // Conventions: all tensors dense NHWC (pixel stride == channel count); "accumulated" outputs are += (the caller
 // zero-fills them once per step), everything else is overwritten.
+#include <stdlib.h>
 #ifdef CRFP_HOST_EMU
 #include "cuda_shim.h"
 #else
@@ -210,11 +211,20 @@ __global__ void __launch_bounds__(512) conv_bwd_weight_v4_kernel(int rows, int h
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static int env_int(const char* name, int dflt, int lo, int hi) {
+  const char* v = getenv(name);
+  if (v == nullptr) return dflt;
+  const int x = atoi(v);
+  return x < lo ? lo : (x > hi ? hi : x);
+}
 
 static int launch_bwd_weight(long long rows, int h, int w, int cin, int cout, int taps, int cin_total, int cin_off,
                              const float* x, const float* g, float* dw, float* db, cudaStream_t st) {
   const bool v4 = (cin % 4 == 0) && (cout % 4 == 0) && aligned16(x) && aligned16(g);   // (dw is only touched by atomics)
   const int elems = v4 ? taps * (cin / 4) * (cout / 4) : taps * cin * cout;
+  // A/B knobs (read once): CTA size cap for the plain mapping and the thread target that sizes the pixel chunks
+  static const int bd_cap = env_int("CRFP_WGRAD_BD", 512, 32, 512);
+  static const int thread_target = env_int("CRFP_WGRAD_THREADS", 160000, 1024, 1 << 24);
   // thread mapping, see the kernel comment
   int lanes = 1, epad = 0, bd;
   unsigned gx;
@@ -225,7 +235,7 @@ static int launch_bwd_weight(long long rows, int h, int w, int cin, int cout, in
     bd = 128;
     gx = 1;
   } else {
-    gx = (unsigned)((elems + 511) / 512);
+    gx = (unsigned)((elems + bd_cap - 1) / bd_cap);
     bd = (int)((elems + gx - 1) / gx);
     bd = (bd + 31) / 32 * 32;
   }
@@ -233,7 +243,7 @@ static int launch_bwd_weight(long long rows, int h, int w, int cin, int cout, in
   // showed the launch time tracking the atomic count (~1e11 atomics/s device-wide, ~1 per 3 clocks on one cache line):
   // use just enough chunks to put ~160 k threads in flight, and for the 4-channel layers (a few cache lines of dw) at
   // most 512 partial sums per element.
-  long long chunks = 160000 / ((long long)gx * bd);
+  long long chunks = (long long)thread_target / ((long long)gx * bd);
   if ((long long)taps * cin * cout <= 1024 && chunks * lanes > 512) chunks = 512 / lanes;
   if (chunks < 1) chunks = 1;
   long long rpb = 1;
