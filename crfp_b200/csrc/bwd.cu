@@ -113,18 +113,19 @@ __global__ void __launch_bounds__(256) conv3x3_bwd_data_v4_kernel(int n, int h, 
 // partial sums meet in dw through atomicAdd.  taps == 1 is the plain (pixels x cin)^T (pixels x cout) product used for
 // the DCN weight gradient (x = the modulated column buffer).
 //
-// Thread mapping (host-chosen): plain — blockDim covers up to 512 weight elements, blockIdx.x the rest, so that ONE CTA
-// reads a pixel chunk for as many elements as possible (the chunk then comes from L2 once and from L1 afterwards);
+// Thread mapping (host-chosen): plain — one thread per weight element, 128 per CTA, unit-stride pixel loop;
 // pixel lanes (few elements, the 4-channel HR layers: `lanes` > 1) — the CTA holds `lanes` copies of the `epad`-padded
 // element set and copy `pl` takes every lanes-th pixel, so that the CTA's threads are not mostly idle.
-__global__ void __launch_bounds__(512) conv_bwd_weight_kernel(int rows, int h, int w, int cin, int cout, int taps,
+template <bool UNIT>   // UNIT: plain mapping (lanes == 1), unit-stride pixel loop with compile-time pointer increments
+__global__ void __launch_bounds__(128) conv_bwd_weight_kernel(int rows, int h, int w, int cin, int cout, int taps,
                                                               int cin_total, int cin_off, int rows_per_block, int xsegs,
                                                               int lanes, int epad, const float* __restrict__ x,
                                                               const float* __restrict__ g, float* __restrict__ dw,
                                                               float* __restrict__ db) {
-  const int e = (lanes > 1) ? (int)(threadIdx.x % epad) : (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  const int pl = (lanes > 1) ? (int)(threadIdx.x / epad) : 0;
-  if (e >= taps * cin * cout || pl >= lanes) return;
+  const int e = UNIT ? (int)(blockIdx.x * blockDim.x + threadIdx.x) : (int)(threadIdx.x % epad);
+  const int pl = UNIT ? 0 : (int)(threadIdx.x / epad);
+  const int step = UNIT ? 1 : lanes;
+  if (e >= taps * cin * cout || pl >= step) return;
   const int co = e % cout;
   const int ci = (e / cout) % cin;
   const int tap = e / (cout * cin);
@@ -144,11 +145,11 @@ __global__ void __launch_bounds__(512) conv_bwd_weight_kernel(int rows, int h, i
     const int yi = y + ky - 1;
     const float* gp = g + r * w * cout + co;
     if (do_bias)
-      for (int xx = c0 + pl; xx < c1; xx += lanes) gsum += gp[(long long)xx * cout];
+      for (int xx = c0 + pl; xx < c1; xx += step) gsum += gp[(long long)xx * cout];
     if (yi < 0 || yi >= h) continue;
     const float* xp = x + (r + (ky - 1)) * w * cin + ci;
 #pragma unroll 4
-    for (int xx = xlo + pl; xx < xhi; xx += lanes) acc += gp[(long long)xx * cout] * xp[(long long)(xx + kx - 1) * cin];
+    for (int xx = xlo + pl; xx < xhi; xx += step) acc += gp[(long long)xx * cout] * xp[(long long)(xx + kx - 1) * cin];
   }
   atomicAdd(dw + ((long long)tap * cin_total + cin_off + ci) * cout + co, acc);
   if (do_bias) atomicAdd(db + co, gsum);
@@ -156,15 +157,17 @@ __global__ void __launch_bounds__(512) conv_bwd_weight_kernel(int rows, int h, i
 
 // Register-tiled variant for cin % 4 == 0 and cout % 4 == 0: one thread per (tap, 4 ci, 4 co) block of dw; per pixel
 // 2 LDG.128 (x: warp broadcast over the co blocks, g: coalesced) feed 16 FMAs.
-__global__ void __launch_bounds__(512) conv_bwd_weight_v4_kernel(int rows, int h, int w, int cin, int cout, int taps,
+template <bool UNIT>
+__global__ void __launch_bounds__(128) conv_bwd_weight_v4_kernel(int rows, int h, int w, int cin, int cout, int taps,
                                                                  int cin_total, int cin_off, int rows_per_block, int xsegs,
                                                                  int lanes, int epad, const float* __restrict__ x,
                                                                  const float* __restrict__ g, float* __restrict__ dw,
                                                                  float* __restrict__ db) {
   const int cq = cin >> 2, oq = cout >> 2;
-  const int e = (lanes > 1) ? (int)(threadIdx.x % epad) : (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  const int pl = (lanes > 1) ? (int)(threadIdx.x / epad) : 0;
-  if (e >= taps * cq * oq || pl >= lanes) return;
+  const int e = UNIT ? (int)(blockIdx.x * blockDim.x + threadIdx.x) : (int)(threadIdx.x % epad);
+  const int pl = UNIT ? 0 : (int)(threadIdx.x / epad);
+  const int step = UNIT ? 1 : lanes;
+  if (e >= taps * cq * oq || pl >= step) return;
   const int co = (e % oq) * 4;
   const int ci = ((e / oq) % cq) * 4;
   const int tap = e / (oq * cq);
@@ -186,14 +189,14 @@ __global__ void __launch_bounds__(512) conv_bwd_weight_v4_kernel(int rows, int h
     const int yi = y + ky - 1;
     const float* gp = g + r * w * cout + co;
     if (do_bias)
-      for (int xx = c0 + pl; xx < c1; xx += lanes) {
+      for (int xx = c0 + pl; xx < c1; xx += step) {
         const float4 gv = *reinterpret_cast<const float4*>(gp + (long long)xx * cout);
         gsum.x += gv.x; gsum.y += gv.y; gsum.z += gv.z; gsum.w += gv.w;
       }
     if (yi < 0 || yi >= h) continue;
     const float* xp = x + (r + (ky - 1)) * w * cin + ci;
 #pragma unroll 4
-    for (int xx = xlo + pl; xx < xhi; xx += lanes) {
+    for (int xx = xlo + pl; xx < xhi; xx += step) {
       const float4 gv = *reinterpret_cast<const float4*>(gp + (long long)xx * cout);
       const float4 xv = *reinterpret_cast<const float4*>(xp + (long long)(xx + kx - 1) * cin);
       acc[0][0] += xv.x * gv.x; acc[0][1] += xv.x * gv.y; acc[0][2] += xv.x * gv.z; acc[0][3] += xv.x * gv.w;
@@ -223,8 +226,9 @@ static int launch_bwd_weight(long long rows, int h, int w, int cin, int cout, in
   const bool v4 = (cin % 4 == 0) && (cout % 4 == 0) && aligned16(x) && aligned16(g);   // (dw is only touched by atomics)
   const int elems = v4 ? taps * (cin / 4) * (cout / 4) : taps * cin * cout;
   // A/B knobs (read once): CTA size cap for the plain mapping and the thread target that sizes the pixel chunks
-  static const int bd_cap = env_int("CRFP_WGRAD_BD", 512, 32, 512);
-  static const int thread_target = env_int("CRFP_WGRAD_THREADS", 160000, 1024, 1 << 24);
+  // (measured on the B200, profiles/r01/v6_train_wgrad_ab.txt: neither knob moves the step time by more than 2 %)
+  static const int bd_cap = env_int("CRFP_WGRAD_BD", 128, 32, 128);
+  static const int thread_target = env_int("CRFP_WGRAD_THREADS", 524288, 1024, 1 << 24);
   // thread mapping, see the kernel comment
   int lanes = 1, epad = 0, bd;
   unsigned gx;
@@ -258,12 +262,12 @@ static int launch_bwd_weight(long long rows, int h, int w, int cin, int cout, in
   unsigned gy = (unsigned)((rows + rpb - 1) / rpb);
   if ((long long)gy * xsegs > 65535) xsegs = (int)(65535 / gy);
   gy *= (unsigned)xsegs;
-  if (v4)
-    CRFP_LAUNCH(conv_bwd_weight_v4_kernel, dim3(gx, gy), dim3(bd), st, (int)rows, h, w, cin, cout, taps, cin_total, cin_off,
-                (int)rpb, xsegs, lanes, epad, x, g, dw, db);
-  else
-    CRFP_LAUNCH(conv_bwd_weight_kernel, dim3(gx, gy), dim3(bd), st, (int)rows, h, w, cin, cout, taps, cin_total, cin_off,
-                (int)rpb, xsegs, lanes, epad, x, g, dw, db);
+#define CRFP_WGRAD_ARGS (int)rows, h, w, cin, cout, taps, cin_total, cin_off, (int)rpb, xsegs, lanes, epad, x, g, dw, db
+  if (v4 && lanes == 1) CRFP_LAUNCH(conv_bwd_weight_v4_kernel<true>, dim3(gx, gy), dim3(bd), st, CRFP_WGRAD_ARGS);
+  else if (v4) CRFP_LAUNCH(conv_bwd_weight_v4_kernel<false>, dim3(gx, gy), dim3(bd), st, CRFP_WGRAD_ARGS);
+  else if (lanes == 1) CRFP_LAUNCH(conv_bwd_weight_kernel<true>, dim3(gx, gy), dim3(bd), st, CRFP_WGRAD_ARGS);
+  else CRFP_LAUNCH(conv_bwd_weight_kernel<false>, dim3(gx, gy), dim3(bd), st, CRFP_WGRAD_ARGS);
+#undef CRFP_WGRAD_ARGS
   return check_launch();
 }
 
