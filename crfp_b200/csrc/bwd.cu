@@ -4,11 +4,13 @@
 // convs, nn.Upsample and AvgPool2d), plus the Charbonnier loss (loss/loss.py:116-124) and the Adam update
 // (trainer.py:149,250).
 //
-// Round-1 design: FIRST CORRECT versions.  Every kernel is a sync-free, shared-memory-free SIMT kernel — one thread
-// per output element (gather form) or per contribution (scatter form with atomicAdd) over dense fp32 NHWC tensors,
-// coalesced along the channel axis.  That keeps them bit-for-bit testable without a GPU: the same kernel bodies and
-// entry points compile with g++ against tests/tools/hostemu/cuda_shim.h (CRFP_HOST_EMU; test infrastructure only)
-// and are checked against torch autograd in the CPU suite.  The tensor-core / smem-tiled versions are round-2 work.
+// Round-1 design: first correct versions, then the three fixes the first ncu launch list asked for (vector DCN backward
+// with a transposed weight, per-source weight gradients, backward-data moved onto the tiled forward conv kernel — see
+// DESIGN.md 11).  Every kernel here is a sync-free, shared-memory-free SIMT kernel — one thread per output element /
+// register tile (gather form) or per contribution (scatter form with atomicAdd) over dense fp32 NHWC tensors, coalesced
+// along the channel axis.  That keeps them testable without a GPU: the same kernel bodies and entry points compile
+// with g++ against tests/tools/hostemu/cuda_shim.h (CRFP_HOST_EMU; test infrastructure only) and are checked against
+// torch autograd in the CPU suite.  Tensor-core / shared-memory-tiled weight gradients are round-2 work.
 //
 // Conventions: all tensors dense NHWC (pixel stride == channel count); "accumulated" outputs are += (the caller
 // zero-fills them once per step), everything else is overwritten.

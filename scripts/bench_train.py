@@ -52,7 +52,6 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
-    _lib.lib().crfp_launch_count_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -70,7 +69,8 @@ def main():
             "value": world * n * t * args.steps / sec, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms.item() / args.steps, "higher_is_better": True, "scaling": "weak",
             "dtype": "fp32", "data": "synthetic", "cuda_graph": bool(args.graphs and tr.use_graphs and tr._graphs),
-            "gpu_launches": int(_lib.lib().crfp_launch_count()),
+            # (the library's launch counter is per host thread and the backward runs on autograd's thread: the kernel
+            # count of a step, 4 190 incl. copies at V7, comes from scripts/train_kernel_times.py instead)
             "config": {"workload": f"{args.shape}: n={n} clips/GPU, t={t}, LR {h}x{w} -> {8 * h}x{8 * w}, FV {fv}",
                        "params": int(tr.flat_p.numel()), "grad_bucket_bytes": int(tr.flat_g.numel() * 4)},
             "loss_first_last": [losses[0], losses[-1]],
