@@ -196,10 +196,15 @@ SYMBOLS = {
     "crfp_charbonnier_fwd_bwd": (C.c_int, [C.c_longlong, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                                            C.c_void_p]),
     "crfp_adam_step": (C.c_int, [C.c_longlong] + [C.c_void_p] * 4 + [C.c_float] * 5 + [C.c_void_p]),
+    # SPyNet operators (spynet.cu)
+    "crfp_conv_kxk_fwd": (C.c_int, [C.c_int] * 7 + [C.c_void_p] * 6),
+    "crfp_resize_bilinear_ac": (C.c_int, [C.c_int] * 4 + [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "crfp_channel_affine": (C.c_int, [C.c_longlong, C.c_int, C.c_int] + [C.c_void_p] * 6),
 }
 
 # the training entry points alone: also exported by the host-emulation build the CPU tests use (tests/tools/hostemu)
 TRAIN_SYMBOLS = [k for k in SYMBOLS if "_bwd" in k or k == "crfp_adam_step"]
+SPYNET_SYMBOLS = ["crfp_conv_kxk_fwd", "crfp_resize_bilinear_ac", "crfp_channel_affine"]
 
 _lib = None
 

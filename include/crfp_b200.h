@@ -27,6 +27,7 @@
  *   crfp_dsv_frame            one iteration of the t-loop of CRFP_DSV.forward   model/CRFP.py:1555-1684
  *                             incl. fovea compositing + encoder_hr (1542-1547) for that frame
  *   crfp_*_bwd, crfp_charbonnier_fwd_bwd, crfp_adam_step   loss.backward() + optimizer.step()   trainer.py:246-250
+ *   crfp_conv_kxk_fwd, crfp_resize_bilinear_ac, crfp_channel_affine   SPyNet (legacy)        model/CRFP.py:554-741
  */
 #ifndef CRFP_B200_H
 #define CRFP_B200_H
@@ -489,6 +490,20 @@ int crfp_charbonnier_fwd_bwd(long long count, const float* pred, const float* ta
  * step_size = lr / (1 - beta1^t), bc2_sqrt = sqrt(1 - beta2^t) */
 int crfp_adam_step(long long count, float* p, const float* g, float* m, float* v, float beta1, float beta2, float eps,
                    float step_size, float bc2_sqrt, crfp_stream stream);
+
+/* ------------------------------------------------------------------ SPyNet operators (legacy flow pyramid) */
+/* the pieces of SPyNet.compute_flow (model/CRFP.py:593-650) the hot path does not already provide; dense fp32 NHWC */
+/* `conv(act(x))` of SPyNetBasicModule (model/CRFP.py:145-152, 687-741): k x k (odd), stride 1, pad k/2, optional ReLU on
+ * the INPUT, optional residual added to the output (flow_up + module(...), :647).  weight = [k*k][cin][cout] */
+int crfp_conv_kxk_fwd(int n, int h, int w, int cin, int cout, int k, int relu_in, const float* x, const float* weight,
+                      const float* bias, const float* residual, float* out, crfp_stream stream);
+/* F.interpolate(mode='bilinear', align_corners=True) (model/CRFP.py:635-639); out = value * mul */
+int crfp_resize_bilinear_ac(int n, int hin, int win, int c, const float* in, int hout, int wout, float mul, float* out,
+                            crfp_stream stream);
+/* out[p][ch] = ((in[p][ch] - sub[ch]) / div[ch]) * mul[ch], ch < c_in; extra output channels [c_in, c_out) are zero:
+ * the ImageNet normalisation (:609-610) into a 4-channel plane, and the per-axis flow rescale (:683-684) */
+int crfp_channel_affine(long long npix, int c_in, int c_out, const float* in, const float* sub, const float* div,
+                        const float* mul, float* out, crfp_stream stream);
 
 #ifdef __cplusplus
 }

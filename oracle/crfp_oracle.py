@@ -408,3 +408,52 @@ class StreamingOracle:
         return torch.stack(outs, dim=1)
 
     __call__ = forward
+
+
+# ----------------------------------------------------------------------------- SPyNet
+SPYNET_MEAN = (0.485, 0.456, 0.406)
+SPYNET_STD = (0.229, 0.224, 0.225)
+SPYNET_WIDTHS = ((8, 32), (32, 64), (64, 32), (32, 16), (16, 2))
+
+
+def spynet_basic_module(sd, level, x, prefix=""):
+    """SPyNetBasicModule.forward (CRFP.py:687-741): five `conv(act(x))` 7x7 layers — ReLU is applied to the INPUT of
+    every conv including the first (`conv.forward`, CRFP.py:145-152), there is no activation on the output."""
+    for i in range(5):
+        name = f"{prefix}basic_module.{level}.basic_module.{i}.conv"
+        x = F.conv2d(F.relu(x), sd[name + ".weight"], sd[name + ".bias"], stride=1, padding=3)
+    return x
+
+
+def spynet_compute_flow(sd, ref, supp, prefix=""):
+    """SPyNet.compute_flow (CRFP.py:593-650): inputs already multiples of 32."""
+    n, _, h, w = ref.shape
+    mean = ref.new_tensor(SPYNET_MEAN).view(1, 3, 1, 1)
+    std = ref.new_tensor(SPYNET_STD).view(1, 3, 1, 1)
+    ref = [(ref - mean) / std]
+    supp = [(supp - mean) / std]
+    for _ in range(5):
+        ref.append(F.avg_pool2d(ref[-1], kernel_size=2, stride=2, count_include_pad=False))
+        supp.append(F.avg_pool2d(supp[-1], kernel_size=2, stride=2, count_include_pad=False))
+    ref, supp = ref[::-1], supp[::-1]
+    flow = ref[0].new_zeros(n, 2, h // 32, w // 32)
+    for level in range(len(ref)):
+        if level == 0:
+            flow_up = flow
+        else:
+            flow_up = F.interpolate(flow, scale_factor=2, mode="bilinear", align_corners=True) * 2.0
+        warped = flow_warp(supp[level], flow_up, padding_mode="border")
+        flow = flow_up + spynet_basic_module(sd, level, torch.cat([ref[level], warped, flow_up], 1), prefix)
+    return flow
+
+
+def spynet(sd, ref, supp, prefix=""):
+    """SPyNet.forward(ref, supp) (CRFP.py:652-685): resize to multiples of 32, pyramid, resize back, rescale the flow."""
+    h, w = ref.shape[2:4]
+    w_up = w if (w % 32) == 0 else 32 * (w // 32 + 1)
+    h_up = h if (h % 32) == 0 else 32 * (h // 32 + 1)
+    ref = F.interpolate(ref, size=(h_up, w_up), mode="bilinear", align_corners=False)
+    supp = F.interpolate(supp, size=(h_up, w_up), mode="bilinear", align_corners=False)
+    flow = F.interpolate(spynet_compute_flow(sd, ref, supp, prefix), size=(h, w), mode="bilinear", align_corners=False)
+    scale = flow.new_tensor([float(w) / float(w_up), float(h) / float(h_up)]).view(1, 2, 1, 1)
+    return flow * scale

@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY: g++ build + ctypes handle of the host emulation of crfp_b200/csrc/bwd.cu.
+"""TEST INFRASTRUCTURE ONLY: g++ build + ctypes handle of the host emulation of crfp_b200/csrc/bwd.cu and spynet.cu.
 
 The backward kernels are sync-free one-thread-per-element SIMT kernels, so the very same source compiles as plain
 C++ against `cuda_shim.h` (a serial loop over the launch grid) and exports the same C-ABI entry points, taking HOST
@@ -13,18 +13,18 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.abspath(os.path.join(_HERE, "..", "..", ".."))
-_SRC = os.path.join(_ROOT, "crfp_b200", "csrc", "bwd.cu")
+_SRCS = [os.path.join(_ROOT, "crfp_b200", "csrc", f) for f in ("bwd.cu", "spynet.cu")]   # the sync-free sources
 _OUT = os.path.join(_HERE, "_build", "libcrfp_bwd_hostemu.so")
 _lib = None
 
 
 def build() -> str:
-    deps = [_SRC, os.path.join(_HERE, "cuda_shim.h"), os.path.join(_ROOT, "include", "crfp_b200.h")]
+    deps = _SRCS + [os.path.join(_HERE, "cuda_shim.h"), os.path.join(_ROOT, "include", "crfp_b200.h")]
     if os.path.exists(_OUT) and all(os.path.getmtime(_OUT) >= os.path.getmtime(d) for d in deps):
         return _OUT
     os.makedirs(os.path.dirname(_OUT), exist_ok=True)
     cmd = ["g++", "-x", "c++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-DCRFP_HOST_EMU",
-           "-I", _HERE, _SRC, "-o", _OUT]
+           "-I", _HERE, *_SRCS, "-o", _OUT]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("host-emulation build of bwd.cu failed:\n" + res.stderr)
@@ -37,7 +37,7 @@ def lib():
     if _lib is None:
         from crfp_b200 import _lib as L
         h = C.CDLL(build())
-        for name in L.TRAIN_SYMBOLS:
+        for name in L.TRAIN_SYMBOLS + L.SPYNET_SYMBOLS:
             res, args = L.SYMBOLS[name]
             fn = getattr(h, name)
             fn.restype, fn.argtypes = res, args
@@ -103,3 +103,41 @@ class HostEmuKernelSet:
 
     def to_nhwc(self, x):
         return self._nhwc(x)
+
+
+def spy_kernels():
+    """SPyNet kernel set for the CPU suite: conv_kxk / resize_ac / channel_affine are the host-emulated kernels of
+    spynet.cu (the code under test); the hot-path kernels SPyNet reuses (GPU-only, verified on the B200 by
+    tests/test_gpu_ops.py) are stood in for by plain PyTorch / oracle ops."""
+    import torch
+    import torch.nn.functional as F
+    from crfp_b200.spynet import SpyKernels
+    from oracle import crfp_oracle as O
+
+    class HostEmuSpyKernels(SpyKernels):
+        def lib(self):
+            return lib()
+
+        def stream(self):
+            return None
+
+        def req(self, t, what):
+            assert isinstance(t, torch.Tensor) and not t.is_cuda, what
+            return t.to(torch.float32).contiguous()
+
+        def to_nhwc(self, x):
+            return x.permute(0, 2, 3, 1).contiguous()
+
+        def to_nchw(self, x):
+            return x.permute(0, 3, 1, 2).contiguous()
+
+        def avgpool2(self, x):
+            return self.to_nhwc(F.avg_pool2d(self.to_nchw(x), 2, 2, count_include_pad=False))
+
+        def resize(self, x, hout, wout):
+            return self.to_nhwc(F.interpolate(self.to_nchw(x), size=(hout, wout), mode="bilinear", align_corners=False))
+
+        def flow_warp_border(self, x, flow):
+            return self.to_nhwc(O.flow_warp(self.to_nchw(x), self.to_nchw(flow), padding_mode="border"))
+
+    return HostEmuSpyKernels()
