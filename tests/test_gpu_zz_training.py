@@ -243,3 +243,28 @@ def test_trainer_steps_reduce_the_loss_and_refresh_inference_weights(A):
     ref = O.crfp_dsv_forward(new_sd, lrs, fvs, mks)
     assert (out.cpu() - ref).abs().max().item() < 1e-3
     assert any((new_sd[k] - sd[k]).abs().max().item() > 0 for k in sd)
+
+
+@pytest.mark.xfail(reason="added after round 1's GPU budget was spent: the graphed step itself ran on the B200 through "
+                          "scripts/bench_train.py --graphs (profiles/r01/v6_train_bench_v7.json), this comparison has not", strict=False)
+def test_graphed_trainer_tracks_the_eager_trainer(A):
+    """Trainer(use_graphs=True): steps 1-2 eager, step 3 captures forward + loss + backward, later steps replay."""
+    from crfp_b200 import CRFP_DSV
+    from crfp_b200.synthetic import make_clip, make_state_dict
+    from crfp_b200.trainer import Trainer
+    sd = make_state_dict(seed=1)
+    lrs, fvs, mks, _ = make_clip(seed=4, n=1, t=3, h=16, w=16, fv_size=48)
+    hr = torch.rand(1, 3, 3, 128, 128, generator=_g(5))
+    args = (lrs.cuda(), fvs.cuda(), mks.cuda(), hr.cuda())
+    losses = {}
+    for graphs in (False, True):
+        model = CRFP_DSV("cuda", mid_channels=32)
+        model.load_state_dict(sd, strict=True)
+        model.cuda()
+        tr = Trainer(model, freeze_flow_iters=0, use_graphs=graphs)
+        losses[graphs] = [tr.step(*args).item() for _ in range(6)]
+        if graphs:
+            assert tr.use_graphs and len(tr._graphs) == 1
+    for a, b in zip(losses[False], losses[True]):
+        assert abs(a - b) < 2e-3 * abs(a), (losses[False], losses[True])      # atomics reorder sums; Adam amplifies
+    assert losses[True][-1] < losses[True][0]
