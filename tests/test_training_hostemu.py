@@ -56,7 +56,8 @@ def test_layout_views_match_torch():
     assert torch.equal(got, ref)
 
 
-@pytest.mark.parametrize("n,t,h,w", [(1, 3, 8, 8), (2, 2, 8, 16)])
+@pytest.mark.parametrize("n,t,h,w", [(1, 3, 8, 8), (2, 2, 8, 16),
+                                     (1, 2, 12, 20)])      # h, w not multiples of 8: FNet resamples 8x16 -> 12x20
 def test_forward_and_every_parameter_gradient_match_the_oracle(n, t, h, w):
     sd, model, lrs, fvs, mks, hr = _setup(1, n, t, h, w)
     model.train()
@@ -83,8 +84,33 @@ def test_forward_and_every_parameter_gradient_match_the_oracle(n, t, h, w):
         rel2 = ((g - rg).norm() / rg.norm()).item()
         relmax = (g - rg).abs().max().item() / scale
         worst = max(worst, rel2)
-        assert rel2 < 2e-3 and relmax < 3e-2, (k, rel2, relmax, scale)
+        assert rel2 < (5e-3 if h % 8 else 2e-3) and relmax < 3e-2, (k, rel2, relmax, scale)   # (resampled flows: noisier)
     print(f"worst relative L2 gradient error over {len(names)} tensors: {worst:.2e}")
+
+
+def test_single_frame_clip_trains_everything_but_the_alignment_path():
+    """t == 1: no flow, no warp, no DCN (CRFP.py:1637-1668 branch only): their parameters get no gradient at all, like in
+    the reference; every other gradient matches."""
+    sd, model, lrs, fvs, mks, hr = _setup(7, 2, 1, 8, 8)
+    model.train()
+    sr = forward_train(model, lrs, fvs, mks, K)
+    sdg = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    ref = oracle_forward_with_grad(sdg, lrs, fvs, mks)
+    assert (sr - ref).abs().max().item() < 1e-4
+    names = list(sdg.keys())
+    ref_grads = torch.autograd.grad(charbonnier(ref, hr), [sdg[k] for k in names], allow_unused=True)
+    charbonnier(sr, hr).backward()
+    params = dict(model.named_parameters())
+    unused = 0
+    for k, rg in zip(names, ref_grads):
+        g = params[k].grad
+        if rg is None:
+            unused += 1
+            assert g is None or g.abs().max().item() == 0, k
+            assert k.startswith(("spynet.", "dcn_", "downsample.")), k
+        else:
+            assert ((g - rg).norm() / rg.norm()).item() < 1e-3, k
+    assert unused > 40
 
 
 def test_trainer_step_matches_torch_adam_on_the_oracle():
