@@ -220,6 +220,32 @@ def test_model_gradients_match_the_oracle(A, n, t, h, w):
     assert rels[len(rels) // 2] < 1e-3
 
 
+def test_loss_and_gradients_match_the_real_reference_fixture(A, golden_dir):
+    """tests/golden/train_dsv_n2_t2_8x16.pt: loss + gradients of the REAL reference's training iteration (reference model in
+    train() mode, reference CharbonnierLoss, loss.backward(); oracle/make_golden_train.py)."""
+    import os
+    from crfp_b200 import CRFP_DSV
+    from crfp_b200.synthetic import make_clip, make_state_dict
+    fix = torch.load(os.path.join(golden_dir, "train_dsv_n2_t2_8x16.pt"))
+    c = fix["case"]
+    sd = make_state_dict(seed=1)
+    lrs, fvs, mks, _ = make_clip(seed=c["seed"], n=c["n"], t=c["t"], h=c["h"], w=c["w"], fv_size=c["fv"])
+    hr = torch.rand(c["n"], c["t"], 3, 8 * c["h"], 8 * c["w"], generator=_g(c["hr_seed"]))
+    model = CRFP_DSV("cuda", mid_channels=32)
+    model.load_state_dict(sd, strict=True)
+    model.cuda().train()
+    sr = model(lrs.cuda(), fvs.cuda(), mks.cuda())
+    nt = c["n"] * c["t"]
+    loss = A.charbonnier_loss(A.CUDA, sr.reshape(nt, 3, *sr.shape[-2:]), hr.cuda().reshape(nt, 3, *sr.shape[-2:]))
+    loss.backward()
+    assert abs(loss.item() - fix["loss"]) < 5e-5
+    params = dict(model.named_parameters())
+    for k, nrm in fix["grad_norms"].items():
+        assert abs(params[k].grad.norm().item() - nrm) <= 1e-2 * nrm, k
+    for k, g in fix["grads"].items():
+        assert ((params[k].grad.cpu() - g).norm() / g.norm()).item() < 1e-2, k
+
+
 def test_trainer_steps_reduce_the_loss_and_refresh_inference_weights(A):
     from crfp_b200 import CRFP_DSV
     from crfp_b200.synthetic import make_clip, make_state_dict

@@ -191,3 +191,25 @@ def test_psnr_matches_reference_formula():
     per = psnr(a, b, batch_avg=True)
     assert per.shape == (2,) and abs(float(per[0]) - (-20 * math.log10(math.sqrt(((a[0] - b[0]) ** 2).mean().item())))) < 1e-5
     assert math.isfinite(float(psnr(a, a))) and float(psnr(a, a)) > 60
+
+
+def test_training_and_spynet_refuse_cpu_tensors():
+    """No CPU fallback anywhere: the training forward, the loss and SPyNet raise on CPU tensors instead of computing."""
+    import pytest
+    import torch
+    from crfp_b200 import CRFP_DSV, SPyNet, _lib
+    from crfp_b200 import autograd as A
+    from crfp_b200.synthetic import make_clip
+    from crfp_b200.training import forward_train
+    lrs, fvs, mks, _ = make_clip(seed=0, n=1, t=2, h=8, w=8, fv_size=16)
+    model = CRFP_DSV("cuda", mid_channels=32).train()
+    with pytest.raises(_lib.CrfpError):
+        forward_train(model, lrs, fvs, mks)                       # default kernel set = the CUDA library
+    with pytest.raises(_lib.CrfpError):
+        model(lrs, fvs, mks)                                      # module entry, training mode
+    with pytest.raises(_lib.CrfpError):
+        A.charbonnier_loss(A.CUDA, torch.rand(1, 3, 4, 4), torch.rand(1, 3, 4, 4))
+    with pytest.raises(_lib.CrfpError):
+        A.conv3x3(A.CUDA, torch.rand(4, 4, 3, 3), torch.rand(4), [torch.rand(1, 5, 5, 4)])
+    with pytest.raises(_lib.CrfpError):
+        SPyNet(None, "cpu")(torch.rand(1, 3, 32, 32), torch.rand(1, 3, 32, 32))

@@ -186,3 +186,38 @@ def test_two_rank_step_equals_the_single_process_step_on_both_clips(tmp_path):
     assert abs(loss.item() - 0.5 * (r0["loss"].item() + r1["loss"].item())) < 1e-6
     gn = tr.flat_g.norm().item()
     assert (tr.flat_g - r0["g"]).norm().item() < 1e-4 * gn                         # mean of per-rank grads == batch grad
+
+
+@pytest.mark.parametrize("name", ["train_dsv_n1_t3_8x8", "train_dsv_n2_t2_8x16"])
+def test_loss_and_gradients_match_the_real_reference_fixture(name, golden_dir):
+    """tests/golden/train_*.pt = loss and gradients of the REAL reference (`CRFP_DSV.train()`, the reference's own
+    CharbonnierLoss, loss.backward(); oracle/make_golden_train.py).  Both the oracle's autograd and the product's
+    training step (backward kernels through the host emulation) must reproduce them."""
+    import os
+    fix = torch.load(os.path.join(golden_dir, name + ".pt"))
+    c = fix["case"]
+    sd = make_state_dict(seed=1)
+    assert abs(float(sum(v.double().sum() for v in sd.values())) - fix["weights_sum"]) < 1e-6
+    lrs, fvs, mks, _ = make_clip(seed=c["seed"], n=c["n"], t=c["t"], h=c["h"], w=c["w"], fv_size=c["fv"])
+    hr = torch.rand(c["n"], c["t"], 3, 8 * c["h"], 8 * c["w"], generator=torch.Generator().manual_seed(c["hr_seed"]))
+    # the oracle
+    sdg = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    oloss = charbonnier(oracle_forward_with_grad(sdg, lrs, fvs, mks), hr)
+    ograds = dict(zip(sdg.keys(), torch.autograd.grad(oloss, list(sdg.values()))))
+    assert abs(oloss.item() - fix["loss"]) < 1e-6
+    for k, nrm in fix["grad_norms"].items():
+        assert abs(ograds[k].norm().item() - nrm) <= 1e-5 * nrm, k
+    for k, g in fix["grads"].items():
+        assert (ograds[k] - g).abs().max().item() <= 1e-6 * g.abs().max().item(), k
+    # the product path
+    model = CRFP_DSV("cuda", mid_channels=32)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    loss = charbonnier(forward_train(model, lrs, fvs, mks, K), hr)
+    loss.backward()
+    assert abs(loss.item() - fix["loss"]) < 1e-5
+    params = dict(model.named_parameters())
+    for k, nrm in fix["grad_norms"].items():
+        assert abs(params[k].grad.norm().item() - nrm) <= 5e-3 * nrm, k
+    for k, g in fix["grads"].items():
+        assert ((params[k].grad - g).norm() / g.norm()).item() < 2e-3, k
