@@ -6,6 +6,7 @@ Public surface (mirrors the reference's module API, /root/reference/model/CRFP.p
     flow_warp(x, flow), DCNv2(...)(input, offset, mask)
     SPyNet(pretrained, device).forward(ref, supp)                       (legacy flow pyramid, model/CRFP.py:554-741)
     Trainer(model, ...).step(lrs, fvs, mks, hr)                         (one iteration of trainer.py:206-293)
+    crfp_b200.runtime.MRCF_simple_v18(...).forward(lrs, fvs, warp_size) (model/CRFP_runtime.py:8364-8682)
 Everything below these signatures runs in libcrfp_b200.so (include/crfp_b200.h); there is no CPU fallback.
 """
 from .model import CRFP, CRFP_DSV, CRFP_simple, MRCF_simple_v18  # noqa: F401

@@ -22,14 +22,14 @@ def pixel_shuffle_nhwc(x, r):
     """F.pixel_shuffle(r) (model/CRFP.py:187-193) on NHWC: channel o*r*r + dy*r + dx -> pixel (y*r+dy, x*r+dx), ch o."""
     n, h, w, c = x.shape
     o = c // (r * r)
-    return x.view(n, h, w, o, r, r).permute(0, 1, 4, 2, 5, 3).reshape(n, h * r, w * r, o)
+    return x.reshape(n, h, w, o, r, r).permute(0, 1, 4, 2, 5, 3).reshape(n, h * r, w * r, o)
 
 
 def pixel_unshuffle_nhwc(x, r):
     """pixel_unshuffle (model/CRFP.py:28-42) on NHWC: (n,h*r,w*r,c) -> (n,h,w,c*r*r), channel c*r*r + dy*r + dx."""
     n, hr, wr, c = x.shape
     h, w = hr // r, wr // r
-    return x.view(n, h, r, w, r, c).permute(0, 1, 3, 5, 2, 4).reshape(n, h, w, c * r * r)
+    return x.reshape(n, h, r, w, r, c).permute(0, 1, 3, 5, 2, 4).reshape(n, h, w, c * r * r)
 
 
 class _Net:

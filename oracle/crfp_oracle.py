@@ -457,3 +457,73 @@ def spynet(sd, ref, supp, prefix=""):
     flow = F.interpolate(spynet_compute_flow(sd, ref, supp, prefix), size=(h, w), mode="bilinear", align_corners=False)
     scale = flow.new_tensor([float(w) / float(w_up), float(h) / float(h_up)]).view(1, 2, 1, 1)
     return flow * scale
+
+
+# ----------------------------------------------------------------------------- CRFP_runtime.MRCF_simple_v18
+def _rt_res_blocks(sd, name, feat1, feat2=None):
+    """ResidualBlocksWithInputConv / _v2 of the runtime file (CRFP_runtime.py:464-556): `conv1(feat1)` pasted into the
+    top-left corner of `conv2(feat2)` when a second (larger) input is given, LeakyReLU, then ONE bottleneck
+    ResidualBlockNoBN (C -> C/2 -> C, CRFP_runtime.py:406-462; `main` = [LeakyReLU, Sequential(block)])."""
+    o1 = conv3x3(feat1, sd, name + ".conv1")
+    if feat2 is not None:
+        feat = conv3x3(feat2, sd, name + ".conv2").clone()
+        feat[:, :, :o1.shape[2], :o1.shape[3]] = o1
+    else:
+        feat = o1
+    x = lrelu(feat)
+    return x + conv3x3(F.relu(conv3x3(x, sd, name + ".main.1.0.conv1")), sd, name + ".main.1.0.conv2")
+
+
+@torch.no_grad()
+def runtime_v18_forward(sd, lrs, fvs, warp_size=(1080, 1920), mid_channels=32):
+    """CRFP_runtime.MRCF_simple_v18.forward(lrs, fvs, warp_size) (CRFP_runtime.py:8472-8664), the timing harness of
+    test_runtime.py: alignment (flow, warps, DCN, state) only inside the top-left `warp_size` (HR pixels) region, `fvs`
+    an HR image of its own size anchored at the top-left corner and fused WITHOUT a mask, no level-to-level propagation
+    of the residual-block outputs after the first frame (CRFP_runtime.py:8552,8567,8582: commented out)."""
+    C = mid_channels
+    WP_h, WP_w = warp_size
+    n, t, c, h, w = lrs.shape
+    flows = compute_flow(sd, lrs[:, :, :, :WP_h // 8, :WP_w // 8]) if t > 1 else None
+    lrs0 = lrs.reshape(n * t, c, h, w)
+    x_lr = lrelu(conv3x3(lrelu(conv3x3(lrs0, sd, "encoder_lr.slice1.0")), sd, "encoder_lr.slice1.2")).view(n, t, -1, h, w)
+    fh, fw = fvs.shape[-2:]
+    f0 = fvs.reshape(n * t, c, fh, fw)
+    x_hr = lrelu(conv3x3(lrelu(conv3x3(torch.cat((f0, f0), 1), sd, "encoder_hr.slice1.0")), sd, "encoder_hr.slice1.2"))
+    x_hr = x_hr.view(n, t, -1, fh, fw)
+    q4 = C // 4
+    outs, S, feats = [], None, [None] * 3
+    for i in range(t):
+        prop = pixel_shuffle_pack(x_lr[:, i], sd, "upsample", 2)
+        if i > 0:
+            flow = flows[:, i - 1]
+            flow_lv3 = up_bilinear(flow, 2) * 2.0
+            flow_lv0 = up_bilinear(flow, 8) * 8.0
+            S0 = S
+            S0_w = flow_warp(S0, flow_lv0)
+            P_w = conv3x3(F.pixel_unshuffle(S0_w, 4), sd, "downsample.downsample_conv")
+            P = conv3x3(F.pixel_unshuffle(S0, 4), sd, "downsample.downsample_conv")
+            feats = list(torch.chunk(flow_warp(torch.cat(feats, dim=1), flow_lv3), 3, dim=1))
+            offfeat = None
+            for k in range(3):
+                cur = torch.cat((prop[:, :, :WP_h // 4, :WP_w // 4], feats[k]), dim=1)
+                A, offfeat = dcn_module(sd, f"dcn_{k}", cur, P, P_w, flow_lv3, offfeat, dg=8)
+                y = _rt_res_blocks(sd, f"forward_resblocks_{k}", torch.cat([cur, A], dim=1), cur)
+                feats[k] = y[:, 3 * q4:][:, :, :WP_h // 4, :WP_w // 4]
+            q = lrelu(pixel_shuffle_pack(prop, sd, "upsample_post", 4))
+            qc = q[:, :, :WP_h, :WP_w]
+            A3, _ = dcn_module(sd, "dcn_3", qc, S0, S0_w, flow_lv0, offfeat, dg=1, repeat=True, pixelshuffle=True)
+            S = _rt_res_blocks(sd, "forward_resblocks_3", torch.cat([qc, A3], dim=1), q)
+        else:
+            for k in range(3):
+                y = _rt_res_blocks(sd, f"forward_resblocks_{k}_", prop)
+                feats[k] = y[:, 3 * q4:][:, :, :WP_h // 4, :WP_w // 4]
+                prop = y[:, :3 * q4]
+            q = lrelu(pixel_shuffle_pack(prop, sd, "upsample_post", 4))
+            S = _rt_res_blocks(sd, "forward_resblocks_3_", q)
+        Fz = conv3x3(torch.cat([S[:, :, :fh, :fw], x_hr[:, i]], dim=1), sd, "conv_tttf")
+        S = S.clone()
+        S[:, :, :fh, :fw] = Fz
+        S = lrelu(S)
+        outs.append(conv3x3(S, sd, "conv_last") + up_bilinear(lrs[:, i], 8))
+        S = S[:, :, :WP_h, :WP_w]
+    return torch.stack(outs, dim=1)
