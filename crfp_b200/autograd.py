@@ -4,7 +4,8 @@ The reference trains through ATen/cuDNN autograd and `dcn_v2`'s own backward (`l
 /root/reference/trainer.py:246-250).  Here torch.autograd is only the tape (it records which op consumed which
 tensor across the t-frame recurrence, i.e. BPTT); the arithmetic of each node is a hand-written kernel behind the C ABI:
 
-  Conv3x3Fn     crfp_conv3x3_fwd  | crfp_act_bwd, crfp_conv3x3_bwd_data, crfp_conv3x3_bwd_weight   (nn.Conv2d + act)
+  Conv3x3Fn     crfp_conv3x3_fwd  | crfp_act_bwd; data: crfp_conv3x3_fwd again on the rotated / transposed weights (or the
+                                    gather kernels crfp_conv3x3_bwd_data, CRFP_DGRAD=direct); crfp_conv3x3_bwd_weight   (nn.Conv2d + act)
   DCNv2Fn       crfp_dcn_v2_fwd   | crfp_dcn_v2_bwd                        (dcn_v2.DCNv2, model/CRFP.py:350)
   FlowWarpFn    crfp_flow_warp_fwd| crfp_flow_warp_bwd                     (flow_warp, model/CRFP.py:90-130)
   ResizeFn      crfp_resize_bilinear | crfp_resize_bilinear_bwd            (nn.Upsample / F.interpolate, bilinear)
