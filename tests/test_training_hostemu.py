@@ -221,3 +221,16 @@ def test_loss_and_gradients_match_the_real_reference_fixture(name, golden_dir):
         assert abs(params[k].grad.norm().item() - nrm) <= 5e-3 * nrm, k
     for k, g in fix["grads"].items():
         assert ((params[k].grad - g).norm() / g.norm()).item() < 2e-3, k
+
+
+def test_graph_capture_failure_falls_back_to_eager_steps():
+    """Trainer(use_graphs=True) where capture is impossible (no CUDA here): the third step's capture attempt raises, the
+    trainer warns, switches graphs off and keeps training eagerly with consistent state."""
+    sd, model, lrs, fvs, mks, hr = _setup(3, 1, 2, 8, 8)
+    tr = Trainer(model, freeze_flow_iters=0, kernels=K, use_graphs=True)
+    losses = [tr.step(lrs, fvs, mks, hr).item() for _ in range(2)]
+    with pytest.warns(UserWarning, match="graph capture failed"):
+        losses.append(tr.step(lrs, fvs, mks, hr).item())
+    assert tr.use_graphs is False and not tr._graphs
+    losses.append(tr.step(lrs, fvs, mks, hr).item())
+    assert tr.cur_iter == 4 and tr.group_steps == [4, 4] and losses[-1] < losses[0]
