@@ -35,6 +35,9 @@ class KernelSet:
     # backward-data through the tiled forward conv kernel (default) or the direct gather kernel crfp_conv3x3_bwd_data
     # (CRFP_DGRAD=direct; kept for A/B and for shapes the forward kernel would not take)
     dgrad_as_conv = os.environ.get("CRFP_DGRAD", "conv") != "direct"
+    # weight gradient of the thin layers: same-line atomics (default, the B200-verified path) or the two-stage reduction
+    # (CRFP_WGRAD_THIN=2stage; CPU-emulation-verified, to be measured and made the default in round 2)
+    wgrad_two_stage = os.environ.get("CRFP_WGRAD_THIN", "atomic") == "2stage"
 
     def lib(self):
         return L.lib()
@@ -161,8 +164,14 @@ class Conv3x3Fn(torch.autograd.Function):
             dbt = torch.zeros(cout, device=dy.device, dtype=torch.float32)
             off = 0
             for i, c in enumerate(ctx.c_list):
+                ws, ws_floats = None, 0
+                if K.wgrad_two_stage:       # opt-in: partial sums + a reduce kernel for the thin (4-channel HR) layers
+                    ws_floats = lib.crfp_conv3x3_bwd_weight_workspace(n, h, w, c, cout)
+                    if ws_floats:
+                        ws = torch.empty(ws_floats, device=dy.device, dtype=torch.float32)
                 _chk(K, lib.crfp_conv3x3_bwd_weight(n, h, w, c, cout, cin, off, srcs[i].data_ptr(), g.data_ptr(),
-                                                    dw.data_ptr(), dbt.data_ptr() if i == 0 else None, st),
+                                                    dw.data_ptr(), dbt.data_ptr() if i == 0 else None,
+                                                    ws.data_ptr() if ws is not None else None, ws_floats, st),
                      "conv3x3_bwd_weight")
                 off += c
             if need_w:

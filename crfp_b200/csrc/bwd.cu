@@ -118,12 +118,15 @@ __global__ void __launch_bounds__(256) conv3x3_bwd_data_v4_kernel(int n, int h, 
 // Thread mapping (host-chosen): plain — one thread per weight element, 128 per CTA, unit-stride pixel loop;
 // pixel lanes (few elements, the 4-channel HR layers: `lanes` > 1) — the CTA holds `lanes` copies of the `epad`-padded
 // element set and copy `pl` takes every lanes-th pixel, so that the CTA's threads are not mostly idle.
-template <bool UNIT>   // UNIT: plain mapping (lanes == 1), unit-stride pixel loop with compile-time pointer increments
+// PARTIAL (pixel-lane mapping only): instead of the atomics, every (chunk, lane) writes its partial sums to row
+// blockIdx.y * lanes + pl of `partial` ([rows][taps*cin*cout + cout], the bias partials behind the weights) and
+// wgrad_reduce_kernel adds the rows up: no same-cache-line atomic contention, so the chunk count is free to grow.
+template <bool UNIT, bool PARTIAL>   // UNIT: plain mapping (lanes == 1), unit-stride loop with compile-time pointer increments
 __global__ void __launch_bounds__(128) conv_bwd_weight_kernel(int rows, int h, int w, int cin, int cout, int taps,
                                                               int cin_total, int cin_off, int rows_per_block, int xsegs,
                                                               int lanes, int epad, const float* __restrict__ x,
                                                               const float* __restrict__ g, float* __restrict__ dw,
-                                                              float* __restrict__ db) {
+                                                              float* __restrict__ db, float* __restrict__ partial) {
   const int e = UNIT ? (int)(blockIdx.x * blockDim.x + threadIdx.x) : (int)(threadIdx.x % epad);
   const int pl = UNIT ? 0 : (int)(threadIdx.x / epad);
   const int step = UNIT ? 1 : lanes;
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_kernel(int rows, int h, i
   const int ci = (e / cout) % cin;
   const int tap = e / (cout * cin);
   const int ky = (taps == 9) ? tap / 3 : 1, kx = (taps == 9) ? tap % 3 : 1;
-  const bool do_bias = (db != nullptr) && ci == 0 && tap == ((taps == 9) ? 4 : 0);
+  const bool do_bias = (PARTIAL || db != nullptr) && ci == 0 && tap == ((taps == 9) ? 4 : 0);
   // blockIdx.y = (row block, column segment): rows [r0, r1), columns [c0, c1)
   const long long r0 = (long long)(blockIdx.y / xsegs) * rows_per_block;
   long long r1 = r0 + rows_per_block;
@@ -153,18 +156,24 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_kernel(int rows, int h, i
 #pragma unroll 4
     for (int xx = xlo + pl; xx < xhi; xx += step) acc += gp[(long long)xx * cout] * xp[(long long)(xx + kx - 1) * cin];
   }
+  if (PARTIAL) {
+    float* prow = partial + ((long long)blockIdx.y * lanes + pl) * ((long long)taps * cin * cout + cout);
+    prow[e] = acc;
+    if (ci == 0 && tap == ((taps == 9) ? 4 : 0)) prow[(long long)taps * cin * cout + co] = gsum;
+    return;
+  }
   atomicAdd(dw + ((long long)tap * cin_total + cin_off + ci) * cout + co, acc);
   if (do_bias) atomicAdd(db + co, gsum);
 }
 
 // Register-tiled variant for cin % 4 == 0 and cout % 4 == 0: one thread per (tap, 4 ci, 4 co) block of dw; per pixel
 // 2 LDG.128 (x: warp broadcast over the co blocks, g: coalesced) feed 16 FMAs.
-template <bool UNIT>
+template <bool UNIT, bool PARTIAL>
 __global__ void __launch_bounds__(128) conv_bwd_weight_v4_kernel(int rows, int h, int w, int cin, int cout, int taps,
                                                                  int cin_total, int cin_off, int rows_per_block, int xsegs,
                                                                  int lanes, int epad, const float* __restrict__ x,
                                                                  const float* __restrict__ g, float* __restrict__ dw,
-                                                                 float* __restrict__ db) {
+                                                                 float* __restrict__ db, float* __restrict__ partial) {
   const int cq = cin >> 2, oq = cout >> 2;
   const int e = UNIT ? (int)(blockIdx.x * blockDim.x + threadIdx.x) : (int)(threadIdx.x % epad);
   const int pl = UNIT ? 0 : (int)(threadIdx.x / epad);
@@ -174,7 +183,7 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_v4_kernel(int rows, int h
   const int ci = ((e / oq) % cq) * 4;
   const int tap = e / (oq * cq);
   const int ky = (taps == 9) ? tap / 3 : 1, kx = (taps == 9) ? tap % 3 : 1;
-  const bool do_bias = (db != nullptr) && ci == 0 && tap == ((taps == 9) ? 4 : 0);
+  const bool do_bias = (PARTIAL || db != nullptr) && ci == 0 && tap == ((taps == 9) ? 4 : 0);
   const long long r0 = (long long)(blockIdx.y / xsegs) * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
@@ -207,11 +216,40 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_v4_kernel(int rows, int h
       acc[3][0] += xv.w * gv.x; acc[3][1] += xv.w * gv.y; acc[3][2] += xv.w * gv.z; acc[3][3] += xv.w * gv.w;
     }
   }
+  if (PARTIAL) {
+    float* prow = partial + ((long long)blockIdx.y * lanes + pl) * ((long long)taps * cin * cout + cout);
+    float* pd = prow + ((long long)tap * cin + ci) * cout + co;
+    for (int a = 0; a < 4; ++a)
+      for (int c = 0; c < 4; ++c) pd[(long long)a * cout + c] = acc[a][c];
+    if (ci == 0 && tap == ((taps == 9) ? 4 : 0)) {
+      float* pb = prow + (long long)taps * cin * cout + co;
+      pb[0] = gsum.x; pb[1] = gsum.y; pb[2] = gsum.z; pb[3] = gsum.w;
+    }
+    return;
+  }
   float* d = dw + ((long long)tap * cin_total + cin_off + ci) * cout + co;
   for (int a = 0; a < 4; ++a)
     for (int c = 0; c < 4; ++c) atomicAdd(d + (long long)a * cout + c, acc[a][c]);
   if (do_bias) {
     atomicAdd(db + co, gsum.x); atomicAdd(db + co + 1, gsum.y); atomicAdd(db + co + 2, gsum.z); atomicAdd(db + co + 3, gsum.w);
+  }
+}
+
+// second stage of the PARTIAL mode: one thread per weight (and bias) element sums the `prows` partial rows
+__global__ void __launch_bounds__(128) wgrad_reduce_kernel(int prows, int taps, int cin, int cout, int cin_total, int cin_off,
+                                                           const float* __restrict__ partial, float* __restrict__ dw,
+                                                           float* __restrict__ db) {
+  const int elems = taps * cin * cout;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= elems + cout) return;
+  float sum = 0.f;
+  const long long pitch = (long long)elems + cout;
+  for (int p = 0; p < prows; ++p) sum += partial[p * pitch + idx];
+  if (idx < elems) {
+    const int co = idx % cout, ci = (idx / cout) % cin, tap = idx / (cout * cin);
+    atomicAdd(dw + ((long long)tap * cin_total + cin_off + ci) * cout + co, sum);
+  } else if (db != nullptr) {
+    atomicAdd(db + (idx - elems), sum);
   }
 }
 
@@ -223,8 +261,52 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
   return x < lo ? lo : (x > hi ? hi : x);
 }
 
+// two-stage (PARTIAL) geometry of a thin layer: pixel lanes per CTA and number of partial rows; 0 rows = not a thin layer
+static void thin_plan(long long rows, int w, int cin, int cout, int taps, bool v4, int* lanes, int* epad, long long* chunks,
+                      int* xsegs, long long* rpb) {
+  const int elems = v4 ? taps * (cin / 4) * (cout / 4) : taps * cin * cout;
+  *lanes = 1; *epad = 0; *chunks = 0; *xsegs = 1; *rpb = 1;
+  if (elems > 64) return;
+  *epad = 16;
+  while (*epad < elems) *epad *= 2;
+  *lanes = 128 / *epad;
+  long long c = 8192 / *lanes;                      // <= 8192 partial rows (a few MB), ~1e5 threads in flight
+  if (c <= rows) {
+    *rpb = (rows + c - 1) / c;
+  } else {
+    *xsegs = (int)(c / rows);
+    if (*xsegs > w / (32 * *lanes)) *xsegs = w / (32 * *lanes);
+    if (*xsegs < 1) *xsegs = 1;
+  }
+  *chunks = ((rows + *rpb - 1) / *rpb) * *xsegs;
+  if (*chunks > 65535) { *xsegs = 1; *chunks = (rows + *rpb - 1) / *rpb; }
+}
+
 static int launch_bwd_weight(long long rows, int h, int w, int cin, int cout, int taps, int cin_total, int cin_off,
-                             const float* x, const float* g, float* dw, float* db, cudaStream_t st) {
+                             const float* x, const float* g, float* dw, float* db, cudaStream_t st,
+                             float* workspace = nullptr, size_t ws_floats = 0) {
+  if (workspace != nullptr) {                       // two-stage reduction for the thin layers (opt-in by the caller)
+    const bool v4t = (cin % 4 == 0) && (cout % 4 == 0) && aligned16(x) && aligned16(g);
+    int lanes_t, epad_t, xsegs_t;
+    long long chunks_t, rpb_t;
+    thin_plan(rows, w, cin, cout, taps, v4t, &lanes_t, &epad_t, &chunks_t, &xsegs_t, &rpb_t);
+    const long long pitch = (long long)taps * cin * cout + cout;
+    if (chunks_t > 0 && (size_t)(chunks_t * lanes_t * pitch) <= ws_floats) {
+      const dim3 grid(1, (unsigned)chunks_t), block(128);
+      float* nobias = nullptr;
+      if (v4t)
+        CRFP_LAUNCH((conv_bwd_weight_v4_kernel<false, true>), grid, block, st, (int)rows, h, w, cin, cout, taps, cin_total,
+                    cin_off, (int)rpb_t, xsegs_t, lanes_t, epad_t, x, g, dw, nobias, workspace);
+      else
+        CRFP_LAUNCH((conv_bwd_weight_kernel<false, true>), grid, block, st, (int)rows, h, w, cin, cout, taps, cin_total,
+                    cin_off, (int)rpb_t, xsegs_t, lanes_t, epad_t, x, g, dw, nobias, workspace);
+      CRFP_TRY(check_launch());
+      const int total = taps * cin * cout + cout;
+      CRFP_LAUNCH(wgrad_reduce_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), st, (int)(chunks_t * lanes_t), taps,
+                  cin, cout, cin_total, cin_off, (const float*)workspace, dw, db);
+      return check_launch();
+    }
+  }
   const bool v4 = (cin % 4 == 0) && (cout % 4 == 0) && aligned16(x) && aligned16(g);   // (dw is only touched by atomics)
   const int elems = v4 ? taps * (cin / 4) * (cout / 4) : taps * cin * cout;
   // A/B knobs (read once): CTA size cap for the plain mapping and the thread target that sizes the pixel chunks
@@ -264,11 +346,12 @@ static int launch_bwd_weight(long long rows, int h, int w, int cin, int cout, in
   unsigned gy = (unsigned)((rows + rpb - 1) / rpb);
   if ((long long)gy * xsegs > 65535) xsegs = (int)(65535 / gy);
   gy *= (unsigned)xsegs;
-#define CRFP_WGRAD_ARGS (int)rows, h, w, cin, cout, taps, cin_total, cin_off, (int)rpb, xsegs, lanes, epad, x, g, dw, db
-  if (v4 && lanes == 1) CRFP_LAUNCH(conv_bwd_weight_v4_kernel<true>, dim3(gx, gy), dim3(bd), st, CRFP_WGRAD_ARGS);
-  else if (v4) CRFP_LAUNCH(conv_bwd_weight_v4_kernel<false>, dim3(gx, gy), dim3(bd), st, CRFP_WGRAD_ARGS);
-  else if (lanes == 1) CRFP_LAUNCH(conv_bwd_weight_kernel<true>, dim3(gx, gy), dim3(bd), st, CRFP_WGRAD_ARGS);
-  else CRFP_LAUNCH(conv_bwd_weight_kernel<false>, dim3(gx, gy), dim3(bd), st, CRFP_WGRAD_ARGS);
+  float* nopartial = nullptr;
+#define CRFP_WGRAD_ARGS (int)rows, h, w, cin, cout, taps, cin_total, cin_off, (int)rpb, xsegs, lanes, epad, x, g, dw, db, nopartial
+  if (v4 && lanes == 1) CRFP_LAUNCH((conv_bwd_weight_v4_kernel<true, false>), dim3(gx, gy), dim3(bd), st, CRFP_WGRAD_ARGS);
+  else if (v4) CRFP_LAUNCH((conv_bwd_weight_v4_kernel<false, false>), dim3(gx, gy), dim3(bd), st, CRFP_WGRAD_ARGS);
+  else if (lanes == 1) CRFP_LAUNCH((conv_bwd_weight_kernel<true, false>), dim3(gx, gy), dim3(bd), st, CRFP_WGRAD_ARGS);
+  else CRFP_LAUNCH((conv_bwd_weight_kernel<false, false>), dim3(gx, gy), dim3(bd), st, CRFP_WGRAD_ARGS);
 #undef CRFP_WGRAD_ARGS
   return check_launch();
 }
@@ -579,11 +662,28 @@ extern "C" int crfp_conv3x3_bwd_data(int n, int h, int w, int cin, int cout, int
 }
 
 extern "C" int crfp_conv3x3_bwd_weight(int n, int h, int w, int cin, int cout, int cin_total, int cin_off, const float* x,
-                                       const float* g, float* dw, float* db, crfp_stream stream) {
+                                       const float* g, float* dw, float* db, float* workspace, size_t ws_floats,
+                                       crfp_stream stream) {
   if (n < 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || cin_off < 0 || cin_off + cin > cin_total) return CRFP_ERR_BAD_SHAPE;
   if (n == 0) return CRFP_OK;
   if (!x || !g || !dw) return CRFP_ERR_NULL;
-  return launch_bwd_weight((long long)n * h, h, w, cin, cout, 9, cin_total, cin_off, x, g, dw, db, (cudaStream_t)stream);
+  return launch_bwd_weight((long long)n * h, h, w, cin, cout, 9, cin_total, cin_off, x, g, dw, db, (cudaStream_t)stream,
+                           workspace, ws_floats);
+}
+
+extern "C" size_t crfp_conv3x3_bwd_weight_workspace(int n, int h, int w, int cin, int cout) {
+  if (n <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0) return 0;
+  int lanes, epad, xsegs;
+  long long chunks, rpb;
+  thin_plan((long long)n * h, w, cin, cout, 9, (cin % 4 == 0) && (cout % 4 == 0), &lanes, &epad, &chunks, &xsegs, &rpb);
+  if (chunks <= 0) return 0;
+  // sized for the scalar mapping as well (an unaligned pointer falls back to it): it never needs more rows
+  int lanes_s, epad_s, xsegs_s;
+  long long chunks_s, rpb_s;
+  thin_plan((long long)n * h, w, cin, cout, 9, false, &lanes_s, &epad_s, &chunks_s, &xsegs_s, &rpb_s);
+  long long prows = chunks * lanes;
+  if (chunks_s * lanes_s > prows) prows = chunks_s * lanes_s;
+  return (size_t)(prows * (9LL * cin * cout + cout));
 }
 
 extern "C" int crfp_dcn_v2_bwd(const crfp_dcn_bwd_desc* d, crfp_stream stream) {

@@ -446,7 +446,11 @@ int crfp_conv3x3_bwd_data(int n, int h, int w, int cin, int cout, int cin_total,
 /* backward-weight: rows [cin_off, cin_off+cin) of dw[tap][cin_total][cout] (accumulated) from x[n,h,w,cin] (dense) and
  * g[n,h,w,cout]; db[cout] (accumulated; pass it with one source only, NULL otherwise) */
 int crfp_conv3x3_bwd_weight(int n, int h, int w, int cin, int cout, int cin_total, int cin_off, const float* x,
-                            const float* g, float* dw, float* db, crfp_stream stream);
+                            const float* g, float* dw, float* db, float* workspace, size_t ws_floats, crfp_stream stream);
+/* optional two-stage reduction for the thin (few-channel) layers: with a workspace of at least this many floats (0 = the
+ * layer is not thin, pass NULL) the pixel chunks write partial sums there and a second kernel adds them up instead of
+ * contending for the same few cache lines of dw with atomics; workspace == NULL selects the atomic path */
+size_t crfp_conv3x3_bwd_weight_workspace(int n, int h, int w, int cin, int cout);
 /*
  * DCNv2 backward (= dcn_v2_backward): non-shared layout only (offset dg*18, mask dg*9 channels per pixel).
  *   weight   [K][cout], K = 9*c, k = (g*9+t)*(c/dg) + c_in_group (crfp_dcn_v2_fwd packing with cout % 4 == 0)

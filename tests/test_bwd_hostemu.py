@@ -33,7 +33,7 @@ def test_emulation_exports_every_training_symbol():
     h = hostemu.lib()
     for name in L.TRAIN_SYMBOLS:
         assert hasattr(h, name)
-    assert len(L.TRAIN_SYMBOLS) == 10
+    assert len(L.TRAIN_SYMBOLS) == 11
     # argument validation returns a status, never crashes
     assert h.crfp_conv3x3_bwd_data(1, 0, 4, 4, 4, 4, 0, None, None, None, None) == -1
     assert h.crfp_conv3x3_bwd_data(1, 4, 4, 4, 4, 6, 4, None, None, None, None) == -1      # slice outside cin_total
@@ -72,6 +72,31 @@ def test_conv3x3_grads(c_list, cout, hw, act, direct):
     assert (got[1] - ref_grads[1]).abs().max().item() < 2e-4
     for a, r in zip(got[2:], ref_grads[2:]):
         assert (nchw(a) - r).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("c_list,cout,hw", [([4, 4], 4, (11, 9)), ([4, 4, 2], 4, (3, 100)), ([6], 4, (6, 70)), ([4], 3, (40, 33)),
+                                            ([32], 32, (9, 13))])
+def test_conv3x3_weight_gradient_two_stage(c_list, cout, hw):
+    """CRFP_WGRAD_THIN=2stage: the thin layers' pixel chunks write partial sums to a workspace and a reduce kernel adds
+    them up (no atomics on dw); wide layers (workspace query returns 0) keep the atomic path."""
+    K2 = hostemu.HostEmuKernelSet(wgrad_two_stage=True)
+    g = _g(8)
+    h, w = hw
+    srcs = [torch.randn(2, c, h, w, generator=g, requires_grad=True) for c in c_list]
+    wt = (torch.randn(cout, sum(c_list), 3, 3, generator=g) * 0.1).requires_grad_()
+    b = (torch.randn(cout, generator=g) * 0.1).requires_grad_()
+    ref = F.leaky_relu(F.conv2d(torch.cat(srcs, 1), wt, b, padding=1), 0.1)
+    dy = torch.randn(ref.shape, generator=g)
+    rg = torch.autograd.grad(ref, [wt, b], dy)
+    w2, b2 = wt.detach().clone().requires_grad_(), b.detach().clone().requires_grad_()
+    out = A.conv3x3(K2, w2, b2, [nhwc(s.detach()) for s in srcs], 1)
+    got = torch.autograd.grad(out, [w2, b2], nhwc(dy))
+    assert (got[0] - rg[0]).abs().max().item() < 1e-5 * rg[0].abs().max().item() + 2e-4
+    assert (got[1] - rg[1]).abs().max().item() < 1e-5 * rg[1].abs().max().item() + 2e-4
+    lib = hostemu.lib()
+    c0 = c_list[0]      # thin = at most 64 threads' worth of weight elements (4x4 register tiles when both counts are % 4)
+    elems = 9 * (c0 // 4) * (cout // 4) if (c0 % 4 == 0 and cout % 4 == 0) else 9 * c0 * cout
+    assert (lib.crfp_conv3x3_bwd_weight_workspace(2, h, w, c0, cout) > 0) == (elems <= 64)
 
 
 def test_conv3x3_partial_requires_grad():

@@ -294,3 +294,24 @@ def test_graphed_trainer_tracks_the_eager_trainer(A):
     for a, b in zip(losses[False], losses[True]):
         assert abs(a - b) < 2e-3 * abs(a), (losses[False], losses[True])      # atomics reorder sums; Adam amplifies
     assert losses[True][-1] < losses[True][0]
+
+
+@pytest.mark.xfail(reason="CRFP_WGRAD_THIN=2stage was written after round 1's GPU budget was spent (CPU emulation twin passes); "
+                          "it is opt-in, the default atomic path is the verified one", strict=False)
+@pytest.mark.parametrize("c_list,cout,hw", [([4, 4], 4, (64, 96)), ([4, 4, 2], 4, (37, 45)), ([6], 4, (40, 130)), ([4], 3, (128, 128))])
+def test_conv3x3_weight_gradient_two_stage(A, c_list, cout, hw):
+    K = A.KernelSet()
+    K.wgrad_two_stage = True
+    g = _g(8)
+    h, w = hw
+    srcs = [torch.randn(2, c, h, w, generator=g) for c in c_list]
+    wt = (torch.randn(cout, sum(c_list), 3, 3, generator=g) * 0.1).requires_grad_()
+    b = (torch.randn(cout, generator=g) * 0.1).requires_grad_()
+    ref = F.leaky_relu(F.conv2d(torch.cat(srcs, 1), wt, b, padding=1), 0.1)
+    dy = torch.randn(ref.shape, generator=g)
+    rg = torch.autograd.grad(ref, [wt, b], dy)
+    w2, b2 = wt.detach().cuda().requires_grad_(), b.detach().cuda().requires_grad_()
+    out = A.conv3x3(K, w2, b2, [nhwc(s) for s in srcs], 1)
+    got = torch.autograd.grad(out, [w2, b2], nhwc(dy))
+    assert (got[0].cpu() - rg[0]).abs().max().item() < 1e-5 * rg[0].abs().max().item() + 5e-4
+    assert (got[1].cpu() - rg[1]).abs().max().item() < 1e-5 * rg[1].abs().max().item() + 5e-4

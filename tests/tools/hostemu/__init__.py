@@ -53,8 +53,9 @@ class HostEmuKernelSet:
 
     name = "hostemu"
 
-    def __init__(self, dgrad_as_conv=True):
+    def __init__(self, dgrad_as_conv=True, wgrad_two_stage=False):
         self.dgrad_as_conv = dgrad_as_conv      # False: exercise the direct crfp_conv3x3_bwd_data kernels
+        self.wgrad_two_stage = wgrad_two_stage  # True: partial sums + reduce kernel for the thin layers
 
     def lib(self):
         return lib()
