@@ -137,6 +137,18 @@ class Trainer:
         entry["graph"].replay()
         return entry["loss"].clone()
 
+    # ---- resume (the reference only saves model weights, trainer.py:276-279; the optimiser state is offered on top)
+    def state_dict(self):
+        return {"cur_iter": self.cur_iter, "group_steps": list(self.group_steps), "exp_avg": self.flat_m.clone(),
+                "exp_avg_sq": self.flat_v.clone()}
+
+    def load_state_dict(self, state):
+        if state["exp_avg"].numel() != self.flat_m.numel():
+            raise ValueError("optimizer state does not match this model")
+        self.cur_iter, self.group_steps = int(state["cur_iter"]), [int(x) for x in state["group_steps"]]
+        self.flat_m.copy_(state["exp_avg"])
+        self.flat_v.copy_(state["exp_avg_sq"])
+
     def _adam(self, train_flow):
         lib, st = self.K.lib(), self.K.stream()
         b1, b2 = self.betas

@@ -234,3 +234,21 @@ def test_graph_capture_failure_falls_back_to_eager_steps():
     assert tr.use_graphs is False and not tr._graphs
     losses.append(tr.step(lrs, fvs, mks, hr).item())
     assert tr.cur_iter == 4 and tr.group_steps == [4, 4] and losses[-1] < losses[0]
+
+
+def test_trainer_resume_continues_the_same_trajectory():
+    """model.state_dict() + Trainer.state_dict() after 2 steps, loaded into a fresh model / trainer: step 3 is identical."""
+    sd, model, lrs, fvs, mks, hr = _setup(3, 1, 2, 8, 8)
+    tr = Trainer(model, freeze_flow_iters=1, period=10, kernels=K)
+    for _ in range(2):
+        tr.step(lrs, fvs, mks, hr)
+    ckpt_model = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ckpt_opt = tr.state_dict()
+    loss_a = tr.step(lrs, fvs, mks, hr)
+    model_b = CRFP_DSV("cuda", mid_channels=32)
+    model_b.load_state_dict(ckpt_model, strict=True)
+    tr_b = Trainer(model_b, freeze_flow_iters=1, period=10, kernels=K)
+    tr_b.load_state_dict(ckpt_opt)
+    loss_b = tr_b.step(lrs, fvs, mks, hr)
+    assert loss_a.item() == loss_b.item() and tr_b.cur_iter == 3 and tr_b.group_steps == [3, 2]
+    assert torch.equal(tr.flat_p, tr_b.flat_p) and torch.equal(tr.flat_m, tr_b.flat_m)
