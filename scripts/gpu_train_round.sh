@@ -12,6 +12,7 @@ timeout 120 python scripts/bench_train.py --shape v7 --steps 5 --warmup 3 > gpur
 timeout 150 python scripts/bench_train.py --shape crop --steps 3 --warmup 4 --graphs > gpurun_out/${TAG}_train_bench_crop.json 2>> gpurun_out/${TAG}_train_err.txt
 timeout 120 python scripts/train_kernel_times.py v7 graphs > gpurun_out/${TAG}_train_kernel_times_v7.txt 2>&1
 CRFP_WGRAD_THIN=2stage timeout 120 python scripts/train_kernel_times.py v7 graphs > gpurun_out/${TAG}_train_kernel_times_v7_2stage.txt 2>&1
+CRFP_WGRAD_THIN=2stage CRFP_WGRAD_KX3=1 timeout 120 python scripts/train_kernel_times.py v7 graphs > gpurun_out/${TAG}_train_kernel_times_v7_2stage_kx3.txt 2>&1
 timeout 150 python tests/tools/torch_gpu_train_baseline.py v7 > gpurun_out/${TAG}_train_stock_pytorch_v7.txt 2>&1
 if [ -n "$NCU" ]; then
   STEPS=1 timeout 600 ncu --metrics gpu__time_duration.sum,launch__grid_size,sm__throughput.avg.pct_of_peak_sustained_elapsed,l1tex__t_sector_hit_rate.pct,sm__warps_active.avg.pct_of_peak_sustained_active \

@@ -48,7 +48,8 @@ def test_emulation_exports_every_training_symbol():
                                                 ([4, 4], 4, (11, 9), 0), ([6], 4, (6, 7), 1), ([4], 3, (5, 5), 0),
                                                 ([24, 32, 8], 32, (6, 6), 1), ([8], 12, (1, 5), 0),
                                                 ([4, 4], 4, (3, 100), 1), ([6], 4, (3, 70), 0),   # wide rows: column-segmented wgrad
-                                                ([64], 64, (40, 8), 0)])                         # several rows per wgrad chunk
+                                                ([64], 64, (40, 8), 0),                          # several rows per wgrad chunk
+                                                ([32], 32, (3, 100), 1)])                        # column segments, 4x4-tile mapping
 @pytest.mark.parametrize("direct", [False, True])
 def test_conv3x3_grads(c_list, cout, hw, act, direct):
     """direct=False: backward-data as a forward conv with the rotated / transposed kernel (the product default);
@@ -228,3 +229,16 @@ def test_charbonnier_and_adam():
         assert h.crfp_adam_step(1000, p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), 0.9, 0.999, 1e-12,
                                 2e-4 / bc1, bc2 ** 0.5, None) == 0
         assert (p - q.detach()).abs().max().item() < 3e-7      # 1 ulp of O(1) parameters
+
+
+def test_opt_in_wgrad_variants_in_a_fresh_process():
+    """CRFP_WGRAD_KX3=1 (sliding-window weight-gradient kernel) is read once per process: run the conv gradient tests
+    again in a child process with the switch on."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, CRFP_WGRAD_KX3="1")
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k", "test_conv3x3_grads",
+                          "-p", "no:cacheprovider"], env=env, capture_output=True, text=True,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
