@@ -240,6 +240,8 @@ class CRFP_DSV(_CRFPBase):
             # whole-frame inference kernels keep no intermediates to differentiate through
             if self.VARIANT != "dsv":
                 raise NotImplementedError("crfp_b200: the training forward is implemented for CRFP_DSV only")
+            if out_host is not None:
+                raise ValueError("out_host streaming is an inference feature: the training output carries grad")
             from .training import forward_train
             lrs, fvs, mks = self._check_inputs(lrs, fvs, mks)
             return forward_train(self, lrs, fvs, mks)

@@ -30,6 +30,10 @@ def annealing_cos(start, end, factor, weight=1.0):
 
 
 class Trainer:
+    """Build it AFTER the model sits on its CUDA device and keep the model there: every `p.data` / `p.grad` becomes a
+    view into the trainer's flat buffers (a later `model.to(...)` / `.half()` would silently detach them).  One instance
+    per process (= per GPU); under torch.distributed every rank calls `step` with its own clips."""
+
     def __init__(self, model, lr_rate=2e-4, lr_rate_flow=2.5e-5, beta1=0.9, beta2=0.999, eps=1e-12, rec_w=1.0,
                  period=600000, min_lr=1e-7, freeze_flow_iters=5000, process_group=None, kernels=None, use_graphs=False):
         self.model = model
