@@ -82,12 +82,14 @@ class WarpDesc(C.Structure):
 class DcnDesc(C.Structure):
     _fields_ = [("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
                 ("c", C.c_int32), ("cout", C.c_int32), ("dg", C.c_int32),
-                ("shared_taps", C.c_int32), ("_pad", C.c_int32),
+                ("shared_taps", C.c_int32), ("head_raw", C.c_int32),
                 ("x", C.c_void_p), ("x_cstride", C.c_int32), ("x_coffset", C.c_int32),
                 ("offset", C.c_void_p), ("off_cstride", C.c_int32), ("off_coffset", C.c_int32),
                 ("mask", C.c_void_p), ("mask_cstride", C.c_int32), ("mask_coffset", C.c_int32),
                 ("weight", C.c_void_p), ("bias", C.c_void_p),
-                ("out", C.c_void_p), ("out_cstride", C.c_int32), ("out_coffset", C.c_int32)]
+                ("out", C.c_void_p), ("out_cstride", C.c_int32), ("out_coffset", C.c_int32),
+                ("head_flow", C.c_void_p), ("head_mag", C.c_float), ("_pad", C.c_int32),
+                ("dbg_y0", C.c_void_p), ("dbg_x0", C.c_void_p)]
 
 
 class DcnBwdDesc(C.Structure):

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #ifdef CRFP_HOST_EMU
 #include "cuda_shim.h"
+#include "dcn_pos.cuh"
 #else
 #include "common.cuh"
 #define CRFP_LAUNCH(kernel, grid, block, st, ...) kernel<<<(grid), (block), 0, (st)>>>(__VA_ARGS__)
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(128) dcn_bwd_sample_kernel(const crfp_dcn_bwd_
   const int K = gts * cpg;
   const float oy = D.offset[pix * gts * 2 + gt * 2], ox = D.offset[pix * gts * 2 + gt * 2 + 1];
   const float m = D.mask[pix * gts + gt];
-  const float py = (float)(y - 1 + i) + oy, px = (float)(x - 1 + j) + ox;
+  const float py = dcn_pos(y, i, oy), px = dcn_pos(x, j, ox);   // dcn_pos.cuh: the forward's expression
   const float fy = floorf(py), fx = floorf(px);
   const int y0 = (int)fy, x0 = (int)fx;
   const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
@@ -524,7 +525,7 @@ __global__ void __launch_bounds__(128) dcn_bwd_sample_v4_kernel(const crfp_dcn_b
   const int K = gts * 4;
   const float oy = D.offset[pix * gts * 2 + gt * 2], ox = D.offset[pix * gts * 2 + gt * 2 + 1];
   const float m = D.mask[pix * gts + gt];
-  const float py = (float)(y - 1 + i) + oy, px = (float)(x - 1 + j) + ox;
+  const float py = dcn_pos(y, i, oy), px = dcn_pos(x, j, ox);   // dcn_pos.cuh: the forward's expression
   const float fy = floorf(py), fx = floorf(px);
   const int y0 = (int)fy, x0 = (int)fx;
   const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;

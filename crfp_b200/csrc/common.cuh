@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include "../../include/crfp_b200.h"
+#include "dcn_pos.cuh"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
 #error "libcrfp_b200 is written for sm_100a (B200) only"
@@ -202,6 +203,25 @@ __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-
 // MUFU-based versions for the tensor-core epilogues (abs error ~1e-7, far inside the parity budget)
 __device__ __forceinline__ float fast_sigmoid(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
 __device__ __forceinline__ float fast_tanh(float v) { return 1.f - __fdividef(2.f, __expf(2.f * v) + 1.f); }
+
+// raw MUFU ops + the DCN head activations built on them (model/CRFP.py:337-349): shared by the conv epilogue
+// (CRFP_ACT_DCN_HEAD) and by the align kernel's sampler (crfp_dcn_desc.head_raw) so both give identical bits
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// mag * tanh(v) + fl = (mag + fl) - 2 mag / (exp(2v) + 1)
+__device__ __forceinline__ float head_offset_act(float v, float mag, float fl) {
+  return fmaf(-2.f * mag, rcp_approx(ex2_approx(v * 2.885390081777927f) + 1.f), mag + fl);
+}
+// sigmoid(v) = 1 - 1 / (exp(v) + 1)
+__device__ __forceinline__ float head_mask_act(float v) { return 1.f - rcp_approx(ex2_approx(v * 1.4426950408889634f) + 1.f); }
 
 // Packed-quad loader shared by the conv kernels: 4 consecutive packed input channels (quad `vq`) of the
 // channel-concatenated input at pixel (n, y, x); zero outside the image and in padding channels.

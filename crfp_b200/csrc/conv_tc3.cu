@@ -147,17 +147,6 @@ __device__ __noinline__ void tc3_issue_row_generic(uint64_t dAh, uint64_t dAl, u
   }
 }
 
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
 // Epilogue of one 32-channel chunk of one pixel: bias, 2-channel extra source, activation / DCN head, residual,
 // post-scale, store (fp32 NHWC segments or pixel shuffle).  Shared by both kernel variants.
 __device__ __forceinline__ void tc3_epilogue_chunk(const Tc3Params& P, float* v, const float* sBiasC, const float* sWxC,

@@ -23,19 +23,10 @@ struct Corner {
   float w00, w01, w10, w11;  // 0 where the corner is out of range or the sample is out of range
 };
 
+// position -> corner set: dcn_pos.cuh holds the one shared definition
 __device__ __forceinline__ Corner dcn_corner(float py, float px, int H, int W) {
   Corner c;
-  const float fy = floorf(py), fx = floorf(px);
-  c.y0 = (int)fy;
-  c.x0 = (int)fx;
-  const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
-  const bool inside = (py > -1.f) && (py < (float)H) && (px > -1.f) && (px < (float)W);
-  const bool vy0 = inside && c.y0 >= 0, vy1 = inside && (c.y0 + 1 <= H - 1);
-  const bool vx0 = c.x0 >= 0, vx1 = (c.x0 + 1 <= W - 1);
-  c.w00 = (vy0 && vx0) ? hy * hx : 0.f;
-  c.w01 = (vy0 && vx1) ? hy * lx : 0.f;
-  c.w10 = (vy1 && vx0) ? ly * hx : 0.f;
-  c.w11 = (vy1 && vx1) ? ly * lx : 0.f;
+  dcn_corner_w(py, px, H, W, c.y0, c.x0, c.w00, c.w01, c.w10, c.w11);
   return c;
 }
 
@@ -86,7 +77,8 @@ __global__ void __launch_bounds__(256, 2) dcn_l1_kernel(const crfp_dcn_desc D) {
       const float m = __ldg(D.mask + pix * D.mask_cstride + D.mask_coffset + gt);
       const int g = gt / 9, t = gt - g * 9;
       const int i = t / 3, j = t - i * 3;
-      const Corner c = dcn_corner((float)(y - 1 + i) + off.x, (float)(x - 1 + j) + off.y, D.h, D.w);
+      const Corner c = dcn_corner(dcn_pos(y, i, off.x), dcn_pos(x, j, off.y), D.h, D.w);
+      if (D.dbg_y0 != nullptr) { D.dbg_y0[pix * 72 + gt] = c.y0; D.dbg_x0[pix * 72 + gt] = c.x0; }
       v = dcn_sample4(img + g * 4, D.x_cstride, D.w, c);
       v.x *= m; v.y *= m; v.z *= m; v.w *= m;
     }
@@ -175,7 +167,8 @@ __global__ void __launch_bounds__(256) dcn_hr_kernel(const crfp_dcn_desc D) {
     const int i = t / 3, j = t - i * 3;
     float dy = dys, dx = dxs, m = ms;
     if (!D.shared_taps) { dy = __ldg(offp + 2 * t); dx = __ldg(offp + 2 * t + 1); m = __ldg(mp + t); }
-    const Corner c = dcn_corner((float)(y - 1 + i) + dy, (float)(x - 1 + j) + dx, D.h, D.w);
+    const Corner c = dcn_corner(dcn_pos(y, i, dy), dcn_pos(x, j, dx), D.h, D.w);
+    if (D.dbg_y0 != nullptr) { D.dbg_y0[pix * 9 + t] = c.y0; D.dbg_x0[pix * 9 + t] = c.x0; }
     float4 v = dcn_sample4(img, D.x_cstride, D.w, c);
     v.x *= m; v.y *= m; v.z *= m; v.w *= m;
     const float4 w0 = s_w[t * 4 + 0], w1 = s_w[t * 4 + 1], w2 = s_w[t * 4 + 2], w3 = s_w[t * 4 + 3];
@@ -202,12 +195,14 @@ __global__ void __launch_bounds__(256) dcn_indices_kernel(const crfp_dcn_desc D,
   float dy, dx;
   if (D.shared_taps) { const int g = gt / 9; dy = offp[g]; dx = offp[D.dg + g]; }
   else { dy = offp[gt * 2]; dx = offp[gt * 2 + 1]; }
-  y0o[idx] = (int)floorf((float)(y - 1 + i) + dy);
-  x0o[idx] = (int)floorf((float)(x - 1 + j) + dx);
+  y0o[idx] = (int)floorf(dcn_pos(y, i, dy));
+  x0o[idx] = (int)floorf(dcn_pos(x, j, dx));
 }
 
 int launch_dcn(const crfp_dcn_desc& d, cudaStream_t st) {
   if ((long long)d.n * d.h * d.w == 0) return CRFP_OK;
+  if (d.head_raw) return CRFP_ERR_UNSUPPORTED;                    // raw heads: tensor-core align kernel only
+  if ((d.dbg_y0 != nullptr) != (d.dbg_x0 != nullptr)) return CRFP_ERR_NULL;
   if (d.c == 32 && d.dg == 8 && d.cout == 32 && !d.shared_taps) {
     if (((d.x_cstride | d.x_coffset | d.out_cstride | d.out_coffset) & 3) || ((d.off_cstride | d.off_coffset) & 1))
       return CRFP_ERR_BAD_SHAPE;

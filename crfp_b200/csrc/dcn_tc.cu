@@ -32,20 +32,6 @@ struct DcnTcParams {
   __nv_bfloat16* out; int out_cstride, out_coffset;
 };
 
-__device__ __forceinline__ void dcn_corner_w(float py, float px, int H, int W, int& y0, int& x0, float& w00, float& w01,
-                                             float& w10, float& w11) {
-  const float fy = floorf(py), fx = floorf(px);
-  y0 = (int)fy; x0 = (int)fx;
-  const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
-  const bool inside = (py > -1.f) && (py < (float)H) && (px > -1.f) && (px < (float)W);
-  const bool vy0 = inside && y0 >= 0, vy1 = inside && (y0 + 1 <= H - 1);
-  const bool vx0 = x0 >= 0, vx1 = (x0 + 1 <= W - 1);
-  w00 = (vy0 && vx0) ? hy * hx : 0.f;
-  w01 = (vy0 && vx1) ? hy * lx : 0.f;
-  w10 = (vy1 && vx0) ? ly * hx : 0.f;
-  w11 = (vy1 && vx1) ? ly * lx : 0.f;
-}
-
 __device__ __forceinline__ void acc4_bf16(float* a, const __nv_bfloat16* p, float wgt) {
   const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
   const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
@@ -59,7 +45,7 @@ __device__ __forceinline__ void dcn_sample_bf16(const DcnTcParams& P, const __nv
   const int i = t / 3, j = t - i * 3;
   int y0, x0;
   float w00, w01, w10, w11;
-  dcn_corner_w((float)(y - 1 + i) + dy, (float)(x - 1 + j) + dx, P.h, P.w, y0, x0, w00, w01, w10, w11);
+  dcn_corner_w(dcn_pos(y, i, dy), dcn_pos(x, j, dx), P.h, P.w, y0, x0, w00, w01, w10, w11);
   v[0] = v[1] = v[2] = v[3] = 0.f;
   const __nv_bfloat16* p = img + ((long long)y0 * P.w + x0) * P.x_cstride + g * 4;
   if (w00 != 0.f) acc4_bf16(v, p, w00);
@@ -173,6 +159,11 @@ struct DcnTc3Params {
   const float* bias;
   float* out; int out_cstride, out_coffset;
   const float* flow_hint;     // optional NHWC 2-channel flow: centres the shared-memory sampling window
+  int head_raw;               // offset / mask are raw head-conv outputs: the sampler applies tanh / sigmoid / + flow
+  const float* head_flow;     // NHWC 2-channel flow added to the offsets (head_raw)
+  float head_mag;
+  int32_t* dbg_y0;            // optional parity dump: floor(py), floor(px) of every sample, int32 [n,h,w,72]
+  int32_t* dbg_x0;
 };
 
 __device__ __forceinline__ void dcn_sample_f32(const DcnTc3Params& P, const float* img, int gt, int y, int x, float dy,
@@ -181,7 +172,7 @@ __device__ __forceinline__ void dcn_sample_f32(const DcnTc3Params& P, const floa
   const int i = t / 3, j = t - i * 3;
   int y0, x0;
   float w00, w01, w10, w11;
-  dcn_corner_w((float)(y - 1 + i) + dy, (float)(x - 1 + j) + dx, P.h, P.w, y0, x0, w00, w01, w10, w11);
+  dcn_corner_w(dcn_pos(y, i, dy), dcn_pos(x, j, dx), P.h, P.w, y0, x0, w00, w01, w10, w11);
   v[0] = v[1] = v[2] = v[3] = 0.f;
   const float* p = img + ((long long)y0 * P.w + x0) * P.x_cstride + g * 4;
 #define CRFP_C4(ptr, wgt)                                                  \
@@ -228,7 +219,7 @@ __device__ __forceinline__ void dcn_sample_win(const DcnTc3Params& P, const floa
   const int i = t / 3, j = t - i * 3;
   int y0, x0;
   float w00, w01, w10, w11;
-  dcn_corner_w((float)(y - 1 + i) + dy, (float)(x - 1 + j) + dx, P.h, P.w, y0, x0, w00, w01, w10, w11);
+  dcn_corner_w(dcn_pos(y, i, dy), dcn_pos(x, j, dx), P.h, P.w, y0, x0, w00, w01, w10, w11);
   const int wy = y0 - wy0, wx = x0 - wx0;
   if (wy >= 0 && wy + 1 < DWH && wx >= 0 && wx + 1 < DWW) {
     const float4* p = sWin + (wy * DWW + wx) * 4 + (g - 4 * half);
@@ -266,12 +257,14 @@ constexpr int WA_RECS = WQC * DAP;            // uint4 records of one A stage (h
 // window variant for the persistent kernel: the window holds 8 channels (the 2 deformable groups of K quarter `q`) per
 // pixel, [32][40][8] floats as written by the TMA tile load; `gtr` = (group, tap) index relative to the quarter (0..17)
 __device__ __forceinline__ void dcn_sample_win8(const DcnTc3Params& P, const float* img, const float4* sWin, int wy0, int wx0,
-                                                int q, int gtr, int y, int x, float dy, float dx, float m, float* v) {
+                                                int q, int gtr, int y, int x, float dy, float dx, float m, float* v,
+                                                long long dbg_idx) {
   const int gl = gtr / 9, t = gtr - gl * 9;
   const int i = t / 3, j = t - i * 3;
   int y0, x0;
   float w00, w01, w10, w11;
-  dcn_corner_w((float)(y - 1 + i) + dy, (float)(x - 1 + j) + dx, P.h, P.w, y0, x0, w00, w01, w10, w11);
+  dcn_corner_w(dcn_pos(y, i, dy), dcn_pos(x, j, dx), P.h, P.w, y0, x0, w00, w01, w10, w11);
+  if (P.dbg_y0 != nullptr) { P.dbg_y0[dbg_idx] = y0; P.dbg_x0[dbg_idx] = x0; }   // parity dump (uniform branch)
   const int wy = y0 - wy0, wx = x0 - wx0;
   if (wy >= 0 && wy + 1 < WWH && wx >= 0 && wx + 1 < WWW) {
     const float4* p = sWin + (wy * WWW + wx) * 2 + gl;
@@ -586,7 +579,8 @@ __global__ void __launch_bounds__(512, 1) dcn_tc3_ws_kernel(const DcnTc3Params P
     }
     float4 offs[3], noffs[3];
     float2 mks[3], nmks[3];
-    auto load_offsets = [&](int kk, float4* o, float2* mk) {
+    float2 fls[3], nfls[3];     // head_raw: flow at the record's pixel
+    auto load_offsets = [&](int kk, float4* o, float2* mk, float2* fl) {
       const int tile = (int)blockIdx.x + (kk >> 2) * (int)gridDim.x, q = kk & 3;
       const int n = tile / tiles_img, tr = tile - n * tiles_img;
       const int ty = tr / tiles_x, tx = tr - ty * tiles_x;
@@ -595,17 +589,19 @@ __global__ void __launch_bounds__(512, 1) dcn_tc3_ws_kernel(const DcnTc3Params P
         const int y = ty * DTH + (rm[r] >> 4), x = tx * DTW + (rm[r] & 15);
         o[r] = make_float4(0.f, 0.f, 0.f, 0.f);
         mk[r] = make_float2(0.f, 0.f);
+        fl[r] = make_float2(0.f, 0.f);
         if (y < P.h && x < P.w) {
           const size_t pix = ((size_t)n * P.h + y) * (size_t)P.w + x;
           const int kc = q * 9 + rkl[r];
           o[r] = __ldg(reinterpret_cast<const float4*>(P.offset + pix * P.off_cstride + P.off_coffset + kc * 4));
           mk[r] = __ldg(reinterpret_cast<const float2*>(P.mask + pix * P.mask_cstride + P.mask_coffset + kc * 2));
+          if (P.head_raw) fl[r] = __ldg(reinterpret_cast<const float2*>(P.head_flow + pix * 2));
         }
       }
     };
-    if (nq > 0) load_offsets(0, offs, mks);
+    if (nq > 0) load_offsets(0, offs, mks, fls);
     for (int k = 0; k < nq; ++k) {
-      if (k + 1 < nq) load_offsets(k + 1, noffs, nmks);   // in flight while this quarter is sampled
+      if (k + 1 < nq) load_offsets(k + 1, noffs, nmks, nfls);   // in flight while this quarter is sampled
       const int tile = (int)blockIdx.x + (k >> 2) * (int)gridDim.x, q = k & 3, stg = k & 1, slot = k % WNW;
       const int n = tile / tiles_img, tr = tile - n * tiles_img;
       const int ty = tr / tiles_x, tx = tr - ty * tiles_x;
@@ -623,8 +619,16 @@ __global__ void __launch_bounds__(512, 1) dcn_tc3_ws_kernel(const DcnTc3Params P
         uint4 rh = make_uint4(0u, 0u, 0u, 0u), rl = rh;
         if (y < P.h && x < P.w) {
           float v0[4], v1[4];
-          dcn_sample_win8(P, img, win, org.x, org.y, q, 2 * kl, y, x, offs[r].x, offs[r].y, mks[r].x, v0);
-          dcn_sample_win8(P, img, win, org.x, org.y, q, 2 * kl + 1, y, x, offs[r].z, offs[r].w, mks[r].y, v1);
+          float4 of = offs[r];
+          float2 mk = mks[r];
+          if (P.head_raw) {   // DCN_module.forward's head activations (CRFP.py:337-349), fused into the sampler
+            of.x = head_offset_act(of.x, P.head_mag, fls[r].y); of.y = head_offset_act(of.y, P.head_mag, fls[r].x);
+            of.z = head_offset_act(of.z, P.head_mag, fls[r].y); of.w = head_offset_act(of.w, P.head_mag, fls[r].x);
+            mk.x = head_mask_act(mk.x); mk.y = head_mask_act(mk.y);
+          }
+          const long long dbg = ((((long long)n * P.h + y) * P.w + x) * 72) + q * 18 + 2 * kl;
+          dcn_sample_win8(P, img, win, org.x, org.y, q, 2 * kl, y, x, of.x, of.y, mk.x, v0, dbg);
+          dcn_sample_win8(P, img, win, org.x, org.y, q, 2 * kl + 1, y, x, of.z, of.w, mk.y, v1, dbg + 1);
           split_pair(v0[0], v0[1], rh.x, rl.x);
           split_pair(v0[2], v0[3], rh.y, rl.y);
           split_pair(v1[0], v1[1], rh.z, rl.z);
@@ -636,7 +640,7 @@ __global__ void __launch_bounds__(512, 1) dcn_tc3_ws_kernel(const DcnTc3Params P
       umma::fence_proxy_async();
       umma::mbar_arrive(&a_full[stg]);
 #pragma unroll
-      for (int r = 0; r < 3; ++r) { offs[r] = noffs[r]; mks[r] = nmks[r]; }
+      for (int r = 0; r < 3; ++r) { offs[r] = noffs[r]; mks[r] = nmks[r]; fls[r] = nfls[r]; }
     }
   }
   umma::fence_before_sync();
@@ -705,8 +709,13 @@ int launch_dcn_tc3(const crfp_dcn_desc& d, const void* w_lo, const float* flow_h
   p.bias = d.bias;
   p.out = d.out; p.out_cstride = d.out_cstride; p.out_coffset = d.out_coffset;
   p.flow_hint = flow_hint;
+  p.head_raw = d.head_raw; p.head_flow = d.head_flow; p.head_mag = d.head_mag;
+  p.dbg_y0 = d.dbg_y0; p.dbg_x0 = d.dbg_x0;
+  if (d.head_raw && !d.head_flow) return CRFP_ERR_NULL;
+  if ((d.dbg_y0 != nullptr) != (d.dbg_x0 != nullptr)) return CRFP_ERR_NULL;
   static const bool use_v1 = (getenv("CRFP_DCN_V1") != nullptr);   // A/B switch: the non-persistent kernel
   if (!use_v1) return launch_dcn_tc3_ws(p, st);
+  if (d.head_raw || d.dbg_y0) return CRFP_ERR_UNSUPPORTED;        // raw heads / index dump: persistent kernel only
   const size_t smem = (size_t)(2 * DKC * 32 + 2 * D3KH * DAP + DWH * DWW * 4) * 16;  // 36864 + 74304 + 64512 B
   cudaError_t e = cudaFuncSetAttribute(dcn_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
@@ -718,6 +727,7 @@ int launch_dcn_tc3(const crfp_dcn_desc& d, const void* w_lo, const float* flow_h
 int launch_dcn_tc(const crfp_dcn_desc& d, cudaStream_t st) {
   if ((long long)d.n * d.h * d.w == 0) return CRFP_OK;
   if (!(d.c == 32 && d.dg == 8 && d.cout == 32 && !d.shared_taps)) return CRFP_ERR_UNSUPPORTED;
+  if (d.head_raw || d.dbg_y0 || d.dbg_x0) return CRFP_ERR_UNSUPPORTED;
   if ((d.x_cstride | d.x_coffset | d.out_cstride | d.out_coffset) & 7) return CRFP_ERR_BAD_SHAPE;
   if (((d.off_cstride | d.off_coffset) & 3) || ((d.mask_cstride | d.mask_coffset) & 1)) return CRFP_ERR_BAD_SHAPE;
   DcnTcParams p;

@@ -2,6 +2,7 @@
 // Reference: /root/reference/model/CRFP.py:1483-1508 (compute_flow), 797-814 (FNet), 1510-1686 (forward).
 // Everything here is host-side sequencing of the library's own kernels on the caller's stream, inside the
 // caller's workspace; no allocation, no synchronisation.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -456,6 +457,35 @@ static size_t carve_frame(const crfp_dsv_shape* s, void* ws, FrameWs* f) {
 }
 
 
+// Offset / mask heads + DCNv2 of one L1 level (DCN_module.forward, model/CRFP.py:337-350): ONE 216-channel conv
+// into `om`, then the align kernel.  Tensor-core precision: the conv stores the RAW head outputs and the align kernel's
+// sampler applies 10*tanh + flow / sigmoid itself (crfp_dcn_desc.head_raw) — the conv epilogue drops to bias + store
+// (it was MUFU / issue bound with the activations in it); CRFP_HEAD_EPI=1 restores the epilogue form for A/B.
+static int run_heads_dcn(const crfp_dsv_weights* W, int n, int h1, int w1, const float* z, const float* flow_l1, float* om,
+                         const float* P, float* A, int l_heads, int l_dcn, cudaStream_t st) {
+  static const bool head_epi = (getenv("CRFP_HEAD_EPI") != nullptr);
+  const bool tc = W->precision == CRFP_PREC_TC3 && W->layer_tc[l_dcn].w_hi && W->layer_tc[l_dcn].w_lo;
+  const bool raw = tc && !head_epi;
+  if (raw)
+    CRFP_TRY(CB(n, h1, w1).src(z, 32, 32).layer(W, l_heads).dst(om, 216, 216).run(st));
+  else
+    CRFP_TRY(CB(n, h1, w1).src(z, 32, 32).layer(W, l_heads).head(flow_l1, 144, 10.f).dst(om, 216, 216).run(st));
+  crfp_dcn_desc dd;
+  memset(&dd, 0, sizeof(dd));
+  dd.n = n; dd.h = h1; dd.w = w1; dd.c = 32; dd.cout = 32; dd.dg = 8;
+  dd.x = P; dd.x_cstride = 32;
+  dd.offset = om; dd.off_cstride = 216; dd.off_coffset = 0;
+  dd.mask = om; dd.mask_cstride = 216; dd.mask_coffset = 144;
+  dd.weight = W->layer[l_dcn].w; dd.bias = W->layer[l_dcn].b;
+  dd.out = A; dd.out_cstride = 32;
+  if (tc) {
+    dd.weight = reinterpret_cast<const float*>(W->layer_tc[l_dcn].w_hi); dd.bias = W->layer_tc[l_dcn].b;
+    if (raw) { dd.head_raw = 1; dd.head_flow = flow_l1; dd.head_mag = 10.f; }
+    return launch_dcn_tc3(dd, W->layer_tc[l_dcn].w_lo, flow_l1, st);
+  }
+  return launch_dcn(dd, st);
+}
+
 // L1 stage of CRFP (v15, model/CRFP.py:1260-1340) and CRFP_simple (v13, model/CRFP.py:968-1050): no DSV split; the HR
 // state is warped first and both the state and its warp go through `downsample`; v15 feeds the warped planes into
 // every residual block as a third concat source.  Same kernels, same hand-off (q, po, S0_w, flow_hr) to the HR stage.
@@ -504,21 +534,7 @@ static int frame_l1_v1x(const crfp_dsv_frame_desc* d, const crfp_dsv_weights* W,
                      .dst(z, 32, 32).run(st));
       }
       offfeat = z;
-      CRFP_TRY(CB(n, h1, w1).src(z, 32, 32).layer(W, lhd[k]).head(f.flow_l1, 144, 10.f).dst(f.om, 216, 216).run(st));
-      crfp_dcn_desc dd;
-      memset(&dd, 0, sizeof(dd));
-      dd.n = n; dd.h = h1; dd.w = w1; dd.c = 32; dd.cout = 32; dd.dg = 8;
-      dd.x = f.P; dd.x_cstride = 32;
-      dd.offset = f.om; dd.off_cstride = 216; dd.off_coffset = 0;
-      dd.mask = f.om; dd.mask_cstride = 216; dd.mask_coffset = 144;
-      dd.weight = W->layer[ldc[k]].w; dd.bias = W->layer[ldc[k]].b;
-      dd.out = f.A; dd.out_cstride = 32;
-      if (W->precision == CRFP_PREC_TC3 && W->layer_tc[ldc[k]].w_hi && W->layer_tc[ldc[k]].w_lo) {
-        dd.weight = reinterpret_cast<const float*>(W->layer_tc[ldc[k]].w_hi); dd.bias = W->layer_tc[ldc[k]].b;
-        CRFP_TRY(launch_dcn_tc3(dd, W->layer_tc[ldc[k]].w_lo, f.flow_l1, st));
-      } else {
-        CRFP_TRY(launch_dcn(dd, st));
-      }
+      CRFP_TRY(run_heads_dcn(W, n, h1, w1, z, f.flow_l1, f.om, f.P, f.A, lhd[k], ldc[k], st));
       CB in(n, h1, w1);
       in.src(cur, 32, 32).src(f.A, 32, 32);
       if (three) in.src(f.P_w, 32, 32);
@@ -817,21 +833,7 @@ extern "C" int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weigh
                        .dst(z, 32, 32).run(st));
         }
         offfeat = z;
-        CRFP_TRY(CB(n, h1, w1).src(z, 32, 32).layer(W, lhd[k]).head(f.flow_l1, 144, 10.f).dst(f.om, 216, 216).run(st));
-        crfp_dcn_desc dd;
-        memset(&dd, 0, sizeof(dd));
-        dd.n = n; dd.h = h1; dd.w = w1; dd.c = 32; dd.cout = 32; dd.dg = 8;
-        dd.x = f.P; dd.x_cstride = 32;
-        dd.offset = f.om; dd.off_cstride = 216; dd.off_coffset = 0;
-        dd.mask = f.om; dd.mask_cstride = 216; dd.mask_coffset = 144;
-        dd.weight = W->layer[ldc[k]].w; dd.bias = W->layer[ldc[k]].b;
-        dd.out = f.A; dd.out_cstride = 32;
-        if (W->precision == CRFP_PREC_TC3 && W->layer_tc[ldc[k]].w_hi && W->layer_tc[ldc[k]].w_lo) {
-          dd.weight = reinterpret_cast<const float*>(W->layer_tc[ldc[k]].w_hi); dd.bias = W->layer_tc[ldc[k]].b;
-          CRFP_TRY(launch_dcn_tc3(dd, W->layer_tc[ldc[k]].w_lo, f.flow_l1, st));
-        } else {
-          CRFP_TRY(launch_dcn(dd, st));
-        }
+        CRFP_TRY(run_heads_dcn(W, n, h1, w1, z, f.flow_l1, f.om, f.P, f.A, lhd[k], ldc[k], st));
         // ResidualBlocksWithInputConv on cat(cur, A) (CRFP.py:1589-1596)
         CB in(n, h1, w1);
         in.src(cur, 32, 32).src(f.A, 32, 32).layer(W, lri[k]).act(CRFP_ACT_LRELU).dst(f.r0, 32, 32);

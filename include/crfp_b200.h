@@ -267,18 +267,28 @@ size_t crfp_sizeof_warp_desc(void);
  * and mask dg channels.
  * weight packed as [k][co] with k = (g*9+t)*(C/dg) + c_in_group, co padded to a multiple of 4; bias[co].
  * Supported: (C=32, dg=8, cout=32) and (C=4, dg=1, cout=4).
+ *
+ * head_raw != 0 (the fused form of DCN_module.forward, model/CRFP.py:337-349; tensor-core align kernel only): `offset`
+ * and `mask` hold the RAW outputs of the dcn_offset / dcn_mask convolutions and the sampler applies
+ *   dy = head_mag * tanh(raw) + head_flow[n,y,x,1],  dx = head_mag * tanh(raw) + head_flow[n,y,x,0],  m = sigmoid(raw)
+ * itself (same ex2 / rcp arithmetic as the conv epilogue's CRFP_ACT_DCN_HEAD), so the activation never costs a pass.
+ * dbg_y0 / dbg_x0 (optional, parity): the kernel that PRODUCES the output also writes floor(py), floor(px) of every
+ * sample it takes: int32 [n,h,w,dg*9] each (shared_taps: the 9 taps of the one group).
  */
 typedef struct {
   int32_t n, h, w;
   int32_t c, cout, dg;
   int32_t shared_taps;
-  int32_t _pad;
+  int32_t head_raw;
   const float* x; int32_t x_cstride, x_coffset;
   const float* offset; int32_t off_cstride, off_coffset;
   const float* mask; int32_t mask_cstride, mask_coffset;
   const float* weight;
   const float* bias;
   float* out; int32_t out_cstride, out_coffset;
+  const float* head_flow;       /* NHWC 2-channel flow (x, y) at this resolution; required when head_raw != 0 */
+  float head_mag; int32_t _pad;
+  int32_t* dbg_y0; int32_t* dbg_x0;
 } crfp_dcn_desc;
 int crfp_dcn_v2_fwd(const crfp_dcn_desc* d, crfp_stream stream);
 /* tensor-core variant (C=32, dg=8, cout=32): x / out bf16 NHWC, weight bf16 [36][32][8] with k = (g*9+t)*4+c,

@@ -240,3 +240,144 @@ def test_conv_tc3_unshuffle_source():
     d.dst[0] = L.TcSrc(ptr=out.data_ptr(), c=32, cstride=32, coffset=0)
     L.check(L.lib().crfp_conv3x3_tc3_fwd(C.byref(d), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "tc3 unshuffle")
     assert (nchw(out) - ref).abs().max().item() < 2e-4
+
+
+def _dcn_desc(L, n, h, w, xd, om, wptr, bptr, out):
+    return L.DcnDesc(n=n, h=h, w=w, c=32, cout=32, dg=8, shared_taps=0, x=xd.data_ptr(), x_cstride=32, x_coffset=0,
+                     offset=om.data_ptr(), off_cstride=216, off_coffset=0, mask=om.data_ptr(), mask_cstride=216,
+                     mask_coffset=144, weight=wptr, bias=bptr, out=out.data_ptr(), out_cstride=32, out_coffset=0)
+
+
+def test_production_align_kernel_dumps_its_own_indices():
+    """Exact integer sampling indices FROM THE KERNEL THAT PRODUCES THE OUTPUT (dcn_tc3_ws_kernel, the persistent
+    TMA + tcgen05 align kernel): floor(py), floor(px) of every (pixel, group, tap) it samples equal floor() of the
+    reference positions computed in torch fp32 (y-1+i + dy as one fp32 add), incl. out-of-range and on-integer offsets."""
+    import ctypes as C
+    from crfp_b200 import _lib as L
+    from crfp_b200.packing import pack_dcn_tc3
+    g = _g(21)
+    n, h, w = 2, 37, 53
+    x = torch.randn(n, 32, h, w, generator=g)
+    off = torch.randn(n, 144, h, w, generator=g) * 4
+    off[0, :, :2] = 40.0       # far outside
+    off[0, :, 2:4] = 0.0       # exactly on integer positions
+    off[1, :, :, :3] = -1.0    # exactly on the -1 border
+    off[1, :, 5:7] = torch.round(off[1, :, 5:7]) + 0.9999999
+    msk = torch.rand(n, 72, h, w, generator=g)
+    wt = torch.randn(32, 32, 3, 3, generator=g) * 0.05
+    b = torch.randn(32, generator=g) * 0.05
+    xd = x.permute(0, 2, 3, 1).contiguous().cuda()
+    om = torch.cat([off, msk], 1).permute(0, 2, 3, 1).contiguous().cuda()
+    hi, lo, bp = pack_dcn_tc3(wt.cuda(), b.cuda(), 8)
+    out = torch.zeros(n, h, w, 32, device="cuda")
+    y0 = torch.full((n, h, w, 72), -12345, device="cuda", dtype=torch.int32)
+    x0 = torch.full_like(y0, -12345)
+    d = _dcn_desc(L, n, h, w, xd, om, hi.data_ptr(), bp.data_ptr(), out)
+    d.dbg_y0, d.dbg_x0 = y0.data_ptr(), x0.data_ptr()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    hint = (torch.randn(n, h, w, 2, generator=g) * 3).cuda()
+    L.check(L.lib().crfp_dcn_v2_tc3_fwd(C.byref(d), lo.data_ptr(), hint.data_ptr(), st), "dcn tc3 + index dump")
+    ys = torch.arange(h).view(1, h, 1, 1).float()
+    xs = torch.arange(w).view(1, 1, w, 1).float()
+    t = torch.arange(72) % 9
+    offp = off.permute(0, 2, 3, 1)
+    ry0 = torch.floor((ys - 1 + (t // 3).float()) + offp[..., 0::2]).int()
+    rx0 = torch.floor((xs - 1 + (t % 3).float()) + offp[..., 1::2]).int()
+    assert torch.equal(y0.cpu(), ry0) and torch.equal(x0.cpu(), rx0)
+    # and the side kernel (crfp_dcn_v2_indices) agrees with the production kernel
+    y1, x1 = torch.empty_like(y0), torch.empty_like(x0)
+    L.check(L.lib().crfp_dcn_v2_indices(C.byref(d), y1.data_ptr(), x1.data_ptr(), st), "indices")
+    assert torch.equal(y0, y1) and torch.equal(x0, x1)
+    from oracle import crfp_oracle as O
+    assert (nchw(out) - O.dcn_v2(x, off, msk, wt, b, 8)).abs().max().item() < 1e-4
+
+
+def test_hr_align_kernel_dumps_its_own_indices():
+    """dcn_hr_kernel (C=4, dg=1, one (dy,dx) per pixel shared by the 9 taps): indices dumped by the kernel itself."""
+    import ctypes as C
+    from crfp_b200 import _lib as L
+    from crfp_b200.packing import pack_dcn
+    g = _g(22)
+    n, h, w = 1, 40, 56
+    x = torch.randn(n, 4, h, w, generator=g)
+    om = torch.randn(n, 2, h, w, generator=g) * 5
+    om[0, :, :2] = 0.0
+    m1 = torch.rand(n, 1, h, w, generator=g)
+    wt = torch.randn(4, 4, 3, 3, generator=g) * 0.2
+    b = torch.randn(4, generator=g) * 0.1
+    wp, bp = pack_dcn(wt.cuda(), b.cuda(), 1)
+    xd = x.permute(0, 2, 3, 1).contiguous().cuda()
+    omd = torch.cat([om, m1], 1).permute(0, 2, 3, 1).contiguous().cuda()      # (dy, dx, m) per pixel
+    out = torch.zeros(n, h, w, 4, device="cuda")
+    y0 = torch.full((n, h, w, 9), -12345, device="cuda", dtype=torch.int32)
+    x0 = torch.full_like(y0, -12345)
+    d = L.DcnDesc(n=n, h=h, w=w, c=4, cout=4, dg=1, shared_taps=1, x=xd.data_ptr(), x_cstride=4, x_coffset=0,
+                  offset=omd.data_ptr(), off_cstride=3, off_coffset=0, mask=omd.data_ptr(), mask_cstride=3, mask_coffset=2,
+                  weight=wp.data_ptr(), bias=bp.data_ptr(), out=out.data_ptr(), out_cstride=4, out_coffset=0)
+    d.dbg_y0, d.dbg_x0 = y0.data_ptr(), x0.data_ptr()
+    L.check(L.lib().crfp_dcn_v2_fwd(C.byref(d), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "dcn hr + dump")
+    ys = torch.arange(h).view(1, h, 1, 1).float()
+    xs = torch.arange(w).view(1, 1, w, 1).float()
+    t = torch.arange(9)
+    omp = om.permute(0, 2, 3, 1)
+    ry0 = torch.floor((ys - 1 + (t // 3).float()) + omp[..., 0:1]).int()
+    rx0 = torch.floor((xs - 1 + (t % 3).float()) + omp[..., 1:2]).int()
+    assert torch.equal(y0.cpu(), ry0) and torch.equal(x0.cpu(), rx0)
+    from oracle import crfp_oracle as O
+    ref = O.dcn_v2(x, om.repeat(1, 9, 1, 1), m1.repeat(1, 9, 1, 1), wt, b, 1)
+    assert (nchw(out) - ref).abs().max().item() < 1e-4
+
+
+def test_align_kernel_raw_heads_equals_epilogue_heads():
+    """crfp_dcn_desc.head_raw: the sampler applies 10*tanh + flow / sigmoid to the RAW head-conv outputs
+    (DCN_module.forward, CRFP.py:337-349) with the conv epilogue's own arithmetic -> bit-identical to the two-pass
+    form, sampled indices included; and within 1e-4 of the oracle's DCN_module tail."""
+    import ctypes as C
+    from crfp_b200 import _lib as L
+    from crfp_b200 import ops
+    from crfp_b200.packing import pack_dcn_tc3
+    from oracle import crfp_oracle as O
+    g = _g(23)
+    n, h, w = 1, 26, 150
+    z = torch.randn(n, 32, h, w, generator=g)
+    x = torch.randn(n, 32, h, w, generator=g)
+    flow = torch.randn(n, 2, h, w, generator=g) * 3
+    w_off = torch.randn(144, 32, 3, 3, generator=g) * 0.05
+    w_msk = torch.randn(72, 32, 3, 3, generator=g) * 0.05
+    b_off = torch.randn(144, generator=g) * 0.05
+    b_msk = torch.randn(72, generator=g) * 0.05
+    wt = torch.randn(32, 32, 3, 3, generator=g) * 0.05
+    b = torch.randn(32, generator=g) * 0.05
+    zd, xd = z.permute(0, 2, 3, 1).contiguous().cuda(), x.permute(0, 2, 3, 1).contiguous().cuda()
+    fd = flow.permute(0, 2, 3, 1).contiguous().cuda()
+    wh = torch.cat([w_off, w_msk], 0).cuda()
+    bh = torch.cat([b_off, b_msk], 0).cuda()
+    om_act = ops.conv3x3_tc3_nhwc([zd], wh, bh, act=L.ACT_DCN_HEAD, flow=fd, head_split=144, head_mag=10.0)
+    om_raw = ops.conv3x3_tc3_nhwc([zd], wh, bh, act=L.ACT_NONE)
+    hi, lo, bp = pack_dcn_tc3(wt.cuda(), b.cuda(), 8)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    outs, idx = [], []
+    for om, raw in ((om_act, 0), (om_raw, 1)):
+        out = torch.zeros(n, h, w, 32, device="cuda")
+        y0 = torch.zeros(n, h, w, 72, device="cuda", dtype=torch.int32)
+        x0 = torch.zeros_like(y0)
+        d = _dcn_desc(L, n, h, w, xd, om, hi.data_ptr(), bp.data_ptr(), out)
+        d.dbg_y0, d.dbg_x0 = y0.data_ptr(), x0.data_ptr()
+        if raw:
+            d.head_raw, d.head_flow, d.head_mag = 1, fd.data_ptr(), 10.0
+        L.check(L.lib().crfp_dcn_v2_tc3_fwd(C.byref(d), lo.data_ptr(), fd.data_ptr(), st), "dcn tc3")
+        outs.append(out); idx.append((y0, x0))
+    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(idx[0][0], idx[1][0]) and torch.equal(idx[0][1], idx[1][1])
+    # oracle tail of DCN_module: offset = 10 tanh(conv) + flow.flip(1).repeat, mask = sigmoid(conv), DCNv2
+    off = 10.0 * torch.tanh(F.conv2d(z, w_off, b_off, padding=1)) + flow.flip(1).repeat(1, 72, 1, 1)
+    msk = torch.sigmoid(F.conv2d(z, w_msk, b_msk, padding=1))
+    ref = O.dcn_v2(x, off, msk, wt, b, 8)
+    err = (nchw(outs[1]) - ref).abs().max().item()
+    print(f"fused-activation align kernel vs oracle DCN_module tail: max-abs {err:.3e}")
+    assert err < 2e-4
+    # the raw mode needs the flow; the SIMT kernels do not implement it
+    d.head_flow = None
+    assert L.lib().crfp_dcn_v2_tc3_fwd(C.byref(d), lo.data_ptr(), fd.data_ptr(), st) < 0
+    d.head_flow = fd.data_ptr()
+    assert L.lib().crfp_dcn_v2_fwd(C.byref(d), st) < 0

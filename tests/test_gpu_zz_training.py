@@ -271,8 +271,6 @@ def test_trainer_steps_reduce_the_loss_and_refresh_inference_weights(A):
     assert any((new_sd[k] - sd[k]).abs().max().item() > 0 for k in sd)
 
 
-@pytest.mark.xfail(reason="added after round 1's GPU budget was spent: the graphed step itself ran on the B200 through "
-                          "scripts/bench_train.py --graphs (profiles/r01/v6_train_bench_v7.json), this comparison has not", strict=False)
 def test_graphed_trainer_tracks_the_eager_trainer(A):
     """Trainer(use_graphs=True): steps 1-2 eager, step 3 captures forward + loss + backward, later steps replay."""
     from crfp_b200 import CRFP_DSV
@@ -296,8 +294,6 @@ def test_graphed_trainer_tracks_the_eager_trainer(A):
     assert losses[True][-1] < losses[True][0]
 
 
-@pytest.mark.xfail(reason="CRFP_WGRAD_THIN=2stage was written after round 1's GPU budget was spent (CPU emulation twin passes); "
-                          "it is opt-in, the default atomic path is the verified one", strict=False)
 @pytest.mark.parametrize("c_list,cout,hw", [([4, 4], 4, (64, 96)), ([4, 4, 2], 4, (37, 45)), ([6], 4, (40, 130)), ([4], 3, (128, 128))])
 def test_conv3x3_weight_gradient_two_stage(A, c_list, cout, hw):
     K = A.KernelSet()

@@ -1,14 +1,12 @@
 """GPU test (-m gpu) of the `CRFP_runtime.MRCF_simple_v18` drop-in against the golden outputs of the real reference class
-(fp32 bar: max-abs <= 1e-3).  CPU twin: tests/test_runtime_shell.py.  Written after round 1's GPU budget was spent: the
-shell only composes operator kernels that ARE verified on the B200 (tests/test_gpu_ops.py), but this composition has not
-run on a GPU yet — hence the non-strict xfail (XPASS when green, cannot turn the verified suite red)."""
+(fp32 bar: max-abs <= 1e-3).  CPU twin: tests/test_runtime_shell.py.  First ran green on the driver's B200 at the end of
+round 1 (GPUTEST_r01.json: XPASS); the xfail marker is gone, a regression turns the suite red."""
 import os
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(reason="runtime shell never ran on a GPU in round 1 (budget spent); CPU twin passes", strict=False)]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", ["runtime_full_n1_t3_16x24", "runtime_region_n2_t3_16x24"])

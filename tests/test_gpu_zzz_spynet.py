@@ -1,18 +1,15 @@
 """GPU tests (-m gpu) of the legacy SPyNet flow pyramid on the B200 against the golden outputs of the real reference
 class (fp32 bar: max-abs <= 1e-3 on flows of ~1 px).  CPU twin: tests/test_spynet.py.
 
-Written after round 1's GPU budget was spent: these tests have NOT run on a B200 yet (the kernels are checked through
-the host emulation only), hence the non-strict xfail — they report XPASS when green and cannot turn the verified
-suite red."""
+First ran green on the driver's B200 at the end of round 1 (GPUTEST_r01.json: XPASS); the xfail marker is gone, a
+regression turns the suite red."""
 import os
 
 import pytest
 import torch
 import torch.nn.functional as F
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(reason="SPyNet kernels were never run on a GPU in round 1 (budget spent); CPU emulation twin passes",
-                                strict=False)]
+pytestmark = pytest.mark.gpu
 
 
 def test_spynet_ops_on_gpu():

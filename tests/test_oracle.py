@@ -99,3 +99,20 @@ def test_sibling_oracles_match_reference_golden(golden_dir, variant):
     lrs, fvs, mks, _ = make_clip(seed=c["seed"], n=c["n"], t=c["t"], h=c["h"], w=c["w"], fv_size=c["fv"])
     out = O.crfp_forward(sdv, lrs, fvs, mks, variant=variant)
     assert (out - fix["out"]).abs().max().item() <= 1e-5
+
+
+def test_oracle_long_golden_prefix(golden_dir, sd):
+    """Long-recurrence fixture (oracle/make_golden_long.py, 100 reference frames at LR 32x48): the recurrence is causal,
+    so the oracle on the first 8 frames must reproduce the first 8 golden frames (sub-grid, fovea crop, checksums)."""
+    fix = torch.load(os.path.join(golden_dir, "long_t100_32x48.pt"))
+    c = fix["case"]
+    lrs, fvs, mks, fv_sp = make_clip(seed=c["seed"], n=1, t=c["t"], h=c["h"], w=c["w"], fv_size=c["fv"])
+    assert torch.equal(fv_sp, fix["fv_sp"]) and abs(float(lrs.double().sum()) - fix["lrs_sum"]) < 1e-6
+    k = 8
+    out = O.crfp_dsv_forward(sd, lrs[:, :k], fvs[:, :k], mks[:, :k])
+    s, crop = fix["stride"], fix["crop"]
+    for i in range(k):
+        oy, ox, cy, cx = fix["origins"][i]
+        assert (out[0, i, :, oy::s, ox::s] - fix["grids"][i]).abs().max().item() <= 1e-5
+        assert (out[0, i, :, cy:cy + crop, cx:cx + crop] - fix["crops"][i]).abs().max().item() <= 1e-5
+        assert abs(float(out[0, i].double().sum()) - fix["sum"][i]) <= 1e-3
