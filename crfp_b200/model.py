@@ -90,6 +90,11 @@ class _CRFPBase(nn.Module):
         # the whole clip into one graph and later calls replay it (one launch per clip: immune to host jitter)
         self.use_graphs = os.environ.get("CRFP_NO_GRAPHS") is None
         self.graph_frames = 20                     # frames per captured graph
+        # A graph owns its output buffer.  Default: a replay returns a COPY of it (one device-to-device copy, < 1 % of
+        # a clip), so tensors returned by earlier calls stay valid like the reference's fresh tensors do.
+        # alias_output = True (or an explicit `out=` buffer) returns the graph-owned tensor itself, overwritten by the
+        # next replay on the same inputs — the cudagraph-style contract, for callers that consume each result at once.
+        self.alias_output = False
         self._graphs = collections.OrderedDict()   # key -> dict(graphs, out, launches)
         self._seen_key = None
 
@@ -146,6 +151,9 @@ class _CRFPBase(nn.Module):
                     W.layer_tc[i].w_extra = wx.data_ptr()
         self._packed = (key, keep, W)
         self._graphs.clear()      # captured graphs point at the previous packed weights
+        for sb in getattr(self, "_sbuf", {}).values():
+            sb["graphs"].clear()
+            sb["seen"].clear()
         return W
 
     def _clip_buffers(self, n, t, h, w, device):
@@ -153,6 +161,13 @@ class _CRFPBase(nn.Module):
         if key not in self._ws:
             self._ws.clear()
             self._graphs.clear()  # captured graphs point at the previous clip buffers
+            if hasattr(self, "_sbuf"):
+                self._sbuf.clear()
+            skey = (n, h, w, str(device))
+            if getattr(self, "_state_bufs", None) is None or self._state_bufs[0] != skey:
+                # recurrent state, O(1) in t: its own cache so that a streaming module may change t between calls
+                self._state_bufs = (skey, torch.zeros(n * 64 * h * w * 4, device=device, dtype=torch.float32),
+                                    torch.zeros(n * 4 * h * w * 24, device=device, dtype=torch.float32))
             lib = L.lib()
             shp = L.DsvShape(n=n, t=t, h=h, w=w, mid_channels=self.mid_channels)
             pw, fw = lib.crfp_dsv_prepare_workspace(C.byref(shp)), lib.crfp_dsv_frame_workspace(C.byref(shp))
@@ -165,8 +180,8 @@ class _CRFPBase(nn.Module):
                 lr4=torch.empty(n * t * h * w * 4, **f32),
                 x_lr=torch.empty(n * t * h * w * self.mid_channels, **f32),
                 flows=torch.zeros(n * t * h * w * 2, **f32),
-                state_hr=torch.zeros(n * 64 * h * w * 4, **f32),
-                state_l1=torch.zeros(n * 4 * h * w * 24, **f32),
+                state_hr=self._state_bufs[1],
+                state_l1=self._state_bufs[2],
             )
         return self._ws[key]
 
@@ -186,6 +201,13 @@ class _CRFPBase(nn.Module):
         fvs = fvs.to(torch.float32).contiguous()
         mks = (mks != 0).to(torch.uint8).contiguous() if mks.dtype != torch.bool else mks.contiguous().view(torch.uint8)
         return lrs, fvs, mks
+
+    @staticmethod
+    def _same_storage(pairs):
+        """True when every converted tensor still IS the caller's storage (fp32 / bool, contiguous): only then may a
+        CUDA graph keyed on the input addresses be captured — a temporary made by a dtype / layout conversion lives at an
+        allocator-chosen address that a later replay must not read."""
+        return all(a.data_ptr() == b.data_ptr() for a, b in pairs)
 
     def _run_frames(self, buf, W, lrs, fvs, mks, fgs, out, first_flags, out_host=None, frames=None):
         """Frame loop.  `out_host` (pinned CPU tensor shaped like `out`): every finished frame is copied to the host on a
@@ -232,9 +254,10 @@ class _CRFPBase(nn.Module):
 class CRFP_DSV(_CRFPBase):
     """Drop-in for `model.CRFP.CRFP_DSV` (the model main.py:34 builds)."""
 
-    def forward(self, lrs, fvs, mks, out_host=None):
+    def forward(self, lrs, fvs, mks, out_host=None, out=None):
         """Reference signature `forward(lrs, fvs, mks)`; the optional `out_host` (pinned CPU tensor) additionally
-        streams every finished frame to the host while the recurrence continues."""
+        streams every finished frame to the host while the recurrence continues; the optional `out` (CUDA fp32 tensor
+        (n,t,3,8h,8w)) receives the result in place of a freshly allocated tensor."""
         if self._wants_grad():
             # training: node-by-node forward over the autograd kernel pairs (crfp_b200/training.py); the fused
             # whole-frame inference kernels keep no intermediates to differentiate through
@@ -246,9 +269,11 @@ class CRFP_DSV(_CRFPBase):
             lrs, fvs, mks = self._check_inputs(lrs, fvs, mks)
             return forward_train(self, lrs, fvs, mks)
         with torch.no_grad():
+            user = (lrs, fvs, mks)
             lrs, fvs, mks = self._check_inputs(lrs, fvs, mks)
             key = ("clip", lrs.data_ptr(), fvs.data_ptr(), mks.data_ptr())
-            return self._forward_clip(key, lrs, fvs, mks, out_host, None)
+            direct = self._same_storage(zip(user, (lrs, fvs, mks)))
+            return self._forward_clip(key, lrs, fvs, mks, out_host, None, out=out, graphable=direct)
 
     def _wants_grad(self):
         return torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters())
@@ -258,11 +283,14 @@ class CRFP_DSV(_CRFPBase):
             raise NotImplementedError("crfp_b200: this entry point is inference-only; call under torch.no_grad() / "
                                       "model.eval(), or use forward(lrs, fvs, mks) for training")
 
-    def _forward_clip(self, key, lrs, fvs, mks, out_host, pre):
+    def _forward_clip(self, key, lrs, fvs, mks, out_host, pre, out=None, graphable=True):
         """prepare + frame loop, eagerly or as a replay of the captured whole-clip graph.  `pre(stream)` = extra work
         at the head of the clip (the fovea paste of forward_patch)."""
         n, t, _, h, w = lrs.shape
         dev = lrs.device
+        if out is not None and (tuple(out.shape) != (n, t, 3, 8 * h, 8 * w) or out.dtype != torch.float32 or
+                                out.device != dev or not out.is_contiguous()):
+            raise ValueError(f"out must be a contiguous CUDA fp32 tensor of shape {(n, t, 3, 8 * h, 8 * w)} on {dev}")
         with torch.cuda.device(dev):
             L.check(L.lib().crfp_check_device(), "device check (sm_100 required)")
             W = self._weights(dev)
@@ -281,30 +309,35 @@ class CRFP_DSV(_CRFPBase):
                 frames = None if part is None else range(part * self.graph_frames, min(t, (part + 1) * self.graph_frames))
                 self._run_frames(buf, W, lrs, fvs, mks, None, out, [i == 0 for i in range(t)], out_host, frames)
 
-            key = key + (n, t, h, w, str(dev), 0 if out_host is None else out_host.data_ptr(), bool(self.skip_outside_fovea))
-            if self.use_graphs and not torch.cuda.is_current_stream_capturing():
+            key = key + (n, t, h, w, str(dev), 0 if out_host is None else out_host.data_ptr(), bool(self.skip_outside_fovea),
+                         0 if out is None else out.data_ptr())
+            if self.use_graphs and graphable and not torch.cuda.is_current_stream_capturing():
                 entry = self._graphs.get(key)
                 if entry is None and self._seen_key == key:
-                    entry = self._capture(key, run, (n, t, 3, 8 * h, 8 * w), dev, (t + self.graph_frames - 1) // self.graph_frames)
+                    entry = self._capture(key, run, (n, t, 3, 8 * h, 8 * w), dev, (t + self.graph_frames - 1) // self.graph_frames,
+                                          out)
                 self._seen_key = key
                 if entry is not None:
                     self._graphs.move_to_end(key)
                     for g in entry["graphs"]:
                         g.replay()
                     L.lib().crfp_launch_count_add(entry["launches"])
-                    return entry["out"]
-            out = torch.empty(n, t, 3, 8 * h, 8 * w, device=dev, dtype=torch.float32)
+                    if out is not None or self.alias_output:
+                        return entry["out"]
+                    return entry["out"].clone()
+            if out is None:
+                out = torch.empty(n, t, 3, 8 * h, 8 * w, device=dev, dtype=torch.float32)
             run(out)
         return out
 
-    def _capture(self, key, run, out_shape, dev, parts):
+    def _capture(self, key, run, out_shape, dev, parts, out=None):
         """Capture one whole-clip forward (prepare + every frame, incl. the streaming device->host copies) into CUDA
         graphs of `graph_frames` frames each: the next graph is launched while the previous one executes, so only
-        the first graph's launch latency is exposed.  The entry owns its output tensor: replays on the same input
-        buffers return that same tensor, overwritten by the next replay (`use_graphs = False` or CRFP_NO_GRAPHS=1
-        restores one fresh tensor per call).  Returns None (and switches graphs off) if the capture fails."""
+        the first graph's launch latency is exposed.  The entry owns its output tensor (or writes the caller's `out`);
+        see `alias_output` for what a replay returns.  Returns None (and switches graphs off) if the capture fails."""
         lib = L.lib()
-        out = torch.empty(*out_shape, device=dev, dtype=torch.float32)
+        if out is None:
+            out = torch.empty(*out_shape, device=dev, dtype=torch.float32)
         graphs = []
         try:
             torch.cuda.synchronize(dev)
@@ -327,7 +360,7 @@ class CRFP_DSV(_CRFPBase):
         self._graphs[key] = entry
         return entry
 
-    def forward_patch(self, lrs, fovea_patch, coords, out_host=None):
+    def forward_patch(self, lrs, fovea_patch, coords, out_host=None, out=None):
         """Convenience entry named by BASELINE.json: `fovea_patch` (n,t,3,FV,FV) pasted at integer top-left
         `coords` (n,t,2) = [y, x] exactly as the data loader does (dataset/reds.py:196-201) — on the device, into
         persistent full-frame fvs / mks buffers (only the previous call's rectangles are cleared)."""
@@ -346,8 +379,10 @@ class CRFP_DSV(_CRFPBase):
             if int(cc.min()) < 0 or int(cc[..., 0].max()) > H - fv or int(cc[..., 1].max()) > Wd - fv:
                 raise ValueError("fovea patch outside the frame")
             dev = lrs.device
+            user = (lrs, fovea_patch)
             lrs = lrs.to(torch.float32).contiguous()
             patch = fovea_patch.to(torch.float32).contiguous()
+            direct = self._same_storage(zip(user, (lrs, patch)))
             pk = (n, t, h, w, fv, str(dev))
             if getattr(self, "_patch_buf", None) is None or self._patch_buf[0] != pk:
                 self._graphs.clear()
@@ -380,7 +415,7 @@ class CRFP_DSV(_CRFPBase):
                 pb["prev"].copy_(pb["coords"])
 
             key = ("patch", lrs.data_ptr(), patch.data_ptr(), fv)
-            return self._forward_clip(key, lrs, pb["fvs"], pb["mks"], out_host, pre)
+            return self._forward_clip(key, lrs, pb["fvs"], pb["mks"], out_host, pre, out=out, graphable=direct)
 
 
 class CRFP(CRFP_DSV):
@@ -395,7 +430,13 @@ class CRFP_simple(CRFP_DSV):
 
 class MRCF_simple_v18(_CRFPBase):
     """Drop-in for the streaming `model.CRFP_test.MRCF_simple_v18`: one (or a few) frames per call, recurrent
-    state kept on the module, `clear_states()` between clips."""
+    state kept on the module, `clear_states()` between clips.
+
+    Latency path: the frame protocol of test_video.py:316-374 is one call per frame at batch 1, i.e. ~60 kernel
+    launches of host work per call.  From the third call of a kind (same n, t, h, w; first-of-stream or not) the call is
+    a CUDA-graph replay: the inputs are copied into persistent staging buffers (4 device copies), ONE graph launch runs
+    FNet + encoder + the frame step(s) + the previous-LR-frame update, and the result is returned as a copy of the
+    graph-owned output (`alias_output = True` returns the graph-owned tensor itself)."""
 
     def __init__(self, device, mid_channels=16, y_only=False, hr_dcn=True, offset_prop=True, split_ratio=3,
                  spynet_pretrained=None, precision="tc"):
@@ -404,10 +445,25 @@ class MRCF_simple_v18(_CRFPBase):
             raise L.CrfpError("split_ratio=3 only")
         self.pre_lr = None
         self._has_state = False
+        self._state_key = None      # (n, h, w, device) the recurrent state was built for
+        self._sbuf = {}             # (n, t, h, w, device) -> staging buffers + graphs
 
     def clear_states(self):
         self.pre_lr = None
         self._has_state = False
+        self._state_key = None
+
+    def _stream_buffers(self, n, t, h, w, dev):
+        key = (n, t, h, w, str(dev))
+        if key not in self._sbuf:
+            self._sbuf.clear()
+            H, Wd = 8 * h, 8 * w
+            f32 = dict(device=dev, dtype=torch.float32)
+            self._sbuf[key] = dict(lrs=torch.empty(n, t, 3, h, w, **f32), fvs=torch.empty(n, t, 3, H, Wd, **f32),
+                                   mks=torch.empty(n, t, 1, H, Wd, device=dev, dtype=torch.uint8),
+                                   fgs=torch.empty(n, t, 1, H, Wd, **f32), out=torch.empty(n, t, 3, H, Wd, **f32),
+                                   graphs={}, seen={})
+        return self._sbuf[key]
 
     @torch.no_grad()
     def forward(self, lrs, fvs, mks, fgs):
@@ -417,20 +473,73 @@ class MRCF_simple_v18(_CRFPBase):
         fgs = fgs.to(device=dev, dtype=torch.float32).contiguous()
         if tuple(fgs.shape) != (n, t, 1, 8 * h, 8 * w):
             raise ValueError(f"fgs must be {(n, t, 1, 8 * h, 8 * w)}")
+        skey = (n, h, w, str(dev))
+        if self._has_state and self._state_key != skey:
+            # the reference would fail with a torch shape error when the warped state meets the new frame size
+            raise ValueError(f"the recurrent state belongs to frames of (n, h, w, device) = {self._state_key}, got {skey}: "
+                             "call clear_states() before changing the stream's shape")
+        if self.pre_lr is not None and tuple(self.pre_lr.shape) != (n, 3, h, w):
+            raise ValueError(f"pre_lr has shape {tuple(self.pre_lr.shape)}, expected {(n, 3, h, w)}: call clear_states()")
         with torch.cuda.device(dev):
+            L.check(L.lib().crfp_check_device(), "device check (sm_100 required)")
             W = self._weights(dev)
             buf = self._clip_buffers(n, t, h, w, dev)
-            out = torch.empty(n, t, 3, 8 * h, 8 * w, device=dev, dtype=torch.float32)
-            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-            shp = L.DsvShape(n=n, t=t, h=h, w=w, mid_channels=self.mid_channels)
-            # first frame of a stream is paired with the last frame of this call (CRFP_test.py:2232-2239); its
-            # flow is never used because that frame takes the no-alignment branch
-            prev = self.pre_lr if self.pre_lr is not None else lrs[:, -1].contiguous()
-            L.check(L.lib().crfp_dsv_prepare(C.byref(shp), C.byref(W), lrs.data_ptr(), prev.data_ptr(),
-                                             buf["lr4"].data_ptr(), buf["x_lr"].data_ptr(), buf["flows"].data_ptr(),
-                                             buf["ws"].data_ptr(), buf["ws"].numel(), st), "dsv_prepare")
-            self.pre_lr = lrs[:, -1].clone()
-            first = [(not self._has_state) and i == 0 for i in range(t)]
-            self._run_frames(buf, W, lrs, fvs, mks, fgs, out, first)
+            if "prev" not in buf:
+                buf["prev"] = torch.empty(n, 3, h, w, device=dev, dtype=torch.float32)
+            first0 = not self._has_state
+            have_prev = self.pre_lr is not None
+            if have_prev and self.pre_lr.data_ptr() != buf["prev"].data_ptr():
+                buf["prev"].copy_(self.pre_lr)      # state carried over from a call with another t (new workspace)
+
+            def run(lrs_, fvs_, mks_, fgs_, out_):
+                st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+                shp = L.DsvShape(n=n, t=t, h=h, w=w, mid_channels=self.mid_channels)
+                # the first frame of a stream is paired with the last frame of this call (CRFP_test.py:2232-2239); its
+                # flow is never used because that frame takes the no-alignment branch
+                if not have_prev:
+                    buf["prev"].copy_(lrs_[:, -1])
+                L.check(L.lib().crfp_dsv_prepare(C.byref(shp), C.byref(W), lrs_.data_ptr(), buf["prev"].data_ptr(),
+                                                 buf["lr4"].data_ptr(), buf["x_lr"].data_ptr(), buf["flows"].data_ptr(),
+                                                 buf["ws"].data_ptr(), buf["ws"].numel(), st), "dsv_prepare")
+                buf["prev"].copy_(lrs_[:, -1])
+                self._run_frames(buf, W, lrs_, fvs_, mks_, fgs_, out_, [first0 and i == 0 for i in range(t)])
+
+            out = None
+            if self.use_graphs and not torch.cuda.is_current_stream_capturing():
+                sb = self._stream_buffers(n, t, h, w, dev)
+                gkey = (first0, have_prev, bool(self.skip_outside_fovea))
+                g = sb["graphs"].get(gkey)
+                if g is None:
+                    sb["seen"][gkey] = sb["seen"].get(gkey, 0) + 1
+                    if sb["seen"][gkey] >= 2 and not first0:       # steady-state calls only: capture on the second one
+                        g = self._capture_stream(sb, gkey, run)
+                if g is not None:
+                    sb["lrs"].copy_(lrs); sb["fvs"].copy_(fvs); sb["mks"].copy_(mks); sb["fgs"].copy_(fgs)
+                    g["graph"].replay()
+                    L.lib().crfp_launch_count_add(g["launches"])
+                    out = sb["out"] if self.alias_output else sb["out"].clone()
+            if out is None:
+                out = torch.empty(n, t, 3, 8 * h, 8 * w, device=dev, dtype=torch.float32)
+                run(lrs, fvs, mks, fgs, out)
+            self.pre_lr = buf["prev"]
             self._has_state = True
+            self._state_key = skey
         return out
+
+    def _capture_stream(self, sb, gkey, run):
+        lib = L.lib()
+        try:
+            torch.cuda.synchronize()
+            before = lib.crfp_launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run(sb["lrs"], sb["fvs"], sb["mks"], sb["fgs"], sb["out"])
+            launches = lib.crfp_launch_count() - before
+            lib.crfp_launch_count_add(-launches)        # captured, not launched
+        except Exception as e:  # noqa: BLE001
+            import warnings
+            warnings.warn(f"crfp_b200: CUDA graph capture of the streaming step failed ({e}); continuing without graphs")
+            self.use_graphs = False
+            return None
+        sb["graphs"][gkey] = dict(graph=g, launches=launches)
+        return sb["graphs"][gkey]

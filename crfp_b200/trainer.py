@@ -70,6 +70,35 @@ class Trainer:
             self.ranges.append((start, off))
         self.group_params = [[p for _, p in grp] for grp in groups]
         self.lr = list(self.base_lr)
+        self.sync_parameters()
+
+    def _world(self):
+        if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            return torch.distributed.get_world_size(self.pg)
+        return 1
+
+    def _src_rank(self):
+        """Global rank of group rank 0 (torch.distributed.broadcast takes the GLOBAL rank of the source)."""
+        if self.pg is None:
+            return 0
+        return torch.distributed.get_global_rank(self.pg, 0)
+
+    def sync_parameters(self):
+        """Replicas must START identical: the reference trains ONE weight copy under DataParallel (main.py:37-38,
+        trainer.py:206-293), so under torch.distributed the flat parameter / moment buffers and the step counters of
+        group-rank 0 are broadcast to every rank (as DistributedDataParallel does at construction).  Called by
+        __init__ and load_state_dict; a no-op in a single process."""
+        if self._world() <= 1:
+            return
+        src = self._src_rank()
+        for buf in (self.flat_p, self.flat_m, self.flat_v):
+            torch.distributed.broadcast(buf, src=src, group=self.pg)
+        counters = torch.tensor([self.cur_iter] + list(self.group_steps), device=self.flat_p.device, dtype=torch.int64)
+        torch.distributed.broadcast(counters, src=src, group=self.pg)
+        self.cur_iter, self.group_steps = int(counters[0]), [int(counters[1]), int(counters[2])]
+        self.model._packed = None                                    # inference-side packed weights are stale now
+        if hasattr(self.model, "_graphs"):
+            self.model._graphs.clear()
 
     # ---- trainer.py:604-622
     def get_lr(self, base_lr):
@@ -94,11 +123,10 @@ class Trainer:
                 if p.grad is None:
                     raise RuntimeError("a parameter lost its flat gradient view")
         loss = self._fwd_bwd_graphed(lrs, fvs, mks, hr, train_flow) if self.use_graphs else self._fwd_bwd(lrs, fvs, mks, hr)
-        if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            ws = torch.distributed.get_world_size(self.pg)
-            if ws > 1:                                               # ONE all-reduce of the 9.14 MB bucket
-                torch.distributed.all_reduce(self.flat_g, group=self.pg)
-                self.flat_g.mul_(1.0 / ws)
+        ws = self._world()
+        if ws > 1:                                                   # ONE all-reduce of the 9.14 MB bucket
+            torch.distributed.all_reduce(self.flat_g, group=self.pg)
+            self.flat_g.mul_(1.0 / ws)
         self._adam(train_flow)
         self.cur_iter += 1
         model._packed = None                                         # inference-side packed weights are stale now
@@ -142,16 +170,37 @@ class Trainer:
         return entry["loss"].clone()
 
     # ---- resume (the reference only saves model weights, trainer.py:276-279; the optimiser state is offered on top)
+    def _hyper(self):
+        return {"base_lr": list(self.base_lr), "betas": list(self.betas), "eps": self.eps, "rec_w": self.rec_w,
+                "period": self.period, "min_lr": self.min_lr, "freeze_flow_iters": self.freeze_flow_iters}
+
     def state_dict(self):
         return {"cur_iter": self.cur_iter, "group_steps": list(self.group_steps), "exp_avg": self.flat_m.clone(),
-                "exp_avg_sq": self.flat_v.clone()}
+                "exp_avg_sq": self.flat_v.clone(), "ranges": [list(r) for r in self.ranges], "hyper": self._hyper()}
 
-    def load_state_dict(self, state):
-        if state["exp_avg"].numel() != self.flat_m.numel():
+    def load_state_dict(self, state, strict_hyper=True):
+        """Restores the moments and counters.  The [main | spynet] split of the flat buffers must match (a checkpoint
+        of a model with the same element count but another split would put moments on the wrong parameters); the
+        schedule / Adam hyper-parameters must match too unless strict_hyper=False (then the checkpoint's win)."""
+        if state["exp_avg"].numel() != self.flat_m.numel() or state["exp_avg_sq"].numel() != self.flat_v.numel():
             raise ValueError("optimizer state does not match this model")
+        if "ranges" in state and [list(r) for r in state["ranges"]] != [list(r) for r in self.ranges]:
+            raise ValueError(f"optimizer state was saved for parameter groups {state['ranges']}, this trainer has {self.ranges}")
+        if "hyper" in state:
+            mine = self._hyper()
+            if state["hyper"] != mine:
+                if strict_hyper:
+                    diff = {k: (state["hyper"].get(k), v) for k, v in mine.items() if state["hyper"].get(k) != v}
+                    raise ValueError(f"optimizer hyper-parameters differ from the checkpoint's (saved, current): {diff}")
+                hp = state["hyper"]
+                self.base_lr, self.betas, self.eps, self.rec_w = list(hp["base_lr"]), tuple(hp["betas"]), hp["eps"], hp["rec_w"]
+                self.period, self.min_lr, self.freeze_flow_iters = hp["period"], hp["min_lr"], hp["freeze_flow_iters"]
         self.cur_iter, self.group_steps = int(state["cur_iter"]), [int(x) for x in state["group_steps"]]
-        self.flat_m.copy_(state["exp_avg"])
-        self.flat_v.copy_(state["exp_avg_sq"])
+        self.flat_m.copy_(state["exp_avg"].to(self.flat_m.device))
+        self.flat_v.copy_(state["exp_avg_sq"].to(self.flat_v.device))
+        self._graphs.clear()                                         # captured steps belong to the previous phase
+        self._seen.clear()
+        self.sync_parameters()
 
     def _adam(self, train_flow):
         lib, st = self.K.lib(), self.K.stream()

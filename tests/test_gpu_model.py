@@ -123,6 +123,51 @@ def test_streaming_module_matches_reference_golden(golden_dir, sd, precision):
     assert torch.equal(again, outs[0])
 
 
+def test_streaming_graph_replay_and_state_validation(sd):
+    """MRCF_simple_v18: per-frame CUDA-graph replay (from the third steady-state call on) is bit-identical to eager
+    launches, the clip protocol clear_states() -> frames works across replays, and a frame of another size while state is
+    held raises instead of reading a stale state (the reference fails with a shape error)."""
+    from crfp_b200 import MRCF_simple_v18, _lib
+    n, t, h, w = 1, 7, 16, 24
+    lrs, fvs, mks, _ = make_clip(seed=19, n=n, t=t, h=h, w=w, fv_size=48)
+    fgs = torch.ones(n, t, 1, 8 * h, 8 * w)
+    fgs[:, 3:, :, : 4 * h] = 0.0
+    lrs, fvs, mks, fgs = lrs.cuda(), fvs.cuda(), mks.cuda(), fgs.cuda()
+
+    def stream(m, keep=True):
+        m.clear_states()
+        outs = []
+        for i in range(t):
+            o = m(lrs[:, i:i + 1], fvs[:, i:i + 1], mks[:, i:i + 1], fgs[:, i:i + 1])
+            outs.append(o if keep else o.clone())
+        return torch.cat(outs, 1)
+
+    m = MRCF_simple_v18("cuda", mid_channels=32).eval()
+    m.load_state_dict(sd, strict=True)
+    m.cuda()
+    m.use_graphs = False
+    eager = stream(m)
+    m.use_graphs = True
+    first = stream(m)                      # frames 1.. : eager, capture on the second steady-state call, then replays
+    assert any(sb["graphs"] for sb in m._sbuf.values())
+    _lib.lib().crfp_launch_count_reset()
+    again = stream(m)                      # frame 0 eager, frames 1.. replayed
+    assert _lib.lib().crfp_launch_count() > 0
+    torch.cuda.synchronize()
+    assert torch.equal(first, eager) and torch.equal(again, eager)
+    # two frames per call take their own graph and continue the same recurrence
+    m.clear_states()
+    o01 = m(lrs[:, 0:2], fvs[:, 0:2], mks[:, 0:2], fgs[:, 0:2])
+    o2 = m(lrs[:, 2:3], fvs[:, 2:3], mks[:, 2:3], fgs[:, 2:3])     # t changes between calls: the state survives
+    assert torch.equal(o01, eager[:, 0:2]) and torch.equal(o2, eager[:, 2:3])
+    # another frame size while state is held
+    lrs2, fvs2, mks2, _ = make_clip(seed=20, n=1, t=1, h=24, w=24, fv_size=48)
+    with pytest.raises(ValueError, match="clear_states"):
+        m(lrs2.cuda(), fvs2.cuda(), mks2.cuda(), torch.ones(1, 1, 1, 192, 192).cuda())
+    m.clear_states()
+    assert torch.isfinite(m(lrs2.cuda(), fvs2.cuda(), mks2.cuda(), torch.ones(1, 1, 1, 192, 192).cuda())).all()
+
+
 def test_reds_native_shape_long_clip_properties(model, sd):
     """BASELINE config-2 shape (LR 90x160 -> 720x1280), t=12: finite, deterministic, and frame i only depends on
     frames <= i (causality of the recurrence): a 12-frame run and an 8-frame run agree on the first 8 frames."""
@@ -183,7 +228,24 @@ def test_cuda_graph_replay_matches_eager(sd):
     o3 = m(lrs, fvs, mks)                 # replay
     assert _lib.lib().crfp_launch_count() == n_eager > 0
     torch.cuda.synchronize()
-    assert o3 is o2 and torch.equal(o1, eager) and torch.equal(o3, eager)
+    assert torch.equal(o1, eager) and torch.equal(o3, eager)
+    # default contract: every call returns its own tensor (results kept by the caller survive later replays) ...
+    assert o3 is not o2 and o3.data_ptr() != o2.data_ptr()
+    # ... aliasing is opt-in: the graph-owned tensor itself, or the caller's own `out` buffer
+    m.alias_output = True
+    a1, a2 = m(lrs, fvs, mks), m(lrs, fvs, mks)
+    assert a1 is a2 and torch.equal(a1, eager)
+    m.alias_output = False
+    mine = torch.empty_like(eager)
+    for _ in range(3):                    # eager, capture, replay — all into the caller's buffer
+        mine.zero_()
+        r = m(lrs, fvs, mks, out=mine)
+        assert r.data_ptr() == mine.data_ptr() and torch.equal(mine, eager)
+    # inputs that need a conversion (temporaries at allocator-chosen addresses) never enter a graph
+    ngraphs = len(m._graphs)
+    for _ in range(3):
+        assert torch.equal(m(lrs.double(), fvs, mks), eager)
+    assert len(m._graphs) == ngraphs
     # the graph reads the buffers, not a snapshot of their contents
     lrs2, fvs2, mks2, _ = make_clip(seed=34, n=1, t=4, h=24, w=40, fv_size=64)
     lrs.copy_(lrs2.cuda()); fvs.copy_(fvs2.cuda()); mks.copy_(mks2.cuda())

@@ -252,3 +252,61 @@ def test_trainer_resume_continues_the_same_trajectory():
     loss_b = tr_b.step(lrs, fvs, mks, hr)
     assert loss_a.item() == loss_b.item() and tr_b.cur_iter == 3 and tr_b.group_steps == [3, 2]
     assert torch.equal(tr.flat_p, tr_b.flat_p) and torch.equal(tr.flat_m, tr_b.flat_m)
+
+
+def _ddp_seed_worker(rank, world, port, out_dir):
+    """Ranks built from DIFFERENT weights (what independent `kaiming_normal_` inits or different checkpoints give): the
+    Trainer must broadcast rank 0's parameters at construction so the replicas start — and stay — identical."""
+    import os
+    import sys
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _, model, lrs, fvs, mks, hr = _setup(5, 2, 2, 8, 8)
+        model.load_state_dict(make_state_dict(seed=11 + rank), strict=True)        # rank-dependent start
+        before = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone()
+        tr = Trainer(model, freeze_flow_iters=0, kernels=hostemu.HostEmuKernelSet())
+        start = tr.flat_p.clone()
+        sl = slice(rank, rank + 1)
+        tr.step(lrs[sl], fvs[sl], mks[sl], hr[sl])
+        st = tr.state_dict()
+        st["cur_iter"] += 7 * rank                                                 # rank-dependent resume state
+        st["exp_avg"] = st["exp_avg"] + float(rank)
+        tr.load_state_dict(st)
+        torch.save({"before": before, "start": start, "p": tr.flat_p.clone(), "m": tr.flat_m.clone(), "it": tr.cur_iter},
+                   os.path.join(out_dir, f"s{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_replicas_are_synchronised_from_rank_zero(tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_ddp_seed_worker, args=(2, 29547, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (torch.load(tmp_path / f"s{r}.pt") for r in (0, 1))
+    assert not torch.equal(r0["before"], r1["before"])                            # the ranks really started apart
+    assert torch.equal(r0["start"], r1["start"])                                   # identical after construction
+    # rank 0's parameters win (the flat buffer is ordered [main | spynet], so compare order-free sums)
+    assert abs(float(r0["start"].double().sum()) - float(r0["before"].double().sum())) < 1e-6
+    assert torch.equal(r0["p"], r1["p"])                                           # still identical after a step
+    assert torch.equal(r0["m"], r1["m"]) and r0["it"] == r1["it"] == 1             # load_state_dict re-syncs from rank 0
+
+
+def test_trainer_state_dict_is_validated():
+    sd, model, lrs, fvs, mks, hr = _setup(3, 1, 2, 8, 8)
+    tr = Trainer(model, freeze_flow_iters=0, period=10, kernels=K)
+    tr.step(lrs, fvs, mks, hr)
+    st = tr.state_dict()
+    assert st["ranges"] == [list(r) for r in tr.ranges] and st["hyper"]["period"] == 10
+    bad = dict(st, ranges=[[0, 5], [5, st["exp_avg"].numel()]])
+    with pytest.raises(ValueError, match="parameter groups"):
+        tr.load_state_dict(bad)
+    model2 = CRFP_DSV("cuda", mid_channels=32)
+    model2.load_state_dict(sd, strict=True)
+    tr2 = Trainer(model2, freeze_flow_iters=0, period=20, kernels=K)
+    with pytest.raises(ValueError, match="hyper-parameters"):
+        tr2.load_state_dict(st)
+    tr2._graphs["x"], tr2._seen["x"] = 1, 1
+    tr2.load_state_dict(st, strict_hyper=False)                                    # the checkpoint's schedule wins
+    assert tr2.period == 10 and tr2.cur_iter == 1 and not tr2._graphs and not tr2._seen
