@@ -1,22 +1,31 @@
 #!/usr/bin/env python
 """bench.py — output frames/s of the CRFP hot path (CRFP_DSV.forward) on B200, per the driver contract.
 
-A "step" is one forward of one synthetic clip (per rank) through the drop-in module:
+A "step" is one forward of this rank's synthetic clip(s) through the drop-in module:
   workload "R-lit"  : LR 180x320 (REDS *_sharp_BI frames, BASELINE.json configs[1]) through the x8 network
                       -> 1440x2560, t frames (default 100)
   workload "R-nat"  : LR 90x160 -> 720x1280 (the x8 network's native route to 1280x720)
   workload "V7"     : LR 64x112, t=7 (configs[0], the reference's CPU-runnable case)
-`value`  = frames/s with the clip already resident in HBM (CUDA events, max over ranks).
-`e2e`    = frames/s through the public API from HOST buffers: pinned lrs + fovea patches + coords H2D, forward,
-           output frames D2H, all inside the timed region.
-`roofline` = the align kernel (DCNv2 @L1, the kernel BASELINE.json's metric names) timed alone through the C ABI.
-`cpu_baseline` / `--impl reference` = the oracle port of the reference's PyTorch path on the host cores.
+`value`    = frames/s with the clip already resident in HBM (CUDA events, max over ranks).
+`e2e`      = frames/s through the public API from HOST buffers: pinned lrs + fovea patches + coords H2D, forward,
+             output frames D2H, all inside the timed region; event-timed AND wall-clock-timed.
+`roofline` = the dominant kernel (conv_tc3_ws, per-frame launch mix) and the align kernel (DCNv2 @L1, the kernel
+             BASELINE.json's metric names), each timed alone through the C ABI with CUDA events; `traffic` is read from the
+             committed ncu DRAM-byte capture under profiles/ (null when there is none for the workload).
+`cpu_baseline` / `--impl reference` = the oracle port of the reference's PyTorch path on the host cores, steady-state
+             frames only.   `gpu_stock_baseline` = the same PyTorch path moved to the B200 (cuDNN,
+             ATen grid_sample, torchvision deform_conv2d; TF32 off and on) — the GPU baseline the kernels must beat.
+`extra`    = the other shapes (R-nat, V7) measured the same way, shorter.
+--total-clips N : BASELINE.json configs[2] — N clips strong-sharded across the ranks (N / world per GPU, sequentially).
 """
 from __future__ import annotations
 
 import argparse
+import csv
+import glob
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -28,6 +37,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {"R-lit": (180, 320, 100), "R-nat": (90, 160, 100), "V7": (64, 112, 7)}
 METRIC = "output frames/sec"
 ALIGN_BYTES_PER_L1_PX = 1120  # (32 in + 144 offset + 72 mask + 32 out) fp32, SURVEY.md 8(d)
+FV = 96
 
 
 def parse():
@@ -38,12 +48,28 @@ def parse():
     ap.add_argument("--impl", default="crfp_b200", choices=["crfp_b200", "reference"])
     ap.add_argument("--workload", default="R-lit", choices=list(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="override frames per clip")
-    ap.add_argument("--clips", type=int, default=1, help="clips per GPU per step")
-    ap.add_argument("--precision", default="tc", choices=["tc", "fp32"],
-                    help="tc: fp32 storage, tcgen05 3 x bf16 split contractions (fp32-grade, default); fp32: all-SIMT FFMA")
+    ap.add_argument("--clips", type=int, default=1, help="clips per forward call (batch dimension n)")
+    ap.add_argument("--total-clips", type=int, default=0,
+                    help="configs[2]: this many clips in total, strong-sharded across the ranks (total/world per GPU per step)")
+    ap.add_argument("--precision", default="tc", choices=["tc", "fp32", "half"],
+                    help="tc: fp32 storage, tcgen05 3 x bf16 split contractions (fp32-grade, default); fp32: all-SIMT FFMA; "
+                         "half: reduced-precision tier (north_star's bf16 tier)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the R-nat / V7 extra lines and the stock-PyTorch GPU baseline")
     return ap.parse_args()
+
+
+def workload_config(workload, h, w, t, clips_per_step, total_clips=0):
+    """The WORKLOAD description both arms print (identical dicts -> same_config)."""
+    tag = {"R-lit": "BASELINE.json configs[1]", "R-nat": "the x8 network's route to 1280x720", "V7": "BASELINE.json configs[0]"}[workload]
+    cfg = {"workload": f"{workload}: LR {h}x{w} -> {8 * h}x{8 * w} (x8 network; {tag}), "
+                       f"{t}-frame clip, fovea {FV}x{FV}, CRFP_DSV mid_channels=32",
+           "clips_per_gpu": clips_per_step, "frames_per_clip": t,
+           "l2": "per-step working set (>= 4 GB of HR planes at R-lit) exceeds the 126 MB L2"}
+    if total_clips:
+        cfg["total_clips"] = total_clips
+    return cfg
 
 
 class ClockSampler:
@@ -90,49 +116,100 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_fps(h, w, frames, threads):
-    """The reference's PyTorch path (oracle port, bit-identical to the reference on CPU) on the host cores."""
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_steady(h, w, frames, threads):
+    """The reference's PyTorch path (oracle port, bit-identical to the reference on CPU) on the host cores, one clip of
+    `frames` frames.  Returns (steady-state frames, seconds attributed to them): the clip-level work (FNet flows,
+    encoders) is prorated per frame and the first frame — which has no alignment path at all (CRFP.py:1634-1670) — is
+    excluded, i.e. frames 2..t as BASELINE.md 3.5 prescribes."""
     import torch
     from crfp_b200.synthetic import make_clip, make_state_dict
     from oracle import crfp_oracle as O
     torch.set_num_threads(threads)
     sd = make_state_dict(seed=1)
-    lrs, fvs, mks, _ = make_clip(seed=2, n=1, t=frames, h=h, w=w, fv_size=96)
-    t0 = time.perf_counter()
-    out = O.crfp_dsv_forward(sd, lrs, fvs, mks)
-    dt = time.perf_counter() - t0
-    assert out.shape[1] == frames
-    return frames / dt, dt
+    lrs, fvs, mks, _ = make_clip(seed=2, n=1, t=frames, h=h, w=w, fv_size=FV)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        flows = O.compute_flow(sd, lrs)
+        x_lr, x_hr = O.encoders(sd, lrs, fvs, mks)
+        t_clip = time.perf_counter() - t0
+        state, t_frames = None, []
+        for i in range(frames):
+            t1 = time.perf_counter()
+            out, state = O.frame_step(sd, 32, state, x_lr[:, i], x_hr[:, i], mks[:, i], lrs[:, i],
+                                      flows[:, i - 1] if i else None)
+            t_frames.append(time.perf_counter() - t1)
+        assert out.shape[-2:] == (8 * h, 8 * w)
+    steady = frames - 1
+    return steady, t_clip * steady / frames + sum(t_frames[1:]), t_clip + sum(t_frames)
 
 
 def run_reference(args):
-    """`--impl reference`: rank 0 times the CPU path on a bounded sample of the same workload."""
+    """`--impl reference`: rank 0 times the CPU path on a bounded sample of the same workload (3-frame clips; the rate
+    counts the 2 steady-state frames of each)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    h, w, _ = WORKLOADS[args.workload]
-    frames = 2
+    h, w, t = WORKLOADS[args.workload]
+    if args.frames:
+        t = args.frames
+    frames = 3
     cores = os.cpu_count() or 1
-    for _ in range(args.warmup):
-        cpu_reference_fps(h, w, frames, cores)
-    times = []
+    for _ in range(min(args.warmup, 2)):          # the CPU path has no lazy state worth more than two warm-ups
+        cpu_reference_steady(h, w, frames, cores)
+    nf, total, wall = 0, 0.0, 0.0
     for _ in range(args.steps):
-        _, dt = cpu_reference_fps(h, w, frames, cores)
-        times.append(dt)
-    total = sum(times)
-    value = frames * args.steps / total
-    sample = f"{frames}-frame clip of {args.workload} (LR {h}x{w} -> {8 * h}x{8 * w}) per step, oracle port, torch CPU fp32"
+        k, dt, full = cpu_reference_steady(h, w, frames, cores)
+        nf, total, wall = nf + k, total + dt, wall + full
+    value = nf / total
+    sample = (f"{frames}-frame clips of {args.workload} (LR {h}x{w} -> {8 * h}x{8 * w}), one per step; rate = steady-state "
+              f"frames 2..{frames} (clip-level FNet / encoder work prorated, the alignment-free first frame excluded), "
+              f"oracle port of the reference's PyTorch path, torch CPU fp32, {wall / args.steps:.1f} s wall per step")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: LR {h}x{w} -> {8 * h}x{8 * w} (x8 network), {frames} frames/step",
-                   "clips_per_gpu": 1},
+        "config": workload_config(args.workload, h, w, t, args.clips, args.total_clips),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+# ------------------------------------------------------------------------------------------------ stock PyTorch on the GPU
+def gpu_stock_baseline(torch, h, w, t=5):
+    """The reference's PyTorch path (oracle port) moved to the B200 as is: cuDNN convs, ATen grid_sample, torchvision
+    deform_conv2d.  Protocol of /root/reference/test_runtime.py:142-186: 30 runs, the first 9 are warm-up, CUDA events
+    around each of the 21 timed runs.  TF32 off and on.  A BASELINE leg (like cpu_baseline), not a product path."""
+    from crfp_b200.synthetic import make_clip, make_state_dict
+    from oracle import crfp_oracle as O
+    sd = {k: v.cuda() for k, v in make_state_dict(seed=1).items()}
+    lrs, fvs, mks, _ = make_clip(seed=2, n=1, t=t, h=h, w=w, fv_size=FV)
+    lrs, fvs, mks = lrs.cuda(), fvs.cuda(), mks.cuda()
+    res = {"frames_per_run": t, "runs": 21, "warmup_runs": 9,
+           "what": "oracle port of the reference's PyTorch path on the same B200 (cuDNN / ATen / torchvision deform_conv2d)"}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for name, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            total = 0.0
+            with torch.no_grad():
+                for i in range(30):
+                    torch.cuda.synchronize()
+                    a.record()
+                    O.crfp_dsv_forward(sd, lrs, fvs, mks)
+                    b.record()
+                    torch.cuda.synchronize()
+                    if i >= 9:
+                        total += a.elapsed_time(b) * 1e-3
+            res[name + "_fps"] = t * 21 / total
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    return res
+
+
+# ------------------------------------------------------------------------------------------------ kernels timed alone
 def _events_avg_ms(torch, launch, reps, warm=3):
     for i in range(warm):
         launch(i)
@@ -148,25 +225,33 @@ def _events_avg_ms(torch, launch, reps, warm=3):
 
 
 def time_align_kernel(torch, h1, w1, precision, reps=12):
-    """Average device time of the DCNv2 @L1 align kernel alone (C ABI), 3 rotating input sets > L2 (cold launches)."""
+    """Average device time of the DCNv2 @L1 align kernel alone (C ABI), 3 rotating input sets > L2 (cold launches).
+    Tensor-core precisions run it the way the frame does: RAW head-conv outputs in, tanh / sigmoid / + flow applied by
+    the sampler (crfp_dcn_desc.head_raw) unless CRFP_HEAD_EPI=1 restores the two-pass form."""
     import ctypes as C
     from crfp_b200 import _lib as L
     from crfp_b200.packing import pack_dcn, pack_dcn_tc3
     dev = torch.device("cuda")
     g = torch.Generator(device="cpu").manual_seed(0)
+    raw = precision != "fp32" and os.environ.get("CRFP_HEAD_EPI") is None
     nbuf = 3  # 3 x (29 + 199) MB > 126 MB L2
     xs = [torch.randn(1, h1, w1, 32, generator=g).to(dev) for _ in range(nbuf)]
     oms, flows = [], []
     for _ in range(nbuf):
         fl = torch.randn(1, h1, w1, 2, generator=g) * 2.0
         om = torch.empty(1, h1, w1, 216)
-        om[..., :144] = torch.tanh(torch.randn(1, h1, w1, 144, generator=g)) * 10.0 * 0.35 + fl.flip(-1).repeat(1, 1, 1, 72)
-        om[..., 144:] = torch.rand(1, h1, w1, 72, generator=g)
+        pre_off = torch.randn(1, h1, w1, 144, generator=g) * 0.37          # 10 * tanh(.) ~ a few pixels
+        pre_msk = torch.randn(1, h1, w1, 72, generator=g)
+        if raw:
+            om[..., :144], om[..., 144:] = pre_off, pre_msk
+        else:
+            om[..., :144] = torch.tanh(pre_off) * 10.0 + fl.flip(-1).repeat(1, 1, 1, 72)
+            om[..., 144:] = torch.sigmoid(pre_msk)
         oms.append(om.to(dev)); flows.append(fl.to(dev))
     wt = (torch.randn(32, 32, 3, 3, generator=g) * 0.05).to(dev)
     out = torch.empty(1, h1, w1, 32, device=dev)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    if precision == "tc":
+    if precision != "fp32":
         hi, lo, bp = pack_dcn_tc3(wt, torch.zeros(32, device=dev), 8)
         wptr = hi.data_ptr()
     else:
@@ -179,12 +264,14 @@ def time_align_kernel(torch, h1, w1, precision, reps=12):
                       x_coffset=0, offset=oms[k].data_ptr(), off_cstride=216, off_coffset=0,
                       mask=oms[k].data_ptr(), mask_cstride=216, mask_coffset=144, weight=wptr,
                       bias=bp.data_ptr(), out=out.data_ptr(), out_cstride=32, out_coffset=0)
-        if precision == "tc":
+        if raw:
+            d.head_raw, d.head_flow, d.head_mag = 1, flows[k].data_ptr(), 10.0
+        if precision != "fp32":
             L.check(L.lib().crfp_dcn_v2_tc3_fwd(C.byref(d), lo.data_ptr(), flows[k].data_ptr(), st), "dcn_v2_tc3")
         else:
             L.check(L.lib().crfp_dcn_v2_fwd(C.byref(d), st), "dcn_v2")
 
-    return _events_avg_ms(torch, launch, reps)
+    return _events_avg_ms(torch, launch, reps), raw
 
 
 def time_conv_mix(torch, h1, w1, reps=4):
@@ -196,6 +283,7 @@ def time_conv_mix(torch, h1, w1, reps=4):
     from crfp_b200.packing import pack_conv_tc3
     dev = torch.device("cuda")
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    raw_heads = os.environ.get("CRFP_HEAD_EPI") is None
     # (source channels, extra flow channels, cout, count per frame, output kind)
     layers = [([32, 32], 2, 32, 3, "nhwc"), ([32], 0, 32, 9, "nhwc"), ([32, 32], 0, 32, 5, "nhwc"),
               ([32], 0, 216, 3, "nhwc"), ([24], 0, 64, 1, "shuffle4"), ([32], 0, 64, 1, "shuffle4")]
@@ -220,8 +308,10 @@ def time_conv_mix(torch, h1, w1, reps=4):
                 t = buf24 if c == 24 else bufs[(rot + i) % 5]
                 d.src[i] = L.TcSrc(ptr=t.data_ptr(), c=c, cstride=t.shape[-1], coffset=0)
             d.cout, d.act = cout, 1
-            if cout == 216:   # the fused offset + mask heads: 10 * tanh + flow on 144 channels, sigmoid on 72
-                d.act, d.flow, d.head_split, d.head_mag = L.ACT_DCN_HEAD, flow.data_ptr(), 144, 10.0
+            if cout == 216:   # the fused offset + mask heads: raw outputs (the align kernel's sampler activates them)
+                d.act = 0     # ... or the two-pass form: 10 * tanh + flow on 144 channels, sigmoid on 72, in this epilogue
+                if not raw_heads:
+                    d.act, d.flow, d.head_split, d.head_mag = L.ACT_DCN_HEAD, flow.data_ptr(), 144, 10.0
             d.weight_hi, d.weight_lo, d.bias = hi.data_ptr(), lo.data_ptr(), bp.data_ptr()
             if extra:
                 d.extra, d.w_extra = flow.data_ptr(), wx.data_ptr()
@@ -246,6 +336,156 @@ def time_conv_mix(torch, h1, w1, reps=4):
     return ms / len(descs), len(descs), tot_bytes / len(descs), tot_flop / len(descs)
 
 
+def dram_traffic_from_profiles(workload, kernel_regex, grid_regex=None):
+    """Mean dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels matching `kernel_regex`, from the newest
+    committed ncu capture profiles/rNN/*dram*<workload>*.csv.  Returns (bytes or None, path or None, launches)."""
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", f"*dram*{workload}*.csv")),
+                   key=lambda p: (re.findall(r"profiles/r(\d+)", p.replace(os.sep, "/"))[-1], os.path.basename(p)))
+    if not paths:
+        return None, None, 0
+    path = paths[-1]
+    per = {}
+    try:
+        with open(path, newline="") as f:
+            rows = [r for r in csv.reader(f) if len(r) >= 15 and r[0].isdigit()]
+        for r in rows:
+            if r[12] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and re.search(kernel_regex, r[4]) and \
+                    (grid_regex is None or re.search(grid_regex, r[8])):
+                v = float(r[14].replace(",", ""))
+                v *= {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[13], 1.0)
+                per[r[0]] = per.get(r[0], 0.0) + v
+    except Exception:
+        return None, None, 0
+    if not per:
+        return None, os.path.relpath(path, ROOT), 0
+    return sum(per.values()) / len(per), os.path.relpath(path, ROOT), len(per)
+
+
+# ------------------------------------------------------------------------------------------------ one workload
+def make_host_inputs(torch, n, t, h, w, seed):
+    """Synthetic clip: smooth-ish LR frames, Gaussian gaze walk, random fovea patches; pinned."""
+    H, W_ = 8 * h, 8 * w
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    coarse = torch.rand(n, t, 3, max(h // 8, 2), max(w // 8, 2), generator=g)
+    lrs_h = torch.nn.functional.interpolate(coarse.view(n * t, 3, *coarse.shape[-2:]), size=(h, w), mode="bicubic",
+                                            align_corners=False).view(n, t, 3, h, w)
+    lrs_h = (lrs_h + 0.05 * torch.rand(n, t, 3, h, w, generator=g)).clamp_(0, 1).contiguous().pin_memory()
+    patch_h = torch.rand(n, t, 3, FV, FV, generator=g).pin_memory()
+    gy = (torch.randn(n, t, generator=g) * 50 + H / 2).floor().long() - FV // 2
+    gx = (torch.randn(n, t, generator=g) * 50 + W_ / 2).floor().long() - FV // 2
+    coords = torch.stack([gy.clamp(0, H - FV), gx.clamp(0, W_ - FV)], -1)
+    return lrs_h, patch_h, coords
+
+
+def measure(torch, dist, model, workload, t, n, calls, steps, warmup, world, rank, dev, do_e2e, sampler=None):
+    """Device-resident and end-to-end throughput of `calls` forward calls of n clips each per step."""
+    from crfp_b200 import _lib
+    h, w, _ = WORKLOADS[workload]
+    H, W_ = 8 * h, 8 * w
+    lrs_h, patch_h, coords = make_host_inputs(torch, n, t, h, w, 100 + rank)
+
+    lrs = lrs_h.to(dev, non_blocking=True)
+    patch = patch_h.to(dev, non_blocking=True)
+    fvs = torch.zeros(n, t, 3, H, W_, device=dev)
+    mks = torch.zeros(n, t, 1, H, W_, device=dev, dtype=torch.bool)
+    for b in range(n):
+        for i in range(t):
+            y, x = int(coords[b, i, 0]), int(coords[b, i, 1])
+            fvs[b, i, :, y:y + FV, x:x + FV] = patch[b, i]
+            mks[b, i, :, y:y + FV, x:x + FV] = True
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def host_decouple():
+        """A device spin kernel ahead of the start event: the host enqueues the timed region (graph launches) while the
+        GPU is still spinning, so a host stall (this pool's VMs page memory in lazily: 50-150 ms hiccups were measured)
+        cannot starve the GPU inside the device-timed region.  The spin ends before the start event fires."""
+        torch.cuda._sleep(int(min(1.0, 0.2 + 0.01 * steps * calls) * 1.9e9))
+
+    def step():
+        for _ in range(calls):             # the clips of this rank, one forward call each (same resident buffers)
+            o = model(lrs, fvs, mks)
+        return o
+
+    for _ in range(warmup):
+        out = step()
+    barrier()
+    _lib.lib().crfp_launch_count_reset()
+    if sampler is not None:
+        sampler.mark()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    host_decouple()
+    e0.record()
+    for _ in range(steps):
+        out = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = int(_lib.lib().crfp_launch_count())
+    clocks = sampler.stop() if sampler is not None else None
+    assert torch.isfinite(out[:, -1]).all()
+    tms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    frames_total = world * n * t * calls * steps
+    res = {"value": frames_total / (ms_max * 1e-3), "ms_per_step": ms_max / steps, "gpu_launches": launches, "clocks": clocks}
+
+    if do_e2e:
+        out_h = torch.empty(n, t, 3, H, W_, dtype=torch.float32).pin_memory()
+        lrs_d, patch_d = torch.empty_like(lrs_h, device=dev), torch.empty_like(patch_h, device=dev)
+
+        def e2e_step():
+            for _ in range(calls):
+                lrs_d.copy_(lrs_h, non_blocking=True)       # H2D from pinned memory, every call
+                patch_d.copy_(patch_h, non_blocking=True)
+                model.forward_patch(lrs_d, patch_d, coords, out_host=out_h)   # coords: host integers, copied inside
+                # every frame is D2H-copied to pinned memory on a side stream while later frames compute
+
+        del fvs, mks, out
+        model._graphs.clear()
+        for _ in range(max(2, min(warmup, 3))):
+            e2e_step()
+        barrier()
+        host_decouple()          # as above: the K steps (H2D copies, graph launches, D2H copies) are enqueued during the spin
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            e2e_step()
+        e1.record()
+        enq = (time.perf_counter() - t0) * 1e3
+        barrier()
+        ems = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        # the same K steps once more under the WALL clock, without the spin: barrier + sync on both sides
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            e2e_step()
+        barrier()
+        wall = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+            dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        d2h = int(out_h.numel() * 4) * calls
+        res["e2e"] = {"value": frames_total / (float(ems.item()) * 1e-3), "unit": "frames/s",
+                      "ms_per_step": float(ems.item()) / steps,
+                      "wall_value": frames_total / (float(wall.item()) * 1e-3), "wall_ms_per_step": float(wall.item()) / steps,
+                      "host_enqueue_ms_per_step": enq / steps,
+                      "h2d_bytes_per_step": int(lrs_h.numel() * 4 + patch_h.numel() * 4 + coords.numel() * 4) * calls,
+                      "d2h_bytes_per_step": d2h,
+                      "d2h_gbs_per_rank": d2h / (float(ems.item()) / steps * 1e-3) / 1e9,
+                      "api": "CRFP_DSV.forward_patch(lrs, fovea_patch, coords, out_host=pinned): H2D of lrs + patches + coords, "
+                             "device-side fovea paste, forward, every frame D2H-copied on a side stream while the recurrence "
+                             "continues. `value`: CUDA events around the K steps (copies included, host enqueue time beside "
+                             "it); `wall_value`: the same K steps under time.perf_counter between two barrier+synchronize"}
+        del out_h
+    return res
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -253,7 +493,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from crfp_b200 import CRFP_DSV, _lib
+    from crfp_b200 import CRFP_DSV
     from crfp_b200.synthetic import make_state_dict
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -270,119 +510,28 @@ def main():
         t = args.frames
     n = args.clips
     H, W_ = 8 * h, 8 * w
-    fv = 96
+    calls, scaling = 1, "weak"
+    if args.total_clips:
+        if args.total_clips % (world * n):
+            raise SystemExit("--total-clips must be a multiple of gpus x clips")
+        calls, scaling = args.total_clips // (world * n), "strong"
 
     model = CRFP_DSV("cuda", mid_channels=32, precision=args.precision).eval()
     model.load_state_dict(make_state_dict(seed=1), strict=True)
     model.to(dev)
 
-    # synthetic clip: smooth-ish LR frames, Gaussian gaze, random fovea patch; seeded per rank
-    g = torch.Generator(device="cpu").manual_seed(100 + rank)
-    coarse = torch.rand(n, t, 3, max(h // 8, 2), max(w // 8, 2), generator=g)
-    lrs_h = torch.nn.functional.interpolate(coarse.view(n * t, 3, *coarse.shape[-2:]), size=(h, w), mode="bicubic",
-                                            align_corners=False).view(n, t, 3, h, w)
-    lrs_h = (lrs_h + 0.05 * torch.rand(n, t, 3, h, w, generator=g)).clamp_(0, 1).contiguous().pin_memory()
-    patch_h = torch.rand(n, t, 3, fv, fv, generator=g).pin_memory()
-    gy = (torch.randn(n, t, generator=g) * 50 + H / 2).floor().long() - fv // 2
-    gx = (torch.randn(n, t, generator=g) * 50 + W_ / 2).floor().long() - fv // 2
-    coords = torch.stack([gy.clamp(0, H - fv), gx.clamp(0, W_ - fv)], -1)
-
-    def build_inputs():
-        lrs = lrs_h.to(dev, non_blocking=True)
-        patch = patch_h.to(dev, non_blocking=True)
-        fvs = torch.zeros(n, t, 3, H, W_, device=dev)
-        mks = torch.zeros(n, t, 1, H, W_, device=dev, dtype=torch.bool)
-        for b in range(n):
-            for i in range(t):
-                y, x = int(coords[b, i, 0]), int(coords[b, i, 1])
-                fvs[b, i, :, y:y + fv, x:x + fv] = patch[b, i]
-                mks[b, i, :, y:y + fv, x:x + fv] = True
-        return lrs, fvs, mks
-
-    lrs, fvs, mks = build_inputs()
-    torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def host_decouple():
-        """A device spin kernel ahead of the start event: the host enqueues the whole timed region (K graph launches)
-        while the GPU is still spinning, so a host stall (this pool's VMs page memory in lazily: 50-150 ms hiccups
-        were measured) cannot starve the GPU inside the timed region.  The spin ends before the start event fires."""
-        torch.cuda._sleep(int(min(1.0, 0.2 + 0.01 * args.steps) * 1.9e9))
-
-    # ---------------- device-resident throughput
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler is not None:
         sampler.start()          # nvidia-smi -lms 100 starts sampling during the warm-up, keeps going through the timed region
-    for _ in range(args.warmup):
-        out = model(lrs, fvs, mks)
-    barrier()
-    _lib.lib().crfp_launch_count_reset()
-    sampler.mark()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    host_decouple()
-    e0.record()
-    for _ in range(args.steps):
-        out = model(lrs, fvs, mks)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = int(_lib.lib().crfp_launch_count())
-    clocks = sampler.stop() if rank == 0 else None
-    assert torch.isfinite(out[:, -1]).all()
-    tms = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_max = float(tms.item())
-    frames_total = world * n * t * args.steps
-    value = frames_total / (ms_max * 1e-3)
-
-    # ---------------- end-to-end through the public API from host buffers
-    e2e = None
-    if not args.no_e2e:
-        out_h = torch.empty(n, t, 3, H, W_, dtype=torch.float32).pin_memory()
-        lrs_d, patch_d = torch.empty_like(lrs_h, device=dev), torch.empty_like(patch_h, device=dev)
-
-        def e2e_step():
-            lrs_d.copy_(lrs_h, non_blocking=True)       # H2D from pinned memory, every step
-            patch_d.copy_(patch_h, non_blocking=True)
-            model.forward_patch(lrs_d, patch_d, coords, out_host=out_h)   # coords: host integers, copied inside
-            # every frame is D2H-copied to pinned memory on a side stream while later frames compute
-
-        del fvs, mks, out
-        model._graphs.clear()
-        for _ in range(max(2, min(args.warmup, 3))):
-            e2e_step()
-        barrier()
-        host_decouple()          # as above: the K steps (H2D copies, graph launches, D2H copies) are enqueued during the spin
-        t0 = time.perf_counter()
-        e0.record()
-        for _ in range(args.steps):
-            e2e_step()
-        e1.record()
-        enq = (time.perf_counter() - t0) * 1e3
-        barrier()
-        ems = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        e2e = {"value": frames_total / (float(ems.item()) * 1e-3), "unit": "frames/s",
-               "ms_per_step": float(ems.item()) / args.steps, "host_enqueue_ms_per_step": enq / args.steps,
-               "h2d_bytes_per_step": int(lrs_h.numel() * 4 + patch_h.numel() * 4 + coords.numel() * 4),
-               "d2h_bytes_per_step": int(out_h.numel() * 4),
-               "api": "CRFP_DSV.forward_patch(lrs, fovea_patch, coords, out_host=pinned): H2D of lrs + patches + coords, "
-                      "device-side fovea paste, forward, every frame D2H-copied on a side stream while the recurrence "
-                      "continues; device-timed (events around the K steps, copies included), host enqueue time reported beside it"}
-        del out_h
+    main_res = measure(torch, dist, model, args.workload, t, n, calls, args.steps, args.warmup, world, rank, dev,
+                       not args.no_e2e, sampler)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---------------- roofline of the align kernel (timed alone, cold inputs)
+    # ---------------- rooflines (kernels timed alone, cold inputs)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -391,23 +540,28 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
-    a_ms = time_align_kernel(torch, 2 * h, 2 * w, args.precision)
+    a_ms, a_raw = time_align_kernel(torch, 2 * h, 2 * w, args.precision)
     alg_bytes = ALIGN_BYTES_PER_L1_PX * (2 * h) * (2 * w)
     a_ach = alg_bytes / (a_ms * 1e-3) / 1e9
-    align = {"kernel": ("dcn_tc3_kernel" if args.precision == "tc" else "dcn_l1_kernel") + " (DCNv2 align @L1, C=32 dg=8)",
+    a_traffic, a_src, a_cnt = dram_traffic_from_profiles(args.workload, r"dcn_tc3_ws_kernel|dcn_l1_kernel")
+    align = {"kernel": ("dcn_tc3_ws_kernel" if args.precision != "fp32" else "dcn_l1_kernel") + " (DCNv2 align @L1, C=32 dg=8" +
+                       (", head activations fused into the sampler)" if a_raw else ")"),
              "bound": "hbm", "achieved": a_ach, "peak": peak, "unit": "GB/s", "frac": a_ach / peak,
-             "traffic": (247.1e6 if (args.workload == "R-lit" and args.precision == "tc") else None),
-             "traffic_source": "dram__bytes_read+write per launch, ncu, profiles/r01/v3_dram_R-lit.csv (R-lit only)",
+             "traffic": a_traffic,
+             "traffic_source": (f"dram__bytes_read+write per launch, mean of {a_cnt} launches, ncu, {a_src}" if a_traffic else
+                                "no committed ncu DRAM capture for this workload"),
              "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": a_ms,
              "timing": "kernel timed alone through the C ABI, CUDA events, 3 rotating input sets > L2"}
-    if args.precision == "tc":
+    if args.precision != "fp32":
         c_ms, c_n, c_bytes, c_flop = time_conv_mix(torch, 2 * h, 2 * w)
         c_ach = c_bytes / (c_ms * 1e-3) / 1e9
+        c_traffic, c_src, c_cnt = dram_traffic_from_profiles(args.workload, r"conv_tc3_ws_kernel", r"\((5|10), ")
         roofline = {"kernel": "conv_tc3_ws_kernel (tcgen05 3x3 implicit-GEMM conv, the per-frame mix of its %d L1 launches)" % c_n,
                     "bound": "hbm", "achieved": c_ach, "peak": peak, "unit": "GB/s", "frac": c_ach / peak,
-                    "traffic": (64.3e6 if args.workload == "R-lit" else None),
-                    "traffic_source": "dram__bytes_read+write, mean over the 23 L1 conv launches of one steady-state frame, "
-                                      "ncu, profiles/r01/v3_dram_R-lit.csv (R-lit only; below the algorithmic bytes: L2 reuse)",
+                    "traffic": c_traffic,
+                    "traffic_source": (f"dram__bytes_read+write, mean over the {c_cnt} L1 conv launches of the captured frames, ncu, "
+                                       f"{c_src} (below the algorithmic bytes: L2 reuse)" if c_traffic else
+                                       "no committed ncu DRAM capture for this workload"),
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": c_bytes, "avg_launch_ms": c_ms,
                     "tensor": {"useful_fp32_tflops": c_flop / (c_ms * 1e-3) / 1e12,
                                "issued_bf16_tflops": 3 * c_flop / (c_ms * 1e-3) / 1e12, "bf16_peak_tflops": bf16_peak,
@@ -419,30 +573,54 @@ def main():
         roofline = dict(align)
         roofline["peak_source"] = peak_src
 
-    cpu = None
-    if not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        fr = 2
-        fps, dt = cpu_reference_fps(h, w, fr, cores)
-        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-               "sample": f"{fr}-frame clip of {args.workload} (LR {h}x{w}), oracle port of the reference's PyTorch path, "
-                         f"torch CPU fp32, {dt:.1f} s"}
+    # ---------------- baselines measured in the same run (rank 0, N = 1 only)
+    cpu = stock = None
+    extra = []
+    if world == 1:
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            fr = 5
+            k, dt, wall = cpu_reference_steady(h, w, fr, cores)
+            cpu = {"value": k / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+                   "sample": f"one {fr}-frame clip of {args.workload} (LR {h}x{w}); rate = steady-state frames 2..{fr} "
+                             f"(BASELINE.md 3.5; clip-level work prorated), oracle port of the reference's PyTorch path, "
+                             f"torch CPU fp32, {wall:.1f} s"}
+        if not args.no_extras:
+            try:
+                stock = gpu_stock_baseline(torch, h, w)
+                stock["workload"] = args.workload
+            except Exception as e:  # noqa: BLE001  (a baseline leg must never take the bench line down)
+                stock = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+            for wl in WORKLOADS:
+                if wl == args.workload or args.total_clips:
+                    continue
+                model._graphs.clear()
+                model._ws.clear()
+                torch.cuda.empty_cache()
+                r = measure(torch, dist, model, wl, WORKLOADS[wl][2], 1, 1, max(2, min(args.steps, 5)), 3, 1, 0, dev,
+                            not args.no_e2e)
+                extra.append({"workload": workload_config(wl, *WORKLOADS[wl][:2], WORKLOADS[wl][2], 1)["workload"],
+                              "value": r["value"], "unit": "frames/s", "ms_per_step": r["ms_per_step"],
+                              "e2e": {k: r["e2e"][k] for k in ("value", "wall_value", "ms_per_step")} if "e2e" in r else None,
+                              "dtype": "f32" if args.precision != "half" else "f16"})
 
+    cfg = workload_config(args.workload, h, w, t, n * calls, args.total_clips)
+    prec = {"tc": "fp32 storage; dense contractions as 3 x bf16 split products on tcgen05 with fp32 TMEM accumulation "
+                  "(parity <= 1e-3 vs the fp32 reference)",
+            "fp32": "fp32 SIMT FFMA everywhere",
+            "half": "reduced-precision tier: fp32 storage, 16-bit tensor-core operands (see DESIGN.md)"}[args.precision]
     line = {
-        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: LR {h}x{w} -> {H}x{W_} (x8 network; BASELINE.json configs[1]), "
-                               f"{t}-frame clip, fovea 96x96, CRFP_DSV mid_channels=32",
-                   "precision": ("fp32 storage; dense contractions as 3 x bf16 split products on tcgen05 with fp32 TMEM "
-                                 "accumulation (parity <= 1e-3 vs the fp32 reference)") if args.precision == "tc"
-                   else "fp32 SIMT FFMA everywhere",
-                   "clips_per_gpu": n, "frames_per_clip": t, "parallelism": f"clip-sharded x{world}, no collective",
-                   "l2": "per-step working set (>= 4 GB of HR planes) exceeds the 126 MB L2",
-                   "launch": ("whole-clip CUDA graph replay (gpu_launches counts the kernels inside the graphs)"
-                              if model.use_graphs else "eager launches") +
-                             "; a 30 ms device spin ahead of the start event lets the host enqueue the timed region early"},
-        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "metric": METRIC, "value": main_res["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": scaling,
+        "vs_baseline": None, "dtype": "f32" if args.precision != "half" else "f16", "data": "synthetic",
+        "config": cfg,
+        "impl_config": {"precision": prec, "clips_per_call": n, "calls_per_step": calls,
+                        "parallelism": f"clip-sharded x{world}, no collective",
+                        "launch": ("whole-clip CUDA graph replay (gpu_launches counts the kernels inside the graphs)"
+                                   if model.use_graphs else "eager launches") +
+                                  "; a >= 200 ms device spin ahead of the start event lets the host enqueue the timed region early"},
+        "e2e": main_res.get("e2e"), "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"],
+        "roofline": roofline, "cpu_baseline": cpu, "gpu_stock_baseline": stock, "extra": extra,
     }
     print(json.dumps(line))
     if world > 1:

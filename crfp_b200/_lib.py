@@ -133,7 +133,8 @@ class DsvFrameDesc(C.Structure):
                 ("mks", C.c_void_p), ("mks_clip_stride", C.c_longlong),
                 ("fg", C.c_void_p), ("fg_clip_stride", C.c_longlong),
                 ("state_hr", C.c_void_p), ("state_l1", C.c_void_p),
-                ("out", C.c_void_p), ("out_clip_stride", C.c_longlong)]
+                ("out", C.c_void_p), ("out_clip_stride", C.c_longlong),
+                ("aux_stream", C.c_void_p), ("aux_events", C.c_void_p * 3)]
 
 
 # every symbol include/crfp_b200.h declares: name -> (restype, argtypes)

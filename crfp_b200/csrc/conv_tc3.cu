@@ -241,6 +241,19 @@ __device__ __forceinline__ void tc3_epilogue_chunk(const Tc3Params& P, float* v,
           float* op = reinterpret_cast<float*>(P.dst[seg]) + pix * P.dst_cstride[seg] + P.dst_coffset[seg] + cl;
           *reinterpret_cast<float4*>(op) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
+      } else if (P.shuffle_r == 2 && nvalid == 32 && !((P.dst_cstride[0] | P.dst_coffset[0]) & 3)) {
+        // PixelShufflePack x2 (upsample: 32 -> 96 @LR -> 24 channels @L1): conv channel o*4 + dy*2 + dx -> output channel o
+        // of sub-pixel (dy, dx); a 32-channel chunk is 8 consecutive output channels of each of the 4 sub-pixels = two
+        // 16-byte stores per sub-pixel instead of 32 scattered 4-byte stores
+        const int Wo = P.w * 2;
+        float* ob = reinterpret_cast<float*>(P.dst[0]) + P.dst_coffset[0] + (cbase >> 2);
+#pragma unroll
+        for (int sub = 0; sub < 4; ++sub) {
+          const size_t opix = ((size_t)n * (P.h * 2) + (y * 2 + (sub >> 1))) * (size_t)Wo + (x * 2 + (sub & 1));
+          float4* op = reinterpret_cast<float4*>(ob + opix * P.dst_cstride[0]);
+          op[0] = make_float4(v[sub], v[4 + sub], v[8 + sub], v[12 + sub]);
+          op[1] = make_float4(v[16 + sub], v[20 + sub], v[24 + sub], v[28 + sub]);
+        }
       } else {  // TC_OUT_SHUFFLE_F32
         const int r_ = P.shuffle_r, rr = r_ * r_;
         const int Wo = P.w * r_;

@@ -457,6 +457,21 @@ static size_t carve_frame(const crfp_dsv_shape* s, void* ws, FrameWs* f) {
 }
 
 
+// Optional fork / join of the off-chain work onto a second stream (crfp_dsv_frame_desc.aux_stream)
+struct Aux {
+  cudaStream_t main, aux;
+  cudaEvent_t ev[3];
+  bool on;
+  // everything enqueued on `to` after this call runs after everything enqueued on `from` before it
+  int order(cudaStream_t from, cudaStream_t to, int e) const {
+    if (!on) return CRFP_OK;
+    cudaError_t r = cudaEventRecord(ev[e], from);
+    if (r == cudaSuccess) r = cudaStreamWaitEvent(to, ev[e], 0);
+    if (r != cudaSuccess) { note_cuda_error(r); return CRFP_ERR_CUDA; }
+    return CRFP_OK;
+  }
+};
+
 // Offset / mask heads + DCNv2 of one L1 level (DCN_module.forward, model/CRFP.py:337-350): ONE 216-channel conv
 // into `om`, then the align kernel.  Tensor-core precision: the conv stores the RAW head outputs and the align kernel's
 // sampler applies 10*tanh + flow / sigmoid itself (crfp_dcn_desc.head_raw) — the conv epilogue drops to bias + store
@@ -764,6 +779,61 @@ extern "C" int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weigh
     CRFP_TRY(gather_images(n, (long long)hw * 32, d->x_lr, d->x_lr_clip_stride, f.x_lr_d, st));
     x_lr = f.x_lr_d;
   }
+  const float* flow_dense = d->flow;
+  if (!d->first && n > 1 && d->flow_clip_stride != (long long)(hw * 2)) {
+    CRFP_TRY(gather_images(n, (long long)hw * 2, d->flow, d->flow_clip_stride, f.flow_d, st));
+    flow_dense = f.flow_d;
+  }
+  const int tiles_x = (Wd + 31) / 32, tiles_y = (H + 31) / 32;
+  const uint8_t* flags = nullptr;
+
+  // ---- off-chain work: depends only on the inputs and on the previous frame's HR state.  With an aux stream it runs
+  // beside the L1 chain (forked here, joined before the HR stage); without one it is enqueued in place.
+  Aux ax;
+  ax.main = st; ax.aux = (cudaStream_t)d->aux_stream;
+  ax.on = d->aux_stream != nullptr && W->variant == CRFP_VARIANT_DSV && W->precision != CRFP_PREC_BF16;
+  for (int i = 0; i < 3; ++i) {
+    ax.ev[i] = (cudaEvent_t)d->aux_events[i];
+    if (ax.on && !ax.ev[i]) return CRFP_ERR_NULL;
+  }
+  auto hr_side_work = [&](cudaStream_t s2, bool with_warp) -> int {
+    if (with_warp && !d->first) {   // flow_lv0 = up8(flow)*8, warped HR state                              (CRFP.py:1566,1571)
+      CRFP_TRY(crfp_resize_bilinear(n, h, w, 2, flow_dense, H, Wd, 0.125f, 0.125f, 8.f, f.flow_hr, s2));
+      crfp_warp_desc wd;
+      memset(&wd, 0, sizeof(wd));
+      wd.n = n; wd.h = H; wd.w = Wd; wd.c = 4; wd.x = d->state_hr; wd.x_cstride = 4; wd.flow = f.flow_hr;
+      wd.out = f.S0_w; wd.out_cstride = 4;
+      CRFP_TRY(launch_flow_warp(wd, s2));
+    }
+    // fovea compositing + encoder_hr for this frame                                          (CRFP.py:1542-1547)
+    // Outside the mask the blend keeps S (0*F + 1*S): encoder_hr and conv_tttf are only CONSUMED within 3 pixels of a
+    // mask pixel, so tiles whose one-tile-dilated neighbourhood holds no mask pixel skip them (bit-identical output).
+    if (d->skip_outside_fovea) {
+      uint8_t* fl = reinterpret_cast<uint8_t*>(f.tile_flags);
+      uint8_t* any = fl + (((size_t)n * tiles_x * tiles_y + 255) & ~(size_t)255);
+      launch_k(fovea_tile_any_kernel, dim3(tiles_y, n), dim3(256), (size_t)tiles_x * sizeof(int), s2, H, Wd, d->mks, d->mks_clip_stride, tiles_x, tiles_y, any);
+      CRFP_TRY(check_launch());
+      launch_k(fovea_tile_dilate_kernel, dim3((n * tiles_x * tiles_y + 255) / 256), dim3(256), (size_t)0, s2, tiles_x, tiles_y, n, (const uint8_t*)any, fl);
+      CRFP_TRY(check_launch());
+      flags = fl;
+    }
+    CRFP_TRY(launch_compose(n, H, Wd, d, f.hr_in, flags, tiles_x, tiles_y, s2));
+    CB e0(n, H, Wd);
+    e0.src(f.hr_in, 6, 8).layer(W, L_ENC_HR_0).act(CRFP_ACT_LRELU).dst(f.e1, 4, 4);
+    e0.p.tile_flags = flags; e0.p.tiles_x = tiles_x; e0.p.tiles_y = tiles_y; e0.p.tile_mode = 1;
+    CRFP_TRY(e0.run(s2));
+    CB e2(n, H, Wd);
+    e2.src(f.e1, 4, 4).layer(W, L_ENC_HR_2).act(CRFP_ACT_LRELU).dst(f.x_hr, 4, 4);
+    e2.p.tile_flags = flags; e2.p.tiles_x = tiles_x; e2.p.tiles_y = tiles_y; e2.p.tile_mode = 1;
+    CRFP_TRY(e2.run(s2));
+    return CRFP_OK;
+  };
+  bool hr_side_done = false;
+  if (ax.on) {
+    CRFP_TRY(ax.order(ax.main, ax.aux, 0));
+    CRFP_TRY(hr_side_work(ax.aux, true));
+    hr_side_done = true;
+  }
 
   if (W->variant != CRFP_VARIANT_DSV) {
     if (W->variant != CRFP_VARIANT_V15 && W->variant != CRFP_VARIANT_V13) return CRFP_ERR_UNSUPPORTED;
@@ -780,14 +850,9 @@ extern "C" int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weigh
 
     const float* prop24 = nullptr;  // input of upsample_post
     if (!d->first) {
-      const float* flow = d->flow;
-      if (n > 1 && d->flow_clip_stride != (long long)(hw * 2)) {
-        CRFP_TRY(gather_images(n, (long long)hw * 2, d->flow, d->flow_clip_stride, f.flow_d, st));
-        flow = f.flow_d;
-      }
-      // flow_lv3 = up2(flow)*2, flow_lv0 = up8(flow)*8                                        (CRFP.py:1565-1566)
+      const float* flow = flow_dense;
+      // flow_lv3 = up2(flow)*2                                                                (CRFP.py:1565)
       CRFP_TRY(crfp_resize_bilinear(n, h, w, 2, flow, h1, w1, 0.5f, 0.5f, 2.f, f.flow_l1, st));
-      CRFP_TRY(crfp_resize_bilinear(n, h, w, 2, flow, H, Wd, 0.125f, 0.125f, 8.f, f.flow_hr, st));
       // P = downsample(S0): pixel_unshuffle(4) + conv 64 -> 32                                (CRFP.py:1569)
       CRFP_TRY(CB(n, h1, w1).src(d->state_hr, 64, 4, 0, CRFP_SRC_UNSHUFFLE4).layer(W, L_DOWNSAMPLE).dst(f.P, 32, 32).run(st));
       // warps                                                                                 (CRFP.py:1570-1577)
@@ -795,9 +860,6 @@ extern "C" int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weigh
       memset(&wd, 0, sizeof(wd));
       wd.n = n; wd.h = h1; wd.w = w1; wd.c = 32; wd.x = f.P; wd.x_cstride = 32; wd.flow = f.flow_l1;
       wd.out = f.P_w; wd.out_cstride = 32;
-      CRFP_TRY(launch_flow_warp(wd, st));
-      wd.h = H; wd.w = Wd; wd.c = 4; wd.x = d->state_hr; wd.x_cstride = 4; wd.flow = f.flow_hr;
-      wd.out = f.S0_w; wd.out_cstride = 4;
       CRFP_TRY(launch_flow_warp(wd, st));
       for (int k = 0; k < 3; ++k) {  // warped feat_lv{k} lands in channels 24..31 of level k's `cur`
         wd.h = h1; wd.w = w1; wd.c = 8; wd.x = d->state_l1; wd.x_cstride = 24; wd.x_coffset = 8 * k; wd.flow = f.flow_l1;
@@ -833,6 +895,10 @@ extern "C" int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weigh
                        .dst(z, 32, 32).run(st));
         }
         offfeat = z;
+        if (k == 2 && ax.on) {   // dcn_3.upsample only needs level 2's offset feature: beside the rest of the chain
+          CRFP_TRY(ax.order(ax.main, ax.aux, 1));
+          CRFP_TRY(CB(n, h1, w1).src(offfeat, 32, 32).layer(W, L_DCN3_UP).shuffle(4).scale(2.f).dst(f.po, 4, 4).run(ax.aux));
+        }
         CRFP_TRY(run_heads_dcn(W, n, h1, w1, z, f.flow_l1, f.om, f.P, f.A, lhd[k], ldc[k], st));
         // ResidualBlocksWithInputConv on cat(cur, A) (CRFP.py:1589-1596)
         CB in(n, h1, w1);
@@ -850,7 +916,8 @@ extern "C" int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weigh
       // L3                                                                                    (CRFP.py:1625-1630)
       CRFP_TRY(CB(n, h1, w1).src(prop24, 24, 24).layer(W, L_UPSAMPLE_POST).act(CRFP_ACT_LRELU).shuffle(4)
                    .dst(f.q, 4, 4).run(st));
-      CRFP_TRY(CB(n, h1, w1).src(offfeat, 32, 32).layer(W, L_DCN3_UP).shuffle(4).scale(2.f).dst(f.po, 4, 4).run(st));
+      if (!ax.on)
+        CRFP_TRY(CB(n, h1, w1).src(offfeat, 32, 32).layer(W, L_DCN3_UP).shuffle(4).scale(2.f).dst(f.po, 4, 4).run(st));
     } else {
       // first frame: no alignment; cat([prop, zeros32, zeros8]) == only weight[:, :24] contributes (CRFP.py:1634-1670)
       static const int lrf[3] = {L_RES0_IN_FIRST, L_RES1_IN_FIRST, L_RES2_IN_FIRST};
@@ -872,6 +939,11 @@ extern "C" int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weigh
   }
 
   // ---------------- HR stage (8h x 8w, 4 channels, fp32 in both precisions)
+  if (ax.on) CRFP_TRY(ax.order(ax.aux, ax.main, 2));   // join: S0_w, flow_hr, x_hr, flags, po are complete
+  if (!hr_side_done && W->variant == CRFP_VARIANT_DSV && W->precision != CRFP_PREC_BF16) {
+    CRFP_TRY(hr_side_work(st, true));
+    hr_side_done = true;
+  }
   if (!d->first) {
     CRFP_TRY(CB(n, H, Wd).src(f.q, 4, 4).src(f.S0_w, 4, 4).src(f.flow_hr, 2, 2).layer(W, L_DCN3_B0).act(CRFP_ACT_LRELU)
                  .dst(f.h1, 4, 4).run(st));
@@ -899,31 +971,8 @@ extern "C" int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weigh
   CRFP_TRY(CB(n, H, Wd).src(f.g0, 4, 4).layer(W, L_RES3_C1).act(CRFP_ACT_RELU).dst(f.g1, 4, 4).run(st));
   CRFP_TRY(CB(n, H, Wd).src(f.g1, 4, 4).layer(W, L_RES3_C2).res(f.g0, 4).dst(f.S_pre, 4, 4).run(st));
 
-  // fovea compositing + encoder_hr for this frame                                          (CRFP.py:1542-1547)
-  // Outside the mask the blend keeps S (0*F + 1*S): encoder_hr and conv_tttf are only CONSUMED within 3 pixels of a
-  // mask pixel, so tiles whose one-tile-dilated neighbourhood holds no mask pixel skip them (bit-identical output).
-  const int tiles_x = (Wd + 31) / 32, tiles_y = (H + 31) / 32;
-  const uint8_t* flags = nullptr;
-  if (d->skip_outside_fovea) {
-    uint8_t* fl = reinterpret_cast<uint8_t*>(f.tile_flags);
-    uint8_t* any = fl + (((size_t)n * tiles_x * tiles_y + 255) & ~(size_t)255);
-    launch_k(fovea_tile_any_kernel, dim3(tiles_y, n), dim3(256), (size_t)tiles_x * sizeof(int), st, H, Wd, d->mks, d->mks_clip_stride, tiles_x, tiles_y, any);
-    CRFP_TRY(check_launch());
-    launch_k(fovea_tile_dilate_kernel, dim3((n * tiles_x * tiles_y + 255) / 256), dim3(256), (size_t)0, st, tiles_x, tiles_y, n, (const uint8_t*)any, fl);
-    CRFP_TRY(check_launch());
-    flags = fl;
-  }
-  CRFP_TRY(launch_compose(n, H, Wd, d, f.hr_in, flags, tiles_x, tiles_y, st));
-  {
-    CB e0(n, H, Wd);
-    e0.src(f.hr_in, 6, 8).layer(W, L_ENC_HR_0).act(CRFP_ACT_LRELU).dst(f.e1, 4, 4);
-    e0.p.tile_flags = flags; e0.p.tiles_x = tiles_x; e0.p.tiles_y = tiles_y; e0.p.tile_mode = 1;
-    CRFP_TRY(e0.run(st));
-    CB e2(n, H, Wd);
-    e2.src(f.e1, 4, 4).layer(W, L_ENC_HR_2).act(CRFP_ACT_LRELU).dst(f.x_hr, 4, 4);
-    e2.p.tile_flags = flags; e2.p.tiles_x = tiles_x; e2.p.tiles_y = tiles_y; e2.p.tile_mode = 1;
-    CRFP_TRY(e2.run(st));
-  }
+  if (!hr_side_done)   // v15 / v13 / bf16 L1 paths resize the flow and warp the HR state themselves: only the fovea part is left
+    CRFP_TRY(hr_side_work(st, false));
   // conv_tttf + blend + LeakyReLU -> new state                                             (CRFP.py:1672-1675)
   {
     CB b(n, H, Wd);

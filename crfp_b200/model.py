@@ -95,6 +95,9 @@ class _CRFPBase(nn.Module):
         # alias_output = True (or an explicit `out=` buffer) returns the graph-owned tensor itself, overwritten by the
         # next replay on the same inputs — the cudagraph-style contract, for callers that consume each result at once.
         self.alias_output = False
+        # second stream for the off-chain work of a frame (crfp_dsv_frame_desc.aux_stream); CRFP_AUX=0 switches it off
+        self.use_aux_stream = os.environ.get("CRFP_AUX", "1") != "0"
+        self._aux = None
         self._graphs = collections.OrderedDict()   # key -> dict(graphs, out, launches)
         self._seen_key = None
 
@@ -229,6 +232,16 @@ class _CRFPBase(nn.Module):
         d.lr4_clip_stride, d.x_lr_clip_stride, d.flow_clip_stride = t * hw * 4, t * hw * self.mid_channels, t * hw * 2
         d.fvs_clip_stride, d.mks_clip_stride, d.out_clip_stride = t * 3 * HW, t * HW, t * 3 * HW
         d.state_hr, d.state_l1 = buf["state_hr"].data_ptr(), buf["state_l1"].data_ptr()
+        if self.use_aux_stream:
+            if self._aux is None or self._aux[0] != out.device:
+                evs = [torch.cuda.Event() for _ in range(3)]
+                aux = torch.cuda.Stream(device=out.device)
+                for e in evs:
+                    e.record(aux)          # events are created lazily: force the handles into existence
+                self._aux = (out.device, aux, evs)
+            d.aux_stream = self._aux[1].cuda_stream
+            for k, e in enumerate(self._aux[2]):
+                d.aux_events[k] = e.cuda_event
         ws = buf["ws"]
         for i in (range(t) if frames is None else frames):
             d.first = int(first_flags[i])

@@ -417,6 +417,12 @@ int crfp_dsv_prepare(const crfp_dsv_shape* s, const crfp_dsv_weights* wts, const
  *   state_hr     in/out NHWC (n, 8h, 8w, 4): feat_prop_lv3 (S)
  *   state_l1     in/out NHWC (n, 2h, 2w, 24): [feat_lv0 | feat_lv1 | feat_lv2]
  *   out          NCHW fp32 (3, 8h, 8w) per clip
+ *   aux_stream   optional second stream + 3 caller-created events (cudaEvent_t, timing disabled): the work of a frame
+ *                that does not sit on the L1 chain (x8 flow resize + warp of the HR state, fovea tile flags, compositing,
+ *                encoder_hr, dcn_3.upsample) is forked onto it and joined back before the HR stage, so these HBM-bound
+ *                kernels fill the launch gaps of the latency-bound tensor-core chain.  The fork starts after everything
+ *                enqueued on `stream` before the call and everything is joined back into `stream` before the call
+ *                returns (also valid under stream capture).  NULL: single-stream execution.  Results are bit-identical.
  */
 typedef struct {
   crfp_dsv_shape shape;   /* t ignored */
@@ -432,6 +438,8 @@ typedef struct {
   float* state_hr;
   float* state_l1;
   float* out;         long long out_clip_stride;
+  crfp_stream aux_stream;
+  void* aux_events[3];
 } crfp_dsv_frame_desc;
 size_t crfp_dsv_frame_workspace(const crfp_dsv_shape* s);
 int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weights* wts, void* workspace, size_t ws_bytes,

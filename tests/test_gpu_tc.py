@@ -215,6 +215,12 @@ def test_conv_tc3_epilogues():
     ref4 = F.leaky_relu(F.pixel_shuffle(F.conv2d(x24, w64, b64, padding=1), 4), 0.1) * 2.0
     got4 = nchw(ops.conv3x3_tc3_nhwc([f32(x24)], w64.cuda(), b64.cuda(), act=1, shuffle_r=4, post_scale=2.0))
     assert (got4 - ref4).abs().max().item() < 2e-4
+    # pixel shuffle x2 (upsample: 32 -> 96 -> 24 channels): the vectorised sub-pixel store
+    w96 = torch.randn(96, 32, 3, 3, generator=g) * 0.08
+    b96 = torch.randn(96, generator=g) * 0.1
+    ref2 = F.pixel_shuffle(F.conv2d(x, w96, b96, padding=1), 2)
+    got2 = nchw(ops.conv3x3_tc3_nhwc([f32(x)], w96.cuda(), b96.cuda(), shuffle_r=2))
+    assert got2.shape == ref2.shape and (got2 - ref2).abs().max().item() < 2e-4
 
 
 def test_conv_tc3_unshuffle_source():
