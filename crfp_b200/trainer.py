@@ -43,6 +43,7 @@ class Trainer:
         # all-reduce and the two Adam launches stay outside the graph (their scalars change every iteration).
         self.use_graphs = use_graphs
         self._graphs, self._seen = {}, {}
+        self.time_comm, self.comm_events = False, []                 # optional CUDA-event timing of the gradient all-reduce
         self.K = kernels or A.CUDA
         self.betas, self.eps, self.rec_w = (beta1, beta2), eps, rec_w
         self.period, self.min_lr, self.freeze_flow_iters = period, min_lr, freeze_flow_iters
@@ -125,8 +126,14 @@ class Trainer:
         loss = self._fwd_bwd_graphed(lrs, fvs, mks, hr, train_flow) if self.use_graphs else self._fwd_bwd(lrs, fvs, mks, hr)
         ws = self._world()
         if ws > 1:                                                   # ONE all-reduce of the 9.14 MB bucket
+            if self.time_comm:                                       # device time of the exchange (bench_train.py)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             torch.distributed.all_reduce(self.flat_g, group=self.pg)
             self.flat_g.mul_(1.0 / ws)
+            if self.time_comm:
+                e1.record()
+                self.comm_events.append((e0, e1))
         self._adam(train_flow)
         self.cur_iter += 1
         model._packed = None                                         # inference-side packed weights are stale now

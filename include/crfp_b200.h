@@ -320,6 +320,22 @@ int crfp_avgpool2(int n, int hin, int win, int c, const float* in, float* out, c
  */
 int crfp_fovea_paste(const float* patch, const int32_t* coords, int frames, int fv, int H, int W, float* fvs,
                      uint8_t* mks, int clear, crfp_stream stream);
+/*
+ * The per-pixel half of the data loader's `fovea_generator` (dataset/reds.py:190-226) for a whole clip: gt / fvs planar
+ * [frames][c][H][W] fp32, rects int32 [frames][4] = (y0, x0, y1, x1) half-open and already clipped to the frame (16-byte
+ * aligned), mks [frames][H][W] bytes: mks = 1 inside the rectangle, fvs = gt * mask.
+ */
+int crfp_fovea_from_gt(const float* gt, const int32_t* rects, int frames, int c, int H, int W, float* fvs, uint8_t* mks,
+                       crfp_stream stream);
+/*
+ * `calc_psnr_and_ssim_cuda` (utils.py:165-254) fused into one pass: planar img1 / img2 [B][C][H][W] in [0,1], optional
+ * mask [B][H][W] (fp32 or bytes; both NULL = all ones), window11 = the 11 normalised Gaussian taps (HOST pointer).
+ * Writes per-CTA partial sums partial[B*C][tiles_y*tiles_x][3] = (sum ssim*m, sum (img1-img2)^2*m, sum m) with
+ * (tiles_x, tiles_y) = crfp_psnr_ssim_tiles(H, W); the caller adds them up (float64) — deterministic, no atomics.
+ */
+int crfp_psnr_ssim_tiles(int H, int W, int32_t* tiles_x, int32_t* tiles_y);
+int crfp_psnr_ssim(int B, int C, int H, int W, const float* img1, const float* img2, const float* mask_f32,
+                   const uint8_t* mask_u8, const float* window11, float* partial, crfp_stream stream);
 /* NCHW (with an explicit image stride in floats) -> NHWC with cpad >= c channels (extra channels zero) */
 int crfp_nchw_to_nhwc(int n, int c, int h, int w, const float* in, long long in_image_stride, int cpad, float* out,
                       crfp_stream stream);

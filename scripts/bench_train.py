@@ -53,11 +53,13 @@ def main():
     if world > 1:
         torch.distributed.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tr.time_comm, tr.comm_events = world > 1, []
     e0.record()
     for _ in range(args.steps):
         loss = tr.step(*batch)
     e1.record()
     torch.cuda.synchronize()
+    comm_ms = [a.elapsed_time(b) for a, b in tr.comm_events]
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     if world > 1:
         torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
@@ -73,6 +75,9 @@ def main():
             # count of a step, 4 190 incl. copies at V7, comes from scripts/train_kernel_times.py instead)
             "config": {"workload": f"{args.shape}: n={n} clips/GPU, t={t}, LR {h}x{w} -> {8 * h}x{8 * w}, FV {fv}",
                        "params": int(tr.flat_p.numel()), "grad_bucket_bytes": int(tr.flat_g.numel() * 4)},
+            "allreduce": ({"ms_per_step_mean": sum(comm_ms) / len(comm_ms), "ms_per_step_max": max(comm_ms), "backend": "nccl",
+                           "what": "ONE all_reduce of the flat fp32 gradient bucket + the 1/world scale, CUDA events on rank 0 "
+                                   "(includes waiting for the slowest rank's backward)"} if comm_ms else None),
             "loss_first_last": [losses[0], losses[-1]],
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
     if world > 1:

@@ -52,24 +52,53 @@ def test_tile_plan_partitions_frame():
 
 
 def _tile_worker(rank, world, port):
-    """The per-frame exchange step of the tiled runner: after it every rank holds every tile's interior state."""
-    from crfp_b200.tiling import TiledClipRunner, tile_plan
+    """The per-frame exchange step of the tiled runner: neighbour strips only.  Every rank starts with the truth inside
+    the INTERIORS of its own tiles and stale halos; after the exchange every extended tile equals the truth crop."""
+    from crfp_b200.tiling import exchange_halos, halo_pairs, tile_plan
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         h, w = 12, 20
         plan = tile_plan(h, w, 2, 3, 4)
+        pairs = halo_pairs(plan)
         truth_hr = torch.arange(8 * h * 8 * w * 4, dtype=torch.float32).view(1, 8 * h, 8 * w, 4)
         truth_l1 = torch.arange(2 * h * 2 * w * 24, dtype=torch.float32).view(1, 2 * h, 2 * w, 24) * 0.5
-        hr, l1 = torch.full_like(truth_hr, -1.0), torch.full_like(truth_l1, -1.0)     # stale everywhere ...
-        for k, ((y0, y1, x0, x1), _) in enumerate(plan):
-            if k % world == rank:                                                      # ... except my own interiors
-                hr[:, 8 * y0:8 * y1, 8 * x0:8 * x1] = truth_hr[:, 8 * y0:8 * y1, 8 * x0:8 * x1]
-                l1[:, 2 * y0:2 * y1, 2 * x0:2 * x1] = truth_l1[:, 2 * y0:2 * y1, 2 * x0:2 * x1]
-        TiledClipRunner(None, grid=(2, 3), halo=4)._allgather_interiors(hr, l1, plan, world, rank)
-        assert torch.equal(hr, truth_hr) and torch.equal(l1, truth_l1)
+        states = {}
+        for k, ((y0, y1, x0, x1), (ey0, ey1, ex0, ex1)) in enumerate(plan):
+            if k % world != rank:
+                continue
+            hr = torch.full((1, 8 * (ey1 - ey0), 8 * (ex1 - ex0), 4), -1.0)             # stale everywhere ...
+            l1 = torch.full((1, 2 * (ey1 - ey0), 2 * (ex1 - ex0), 24), -1.0)
+            hr[:, 8 * (y0 - ey0):8 * (y1 - ey0), 8 * (x0 - ex0):8 * (x1 - ex0)] = truth_hr[:, 8 * y0:8 * y1, 8 * x0:8 * x1]
+            l1[:, 2 * (y0 - ey0):2 * (y1 - ey0), 2 * (x0 - ex0):2 * (x1 - ex0)] = truth_l1[:, 2 * y0:2 * y1, 2 * x0:2 * x1]
+            states[k] = (hr, l1)                                                           # ... except my own interiors
+        got = exchange_halos(states, plan, pairs, world, rank)
+        for k, (hr, l1) in states.items():
+            (_, (ey0, ey1, ex0, ex1)) = plan[k]
+            assert torch.equal(hr, truth_hr[:, 8 * ey0:8 * ey1, 8 * ex0:8 * ex1]), k
+            assert torch.equal(l1, truth_l1[:, 2 * ey0:2 * ey1, 2 * ex0:2 * ex1]), k
+        # only neighbour strips crossed the wire: far less than the all-gather of every interior
+        everything = (truth_hr.numel() + truth_l1.numel()) * 4
+        assert 0 < got < everything
     finally:
         dist.destroy_process_group()
+
+
+def test_halo_pairs_cover_exactly_the_halos():
+    from crfp_b200.tiling import halo_pairs, tile_plan
+    for h, w, gy, gx, halo in [(24, 40, 2, 4, 5), (30, 30, 3, 3, 8), (16, 48, 1, 3, 4)]:
+        plan = tile_plan(h, w, gy, gx, halo)
+        pairs = halo_pairs(plan)
+        for j, ((y0, y1, x0, x1), (ey0, ey1, ex0, ex1)) in enumerate(plan):
+            cover = torch.zeros(h, w, dtype=torch.int32)
+            cover[y0:y1, x0:x1] += 1
+            for (k, jj, (a0, a1, b0, b1)) in pairs:
+                if jj == j:
+                    assert k != j
+                    cover[a0:a1, b0:b1] += 1
+            assert torch.all(cover[ey0:ey1, ex0:ex1] == 1)          # halo fully covered, exactly once
+            cover[ey0:ey1, ex0:ex1] = 0
+            assert torch.all(cover == 0)                            # and nothing outside the extended tile
 
 
 def test_tile_state_exchange_world2_gloo():
