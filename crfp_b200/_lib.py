@@ -175,6 +175,7 @@ SYMBOLS = {
                                    C.c_void_p]),
     "crfp_fovea_from_gt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p]),
+    "crfp_quantize_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "crfp_psnr_ssim_tiles": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "crfp_psnr_ssim": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),

@@ -32,6 +32,25 @@ __global__ void __launch_bounds__(256) fovea_from_gt_kernel(int frames, int c, i
   }
 }
 
+// frames as the reference SAVES them (trainer.py:446-474, 535-537): (sr * 255).clip(0, 255).round() -> uint8; 16 pixels per
+// thread (4 x LDG.128 -> one STG.128), round-half-to-even like torch.round
+__global__ void __launch_bounds__(256) quantize_u8_kernel(long long count16, long long count, const float* __restrict__ in,
+                                                          uint8_t* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  auto q = [](float v) -> uint32_t { return (uint32_t)__float2int_rn(fminf(fmaxf(v * 255.f, 0.f), 255.f)); };
+  if (i < count16) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i * 4 + k);
+      w[k] = q(v.x) | (q(v.y) << 8) | (q(v.z) << 16) | (q(v.w) << 24);
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  } else if (i == count16) {
+    for (long long j = count16 * 16; j < count; ++j) out[j] = (uint8_t)q(in[j]);   // tail (< 16 elements)
+  }
+}
+
 constexpr int ST = 32;          // output tile
 constexpr int SR = 5;           // window radius (11 taps)
 constexpr int SW = ST + 2 * SR; // 42
@@ -120,6 +139,15 @@ extern "C" int crfp_fovea_from_gt(const float* gt, const int32_t* rects, int fra
   if ((uintptr_t)rects & 15) return CRFP_ERR_BAD_SHAPE;
   const long long total = (long long)frames * H * W;
   fovea_from_gt_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(frames, c, H, W, gt, rects, fvs, mks);
+  return check_launch();
+}
+
+extern "C" int crfp_quantize_u8(const float* in, uint8_t* out, long long count, crfp_stream stream) {
+  if (!in || !out) return CRFP_ERR_NULL;
+  if (count < 0 || ((uintptr_t)in & 15) || ((uintptr_t)out & 15)) return CRFP_ERR_BAD_SHAPE;
+  if (count == 0) return CRFP_OK;
+  const long long c16 = count / 16;
+  quantize_u8_kernel<<<(unsigned)((c16 + 1 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c16, count, in, out);
   return check_launch();
 }
 

@@ -217,9 +217,18 @@ class _CRFPBase(nn.Module):
         side stream while the next frames are computed (device->host traffic overlaps the recurrence)."""
         lib = L.lib()
         copy_stream = None
+        u8 = None
         if out_host is not None:
-            if tuple(out_host.shape) != tuple(out.shape) or out_host.dtype != out.dtype or not out_host.is_pinned():
-                raise ValueError("out_host must be a pinned CPU tensor with the output's shape and dtype")
+            if tuple(out_host.shape) != tuple(out.shape) or out_host.dtype not in (out.dtype, torch.uint8) or not out_host.is_pinned():
+                raise ValueError("out_host must be a pinned CPU tensor with the output's shape, fp32 or uint8")
+            if out_host.dtype == torch.uint8:
+                # frames quantised on the device exactly as the reference saves them ((sr * 255).clip(0, 255).round(),
+                # trainer.py:446-474): 4x fewer bytes over PCIe; two staging frames so the copy of frame i overlaps the
+                # quantisation of frame i + 1
+                if getattr(self, "_u8", None) is None or self._u8[0].shape != out[:, 0].shape or self._u8[0].device != out.device:
+                    self._u8 = [torch.empty(out[:, 0].shape, device=out.device, dtype=torch.uint8) for _ in range(2)]
+                self._u8_ev = [None, None]   # per call: the previous call ended with wait_stream(copy_stream)
+                u8 = self._u8
             if getattr(self, "_copy_stream", None) is None or self._copy_stream.device != out.device:
                 self._copy_stream = torch.cuda.Stream(device=out.device)
             copy_stream = self._copy_stream
@@ -255,11 +264,25 @@ class _CRFPBase(nn.Module):
             d.out = out.data_ptr() + i * 3 * HW * 4
             L.check(lib.crfp_dsv_frame(C.byref(d), C.byref(W), ws.data_ptr(), ws.numel(), st), f"dsv_frame[{i}]")
             if copy_stream is not None:
+                src = out[:, i]
+                if u8 is not None:
+                    k = i & 1
+                    if self._u8_ev[k] is not None:               # the copy that last read this staging frame is done
+                        torch.cuda.current_stream().wait_event(self._u8_ev[k])
+                    if n == 1:
+                        L.check(lib.crfp_quantize_u8(src.data_ptr(), u8[k].data_ptr(), src.numel(), st), "quantize_u8")
+                    else:                                        # strided over clips: one launch per clip
+                        for b in range(n):
+                            L.check(lib.crfp_quantize_u8(out[b, i].data_ptr(), u8[k][b].data_ptr(), out[b, i].numel(), st), "quantize_u8")
+                    src = u8[k]
                 ev = torch.cuda.Event()
                 ev.record()
                 copy_stream.wait_event(ev)
                 with torch.cuda.stream(copy_stream):
-                    out_host[:, i].copy_(out[:, i], non_blocking=True)
+                    out_host[:, i].copy_(src, non_blocking=True)
+                    if u8 is not None:
+                        self._u8_ev[i & 1] = torch.cuda.Event()
+                        self._u8_ev[i & 1].record(copy_stream)
         if copy_stream is not None:
             torch.cuda.current_stream().wait_stream(copy_stream)
 

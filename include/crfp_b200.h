@@ -334,6 +334,9 @@ int crfp_fovea_from_gt(const float* gt, const int32_t* rects, int frames, int c,
  * (tiles_x, tiles_y) = crfp_psnr_ssim_tiles(H, W); the caller adds them up (float64) — deterministic, no atomics.
  */
 int crfp_psnr_ssim_tiles(int H, int W, int32_t* tiles_x, int32_t* tiles_y);
+/* frames as the reference SAVES them (trainer.py:446-474, 535-537): out[i] = uint8(round(clip(in[i] * 255, 0, 255))),
+ * round-half-to-even; in / out 16-byte aligned.  Used to stream uint8 frames to the host (4x fewer PCIe bytes). */
+int crfp_quantize_u8(const float* in, uint8_t* out, long long count, crfp_stream stream);
 int crfp_psnr_ssim(int B, int C, int H, int W, const float* img1, const float* img2, const float* mask_f32,
                    const uint8_t* mask_u8, const float* window11, float* partial, crfp_stream stream);
 /* NCHW (with an explicit image stride in floats) -> NHWC with cpad >= c channels (extra channels zero) */

@@ -28,3 +28,12 @@ d=json.loads(open('$O/multi${NG}_bench_64clips.json').read().strip().splitlines(
 print('64 clips x 20 frames strong-sharded:', round(d['value'],1), 'fps', d['scaling'], d['config'])
 "
 fi
+if [ -n "$WC" ]; then
+CRFP_PIN_WC=1 timeout 900 $T 29617 bench.py --gpus $NG --steps 5 --warmup 3 > $O/multi${NG}_bench_wc.json 2> $O/multi${NG}_bench_wc.err
+echo "bench WC rc $?"; python -c "
+import json
+d=json.loads(open('$O/multi${NG}_bench_wc.json').read().strip().splitlines()[-1])
+print('WC: value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'wall', round(d['e2e']['wall_value'],1), d['e2e']['pinned'])
+"; tail -2 $O/multi${NG}_bench_wc.err
+fi
+timeout 120 python scripts/d2h_bw.py > $O/multi${NG}_d2h_single.txt 2>&1; cat $O/multi${NG}_d2h_single.txt

@@ -92,6 +92,22 @@ def test_out_host_streaming_copy(model):
     assert torch.equal(host, ref) and torch.equal(out.cpu(), ref)
 
 
+def test_out_host_uint8_frames(model):
+    """out_host may be a pinned uint8 tensor: frames quantised on the device as the reference saves them
+    ((sr * 255).clip(0, 255).round(), trainer.py:446-474) — eager and graph replay, n = 1 and n = 2."""
+    for n in (1, 2):
+        lrs, fvs, mks, _ = make_clip(seed=18, n=n, t=5, h=16, w=24, fv_size=48)
+        ref = _run(model, lrs, fvs, mks)
+        want = (ref * 255.0).clip(0.0, 255.0).round().to(torch.uint8)
+        host = torch.zeros(ref.shape, dtype=torch.uint8).pin_memory()
+        a, b, c = lrs.cuda(), fvs.cuda(), mks.cuda()
+        for _ in range(3):                       # eager, capture, replay
+            host.zero_()
+            out = model(a, b, c, out_host=host)
+            torch.cuda.synchronize()
+            assert torch.equal(host, want) and torch.equal(out.cpu(), ref)
+
+
 def test_clip_batch_equals_single_clips(model):
     """Clips are independent (the multi-GPU sharding unit): a batch of 3 equals three batch-1 runs bit for bit."""
     lrs, fvs, mks, _ = make_clip(seed=13, n=3, t=3, h=16, w=24, fv_size=48)
