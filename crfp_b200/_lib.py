@@ -92,6 +92,18 @@ class DcnDesc(C.Structure):
                 ("dbg_y0", C.c_void_p), ("dbg_x0", C.c_void_p)]
 
 
+class AlignFusedDesc(C.Structure):
+    _fields_ = [("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("_pad", C.c_int32),
+                ("z", C.c_void_p), ("z_cstride", C.c_int32), ("z_coffset", C.c_int32),
+                ("flow", C.c_void_p),
+                ("x", C.c_void_p), ("x_cstride", C.c_int32), ("x_coffset", C.c_int32),
+                ("heads_w", C.c_void_p), ("heads_b", C.c_void_p),
+                ("dcn_w_hi", C.c_void_p), ("dcn_w_lo", C.c_void_p), ("dcn_b", C.c_void_p),
+                ("out", C.c_void_p), ("out_cstride", C.c_int32), ("out_coffset", C.c_int32),
+                ("head_mag", C.c_float), ("_pad2", C.c_int32),
+                ("dbg_y0", C.c_void_p), ("dbg_x0", C.c_void_p)]
+
+
 class DcnBwdDesc(C.Structure):
     _fields_ = [("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
                 ("c", C.c_int32), ("cout", C.c_int32), ("dg", C.c_int32),
@@ -105,7 +117,8 @@ class Layer(C.Structure):
 
 
 class LayerTc(C.Structure):
-    _fields_ = [("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("b", C.c_void_p), ("w_extra", C.c_void_p)]
+    _fields_ = [("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("b", C.c_void_p), ("w_extra", C.c_void_p),
+                ("w_fused", C.c_void_p), ("b_fused", C.c_void_p)]
 
 
 class DsvWeights(C.Structure):
@@ -147,6 +160,7 @@ SYMBOLS = {
     "crfp_launch_count_add": (None, [C.c_longlong]),
     "crfp_check_device": (C.c_int, []),
     "crfp_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crfp_selftest_umma_sbo": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "crfp_selftest_umma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "crfp_conv3x3_fwd": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "crfp_conv3x3_tc_fwd": (C.c_int, [C.POINTER(ConvTcDesc), C.c_void_p]),
@@ -166,6 +180,8 @@ SYMBOLS = {
     "crfp_dcn_v2_fwd": (C.c_int, [C.POINTER(DcnDesc), C.c_void_p]),
     "crfp_dcn_v2_tc_fwd": (C.c_int, [C.POINTER(DcnDesc), C.c_void_p]),
     "crfp_dcn_v2_tc3_fwd": (C.c_int, [C.POINTER(DcnDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crfp_dcn_align_fused": (C.c_int, [C.POINTER(AlignFusedDesc), C.c_void_p]),
+    "crfp_sizeof_align_fused_desc": (C.c_size_t, []),
     "crfp_dcn_v2_indices": (C.c_int, [C.POINTER(DcnDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "crfp_sizeof_dcn_desc": (C.c_size_t, []),
     "crfp_resize_bilinear": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float,

@@ -479,7 +479,22 @@ struct Aux {
 static int run_heads_dcn(const crfp_dsv_weights* W, int n, int h1, int w1, const float* z, const float* flow_l1, float* om,
                          const float* P, float* A, int l_heads, int l_dcn, cudaStream_t st) {
   static const bool head_epi = (getenv("CRFP_HEAD_EPI") != nullptr);
+  static const bool no_fused = (getenv("CRFP_ALIGN_UNFUSED") != nullptr);   // A/B switch: heads conv + align kernel
   const bool tc = W->precision == CRFP_PREC_TC3 && W->layer_tc[l_dcn].w_hi && W->layer_tc[l_dcn].w_lo;
+  if (tc && !no_fused && !head_epi && W->layer_tc[l_heads].w_fused && W->layer_tc[l_heads].b_fused) {
+    // ONE kernel: the offset / mask tensor stays in TMEM (dcn_fused.cu)
+    crfp_align_fused_desc fd;
+    memset(&fd, 0, sizeof(fd));
+    fd.n = n; fd.h = h1; fd.w = w1;
+    fd.z = z; fd.z_cstride = 32;
+    fd.flow = flow_l1;
+    fd.x = P; fd.x_cstride = 32;
+    fd.heads_w = W->layer_tc[l_heads].w_fused; fd.heads_b = W->layer_tc[l_heads].b_fused;
+    fd.dcn_w_hi = W->layer_tc[l_dcn].w_hi; fd.dcn_w_lo = W->layer_tc[l_dcn].w_lo; fd.dcn_b = W->layer_tc[l_dcn].b;
+    fd.out = A; fd.out_cstride = 32;
+    fd.head_mag = 10.f;
+    return launch_align_fused(fd, st);
+  }
   const bool raw = tc && !head_epi;
   if (raw)
     CRFP_TRY(CB(n, h1, w1).src(z, 32, 32).layer(W, l_heads).dst(om, 216, 216).run(st));

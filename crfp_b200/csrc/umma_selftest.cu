@@ -8,7 +8,7 @@ namespace crfp {
 
 __global__ void __launch_bounds__(128) umma_selftest_kernel(const __nv_bfloat16* __restrict__ A,
                                                             const __nv_bfloat16* __restrict__ B, float* __restrict__ D,
-                                                            int rowsA, int K, int N, int shift) {
+                                                            int rowsA, int K, int N, int shift, int sbo_recs) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base;
@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const __nv_bfloat16*
     const uint32_t idesc = umma::make_idesc_bf16(128, N);
     const uint32_t lboA = (uint32_t)rowsA * 16, lboB = (uint32_t)N * 16;
     for (int ks = 0; ks < K / 16; ++ks) {
-      const uint64_t da = umma::make_desc(umma::smem_u32(sA) + (uint32_t)(2 * ks) * lboA + (uint32_t)shift * 16, lboA, 128);
+      const uint64_t da = umma::make_desc(umma::smem_u32(sA) + (uint32_t)(2 * ks) * lboA + (uint32_t)shift * 16, lboA,
+                                          (uint32_t)sbo_recs * 16);
       const uint64_t db = umma::make_desc(umma::smem_u32(sB) + (uint32_t)(2 * ks) * lboB, lboB, 128);
       umma::mma_bf16(taddr, da, db, idesc, ks > 0 ? 1u : 0u);
     }
@@ -70,7 +71,24 @@ extern "C" int crfp_selftest_umma(int rowsA, int K, int N, int shift, const void
   cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
   umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, D, rowsA,
-                                                              K, N, shift);
+                                                              K, N, shift, 8);
+  return check_launch();
+}
+
+// Same with an explicit stride between the 8-row groups of the A operand (SBO, in 16-byte records): row m of the MMA reads
+// record shift + (m / 8) * sbo_recs + m % 8.  sbo_recs = 10 is how the fused align kernel addresses an 8-pixel-wide tile
+// inside a 10-pixel-wide halo tile (one descriptor start address per 3x3 tap).
+extern "C" int crfp_selftest_umma_sbo(int rowsA, int K, int N, int shift, int sbo_recs, const void* A, const void* B, float* D,
+                                      crfp_stream stream) {
+  using namespace crfp;
+  if (!A || !B || !D) return CRFP_ERR_NULL;
+  if (K % 16 || N % 16 || N < 16 || N > 256 || shift < 0 || sbo_recs < 8 || rowsA < shift + 15 * sbo_recs + 8) return CRFP_ERR_BAD_SHAPE;
+  const size_t smem = (size_t)(K / 8) * (rowsA + N) * 16;
+  if (smem > 200 * 1024) return CRFP_ERR_UNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
+  umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, D, rowsA,
+                                                              K, N, shift, sbo_recs);
   return check_launch();
 }
 

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
-from .packing import pack_layer, pack_layer_tc3
+from .packing import pack_align_heads, pack_layer, pack_layer_tc3
 from .spec import crfp_param_shapes
 from .synthetic import fovea_rect
 
@@ -152,6 +152,11 @@ class _CRFPBase(nn.Module):
                 W.layer_tc[i].w_hi, W.layer_tc[i].w_lo, W.layer_tc[i].b = hi.data_ptr(), lo.data_ptr(), bt.data_ptr()
                 if wx is not None:
                     W.layer_tc[i].w_extra = wx.data_ptr()
+                if info["kind"] == 2 and info["cout"] == 216:     # L1 offset / mask heads: the fused align kernel's packing
+                    wf, bf = pack_align_heads(sd[info["key"] + ".weight"], sd[info["key"] + ".bias"],
+                                              sd[info["key2"] + ".weight"], sd[info["key2"] + ".bias"])
+                    keep.append((wf, bf))
+                    W.layer_tc[i].w_fused, W.layer_tc[i].b_fused = wf.data_ptr(), bf.data_ptr()
         self._packed = (key, keep, W)
         self._graphs.clear()      # captured graphs point at the previous packed weights
         for sb in getattr(self, "_sbuf", {}).values():

@@ -279,3 +279,25 @@ def conv3x3_tc3_nhwc(srcs, weight, bias, act=L.ACT_NONE, residual=None, shuffle_
         d.dst[i] = L.TcSrc(ptr=o.data_ptr(), c=o.shape[-1], cstride=o.shape[-1], coffset=0)
     L.check(L.lib().crfp_conv3x3_tc3_fwd(C.byref(d), _stream()), "conv3x3_tc3")
     return outs[0] if len(outs) == 1 else tuple(outs)
+
+
+def dcn_align_fused_nhwc(z, flow, x, w_off, b_off, w_msk, b_msk, w_dcn, b_dcn, head_mag=10.0, indices=False):
+    """The tail of DCN_module.forward (CRFP.py:337-350) as ONE kernel (`crfp_dcn_align_fused`): z, x (n,h,w,32), flow
+    (n,h,w,2) fp32 NHWC; dcn_offset / dcn_mask / dcn weights in the reference's OIHW layout.  Returns the aligned tensor
+    (n,h,w,32) — and, with indices=True, the int32 (n,h,w,72) floor(py), floor(px) the kernel sampled at."""
+    from .packing import pack_align_heads, pack_dcn_tc3
+    z, flow, x = _req(z, "z"), _req(flow, "flow"), _req(x, "x")
+    n, h, w, _ = z.shape
+    wf, bf = pack_align_heads(w_off, b_off, w_msk, b_msk)
+    hi, lo, bp = pack_dcn_tc3(w_dcn, b_dcn, 8)
+    out = torch.empty(n, h, w, 32, device=z.device, dtype=torch.float32)
+    d = L.AlignFusedDesc(n=n, h=h, w=w, z=z.data_ptr(), z_cstride=32, z_coffset=0, flow=flow.data_ptr(), x=x.data_ptr(),
+                         x_cstride=32, x_coffset=0, heads_w=wf.data_ptr(), heads_b=bf.data_ptr(), dcn_w_hi=hi.data_ptr(),
+                         dcn_w_lo=lo.data_ptr(), dcn_b=bp.data_ptr(), out=out.data_ptr(), out_cstride=32, out_coffset=0,
+                         head_mag=head_mag)
+    if indices:
+        y0 = torch.full((n, h, w, 72), -12345, device=z.device, dtype=torch.int32)
+        x0 = torch.full_like(y0, -12345)
+        d.dbg_y0, d.dbg_x0 = y0.data_ptr(), x0.data_ptr()
+    L.check(L.lib().crfp_dcn_align_fused(C.byref(d), _stream()), "dcn_align_fused")
+    return (out, y0, x0) if indices else out

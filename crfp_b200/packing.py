@@ -193,6 +193,26 @@ def pack_dcn_tc3(weight: torch.Tensor, bias: torch.Tensor, dg: int):
     return hi.contiguous(), lo.contiguous(), b
 
 
+def pack_align_heads(w_off: torch.Tensor, b_off: torch.Tensor, w_msk: torch.Tensor, b_msk: torch.Tensor):
+    """dcn_offset (144,32,3,3) + dcn_mask (72,32,3,3) -> the B operand of crfp_dcn_align_fused's heads GEMM:
+    bf16 [6 sixths][hi | lo][6 chunks][224][8] and fp32 bias [224].
+    Column n = 3*s + {0: dy, 1: dx, 2: mask} for sample s = g*9 + t (offset channels 2s, 2s+1; mask channel s), 216..223
+    zero.  K = tap*32 + c (tap-major), chunk kc = K // 8 = tap*4 + c // 8; a sixth is 6 consecutive chunks."""
+    assert tuple(w_off.shape) == (144, 32, 3, 3) and tuple(w_msk.shape) == (72, 32, 3, 3)
+    dev = w_off.device
+    w = torch.zeros(224, 32, 9, device=dev, dtype=torch.float32)
+    b = torch.zeros(224, device=dev, dtype=torch.float32)
+    wo, wm = w_off.detach().to(torch.float32).reshape(144, 32, 9), w_msk.detach().to(torch.float32).reshape(72, 32, 9)
+    s = torch.arange(72, device=dev)
+    w[3 * s], w[3 * s + 1], w[3 * s + 2] = wo[2 * s], wo[2 * s + 1], wm[s]
+    b[3 * s], b[3 * s + 1], b[3 * s + 2] = b_off.detach().float()[2 * s], b_off.detach().float()[2 * s + 1], b_msk.detach().float()[s]
+    wk = w.permute(0, 2, 1).reshape(224, 288)                       # [n][K = tap*32 + c]
+    chunks = wk.view(224, 36, 8).permute(1, 0, 2).contiguous()      # [kc][n][8]
+    hi, lo = split_bf16(chunks)
+    packed = torch.stack([hi.view(6, 6, 224, 8), lo.view(6, 6, 224, 8)], dim=1).contiguous()   # [sixth][hi|lo][6][224][8]
+    return packed, b.contiguous()
+
+
 def pack_layer_tc(info: dict, sd):
     """bf16-storage tensor-core packing (experimental CRFP_PREC_BF16) of a layer with crfp_layer_info.tc in (1, 2)."""
     w, b = sd[info["key"] + ".weight"], sd[info["key"] + ".bias"]

@@ -72,6 +72,10 @@ int crfp_selftest_umma(int rowsA, int K, int N, int shift, const void* A, const 
 
 /* micro-benchmark: `ctas` CTAs each issue `reps` back-to-back tcgen05.mma (M128 x N x K16 bf16) from one thread;
  * cycles_out[cta] = SM cycles from first issue to completion (device buffer of `ctas` int64). */
+/* as crfp_selftest_umma with an explicit A-operand SBO (16-byte records between 8-row groups):
+ * D[m][n] = sum_k A[shift + (m/8)*sbo_recs + m%8][k] * B[n][k] */
+int crfp_selftest_umma_sbo(int rowsA, int K, int N, int shift, int sbo_recs, const void* A, const void* B, float* D,
+                           crfp_stream stream);
 int crfp_selftest_umma_rate(int N, int reps, int ctas, long long* cycles_out, crfp_stream stream);
 
 /* ------------------------------------------------------------------ activations / epilogues */
@@ -299,6 +303,37 @@ int crfp_dcn_v2_tc_fwd(const crfp_dcn_desc* d, crfp_stream stream);
  * flow_hint (optional, NHWC 2-channel flow at this resolution) centres the shared-memory sampling window of each tile;
  * it only affects speed (samples outside the window are gathered from global memory). */
 int crfp_dcn_v2_tc3_fwd(const crfp_dcn_desc* d, const void* weight_lo, const float* flow_hint, crfp_stream stream);
+/*
+ * dcn_align_fused — the tail of DCN_module.forward (model/CRFP.py:337-350) as ONE kernel:
+ *   offset = head_mag * tanh(conv3x3(z; dcn_offset)) + flow.flip(1).repeat(72)   (144 channels)
+ *   mask   = sigmoid(conv3x3(z; dcn_mask))                                        (72 channels)
+ *   out    = DCNv2(x, offset, mask; dcn.weight, dcn.bias)      C = 32, dg = 8, cout = 32
+ * The offset / mask tensor never reaches HBM: the head convolution's accumulator stays in TMEM and the sampler threads
+ * read their raw offsets from it.  fp32 NHWC tensors; 3 x bf16 split products on tcgen05 (fp32-grade).
+ *   z        32-channel offset feature (cstride / coffset in floats, multiples of 4); flow: dense NHWC 2-channel (x, y)
+ *   x        32-channel tensor to align
+ *   heads_w  bf16 [6][2][6][224][8]: six K "sixths" (6 chunks of 8 input channels of the tap-major K = tap*32 + c), each
+ *            the hi half then the lo half, [chunk][n][8]; column n = 3*(g*9+t) + {0: dy, 1: dx, 2: mask}, columns 216..223
+ *            zero (crfp_b200.packing.pack_align_heads); heads_b fp32 [224] in the same column order
+ *   dcn_w_hi / dcn_w_lo / dcn_b: as crfp_dcn_v2_tc3_fwd ([36][32][8] packing, k = (g*9+t)*4 + c)
+ *   dbg_y0 / dbg_x0: optional int32 [n,h,w,72] dump of floor(py), floor(px) of every sample taken (parity)
+ */
+typedef struct {
+  int32_t n, h, w, _pad;
+  const float* z; int32_t z_cstride, z_coffset;
+  const float* flow;
+  const float* x; int32_t x_cstride, x_coffset;
+  const void* heads_w;
+  const float* heads_b;
+  const void* dcn_w_hi;
+  const void* dcn_w_lo;
+  const float* dcn_b;
+  float* out; int32_t out_cstride, out_coffset;
+  float head_mag; int32_t _pad2;
+  int32_t* dbg_y0; int32_t* dbg_x0;
+} crfp_align_fused_desc;
+int crfp_dcn_align_fused(const crfp_align_fused_desc* d, crfp_stream stream);
+size_t crfp_sizeof_align_fused_desc(void);
 /* debug/parity: floor(py), floor(px) for every (pixel, group, tap): int32 [n,h,w,dg*9] each (non-shared form) */
 int crfp_dcn_v2_indices(const crfp_dcn_desc* d, int32_t* y0, int32_t* x0, crfp_stream stream);
 size_t crfp_sizeof_dcn_desc(void);
@@ -362,6 +397,8 @@ typedef struct {
   const void* w_lo;     /* TC3: lo half (NULL in bf16 mode) */
   const float* b;
   const float* w_extra; /* TC3: fp32 [9][2][cout_packed] weights of a trailing 2-channel source, else NULL */
+  const void* w_fused;  /* TC3, dcn_k heads layers: crfp_align_fused_desc.heads_w packing (NULL: unfused heads + align) */
+  const float* b_fused; /* ... and heads_b */
 } crfp_layer_tc;
 typedef struct {
   int32_t mid_channels; /* 32 */

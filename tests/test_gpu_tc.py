@@ -387,3 +387,52 @@ def test_align_kernel_raw_heads_equals_epilogue_heads():
     assert L.lib().crfp_dcn_v2_tc3_fwd(C.byref(d), lo.data_ptr(), fd.data_ptr(), st) < 0
     d.head_flow = fd.data_ptr()
     assert L.lib().crfp_dcn_v2_fwd(C.byref(d), st) < 0
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 16, 8), (1, 26, 150), (2, 37, 53), (1, 48, 64)])
+def test_dcn_align_fused(n, h, w):
+    """crfp_dcn_align_fused (heads conv + activations + DCNv2 in one kernel, offsets never in HBM) against the oracle's
+    DCN_module tail (CRFP.py:337-350) and against the two-kernel path (same arithmetic -> same sampled integer indices)."""
+    import ctypes as C
+    from crfp_b200 import _lib as L
+    from crfp_b200 import ops
+    from crfp_b200.packing import pack_dcn_tc3
+    from oracle import crfp_oracle as O
+    g = _g(31 + h)
+    z = torch.randn(n, 32, h, w, generator=g)
+    x = torch.randn(n, 32, h, w, generator=g)
+    flow = torch.randn(n, 2, h, w, generator=g) * 3
+    flow[0, :, : h // 3] *= 6.0            # large flows: window centred by the flow, global fallback beyond it
+    w_off = torch.randn(144, 32, 3, 3, generator=g) * 0.05
+    w_msk = torch.randn(72, 32, 3, 3, generator=g) * 0.05
+    b_off = torch.randn(144, generator=g) * 0.05
+    b_msk = torch.randn(72, generator=g) * 0.05
+    wt = torch.randn(32, 32, 3, 3, generator=g) * 0.05
+    b = torch.randn(32, generator=g) * 0.05
+    f32 = lambda t: t.permute(0, 2, 3, 1).contiguous().cuda()
+    zd, xd, fd = f32(z), f32(x), f32(flow)
+    out, y0, x0 = ops.dcn_align_fused_nhwc(zd, fd, xd, w_off.cuda(), b_off.cuda(), w_msk.cuda(), b_msk.cuda(), wt.cuda(), b.cuda(),
+                                           indices=True)
+    torch.cuda.synchronize()
+    off = 10.0 * torch.tanh(F.conv2d(z, w_off, b_off, padding=1)) + flow.flip(1).repeat(1, 72, 1, 1)
+    msk = torch.sigmoid(F.conv2d(z, w_msk, b_msk, padding=1))
+    ref = O.dcn_v2(x, off, msk, wt, b, 8)
+    err = (nchw(out) - ref).abs().max().item()
+    print(f"dcn_align_fused {n}x{h}x{w}: max-abs vs oracle DCN_module tail {err:.3e}")
+    assert err < 2e-4
+    # the two-kernel tensor-core path: raw heads conv + align kernel with the activations in its sampler
+    om_raw = ops.conv3x3_tc3_nhwc([zd], torch.cat([w_off, w_msk], 0).cuda(), torch.cat([b_off, b_msk], 0).cuda(), act=L.ACT_NONE)
+    hi, lo, bp = pack_dcn_tc3(wt.cuda(), b.cuda(), 8)
+    out2 = torch.zeros(n, h, w, 32, device="cuda")
+    y1 = torch.zeros(n, h, w, 72, device="cuda", dtype=torch.int32)
+    x1 = torch.zeros_like(y1)
+    d = _dcn_desc(L, n, h, w, xd, om_raw, hi.data_ptr(), bp.data_ptr(), out2)
+    d.head_raw, d.head_flow, d.head_mag = 1, fd.data_ptr(), 10.0
+    d.dbg_y0, d.dbg_x0 = y1.data_ptr(), x1.data_ptr()
+    L.check(L.lib().crfp_dcn_v2_tc3_fwd(C.byref(d), lo.data_ptr(), fd.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "dcn tc3")
+    torch.cuda.synchronize()
+    same_idx = (y0 == y1).float().mean().item(), (x0 == x1).float().mean().item()
+    print(f"   vs two-kernel path: max-abs {(out - out2).abs().max().item():.3e}, identical sampled indices {same_idx}")
+    assert (out - out2).abs().max().item() < 1e-4
+    assert min(same_idx) > 0.9999          # the head values differ by accumulation order at most: floor() may flip on a tie
+    assert int((y0 == -12345).sum()) == 0 and int((x0 == -12345).sum()) == 0   # every sample of every pixel was taken
