@@ -181,6 +181,7 @@ SYMBOLS = {
     "crfp_dcn_v2_tc_fwd": (C.c_int, [C.POINTER(DcnDesc), C.c_void_p]),
     "crfp_dcn_v2_tc3_fwd": (C.c_int, [C.POINTER(DcnDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "crfp_dcn_align_fused": (C.c_int, [C.POINTER(AlignFusedDesc), C.c_void_p]),
+    "crfp_dcn_align_fused_trace": (C.c_int, [C.POINTER(AlignFusedDesc), C.c_void_p, C.c_void_p]),
     "crfp_sizeof_align_fused_desc": (C.c_size_t, []),
     "crfp_dcn_v2_indices": (C.c_int, [C.POINTER(DcnDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "crfp_sizeof_dcn_desc": (C.c_size_t, []),

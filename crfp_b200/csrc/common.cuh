@@ -185,7 +185,7 @@ int launch_flow_warp(const crfp_warp_desc& d, cudaStream_t st);
 int launch_dcn(const crfp_dcn_desc& d, cudaStream_t st);
 int launch_dcn_tc(const crfp_dcn_desc& d, cudaStream_t st);
 int launch_dcn_tc3(const crfp_dcn_desc& d, const void* w_lo, const float* flow_hint, cudaStream_t st);
-int launch_align_fused(const crfp_align_fused_desc& d, cudaStream_t st);
+int launch_align_fused(const crfp_align_fused_desc& d, cudaStream_t st, long long* trace = nullptr);
 int launch_flow_warp_bf16(const crfp_warp_desc& d, cudaStream_t st);
 int launch_flow_up2_dual(int n, int h, int w, const float* flow, float* out_f32, void* out_bf8, cudaStream_t st);
 

@@ -13,14 +13,15 @@
 //        ADDRESS into it and the 8-pixel tile rows are addressed with SBO = 10 records (160 B).
 //     B: 258 KB of split weights do not fit: they stream from L2 in six 42 KB "sixths" (6 K chunks each) through a ring of
 //        two slots with cp.async.bulk + mbarrier; the next tile's first sixth is prefetched during phase S.
-//  S  for each K quarter (2 deformable groups): ONE TMA tensor-tile load of the 32 x 40 x 8-channel sampling window of x
+//  S  for each K quarter (2 deformable groups): two TMA tensor-tile loads (one 33 x 40 x 4-channel plane per group) of the sampling window of x
 //     (origin shifted by the rounded flow at the tile centre; samples outside it fall back to global loads), 12 sampler
 //     warps = (TMEM lane quadrant, third of the quarter's 18 samples): tcgen05.ld of the thread's 18 raw head values, bias,
 //     tanh / sigmoid / + flow (same ex2 / rcp arithmetic as the unfused path), bilinear gather with LDS.128, modulate,
 //     split hi / lo into the UMMA A stage (thread = pixel: conflict-free stores), 15 tcgen05.mma into TMEM columns
 //     224..255; after the 4th quarter warps 0-3 drain the 32-channel result.
 //
-// Shared memory (204 KB): [W slot 0 42 KB][W slot 1 42 KB | window B 40 KB][DCN weights 40 KB][A stage 40 KB][window A 40 KB | z hi/lo 23 KB].
+// Shared memory (204 KB): [W slot 0 42 KB][W slot 1 42 KB | window B 40 KB][DCN weights 40 KB][A stage 40 KB | z hi/lo 23 KB][window A 40 KB].
+// Window A is free during phase H, so the first quarter's window is fetched while the heads GEMM runs.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -37,8 +38,10 @@ constexpr int FNH = 224;                       // heads GEMM N
 constexpr int FWREC = 6 * FNH;                 // records per sixth and half (hi / lo)
 constexpr int FWSLOT = 2 * FWREC * 16;         // 43008 B
 constexpr int FWR = 12;                        // window reach: 10 (max |residual offset|) + 1 (tap) + 1 (bilinear corner)
-constexpr int FWW = FTW + 2 * FWR, FWH = FTH + 2 * FWR;   // 32 x 40 pixels
-constexpr int FWIN_BYTES = FWH * FWW * 8 * 4;  // 40960
+constexpr int FWW = FTW + 2 * FWR + 1, FWH = FTH + 2 * FWR;   // 33 x 40 pixels: the odd width is the row pitch of the staged
+                                                              // planes (528 B), so the 4 pixel rows of a warp fall into different banks
+constexpr int FWPLANE = FWH * FWW;             // float4 records per deformable-group plane
+constexpr int FWIN_BYTES = 2 * FWPLANE * 16;   // 42240: two group planes [gl][40][33][4 floats]
 constexpr int FQC = 10;                        // K chunks per DCN quarter (9 real + 1 zero)
 constexpr int FAP = 128;                       // records per chunk row of the DCN A stage
 constexpr int FA_RECS = FQC * FAP;
@@ -48,10 +51,11 @@ constexpr int OFF_W0 = 0;
 constexpr int OFF_W1 = FWSLOT;                          // also window B
 constexpr int OFF_DW = 2 * FWSLOT;                      // DCN weights hi | lo: 2 x 4 x 10 x 32 records
 constexpr int OFF_A = OFF_DW + 2 * 4 * FQC * 32 * 16;   // A stage hi | lo
-constexpr int OFF_WA = OFF_A + 2 * FA_RECS * 16;        // window A, also z hi | lo
+constexpr int OFF_WA = OFF_A + 2 * FA_RECS * 16;        // window A
+constexpr int OFF_Z = OFF_A;                            // z hi | lo share the A stage (phase H only)
 constexpr int FUSED_SMEM = OFF_WA + FWIN_BYTES;         // 208896
 static_assert(FWIN_BYTES <= FWSLOT, "window B must fit in W slot 1");
-static_assert(2 * 4 * FZP * 16 <= FWIN_BYTES, "z operand must fit in window A");
+static_assert(2 * 4 * FZP * 16 <= 2 * FA_RECS * 16, "z operand must fit in the A stage");
 static_assert(OFF_W1 % 128 == 0 && OFF_WA % 128 == 0, "TMA destinations must be 128-byte aligned");
 
 struct FusedParams {
@@ -68,6 +72,7 @@ struct FusedParams {
   float head_mag;
   int32_t* dbg_y0;
   int32_t* dbg_x0;
+  long long* trace;            // optional clock64 timeline of CTA 0 (profiling aid): [tile][16]
 };
 
 __device__ __forceinline__ void fused_split8(const float4 a, const float4 b, uint4& hi, uint4& lo) {
@@ -90,44 +95,6 @@ __device__ __forceinline__ void fused_split_pair(float a, float b, uint32_t& hi,
   lo = umma::pack_bf16(a - __bfloat162float(h0), b - __bfloat162float(h1));
 }
 
-// one modulated sample (4 channels of deformable group 2q + gl) from the staged window, global fallback outside it
-__device__ __forceinline__ void fused_sample(const FusedParams& P, const float* img, const float4* sWin, int wy0, int wx0, int q,
-                                             int gtr, int y, int x, float dy, float dx, float m, float* v, long long dbg_idx) {
-  const int gl = gtr / 9, t = gtr - gl * 9;
-  const int i = t / 3, j = t - i * 3;
-  int y0, x0;
-  float w00, w01, w10, w11;
-  dcn_corner_w(dcn_pos(y, i, dy), dcn_pos(x, j, dx), P.h, P.w, y0, x0, w00, w01, w10, w11);
-  if (P.dbg_y0 != nullptr) { P.dbg_y0[dbg_idx] = y0; P.dbg_x0[dbg_idx] = x0; }
-  const int wy = y0 - wy0, wx = x0 - wx0;
-  if (wy >= 0 && wy + 1 < FWH && wx >= 0 && wx + 1 < FWW) {
-    const float4* p = sWin + (wy * FWW + wx) * 2 + gl;
-    const float4 c00 = p[0], c01 = p[2], c10 = p[FWW * 2], c11 = p[FWW * 2 + 2];
-    const float2 k00 = make_float2(w00, w00), k01 = make_float2(w01, w01), k10 = make_float2(w10, w10), k11 = make_float2(w11, w11);
-    const float2 mm = make_float2(m, m), zz = make_float2(0.f, 0.f);
-    float2 a = __ffma2_rn(k00, make_float2(c00.x, c00.y), zz), b = __ffma2_rn(k00, make_float2(c00.z, c00.w), zz);
-    a = __ffma2_rn(k01, make_float2(c01.x, c01.y), a); b = __ffma2_rn(k01, make_float2(c01.z, c01.w), b);
-    a = __ffma2_rn(k10, make_float2(c10.x, c10.y), a); b = __ffma2_rn(k10, make_float2(c10.z, c10.w), b);
-    a = __ffma2_rn(k11, make_float2(c11.x, c11.y), a); b = __ffma2_rn(k11, make_float2(c11.z, c11.w), b);
-    a = __ffma2_rn(a, mm, zz); b = __ffma2_rn(b, mm, zz);
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-    return;
-  }
-  v[0] = v[1] = v[2] = v[3] = 0.f;
-  const float* p = img + ((long long)y0 * P.w + x0) * P.x_cstride + (2 * q + gl) * 4;
-#define CRFP_C4(ptr, wgt)                                                  \
-  if ((wgt) != 0.f) {                                                      \
-    const float4 t4 = __ldg(reinterpret_cast<const float4*>(ptr));         \
-    v[0] += (wgt) * t4.x; v[1] += (wgt) * t4.y; v[2] += (wgt) * t4.z; v[3] += (wgt) * t4.w; \
-  }
-  CRFP_C4(p, w00)
-  CRFP_C4(p + P.x_cstride, w01)
-  CRFP_C4(p + (long long)P.w * P.x_cstride, w10)
-  CRFP_C4(p + (long long)P.w * P.x_cstride + P.x_cstride, w11)
-#undef CRFP_C4
-  v[0] *= m; v[1] *= m; v[2] *= m; v[3] *= m;
-}
-
 __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t w_full[2], w_empty[2], win_full[2], a_full, a_empty, hacc_full, dacc_full;
@@ -141,7 +108,7 @@ __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedPara
   uint4* sBl = sBh + 4 * FQC * 32;
   uint4* sAh = reinterpret_cast<uint4*>(smem + OFF_A);           // [10][128]
   uint4* sAl = sAh + FA_RECS;
-  uint4* sZh = reinterpret_cast<uint4*>(smem + OFF_WA);          // [4][184]
+  uint4* sZh = reinterpret_cast<uint4*>(smem + OFF_Z);           // [4][184]
   uint4* sZl = sZh + 4 * FZP;
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -162,10 +129,6 @@ __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedPara
   for (int i = tid; i < 4 * 32; i += 512) {
     sBh[((i >> 5) * FQC + 9) * 32 + (i & 31)] = make_uint4(0u, 0u, 0u, 0u);
     sBl[((i >> 5) * FQC + 9) * 32 + (i & 31)] = make_uint4(0u, 0u, 0u, 0u);
-  }
-  for (int i = tid; i < FAP; i += 512) {       // the zero K chunk of the A stage
-    sAh[9 * FAP + i] = make_uint4(0u, 0u, 0u, 0u);
-    sAl[9 * FAP + i] = make_uint4(0u, 0u, 0u, 0u);
   }
   for (int i = tid; i < FNH; i += 512) s_hbias[i] = P.heads_b[i];
   if (tid < 32) s_dbias[tid] = P.dbias[tid];
@@ -201,34 +164,67 @@ __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedPara
     const int tyi = trm / tiles_x, txi = trm - tyi * tiles_x;
     const int y0t = tyi * FTH, x0t = txi * FTW;
 
+    long long* tr = (P.trace != nullptr && blockIdx.x == 0 && it < 16) ? P.trace + it * 16 : nullptr;
+    if (tr && tid == 0) tr[0] = clock64();
+    // flow at the tile centre: centres the sampling windows (loaded here so that its latency hides behind the z conversion)
+    float2 flc = make_float2(0.f, 0.f);
+    if (warp == 0) {
+      const int cy = min(y0t + FTH / 2, P.h - 1), cx = min(x0t + FTW / 2, P.w - 1);
+      flc = __ldg(reinterpret_cast<const float2*>(P.flow + (((size_t)n * P.h + cy) * (size_t)P.w + cx) * 2));
+    }
     // ================================================================ phase H: z halo -> hi / lo operand
-    for (int i = tid; i < FHPX * 4; i += 512) {
-      const int p = i >> 2, c8 = i & 3;
-      const int hy = p / FHW, hx = p - hy * FHW;
-      const int gy = y0t - 1 + hy, gx = x0t - 1 + hx;
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-      if (gy >= 0 && gy < P.h && gx >= 0 && gx < P.w) {
-        const float4* g = reinterpret_cast<const float4*>(P.z + (((size_t)n * P.h + gy) * (size_t)P.w + gx) * P.z_cstride + P.z_coffset + c8 * 8);
-        a = __ldg(g); b = __ldg(g + 1);
+    {
+      float4 za[2], zb[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {     // 720 records over 512 threads: both loads of a thread in flight before the split
+        const int i = tid + u * 512;
+        za[u] = make_float4(0.f, 0.f, 0.f, 0.f); zb[u] = za[u];
+        if (i < FHPX * 4) {
+          const int p = i >> 2, c8 = i & 3;
+          const int hy = p / FHW, hx = p - hy * FHW;
+          const int gy = y0t - 1 + hy, gx = x0t - 1 + hx;
+          if (gy >= 0 && gy < P.h && gx >= 0 && gx < P.w) {
+            const float4* g = reinterpret_cast<const float4*>(P.z + (((size_t)n * P.h + gy) * (size_t)P.w + gx) * P.z_cstride + P.z_coffset + c8 * 8);
+            za[u] = __ldg(g); zb[u] = __ldg(g + 1);
+          }
+        }
       }
-      uint4 hi, lo;
-      fused_split8(a, b, hi, lo);
-      sZh[c8 * FZP + p] = hi;
-      sZl[c8 * FZP + p] = lo;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = tid + u * 512;
+        if (i < FHPX * 4) {
+          uint4 hi, lo;
+          fused_split8(za[u], zb[u], hi, lo);
+          sZh[(i & 3) * FZP + (i >> 2)] = hi;
+          sZl[(i & 3) * FZP + (i >> 2)] = lo;
+        }
+      }
     }
     umma::fence_proxy_async();
     __syncthreads();
+    if (tr && tid == 0) tr[1] = clock64();   // z operand ready
 
+    auto issue_window = [&](int q) {
+      const int wy0 = y0t - FWR + (int)rintf(fminf(fmaxf(flc.y, -4096.f), 4096.f));
+      const int wx0 = x0t - FWR + (int)rintf(fminf(fmaxf(flc.x, -4096.f), 4096.f));
+      const int slot = q & 1;
+      s_org[slot] = make_int2(wy0, wx0);
+      umma::mbar_arrive_expect_tx(&win_full[slot], (uint32_t)FWIN_BYTES);
+      umma::tma_load_4d(sWinP(slot), &tmap, &win_full[slot], 8 * q, wx0, wy0, n);                    // group 2q
+      umma::tma_load_4d(sWinP(slot) + FWPLANE * 4, &tmap, &win_full[slot], 8 * q + 4, wx0, wy0, n);   // group 2q + 1
+    };
     if (warp == 0) {
       if (umma::elect_one()) {
         umma::fence_after_sync();
-        load_sixth(1);   // slot 1 (= window B of the previous tile) is free since the tile-end barrier
+        load_sixth(1);     // slot 1 (= window B of the previous tile) is free since the tile-end barrier
+        issue_window(0);   // window A is not needed by phase H: the first quarter's window lands behind the heads GEMM
         const uint64_t dZh = umma::make_desc(umma::smem_u32(sZh), FZP * 16, FHW * 16), dZl = umma::make_desc(umma::smem_u32(sZl), FZP * 16, FHW * 16);
         const uint32_t zhl = (uint32_t)dZh, zhh = (uint32_t)(dZh >> 32), zll = (uint32_t)dZl, zlh = (uint32_t)(dZl >> 32);
 #pragma unroll 1
         for (int s = 0; s < 6; ++s) {
           const int slot = s & 1;
           umma::mbar_wait_safe(&w_full[slot], (uint32_t)((it * 3 + (s >> 1)) & 1));
+          if (tr && s == 0) tr[2] = clock64();   // first W sixth landed
           const uint64_t dWh = umma::make_desc(umma::smem_u32(sW(slot)), FNH * 16, 128);
           const uint64_t dWl = umma::make_desc(umma::smem_u32(sW(slot) + FWREC), FNH * 16, 128);
           const uint32_t whl = (uint32_t)dWh, whh = (uint32_t)(dWh >> 32), wll = (uint32_t)dWl, wlh = (uint32_t)(dWl >> 32);
@@ -258,20 +254,10 @@ __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedPara
     // ================================================================ phase S
     umma::mbar_wait_safe(&hacc_full, (uint32_t)(it & 1));   // heads accumulator complete; z and W slot 1 are free
     umma::fence_after_sync();
+    if (tr && tid == 0) tr[3] = clock64();     // heads GEMM done
     if (warp < 4) {
-      auto issue_window = [&](int q) {
-        int wy0 = y0t - FWR, wx0 = x0t - FWR;
-        const int cy = min(y0t + FTH / 2, P.h - 1), cx = min(x0t + FTW / 2, P.w - 1);
-        const float2 fl = __ldg(reinterpret_cast<const float2*>(P.flow + (((size_t)n * P.h + cy) * (size_t)P.w + cx) * 2));
-        wy0 += (int)rintf(fminf(fmaxf(fl.y, -4096.f), 4096.f));
-        wx0 += (int)rintf(fminf(fmaxf(fl.x, -4096.f), 4096.f));
-        const int slot = q & 1;
-        s_org[slot] = make_int2(wy0, wx0);
-        umma::mbar_arrive_expect_tx(&win_full[slot], (uint32_t)FWIN_BYTES);
-        umma::tma_load_4d(sWinP(slot), &tmap, &win_full[slot], 8 * q, wx0, wy0, n);
-      };
       if (warp == 0) {
-        if (umma::elect_one()) { issue_window(0); issue_window(1); }
+        if (umma::elect_one()) issue_window(1);   // window B shares W slot 1: free now that the heads GEMM is done
         __syncwarp();
         for (int q = 0; q < 4; ++q) {
           umma::mbar_wait_safe(&a_full, (uint32_t)(q & 1));
@@ -329,33 +315,104 @@ __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedPara
         umma::tmem_ld2(taddr + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(col + 16), raw + 16);
 #pragma unroll
         for (int i = 0; i < 18; ++i) raw[i] += s_hbias[col + i];
+        if (tr && tid == 128) tr[4 + 3 * q] = clock64();        // sampler: raw offsets in registers
         umma::mbar_wait_safe(&win_full[q & 1], (uint32_t)((q >> 1) & 1));
-        if (q > 0) umma::mbar_wait_safe(&a_empty, (uint32_t)((q - 1) & 1));   // the MMAs of quarter q-1 have read the A stage
+        if (tr && tid == 128) tr[5 + 3 * q] = clock64();        // window landed
         const int2 org = s_org[q & 1];
         const float4* win = reinterpret_cast<const float4*>(sWinP(q & 1));
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           const int kl = 3 * jthird + r;
+          // both samples of the record: positions, corner weights and window addresses first, then all 8 LDS.128 back to
+          // back (no branch in between), then the arithmetic; samples that leave the window are redone from global
+          // memory afterwards (rare)
+          float sv[2][4];
+          int sy0[2], sx0[2];
+          float sw[2][4], smk[2], spy[2], spx[2];
+          bool sin[2];
+          const float4* sp[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int gtr = 2 * kl + e, gl = gtr / 9, t = gtr - gl * 9;
+            const int i = t / 3, j = t - i * 3;
+            const float dy = head_offset_act(raw[6 * r + 3 * e + 0], P.head_mag, fl.y);
+            const float dx = head_offset_act(raw[6 * r + 3 * e + 1], P.head_mag, fl.x);
+            smk[e] = head_mask_act(raw[6 * r + 3 * e + 2]);
+            // the staged planes are zero outside the image (TMA out-of-bounds fill), so in-window samples need no
+            // per-corner validity: out-of-image corners contribute w * 0 exactly like the reference's zero padding
+            spy[e] = dcn_pos(y, i, dy); spx[e] = dcn_pos(x, j, dx);
+            const float fy = floorf(spy[e]), fx = floorf(spx[e]);
+            sy0[e] = (int)fy; sx0[e] = (int)fx;
+            const float ly = spy[e] - fy, lx = spx[e] - fx, hy = 1.f - ly, hx = 1.f - lx;
+            sw[e][0] = hy * hx; sw[e][1] = hy * lx; sw[e][2] = ly * hx; sw[e][3] = ly * lx;
+            const int wy = sy0[e] - org.x, wx = sx0[e] - org.y;
+            sin[e] = wy >= 0 && wy + 1 < FWH && wx >= 0 && wx + 1 < FWW;
+            sp[e] = win + gl * FWPLANE + (sin[e] ? wy * FWW + wx : 0);
+          }
+          float4 c[2][4];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) { c[e][0] = sp[e][0]; c[e][1] = sp[e][1]; c[e][2] = sp[e][FWW]; c[e][3] = sp[e][FWW + 1]; }
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float2 zz = make_float2(0.f, 0.f), mm = make_float2(smk[e], smk[e]);
+            float2 a = zz, b = zz;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 kw = make_float2(sw[e][k], sw[e][k]);
+              a = __ffma2_rn(kw, make_float2(c[e][k].x, c[e][k].y), a);
+              b = __ffma2_rn(kw, make_float2(c[e][k].z, c[e][k].w), b);
+            }
+            a = __ffma2_rn(a, mm, zz); b = __ffma2_rn(b, mm, zz);
+            sv[e][0] = a.x; sv[e][1] = a.y; sv[e][2] = b.x; sv[e][3] = b.y;
+          }
+          if (valid) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int gtr = 2 * kl + e;
+              if (P.dbg_y0 != nullptr) {
+                const long long dbg = (long long)pix * 72 + q * 18 + gtr;
+                P.dbg_y0[dbg] = sy0[e]; P.dbg_x0[dbg] = sx0[e];
+              }
+              if (!sin[e]) {   // outside the staged window: global gather with the full per-corner validity
+                const int gl = gtr / 9;
+                int gy0, gx0;
+                dcn_corner_w(spy[e], spx[e], P.h, P.w, gy0, gx0, sw[e][0], sw[e][1], sw[e][2], sw[e][3]);
+                const float* p = img + ((long long)sy0[e] * P.w + sx0[e]) * P.x_cstride + (2 * q + gl) * 4;
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+#define CRFP_C4(ptr, wgt)                                                  \
+  if ((wgt) != 0.f) {                                                      \
+    const float4 t4 = __ldg(reinterpret_cast<const float4*>(ptr));         \
+    v[0] += (wgt) * t4.x; v[1] += (wgt) * t4.y; v[2] += (wgt) * t4.z; v[3] += (wgt) * t4.w; \
+  }
+                CRFP_C4(p, sw[e][0])
+                CRFP_C4(p + P.x_cstride, sw[e][1])
+                CRFP_C4(p + (long long)P.w * P.x_cstride, sw[e][2])
+                CRFP_C4(p + (long long)P.w * P.x_cstride + P.x_cstride, sw[e][3])
+#undef CRFP_C4
+                sv[e][0] = v[0] * smk[e]; sv[e][1] = v[1] * smk[e]; sv[e][2] = v[2] * smk[e]; sv[e][3] = v[3] * smk[e];
+              }
+            }
+          }
           uint4 rh = make_uint4(0u, 0u, 0u, 0u), rl = rh;
           if (valid) {
-            float v0[4], v1[4];
-            const float dy0 = head_offset_act(raw[6 * r + 0], P.head_mag, fl.y), dx0 = head_offset_act(raw[6 * r + 1], P.head_mag, fl.x);
-            const float m0 = head_mask_act(raw[6 * r + 2]);
-            const float dy1 = head_offset_act(raw[6 * r + 3], P.head_mag, fl.y), dx1 = head_offset_act(raw[6 * r + 4], P.head_mag, fl.x);
-            const float m1 = head_mask_act(raw[6 * r + 5]);
-            const long long dbg = (long long)pix * 72 + q * 18 + 2 * kl;
-            fused_sample(P, img, win, org.x, org.y, q, 2 * kl, y, x, dy0, dx0, m0, v0, dbg);
-            fused_sample(P, img, win, org.x, org.y, q, 2 * kl + 1, y, x, dy1, dx1, m1, v1, dbg + 1);
-            fused_split_pair(v0[0], v0[1], rh.x, rl.x);
-            fused_split_pair(v0[2], v0[3], rh.y, rl.y);
-            fused_split_pair(v1[0], v1[1], rh.z, rl.z);
-            fused_split_pair(v1[2], v1[3], rh.w, rl.w);
+            fused_split_pair(sv[0][0], sv[0][1], rh.x, rl.x);
+            fused_split_pair(sv[0][2], sv[0][3], rh.y, rl.y);
+            fused_split_pair(sv[1][0], sv[1][1], rh.z, rl.z);
+            fused_split_pair(sv[1][2], sv[1][3], rh.w, rl.w);
+          }
+          if (r == 0) {
+            if (q > 0) umma::mbar_wait_safe(&a_empty, (uint32_t)((q - 1) & 1));   // the MMAs of quarter q-1 have read the A stage
+            else if (tid - 128 < FAP) {   // z lived here during phase H: restore the zero K chunk of the stage
+              sAh[9 * FAP + (tid - 128)] = make_uint4(0u, 0u, 0u, 0u);
+              sAl[9 * FAP + (tid - 128)] = make_uint4(0u, 0u, 0u, 0u);
+            }
           }
           sAh[kl * FAP + m] = rh;
           sAl[kl * FAP + m] = rl;
         }
         umma::fence_proxy_async();
         umma::mbar_arrive(&a_full);
+        if (tr && tid == 128) tr[6 + 3 * q] = clock64();        // quarter sampled
       }
       umma::fence_before_sync();
     }
@@ -380,7 +437,7 @@ static tmap_encode_fn fused_tmap_encoder() {
   return fn;
 }
 
-int launch_align_fused(const crfp_align_fused_desc& d, cudaStream_t st) {
+int launch_align_fused(const crfp_align_fused_desc& d, cudaStream_t st, long long* trace) {
   if ((long long)d.n * d.h * d.w == 0) return CRFP_OK;
   if (!d.z || !d.flow || !d.x || !d.heads_w || !d.heads_b || !d.dcn_w_hi || !d.dcn_w_lo || !d.dcn_b || !d.out) return CRFP_ERR_NULL;
   if ((d.dbg_y0 != nullptr) != (d.dbg_x0 != nullptr)) return CRFP_ERR_NULL;
@@ -394,7 +451,7 @@ int launch_align_fused(const crfp_align_fused_desc& d, cudaStream_t st) {
   CUtensorMap tmap;
   const cuuint64_t gdim[4] = {32, (cuuint64_t)d.w, (cuuint64_t)d.h, (cuuint64_t)d.n};
   const cuuint64_t gstr[3] = {(cuuint64_t)d.x_cstride * 4, (cuuint64_t)d.w * d.x_cstride * 4, (cuuint64_t)d.h * d.w * d.x_cstride * 4};
-  const cuuint32_t box[4] = {8, FWW, FWH, 1};
+  const cuuint32_t box[4] = {4, FWW, FWH, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -410,6 +467,7 @@ int launch_align_fused(const crfp_align_fused_desc& d, cudaStream_t st) {
   p.out = d.out; p.out_cstride = d.out_cstride; p.out_coffset = d.out_coffset;
   p.head_mag = d.head_mag;
   p.dbg_y0 = d.dbg_y0; p.dbg_x0 = d.dbg_x0;
+  p.trace = trace;
   cudaError_t e = cudaFuncSetAttribute(dcn_align_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
   if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
   int dev = 0, sms = 148;
@@ -426,7 +484,15 @@ using namespace crfp;
 
 extern "C" int crfp_dcn_align_fused(const crfp_align_fused_desc* d, crfp_stream stream) {
   if (!d) return CRFP_ERR_NULL;
-  return launch_align_fused(*d, (cudaStream_t)stream);
+  return launch_align_fused(*d, (cudaStream_t)stream, nullptr);
+}
+
+// profiling aid: same launch + a clock64 timeline of CTA 0's first 16 tiles into trace[16][16] (device int64):
+// [0] tile start, [1] z operand ready, [2] first W sixth landed, [3] heads GEMM done, then per quarter q:
+// [4+3q] sampler has its raw offsets, [5+3q] window landed and A stage free, [6+3q] quarter sampled
+extern "C" int crfp_dcn_align_fused_trace(const crfp_align_fused_desc* d, long long* trace, crfp_stream stream) {
+  if (!d || !trace) return CRFP_ERR_NULL;
+  return launch_align_fused(*d, (cudaStream_t)stream, trace);
 }
 
 extern "C" size_t crfp_sizeof_align_fused_desc(void) { return sizeof(crfp_align_fused_desc); }

@@ -333,6 +333,8 @@ typedef struct {
   int32_t* dbg_y0; int32_t* dbg_x0;
 } crfp_align_fused_desc;
 int crfp_dcn_align_fused(const crfp_align_fused_desc* d, crfp_stream stream);
+/* profiling aid: same launch + a clock64 timeline of CTA 0's first 16 tiles into trace[16][16] (device int64) */
+int crfp_dcn_align_fused_trace(const crfp_align_fused_desc* d, long long* trace, crfp_stream stream);
 size_t crfp_sizeof_align_fused_desc(void);
 /* debug/parity: floor(py), floor(px) for every (pixel, group, tap): int32 [n,h,w,dg*9] each (non-shared form) */
 int crfp_dcn_v2_indices(const crfp_dcn_desc* d, int32_t* y0, int32_t* x0, crfp_stream stream);
