@@ -97,7 +97,7 @@ __device__ __forceinline__ void fused_split_pair(float a, float b, uint32_t& hi,
 
 __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t w_full[2], w_empty[2], win_full[2], a_full, a_empty, hacc_full, dacc_full;
+  __shared__ uint64_t w_full[2], w_empty[2], win_full[2], a_full, a_empty, hacc_full, dacc_full, dacc_empty;
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_hbias[FNH];
   __shared__ float s_dbias[32];
@@ -109,13 +109,12 @@ __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedPara
   uint4* sAh = reinterpret_cast<uint4*>(smem + OFF_A);           // [10][128]
   uint4* sAl = sAh + FA_RECS;
   uint4* sZh = reinterpret_cast<uint4*>(smem + OFF_Z);           // [4][184]
-  uint4* sZl = sZh + 4 * FZP;
+  uint4* sZ1h = reinterpret_cast<uint4*>(smem + OFF_WA);         // second tile of a round: [hi 4][184] | [lo 4][184]
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int lane = tid & 31;
   const int tiles_x = (P.w + FTW - 1) / FTW, tiles_y = (P.h + FTH - 1) / FTH;
   const int tiles_img = tiles_x * tiles_y, total = tiles_img * P.n;
-  const int my_tiles = ((int)blockIdx.x < total) ? (total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   // ---- constant-only prologue (overlaps the previous kernel under PDL)
   pdl_trigger();
@@ -132,11 +131,11 @@ __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedPara
   }
   for (int i = tid; i < FNH; i += 512) s_hbias[i] = P.heads_b[i];
   if (tid < 32) s_dbias[tid] = P.dbias[tid];
-  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 256);
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&w_full[i], 1); umma::mbar_init(&w_empty[i], 1); umma::mbar_init(&win_full[i], 1); }
     umma::mbar_init(&a_full, FSAMP); umma::mbar_init(&a_empty, 1);
-    umma::mbar_init(&hacc_full, 1); umma::mbar_init(&dacc_full, 1);
+    umma::mbar_init(&hacc_full, 1); umma::mbar_init(&dacc_full, 1); umma::mbar_init(&dacc_empty, 128);
     umma::fence_mbar_init();
     umma::tma_prefetch_desc(&tmap);
   }
@@ -146,84 +145,113 @@ __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedPara
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t taddr = tmem_base_s;
-  const uint32_t dacc = taddr + (uint32_t)FNH;     // DCN accumulator: TMEM columns 224..255
+  const uint32_t dacc = taddr + (uint32_t)(2 * FNH);   // DCN accumulator: TMEM columns 448..479
   pdl_wait();   // activations (z, flow, x, out) are only touched from here on
 
+  // Work list: ROUNDS of up to two tiles that share one pass over the streamed head weights (the W stream from L2 is what
+  // bounds phase H: 258 KB per pass, so two tiles per pass halve it).  Full rounds take tiles 2*(r*G + b), +1; the
+  // remainder (< 2G tiles) is dealt one tile per CTA, then a second one, so no CTA does more than ceil(total / G) tiles.
+  const int G = (int)gridDim.x, bx = (int)blockIdx.x;
+  const int full_rounds = total / (2 * G);
+  const int rem_base = 2 * G * full_rounds;
+  const int rem0 = rem_base + bx, rem1 = rem_base + G + bx;
+  const int rounds = full_rounds + (rem0 < total ? 1 : 0);
+
   const uint32_t idesc_h = umma::make_idesc_bf16(128, FNH), idesc_d = umma::make_idesc_bf16(128, 32);
-  // the W stream is owned by ONE thread (warp 0's elected lane); sixth k of tile it lands in slot k & 1
+  // the W stream is owned by ONE thread (warp 0's elected lane); sixth s of a round lands in slot s & 1
   auto load_sixth = [&](int s) {
     umma::mbar_arrive_expect_tx(&w_full[s & 1], (uint32_t)FWSLOT);
     umma::bulk_load(sW(s & 1), reinterpret_cast<const unsigned char*>(P.heads_w) + (size_t)s * FWSLOT, (uint32_t)FWSLOT, &w_full[s & 1]);
   };
-  if (warp == 0 && my_tiles > 0 && umma::elect_one()) load_sixth(0);
+  if (warp == 0 && rounds > 0 && umma::elect_one()) load_sixth(0);
   __syncwarp();
 
-  for (int it = 0; it < my_tiles; ++it) {
-    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-    const int n = tile / tiles_img, trm = tile - n * tiles_img;
-    const int tyi = trm / tiles_x, txi = trm - tyi * tiles_x;
-    const int y0t = tyi * FTH, x0t = txi * FTW;
-
-    long long* tr = (P.trace != nullptr && blockIdx.x == 0 && it < 16) ? P.trace + it * 16 : nullptr;
-    if (tr && tid == 0) tr[0] = clock64();
-    // flow at the tile centre: centres the sampling windows (loaded here so that its latency hides behind the z conversion)
-    float2 flc = make_float2(0.f, 0.f);
-    if (warp == 0) {
-      const int cy = min(y0t + FTH / 2, P.h - 1), cx = min(x0t + FTW / 2, P.w - 1);
-      flc = __ldg(reinterpret_cast<const float2*>(P.flow + (((size_t)n * P.h + cy) * (size_t)P.w + cx) * 2));
-    }
-    // ================================================================ phase H: z halo -> hi / lo operand
-    {
-      float4 za[2], zb[2];
+  int kq = 0;        // quarters processed so far by this CTA (barrier phase bookkeeping)
+  int ntile = 0;     // tiles processed so far
+  for (int rd = 0; rd < rounds; ++rd) {
+    int tl[2];
+    if (rd < full_rounds) { tl[0] = 2 * (rd * G + bx); tl[1] = tl[0] + 1; }
+    else { tl[0] = rem0; tl[1] = rem1 < total ? rem1 : -1; }
+    const int nt = tl[1] >= 0 ? 2 : 1;
+    int tn[2], ty0[2], tx0[2];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {     // 720 records over 512 threads: both loads of a thread in flight before the split
+    for (int u = 0; u < 2; ++u) {
+      const int t_ = tl[u] >= 0 ? tl[u] : 0;
+      tn[u] = t_ / tiles_img;
+      const int trm = t_ - tn[u] * tiles_img;
+      const int tyi = trm / tiles_x;
+      ty0[u] = tyi * FTH; tx0[u] = (trm - tyi * tiles_x) * FTW;
+    }
+    long long* tr = (P.trace != nullptr && blockIdx.x == 0 && rd < 8) ? P.trace + rd * 32 : nullptr;
+    if (tr && tid == 0) tr[0] = clock64();
+    // flow at the tile centres: centres the sampling windows (loaded here: its latency hides behind the z conversion)
+    float2 flc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    if (warp == 0) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int cy = min(ty0[u] + FTH / 2, P.h - 1), cx = min(tx0[u] + FTW / 2, P.w - 1);
+        flc[u] = __ldg(reinterpret_cast<const float2*>(P.flow + (((size_t)tn[u] * P.h + cy) * (size_t)P.w + cx) * 2));
+      }
+    }
+    // ================================================================ phase H: z halos -> hi / lo operands
+    // tile 0's operand lives in the A stage, tile 1's in window A (both idle during phase H)
+    {
+      float4 za[3], zb[3];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {     // 2 x 720 records over 512 threads: all loads of a thread in flight before the split
         const int i = tid + u * 512;
         za[u] = make_float4(0.f, 0.f, 0.f, 0.f); zb[u] = za[u];
-        if (i < FHPX * 4) {
-          const int p = i >> 2, c8 = i & 3;
+        const int sel = i >= FHPX * 4 ? 1 : 0, il = i - sel * FHPX * 4;
+        if (i < nt * FHPX * 4) {
+          const int p = il >> 2, c8 = il & 3;
           const int hy = p / FHW, hx = p - hy * FHW;
-          const int gy = y0t - 1 + hy, gx = x0t - 1 + hx;
+          const int gy = ty0[sel] - 1 + hy, gx = tx0[sel] - 1 + hx;
           if (gy >= 0 && gy < P.h && gx >= 0 && gx < P.w) {
-            const float4* g = reinterpret_cast<const float4*>(P.z + (((size_t)n * P.h + gy) * (size_t)P.w + gx) * P.z_cstride + P.z_coffset + c8 * 8);
+            const float4* g = reinterpret_cast<const float4*>(P.z + (((size_t)tn[sel] * P.h + gy) * (size_t)P.w + gx) * P.z_cstride + P.z_coffset + c8 * 8);
             za[u] = __ldg(g); zb[u] = __ldg(g + 1);
           }
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < 3; ++u) {
         const int i = tid + u * 512;
-        if (i < FHPX * 4) {
+        const int sel = i >= FHPX * 4 ? 1 : 0, il = i - sel * FHPX * 4;
+        if (i < nt * FHPX * 4) {
           uint4 hi, lo;
           fused_split8(za[u], zb[u], hi, lo);
-          sZh[(i & 3) * FZP + (i >> 2)] = hi;
-          sZl[(i & 3) * FZP + (i >> 2)] = lo;
+          uint4* zh = sel ? sZ1h : sZh;
+          zh[(il & 3) * FZP + (il >> 2)] = hi;
+          zh[4 * FZP + (il & 3) * FZP + (il >> 2)] = lo;
         }
       }
     }
     umma::fence_proxy_async();
     __syncthreads();
-    if (tr && tid == 0) tr[1] = clock64();   // z operand ready
+    if (tr && tid == 0) tr[1] = clock64();   // z operands ready
 
-    auto issue_window = [&](int q) {
-      const int wy0 = y0t - FWR + (int)rintf(fminf(fmaxf(flc.y, -4096.f), 4096.f));
-      const int wx0 = x0t - FWR + (int)rintf(fminf(fmaxf(flc.x, -4096.f), 4096.f));
-      const int slot = q & 1;
+    // window of global quarter k (tile k >> 2 of the round, K quarter k & 3) into slot k & 1
+    auto issue_window = [&](int k) {
+      const int u = k >> 2, q = k & 3;
+      const int wy0 = ty0[u] - FWR + (int)rintf(fminf(fmaxf(flc[u].y, -4096.f), 4096.f));
+      const int wx0 = tx0[u] - FWR + (int)rintf(fminf(fmaxf(flc[u].x, -4096.f), 4096.f));
+      const int slot = k & 1;
       s_org[slot] = make_int2(wy0, wx0);
       umma::mbar_arrive_expect_tx(&win_full[slot], (uint32_t)FWIN_BYTES);
-      umma::tma_load_4d(sWinP(slot), &tmap, &win_full[slot], 8 * q, wx0, wy0, n);                    // group 2q
-      umma::tma_load_4d(sWinP(slot) + FWPLANE * 4, &tmap, &win_full[slot], 8 * q + 4, wx0, wy0, n);   // group 2q + 1
+      umma::tma_load_4d(sWinP(slot), &tmap, &win_full[slot], 8 * q, wx0, wy0, tn[u]);                    // group 2q
+      umma::tma_load_4d(sWinP(slot) + FWPLANE * 4, &tmap, &win_full[slot], 8 * q + 4, wx0, wy0, tn[u]);   // group 2q + 1
     };
     if (warp == 0) {
       if (umma::elect_one()) {
         umma::fence_after_sync();
-        load_sixth(1);     // slot 1 (= window B of the previous tile) is free since the tile-end barrier
-        issue_window(0);   // window A is not needed by phase H: the first quarter's window lands behind the heads GEMM
-        const uint64_t dZh = umma::make_desc(umma::smem_u32(sZh), FZP * 16, FHW * 16), dZl = umma::make_desc(umma::smem_u32(sZl), FZP * 16, FHW * 16);
+        load_sixth(1);     // slot 1 (= window B of the previous round) is free since the round-end barrier
+        const uint64_t dZh = umma::make_desc(umma::smem_u32(sZh), FZP * 16, FHW * 16), dZl = umma::make_desc(umma::smem_u32(sZh + 4 * FZP), FZP * 16, FHW * 16);
+        const uint64_t dYh = umma::make_desc(umma::smem_u32(sZ1h), FZP * 16, FHW * 16), dYl = umma::make_desc(umma::smem_u32(sZ1h + 4 * FZP), FZP * 16, FHW * 16);
         const uint32_t zhl = (uint32_t)dZh, zhh = (uint32_t)(dZh >> 32), zll = (uint32_t)dZl, zlh = (uint32_t)(dZl >> 32);
+        const uint32_t yhl = (uint32_t)dYh, yhh = (uint32_t)(dYh >> 32), yll = (uint32_t)dYl, ylh = (uint32_t)(dYl >> 32);
 #pragma unroll 1
         for (int s = 0; s < 6; ++s) {
           const int slot = s & 1;
-          umma::mbar_wait_safe(&w_full[slot], (uint32_t)((it * 3 + (s >> 1)) & 1));
+          umma::mbar_wait_safe(&w_full[slot], (uint32_t)((rd * 3 + (s >> 1)) & 1));
           if (tr && s == 0) tr[2] = clock64();   // first W sixth landed
           const uint64_t dWh = umma::make_desc(umma::smem_u32(sW(slot)), FNH * 16, 128);
           const uint64_t dWl = umma::make_desc(umma::smem_u32(sW(slot) + FWREC), FNH * 16, 128);
@@ -233,34 +261,61 @@ __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedPara
             const int ks = s * 3 + jj, tap = ks >> 1, half = ks & 1;
             const int ky = tap / 3, kx = tap - ky * 3;
             const uint32_t arec = (uint32_t)((2 * half) * FZP + ky * FHW + kx), brec = (uint32_t)(2 * jj * FNH);
-            const uint64_t dah = umma::desc_advance(zhl, zhh, arec), dal = umma::desc_advance(zll, zlh, arec);
             const uint64_t dbh = umma::desc_advance(whl, whh, brec), dbl = umma::desc_advance(wll, wlh, brec);
+            const uint64_t dah = umma::desc_advance(zhl, zhh, arec), dal = umma::desc_advance(zll, zlh, arec);
             umma::mma_bf16(taddr, dah, dbh, idesc_h, ks != 0 ? 1u : 0u);
             umma::mma_bf16(taddr, dal, dbh, idesc_h, 1u);
             umma::mma_bf16(taddr, dah, dbl, idesc_h, 1u);
+            if (nt == 2) {   // the second tile of the round reuses the sixth while it is resident
+              const uint64_t dch = umma::desc_advance(yhl, yhh, arec), dcl = umma::desc_advance(yll, ylh, arec);
+              umma::mma_bf16(taddr + (uint32_t)FNH, dch, dbh, idesc_h, ks != 0 ? 1u : 0u);
+              umma::mma_bf16(taddr + (uint32_t)FNH, dcl, dbh, idesc_h, 1u);
+              umma::mma_bf16(taddr + (uint32_t)FNH, dch, dbl, idesc_h, 1u);
+            }
           }
           umma::mma_commit(&w_empty[slot]);
           if (s == 5) umma::mma_commit(&hacc_full);
-          if (s >= 1) {   // sixth s-1 is consumed: refill its slot with sixth s+1, or (s == 5) the NEXT tile's first sixth
-            umma::mbar_wait_safe(&w_empty[(s - 1) & 1], (uint32_t)((it * 3 + ((s - 1) >> 1)) & 1));
+          if (s >= 1) {   // sixth s-1 is consumed: refill its slot with sixth s+1, or (s == 5) the NEXT round's first sixth
+            umma::mbar_wait_safe(&w_empty[(s - 1) & 1], (uint32_t)((rd * 3 + ((s - 1) >> 1)) & 1));
             if (s < 5) load_sixth(s + 1);
-            else if (it + 1 < my_tiles) load_sixth(0);
+            else if (rd + 1 < rounds) load_sixth(0);
           }
         }
       }
       __syncwarp();
     }
 
-    // ================================================================ phase S
-    umma::mbar_wait_safe(&hacc_full, (uint32_t)(it & 1));   // heads accumulator complete; z and W slot 1 are free
+    // ================================================================ phase S: 4 quarters per tile, tiles back to back
+    umma::mbar_wait_safe(&hacc_full, (uint32_t)(rd & 1));   // heads accumulators complete; both z operands and W slot 1 are free
     umma::fence_after_sync();
-    if (tr && tid == 0) tr[3] = clock64();     // heads GEMM done
+    if (tr && tid == 0) tr[3] = clock64();     // heads GEMMs done
+    const int nk = 4 * nt;
     if (warp < 4) {
+      // epilogue of tile u of the round: thread = pixel = TMEM lane
+      auto epilogue = [&](int u) {
+        umma::mbar_wait_safe(&dacc_full, (uint32_t)((ntile + u) & 1));
+        umma::fence_after_sync();
+        float v[32];
+        umma::tmem_ld32(dacc + ((uint32_t)(32 * warp) << 16), v);
+        umma::fence_before_sync();
+        umma::mbar_arrive(&dacc_empty);    // the accumulator may be overwritten by the next tile's first quarter
+        const int y = ty0[u] + (tid >> 3), x = tx0[u] + (tid & 7);
+        if (y < P.h && x < P.w) {
+          const size_t pix = ((size_t)tn[u] * P.h + y) * (size_t)P.w + x;
+          float* op = P.out + pix * P.out_cstride + P.out_coffset;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(op + 4 * j) = make_float4(v[4 * j] + s_dbias[4 * j], v[4 * j + 1] + s_dbias[4 * j + 1],
+                                                                 v[4 * j + 2] + s_dbias[4 * j + 2], v[4 * j + 3] + s_dbias[4 * j + 3]);
+        }
+      };
       if (warp == 0) {
-        if (umma::elect_one()) issue_window(1);   // window B shares W slot 1: free now that the heads GEMM is done
+        if (umma::elect_one()) { issue_window(0); issue_window(1); }
         __syncwarp();
-        for (int q = 0; q < 4; ++q) {
-          umma::mbar_wait_safe(&a_full, (uint32_t)(q & 1));
+        for (int k = 0; k < nk; ++k) {
+          const int q = k & 3;
+          umma::mbar_wait_safe(&a_full, (uint32_t)((kq + k) & 1));
+          if (k == 4) umma::mbar_wait_safe(&dacc_empty, (uint32_t)(ntile & 1));   // tile 0's result has left TMEM (all 4 warps)
           umma::fence_after_sync();
           if (umma::elect_one()) {
             const uint64_t dAh = umma::make_desc(umma::smem_u32(sAh), FAP * 16, 128), dAl = umma::make_desc(umma::smem_u32(sAl), FAP * 16, 128);
@@ -278,48 +333,37 @@ __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedPara
             }
             umma::mma_commit(&a_empty);
             if (q == 3) umma::mma_commit(&dacc_full);
-            if (q + 2 < 4) issue_window(q + 2);   // a_full(q): every sampler is done with window q, its slot is free
+            if (k + 2 < nk) issue_window(k + 2);   // a_full(k): every sampler is done with window k, its slot is free
           }
           __syncwarp();
+          if (q == 3) epilogue(k >> 2);   // warp 0's quarter of the tile's result (drained while the samplers go on)
         }
-      }
-      // ---- epilogue of this tile: thread = pixel = TMEM lane
-      umma::mbar_wait_safe(&dacc_full, (uint32_t)(it & 1));
-      umma::fence_after_sync();
-      float v[32];
-      umma::tmem_ld32(dacc + ((uint32_t)(32 * warp) << 16), v);
-      umma::fence_before_sync();
-      const int y = y0t + (tid >> 3), x = x0t + (tid & 7);
-      if (y < P.h && x < P.w) {
-        const size_t pix = ((size_t)n * P.h + y) * (size_t)P.w + x;
-        float* op = P.out + pix * P.out_cstride + P.out_coffset;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(op + 4 * j) = make_float4(v[4 * j] + s_dbias[4 * j], v[4 * j + 1] + s_dbias[4 * j + 1],
-                                                               v[4 * j + 2] + s_dbias[4 * j + 2], v[4 * j + 3] + s_dbias[4 * j + 3]);
+      } else {
+        for (int u = 0; u < nt; ++u) epilogue(u);   // warps 1-3 wait here from the start of phase S
       }
     } else {
       // ---- samplers: warp = (TMEM lane quadrant warp % 4, third j of the quarter's 18 samples); thread = pixel
       const int jthird = (warp - 4) >> 2;
       const int m = 32 * (warp & 3) + lane;
-      const int y = y0t + (m >> 3), x = x0t + (m & 7);
-      const bool valid = y < P.h && x < P.w;
-      const size_t pix = ((size_t)n * P.h + (valid ? y : 0)) * (size_t)P.w + (valid ? x : 0);
-      const float* img = P.x + (size_t)n * P.h * P.w * P.x_cstride + P.x_coffset;
-      const float2 fl = valid ? __ldg(reinterpret_cast<const float2*>(P.flow + pix * 2)) : make_float2(0.f, 0.f);
-      for (int q = 0; q < 4; ++q) {
+      for (int k = 0; k < nk; ++k) {
+        const int u = k >> 2, q = k & 3;
+        const int y = ty0[u] + (m >> 3), x = tx0[u] + (m & 7);
+        const bool valid = y < P.h && x < P.w;
+        const size_t pix = ((size_t)tn[u] * P.h + (valid ? y : 0)) * (size_t)P.w + (valid ? x : 0);
+        const float* img = P.x + (size_t)tn[u] * P.h * P.w * P.x_cstride + P.x_coffset;
+        const float2 fl = valid ? __ldg(reinterpret_cast<const float2*>(P.flow + pix * 2)) : make_float2(0.f, 0.f);
         // raw head outputs of this thread's 6 samples: 18 consecutive TMEM columns (dy, dx, m per sample)
         const int col = 54 * q + 18 * jthird;
         float raw[18];
-        umma::tmem_ld16(taddr + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col, raw);
-        umma::tmem_ld2(taddr + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(col + 16), raw + 16);
+        umma::tmem_ld16(taddr + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(u * FNH + col), raw);
+        umma::tmem_ld2(taddr + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(u * FNH + col + 16), raw + 16);
 #pragma unroll
         for (int i = 0; i < 18; ++i) raw[i] += s_hbias[col + i];
-        if (tr && tid == 128) tr[4 + 3 * q] = clock64();        // sampler: raw offsets in registers
-        umma::mbar_wait_safe(&win_full[q & 1], (uint32_t)((q >> 1) & 1));
-        if (tr && tid == 128) tr[5 + 3 * q] = clock64();        // window landed
-        const int2 org = s_org[q & 1];
-        const float4* win = reinterpret_cast<const float4*>(sWinP(q & 1));
+        if (tr && tid == 128) tr[4 + 3 * k] = clock64();        // sampler: raw offsets in registers
+        umma::mbar_wait_safe(&win_full[k & 1], (uint32_t)(((kq + k) >> 1) & 1));
+        if (tr && tid == 128) tr[5 + 3 * k] = clock64();        // window landed
+        const int2 org = s_org[k & 1];
+        const float4* win = reinterpret_cast<const float4*>(sWinP(k & 1));
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           const int kl = 3 * jthird + r;
@@ -357,10 +401,10 @@ __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedPara
             const float2 zz = make_float2(0.f, 0.f), mm = make_float2(smk[e], smk[e]);
             float2 a = zz, b = zz;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 kw = make_float2(sw[e][k], sw[e][k]);
-              a = __ffma2_rn(kw, make_float2(c[e][k].x, c[e][k].y), a);
-              b = __ffma2_rn(kw, make_float2(c[e][k].z, c[e][k].w), b);
+            for (int kk = 0; kk < 4; ++kk) {
+              const float2 kw = make_float2(sw[e][kk], sw[e][kk]);
+              a = __ffma2_rn(kw, make_float2(c[e][kk].x, c[e][kk].y), a);
+              b = __ffma2_rn(kw, make_float2(c[e][kk].z, c[e][kk].w), b);
             }
             a = __ffma2_rn(a, mm, zz); b = __ffma2_rn(b, mm, zz);
             sv[e][0] = a.x; sv[e][1] = a.y; sv[e][2] = b.x; sv[e][3] = b.y;
@@ -401,8 +445,8 @@ __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedPara
             fused_split_pair(sv[1][2], sv[1][3], rh.w, rl.w);
           }
           if (r == 0) {
-            if (q > 0) umma::mbar_wait_safe(&a_empty, (uint32_t)((q - 1) & 1));   // the MMAs of quarter q-1 have read the A stage
-            else if (tid - 128 < FAP) {   // z lived here during phase H: restore the zero K chunk of the stage
+            if (k > 0) umma::mbar_wait_safe(&a_empty, (uint32_t)((kq + k - 1) & 1));   // the MMAs of the previous quarter have read the A stage
+            else if (tid - 128 < FAP) {   // a z operand lived here during phase H: restore the zero K chunk of the stage
               sAh[9 * FAP + (tid - 128)] = make_uint4(0u, 0u, 0u, 0u);
               sAl[9 * FAP + (tid - 128)] = make_uint4(0u, 0u, 0u, 0u);
             }
@@ -412,16 +456,18 @@ __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedPara
         }
         umma::fence_proxy_async();
         umma::mbar_arrive(&a_full);
-        if (tr && tid == 128) tr[6 + 3 * q] = clock64();        // quarter sampled
+        if (tr && tid == 128) tr[6 + 3 * k] = clock64();        // quarter sampled
       }
       umma::fence_before_sync();
     }
-    __syncthreads();   // tile end: TMEM, the A stage, both windows / z / W slot 1 may be reused
+    kq += nk;
+    ntile += nt;
+    __syncthreads();   // round end: TMEM, the A stage, both windows / z operands / W slot 1 may be reused
     umma::fence_after_sync();
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(taddr, 256);
+  if (warp == 0) umma::tmem_dealloc(taddr, 512);
 }
 
 typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

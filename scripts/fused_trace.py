@@ -31,9 +31,9 @@ for _ in range(5):
 print(f"fused align 360x640: {min(ts):.1f} us/launch (L2 flushed), {sorted(ts)[2]:.1f} median")
 tr = torch.zeros(256, dtype=torch.int64, device='cuda')
 L.check(L.lib().crfp_dcn_align_fused_trace(C.byref(d), tr.data_ptr(), st)); torch.cuda.synchronize()
-t = tr.cpu().view(16, 16)
-for i in range(8):
+t = tr.cpu().view(8, 32)
+for i in range(6):
     r = t[i]; t0 = int(r[0])
-    q = "  ".join(f"q{k}: raw {int(r[4+3*k])-t0:6d} win {int(r[5+3*k])-t0:6d} done {int(r[6+3*k])-t0:6d}" for k in range(4))
+    q = "  ".join(f"k{k}: raw {int(r[4+3*k])-t0:6d} win {int(r[5+3*k])-t0:6d} done {int(r[6+3*k])-t0:6d}" for k in range(8) if int(r[6+3*k]))
     nxt = int(t[i + 1][0]) - t0
-    print(f"tile {i}: z {int(r[1])-t0:5d} W0 {int(r[2])-t0:5d} heads {int(r[3])-t0:6d} | {q} | next tile {nxt}")
+    print(f"round {i}: z {int(r[1])-t0:5d} W0 {int(r[2])-t0:5d} heads {int(r[3])-t0:6d} | {q} | next round {nxt}")
