@@ -659,7 +659,25 @@ def main():
                 extra.append({"workload": workload_config(wl, *WORKLOADS[wl][:2], WORKLOADS[wl][2], 1)["workload"],
                               "value": r["value"], "unit": "frames/s", "ms_per_step": r["ms_per_step"],
                               "e2e": {k: r["e2e"][k] for k in ("value", "wall_value", "ms_per_step")} if "e2e" in r else None,
-                              "dtype": "f32" if args.precision != "half" else "f16"})
+                              "precision": args.precision, "dtype": "f32" if args.precision != "half" else "f16"})
+
+        if not args.no_extras and args.precision == "tc" and not args.total_clips:
+            # the reduced-precision tier (north_star's "bf16" tier, <= 5e-3: tests/test_gpu_half.py) on the headline workload
+            try:
+                del model
+                torch.cuda.empty_cache()
+                mh = CRFP_DSV("cuda", mid_channels=32, precision="half").eval()
+                mh.load_state_dict(make_state_dict(seed=1), strict=True)
+                mh.to(dev)
+                r = measure(torch, dist, mh, args.workload, t, 1, 1, max(2, min(args.steps, 5)), 3, 1, 0, dev, not args.no_e2e)
+                extra.append({"workload": workload_config(args.workload, h, w, t, 1)["workload"], "precision": "half",
+                              "dtype": "f16 operands (one fp16 activation product x fp16 hi/lo split weights), fp32 storage and accumulation",
+                              "value": r["value"], "unit": "frames/s", "ms_per_step": r["ms_per_step"],
+                              "e2e": {k: r["e2e"][k] for k in ("value", "wall_value", "ms_per_step")} if "e2e" in r else None,
+                              "parity": "max-abs <= 5e-3 vs the reference goldens over 100 frames (tests/test_gpu_half.py)"})
+                model = mh
+            except Exception as e:  # noqa: BLE001
+                extra.append({"precision": "half", "unavailable": f"{type(e).__name__}: {e}"[:200]})
 
     cfg = workload_config(args.workload, h, w, t, n * calls, args.total_clips)
     prec = {"tc": "fp32 storage; dense contractions as 3 x bf16 split products on tcgen05 with fp32 TMEM accumulation "

@@ -17,7 +17,7 @@ ACT_NONE, ACT_LRELU, ACT_RELU, ACT_DCN_HEAD, ACT_TANH256 = 0, 1, 2, 3, 4
 SRC_PLAIN, SRC_UNSHUFFLE4 = 0, 1
 OUT_NHWC, OUT_SHUFFLE = 0, 1
 TC_OUT_BF16, TC_OUT_F32, TC_OUT_SHUFFLE_F32 = 0, 1, 2
-PREC_FP32, PREC_BF16, PREC_TC3 = 0, 1, 2
+PREC_FP32, PREC_BF16, PREC_TC3, PREC_HALF = 0, 1, 2, 3
 MAX_LAYERS = 72
 
 c_float_p = C.POINTER(C.c_float)
@@ -68,7 +68,8 @@ class ConvTc3Desc(C.Structure):
                 ("out_kind", C.c_int32), ("shuffle_r", C.c_int32), ("ndst", C.c_int32), ("head_split", C.c_int32),
                 ("dst", TcSrc * 2),
                 ("residual", C.c_void_p), ("res_cstride", C.c_int32), ("res_coffset", C.c_int32),
-                ("flow", C.c_void_p), ("post_scale", C.c_float), ("head_mag", C.c_float)]
+                ("flow", C.c_void_p), ("post_scale", C.c_float), ("head_mag", C.c_float),
+                ("half", C.c_int32), ("_pad", C.c_int32)]
 
 
 class WarpDesc(C.Structure):
@@ -100,7 +101,7 @@ class AlignFusedDesc(C.Structure):
                 ("heads_w", C.c_void_p), ("heads_b", C.c_void_p),
                 ("dcn_w_hi", C.c_void_p), ("dcn_w_lo", C.c_void_p), ("dcn_b", C.c_void_p),
                 ("out", C.c_void_p), ("out_cstride", C.c_int32), ("out_coffset", C.c_int32),
-                ("head_mag", C.c_float), ("_pad2", C.c_int32),
+                ("head_mag", C.c_float), ("half", C.c_int32),
                 ("dbg_y0", C.c_void_p), ("dbg_x0", C.c_void_p)]
 
 

@@ -172,6 +172,7 @@ struct Tc3Params {
   float head_mag, post_scale;
   int rows_per_cta;
   int ncat;         // ws kernel: hi | lo weights as one 64-wide B operand (2 MMAs per K step)
+  int half;         // CRFP_PREC_HALF: fp16 operands, activations as ONE product (no lo half), weights fp16 hi / lo
   long long* dbg;   // optional per-phase clock64 trace of CTA (0,0,0): [row][8] (debug / profiling only)
 };
 int tc3_cout_tile(int cout, int kc_real, int* nt, int* ntiles);
@@ -182,6 +183,8 @@ int launch_conv_wide(const ConvParams& p, cudaStream_t st);
 int launch_conv_thin(const ConvParams& p, cudaStream_t st);
 int launch_conv(const ConvParams& p, cudaStream_t st);  // dispatch on cout
 int launch_flow_warp(const crfp_warp_desc& d, cudaStream_t st);
+int launch_flow_warp_l1(int n, int h, int w, const float* flow, const float* P, float* P_w, const float* state, float* cur0,
+                        float* cur1, float* cur2, cudaStream_t st);
 int launch_dcn(const crfp_dcn_desc& d, cudaStream_t st);
 int launch_dcn_tc(const crfp_dcn_desc& d, cudaStream_t st);
 int launch_dcn_tc3(const crfp_dcn_desc& d, const void* w_lo, const float* flow_hint, cudaStream_t st);

@@ -129,6 +129,38 @@ __device__ __forceinline__ void tc3_issue_row_cat(uint64_t dAh, uint64_t dAl, ui
   }
 }
 
+// CRFP_PREC_HALF: the activation operand is ONE fp16 tile.  N-concatenated weights: a single N = 64 MMA per K step;
+// otherwise A x W_hi + A x W_lo.
+template <int KC>
+__device__ __forceinline__ void tc3_issue_row_half_cat(uint64_t dA, uint64_t dB, uint32_t s0, uint32_t s1, uint32_t s2,
+                                                       uint32_t idesc64, uint32_t taddr) {
+  const uint32_t al = (uint32_t)dA, ah = (uint32_t)(dA >> 32), bl = (uint32_t)dB, bh = (uint32_t)(dB >> 32);
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int ky = tap / 3, kx = tap % 3;
+    const uint32_t arow = (ky == 0 ? s0 : ky == 1 ? s1 : s2) + kx;
+#pragma unroll
+    for (int ks = 0; ks < KC / 2; ++ks)
+      umma::mma_bf16(taddr, umma::desc_advance(al, ah, arow + 2 * ks * T3WP), umma::desc_advance(bl, bh, (uint32_t)(tap * KC + 2 * ks) * 64),
+                     idesc64, (tap | ks) != 0 ? 1u : 0u);
+  }
+}
+__device__ __noinline__ void tc3_issue_row_half_generic(uint64_t dA, uint64_t dBh, uint64_t dBl, uint32_t s0, uint32_t s1, uint32_t s2,
+                                                        uint32_t NT, int KC, uint32_t idesc, uint32_t taddr) {
+  const uint32_t al = (uint32_t)dA, ah = (uint32_t)(dA >> 32);
+  const uint32_t bhl = (uint32_t)dBh, bhh = (uint32_t)(dBh >> 32), bll = (uint32_t)dBl, blh = (uint32_t)(dBl >> 32);
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const int ky = tap / 3, kx = tap - ky * 3;
+    uint32_t a = (ky == 0 ? s0 : ky == 1 ? s1 : s2) + kx, b = (uint32_t)(tap * KC) * NT;
+    for (int ks = 0; ks < KC / 2; ++ks, a += 2 * T3WP, b += 2 * NT) {
+      const uint64_t da = umma::desc_advance(al, ah, a);
+      umma::mma_bf16(taddr, da, umma::desc_advance(bhl, bhh, b), idesc, (tap | ks) != 0 ? 1u : 0u);
+      umma::mma_bf16(taddr, da, umma::desc_advance(bll, blh, b), idesc, 1u);
+    }
+  }
+}
+
 __device__ __noinline__ void tc3_issue_row_generic(uint64_t dAh, uint64_t dAl, uint64_t dBh, uint64_t dBl, uint32_t s0,
                                                    uint32_t s1, uint32_t s2, uint32_t NT, int KC, uint32_t idesc, uint32_t taddr, uint32_t leader) {
   const uint32_t ahl = (uint32_t)dAh, ahh = (uint32_t)(dAh >> 32), all_ = (uint32_t)dAl, alh = (uint32_t)(dAl >> 32);
@@ -423,7 +455,12 @@ constexpr int WS_EPI = 128, WS_NPROD = 192, WS_THREADS = 384, WS_SLOTS = 4;
 // channels of one pixel of one source; same (source, pixel, channel group) for every row, so all addressing is hoisted
 // out of the row loop).  The loads of row u+D are issued before row u is split and stored: D+1 rows of HBM latency
 // overlap with the conversion and with the wait for a free ring slot.
-template <int RPT, int D>
+// CRFP_PREC_HALF: 8 channels -> one record of fp16 (no lo half)
+__device__ __forceinline__ uint4 cvt8_f16(const float4 a, const float4 b) {
+  return make_uint4(umma::pack_f16(a.x, a.y), umma::pack_f16(a.z, a.w), umma::pack_f16(b.x, b.y), umma::pack_f16(b.z, b.w));
+}
+
+template <int RPT, int D, bool HALF>
 __device__ __forceinline__ void ws_producer_loop(const Tc3Params& P, uint4* sAh, uint4* sAl, int slot_recs, int n, int y_begin,
                                                  int rows_out, int x0, int ptid, uint64_t* full_bar, uint64_t* accf_bar,
                                                  long long* tr) {
@@ -490,10 +527,14 @@ __device__ __forceinline__ void ws_producer_loop(const Tc3Params& P, uint4* sAh,
         a.x *= f; a.y *= f; a.z *= f; a.w *= f;
         b.x *= f; b.y *= f; b.z *= f; b.w *= f;
       }
-      uint4 h, l;
-      split8(a, b, h, l);
-      hi[dst[k]] = h;
-      lo[dst[k]] = l;
+      if (HALF) {
+        hi[dst[k]] = cvt8_f16(a, b);
+      } else {
+        uint4 h, l;
+        split8(a, b, h, l);
+        hi[dst[k]] = h;
+        lo[dst[k]] = l;
+      }
     }
     umma::fence_proxy_async();
     umma::mbar_arrive(&full_bar[slot]);
@@ -506,6 +547,7 @@ __device__ __forceinline__ void ws_producer_loop(const Tc3Params& P, uint4* sAh,
   }
 }
 
+template <bool HALF>
 __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Params P) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full_bar[WS_SLOTS], accf_bar[2], acce_bar[2];
@@ -578,14 +620,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
     const int ptid = tid - 192;
     long long* tr = (trace_cta && ptid == 0) ? P.dbg + 1024 : nullptr;        // ws trace, role 1: producers
     if (P.kc_real <= 4)
-      ws_producer_loop<3, 2>(P, sAh, sAl, slot_recs, n, y_begin, rows_out, x0, ptid, full_bar, accf_bar, tr);
+      ws_producer_loop<3, 2, HALF>(P, sAh, sAl, slot_recs, n, y_begin, rows_out, x0, ptid, full_bar, accf_bar, tr);
     else
-      ws_producer_loop<6, 0>(P, sAh, sAl, slot_recs, n, y_begin, rows_out, x0, ptid, full_bar, accf_bar, tr);
+      ws_producer_loop<6, 0, HALF>(P, sAh, sAl, slot_recs, n, y_begin, rows_out, x0, ptid, full_bar, accf_bar, tr);
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ MMA issuers: warp 4 = even rows (accumulator
     // 0), warp 5 = odd rows (accumulator 1).  While one warp is blocked feeding the tensor pipe, the other one has
     // already passed the barriers of the next row, so the pipe never drains between rows.
-    const uint32_t idesc = umma::make_idesc_bf16(T3M, NT);
+    const uint32_t idesc = HALF ? umma::make_idesc_f16(T3M, NT) : umma::make_idesc_bf16(T3M, NT);
     const uint64_t dAh = umma::make_desc(umma::smem_u32(sAh), T3WP * 16, 128), dAl = umma::make_desc(umma::smem_u32(sAl), T3WP * 16, 128);
     const uint64_t dBh = umma::make_desc(umma::smem_u32(sWh), (uint32_t)NT * 16, 128), dBl = umma::make_desc(umma::smem_u32(sWl), (uint32_t)NT * 16, 128);
     long long* tr = (trace_cta && (tid & 31) == 0) ? P.dbg + 2048 : nullptr;  // role 2: MMA issuers
@@ -603,7 +645,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
         const uint32_t s0 = (uint32_t)((v & 3) * slot_recs), s1 = (uint32_t)(((v + 1) & 3) * slot_recs),
                        s2 = (uint32_t)(((v + 2) & 3) * slot_recs);
         const uint32_t acc = taddr + (uint32_t)b * ncols;
-        if (P.ncat && KC == 8)
+        if (HALF) {
+          if (P.ncat && KC == 8)
+            tc3_issue_row_half_cat<8>(dAh, umma::make_desc(umma::smem_u32(sWh), 64 * 16, 128), s0, s1, s2, umma::make_idesc_f16(T3M, 64), acc);
+          else if (P.ncat)
+            tc3_issue_row_half_cat<4>(dAh, umma::make_desc(umma::smem_u32(sWh), 64 * 16, 128), s0, s1, s2, umma::make_idesc_f16(T3M, 64), acc);
+          else
+            tc3_issue_row_half_generic(dAh, dBh, dBl, s0, s1, s2, (uint32_t)NT, KC, idesc, acc);
+        } else if (P.ncat && KC == 8)
           tc3_issue_row_cat<8>(dAh, dAl, umma::make_desc(umma::smem_u32(sWh), 64 * 16, 128), s0, s1, s2,
                                umma::make_idesc_bf16(T3M, 64), idesc, acc);
         else if (P.ncat)
@@ -754,7 +803,8 @@ int launch_conv_tc3(Tc3Params p, cudaStream_t st) {
   if (p.post_scale == 0.f) p.post_scale = 1.f;
   const int strips = ceil_div(p.w, T3M);
   const int per_seg = strips * p.n * p.ntiles;
-  static const bool use_v1 = (getenv("CRFP_TC3_V1") != nullptr);   // A/B switch: the non-specialised kernel
+  static const bool use_v1_env = (getenv("CRFP_TC3_V1") != nullptr);   // A/B switch: the non-specialised kernel
+  const bool use_v1 = use_v1_env && !p.half;                            // (it has no CRFP_PREC_HALF variant)
   for (int s = 0; s < p.nsrc; ++s)
     if (use_v1 && p.src_mode[s] != CRFP_SRC_PLAIN) return CRFP_ERR_UNSUPPORTED;
   if (!use_v1) {
@@ -770,10 +820,11 @@ int launch_conv_tc3(Tc3Params p, cudaStream_t st) {
     if (segs > ceil_div(p.h, 4)) segs = ceil_div(p.h, 4);
     p.rows_per_cta = ceil_div(p.h, segs);
     segs = ceil_div(p.h, p.rows_per_cta);
-    cudaError_t e = cudaFuncSetAttribute(conv_tc3_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    void (*kern)(const Tc3Params) = p.half ? conv_tc3_ws_kernel<true> : conv_tc3_ws_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
     dim3 grid(strips, segs, p.n * p.ntiles);
-    launch_k_ws(conv_tc3_ws_kernel, dim3(grid), dim3(WS_THREADS), (size_t)(smem), st, p);
+    launch_k_ws(kern, dim3(grid), dim3(WS_THREADS), (size_t)(smem), st, p);
     return check_launch();
   }
   const size_t smem = tc3_smem_bytes(p.kc_real, p.kc_total, p.nt, p.extra != nullptr);
@@ -830,6 +881,7 @@ static int tc3_fwd_impl(const crfp_conv_tc3_desc* d, long long* trace, crfp_stre
   if (d->act == CRFP_ACT_DCN_HEAD && !d->flow) return CRFP_ERR_NULL;
   if (d->out_kind == CRFP_TC_OUT_SHUFFLE_F32 && (d->shuffle_r < 1 || d->cout % (d->shuffle_r * d->shuffle_r))) return CRFP_ERR_BAD_SHAPE;
   p.dbg = trace;
+  p.half = d->half ? 1 : 0;
   return launch_conv_tc3(p, (cudaStream_t)stream);
 }
 

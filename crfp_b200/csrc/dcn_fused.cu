@@ -95,6 +95,8 @@ __device__ __forceinline__ void fused_split_pair(float a, float b, uint32_t& hi,
   lo = umma::pack_bf16(a - __bfloat162float(h0), b - __bfloat162float(h1));
 }
 
+// HALF = CRFP_PREC_HALF: every activation operand (z, the modulated columns) is ONE fp16 tile, the weights are fp16 hi / lo
+template <bool HALF>
 __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t w_full[2], w_empty[2], win_full[2], a_full, a_empty, hacc_full, dacc_full, dacc_empty;
@@ -157,7 +159,8 @@ __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedPara
   const int rem0 = rem_base + bx, rem1 = rem_base + G + bx;
   const int rounds = full_rounds + (rem0 < total ? 1 : 0);
 
-  const uint32_t idesc_h = umma::make_idesc_bf16(128, FNH), idesc_d = umma::make_idesc_bf16(128, 32);
+  const uint32_t idesc_h = HALF ? umma::make_idesc_f16(128, FNH) : umma::make_idesc_bf16(128, FNH);
+  const uint32_t idesc_d = HALF ? umma::make_idesc_f16(128, 32) : umma::make_idesc_bf16(128, 32);
   // the W stream is owned by ONE thread (warp 0's elected lane); sixth s of a round lands in slot s & 1
   auto load_sixth = [&](int s) {
     umma::mbar_arrive_expect_tx(&w_full[s & 1], (uint32_t)FWSLOT);
@@ -217,11 +220,16 @@ __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedPara
         const int i = tid + u * 512;
         const int sel = i >= FHPX * 4 ? 1 : 0, il = i - sel * FHPX * 4;
         if (i < nt * FHPX * 4) {
-          uint4 hi, lo;
-          fused_split8(za[u], zb[u], hi, lo);
           uint4* zh = sel ? sZ1h : sZh;
-          zh[(il & 3) * FZP + (il >> 2)] = hi;
-          zh[4 * FZP + (il & 3) * FZP + (il >> 2)] = lo;
+          if (HALF) {
+            zh[(il & 3) * FZP + (il >> 2)] = make_uint4(umma::pack_f16(za[u].x, za[u].y), umma::pack_f16(za[u].z, za[u].w),
+                                                        umma::pack_f16(zb[u].x, zb[u].y), umma::pack_f16(zb[u].z, zb[u].w));
+          } else {
+            uint4 hi, lo;
+            fused_split8(za[u], zb[u], hi, lo);
+            zh[(il & 3) * FZP + (il >> 2)] = hi;
+            zh[4 * FZP + (il & 3) * FZP + (il >> 2)] = lo;
+          }
         }
       }
     }
@@ -264,12 +272,12 @@ __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedPara
             const uint64_t dbh = umma::desc_advance(whl, whh, brec), dbl = umma::desc_advance(wll, wlh, brec);
             const uint64_t dah = umma::desc_advance(zhl, zhh, arec), dal = umma::desc_advance(zll, zlh, arec);
             umma::mma_bf16(taddr, dah, dbh, idesc_h, ks != 0 ? 1u : 0u);
-            umma::mma_bf16(taddr, dal, dbh, idesc_h, 1u);
+            if (!HALF) umma::mma_bf16(taddr, dal, dbh, idesc_h, 1u);
             umma::mma_bf16(taddr, dah, dbl, idesc_h, 1u);
             if (nt == 2) {   // the second tile of the round reuses the sixth while it is resident
               const uint64_t dch = umma::desc_advance(yhl, yhh, arec), dcl = umma::desc_advance(yll, ylh, arec);
               umma::mma_bf16(taddr + (uint32_t)FNH, dch, dbh, idesc_h, ks != 0 ? 1u : 0u);
-              umma::mma_bf16(taddr + (uint32_t)FNH, dcl, dbh, idesc_h, 1u);
+              if (!HALF) umma::mma_bf16(taddr + (uint32_t)FNH, dcl, dbh, idesc_h, 1u);
               umma::mma_bf16(taddr + (uint32_t)FNH, dch, dbl, idesc_h, 1u);
             }
           }
@@ -328,7 +336,7 @@ __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedPara
               const uint64_t dah = umma::desc_advance(ahl, ahh, 2 * ks * FAP), dal = umma::desc_advance(all_, alh, 2 * ks * FAP);
               const uint64_t dbh = umma::desc_advance(bhl, bhh, 2 * ks * 32), dbl = umma::desc_advance(bll, blh, 2 * ks * 32);
               umma::mma_bf16(dacc, dah, dbh, idesc_d, (q | ks) != 0 ? 1u : 0u);
-              umma::mma_bf16(dacc, dal, dbh, idesc_d, 1u);
+              if (!HALF) umma::mma_bf16(dacc, dal, dbh, idesc_d, 1u);
               umma::mma_bf16(dacc, dah, dbl, idesc_d, 1u);
             }
             umma::mma_commit(&a_empty);
@@ -439,10 +447,15 @@ __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedPara
           }
           uint4 rh = make_uint4(0u, 0u, 0u, 0u), rl = rh;
           if (valid) {
-            fused_split_pair(sv[0][0], sv[0][1], rh.x, rl.x);
-            fused_split_pair(sv[0][2], sv[0][3], rh.y, rl.y);
-            fused_split_pair(sv[1][0], sv[1][1], rh.z, rl.z);
-            fused_split_pair(sv[1][2], sv[1][3], rh.w, rl.w);
+            if (HALF) {
+              rh = make_uint4(umma::pack_f16(sv[0][0], sv[0][1]), umma::pack_f16(sv[0][2], sv[0][3]),
+                              umma::pack_f16(sv[1][0], sv[1][1]), umma::pack_f16(sv[1][2], sv[1][3]));
+            } else {
+              fused_split_pair(sv[0][0], sv[0][1], rh.x, rl.x);
+              fused_split_pair(sv[0][2], sv[0][3], rh.y, rl.y);
+              fused_split_pair(sv[1][0], sv[1][1], rh.z, rl.z);
+              fused_split_pair(sv[1][2], sv[1][3], rh.w, rl.w);
+            }
           }
           if (r == 0) {
             if (k > 0) umma::mbar_wait_safe(&a_empty, (uint32_t)((kq + k - 1) & 1));   // the MMAs of the previous quarter have read the A stage
@@ -452,7 +465,7 @@ __global__ void __launch_bounds__(512, 1) dcn_align_fused_kernel(const FusedPara
             }
           }
           sAh[kl * FAP + m] = rh;
-          sAl[kl * FAP + m] = rl;
+          if (!HALF) sAl[kl * FAP + m] = rl;
         }
         umma::fence_proxy_async();
         umma::mbar_arrive(&a_full);
@@ -514,13 +527,14 @@ int launch_align_fused(const crfp_align_fused_desc& d, cudaStream_t st, long lon
   p.head_mag = d.head_mag;
   p.dbg_y0 = d.dbg_y0; p.dbg_x0 = d.dbg_x0;
   p.trace = trace;
-  cudaError_t e = cudaFuncSetAttribute(dcn_align_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
+  void (*kern)(const FusedParams, const CUtensorMap) = d.half ? dcn_align_fused_kernel<true> : dcn_align_fused_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
   if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   const int total = ceil_div(d.w, FTW) * ceil_div(d.h, FTH) * d.n;
   const int grid = total < sms ? total : sms;
-  launch_k_ws(dcn_align_fused_kernel, dim3(grid), dim3(512), (size_t)FUSED_SMEM, st, p, tmap);
+  launch_k_ws(kern, dim3(grid), dim3(512), (size_t)FUSED_SMEM, st, p, tmap);
   return check_launch();
 }
 

@@ -142,7 +142,9 @@ struct CB {
   }
   // TC3 precision: the same layer on the tensor cores (3 x bf16 split) when it is eligible
   bool tc3_eligible() const {
-    if (!W_ || li_ < 0 || W_->precision != CRFP_PREC_TC3 || !W_->layer_tc[li_].w_hi || !W_->layer_tc[li_].w_lo) return false;
+    if (!W_ || li_ < 0 || (W_->precision != CRFP_PREC_TC3 && W_->precision != CRFP_PREC_HALF) || !W_->layer_tc[li_].w_hi ||
+        !W_->layer_tc[li_].w_lo)
+      return false;
     if (p.epi != EPI_STD || p.out_bf16 || p.cout <= 4) return false;
     int kc = 0;
     for (int s = 0; s < p.nsrc; ++s) {
@@ -183,6 +185,9 @@ struct CB {
     }
     t.residual = p.residual; t.res_cstride = p.res_cstride; t.res_coffset = p.res_coffset;
     t.flow = p.flow; t.head_split = p.head_split; t.head_mag = p.head_mag; t.post_scale = p.post_scale;
+    // CRFP_PREC_HALF keeps the flow network at the full 3-product split (its weights stay bf16-packed): the flow is
+    // 256 * tanh(.) and feeds every warp and every DCN offset
+    t.half = (W_->precision == CRFP_PREC_HALF && li_ > L_FNET_F2) ? 1 : 0;
     return launch_conv_tc3(t, st);
   }
   CB& act(int a) { p.act = a; return *this; }
@@ -480,8 +485,10 @@ static int run_heads_dcn(const crfp_dsv_weights* W, int n, int h1, int w1, const
                          const float* P, float* A, int l_heads, int l_dcn, cudaStream_t st) {
   static const bool head_epi = (getenv("CRFP_HEAD_EPI") != nullptr);
   static const bool no_fused = (getenv("CRFP_ALIGN_UNFUSED") != nullptr);   // A/B switch: heads conv + align kernel
-  const bool tc = W->precision == CRFP_PREC_TC3 && W->layer_tc[l_dcn].w_hi && W->layer_tc[l_dcn].w_lo;
-  if (tc && !no_fused && !head_epi && W->layer_tc[l_heads].w_fused && W->layer_tc[l_heads].b_fused) {
+  const bool half = W->precision == CRFP_PREC_HALF;
+  const bool tc = (W->precision == CRFP_PREC_TC3 || half) && W->layer_tc[l_dcn].w_hi && W->layer_tc[l_dcn].w_lo;
+  if (half && !(W->layer_tc[l_heads].w_fused && W->layer_tc[l_heads].b_fused)) return CRFP_ERR_NULL;   // half: fused kernel only
+  if (tc && ((!no_fused && !head_epi) || half) && W->layer_tc[l_heads].w_fused && W->layer_tc[l_heads].b_fused) {
     // ONE kernel: the offset / mask tensor stays in TMEM (dcn_fused.cu)
     crfp_align_fused_desc fd;
     memset(&fd, 0, sizeof(fd));
@@ -493,6 +500,7 @@ static int run_heads_dcn(const crfp_dsv_weights* W, int n, int h1, int w1, const
     fd.dcn_w_hi = W->layer_tc[l_dcn].w_hi; fd.dcn_w_lo = W->layer_tc[l_dcn].w_lo; fd.dcn_b = W->layer_tc[l_dcn].b;
     fd.out = A; fd.out_cstride = 32;
     fd.head_mag = 10.f;
+    fd.half = half ? 1 : 0;
     return launch_align_fused(fd, st);
   }
   const bool raw = tc && !head_epi;
@@ -871,16 +879,8 @@ extern "C" int crfp_dsv_frame(const crfp_dsv_frame_desc* d, const crfp_dsv_weigh
       // P = downsample(S0): pixel_unshuffle(4) + conv 64 -> 32                                (CRFP.py:1569)
       CRFP_TRY(CB(n, h1, w1).src(d->state_hr, 64, 4, 0, CRFP_SRC_UNSHUFFLE4).layer(W, L_DOWNSAMPLE).dst(f.P, 32, 32).run(st));
       // warps                                                                                 (CRFP.py:1570-1577)
-      crfp_warp_desc wd;
-      memset(&wd, 0, sizeof(wd));
-      wd.n = n; wd.h = h1; wd.w = w1; wd.c = 32; wd.x = f.P; wd.x_cstride = 32; wd.flow = f.flow_l1;
-      wd.out = f.P_w; wd.out_cstride = 32;
-      CRFP_TRY(launch_flow_warp(wd, st));
-      for (int k = 0; k < 3; ++k) {  // warped feat_lv{k} lands in channels 24..31 of level k's `cur`
-        wd.h = h1; wd.w = w1; wd.c = 8; wd.x = d->state_l1; wd.x_cstride = 24; wd.x_coffset = 8 * k; wd.flow = f.flow_l1;
-        wd.out = f.cur[k]; wd.out_cstride = 32; wd.out_coffset = 24;
-        CRFP_TRY(launch_flow_warp(wd, st));
-      }
+      // P -> P_w and the warped feat_lv{k} (channels 24..31 of level k's `cur`): one launch for all four warps
+      CRFP_TRY(launch_flow_warp_l1(n, h1, w1, f.flow_l1, f.P, f.P_w, d->state_l1, f.cur[0], f.cur[1], f.cur[2], st));
       const float* fg_l1 = nullptr;
       if (d->fg) {  // streaming regional mask at L1: bilinear x0.25                            (CRFP_test.py:2299-2300)
         if (n > 1 && d->fg_clip_stride != (long long)H * Wd) return CRFP_ERR_UNSUPPORTED;

@@ -59,6 +59,55 @@ __global__ void __launch_bounds__(256) flow_warp_kernel(const crfp_warp_desc D) 
   *reinterpret_cast<float4*>(D.out + (size_t)pix * D.out_cstride + D.out_coffset + q * 4) = acc;
 }
 
+// The four L1 warps of a CRFP_DSV frame in ONE launch (model/CRFP.py:1570-1577): P (32 ch) -> P_w and the three 8-channel
+// slices of the recurrent L1 state -> channels 24..31 of level k's input, all along the same flow.  One thread per
+// (pixel, 4-channel quad); 14 quads per pixel; the same coordinate arithmetic as flow_warp_kernel.
+__global__ void __launch_bounds__(256) flow_warp_l1_kernel(int n, int h, int w, const float* __restrict__ flow,
+                                                           const float* __restrict__ P, float* __restrict__ P_w,
+                                                           const float* __restrict__ state, float* __restrict__ cur0,
+                                                           float* __restrict__ cur1, float* __restrict__ cur2) {
+  pdl_trigger();
+  pdl_wait();
+  const long long total = (long long)n * h * w * 14;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int q = (int)(idx % 14);
+  const long long pix = idx / 14;
+  const int x = (int)(pix % w);
+  const int y = (int)((pix / w) % h);
+  const int b = (int)(pix / ((long long)w * h));
+  const float2 fl = __ldg(reinterpret_cast<const float2*>(flow + pix * 2));
+  const float ix = warp_coord(x, fl.x, w), iy = warp_coord(y, fl.y, h);
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+  const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix;
+  const float wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
+  const float* base;
+  float* out;
+  int cs;
+  if (q < 8) { base = P + (size_t)b * h * w * 32 + q * 4; cs = 32; out = P_w + pix * 32 + q * 4; }
+  else {
+    const int j = q - 8, k = j >> 1;
+    base = state + (size_t)b * h * w * 24 + j * 4; cs = 24;
+    out = (k == 0 ? cur0 : k == 1 ? cur1 : cur2) + pix * 32 + 24 + (j & 1) * 4;
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool vx0 = (x0 >= 0 && x0 < w), vx1 = (x1 >= 0 && x1 < w);
+  const bool vy0 = (y0 >= 0 && y0 < h), vy1 = (y1 >= 0 && y1 < h);
+#define CRFP_ACC(vy, vx, yy, xx, wgt)                                                                  \
+  if ((vy) && (vx)) {                                                                                  \
+    const float4 t = __ldg(reinterpret_cast<const float4*>(base + ((size_t)(yy) * w + (xx)) * cs));   \
+    const float w_ = (wgt);                                                                            \
+    acc.x += t.x * w_; acc.y += t.y * w_; acc.z += t.z * w_; acc.w += t.w * w_;                        \
+  }
+  CRFP_ACC(vy0, vx0, y0, x0, wx0 * wy0)
+  CRFP_ACC(vy0, vx1, y0, x1, wx1 * wy0)
+  CRFP_ACC(vy1, vx0, y1, x0, wx0 * wy1)
+  CRFP_ACC(vy1, vx1, y1, x1, wx1 * wy1)
+#undef CRFP_ACC
+  *reinterpret_cast<float4*>(out) = acc;
+}
+
 __global__ void __launch_bounds__(256) flow_warp_indices_kernel(int n, int h, int w, const float* __restrict__ flow,
                                                                 int32_t* __restrict__ x0, int32_t* __restrict__ y0) {
   pdl_trigger();
@@ -265,6 +314,14 @@ int launch_flow_warp_bf16(const crfp_warp_desc& d, cudaStream_t st) {
 int launch_flow_up2_dual(int n, int h, int w, const float* flow, float* out_f32, void* out_bf8, cudaStream_t st) {
   const long long total = (long long)n * 4 * h * w;
   launch_k(flow_up2_dual_kernel, dim3(grid1d(total)), dim3(256), (size_t)(0), st, n, h, w, flow, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf8));
+  return check_launch();
+}
+
+int launch_flow_warp_l1(int n, int h, int w, const float* flow, const float* P, float* P_w, const float* state, float* cur0,
+                        float* cur1, float* cur2, cudaStream_t st) {
+  const long long total = (long long)n * h * w * 14;
+  if (total == 0) return CRFP_OK;
+  launch_k(flow_warp_l1_kernel, dim3(grid1d(total)), dim3(256), (size_t)(0), st, n, h, w, flow, P, P_w, state, cur0, cur1, cur2);
   return check_launch();
 }
 

@@ -65,9 +65,10 @@ class _CRFPBase(nn.Module):
     def __init__(self, device, mid_channels=16, y_only=False, hr_dcn=True, offset_prop=True, spynet_pretrained=None,
                  precision="tc"):
         super().__init__()
-        if precision not in ("fp32", "tc"):
-            raise L.CrfpError("precision must be 'tc' (fp32 storage, tcgen05 3 x bf16 split contractions, fp32-grade) "
-                              "or 'fp32' (all-SIMT fp32 FFMA)")
+        if precision not in ("fp32", "tc", "half"):
+            raise L.CrfpError("precision must be 'tc' (fp32 storage, tcgen05 3 x bf16 split contractions, fp32-grade), "
+                              "'fp32' (all-SIMT fp32 FFMA) or 'half' (reduced-precision tier: one fp16 activation product "
+                              "against fp16 hi / lo split weights, fp32 storage and accumulation; <= 5e-3)")
         self.precision = precision
         if mid_channels != 32:
             raise L.CrfpError("crfp_b200 implements the shipped configuration mid_channels=32 (main.py:34)")
@@ -95,8 +96,10 @@ class _CRFPBase(nn.Module):
         # alias_output = True (or an explicit `out=` buffer) returns the graph-owned tensor itself, overwritten by the
         # next replay on the same inputs — the cudagraph-style contract, for callers that consume each result at once.
         self.alias_output = False
-        # second stream for the off-chain work of a frame (crfp_dsv_frame_desc.aux_stream); CRFP_AUX=0 switches it off
-        self.use_aux_stream = os.environ.get("CRFP_AUX", "1") != "0"
+        # second stream for the off-chain work of a frame (crfp_dsv_frame_desc.aux_stream).  Opt-in (CRFP_AUX=1): measured
+        # on B200 at R-lit it is 1 % SLOWER than one stream (351.8 vs 354.9 fps) — the tensor-core kernels hold every SM's
+        # registers, so forked kernels only run in their launch gaps and lengthen the critical path's tail
+        self.use_aux_stream = os.environ.get("CRFP_AUX", "0") == "1"
         self._aux = None
         self._graphs = collections.OrderedDict()   # key -> dict(graphs, out, launches)
         self._seen_key = None
@@ -139,22 +142,24 @@ class _CRFPBase(nn.Module):
         table = L.layer_table(self.VARIANT)
         W = L.DsvWeights()
         W.mid_channels, W.nlayers = self.mid_channels, len(table)
-        W.precision = L.PREC_TC3 if self.precision == "tc" else L.PREC_FP32
+        W.precision = {"tc": L.PREC_TC3, "half": L.PREC_HALF, "fp32": L.PREC_FP32}[self.precision]
+        wdt = torch.float16 if self.precision == "half" else torch.bfloat16
         W.variant = L.VARIANTS[self.VARIANT]
         keep = []
         for i, info in enumerate(table):
             w, b = pack_layer(info, sd)
             keep.append((w, b))
             W.layer[i].w, W.layer[i].b = w.data_ptr(), b.data_ptr()
-            if info["tc"] and self.precision == "tc":
-                hi, lo, bt, wx = pack_layer_tc3(info, sd)
+            if info["tc"] and self.precision in ("tc", "half"):
+                # the flow network keeps the 3 x bf16 split in every precision (crfp_dsv_frame routes it accordingly)
+                hi, lo, bt, wx = pack_layer_tc3(info, sd, torch.bfloat16 if info["key"].startswith("spynet.") else wdt)
                 keep.append((hi, lo, bt, wx))
                 W.layer_tc[i].w_hi, W.layer_tc[i].w_lo, W.layer_tc[i].b = hi.data_ptr(), lo.data_ptr(), bt.data_ptr()
                 if wx is not None:
                     W.layer_tc[i].w_extra = wx.data_ptr()
                 if info["kind"] == 2 and info["cout"] == 216:     # L1 offset / mask heads: the fused align kernel's packing
                     wf, bf = pack_align_heads(sd[info["key"] + ".weight"], sd[info["key"] + ".bias"],
-                                              sd[info["key2"] + ".weight"], sd[info["key2"] + ".bias"])
+                                              sd[info["key2"] + ".weight"], sd[info["key2"] + ".bias"], wdt)
                     keep.append((wf, bf))
                     W.layer_tc[i].w_fused, W.layer_tc[i].b_fused = wf.data_ptr(), bf.data_ptr()
         self._packed = (key, keep, W)

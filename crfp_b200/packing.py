@@ -140,14 +140,15 @@ def tc3_cout_tile(cout: int, cin: int):
     return None
 
 
-def split_bf16(x: torch.Tensor):
-    """x (fp32) -> (hi, lo) bf16 with hi = bf16(x), lo = bf16(x - hi)."""
-    hi = x.to(torch.bfloat16)
-    lo = (x - hi.to(torch.float32)).to(torch.bfloat16)
+def split_bf16(x: torch.Tensor, dtype=torch.bfloat16):
+    """x (fp32) -> (hi, lo) of `dtype` (bf16: CRFP_PREC_TC3; fp16: CRFP_PREC_HALF) with hi = dtype(x), lo = dtype(x - hi)."""
+    hi = x.to(dtype)
+    lo = (x - hi.to(torch.float32)).to(dtype)
     return hi, lo
 
 
-def pack_conv_tc3(weight: torch.Tensor, bias: torch.Tensor, c_list, ci_lo: int = 0, extra: int = 0, modes=None):
+def pack_conv_tc3(weight: torch.Tensor, bias: torch.Tensor, c_list, ci_lo: int = 0, extra: int = 0, modes=None,
+                  dtype=torch.bfloat16):
     """OIHW fp32 -> (w_hi, w_lo bf16 [ntiles][9][kc][nt][8], bias fp32 [ntiles*nt], w_extra fp32 [9][extra][ntiles*nt])
     for crfp_conv3x3_tc3_fwd.  `c_list`: channels of the tensor-core sources (multiples of 8); `extra`: trailing
     input channels convolved on the CUDA cores (the 2 flow channels of dcn_block.0)."""
@@ -166,7 +167,7 @@ def pack_conv_tc3(weight: torch.Tensor, bias: torch.Tensor, c_list, ci_lo: int =
     assert all(i >= 0 for i in idx)
     wm[:cout, :k] = w[:, torch.tensor(idx, device=w.device)].reshape(cout, k, 9)
     packed = wm.view(ntiles, nt, kc, 8, 9).permute(0, 4, 2, 1, 3).contiguous()      # (tile, tap, kc, n, j)
-    hi, lo = split_bf16(packed)
+    hi, lo = split_bf16(packed, dtype)
     b = torch.zeros(ntiles * nt, device=w.device, dtype=torch.float32)
     b[:cout] = bias.detach().to(torch.float32)
     wx = None
@@ -185,15 +186,15 @@ def pack_dcn_tc(weight: torch.Tensor, bias: torch.Tensor, dg: int):
     return out.to(torch.bfloat16).contiguous(), b
 
 
-def pack_dcn_tc3(weight: torch.Tensor, bias: torch.Tensor, dg: int):
-    """DCNv2 weight -> (hi, lo) bf16 UMMA B operands [K/8][cout][8] + fp32 bias, for crfp_dcn_v2_tc3_fwd."""
+def pack_dcn_tc3(weight: torch.Tensor, bias: torch.Tensor, dg: int, dtype=torch.bfloat16):
+    """DCNv2 weight -> (hi, lo) bf16 (fp16: CRFP_PREC_HALF) UMMA B operands [K/8][cout][8] + fp32 bias, for crfp_dcn_v2_tc3_fwd."""
     wk, b = pack_dcn(weight, bias, dg)
     k, cout = wk.shape
-    hi, lo = split_bf16(wk.view(k // 8, 8, cout).permute(0, 2, 1).contiguous())
+    hi, lo = split_bf16(wk.view(k // 8, 8, cout).permute(0, 2, 1).contiguous(), dtype)
     return hi.contiguous(), lo.contiguous(), b
 
 
-def pack_align_heads(w_off: torch.Tensor, b_off: torch.Tensor, w_msk: torch.Tensor, b_msk: torch.Tensor):
+def pack_align_heads(w_off: torch.Tensor, b_off: torch.Tensor, w_msk: torch.Tensor, b_msk: torch.Tensor, dtype=torch.bfloat16):
     """dcn_offset (144,32,3,3) + dcn_mask (72,32,3,3) -> the B operand of crfp_dcn_align_fused's heads GEMM:
     bf16 [6 sixths][hi | lo][6 chunks][224][8] and fp32 bias [224].
     Column n = 3*s + {0: dy, 1: dx, 2: mask} for sample s = g*9 + t (offset channels 2s, 2s+1; mask channel s), 216..223
@@ -208,7 +209,7 @@ def pack_align_heads(w_off: torch.Tensor, b_off: torch.Tensor, w_msk: torch.Tens
     b[3 * s], b[3 * s + 1], b[3 * s + 2] = b_off.detach().float()[2 * s], b_off.detach().float()[2 * s + 1], b_msk.detach().float()[s]
     wk = w.permute(0, 2, 1).reshape(224, 288)                       # [n][K = tap*32 + c]
     chunks = wk.view(224, 36, 8).permute(1, 0, 2).contiguous()      # [kc][n][8]
-    hi, lo = split_bf16(chunks)
+    hi, lo = split_bf16(chunks, dtype)
     packed = torch.stack([hi.view(6, 6, 224, 8), lo.view(6, 6, 224, 8)], dim=1).contiguous()   # [sixth][hi|lo][6][224][8]
     return packed, b.contiguous()
 
@@ -224,11 +225,12 @@ def pack_layer_tc(info: dict, sd):
     return pack_conv_tc(w, b, info["c"], info["ci_lo"])
 
 
-def pack_layer_tc3(info: dict, sd):
-    """CRFP_PREC_TC3 packing of a layer with crfp_layer_info.tc != 0: (w_hi, w_lo, bias, w_extra or None)."""
+def pack_layer_tc3(info: dict, sd, dtype=torch.bfloat16):
+    """CRFP_PREC_TC3 (bf16) / CRFP_PREC_HALF (fp16) packing of a layer with crfp_layer_info.tc != 0:
+    (w_hi, w_lo, bias, w_extra or None)."""
     w, b = sd[info["key"] + ".weight"], sd[info["key"] + ".bias"]
     if info["tc"] == 2:
-        hi, lo, bb = pack_dcn_tc3(w, b, info["dg"])
+        hi, lo, bb = pack_dcn_tc3(w, b, info["dg"], dtype)
         return hi, lo, bb, None
     if info["kind"] == 2:
         w = torch.cat([w, sd[info["key2"] + ".weight"]], dim=0)
@@ -237,7 +239,7 @@ def pack_layer_tc3(info: dict, sd):
     extra = info["c"][-1] if info["c"][-1] % 8 else 0
     assert sum(c_tc) + extra == sum(info["c"]) and extra in (0, 2)
     m_tc = [m for c, m in zip(info["c"], info["mode"]) if c % 8 == 0]
-    return pack_conv_tc3(w, b, c_tc, info["ci_lo"], extra, m_tc)
+    return pack_conv_tc3(w, b, c_tc, info["ci_lo"], extra, m_tc, dtype)
 
 
 def pack_layer(info: dict, sd):

@@ -228,6 +228,8 @@ typedef struct {
   const float* flow;
   float post_scale;
   float head_mag;
+  int32_t half;    /* != 0: CRFP_PREC_HALF arithmetic (weight_hi / weight_lo are fp16, activations one fp16 product) */
+  int32_t _pad;
 } crfp_conv_tc3_desc;
 int crfp_conv3x3_tc3_fwd(const crfp_conv_tc3_desc* d, crfp_stream stream);
 /* profiling aid: same launch + a clock64 trace of CTA (0,0,0): trace[0..1] = kernel start / loop start, then per row
@@ -329,7 +331,7 @@ typedef struct {
   const void* dcn_w_lo;
   const float* dcn_b;
   float* out; int32_t out_cstride, out_coffset;
-  float head_mag; int32_t _pad2;
+  float head_mag; int32_t half;   /* half != 0: CRFP_PREC_HALF arithmetic (all packed weights fp16) */
   int32_t* dbg_y0; int32_t* dbg_x0;
 } crfp_align_fused_desc;
 int crfp_dcn_align_fused(const crfp_align_fused_desc* d, crfp_stream stream);
@@ -390,7 +392,7 @@ typedef struct {
   const float* b;
 } crfp_layer;
 
-enum { CRFP_PREC_FP32 = 0, CRFP_PREC_BF16 = 1, CRFP_PREC_TC3 = 2 };
+enum { CRFP_PREC_FP32 = 0, CRFP_PREC_BF16 = 1, CRFP_PREC_TC3 = 2, CRFP_PREC_HALF = 3 };
 /* model variants sharing every kernel and parameter name (model/CRFP.py): CRFP_DSV :1387 (24/8 split state),
  * CRFP :1101 (3-way concat, HR state warped before down-sampling), CRFP_simple :816 (2-way concat) */
 enum { CRFP_VARIANT_DSV = 0, CRFP_VARIANT_V15 = 1, CRFP_VARIANT_V13 = 2 };
@@ -409,6 +411,11 @@ typedef struct {
                            CRFP_PREC_TC3 : fp32 storage, the dense layers (cin <= 64) and the L1 DCN contraction on
                                            tcgen05 as 3 x bf16 split products with fp32 TMEM accumulation — fp32-grade
                                            (parity <= 1e-3), the default of the Python shell;
+                           CRFP_PREC_HALF: the reduced-precision tier (north_star's "bf16" tier, <= 5e-3): same kernels and fp32
+                                           storage as TC3, but every tensor-core ACTIVATION operand is rounded once to fp16
+                                           (11-bit mantissa; bf16's 8 bits measured 1.1e-2) and used as ONE product against
+                                           the fp16 hi / lo split weights: a third of TC3's MMAs and half its operand bytes
+                                           through shared memory; weights packed with dtype fp16;
                            CRFP_PREC_BF16: experimental, L1 layers with bf16 STORAGE (not parity-certified) */
   int32_t variant;      /* CRFP_VARIANT_DSV (CRFP_DSV, v18), CRFP_VARIANT_V15 (CRFP), CRFP_VARIANT_V13 (CRFP_simple) */
   crfp_layer layer[CRFP_DSV_MAX_LAYERS];
