@@ -274,7 +274,38 @@ def time_align_kernel(torch, h1, w1, precision, reps=12):
     return _events_avg_ms(torch, launch, reps), raw
 
 
-def time_conv_mix(torch, h1, w1, reps=4):
+def time_align_fused(torch, h1, w1, precision, reps=12):
+    """Average device time of crfp_dcn_align_fused (offset / mask heads + activations + DCNv2 @L1 in ONE kernel: what the
+    frame runs in the tensor-core precisions), 3 rotating input sets, cold launches."""
+    import ctypes as C
+    from crfp_b200 import _lib as L
+    from crfp_b200.packing import pack_align_heads, pack_dcn_tc3
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(0)
+    wdt = torch.float16 if precision == "half" else torch.bfloat16
+    nbuf = 3
+    zs = [torch.randn(1, h1, w1, 32, generator=g).to(dev) for _ in range(nbuf)]
+    xs = [torch.randn(1, h1, w1, 32, generator=g).to(dev) for _ in range(nbuf)]
+    fls = [(torch.randn(1, h1, w1, 2, generator=g) * 2.0).to(dev) for _ in range(nbuf)]
+    w_off = (torch.randn(144, 32, 3, 3, generator=g) * 0.02).to(dev)     # 10 * tanh(.) ~ a few pixels
+    w_msk = (torch.randn(72, 32, 3, 3, generator=g) * 0.05).to(dev)
+    wf, bf = pack_align_heads(w_off, torch.zeros(144, device=dev), w_msk, torch.zeros(72, device=dev), wdt)
+    hi, lo, bp = pack_dcn_tc3((torch.randn(32, 32, 3, 3, generator=g) * 0.05).to(dev), torch.zeros(32, device=dev), 8, wdt)
+    out = torch.empty(1, h1, w1, 32, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def launch(i):
+        k = i % nbuf
+        d = L.AlignFusedDesc(n=1, h=h1, w=w1, z=zs[k].data_ptr(), z_cstride=32, z_coffset=0, flow=fls[k].data_ptr(),
+                             x=xs[k].data_ptr(), x_cstride=32, x_coffset=0, heads_w=wf.data_ptr(), heads_b=bf.data_ptr(),
+                             dcn_w_hi=hi.data_ptr(), dcn_w_lo=lo.data_ptr(), dcn_b=bp.data_ptr(), out=out.data_ptr(),
+                             out_cstride=32, out_coffset=0, head_mag=10.0, half=int(precision == "half"))
+        L.check(L.lib().crfp_dcn_align_fused(C.byref(d), st), "dcn_align_fused")
+
+    return _events_avg_ms(torch, launch, reps)
+
+
+def time_conv_mix(torch, h1, w1, reps=4, precision="tc", with_heads=True):
     """The per-frame mix of tensor-core conv launches (conv_tc3_ws_kernel, the dominant kernel of the step): every L1
     layer shape of one steady-state frame through crfp_conv3x3_tc3_fwd.  Returns (avg ms per launch, launches,
     algorithmic bytes per launch = unique fp32 operands in + out, useful fp32 FLOP per launch)."""
@@ -287,6 +318,9 @@ def time_conv_mix(torch, h1, w1, reps=4):
     # (source channels, extra flow channels, cout, count per frame, output kind)
     layers = [([32, 32], 2, 32, 3, "nhwc"), ([32], 0, 32, 9, "nhwc"), ([32, 32], 0, 32, 5, "nhwc"),
               ([32], 0, 216, 3, "nhwc"), ([24], 0, 64, 1, "shuffle4"), ([32], 0, 64, 1, "shuffle4")]
+    if not with_heads:   # the fused align kernel computes the 216-channel heads itself: no such conv launch in the frame
+        layers = [l for l in layers if l[2] != 216]
+    wdt = torch.float16 if precision == "half" else torch.bfloat16
     bufs = [torch.randn(1, h1, w1, 32, device=dev) for _ in range(5)]   # 5 x 29.5 MB planes, rotated: > L2 together
     buf24 = torch.randn(1, h1, w1, 24, device=dev)
     flow = torch.randn(1, h1, w1, 2, device=dev)
@@ -299,7 +333,7 @@ def time_conv_mix(torch, h1, w1, reps=4):
     for srcs, extra, cout, count, kind in layers:
         cin = sum(srcs) + extra
         w = torch.randn(cout, cin, 3, 3, device=dev) * 0.05
-        hi, lo, bp, wx = pack_conv_tc3(w, torch.zeros(cout, device=dev), srcs, extra=extra)
+        hi, lo, bp, wx = pack_conv_tc3(w, torch.zeros(cout, device=dev), srcs, extra=extra, dtype=wdt)
         keep.append((hi, lo, bp, wx))
         for _ in range(count):
             d = L.ConvTc3Desc()
@@ -316,6 +350,7 @@ def time_conv_mix(torch, h1, w1, reps=4):
             if extra:
                 d.extra, d.w_extra = flow.data_ptr(), wx.data_ptr()
             d.post_scale, d.ndst = 1.0, 1
+            d.half = int(precision == "half")
             if kind == "shuffle4":
                 d.out_kind, d.shuffle_r = L.TC_OUT_SHUFFLE_F32, 4
                 d.dst[0] = L.TcSrc(ptr=out_hr.data_ptr(), c=4, cstride=4, coffset=0)
@@ -597,20 +632,45 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
-    a_ms, a_raw = time_align_kernel(torch, 2 * h, 2 * w, args.precision)
-    alg_bytes = ALIGN_BYTES_PER_L1_PX * (2 * h) * (2 * w)
-    a_ach = alg_bytes / (a_ms * 1e-3) / 1e9
-    a_traffic, a_src, a_cnt = dram_traffic_from_profiles(args.workload, r"dcn_tc3_ws_kernel|dcn_l1_kernel")
-    align = {"kernel": ("dcn_tc3_ws_kernel" if args.precision != "fp32" else "dcn_l1_kernel") + " (DCNv2 align @L1, C=32 dg=8" +
-                       (", head activations fused into the sampler)" if a_raw else ")"),
-             "bound": "hbm", "achieved": a_ach, "peak": peak, "unit": "GB/s", "frac": a_ach / peak,
-             "traffic": a_traffic,
-             "traffic_source": (f"dram__bytes_read+write per launch, mean of {a_cnt} launches, ncu, {a_src}" if a_traffic else
-                                "no committed ncu DRAM capture for this workload"),
-             "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": a_ms,
-             "timing": "kernel timed alone through the C ABI, CUDA events, 3 rotating input sets > L2"}
+    px1 = (2 * h) * (2 * w)
+    fused = args.precision != "fp32" and os.environ.get("CRFP_ALIGN_UNFUSED") is None and os.environ.get("CRFP_HEAD_EPI") is None
+    if fused:
+        # the align kernel of the tensor-core precisions: DCN_module's heads + activations + DCNv2 in one launch
+        a_ms = time_align_fused(torch, 2 * h, 2 * w, args.precision)
+        fused_bytes = (32 + 2 + 32 + 32) * 4 * px1           # z + flow + x in, aligned out: 392 B per L1 pixel
+        unfused_bytes = ALIGN_BYTES_PER_L1_PX * px1            # what the DCNv2 op alone moves when offsets / masks live in HBM
+        flop = (3 if args.precision == "tc" else 2) * 2 * 288 * (224 + 32) * px1   # issued 16-bit MMA FLOP (split products)
+        a_traffic, a_src, a_cnt = dram_traffic_from_profiles(args.workload, r"dcn_align_fused_kernel")
+        align = {"kernel": "dcn_align_fused_kernel (dcn_offset + dcn_mask convs, 10*tanh + flow / sigmoid, DCNv2 @L1 C=32 dg=8: "
+                           "the 216-channel offset / mask tensor stays in TMEM)",
+                 "bound": "tensor", "achieved": flop / (a_ms * 1e-3) / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
+                 "frac": flop / (a_ms * 1e-3) / 1e12 / bf16_peak,
+                 "note": "bound by the shared-memory pipe feeding small-N tcgen05 MMAs and the bilinear gather, not by HBM; "
+                         "the HBM view is kept below for continuity with the DCNv2-op figure of SURVEY.md 8(d)",
+                 "hbm": {"algorithmic_bytes_per_launch": fused_bytes, "achieved_gbs": fused_bytes / (a_ms * 1e-3) / 1e9,
+                         "frac_of_hbm_peak": fused_bytes / (a_ms * 1e-3) / 1e9 / peak,
+                         "dcnv2_op_equivalent_bytes": unfused_bytes,
+                         "dcnv2_op_equivalent_frac": unfused_bytes / (a_ms * 1e-3) / 1e9 / peak},
+                 "traffic": a_traffic,
+                 "traffic_source": (f"dram__bytes_read+write per launch, mean of {a_cnt} launches, ncu, {a_src}" if a_traffic else
+                                    "no committed ncu DRAM capture for this workload"),
+                 "issued_flop_per_launch": flop, "avg_launch_ms": a_ms,
+                 "timing": "kernel timed alone through the C ABI, CUDA events, 3 rotating input sets > L2"}
+    else:
+        a_ms, a_raw = time_align_kernel(torch, 2 * h, 2 * w, args.precision)
+        alg_bytes = ALIGN_BYTES_PER_L1_PX * px1
+        a_ach = alg_bytes / (a_ms * 1e-3) / 1e9
+        a_traffic, a_src, a_cnt = dram_traffic_from_profiles(args.workload, r"dcn_tc3_ws_kernel|dcn_l1_kernel")
+        align = {"kernel": ("dcn_tc3_ws_kernel" if args.precision != "fp32" else "dcn_l1_kernel") + " (DCNv2 align @L1, C=32 dg=8" +
+                           (", head activations fused into the sampler)" if a_raw else ")"),
+                 "bound": "hbm", "achieved": a_ach, "peak": peak, "unit": "GB/s", "frac": a_ach / peak,
+                 "traffic": a_traffic,
+                 "traffic_source": (f"dram__bytes_read+write per launch, mean of {a_cnt} launches, ncu, {a_src}" if a_traffic else
+                                    "no committed ncu DRAM capture for this workload"),
+                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": a_ms,
+                 "timing": "kernel timed alone through the C ABI, CUDA events, 3 rotating input sets > L2"}
     if args.precision != "fp32":
-        c_ms, c_n, c_bytes, c_flop = time_conv_mix(torch, 2 * h, 2 * w)
+        c_ms, c_n, c_bytes, c_flop = time_conv_mix(torch, 2 * h, 2 * w, precision=args.precision, with_heads=not fused)
         c_ach = c_bytes / (c_ms * 1e-3) / 1e9
         c_traffic, c_src, c_cnt = dram_traffic_from_profiles(args.workload, r"conv_tc3_ws_kernel", r"\((5|10), ")
         roofline = {"kernel": "conv_tc3_ws_kernel (tcgen05 3x3 implicit-GEMM conv, the per-frame mix of its %d L1 launches)" % c_n,
@@ -621,10 +681,11 @@ def main():
                                        "no committed ncu DRAM capture for this workload"),
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": c_bytes, "avg_launch_ms": c_ms,
                     "tensor": {"useful_fp32_tflops": c_flop / (c_ms * 1e-3) / 1e12,
-                               "issued_bf16_tflops": 3 * c_flop / (c_ms * 1e-3) / 1e12, "bf16_peak_tflops": bf16_peak,
-                               "frac_of_bf16_peak": 3 * c_flop / (c_ms * 1e-3) / 1e12 / bf16_peak},
+                               "issued_bf16_tflops": (3 if args.precision == "tc" else 2) * c_flop / (c_ms * 1e-3) / 1e12,
+                               "bf16_peak_tflops": bf16_peak,
+                               "frac_of_bf16_peak": (3 if args.precision == "tc" else 2) * c_flop / (c_ms * 1e-3) / 1e12 / bf16_peak},
                     "timing": "all L1 conv launches of one steady-state frame replayed back to back through "
-                              "crfp_conv3x3_tc3_fwd, CUDA events, rotating 29.5 MB planes + 199 MB heads output (> L2)",
+                              "crfp_conv3x3_tc3_fwd, CUDA events, rotating 29.5 MB planes (5 x 29.5 + HR outputs > L2)",
                     "align_kernel": align}
     else:
         roofline = dict(align)
