@@ -110,7 +110,8 @@ class DcnBwdDesc(C.Structure):
                 ("c", C.c_int32), ("cout", C.c_int32), ("dg", C.c_int32),
                 ("x", C.c_void_p), ("offset", C.c_void_p), ("mask", C.c_void_p), ("weight", C.c_void_p),
                 ("dout", C.c_void_p), ("dx", C.c_void_p), ("doffset", C.c_void_p), ("dmask", C.c_void_p),
-                ("dweight", C.c_void_p), ("dbias", C.c_void_p), ("col", C.c_void_p), ("weight_t", C.c_void_p)]
+                ("dweight", C.c_void_p), ("dbias", C.c_void_p), ("col", C.c_void_p), ("weight_t", C.c_void_p),
+                ("wg_workspace", C.c_void_p), ("wg_ws_floats", C.c_size_t)]
 
 
 class Layer(C.Structure):
@@ -216,6 +217,7 @@ SYMBOLS = {
     "crfp_conv3x3_bwd_data": (C.c_int, [C.c_int] * 7 + [C.c_void_p] * 4),
     "crfp_conv3x3_bwd_weight": (C.c_int, [C.c_int] * 7 + [C.c_void_p] * 5 + [C.c_size_t, C.c_void_p]),
     "crfp_conv3x3_bwd_weight_workspace": (C.c_size_t, [C.c_int] * 5),
+    "crfp_dcn_v2_bwd_workspace": (C.c_size_t, [C.c_int] * 5),
     "crfp_dcn_v2_bwd": (C.c_int, [C.POINTER(DcnBwdDesc), C.c_void_p]),
     "crfp_sizeof_dcn_bwd_desc": (C.c_size_t, []),
     "crfp_flow_warp_bwd": (C.c_int, [C.c_int] * 4 + [C.c_void_p] * 6),

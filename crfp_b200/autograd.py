@@ -35,9 +35,11 @@ class KernelSet:
     # backward-data through the tiled forward conv kernel (default) or the direct gather kernel crfp_conv3x3_bwd_data
     # (CRFP_DGRAD=direct; kept for A/B and for shapes the forward kernel would not take)
     dgrad_as_conv = os.environ.get("CRFP_DGRAD", "conv") != "direct"
-    # weight gradient of the thin layers: same-line atomics (default, the B200-verified path) or the two-stage reduction
-    # (CRFP_WGRAD_THIN=2stage; CPU-emulation-verified, to be measured and made the default in round 2)
-    wgrad_two_stage = os.environ.get("CRFP_WGRAD_THIN", "atomic") == "2stage"
+    # The weight-gradient entry points take an optional workspace (partial sums + a reduce kernel instead of same-address
+    # atomics).  The library says how much it wants: the round-2 tiled kernel (wgrad.cu) for the wide layers; 0 for the
+    # shapes that do not need one.  CRFP_WGRAD_V1=1 (read by the library) switches back to round 1's kernels, for which
+    # CRFP_WGRAD_THIN=2stage selects their two-stage variant on the thin layers (measured slower: 81.6 vs 76.5 ms).
+    wgrad_two_stage = os.environ.get("CRFP_WGRAD_V1") is None or os.environ.get("CRFP_WGRAD_THIN", "atomic") == "2stage"
 
     def lib(self):
         return L.lib()
@@ -165,7 +167,7 @@ class Conv3x3Fn(torch.autograd.Function):
             off = 0
             for i, c in enumerate(ctx.c_list):
                 ws, ws_floats = None, 0
-                if K.wgrad_two_stage:       # opt-in: partial sums + a reduce kernel for the thin (4-channel HR) layers
+                if K.wgrad_two_stage:       # partial sums + a reduce kernel where the library asks for a workspace
                     ws_floats = lib.crfp_conv3x3_bwd_weight_workspace(n, h, w, c, cout)
                     if ws_floats:
                         ws = torch.empty(ws_floats, device=dy.device, dtype=torch.float32)
@@ -223,10 +225,13 @@ class DCNv2Fn(torch.autograd.Function):
         dwk = torch.zeros(kk, cout, **f32)
         dbias = torch.zeros(cout, **f32)
         col = torch.empty(n * h * w, kk, **f32)
+        ws_floats = K.lib().crfp_dcn_v2_bwd_workspace(n, h, w, c, cout) if K.wgrad_two_stage else 0
+        ws = torch.empty(ws_floats, **f32) if ws_floats else None
         d = L.DcnBwdDesc(n=n, h=h, w=w, c=c, cout=cout, dg=dg, x=x.data_ptr(), offset=offset.data_ptr(),
                          mask=mask.data_ptr(), weight=wk.data_ptr(), dout=dout.data_ptr(), dx=dx.data_ptr(),
                          doffset=doff.data_ptr(), dmask=dmask.data_ptr(), dweight=dwk.data_ptr(),
-                         dbias=dbias.data_ptr(), col=col.data_ptr(), weight_t=wk_t.data_ptr())
+                         dbias=dbias.data_ptr(), col=col.data_ptr(), weight_t=wk_t.data_ptr(),
+                         wg_workspace=ws.data_ptr() if ws is not None else None, wg_ws_floats=ws_floats)
         _chk(K, K.lib().crfp_dcn_v2_bwd(C.byref(d), K.stream()), "dcn_v2_bwd")
         dW = dwk.view(dg, 9, cpg, cout).permute(3, 0, 2, 1).reshape(cout, c, 3, 3)
         ng = ctx.needs_input_grad

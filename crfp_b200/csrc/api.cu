@@ -101,13 +101,13 @@ extern "C" void crfp_launch_count_reset(void) { g_launches = 0; }
 extern "C" void crfp_launch_count_add(long long n) { g_launches += n; }
 
 extern "C" int crfp_check_device(void) {
-  int dev = 0;
+  // cudaDeviceGetAttribute, not cudaGetDeviceProperties: the latter takes 2.5-3.7 ms per call on the B200 box (measured,
+  // profiles/r02/r2i_stream_host.txt) and used to run once per forward — half of a streaming call's latency
+  int dev = 0, major = 0;
   cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
-  cudaDeviceProp prop;
-  e = cudaGetDeviceProperties(&prop, dev);
-  if (e != cudaSuccess) { note_cuda_error(e); return CRFP_ERR_CUDA; }
-  return (prop.major == 10) ? CRFP_OK : CRFP_ERR_UNSUPPORTED;
+  return (major == 10) ? CRFP_OK : CRFP_ERR_UNSUPPORTED;
 }
 
 extern "C" int crfp_conv_cin_packed(int nsrc, const int32_t* c) {

@@ -349,6 +349,12 @@ static void thin_plan(long long rows, int w, int cin, int cout, int taps, bool v
 static int launch_bwd_weight(long long rows, int h, int w, int cin, int cout, int taps, int cin_total, int cin_off,
                              const float* x, const float* g, float* dw, float* db, cudaStream_t st,
                              float* workspace = nullptr, size_t ws_floats = 0) {
+#ifndef CRFP_HOST_EMU
+  {  // round-2 kernels (wgrad.cu): shared-memory tiled / register-tiled, no same-address atomics per pixel chunk
+    const int s2 = launch_bwd_weight_v2(rows, h, w, cin, cout, taps, cin_total, cin_off, x, g, dw, db, workspace, ws_floats, st);
+    if (s2 != 1) return s2;
+  }
+#endif
   if (workspace != nullptr) {                       // two-stage reduction for the thin layers (opt-in by the caller)
     const bool v4t = (cin % 4 == 0) && (cout % 4 == 0) && aligned16(x) && aligned16(g);
     int lanes_t, epad_t, xsegs_t;
@@ -761,6 +767,12 @@ extern "C" int crfp_conv3x3_bwd_weight(int n, int h, int w, int cin, int cout, i
 
 extern "C" size_t crfp_conv3x3_bwd_weight_workspace(int n, int h, int w, int cin, int cout) {
   if (n <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0) return 0;
+#ifndef CRFP_HOST_EMU
+  {
+    const size_t v2 = wgrad_workspace_floats((long long)n * h, w, cin, cout, 9);
+    if (v2) return v2;
+  }
+#endif
   int lanes, epad, xsegs;
   long long chunks, rpb;
   thin_plan((long long)n * h, w, cin, cout, 9, (cin % 4 == 0) && (cout % 4 == 0), &lanes, &epad, &chunks, &xsegs, &rpb);
@@ -791,7 +803,16 @@ extern "C" int crfp_dcn_v2_bwd(const crfp_dcn_bwd_desc* d, crfp_stream stream) {
   CRFP_TRY(check_launch());
   // dweight[k][co] += col^T dout, dbias[co] += sum dout
   return launch_bwd_weight((long long)d->n * d->h, d->h, d->w, 9 * d->c, d->cout, 1, 9 * d->c, 0, d->col, d->dout, d->dweight,
-                           d->dbias, (cudaStream_t)stream);
+                           d->dbias, (cudaStream_t)stream, d->wg_workspace, d->wg_ws_floats);
+}
+
+extern "C" size_t crfp_dcn_v2_bwd_workspace(int n, int h, int w, int c, int cout) {
+  if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || cout <= 0) return 0;
+#ifndef CRFP_HOST_EMU
+  return wgrad_workspace_floats((long long)n * h, w, 9 * c, cout, 1);
+#else
+  return 0;
+#endif
 }
 
 extern "C" int crfp_flow_warp_bwd(int n, int h, int w, int c, const float* x, const float* flow, const float* dy,

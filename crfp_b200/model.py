@@ -59,6 +59,17 @@ def _kaiming_fan_in_(conv: nn.Conv2d, scale: float):
     nn.init.constant_(conv.bias, 0)
 
 
+_DEVICE_OK = set()
+
+
+def _check_device(dev):
+    """sm_100 check, once per device and process (inside `with torch.cuda.device(dev)`)."""
+    key = str(dev)
+    if key not in _DEVICE_OK:
+        L.check(L.lib().crfp_check_device(), "device check (sm_100 required)")
+        _DEVICE_OK.add(key)
+
+
 class _CRFPBase(nn.Module):
     VARIANT = "dsv"
 
@@ -338,7 +349,7 @@ class CRFP_DSV(_CRFPBase):
                                 out.device != dev or not out.is_contiguous()):
             raise ValueError(f"out must be a contiguous CUDA fp32 tensor of shape {(n, t, 3, 8 * h, 8 * w)} on {dev}")
         with torch.cuda.device(dev):
-            L.check(L.lib().crfp_check_device(), "device check (sm_100 required)")
+            _check_device(dev)
             W = self._weights(dev)
             buf = self._clip_buffers(n, t, h, w, dev)
 
@@ -527,7 +538,7 @@ class MRCF_simple_v18(_CRFPBase):
         if self.pre_lr is not None and tuple(self.pre_lr.shape) != (n, 3, h, w):
             raise ValueError(f"pre_lr has shape {tuple(self.pre_lr.shape)}, expected {(n, 3, h, w)}: call clear_states()")
         with torch.cuda.device(dev):
-            L.check(L.lib().crfp_check_device(), "device check (sm_100 required)")
+            _check_device(dev)
             W = self._weights(dev)
             buf = self._clip_buffers(n, t, h, w, dev)
             if "prev" not in buf:

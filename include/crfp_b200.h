@@ -558,8 +558,11 @@ typedef struct {
   float* dbias;
   float* col;
   const float* weight_t;
+  float* wg_workspace;   /* optional: crfp_dcn_v2_bwd_workspace() floats for the tiled weight-gradient kernel (NULL: atomics) */
+  size_t wg_ws_floats;
 } crfp_dcn_bwd_desc;
 int crfp_dcn_v2_bwd(const crfp_dcn_bwd_desc* d, crfp_stream stream);
+size_t crfp_dcn_v2_bwd_workspace(int n, int h, int w, int c, int cout);
 size_t crfp_sizeof_dcn_bwd_desc(void);
 /* flow_warp backward (zeros padding): dx [n,h,w,c] accumulated (may be NULL), dflow [n,h,w,2] overwritten (may be NULL) */
 int crfp_flow_warp_bwd(int n, int h, int w, int c, const float* x, const float* flow, const float* dy, float* dx,

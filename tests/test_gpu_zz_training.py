@@ -311,3 +311,53 @@ def test_conv3x3_weight_gradient_two_stage(A, c_list, cout, hw):
     got = torch.autograd.grad(out, [w2, b2], nhwc(dy))
     assert (got[0].cpu() - rg[0]).abs().max().item() < 1e-5 * rg[0].abs().max().item() + 5e-4
     assert (got[1].cpu() - rg[1]).abs().max().item() < 1e-5 * rg[1].abs().max().item() + 5e-4
+
+
+# round-2 weight-gradient kernels (csrc/wgrad.cu): shared-memory tiled (wide layers), register-tiled (thin HR layers); every
+# geometry class they branch on — several 32-blocks of ci / co, ragged widths, row segments, partial quads, heads width 216
+@pytest.mark.parametrize("c_list,cout,nhw", [
+    ([32], 32, (2, 13, 70)), ([32, 32, 2], 32, (1, 9, 131)), ([24], 64, (1, 17, 64)), ([32], 216, (1, 6, 65)),
+    ([64], 32, (2, 5, 33)), ([128], 96, (1, 4, 7)), ([8, 12], 40, (1, 3, 1)),
+    ([4, 4], 4, (1, 70, 300)), ([4, 4, 2], 4, (2, 37, 45)), ([6], 4, (1, 40, 130)), ([4], 3, (1, 65, 129)), ([3], 4, (1, 9, 5))])
+def test_conv3x3_weight_gradient_round2_kernels(A, c_list, cout, nhw):
+    K = A.KernelSet()
+    assert K.wgrad_two_stage
+    g = _g(18)
+    n, h, w = nhw
+    srcs = [torch.randn(n, c, h, w, generator=g) for c in c_list]
+    wt = (torch.randn(cout, sum(c_list), 3, 3, generator=g) * 0.1).requires_grad_()
+    b = (torch.randn(cout, generator=g) * 0.1).requires_grad_()
+    ref = F.conv2d(torch.cat(srcs, 1).double(), wt.double(), b.double(), padding=1)
+    dy = torch.randn(ref.shape, generator=g)
+    rg = torch.autograd.grad(ref, [wt, b], dy.double())
+    w2, b2 = wt.detach().cuda().requires_grad_(), b.detach().cuda().requires_grad_()
+    out = A.conv3x3(K, w2, b2, [nhwc(s) for s in srcs], 0)
+    got = torch.autograd.grad(out, [w2, b2], nhwc(dy))
+    for a_, r_ in zip(got, rg):
+        assert (a_.cpu().double() - r_).abs().max().item() < 2e-6 * r_.abs().max().item() * (n * h * w) ** 0.5 + 1e-5
+
+
+def test_wgrad_round2_equals_round1_through_the_c_abi(A):
+    """The same C entry point with and without a workspace (= tiled kernel vs round 1's atomics) on one wide layer."""
+    import ctypes as C
+    from crfp_b200 import _lib as L
+    lib = L.lib()
+    g = _g(19)
+    n, h, w, cin, cout = 2, 11, 77, 32, 64
+    x = torch.randn(n, h, w, cin, generator=g).cuda()
+    dy = torch.randn(n, h, w, cout, generator=g).cuda()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    res = []
+    for use_ws in (False, True):
+        dw = torch.zeros(9, cin, cout, device="cuda")
+        db = torch.zeros(cout, device="cuda")
+        nws = lib.crfp_conv3x3_bwd_weight_workspace(n, h, w, cin, cout) if use_ws else 0
+        assert nws > 0 or not use_ws
+        ws = torch.empty(max(nws, 1), device="cuda")
+        L.check(lib.crfp_conv3x3_bwd_weight(n, h, w, cin, cout, cin, 0, x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(),
+                                            ws.data_ptr() if use_ws else None, nws, st), "bwd_weight")
+        res.append((dw.cpu(), db.cpu()))
+    assert (res[0][0] - res[1][0]).abs().max().item() < 1e-3
+    assert (res[0][1] - res[1][1]).abs().max().item() < 1e-3
+    ref = torch.einsum("nyxo,nyxi->io", dy.cpu().double(), x.cpu().double())           # centre tap
+    assert (res[1][0][4].double() - ref).abs().max().item() < 1e-3
