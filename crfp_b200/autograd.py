@@ -57,15 +57,56 @@ class KernelSet:
     # ---- forward primitives (GPU-verified SIMT fp32 kernels of the inference library)
     # `cache` (a dict owned by the caller, valid while the weights do not change — one training step): the packed
     # weight layouts are built once per layer and step instead of once per frame
+    # training forward / backward-data through the tensor-core conv (crfp_conv3x3_tc3_fwd: 3 x bf16 split products, fp32
+    # accumulation, ~1e-6 relative) wherever its shape rules hold; CRFP_TRAIN_TC=0: everything on the fp32 SIMT kernels
+    train_tc = os.environ.get("CRFP_TRAIN_TC", "1") != "0"
+
+    @staticmethod
+    def _tc3_split(c_list, cout):
+        """(tensor-core channel list, extra channels) if crfp_conv3x3_tc3_fwd takes this conv, else None."""
+        from .packing import tc3_cout_tile
+        c_list = list(c_list)
+        extra = 0
+        if len(c_list) > 1 and c_list[-1] == 2:
+            extra, c_list = 2, c_list[:-1]
+        k = sum(c_list)
+        if not c_list or len(c_list) > 3 or any(c % 8 for c in c_list) or k > 64 or cout % 4 or tc3_cout_tile(cout, k) is None:
+            return None
+        return c_list, extra
+
     def conv3x3(self, srcs, weight, bias, act, cache=None):
         from . import ops
         from .packing import pack_conv
+        if self.train_tc and act in (ACT_NONE, ACT_LRELU, ACT_RELU) and not (cache is not None and cache.get("no_tc")):
+            sp = self._tc3_split([s.shape[-1] for s in srcs], weight.shape[0])
+            if sp is not None:
+                from .packing import pack_conv_tc3_device
+                tc, extra = sp
+                packed = cache.get("fwd_tc") if cache is not None else None
+                if packed is None:
+                    packed = pack_conv_tc3_device(weight, bias, sum(tc), extra)
+                    if cache is not None:
+                        cache["fwd_tc"] = packed
+                return ops.conv3x3_tc3_nhwc(srcs[:len(tc)], None, None, act=act, extra=srcs[-1] if extra else None,
+                                            packed=packed, cout=weight.shape[0])
         packed = None
         if cache is not None:
             packed = cache.get("fwd")
             if packed is None:
                 packed = cache["fwd"] = pack_conv(weight, bias, [s.shape[-1] for s in srcs])
         return ops.conv3x3_nhwc(srcs, weight, bias, act=act, packed=packed)
+
+    def conv3x3_dgrad(self, g, weight, off, c, cache):
+        """Backward data of input channels [off, off + c) as a tensor-core conv of g with the transposed, rotated kernel
+        (packed on the device straight from the OIHW parameter); None when the shape is not the tensor-core kernel's."""
+        if not self.train_tc or self._tc3_split([g.shape[-1]], c) is None:
+            return None
+        from . import ops
+        from .packing import pack_conv_tc3_device
+        packed = cache.get("dgrad_tc")
+        if packed is None:
+            packed = cache["dgrad_tc"] = pack_conv_tc3_device(weight, None, g.shape[-1], 0, lo=off, transposed=True, nout=c)
+        return ops.conv3x3_tc3_nhwc([g], None, None, act=ACT_NONE, packed=packed, cout=c)
 
     def dcn_v2(self, x, offset, mask, weight, bias, dg, cache=None):
         from . import ops
@@ -141,12 +182,20 @@ class Conv3x3Fn(torch.autograd.Function):
                 # kernel: dx[ci] = sum_co conv(g[co], W[co,ci,2-ky,2-kx]).  Running it through the library's tiled
                 # forward conv kernel (shared-memory tiles, ~40 % of the FFMA peak) replaced the one-thread-per-
                 # (pixel, 4 ci) gather kernel, which sat on the L1 load pipe (ncu: 156 us per 32-channel L1 layer).
-                w2 = cache.get("w2")
-                if w2 is None:
-                    w2 = cache["w2"] = weight.detach().transpose(0, 1).flip(2, 3).contiguous()   # (cin, cout, 3, 3)
+                tc_dgrad = getattr(K, "conv3x3_dgrad", None)
                 for i, c in enumerate(ctx.c_list):  # one launch per source of the concat: dense per-source gradients
                     if ctx.needs_input_grad[5 + i]:
                         sub = cache.setdefault(("dgrad", i), {})
+                        if cache.get("no_tc"):
+                            sub["no_tc"] = True
+                        elif tc_dgrad is not None:
+                            dxs[i] = tc_dgrad(g, weight, off, c, sub)
+                            if dxs[i] is not None:
+                                off += c
+                                continue
+                        w2 = cache.get("w2")
+                        if w2 is None:
+                            w2 = cache["w2"] = weight.detach().transpose(0, 1).flip(2, 3).contiguous()   # (cin, cout, 3, 3)
                         if "zb" not in sub:
                             sub["zb"] = torch.zeros(c, device=dy.device, dtype=torch.float32)
                         dxs[i] = K.conv3x3([g], w2[off:off + c], sub["zb"], ACT_NONE, sub)

@@ -241,14 +241,15 @@ def conv3x3_tc_nhwc(srcs, weight, bias, act=L.ACT_NONE, residual=None, out_kind=
 
 
 def conv3x3_tc3_nhwc(srcs, weight, bias, act=L.ACT_NONE, residual=None, shuffle_r=0, post_scale=1.0, split=None,
-                     flow=None, head_split=0, head_mag=10.0, extra=None):
+                     flow=None, head_split=0, head_mag=10.0, extra=None, packed=None, cout=None):
     """fp32-accurate tensor-core conv (3 x bf16 split) over the channel concat of fp32 NHWC `srcs` (+ optional
-    2-channel fp32 `extra` source whose weights are the trailing input channels of `weight`)."""
+    2-channel fp32 `extra` source whose weights are the trailing input channels of `weight`).  `packed` = the
+    (hi, lo, bias, w_extra) operands of a caller-side cache (then `weight` / `bias` are not read and `cout` is required)."""
     srcs = [_req(s, "src") for s in srcs]
     n, h, w, _ = srcs[0].shape
     c_list = [s.shape[-1] for s in srcs]
-    cout = weight.shape[0]
-    hi, lo, bp, wx = pack_conv_tc3(weight, bias, c_list, extra=0 if extra is None else extra.shape[-1])
+    cout = weight.shape[0] if cout is None else cout
+    hi, lo, bp, wx = packed if packed is not None else pack_conv_tc3(weight, bias, c_list, extra=0 if extra is None else extra.shape[-1])
     d = L.ConvTc3Desc()
     d.n, d.h, d.w, d.nsrc = n, h, w, len(srcs)
     for i, s in enumerate(srcs):

@@ -178,6 +178,30 @@ def pack_conv_tc3(weight: torch.Tensor, bias: torch.Tensor, c_list, ci_lo: int =
     return hi.contiguous(), lo.contiguous(), b.contiguous(), wx
 
 
+def pack_conv_tc3_device(weight: torch.Tensor, bias, k: int, extra: int = 0, lo: int = 0, transposed: bool = False,
+                         nout: int | None = None):
+    """pack_conv_tc3 as ONE kernel launch on the device (crfp_pack_conv_tc3; the training step repacks every layer every
+    iteration).  transposed=True packs the backward-data operator of input channels [lo, lo + nout) (k = cout of `weight`)."""
+    import ctypes as C
+    from . import _lib as L
+    cout_w, cin_w = weight.shape[0], weight.shape[1]
+    nout = cout_w if nout is None else nout
+    nt, ntiles = tc3_cout_tile(nout, k)
+    kc = k // 8 + (k // 8) % 2
+    dev = weight.device
+    hi = torch.empty(ntiles, 9, kc, nt, 8, device=dev, dtype=torch.bfloat16)
+    lo_t = torch.empty_like(hi)
+    bp = torch.empty(ntiles * nt, device=dev, dtype=torch.float32)
+    wx = torch.empty(9, extra, ntiles * nt, device=dev, dtype=torch.float32) if extra else None
+    w = weight.detach()
+    assert w.dtype == torch.float32 and w.is_contiguous()
+    L.check(L.lib().crfp_pack_conv_tc3(w.data_ptr(), None if (bias is None or transposed) else bias.detach().data_ptr(), cout_w,
+                                       cin_w, int(transposed), lo, nout, k, extra, hi.data_ptr(), lo_t.data_ptr(), bp.data_ptr(),
+                                       wx.data_ptr() if wx is not None else None,
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pack_conv_tc3")
+    return hi, lo_t, bp, wx
+
+
 def pack_dcn_tc(weight: torch.Tensor, bias: torch.Tensor, dg: int):
     """DCNv2 weight -> bf16 UMMA B operand [K/8][cout][8] (k = (g*9+t)*(C/dg)+c) + fp32 bias, for crfp_dcn_v2_tc_fwd."""
     wk, b = pack_dcn(weight, bias, dg)                     # [K, cout]

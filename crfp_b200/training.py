@@ -44,9 +44,17 @@ class _Net:
         # weight layouts per layer, and the concatenated head weights (one torch.cat node per step, not per frame)
         self._cache = {}
         self._cat = {}
+        import os
+        self.fnet_fp32 = os.environ.get("CRFP_TRAIN_TC_FNET", "0") != "1"
 
     def _layer_cache(self, key, srcs):
-        return self._cache.setdefault((key, tuple(s.shape[-1] for s in srcs)), {})
+        d = self._cache.setdefault((key, tuple(s.shape[-1] for s in srcs)), {})
+        # the flow network stays on the fp32 SIMT kernels: flow = 256 * tanh(.) positions every warp and DCN sample, and its
+        # gradients are the most ill-conditioned of the model (the 3 x bf16 split's ~1e-6 relative error was measured to
+        # take the worst per-tensor gradient error from 2e-3 to 1.5e-2 when the flow network ran on it)
+        if isinstance(key, str) and key.startswith("spynet.") and self.fnet_fp32:
+            d["no_tc"] = True
+        return d
 
     def conv(self, name, srcs, act=A.ACT_NONE):
         srcs = list(srcs)

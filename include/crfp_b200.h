@@ -239,6 +239,17 @@ int crfp_conv3x3_tc3_trace(const crfp_conv_tc3_desc* d, long long* trace, crfp_s
  * the shared-memory resident rings (cin > 64) */
 int crfp_tc3_cout_tile(int cout, int cin, int32_t* nt, int32_t* ntiles);
 size_t crfp_sizeof_conv_tc3_desc(void);
+/*
+ * Packs an OIHW fp32 nn.Conv2d weight (+ bias) into crfp_conv3x3_tc3_fwd's operands in one launch (the training step
+ * repacks every layer after every optimiser update).  Logical operator V[o][i][tap], o < nout, i < k + extra:
+ *   transposed == 0: V[o][i][tap] = W[o][lo + i][tap]            (forward; nout == cout_w)
+ *   transposed == 1: V[o][i][tap] = W[i][lo + o][8 - tap]        (backward data of input channels [lo, lo + nout): the
+ *                    transposed, 180-degree rotated kernel; k == cout_w, extra == 0, bias ignored -> zeros)
+ * w_hi / w_lo: bf16 [ntiles][9][kc][nt][8] with (nt, ntiles) = crfp_tc3_cout_tile(nout, k), kc = k/8 rounded up to even;
+ * bias_packed fp32 [ntiles*nt]; w_extra fp32 [9][extra][ntiles*nt] (extra > 0 only).
+ */
+int crfp_pack_conv_tc3(const float* weight, const float* bias, int cout_w, int cin_w, int transposed, int lo, int nout, int k,
+                       int extra, void* w_hi, void* w_lo, float* bias_packed, float* w_extra, crfp_stream stream);
 
 /* ------------------------------------------------------------------ flow_warp */
 /*
