@@ -201,6 +201,15 @@ __device__ __forceinline__ void tc3_epilogue_chunk(const Tc3Params& P, float* v,
           }
         }
       }
+      if (P.res_pre && P.residual != nullptr) {   // K-split pass 2..: the earlier passes' partial sums, BEFORE the activation
+        const float* rp = P.residual + pix * P.res_cstride + P.res_coffset + cbase;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (4 * j >= nvalid) break;
+          const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + 4 * j));
+          v[4 * j] += rv.x; v[4 * j + 1] += rv.y; v[4 * j + 2] += rv.z; v[4 * j + 3] += rv.w;
+        }
+      }
       if (P.act == CRFP_ACT_LRELU) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = lrelu01(v[i]);
@@ -230,7 +239,8 @@ __device__ __forceinline__ void tc3_epilogue_chunk(const Tc3Params& P, float* v,
           }
         }
       }
-      if (rpre != nullptr) {   // residual of this chunk already in registers (loaded while the MMAs were running)
+      if (P.res_pre) {
+      } else if (rpre != nullptr) {   // residual of this chunk already in registers (loaded while the MMAs were running)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           v[4 * j] += rpre[j].x; v[4 * j + 1] += rpre[j].y; v[4 * j + 2] += rpre[j].z; v[4 * j + 3] += rpre[j].w;
@@ -693,7 +703,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
         }
       }
       float4 rpre[8];
-      const bool use_rpre = P.residual != nullptr && xvalid && NT >= 32 && cotile * NT + 32 <= P.cout;
+      const bool use_rpre = P.residual != nullptr && !P.res_pre && xvalid && NT >= 32 && cotile * NT + 32 <= P.cout;
       if (use_rpre) {   // the residual of the first 32-channel chunk is fetched while the MMAs of this row run
         const float* rpp = P.residual + pix * P.res_cstride + P.res_coffset + cotile * NT;
 #pragma unroll

@@ -115,6 +115,11 @@ static int layer_tc_kind(int li) {
     case L_FNET_E1_2: case L_FNET_E2_0: case L_FNET_E2_2: case L_FNET_E3_0: case L_FNET_D3_2: case L_FNET_F0:
     case L_ENC_LR_2: case L_UPSAMPLE: case L_DOWNSAMPLE:
       return 3;
+    // K-split: 128 / 256 input channels as 2 / 4 passes of 64 through the tensor-core conv; the later passes add the partial
+    // sums of the earlier ones before the activation (Tc3Params.res_pre).  packing: [passes][ntiles][9][8][nt][8] hi / lo,
+    // bias [2][ntiles*nt] = (bias, zeros)
+    case L_FNET_E3_2: case L_FNET_D1_0: case L_FNET_D1_2: case L_FNET_D2_0: case L_FNET_D2_2: case L_FNET_D3_0:
+      return 4;
     default:
       return 0;
   }
@@ -146,6 +151,9 @@ struct CB {
         !W_->layer_tc[li_].w_lo)
       return false;
     if (p.epi != EPI_STD || p.out_bf16 || p.cout <= 4) return false;
+    if (layer_tc_kind(li_) == 4)
+      return ksplit_enabled() && p.nsrc == 1 && p.src_mode[0] == CRFP_SRC_PLAIN && p.src_c[0] > 64 && p.src_c[0] % 64 == 0 &&
+             p.ndst == 1 && p.out_mode == CRFP_OUT_NHWC && p.residual == nullptr && p.act != CRFP_ACT_DCN_HEAD;
     int kc = 0;
     for (int s = 0; s < p.nsrc; ++s) {
       if (p.src_mode[s] == CRFP_SRC_UNSHUFFLE4) {
@@ -159,7 +167,39 @@ struct CB {
     }
     return kc >= 1 && kc <= 8;
   }
+  static bool ksplit_enabled() {
+    static const bool on = getenv("CRFP_NO_KSPLIT") == nullptr;   // A/B: the fp32 SIMT conv for the > 64-channel layers
+    return on;
+  }
+  int run_tc3_ksplit(cudaStream_t st) const {
+    int32_t nt = 0, ntiles = 0;
+    CRFP_TRY(crfp_tc3_cout_tile(p.cout, 64, &nt, &ntiles));
+    const size_t pass_elems = (size_t)ntiles * 9 * 8 * nt * 8;
+    const int passes = p.src_c[0] / 64;
+    for (int k = 0; k < passes; ++k) {
+      Tc3Params t;
+      memset(&t, 0, sizeof(t));
+      t.n = p.n; t.h = p.h; t.w = p.w;
+      t.nsrc = 1;
+      t.src[0] = p.src[0]; t.src_c[0] = 64; t.src_cstride[0] = p.src_cstride[0]; t.src_coffset[0] = p.src_coffset[0] + 64 * k;
+      t.src_mode[0] = CRFP_SRC_PLAIN;
+      t.cout = p.cout;
+      t.act = (k == passes - 1) ? p.act : CRFP_ACT_NONE;
+      t.weight_hi = reinterpret_cast<const __nv_bfloat16*>(W_->layer_tc[li_].w_hi) + k * pass_elems;
+      t.weight_lo = reinterpret_cast<const __nv_bfloat16*>(W_->layer_tc[li_].w_lo) + k * pass_elems;
+      t.bias = W_->layer_tc[li_].b + (k == 0 ? 0 : (size_t)ntiles * nt);
+      t.out_kind = TC_OUT_F32; t.ndst = 1;
+      t.dst[0] = p.dst[0]; t.dst_c[0] = p.dst_c[0]; t.dst_cstride[0] = p.dst_cstride[0]; t.dst_coffset[0] = p.dst_coffset[0];
+      if (k > 0) {   // in place: every thread reads the partial sum of exactly the elements it then overwrites
+        t.residual = p.dst[0]; t.res_cstride = p.dst_cstride[0]; t.res_coffset = p.dst_coffset[0]; t.res_pre = 1;
+      }
+      t.post_scale = (k == passes - 1) ? p.post_scale : 1.f;
+      CRFP_TRY(launch_conv_tc3(t, st));
+    }
+    return CRFP_OK;
+  }
   int run_tc3(cudaStream_t st) const {
+    if (layer_tc_kind(li_) == 4) return run_tc3_ksplit(st);
     Tc3Params t;
     memset(&t, 0, sizeof(t));
     t.n = p.n; t.h = p.h; t.w = p.w;

@@ -256,6 +256,16 @@ def pack_layer_tc3(info: dict, sd, dtype=torch.bfloat16):
     if info["tc"] == 2:
         hi, lo, bb = pack_dcn_tc3(w, b, info["dg"], dtype)
         return hi, lo, bb, None
+    if info["tc"] == 4:
+        # K-split (> 64 input channels): one packing per 64-channel slice, [passes][ntiles][9][8][nt][8]; bias [2][ntiles*nt] =
+        # (bias, zeros) — pass 0 adds the bias, the later passes add the earlier partial sums instead
+        cin = sum(info["c"])
+        assert len(info["c"]) == 1 and cin % 64 == 0 and cin > 64
+        parts = [pack_conv_tc3(w[:, k:k + 64].contiguous(), b, [64], 0, 0, None, dtype) for k in range(0, cin, 64)]
+        hi = torch.stack([q[0] for q in parts]).contiguous()
+        lo = torch.stack([q[1] for q in parts]).contiguous()
+        bb = torch.stack([parts[0][2], torch.zeros_like(parts[0][2])]).contiguous()
+        return hi, lo, bb, None
     if info["kind"] == 2:
         w = torch.cat([w, sd[info["key2"] + ".weight"]], dim=0)
         b = torch.cat([b, sd[info["key2"] + ".bias"]], dim=0)
