@@ -8,7 +8,10 @@
 //   EPI_OUT_NCHW conv_last + bilinear x8 base of the LR frame, planar NCHW store     (model/CRFP.py:1678-1683)
 #include <stdlib.h>
 
+#include <cuda.h>
+
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace crfp {
 
@@ -47,7 +50,9 @@ __device__ __forceinline__ void thin_epilogue(const ConvParams& P, int n, int y,
                          hy * (hx * p00.z + lx * p01.z) + ly * (hx * p10.z + lx * p11.z)};
     float* ob = P.dst[0] + (size_t)n * P.out_clip_stride + (size_t)y * P.w + x;
     const size_t plane = (size_t)P.h * P.w;
-    for (int c = 0; c < P.out_planes; ++c) ob[c * plane] = v[c] + bs[c];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)      // static indices: v[] / bs[] stay in registers
+      if (c < P.out_planes) ob[c * plane] = v[c] + bs[c];
     return;
   }
 
@@ -70,9 +75,14 @@ __device__ __forceinline__ void thin_epilogue(const ConvParams& P, int n, int y,
   }
   if (P.residual != nullptr) {
     const float* rp = P.residual + pix * P.res_cstride + P.res_coffset;
+    if (P.cout == 4 && ((P.res_cstride | P.res_coffset) & 3) == 0) {
+      const float4 rv = __ldg(reinterpret_cast<const float4*>(rp));
+      v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
+    } else {
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-      if (c < P.cout) v[c] += __ldg(rp + c);
+      for (int c = 0; c < 4; ++c)
+        if (c < P.cout) v[c] += __ldg(rp + c);
+    }
   }
   const float ps = (P.post_scale == 0.f) ? 1.f : P.post_scale;
   float* op = P.dst[0] + pix * P.dst_cstride[0] + P.dst_coffset[0];
@@ -83,8 +93,11 @@ __device__ __forceinline__ void thin_epilogue(const ConvParams& P, int n, int y,
     for (int c = 0; c < 4; ++c)
       if (c < P.cout) op[c] = v[c] * ps;
     // zero the padding channels of a 4-wide destination pixel so float4 consumers read zeros
-    if (P.dst_c[0] > P.cout)
-      for (int c = P.cout; c < P.dst_c[0] && c < 4; ++c) op[c] = 0.f;
+    if (P.dst_c[0] > P.cout) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c >= P.cout && c < P.dst_c[0]) op[c] = 0.f;
+    }
   }
 }
 
@@ -311,7 +324,7 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) conv_thin4p_kernel(const
       thin4_skip_tile(P, next, per_img, tiles_x);
       next += gridDim.x;
     }
-    if (next < total) prefetch(next, stage ^ 1);
+    if (next < total && !(P.exp & 1)) prefetch(next, stage ^ 1);
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncthreads();
@@ -321,6 +334,7 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) conv_thin4p_kernel(const
     float2 acc[4][2];
 #pragma unroll
     for (int r = 0; r < 4; ++r) acc[r][0] = acc[r][1] = make_float2(0.f, 0.f);
+    if (!(P.exp & 4))
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
 #pragma unroll
@@ -346,7 +360,7 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) conv_thin4p_kernel(const
     }
     const int n = tile / per_img, tr = tile - n * per_img;
     const int y0 = (tr / tiles_x) * TS, x = (tr % tiles_x) * TS + tx;
-    if (x < P.w) {
+    if (x < P.w && (!(P.exp & 2) || acc[0][0].x == 12345.678f)) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int y = y0 + 4 * ty + r;
@@ -360,9 +374,166 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) conv_thin4p_kernel(const
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// TMA-fed variant of the persistent kernel: the per-thread halo prefetch (five cp.async with their address arithmetic per
+// quad, measured at 18-29 % of the kernel) becomes ONE cp.async.bulk.tensor per quad and tile issued by thread 0; out-of-image
+// halo pixels are the TMA's zero fill.  The tile of a quad is a dense [34][34] float4 block (a warp's 32 consecutive
+// float4 of one row are conflict-free at any pitch).  2-channel sources (kind 1: the flow input of dcn_3.dcn_block.0) keep the
+// 8-byte cp.async path into the same layout.  Completion: one mbarrier per stage (tx bytes), so the per-tile __syncthreads
+// in front of the FFMA loop is only needed when a cp.async quad is present.
+constexpr int T4T_TILE_BYTES = 34 * 34 * 16;
+constexpr int T4T_TILE_PITCH = (T4T_TILE_BYTES + 127) / 128 * 128;   // 18560: TMA destinations 128-byte aligned
+
+template <int NQ>
+__global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) conv_thin4t_kernel(const ConvParams P, const __grid_constant__ CUtensorMap tm0,
+                                                                           const __grid_constant__ CUtensorMap tm1,
+                                                                           const __grid_constant__ CUtensorMap tm2) {
+  constexpr int TS = 32, HS = TS + 2, STAGE = NQ * T4T_TILE_PITCH;   // bytes per stage
+  extern __shared__ __align__(128) unsigned char smem_t4t[];
+  __shared__ uint64_t full[2];
+  float4* s_w = reinterpret_cast<float4*>(smem_t4t + 2 * STAGE);     // [9][cin_packed]
+  const int tid = threadIdx.x + threadIdx.y * 32;
+  const int tiles_x = (P.w + TS - 1) / TS, tiles_y = (P.h + TS - 1) / TS;
+  const int per_img = tiles_x * tiles_y, total = per_img * P.n;
+  bool any_k1 = false;
+  int ntma = 0;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    any_k1 = any_k1 || P.qkind[q] == 1;
+    ntma += P.qkind[q] == 0 ? 1 : 0;
+  }
+  pdl_trigger();
+  if (any_k1)
+    for (int i = tid; i < 2 * STAGE / 16; i += 256) reinterpret_cast<float4*>(smem_t4t)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < 9 * P.cin_packed; i += 256) s_w[i] = __ldg(reinterpret_cast<const float4*>(P.weight) + i);
+  if (tid == 0) {
+    umma::mbar_init(&full[0], 1);
+    umma::mbar_init(&full[1], 1);
+    umma::fence_mbar_init();
+    umma::tma_prefetch_desc(&tm0);
+    if (NQ > 1) umma::tma_prefetch_desc(&tm1);
+    if (NQ > 2) umma::tma_prefetch_desc(&tm2);
+  }
+  umma::fence_proxy_async();   // the zero fill above (generic proxy) precedes any TMA write into the same bytes
+  pdl_wait();
+  __syncthreads();
+
+  auto tile_live = [&](int tile) { return P.tile_flags == nullptr || P.tile_flags[tile] != 0; };
+  auto issue = [&](int tile, int stage) {
+    const int n = tile / per_img, tr = tile - n * per_img;
+    const int y0 = (tr / tiles_x) * TS, x0 = (tr % tiles_x) * TS;
+    if (tid == 0) {
+      umma::mbar_arrive_expect_tx(&full[stage], (uint32_t)(ntma * T4T_TILE_BYTES));
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        if (P.qkind[q] != 0) continue;
+        const CUtensorMap* tm = q == 0 ? &tm0 : (q == 1 ? &tm1 : &tm2);
+        umma::tma_load_4d(smem_t4t + stage * STAGE + q * T4T_TILE_PITCH, tm, &full[stage], 0, x0 - 1, y0 - 1, n);
+      }
+    }
+    if (any_k1) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        if (P.qkind[q] != 1) continue;
+        const float* base = P.qptr[q] + (size_t)n * P.h * P.w * P.qcs[q];
+        float4* dstq = reinterpret_cast<float4*>(smem_t4t + stage * STAGE + q * T4T_TILE_PITCH);
+        for (int r = tid; r < HS * HS; r += 256) {
+          const int py = r / HS, px = r - py * HS;
+          const int y = y0 + py - 1, x = x0 + px - 1;
+          const bool in = y >= 0 && y < P.h && x >= 0 && x < P.w;
+          const float* g = in ? base + ((size_t)y * P.w + x) * P.qcs[q] : base;
+          umma_cp8(dstq + r, g, in ? 8u : 0u);
+        }
+      }
+    }
+  };
+
+  int tile = blockIdx.x;
+  while (tile < total && !tile_live(tile)) {
+    thin4_skip_tile(P, tile, per_img, tiles_x);
+    tile += gridDim.x;
+  }
+  if (tile < total) issue(tile, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  int stage = 0;
+  uint32_t phase = 0;   // bit s = parity the next wait on full[s] expects
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const float4 bias = __ldg(reinterpret_cast<const float4*>(P.bias));
+  while (tile < total) {
+    int next = tile + gridDim.x;
+    while (next < total && !tile_live(next)) {
+      thin4_skip_tile(P, next, per_img, tiles_x);
+      next += gridDim.x;
+    }
+    if (next < total) issue(next, stage ^ 1);
+    if (any_k1) {
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    }
+    umma::mbar_wait(&full[stage], (phase >> stage) & 1u);
+    phase ^= 1u << stage;
+    if (any_k1) __syncthreads();   // the cp.async quad was written by all threads
+    const float4* sb = reinterpret_cast<const float4*>(smem_t4t + stage * STAGE);
+    float2 acc[4][2];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r][0] = acc[r][1] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const float4* sq = sb + q * (T4T_TILE_PITCH / 16);
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        float4 col[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) col[r] = sq[(4 * ty + r) * HS + tx + kx];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const float4* wt = s_w + (ky * 3 + kx) * P.cin_packed + q * 4;
+          const float4 w0 = wt[0], w1 = wt[1], w2 = wt[2], w3 = wt[3];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const float4 v = col[r + ky];
+            const float2 vx = make_float2(v.x, v.x), vy = make_float2(v.y, v.y), vz = make_float2(v.z, v.z), vw = make_float2(v.w, v.w);
+            acc[r][0] = __ffma2_rn(vx, make_float2(w0.x, w0.y), __ffma2_rn(vy, make_float2(w1.x, w1.y),
+                        __ffma2_rn(vz, make_float2(w2.x, w2.y), __ffma2_rn(vw, make_float2(w3.x, w3.y), acc[r][0]))));
+            acc[r][1] = __ffma2_rn(vx, make_float2(w0.z, w0.w), __ffma2_rn(vy, make_float2(w1.z, w1.w),
+                        __ffma2_rn(vz, make_float2(w2.z, w2.w), __ffma2_rn(vw, make_float2(w3.z, w3.w), acc[r][1]))));
+          }
+        }
+      }
+    }
+    const int n = tile / per_img, tr = tile - n * per_img;
+    const int y0 = (tr / tiles_x) * TS, x = (tr % tiles_x) * TS + tx;
+    if (x < P.w) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int y = y0 + 4 * ty + r;
+        if (y < P.h) thin_epilogue(P, n, y, x, acc[r][0].x + bias.x, acc[r][0].y + bias.y, acc[r][1].x + bias.z, acc[r][1].y + bias.w);
+      }
+    }
+    __syncthreads();   // everybody is done reading this stage before the next TMA / cp.async refills it
+    tile = next;
+    stage ^= 1;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+typedef CUresult (*thin_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static thin_tmap_encode_fn thin_tmap_encoder() {
+  static thin_tmap_encode_fn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (thin_tmap_encode_fn)p;
+  }();
+  return fn;
+}
+
 int launch_conv_thin(const ConvParams& p_in, cudaStream_t st) {
   ConvParams p = p_in;
   if (p.cout > 4 || p.cout_packed != 4) return CRFP_ERR_BAD_SHAPE;
+  static const int exp_env = getenv("CRFP_THIN_EXP") ? atoi(getenv("CRFP_THIN_EXP")) : 0;
+  p.exp = exp_env;
   {  // per-quad fast addressing
     const int nqr = p.qstart[p.nsrc];
     for (int q = 0; q < 3; ++q) { p.qptr[q] = p.src[0]; p.qcs[q] = p.src_cstride[0]; p.qkind[q] = 2; }
@@ -400,6 +571,32 @@ int launch_conv_thin(const ConvParams& p_in, cudaStream_t st) {
       }();
       const int ctas = sms * (nq == 1 ? 3 : 2);
       dim3 pgrid(total < ctas ? total : ctas);
+      static const bool use_tma = getenv("CRFP_THIN_NOTMA") == nullptr;   // A/B: per-thread cp.async halo prefetch
+      thin_tmap_encode_fn enc = use_tma ? thin_tmap_encoder() : nullptr;
+      bool tma_ok = enc != nullptr && p.qkind[0] == 0;
+      CUtensorMap tm[3];
+      memset(tm, 0, sizeof(tm));
+      for (int q = 0; q < nq && tma_ok; ++q) {
+        if (p.qkind[q] != 0) continue;
+        const cuuint64_t gdim[4] = {4, (cuuint64_t)p.w, (cuuint64_t)p.h, (cuuint64_t)p.n};
+        const cuuint64_t gstr[3] = {(cuuint64_t)p.qcs[q] * 4, (cuuint64_t)p.w * p.qcs[q] * 4, (cuuint64_t)p.h * p.w * p.qcs[q] * 4};
+        const cuuint32_t box[4] = {4, 34, 34, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        tma_ok = enc(&tm[q], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.qptr[q]), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+      }
+      if (tma_ok) {
+        const size_t smemt = (size_t)2 * nq * T4T_TILE_PITCH + (size_t)9 * p.cin_packed * 16;
+#define CRFP_THIN4T(NQ_)                                                                                       \
+  do {                                                                                                         \
+    cudaFuncSetAttribute(conv_thin4t_kernel<NQ_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemt);    \
+    launch_k(conv_thin4t_kernel<NQ_>, dim3(pgrid), dim3(32, 8), (size_t)(smemt), st, p, tm[0], tm[1], tm[2]);   \
+  } while (0)
+        if (nq == 1) CRFP_THIN4T(1); else if (nq == 2) CRFP_THIN4T(2); else CRFP_THIN4T(3);
+#undef CRFP_THIN4T
+        return check_launch();
+      }
 #define CRFP_THIN4P(NQ_)                                                                                       \
   do {                                                                                                         \
     cudaFuncSetAttribute(conv_thin4p_kernel<NQ_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp);    \

@@ -1,0 +1,22 @@
+#!/bin/bash
+# TMA-fed thin conv: op microbench A/B, full GPU suite, clip bench A/B
+mkdir -p gpurun_out
+TAG=${TAG:-r2n}
+python scripts/thin_exp.py 2>&1 | tail -1
+CRFP_THIN_NOTMA=1 python scripts/thin_exp.py 2>&1 | tail -1
+(timeout 1500 python -m pytest tests -m gpu -x -q --tb=short > gpurun_out/${TAG}_tests.log 2>&1; echo "pytest exit $?" >> gpurun_out/${TAG}_tests.log)
+tail -5 gpurun_out/${TAG}_tests.log
+B="python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-extras"
+timeout 600 $B > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+CRFP_THIN_NOTMA=1 timeout 600 $B > gpurun_out/${TAG}_bench_notma.json 2>> gpurun_out/${TAG}_bench.err
+python - << 'PY'
+import json, os
+t = os.environ.get("TAG", "r2n")
+for k in ("bench", "bench_notma"):
+    try:
+        d = json.loads(open(f"gpurun_out/{t}_{k}.json").read().strip().splitlines()[-1])
+        print(k, "value", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "wall", round(d["e2e"]["wall_value"], 1))
+    except Exception as e:
+        print(k, "failed", e)
+PY
+tail -3 gpurun_out/${TAG}_bench.err
