@@ -69,7 +69,7 @@ class ConvTc3Desc(C.Structure):
                 ("dst", TcSrc * 2),
                 ("residual", C.c_void_p), ("res_cstride", C.c_int32), ("res_coffset", C.c_int32),
                 ("flow", C.c_void_p), ("post_scale", C.c_float), ("head_mag", C.c_float),
-                ("half", C.c_int32), ("_pad", C.c_int32)]
+                ("half", C.c_int32), ("res_pre", C.c_int32)]
 
 
 class WarpDesc(C.Structure):
@@ -216,7 +216,7 @@ SYMBOLS = {
     "crfp_act_bwd": (C.c_int, [C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "crfp_conv3x3_bwd_data": (C.c_int, [C.c_int] * 7 + [C.c_void_p] * 4),
     "crfp_conv3x3_bwd_weight": (C.c_int, [C.c_int] * 7 + [C.c_void_p] * 5 + [C.c_size_t, C.c_void_p]),
-    "crfp_pack_conv_tc3": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p] * 5),
+    "crfp_pack_conv_tc3": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p] * 5),
     "crfp_conv3x3_bwd_weight_workspace": (C.c_size_t, [C.c_int] * 5),
     "crfp_dcn_v2_bwd_workspace": (C.c_size_t, [C.c_int] * 5),
     "crfp_dcn_v2_bwd": (C.c_int, [C.POINTER(DcnBwdDesc), C.c_void_p]),

@@ -78,6 +78,8 @@ class KernelSet:
         from . import ops
         from .packing import pack_conv
         if self.train_tc and act in (ACT_NONE, ACT_LRELU, ACT_RELU) and not (cache is not None and cache.get("no_tc")):
+            if len(srcs) == 1 and srcs[0].shape[-1] in (128, 192, 256) and self._tc3_split([64], weight.shape[0]) is not None:
+                return self._conv3x3_ksplit(srcs[0], weight, bias, act, cache, transposed=False, lo=0, nout=weight.shape[0])
             sp = self._tc3_split([s.shape[-1] for s in srcs], weight.shape[0])
             if sp is not None:
                 from .packing import pack_conv_tc3_device
@@ -96,10 +98,38 @@ class KernelSet:
                 packed = cache["fwd"] = pack_conv(weight, bias, [s.shape[-1] for s in srcs])
         return ops.conv3x3_nhwc(srcs, weight, bias, act=act, packed=packed)
 
+    def _conv3x3_ksplit(self, x, weight, bias, act, cache, transposed, lo, nout):
+        """A conv over 128 / 192 / 256 input channels as passes of 64 through the tensor-core kernel: pass 1 adds the bias,
+        the later passes add the partial sums (in place, before the activation: crfp_conv_tc3_desc.res_pre), the last one
+        applies the activation.  transposed: backward data (x = dy, K = the layer's output channels)."""
+        from . import ops
+        from .packing import pack_conv_tc3_device
+        key = "ksplit_t" if transposed else "ksplit"
+        packs = cache.get(key) if cache is not None else None
+        passes = x.shape[-1] // 64
+        if packs is None:
+            packs = []
+            for k in range(passes):
+                if transposed:
+                    packs.append(pack_conv_tc3_device(weight, None, 64, 0, lo=lo, transposed=True, nout=nout, k_lo=64 * k))
+                else:
+                    packs.append(pack_conv_tc3_device(weight, bias if k == 0 else None, 64, 0, lo=64 * k))
+            if cache is not None:
+                cache[key] = packs
+        out = None
+        for k in range(passes):
+            out = ops.conv3x3_tc3_nhwc([x], None, None, act=act if k == passes - 1 else ACT_NONE, packed=packs[k], cout=nout,
+                                       src_slice=(64 * k, 64), residual=out, res_pre=k > 0, out=out)
+        return out
+
     def conv3x3_dgrad(self, g, weight, off, c, cache):
         """Backward data of input channels [off, off + c) as a tensor-core conv of g with the transposed, rotated kernel
         (packed on the device straight from the OIHW parameter); None when the shape is not the tensor-core kernel's."""
-        if not self.train_tc or self._tc3_split([g.shape[-1]], c) is None:
+        if not self.train_tc:
+            return None
+        if g.shape[-1] in (128, 192, 256) and self._tc3_split([64], c) is not None:
+            return self._conv3x3_ksplit(g, weight, None, ACT_NONE, cache, transposed=True, lo=off, nout=c)
+        if self._tc3_split([g.shape[-1]], c) is None:
             return None
         from . import ops
         from .packing import pack_conv_tc3_device

@@ -892,6 +892,7 @@ static int tc3_fwd_impl(const crfp_conv_tc3_desc* d, long long* trace, crfp_stre
   if (d->out_kind == CRFP_TC_OUT_SHUFFLE_F32 && (d->shuffle_r < 1 || d->cout % (d->shuffle_r * d->shuffle_r))) return CRFP_ERR_BAD_SHAPE;
   p.dbg = trace;
   p.half = d->half ? 1 : 0;
+  p.res_pre = d->res_pre ? 1 : 0;
   return launch_conv_tc3(p, (cudaStream_t)stream);
 }
 

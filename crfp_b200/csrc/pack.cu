@@ -14,6 +14,7 @@ struct PackTc3 {
   int cout_w, cin_w;
   int transposed;          // 0: V[o][i][tap] = W[o][lo + i][tap];  1 (backward data): V[o][i][tap] = W[i][lo + o][8 - tap]
   int lo;
+  int k_lo;                // transposed only: first row (output channel of W) of this K slice
   int nout, k, extra;      // logical outputs, tensor-core inputs, trailing fp32 inputs
   int nt, ntiles, kc;      // kc = K chunks of 8 incl. the pad chunk
   __nv_bfloat16* hi;
@@ -23,7 +24,7 @@ struct PackTc3 {
 };
 
 __device__ __forceinline__ float pack_v(const PackTc3& P, int o, int i, int tap) {
-  if (P.transposed) return P.weight[((size_t)i * P.cin_w + P.lo + o) * 9 + (8 - tap)];
+  if (P.transposed) return P.weight[((size_t)(P.k_lo + i) * P.cin_w + P.lo + o) * 9 + (8 - tap)];
   return P.weight[((size_t)o * P.cin_w + P.lo + i) * 9 + tap];
 }
 
@@ -62,20 +63,20 @@ __global__ void __launch_bounds__(256) pack_conv_tc3_kernel(const PackTc3 P) {
 using namespace crfp;
 
 extern "C" int crfp_pack_conv_tc3(const float* weight, const float* bias, int cout_w, int cin_w, int transposed, int lo, int nout,
-                                  int k, int extra, void* w_hi, void* w_lo, float* bias_packed, float* w_extra,
+                                  int k, int extra, int k_lo, void* w_hi, void* w_lo, float* bias_packed, float* w_extra,
                                   crfp_stream stream) {
   if (!weight || !w_hi || !w_lo || !bias_packed) return CRFP_ERR_NULL;
   if (cout_w <= 0 || cin_w <= 0 || nout <= 0 || k <= 0 || k % 8 != 0 || extra < 0 || lo < 0) return CRFP_ERR_BAD_SHAPE;
   if (extra > 0 && !w_extra) return CRFP_ERR_NULL;
   if (transposed) {
-    if (extra != 0 || k != cout_w || lo + nout > cin_w) return CRFP_ERR_BAD_SHAPE;
+    if (extra != 0 || k_lo < 0 || k_lo + k > cout_w || lo + nout > cin_w) return CRFP_ERR_BAD_SHAPE;
   } else {
-    if (nout != cout_w || lo + k + extra > cin_w) return CRFP_ERR_BAD_SHAPE;
+    if (nout != cout_w || k_lo != 0 || lo + k + extra > cin_w) return CRFP_ERR_BAD_SHAPE;
   }
   int32_t nt = 0, ntiles = 0;
   CRFP_TRY(crfp_tc3_cout_tile(nout, k, &nt, &ntiles));
   PackTc3 P;
-  P.weight = weight; P.bias = bias; P.cout_w = cout_w; P.cin_w = cin_w; P.transposed = transposed; P.lo = lo;
+  P.weight = weight; P.bias = bias; P.cout_w = cout_w; P.cin_w = cin_w; P.transposed = transposed; P.lo = lo; P.k_lo = k_lo;
   P.nout = nout; P.k = k; P.extra = extra; P.nt = nt; P.ntiles = ntiles;
   P.kc = k / 8 + (k / 8) % 2;
   P.hi = (__nv_bfloat16*)w_hi; P.lo_out = (__nv_bfloat16*)w_lo; P.bias_p = bias_packed; P.wx = extra ? w_extra : nullptr;

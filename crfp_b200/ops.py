@@ -241,20 +241,28 @@ def conv3x3_tc_nhwc(srcs, weight, bias, act=L.ACT_NONE, residual=None, out_kind=
 
 
 def conv3x3_tc3_nhwc(srcs, weight, bias, act=L.ACT_NONE, residual=None, shuffle_r=0, post_scale=1.0, split=None,
-                     flow=None, head_split=0, head_mag=10.0, extra=None, packed=None, cout=None):
+                     flow=None, head_split=0, head_mag=10.0, extra=None, packed=None, cout=None, src_slice=None, res_pre=False,
+                     out=None):
     """fp32-accurate tensor-core conv (3 x bf16 split) over the channel concat of fp32 NHWC `srcs` (+ optional
     2-channel fp32 `extra` source whose weights are the trailing input channels of `weight`).  `packed` = the
-    (hi, lo, bias, w_extra) operands of a caller-side cache (then `weight` / `bias` are not read and `cout` is required)."""
+    (hi, lo, bias, w_extra) operands of a caller-side cache (then `weight` / `bias` are not read and `cout` is required).
+    K-split passes of a conv over more than 64 input channels: `src_slice=(offset, count)` reads a channel slice of the single
+    source, `res_pre=True` adds `residual` before the activation, `out=` writes into an existing tensor (in place over the
+    residual)."""
     srcs = [_req(s, "src") for s in srcs]
     n, h, w, _ = srcs[0].shape
-    c_list = [s.shape[-1] for s in srcs]
+    c_list = [s.shape[-1] for s in srcs] if src_slice is None else [src_slice[1]]
     cout = weight.shape[0] if cout is None else cout
     hi, lo, bp, wx = packed if packed is not None else pack_conv_tc3(weight, bias, c_list, extra=0 if extra is None else extra.shape[-1])
     d = L.ConvTc3Desc()
     d.n, d.h, d.w, d.nsrc = n, h, w, len(srcs)
     for i, s in enumerate(srcs):
-        d.src[i] = L.TcSrc(ptr=s.data_ptr(), c=s.shape[-1], cstride=s.shape[-1], coffset=0)
+        if src_slice is None:
+            d.src[i] = L.TcSrc(ptr=s.data_ptr(), c=s.shape[-1], cstride=s.shape[-1], coffset=0)
+        else:
+            d.src[i] = L.TcSrc(ptr=s.data_ptr(), c=src_slice[1], cstride=s.shape[-1], coffset=src_slice[0])
     d.cout, d.act = cout, act
+    d.res_pre = int(res_pre)
     d.weight_hi, d.weight_lo, d.bias = hi.data_ptr(), lo.data_ptr(), bp.data_ptr()
     if extra is not None:
         extra = _req(extra, "extra")
@@ -273,7 +281,9 @@ def conv3x3_tc3_nhwc(srcs, weight, bias, act=L.ACT_NONE, residual=None, shuffle_
         d.out_kind, d.shuffle_r = L.TC_OUT_SHUFFLE_F32, r
     else:
         parts = list(split) if split else [cout]
-        outs = [torch.zeros(n, h, w, c, device=dev, dtype=torch.float32) for c in parts]
+        # every channel of every pixel is written when the segments are whole 4-channel groups (the kernel's store unit)
+        alloc = torch.empty if all(c % 4 == 0 for c in parts) else torch.zeros
+        outs = [out] if out is not None else [alloc(n, h, w, c, device=dev, dtype=torch.float32) for c in parts]
         d.out_kind = L.TC_OUT_F32
     d.ndst = len(outs)
     for i, o in enumerate(outs):

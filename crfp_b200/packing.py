@@ -179,7 +179,7 @@ def pack_conv_tc3(weight: torch.Tensor, bias: torch.Tensor, c_list, ci_lo: int =
 
 
 def pack_conv_tc3_device(weight: torch.Tensor, bias, k: int, extra: int = 0, lo: int = 0, transposed: bool = False,
-                         nout: int | None = None):
+                         nout: int | None = None, k_lo: int = 0):
     """pack_conv_tc3 as ONE kernel launch on the device (crfp_pack_conv_tc3; the training step repacks every layer every
     iteration).  transposed=True packs the backward-data operator of input channels [lo, lo + nout) (k = cout of `weight`)."""
     import ctypes as C
@@ -196,7 +196,7 @@ def pack_conv_tc3_device(weight: torch.Tensor, bias, k: int, extra: int = 0, lo:
     w = weight.detach()
     assert w.dtype == torch.float32 and w.is_contiguous()
     L.check(L.lib().crfp_pack_conv_tc3(w.data_ptr(), None if (bias is None or transposed) else bias.detach().data_ptr(), cout_w,
-                                       cin_w, int(transposed), lo, nout, k, extra, hi.data_ptr(), lo_t.data_ptr(), bp.data_ptr(),
+                                       cin_w, int(transposed), lo, nout, k, extra, k_lo, hi.data_ptr(), lo_t.data_ptr(), bp.data_ptr(),
                                        wx.data_ptr() if wx is not None else None,
                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pack_conv_tc3")
     return hi, lo_t, bp, wx

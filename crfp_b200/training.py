@@ -49,9 +49,10 @@ class _Net:
 
     def _layer_cache(self, key, srcs):
         d = self._cache.setdefault((key, tuple(s.shape[-1] for s in srcs)), {})
-        # the flow network stays on the fp32 SIMT kernels: flow = 256 * tanh(.) positions every warp and DCN sample, and its
-        # gradients are the most ill-conditioned of the model (the 3 x bf16 split's ~1e-6 relative error was measured to
-        # take the worst per-tensor gradient error from 2e-3 to 1.5e-2 when the flow network ran on it)
+        # The flow network stays on the fp32 SIMT kernels unless CRFP_TRAIN_TC_FNET=1: flow = 256 * tanh(.) positions every
+        # warp and DCN sample and its gradients are the most ill-conditioned of the model.  Measured on the B200 with the
+        # flow network on the tensor-core convs as well: worst per-tensor gradient error 5.1e-2 (spynet.encoder3.2.weight,
+        # LR 8x16 case) instead of 2.1e-2, for 1.7 ms of a 37.9 ms V7 step.
         if isinstance(key, str) and key.startswith("spynet.") and self.fnet_fp32:
             d["no_tc"] = True
         return d

@@ -229,7 +229,9 @@ typedef struct {
   float post_scale;
   float head_mag;
   int32_t half;    /* != 0: CRFP_PREC_HALF arithmetic (weight_hi / weight_lo are fp16, activations one fp16 product) */
-  int32_t _pad;
+  int32_t res_pre; /* != 0: `residual` is added BEFORE the activation: a conv over more than 64 input channels runs as passes of
+                      64 whose partial sums meet here (pass 1: bias, no activation; last pass: zero bias, residual = the
+                      destination itself, the layer's activation) */
 } crfp_conv_tc3_desc;
 int crfp_conv3x3_tc3_fwd(const crfp_conv_tc3_desc* d, crfp_stream stream);
 /* profiling aid: same launch + a clock64 trace of CTA (0,0,0): trace[0..1] = kernel start / loop start, then per row
@@ -243,13 +245,14 @@ size_t crfp_sizeof_conv_tc3_desc(void);
  * Packs an OIHW fp32 nn.Conv2d weight (+ bias) into crfp_conv3x3_tc3_fwd's operands in one launch (the training step
  * repacks every layer after every optimiser update).  Logical operator V[o][i][tap], o < nout, i < k + extra:
  *   transposed == 0: V[o][i][tap] = W[o][lo + i][tap]            (forward; nout == cout_w)
- *   transposed == 1: V[o][i][tap] = W[i][lo + o][8 - tap]        (backward data of input channels [lo, lo + nout): the
- *                    transposed, 180-degree rotated kernel; k == cout_w, extra == 0, bias ignored -> zeros)
+ *   transposed == 1: V[o][i][tap] = W[k_lo + i][lo + o][8 - tap] (backward data of input channels [lo, lo + nout): the
+ *                    transposed, 180-degree rotated kernel; K slice [k_lo, k_lo + k) of W's output channels; extra == 0,
+ *                    bias ignored -> zeros).  k_lo must be 0 when transposed == 0 (use `lo`).
  * w_hi / w_lo: bf16 [ntiles][9][kc][nt][8] with (nt, ntiles) = crfp_tc3_cout_tile(nout, k), kc = k/8 rounded up to even;
  * bias_packed fp32 [ntiles*nt]; w_extra fp32 [9][extra][ntiles*nt] (extra > 0 only).
  */
 int crfp_pack_conv_tc3(const float* weight, const float* bias, int cout_w, int cin_w, int transposed, int lo, int nout, int k,
-                       int extra, void* w_hi, void* w_lo, float* bias_packed, float* w_extra, crfp_stream stream);
+                       int extra, int k_lo, void* w_hi, void* w_lo, float* bias_packed, float* w_extra, crfp_stream stream);
 
 /* ------------------------------------------------------------------ flow_warp */
 /*

@@ -415,3 +415,24 @@ def test_training_forward_uses_the_tensor_core_conv(A):
     dx_simt = K2.conv3x3([dy], w2[32:64], torch.zeros(32, device="cuda"), A.ACT_NONE, {})
     assert dx_tc is not None and (dx_tc - dx_simt).abs().max().item() < 2e-4
     assert lib.crfp_launch_count() > before
+
+
+@pytest.mark.parametrize("cin,cout", [(128, 128), (256, 128), (128, 64)])
+def test_training_ksplit_conv_over_more_than_64_channels(A, cin, cout):
+    """Forward and backward-data convs with 128 / 256 input channels: passes of 64 through the tensor-core kernel (partial sums
+    added before the activation) == the fp32 SIMT conv."""
+    g = _g(31)
+    K, K2 = A.KernelSet(), A.KernelSet()
+    K2.train_tc = False
+    x = torch.randn(2, 9, 21, cin, generator=g).cuda()
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) * 0.05).cuda()
+    b = torch.randn(cout, generator=g).cuda()
+    out_tc = K.conv3x3([x], wt, b, A.ACT_RELU, {})
+    out_simt = K2.conv3x3([x], wt, b, A.ACT_RELU, {})
+    assert (out_tc - out_simt).abs().max().item() < 3e-4 * out_simt.abs().max().item()
+    dy = torch.randn(2, 9, 21, cout, generator=g).cuda()
+    if cout in (128, 256):
+        dx_tc = K.conv3x3_dgrad(dy, wt, 0, cin, {})
+        w2 = wt.transpose(0, 1).flip(2, 3).contiguous()
+        dx_simt = K2.conv3x3([dy], w2, torch.zeros(cin, device="cuda"), A.ACT_NONE, {})
+        assert dx_tc is not None and (dx_tc - dx_simt).abs().max().item() < 3e-4 * dx_simt.abs().max().item()
