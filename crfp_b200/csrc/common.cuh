@@ -113,7 +113,6 @@ struct ConvParams {
   // tile_mode 1: untouched tiles are skipped; 2 (EPI_BLEND): untouched tiles get S = lrelu(S_old) without the conv
   const uint8_t* tile_flags;
   int tiles_x, tiles_y, tile_mode;
-  int exp;   // perf experiments only (CRFP_THIN_EXP): 1 no prefetch after the first tile, 2 no epilogue, 4 no FFMA loop
 };
 
 // ---- tensor-core (tcgen05) conv description: bf16 NHWC sources, channel counts multiples of 8

@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) conv_thin4p_kernel(const
       thin4_skip_tile(P, next, per_img, tiles_x);
       next += gridDim.x;
     }
-    if (next < total && !(P.exp & 1)) prefetch(next, stage ^ 1);
+    if (next < total) prefetch(next, stage ^ 1);
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncthreads();
@@ -334,7 +334,6 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) conv_thin4p_kernel(const
     float2 acc[4][2];
 #pragma unroll
     for (int r = 0; r < 4; ++r) acc[r][0] = acc[r][1] = make_float2(0.f, 0.f);
-    if (!(P.exp & 4))
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
 #pragma unroll
@@ -360,7 +359,7 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) conv_thin4p_kernel(const
     }
     const int n = tile / per_img, tr = tile - n * per_img;
     const int y0 = (tr / tiles_x) * TS, x = (tr % tiles_x) * TS + tx;
-    if (x < P.w && (!(P.exp & 2) || acc[0][0].x == 12345.678f)) {
+    if (x < P.w) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int y = y0 + 4 * ty + r;
@@ -532,8 +531,6 @@ static thin_tmap_encode_fn thin_tmap_encoder() {
 int launch_conv_thin(const ConvParams& p_in, cudaStream_t st) {
   ConvParams p = p_in;
   if (p.cout > 4 || p.cout_packed != 4) return CRFP_ERR_BAD_SHAPE;
-  static const int exp_env = getenv("CRFP_THIN_EXP") ? atoi(getenv("CRFP_THIN_EXP")) : 0;
-  p.exp = exp_env;
   {  // per-quad fast addressing
     const int nqr = p.qstart[p.nsrc];
     for (int q = 0; q < 3; ++q) { p.qptr[q] = p.src[0]; p.qcs[q] = p.src_cstride[0]; p.qkind[q] = 2; }

@@ -1,5 +1,5 @@
-"""Microbenchmark of the HR thin conv (4k -> 4 channels at 1440x2560) through the C ABI; CRFP_THIN_EXP selects perf-only
-experiments (results are wrong for exp != 0).  usage: [CRFP_THIN_EXP=n] python scripts/thin_exp.py"""
+"""Microbenchmark of the HR thin conv (4k -> 4 channels at 1440x2560) through the C ABI (host-bound below ~22 us per call).
+usage: [CRFP_THIN_NOTMA=1] python scripts/thin_exp.py"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from crfp_b200 import ops, _lib as L
@@ -24,4 +24,4 @@ for nq, res_on in ((1, False), (1, True), (2, False), (3, False)):
     e1.record()
     torch.cuda.synchronize()
     res.append(f"nq={nq}{'+res' if res_on else ''}: {e0.elapsed_time(e1) / 40 * 1e3:.1f} us")
-print(f"EXP={os.environ.get('CRFP_THIN_EXP', '0')}  " + "  ".join(res))
+print(f"NOTMA={os.environ.get('CRFP_THIN_NOTMA', '0')}  " + "  ".join(res))
