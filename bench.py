@@ -15,7 +15,8 @@ A "step" is one forward of this rank's synthetic clip(s) through the drop-in mod
 `cpu_baseline` / `--impl reference` = the oracle port of the reference's PyTorch path on the host cores, steady-state
              frames only.   `gpu_stock_baseline` = the same PyTorch path moved to the B200 (cuDNN,
              ATen grid_sample, torchvision deform_conv2d; TF32 off and on) — the GPU baseline the kernels must beat.
-`extra`    = the other shapes (R-nat, V7) measured the same way, shorter.
+`extra`    = the other shapes (R-nat, V7) measured the same way, shorter; the reduced-precision tier on the headline
+             workload; the streaming shell's per-frame latency.
 --total-clips N : BASELINE.json configs[2] — N clips strong-sharded across the ranks (N / world per GPU, sequentially).
 """
 from __future__ import annotations
@@ -578,6 +579,40 @@ def measure(torch, dist, model, workload, t, n, calls, steps, warmup, world, ran
     return res
 
 
+def stream_latency(torch, precision, h=134, w=240, frames=40):
+    """Median wall-clock latency of one streaming call (MRCF_simple_v18, batch 1, one frame, device synchronised after the
+    call): what a display loop sees per frame."""
+    import statistics
+    from crfp_b200 import MRCF_simple_v18
+    from crfp_b200.synthetic import make_clip, make_state_dict
+    lrs, fvs, mks, fv_sp = make_clip(seed=3, n=1, t=frames, h=h, w=w, fv_size=96)
+    fgs = torch.zeros(1, frames, 1, 8 * h, 8 * w)
+    for i in range(frames):
+        cy, cx = int(fv_sp[0, i, 0]) + 48, int(fv_sp[0, i, 1]) + 48
+        fgs[0, i, 0, max(cy - 270, 0):cy + 270, max(cx - 480, 0):cx + 480] = 1
+    lrs, fvs, mks, fgs = lrs.cuda(), fvs.cuda(), mks.cuda(), fgs.cuda()
+    m = MRCF_simple_v18("cuda", mid_channels=32, precision=precision).eval()
+    m.load_state_dict(make_state_dict(seed=1), strict=True)
+    m.cuda()
+    m.alias_output = True
+    lat = []
+    for rep in range(2):                     # first pass warms up and captures the per-frame graph
+        m.clear_states()
+        lat = []
+        for i in range(frames):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            m(lrs[:, i:i + 1], fvs[:, i:i + 1], mks[:, i:i + 1], fgs[:, i:i + 1])
+            torch.cuda.synchronize()
+            lat.append((time.perf_counter() - t0) * 1e3)
+    steady = sorted(lat[3:])
+    return {"workload": f"streaming: MRCF_simple_v18, one frame per call at LR {h}x{w} -> {8 * h}x{8 * w}, regional fg mask, "
+                        "device synchronised after every call (test_video.py:316-374)",
+            "metric": "latency per frame", "unit": "ms", "value": statistics.median(steady), "p95": steady[int(0.95 * len(steady))],
+            "frames_per_s": 1e3 / statistics.median(steady), "higher_is_better": False, "precision": precision,
+            "launch": "per-frame CUDA-graph replay"}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -739,6 +774,14 @@ def main():
                 model = mh
             except Exception as e:  # noqa: BLE001
                 extra.append({"precision": "half", "unavailable": f"{type(e).__name__}: {e}"[:200]})
+
+        if not args.no_extras and not args.total_clips:
+            # the reference's real-time protocol: one frame per call through the streaming shell, a device synchronisation
+            # after every call (test_video.py:316-374), LR 134x240 -> 1072x1920 (test_video.py:234-240), regional fg mask
+            try:
+                extra.append(stream_latency(torch, args.precision))
+            except Exception as e:  # noqa: BLE001
+                extra.append({"workload": "streaming", "unavailable": f"{type(e).__name__}: {e}"[:200]})
 
     cfg = workload_config(args.workload, h, w, t, n * calls, args.total_clips)
     prec = {"tc": "fp32 storage; dense contractions as 3 x bf16 split products on tcgen05 with fp32 TMEM accumulation "

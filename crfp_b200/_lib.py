@@ -218,6 +218,8 @@ SYMBOLS = {
     "crfp_conv3x3_bwd_weight": (C.c_int, [C.c_int] * 7 + [C.c_void_p] * 5 + [C.c_size_t, C.c_void_p]),
     "crfp_pack_conv_tc3": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p] * 5),
     "crfp_conv3x3_bwd_weight_workspace": (C.c_size_t, [C.c_int] * 5),
+    "crfp_conv3x3_bwd_weight_batched": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)] + [C.c_int] * 7 +
+                                        [C.c_void_p] * 3 + [C.c_size_t, C.c_void_p]),
     "crfp_dcn_v2_bwd_workspace": (C.c_size_t, [C.c_int] * 5),
     "crfp_dcn_v2_bwd": (C.c_int, [C.POINTER(DcnBwdDesc), C.c_void_p]),
     "crfp_sizeof_dcn_bwd_desc": (C.c_size_t, []),

@@ -175,6 +175,62 @@ def _chk(K, status, what):
         raise L.CrfpError(f"{what} failed with status {status}")
 
 
+# ----------------------------------------------------------------------------------------------- deferred weight gradients
+class WgradDeferral:
+    """The weight gradient of a conv layer is a sum over the t frames of the recurrence (and over the sources of a concat).
+    Instead of one launch + one zero fill + one accumulation add per layer AND frame inside the backward pass, the
+    (x, dy) pairs of a layer are collected and ONE crfp_conv3x3_bwd_weight_batched launch per layer and source runs when
+    the pass ends (torch's queue_callback: after the last node, on the thread that called backward(), inside a CUDA-graph
+    capture if there is one).  The result is added into `param.grad` directly, so this is only used where the caller reads
+    gradients from `.grad` (the Trainer): `torch.autograd.grad` would see None for the deferred weights."""
+
+    def __init__(self, K):
+        self.K = K
+        self.layers = []
+        self.armed = False
+
+    def add(self, cache, srcs, g, c_list, need_w, need_b):
+        pend = cache.setdefault("wg_pending", [])
+        if not pend:
+            self.layers.append((cache, tuple(c_list), need_w, need_b))
+        pend.append((srcs, g))
+        if not self.armed:
+            self.armed = True
+            torch.autograd.Variable._execution_engine.queue_callback(self.flush)
+
+    def flush(self):
+        K = self.K
+        lib, st = K.lib(), K.stream()
+        layers, self.layers, self.armed = self.layers, [], False
+        for cache, c_list, need_w, need_b in layers:
+            pend = cache.pop("wg_pending")
+            g0 = pend[0][1]
+            n, h, w, cout = g0.shape
+            cin = sum(c_list)
+            dev = g0.device
+            dw = torch.zeros(9, cin, cout, device=dev, dtype=torch.float32)
+            dbt = torch.zeros(cout, device=dev, dtype=torch.float32)
+            cnt = len(pend)
+            gs = (C.c_void_p * cnt)(*[g.data_ptr() for _, g in pend])
+            off = 0
+            for i, c in enumerate(c_list):
+                xs = (C.c_void_p * cnt)(*[srcs[i].data_ptr() for srcs, _ in pend])
+                ws_floats = lib.crfp_conv3x3_bwd_weight_workspace(n * min(cnt, 16), h, w, c, cout)
+                ws = torch.empty(ws_floats, device=dev, dtype=torch.float32) if ws_floats else None
+                _chk(K, lib.crfp_conv3x3_bwd_weight_batched(cnt, xs, gs, n, h, w, c, cout, cin, off, dw.data_ptr(),
+                                                            dbt.data_ptr() if i == 0 else None,
+                                                            ws.data_ptr() if ws is not None else None, ws_floats, st),
+                     "conv3x3_bwd_weight_batched")
+                off += c
+            dW = dw.permute(2, 1, 0).reshape(cout, cin, 3, 3)
+            for param, lo, hi in cache["wparams"] if need_w else ():
+                if param.requires_grad:
+                    param.grad = dW[lo:hi].contiguous() if param.grad is None else param.grad.add_(dW[lo:hi])
+            for param, lo, hi in cache["bparams"] if need_b else ():
+                if param.requires_grad:
+                    param.grad = dbt[lo:hi].clone() if param.grad is None else param.grad.add_(dbt[lo:hi])
+
+
 # ----------------------------------------------------------------------------------------------- conv3x3 (+bias+act)
 class Conv3x3Fn(torch.autograd.Function):
     """act(conv3x3(cat(srcs, -1), weight) + bias); weight OIHW (the reference's nn.Conv2d parameter)."""
@@ -240,7 +296,10 @@ class Conv3x3Fn(torch.autograd.Function):
                         _chk(K, lib.crfp_conv3x3_bwd_data(n, h, w, c, cout, cin, off, g.data_ptr(), w_t.data_ptr(),
                                                           dxs[i].data_ptr(), st), "conv3x3_bwd_data")
                     off += c
-        if need_w or need_b:
+        defer = ctx.cache.get("defer") if ctx.cache is not None else None
+        if (need_w or need_b) and defer is not None:
+            defer.add(ctx.cache, srcs, g, ctx.c_list, need_w, need_b)   # launched once per layer when the pass ends
+        elif need_w or need_b:
             dw = torch.zeros(9, cin, cout, device=dy.device, dtype=torch.float32)
             dbt = torch.zeros(cout, device=dy.device, dtype=torch.float32)
             off = 0

@@ -351,7 +351,7 @@ static int launch_bwd_weight(long long rows, int h, int w, int cin, int cout, in
                              float* workspace = nullptr, size_t ws_floats = 0) {
 #ifndef CRFP_HOST_EMU
   {  // round-2 kernels (wgrad.cu): shared-memory tiled / register-tiled, no same-address atomics per pixel chunk
-    const int s2 = launch_bwd_weight_v2(rows, h, w, cin, cout, taps, cin_total, cin_off, x, g, dw, db, workspace, ws_floats, st);
+    const int s2 = launch_bwd_weight_v2(rows, h, w, cin, cout, taps, cin_total, cin_off, &x, &g, 1, dw, db, workspace, ws_floats, st);
     if (s2 != 1) return s2;
   }
 #endif
@@ -763,6 +763,35 @@ extern "C" int crfp_conv3x3_bwd_weight(int n, int h, int w, int cin, int cout, i
   if (!x || !g || !dw) return CRFP_ERR_NULL;
   return launch_bwd_weight((long long)n * h, h, w, cin, cout, 9, cin_total, cin_off, x, g, dw, db, (cudaStream_t)stream,
                            workspace, ws_floats);
+}
+
+// `count` (x, g) pairs of identical shape (the frames of the recurrence) accumulated into the same dw / db: one launch of the
+// round-2 kernels per 16 pairs (xs / gs are HOST arrays of device pointers); shapes those kernels do not take go pair by pair
+// through crfp_conv3x3_bwd_weight's path.  workspace: crfp_conv3x3_bwd_weight_workspace(n * min(count, 16), ...) floats.
+extern "C" int crfp_conv3x3_bwd_weight_batched(int count, const float* const* xs, const float* const* gs, int n, int h, int w,
+                                               int cin, int cout, int cin_total, int cin_off, float* dw, float* db,
+                                               float* workspace, size_t ws_floats, crfp_stream stream) {
+  if (count < 0 || n < 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || cin_off < 0 || cin_off + cin > cin_total) return CRFP_ERR_BAD_SHAPE;
+  if (count == 0 || n == 0) return CRFP_OK;
+  if (!xs || !gs || !dw) return CRFP_ERR_NULL;
+  for (int e = 0; e < count; ++e)
+    if (!xs[e] || !gs[e]) return CRFP_ERR_NULL;
+  for (int e0 = 0; e0 < count; e0 += 16) {
+    const int ne = count - e0 < 16 ? count - e0 : 16;
+    int s2 = 1;
+#ifndef CRFP_HOST_EMU
+    s2 = launch_bwd_weight_v2((long long)n * h, h, w, cin, cout, 9, cin_total, cin_off, xs + e0, gs + e0, ne, dw, db, workspace,
+                              ws_floats, (cudaStream_t)stream);
+#endif
+    if (s2 == 1) {
+      for (int e = e0; e < e0 + ne; ++e)
+        CRFP_TRY(launch_bwd_weight((long long)n * h, h, w, cin, cout, 9, cin_total, cin_off, xs[e], gs[e], dw, db,
+                                   (cudaStream_t)stream, workspace, ws_floats));
+    } else if (s2 != CRFP_OK) {
+      return s2;
+    }
+  }
+  return CRFP_OK;
 }
 
 extern "C" size_t crfp_conv3x3_bwd_weight_workspace(int n, int h, int w, int cin, int cout) {

@@ -191,8 +191,9 @@ int launch_dcn_tc(const crfp_dcn_desc& d, cudaStream_t st);
 int launch_dcn_tc3(const crfp_dcn_desc& d, const void* w_lo, const float* flow_hint, cudaStream_t st);
 // round-2 weight-gradient kernels (wgrad.cu); launch_bwd_weight_v2 returns 1 when the shape is not theirs
 size_t wgrad_workspace_floats(long long rows, int w, int cin, int cout, int taps);
-int launch_bwd_weight_v2(long long rows, int h, int w, int cin, int cout, int taps, int cin_total, int cin_off, const float* x,
-                         const float* g, float* dw, float* db, float* workspace, size_t ws_floats, cudaStream_t st);
+int launch_bwd_weight_v2(long long rows, int h, int w, int cin, int cout, int taps, int cin_total, int cin_off,
+                         const float* const* xs, const float* const* gs, int nent, float* dw, float* db, float* workspace,
+                         size_t ws_floats, cudaStream_t st);
 int launch_align_fused(const crfp_align_fused_desc& d, cudaStream_t st, long long* trace = nullptr);
 int launch_flow_warp_bf16(const crfp_warp_desc& d, cudaStream_t st);
 int launch_flow_up2_dual(int n, int h, int w, const float* flow, float* out_f32, void* out_bf8, cudaStream_t st);

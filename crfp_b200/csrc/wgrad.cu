@@ -46,13 +46,16 @@ __device__ __forceinline__ void wg_fma48(float2 (&acc)[3][4][2], const float4& x
 }
 
 // ------------------------------------------------------------------------------------------------ tiled (wide layers)
+constexpr int WG_MAX_ENT = 16;
+
 struct WgTile {
   int rows, h, w;          // rows = n*h image rows
   int cin, cout;           // channels (= pixel strides) of x and g
   int ncob;                // 32-wide co blocks; blockIdx.x = cib * ncob + cob
-  int nchunks, segs;       // pixel chunks = rows * segs, segs = ceil(w / SEG)
-  const float* x;
-  const float* g;
+  int nchunks, segs;       // pixel chunks = nent * rows * segs, segs = ceil(w / SEG)
+  int nent;                // (x, g) pairs of identical shape handled by this launch (frames of the recurrence), <= WG_MAX_ENT
+  const float* x[WG_MAX_ENT];
+  const float* g[WG_MAX_ENT];
   float* partial;          // [gridDim.y][pitch]
   long long pitch;         // taps*cin*cout + cout
 };
@@ -72,13 +75,17 @@ __global__ void __launch_bounds__(192, 2) conv_wgrad_tile_kernel(const WgTile A)
   auto load = [&](int chunk, int stage) {
     float* sx = wg_smem + stage * STAGE;
     float* sg = sx + XS;
-    const int r = chunk / A.segs, x0 = (chunk - r * A.segs) * SEG;
+    const int per_ent = A.rows * A.segs;
+    const int ent = chunk / per_ent, lc = chunk - ent * per_ent;
+    const int r = lc / A.segs, x0 = (lc - r * A.segs) * SEG;
+    const float* __restrict__ xe = A.x[ent];
+    const float* __restrict__ ge = A.g[ent];
     if (FLAT) {
       for (int i = tid; i < 3 * SEG * 24; i += 192) {
         const int q = i % 24, px = (i / 24) % SEG, jj = i / (24 * SEG);
         const int col = x0 + px;
         const bool in = col < A.w;
-        const float* src = in ? A.x + ((long long)r * A.w + col) * A.cin + jj * 96 + q * 4 : A.x;
+        const float* src = in ? xe + ((long long)r * A.w + col) * A.cin + jj * 96 + q * 4 : xe;
         wg_cp16(sx + (jj * XPX + px) * XCH + q * 4, src, in ? 16u : 0u);
       }
     } else {
@@ -87,7 +94,7 @@ __global__ void __launch_bounds__(192, 2) conv_wgrad_tile_kernel(const WgTile A)
         const int q = i & 7, px = (i >> 3) % XPX, jj = (i >> 3) / XPX;
         const int col = x0 - 1 + px, yi = y + jj - 1;
         const bool in = col >= 0 && col < A.w && yi >= 0 && yi < A.h && ci0 + q * 4 < A.cin;
-        const float* src = in ? A.x + ((long long)(r + jj - 1) * A.w + col) * A.cin + ci0 + q * 4 : A.x;
+        const float* src = in ? xe + ((long long)(r + jj - 1) * A.w + col) * A.cin + ci0 + q * 4 : xe;
         wg_cp16(sx + (jj * XPX + px) * XCH + q * 4, src, in ? 16u : 0u);
       }
     }
@@ -95,7 +102,7 @@ __global__ void __launch_bounds__(192, 2) conv_wgrad_tile_kernel(const WgTile A)
       const int q = i & 7, px = i >> 3;
       const int col = x0 + px;
       const bool in = col < A.w && co0 + q * 4 < A.cout;
-      const float* src = in ? A.g + ((long long)r * A.w + col) * A.cout + co0 + q * 4 : A.g;
+      const float* src = in ? ge + ((long long)r * A.w + col) * A.cout + co0 + q * 4 : ge;
       wg_cp16(sg + px * 32 + q * 4, src, in ? 16u : 0u);
     }
   };
@@ -208,8 +215,9 @@ struct WgThin {
   int rb;                  // image rows per CTA
   int flat;                // 1: DCNv2 HR weight gradient — the (ky, kx) "taps" are the nine 4-channel blocks of col[.][36]
   int vecx, vecg;          // 16-byte loads allowed
-  const float* x;
-  const float* g;
+  int nent;                // (x, g) pairs handled by this launch; blockIdx.y walks nent * rows image rows
+  const float* x[WG_MAX_ENT];
+  const float* g[WG_MAX_ENT];
   float* dw;
   float* db;
 };
@@ -229,9 +237,10 @@ __global__ void __launch_bounds__(128) conv_wgrad_thin_kernel(const WgThin A) {
   __shared__ float red[4][52];
   const int px = blockIdx.x * 128 + threadIdx.x;
   const int ky = blockIdx.z;
+  const long long all_rows = (long long)A.nent * A.rows;
   const long long r0 = (long long)blockIdx.y * A.rb;
   long long r1 = r0 + A.rb;
-  if (r1 > A.rows) r1 = A.rows;
+  if (r1 > all_rows) r1 = all_rows;
   float2 acc[3][4][2];
 #pragma unroll
   for (int kx = 0; kx < 3; ++kx)
@@ -241,19 +250,22 @@ __global__ void __launch_bounds__(128) conv_wgrad_thin_kernel(const WgThin A) {
   const bool do_bias = ky == 1 && A.db != nullptr;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   if (px < A.w) {
-    for (long long r = r0; r < r1; ++r) {
-      const float4 gv = wg_ld4(A.g + (r * A.w + px) * A.cout, A.cout, A.vecg != 0);
+    for (long long rr = r0; rr < r1; ++rr) {
+      const int ent = (int)(rr / A.rows);
+      const long long r = rr - (long long)ent * A.rows;
+      const float* __restrict__ xe = A.x[ent];
+      const float4 gv = wg_ld4(A.g[ent] + (r * A.w + px) * A.cout, A.cout, A.vecg != 0);
       if (do_bias) { gsum.x += gv.x; gsum.y += gv.y; gsum.z += gv.z; gsum.w += gv.w; }
       float4 xm, xc, xp;
       if (A.flat) {
-        const float* xb = A.x + (r * A.w + px) * A.cin + ky * 12;
+        const float* xb = xe + (r * A.w + px) * A.cin + ky * 12;
         xm = wg_ld4(xb, 4, A.vecx != 0);
         xc = wg_ld4(xb + 4, 4, A.vecx != 0);
         xp = wg_ld4(xb + 8, 4, A.vecx != 0);
       } else {
         const int yi = (int)(r % A.h) + ky - 1;
         if (yi < 0 || yi >= A.h) continue;
-        const float* xr = A.x + ((r + ky - 1) * A.w + px) * A.cin + A.cq;
+        const float* xr = xe + ((r + ky - 1) * A.w + px) * A.cin + A.cq;
         xm = px > 0 ? wg_ld4(xr - A.cin, A.nci, A.vecx != 0) : zero;
         xc = wg_ld4(xr, A.nci, A.vecx != 0);
         xp = px + 1 < A.w ? wg_ld4(xr + A.cin, A.nci, A.vecx != 0) : zero;
@@ -332,39 +344,44 @@ size_t wgrad_workspace_floats(long long rows, int w, int cin, int cout, int taps
   return (size_t)wg_tile_workers(rows, w, cin, cout, taps) * ((size_t)taps * cin * cout + cout);
 }
 
-// returns CRFP_OK when one of the round-2 kernels took the job, 1 when the caller should fall back to round 1's
-int launch_bwd_weight_v2(long long rows, int h, int w, int cin, int cout, int taps, int cin_total, int cin_off, const float* x,
-                         const float* g, float* dw, float* db, float* workspace, size_t ws_floats, cudaStream_t st) {
-  if (!wg_enabled() || rows * w >= (1LL << 31)) return 1;
+// returns CRFP_OK when one of the round-2 kernels took the job, 1 when the caller should fall back to round 1's.
+// nent (x, g) pairs of identical shape (rows = n*h image rows each) are summed into the same dw / db by ONE launch.
+int launch_bwd_weight_v2(long long rows, int h, int w, int cin, int cout, int taps, int cin_total, int cin_off,
+                         const float* const* xs, const float* const* gs, int nent, float* dw, float* db, float* workspace,
+                         size_t ws_floats, cudaStream_t st) {
+  if (!wg_enabled() || nent < 1 || nent > WG_MAX_ENT || rows * nent * w >= (1LL << 31)) return 1;
+  bool al = true;
+  for (int e = 0; e < nent; ++e) al = al && wg_aligned16(xs[e]) && wg_aligned16(gs[e]);
   if (wg_thin_ok(cin, cout, taps)) {
     WgThin A;
     A.rows = (int)rows; A.h = h; A.w = w; A.cin = cin; A.cout = cout; A.cin_total = cin_total; A.cin_off = cin_off;
-    A.flat = taps == 1; A.x = x; A.g = g; A.dw = dw;
-    A.vecg = cout == 4 && wg_aligned16(g);
+    A.flat = taps == 1; A.dw = dw; A.nent = nent;
+    for (int e = 0; e < nent; ++e) { A.x[e] = xs[e]; A.g[e] = gs[e]; }
+    A.vecg = cout == 4 && al;
     const int gx = (w + 127) / 128;
-    long long rb = (rows * gx * 3 + 4LL * sm_count() - 1) / (4LL * sm_count());
+    const long long all_rows = rows * nent;
+    long long rb = (all_rows * gx * 3 + 4LL * sm_count() - 1) / (4LL * sm_count());
     if (rb < 8) rb = 8;
     if (rb > 64) rb = 64;
     A.rb = (int)rb;
-    const dim3 grid(gx, (unsigned)((rows + rb - 1) / rb), 3);
+    const dim3 grid(gx, (unsigned)((all_rows + rb - 1) / rb), 3);
     if (grid.y > 65535) return 1;
     if (taps == 1) {
-      A.cq = 0; A.nci = 4; A.db = db; A.vecx = wg_aligned16(x);
+      A.cq = 0; A.nci = 4; A.db = db; A.vecx = al;
       conv_wgrad_thin_kernel<<<grid, 128, 0, st>>>(A);
       return check_launch();
     }
     for (int cq = 0; cq < cin; cq += 4) {
       A.cq = cq; A.nci = cin - cq < 4 ? cin - cq : 4;
       A.db = cq == 0 ? db : nullptr;
-      A.vecx = (cin % 4 == 0) && wg_aligned16(x);
+      A.vecx = (cin % 4 == 0) && al;
       conv_wgrad_thin_kernel<<<grid, 128, 0, st>>>(A);
       CRFP_TRY(check_launch());
     }
     return CRFP_OK;
   }
-  if (!wg_tile_ok(cin, cout, taps) || workspace == nullptr || !wg_aligned16(x) || !wg_aligned16(g) || !wg_aligned16(workspace))
-    return 1;
-  const int workers = wg_tile_workers(rows, w, cin, cout, taps);
+  if (!wg_tile_ok(cin, cout, taps) || workspace == nullptr || !al || !wg_aligned16(workspace)) return 1;
+  const int workers = wg_tile_workers(rows * nent, w, cin, cout, taps);
   const long long pitch = (long long)taps * cin * cout + cout;
   if ((size_t)workers * (size_t)pitch > ws_floats) return 1;
   WgTile A;
@@ -372,9 +389,11 @@ int launch_bwd_weight_v2(long long rows, int h, int w, int cin, int cout, int ta
   A.ncob = (cout + 31) / 32;
   const int seg = taps == 9 ? 64 : 32;
   A.segs = (w + seg - 1) / seg;
-  if (rows * A.segs >= (1LL << 31)) return 1;
-  A.nchunks = (int)(rows * A.segs);
-  A.x = x; A.g = g; A.partial = workspace; A.pitch = pitch;
+  if (rows * nent * A.segs >= (1LL << 31)) return 1;
+  A.nchunks = (int)(rows * nent * A.segs);
+  A.nent = nent;
+  for (int e = 0; e < nent; ++e) { A.x[e] = xs[e]; A.g[e] = gs[e]; }
+  A.partial = workspace; A.pitch = pitch;
   const int ncib = taps == 9 ? (cin + 31) / 32 : 1;
   const dim3 grid(ncib * A.ncob, workers);
   if (taps == 9) {

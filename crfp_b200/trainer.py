@@ -16,6 +16,7 @@ of one bucket and the optimiser is one `crfp_adam_step` launch 
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -45,6 +46,9 @@ class Trainer:
         self._graphs, self._seen = {}, {}
         self.time_comm, self.comm_events = False, []                 # optional CUDA-event timing of the gradient all-reduce
         self.K = kernels or A.CUDA
+        # weight gradients of the conv layers: one launch per layer over all frames at the end of the backward pass (the
+        # Trainer reads gradients from the flat .grad views, which is what the deferral writes); CRFP_WGRAD_DEFER=0: per frame
+        self.defer_wgrad = os.environ.get("CRFP_WGRAD_DEFER", "1") != "0" and self.K is A.CUDA
         self.betas, self.eps, self.rec_w = (beta1, beta2), eps, rec_w
         self.period, self.min_lr, self.freeze_flow_iters = period, min_lr, freeze_flow_iters
         self.base_lr = [lr_rate, lr_rate_flow]
@@ -143,7 +147,7 @@ class Trainer:
 
     def _fwd_bwd(self, lrs, fvs, mks, hr):
         K = self.K
-        sr = forward_train(self.model, lrs, fvs, mks, K)
+        sr = forward_train(self.model, lrs, fvs, mks, K, defer_wgrad=self.defer_wgrad)
         b, n, c, h, w = sr.shape
         loss = A.charbonnier_loss(K, sr.reshape(b * n, c, h, w), hr.reshape(b * n, c, h, w).to(torch.float32), 1e-12,
                                   self.rec_w)

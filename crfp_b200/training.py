@@ -35,8 +35,10 @@ def pixel_unshuffle_nhwc(x, r):
 class _Net:
     """Functional view over the model's parameters (reference names, model/CRFP.py state_dict)."""
 
-    def __init__(self, model, K):
+    def __init__(self, model, K, defer_wgrad=False):
         self.p = dict(model.named_parameters())
+        # deferred weight gradients (Trainer): one launch per layer over all frames at the end of the backward pass
+        self.defer = A.WgradDeferral(K) if (defer_wgrad and K is A.CUDA) else None
         self.K = K
         self.C = model.mid_channels
         self.max_mag = float(model.max_residue_magnitude)
@@ -59,7 +61,11 @@ class _Net:
 
     def conv(self, name, srcs, act=A.ACT_NONE):
         srcs = list(srcs)
-        return A.conv3x3(self.K, self.p[name + ".weight"], self.p[name + ".bias"], srcs, act, self._layer_cache(name, srcs))
+        cache = self._layer_cache(name, srcs)
+        wt, b = self.p[name + ".weight"], self.p[name + ".bias"]
+        if self.defer is not None and "defer" not in cache:
+            cache["defer"], cache["wparams"], cache["bparams"] = self.defer, [(wt, 0, wt.shape[0])], [(b, 0, b.shape[0])]
+        return A.conv3x3(self.K, wt, b, srcs, act, cache)
 
     def conv_cat(self, names, srcs, act=A.ACT_NONE):
         """one conv over the concatenated output channels of several reference convs sharing an input"""
@@ -69,7 +75,16 @@ class _Net:
                               torch.cat([self.p[n + ".bias"] for n in names], dim=0))
         w, b = self._cat[key]
         srcs = list(srcs)
-        return A.conv3x3(self.K, w, b, srcs, act, self._layer_cache(key, srcs))
+        cache = self._layer_cache(key, srcs)
+        if self.defer is not None and "defer" not in cache:
+            wp, bp, lo = [], [], 0
+            for n_ in names:
+                co = self.p[n_ + ".weight"].shape[0]
+                wp.append((self.p[n_ + ".weight"], lo, lo + co))
+                bp.append((self.p[n_ + ".bias"], lo, lo + co))
+                lo += co
+            cache["defer"], cache["wparams"], cache["bparams"] = self.defer, wp, bp
+        return A.conv3x3(self.K, w, b, srcs, act, cache)
 
     # ---- ResidualBlocksWithInputConv (model/CRFP.py:433-552): conv+LReLU, then x + conv2(relu(conv1(x)))
     def res_blocks(self, name, srcs):
@@ -157,11 +172,11 @@ class _Net:
         return out, (S, torch.cat(feats, dim=-1))
 
 
-def forward_train(model, lrs, fvs, mks, K=None):
+def forward_train(model, lrs, fvs, mks, K=None, defer_wgrad=False):
     """CRFP_DSV.forward(lrs, fvs, mks) with autograd: returns (n,t,3,8h,8w) carrying grad to every parameter that
     requires it.  `K` is the kernel set (default: the CUDA library)."""
     K = K or A.CUDA
-    net = _Net(model, K)
+    net = _Net(model, K, defer_wgrad)
     n, t, c, h, w = lrs.shape
     lrs = lrs.to(torch.float32)
     lr = K.to_nhwc(lrs.reshape(n * t, c, h, w).contiguous())                                 # (n*t, h, w, 3)

@@ -548,6 +548,12 @@ int crfp_conv3x3_bwd_weight(int n, int h, int w, int cin, int cout, int cin_tota
  * layer is not thin, pass NULL) the pixel chunks write partial sums there and a second kernel adds them up instead of
  * contending for the same few cache lines of dw with atomics; workspace == NULL selects the atomic path */
 size_t crfp_conv3x3_bwd_weight_workspace(int n, int h, int w, int cin, int cout);
+/* `count` (x, g) pairs of identical shape — the t frames of the recurrence, whose weight gradients the trainer defers to the
+ * end of the backward pass — accumulated into the same dw / db by one launch per 16 pairs.  xs / gs: HOST arrays of device
+ * pointers.  workspace: crfp_conv3x3_bwd_weight_workspace(n * min(count, 16), h, w, cin, cout) floats (may be NULL: atomics). */
+int crfp_conv3x3_bwd_weight_batched(int count, const float* const* xs, const float* const* gs, int n, int h, int w, int cin,
+                                    int cout, int cin_total, int cin_off, float* dw, float* db, float* workspace,
+                                    size_t ws_floats, crfp_stream stream);
 /*
  * DCNv2 backward (= dcn_v2_backward): non-shared layout only (offset dg*18, mask dg*9 channels per pixel).
  *   weight   [K][cout], K = 9*c, k = (g*9+t)*(c/dg) + c_in_group (crfp_dcn_v2_fwd packing with cout % 4 == 0)

@@ -46,7 +46,7 @@ cap() {  # kernel regex, skip, count
 }
 cap conv_tc3_ws_kernel 60 6
 cap dcn_align_fused_kernel 3 2
-cap conv_thin4p_kernel 30 4
+cap conv_thin4t_kernel 30 4
 cap dcn_hr_kernel 2 1
 unset CRFP_NO_GRAPHS
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_sanitizer_memcheck.log 2>&1; echo "memcheck rc $?"; tail -3 $O/${TAG}_sanitizer_memcheck.log

@@ -33,7 +33,7 @@ def test_emulation_exports_every_training_symbol():
     h = hostemu.lib()
     for name in L.TRAIN_SYMBOLS:
         assert hasattr(h, name)
-    assert len(L.TRAIN_SYMBOLS) == 12
+    assert len(L.TRAIN_SYMBOLS) == 13
     # argument validation returns a status, never crashes
     assert h.crfp_conv3x3_bwd_data(1, 0, 4, 4, 4, 4, 0, None, None, None, None) == -1
     assert h.crfp_conv3x3_bwd_data(1, 4, 4, 4, 4, 6, 4, None, None, None, None) == -1      # slice outside cin_total
