@@ -15,12 +15,16 @@
 
 namespace crfp {
 
-// Shared epilogue of the thin kernels for one output pixel (v = conv + bias, 4 channels).
+// Shared epilogue of the thin kernels for one output pixel (v = conv + bias, 4 channels).  EPI >= 0: the epilogue kind is a
+// compile-time constant (the persistent TMA kernel is instantiated per kind: a third of the code, no instruction-fetch
+// stalls on the untaken variants); EPI < 0: runtime dispatch on P.epi.
+template <int EPI = -1>
 __device__ __forceinline__ void thin_epilogue(const ConvParams& P, int n, int y, int x, float e0, float e1, float e2, float e3) {
   float v[4] = {e0, e1, e2, e3};
   const size_t pix = ((size_t)n * P.h + y) * (size_t)P.w + x;
+  const int epi = EPI >= 0 ? EPI : P.epi;
 
-  if (P.epi == EPI_BLEND) {
+  if (epi == EPI_BLEND) {
     // m*F + (1-m)*S with m in {0,1}: a select (identical for finite operands, immune to values the mask discards)
     const bool m = P.mask[(size_t)n * P.mask_clip_stride + (size_t)y * P.w + x] != 0;
     const float4 so = __ldg(reinterpret_cast<const float4*>(P.blend_old + pix * 4));
@@ -32,7 +36,7 @@ __device__ __forceinline__ void thin_epilogue(const ConvParams& P, int n, int y,
     *reinterpret_cast<float4*>(P.dst[0] + pix * 4) = o;
     return;
   }
-  if (P.epi == EPI_OUT_NCHW) {
+  if (epi == EPI_OUT_NCHW) {
     // base = nn.Upsample(x8, bilinear, align_corners=False)(lr): rscale = 1/8
     const int hl = P.h >> 3, wl = P.w >> 3;
     int y0, y1, x0, x1;
@@ -382,7 +386,7 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) conv_thin4p_kernel(const
 constexpr int T4T_TILE_BYTES = 34 * 34 * 16;
 constexpr int T4T_TILE_PITCH = (T4T_TILE_BYTES + 127) / 128 * 128;   // 18560: TMA destinations 128-byte aligned
 
-template <int NQ>
+template <int NQ, int EPI>
 __global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) conv_thin4t_kernel(const ConvParams P, const __grid_constant__ CUtensorMap tm0,
                                                                            const __grid_constant__ CUtensorMap tm1,
                                                                            const __grid_constant__ CUtensorMap tm2) {
@@ -505,7 +509,7 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) conv_thin4t_kernel(const
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int y = y0 + 4 * ty + r;
-        if (y < P.h) thin_epilogue(P, n, y, x, acc[r][0].x + bias.x, acc[r][0].y + bias.y, acc[r][1].x + bias.z, acc[r][1].y + bias.w);
+        if (y < P.h) thin_epilogue<EPI>(P, n, y, x, acc[r][0].x + bias.x, acc[r][0].y + bias.y, acc[r][1].x + bias.z, acc[r][1].y + bias.w);
       }
     }
     __syncthreads();   // everybody is done reading this stage before the next TMA / cp.async refills it
@@ -585,13 +589,20 @@ int launch_conv_thin(const ConvParams& p_in, cudaStream_t st) {
       }
       if (tma_ok) {
         const size_t smemt = (size_t)2 * nq * T4T_TILE_PITCH + (size_t)9 * p.cin_packed * 16;
-#define CRFP_THIN4T(NQ_)                                                                                       \
-  do {                                                                                                         \
-    cudaFuncSetAttribute(conv_thin4t_kernel<NQ_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemt);    \
-    launch_k(conv_thin4t_kernel<NQ_>, dim3(pgrid), dim3(32, 8), (size_t)(smemt), st, p, tm[0], tm[1], tm[2]);   \
+#define CRFP_THIN4T_E(NQ_, EPI_)                                                                                      \
+  do {                                                                                                                \
+    cudaFuncSetAttribute(conv_thin4t_kernel<NQ_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemt);     \
+    launch_k(conv_thin4t_kernel<NQ_, EPI_>, dim3(pgrid), dim3(32, 8), (size_t)(smemt), st, p, tm[0], tm[1], tm[2]);    \
+  } while (0)
+#define CRFP_THIN4T(NQ_)                                                  \
+  do {                                                                    \
+    if (p.epi == EPI_STD) CRFP_THIN4T_E(NQ_, EPI_STD);                    \
+    else if (p.epi == EPI_BLEND) CRFP_THIN4T_E(NQ_, EPI_BLEND);           \
+    else CRFP_THIN4T_E(NQ_, EPI_OUT_NCHW);                                \
   } while (0)
         if (nq == 1) CRFP_THIN4T(1); else if (nq == 2) CRFP_THIN4T(2); else CRFP_THIN4T(3);
 #undef CRFP_THIN4T
+#undef CRFP_THIN4T_E
         return check_launch();
       }
 #define CRFP_THIN4P(NQ_)                                                                                       \

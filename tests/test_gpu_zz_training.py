@@ -458,7 +458,7 @@ def test_deferred_weight_gradients_equal_the_per_frame_ones(A):
         tr._set_flow_trainable()
         losses[defer] = tr._fwd_bwd(*args).item()
         grads[defer] = tr.flat_g.clone()
-    assert losses[False] == losses[True]
+    assert abs(losses[False] - losses[True]) < 1e-5      # the Charbonnier mean meets in atomics: last-bit differences
     ref = grads[False]
     assert ref.abs().max().item() > 0
     err = (grads[True] - ref).norm().item() / ref.norm().item()
