@@ -13,7 +13,7 @@ import json, os
 t = os.environ.get("TAG", "r02")
 try:
     d = json.loads(open(f"gpurun_out/{t}_bench_R-lit.json").read().strip().splitlines()[-1])
-    print("value", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "wall", round(d["e2e"]["wall_value"], 1), "u8", round(d["e2e_u8"]["value"], 1),
+    print("value", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "wall", round(d["e2e"]["wall_value"], 1), "f32", round(d["e2e_f32"]["value"], 1),
           "| conv frac", round(d["roofline"]["frac"], 3), "align", d["roofline"]["align_kernel"]["bound"], round(d["roofline"]["align_kernel"]["frac"], 3),
           round(d["roofline"]["align_kernel"]["avg_launch_ms"], 4), "ms | cpu", round(d["cpu_baseline"]["value"], 3), "stock", d["gpu_stock_baseline"].get("fp32_fps"), d["gpu_stock_baseline"].get("tf32_fps"))
     print("extra", [(e.get("workload", "")[:5], e.get("precision"), round(e.get("value", 0), 1)) for e in d["extra"]])

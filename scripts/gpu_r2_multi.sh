@@ -18,7 +18,7 @@ timeout 900 $T 29615 bench.py --gpus $NG --steps 5 --warmup 3 > $O/multi${NG}_be
 echo "bench rc $?"; python -c "
 import json
 d=json.loads(open('$O/multi${NG}_bench.json').read().strip().splitlines()[-1])
-print('value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'wall', round(d['e2e']['wall_value'],1), 'd2h GB/s/rank', round(d['e2e']['d2h_gbs_per_rank'],1))
+print('value', round(d['value'],1), 'e2e(u8)', round(d['e2e']['value'],1), 'wall', round(d['e2e']['wall_value'],1), 'e2e_f32', round(d['e2e_f32']['value'],1), 'f32 d2h GB/s/rank', round(d['e2e_f32']['d2h_gbs_per_rank'],1))
 "; tail -2 $O/multi${NG}_bench.err
 if [ -n "$STRONG" ]; then
 timeout 900 $T 29616 bench.py --gpus $NG --total-clips 64 --frames 20 --steps 1 --warmup 1 --no-e2e > $O/multi${NG}_bench_64clips.json 2>> $O/multi${NG}_bench.err
