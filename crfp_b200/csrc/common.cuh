@@ -173,6 +173,7 @@ struct Tc3Params {
   int rows_per_cta;
   int ncat;         // ws kernel: hi | lo weights as one 64-wide B operand (2 MMAs per K step)
   int half;         // CRFP_PREC_HALF: fp16 operands, activations as ONE product (no lo half), weights fp16 hi / lo
+  int fast16;       // ws kernel: coalesced 16x256b epilogue for the plain 32-channel tiles (CRFP_TC3_NOFAST16 turns it off)
   int res_pre;      // residual is added BEFORE the activation (K-split layers: the partial sums of the earlier passes)
   long long* dbg;   // optional per-phase clock64 trace of CTA (0,0,0): [row][8] (debug / profiling only)
 };

@@ -687,6 +687,91 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
     const bool shuffle4_fast = P.out_kind == TC_OUT_SHUFFLE_F32 && P.shuffle_r == 4 && NT == 64 && P.cout == 64 &&
                                P.dst_cstride[0] == 4 && P.dst_coffset[0] == 0 && P.residual == nullptr &&
                                P.extra == nullptr && (P.act == CRFP_ACT_NONE || P.act == CRFP_ACT_LRELU);
+    // Coalesced epilogue for the plain 32-channel tiles (most L1 / LR layers): the accumulator is read in the 16x256b fragment
+    // layout, where a quad of threads owns 8 consecutive channels of one pixel, so every store instruction of a warp writes
+    // eight full 32-byte sectors (the one-pixel-per-thread layout writes 32 half sectors), and a thread needs only 8 bias
+    // values — kept in registers for the whole CTA instead of 8 LDS.128 per row queued behind the UMMA operand reads.
+    const bool fast16 = P.fast16 && NT == 32 && P.out_kind == TC_OUT_F32 && P.extra == nullptr && P.cout % 8 == 0 &&
+                        (P.act == CRFP_ACT_NONE || P.act == CRFP_ACT_LRELU || P.act == CRFP_ACT_RELU) &&
+                        (P.ndst == 1 || P.dst_c[0] % 8 == 0);
+    if (fast16) {
+      const int lane = tid & 31, q2 = (lane & 3) * 2, rr = lane >> 2;
+      const int cbase = cotile * NT;
+      float bias8[8];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) { bias8[2 * g] = sBias[8 * g + q2]; bias8[2 * g + 1] = sBias[8 * g + q2 + 1]; }
+      // per column group (loop invariant): destination pointer of pixel 0 and pixel stride, or NULL past cout
+      float* gptr[4];
+      int gstr[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int cc = cbase + 8 * g + q2;
+        const bool s1 = P.ndst > 1 && cc >= P.dst_c[0];
+        gstr[g] = s1 ? P.dst_cstride[1] : P.dst_cstride[0];
+        gptr[g] = (cbase + 8 * g < P.cout)
+                      ? reinterpret_cast<float*>(s1 ? P.dst[1] : P.dst[0]) + (s1 ? P.dst_coffset[1] + cc - P.dst_c[0] : P.dst_coffset[0] + cc)
+                      : nullptr;
+      }
+      const float* resb = P.residual != nullptr ? P.residual + P.res_coffset + cbase + q2 : nullptr;
+      const int px0 = x0 + 32 * warp + rr;
+      const bool lrelu = P.act == CRFP_ACT_LRELU, relu = P.act == CRFP_ACT_RELU, scale = P.post_scale != 1.f;
+      for (int v = 0; v < rows_out; ++v) {
+        const int y = y_begin + v, b = v & 1;
+        const size_t rowpix = ((size_t)n * P.h + y) * (size_t)P.w;
+        float2 rp[4][4];
+        if (resb != nullptr) {   // residual (or K-split partial sums) fetched while the MMAs of this row run
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const int px = px0 + 8 * h;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              rp[h][g] = (px < P.w && gptr[g] != nullptr)
+                             ? __ldg(reinterpret_cast<const float2*>(resb + (rowpix + px) * P.res_cstride + 8 * g))
+                             : make_float2(0.f, 0.f);
+          }
+        }
+        if (tr && v < 60) tr[v * 4 + 0] = clock64();
+        umma::mbar_wait_safe(&accf_bar[b], (uint32_t)((v >> 1) & 1));
+        if (tr && v < 60) tr[v * 4 + 1] = clock64();
+        umma::fence_after_sync();
+        float a0[16], a1[16];
+        const uint32_t tb = taddr + ((uint32_t)(32 * warp) << 16) + (uint32_t)b * ncols;
+        umma::tmem_ld16x256b_x4(tb, a0);
+        umma::tmem_ld16x256b_x4(tb + (16u << 16), a1);
+        if (P.ncat) {   // columns 32..63 hold A_hi x W_lo
+          float c0[16], c1[16];
+          umma::tmem_ld16x256b_x4(tb + 32u, c0);
+          umma::tmem_ld16x256b_x4(tb + (16u << 16) + 32u, c1);
+          umma::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { a0[i] += c0[i]; a1[i] += c1[i]; }
+        } else {
+          umma::tmem_ld_wait();
+        }
+        if (tr && v < 60) tr[v * 4 + 3] = clock64();
+        umma::fence_before_sync();
+        umma::mbar_arrive(&acce_bar[b]);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int px = px0 + 8 * h;
+          if (px >= P.w) continue;
+          const size_t pix = rowpix + px;
+          const float* av = (h < 2) ? a0 : a1;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (gptr[g] == nullptr) continue;
+            float v0 = av[4 * g + 2 * (h & 1)] + bias8[2 * g], v1 = av[4 * g + 2 * (h & 1) + 1] + bias8[2 * g + 1];
+            if (P.res_pre && resb != nullptr) { v0 += rp[h][g].x; v1 += rp[h][g].y; }
+            if (lrelu) { v0 = lrelu01(v0); v1 = lrelu01(v1); }
+            else if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            if (!P.res_pre && resb != nullptr) { v0 += rp[h][g].x; v1 += rp[h][g].y; }
+            if (scale) { v0 *= P.post_scale; v1 *= P.post_scale; }
+            *reinterpret_cast<float2*>(gptr[g] + pix * (size_t)gstr[g]) = make_float2(v0, v1);
+          }
+        }
+        if (tr && v < 60) tr[v * 4 + 2] = clock64();
+      }
+    } else
     for (int v = 0; v < rows_out; ++v) {
       const int y = y_begin + v, b = v & 1;
       const size_t pix = ((size_t)n * P.h + y) * (size_t)P.w + x;
@@ -824,6 +909,8 @@ int launch_conv_tc3(Tc3Params p, cudaStream_t st) {
     if (smem > 227 * 1024) return CRFP_ERR_UNSUPPORTED;
     static const bool no_cat = (getenv("CRFP_TC3_NOCAT") != nullptr);
     static const bool cat4 = (getenv("CRFP_TC3_NOCAT4") == nullptr);   // also for the 32-channel layers (+0.5 %)
+    static const bool fast16_env = (getenv("CRFP_TC3_NOFAST16") == nullptr);   // A/B: one-pixel-per-thread epilogue
+    p.fast16 = fast16_env ? 1 : 0;
     p.ncat = (!no_cat && (p.kc_total == 8 || (cat4 && p.kc_total == 4)) && p.nt == 32 && p.out_kind == TC_OUT_F32) ? 1 : 0;
     int segs = 148 / per_seg;
     if (segs < 1) segs = 1;

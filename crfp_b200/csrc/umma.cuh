@@ -173,6 +173,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 16 lanes x 32 consecutive fp32 columns in the 16x256b fragment layout: thread T holds rows T/4 and T/4 + 8 of the 16 lanes at
+// taddr's lane, and of every 8-column group g the column pair 8g + 2(T%4), +1 — v[4g + 2h + e] = (row T/4 + 8h, column
+// 8g + 2(T%4) + e).  A quad of threads owns 8 consecutive columns (32 bytes of an NHWC pixel): coalesced full-sector stores
+// straight from the accumulator layout.  NO wait::ld inside (the caller issues several loads, then tmem_ld_wait()).
+__device__ __forceinline__ void tmem_ld16x256b_x4(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // 16 and 2 consecutive columns (same lane mapping)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
