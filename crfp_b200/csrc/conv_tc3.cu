@@ -691,7 +691,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc3_ws_kernel(const Tc3Par
     // layout, where a quad of threads owns 8 consecutive channels of one pixel, so every store instruction of a warp writes
     // eight full 32-byte sectors (the one-pixel-per-thread layout writes 32 half sectors), and a thread needs only 8 bias
     // values — kept in registers for the whole CTA instead of 8 LDS.128 per row queued behind the UMMA operand reads.
-    const bool fast16 = P.fast16 && NT == 32 && P.out_kind == TC_OUT_F32 && P.extra == nullptr && P.cout % 8 == 0 &&
+    // (not in the fp16 instantiation: the extra live ranges spill at its 168-register cap — measured 409 vs 435 fps)
+    const bool fast16 = !HALF && P.fast16 && NT == 32 && P.out_kind == TC_OUT_F32 && P.extra == nullptr && P.cout % 8 == 0 &&
                         (P.act == CRFP_ACT_NONE || P.act == CRFP_ACT_LRELU || P.act == CRFP_ACT_RELU) &&
                         (P.ndst == 1 || P.dst_c[0] % 8 == 0);
     if (fast16) {
