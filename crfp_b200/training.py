@@ -38,7 +38,7 @@ class _Net:
     def __init__(self, model, K, defer_wgrad=False):
         self.p = dict(model.named_parameters())
         # deferred weight gradients (Trainer): one launch per layer over all frames at the end of the backward pass
-        self.defer = A.WgradDeferral(K) if (defer_wgrad and K is A.CUDA) else None
+        self.defer = A.WgradDeferral(K) if defer_wgrad else None
         self.K = K
         self.C = model.mid_channels
         self.max_mag = float(model.max_residue_magnitude)

@@ -310,3 +310,31 @@ def test_trainer_state_dict_is_validated():
     tr2._graphs["x"], tr2._seen["x"] = 1, 1
     tr2.load_state_dict(st, strict_hyper=False)                                    # the checkpoint's schedule wins
     assert tr2.period == 10 and tr2.cur_iter == 1 and not tr2._graphs and not tr2._seen
+
+
+def test_deferred_weight_gradients_equal_the_per_frame_ones():
+    """forward_train(defer_wgrad=True): the conv weight gradients are collected per layer during the backward pass and
+    launched once per layer and source when it ends (autograd.WgradDeferral, torch's queue_callback), incl. the fused
+    offset / mask heads whose gradient is routed back to the two reference parameters — same .grad as the per-frame path."""
+    grads = {}
+    for defer in (False, True):
+        sd, model, lrs, fvs, mks, hr = _setup(1, 2, 3, 8, 8)
+        model.train()
+        sr = forward_train(model, lrs, fvs, mks, K, defer_wgrad=defer)
+        charbonnier(sr, hr).backward()
+        grads[defer] = {k: p.grad.clone() for k, p in model.named_parameters()}
+        assert all(g is not None for g in grads[defer].values())
+    for k, g in grads[False].items():
+        d = grads[True][k]
+        assert d.shape == g.shape
+        assert (d - g).abs().max().item() <= 1e-5 * g.abs().max().item() + 1e-9, k      # summation order over frames
+    # a second backward through a fresh graph accumulates into .grad like autograd does
+    sd, model, lrs, fvs, mks, hr = _setup(1, 1, 2, 8, 8)
+    model.train()
+    for _ in range(2):
+        charbonnier(forward_train(model, lrs, fvs, mks, K, defer_wgrad=True), hr).backward()
+    once = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    charbonnier(forward_train(model, lrs, fvs, mks, K, defer_wgrad=True), hr).backward()
+    for k, p in model.named_parameters():
+        assert (once[k] - 2 * p.grad).abs().max().item() <= 2e-5 * p.grad.abs().max().item() + 1e-9, k
