@@ -381,6 +381,48 @@ def dcn_v2(K, x, offset, mask, weight, bias, dg, cache=None):
     return DCNv2Fn.apply(K, dg, cache, x, offset, mask, weight, bias)
 
 
+# ----------------------------------------------------------------------------------------------- DCN heads activation
+class DcnHeadsActFn(torch.autograd.Function):
+    """(offset, mask) of DCN_module.forward from the fused heads conv output and the flow (model/CRFP.py:337-347):
+    offset = mag * tanh(heads[..., :noff]) + flow.flip(-1) (repeated over the pairs), mask = sigmoid(heads[..., noff:]);
+    repeat=True: one pair / one mask per pixel shared by the nk taps.  One kernel forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, K, nk, repeat, mag, heads, flow):
+        heads, flow = K.req(heads.detach(), "heads"), K.req(flow.detach(), "flow")
+        n, h, w, ch = heads.shape
+        if ch != (3 if repeat else 3 * nk) or tuple(flow.shape) != (n, h, w, 2):
+            raise L.CrfpError("dcn_heads_act: heads / flow shapes do not match")
+        offset = torch.empty(n, h, w, 2 * nk, device=heads.device, dtype=torch.float32)
+        mask = torch.empty(n, h, w, nk, device=heads.device, dtype=torch.float32)
+        _chk(K, K.lib().crfp_dcn_heads_act_fwd(n * h * w, nk, int(repeat), float(mag), heads.data_ptr(), flow.data_ptr(),
+                                               offset.data_ptr(), mask.data_ptr(), K.stream()), "dcn_heads_act_fwd")
+        ctx.K, ctx.nk, ctx.repeat, ctx.mag = K, nk, repeat, mag
+        ctx.save_for_backward(heads)
+        return offset, mask
+
+    @staticmethod
+    def backward(ctx, doffset, dmask):
+        K = ctx.K
+        (heads,) = ctx.saved_tensors
+        n, h, w, _ = heads.shape
+        if doffset is None:
+            doffset = torch.zeros(n, h, w, 2 * ctx.nk, device=heads.device, dtype=torch.float32)
+        if dmask is None:
+            dmask = torch.zeros(n, h, w, ctx.nk, device=heads.device, dtype=torch.float32)
+        doffset, dmask = K.req(doffset, "grad_offset"), K.req(dmask, "grad_mask")
+        dheads = torch.empty_like(heads)
+        dflow = torch.empty(n, h, w, 2, device=heads.device, dtype=torch.float32)
+        _chk(K, K.lib().crfp_dcn_heads_act_bwd(n * h * w, ctx.nk, int(ctx.repeat), float(ctx.mag), heads.data_ptr(),
+                                               doffset.data_ptr(), dmask.data_ptr(), dheads.data_ptr(), dflow.data_ptr(),
+                                               K.stream()), "dcn_heads_act_bwd")
+        return None, None, None, None, dheads, dflow
+
+
+def dcn_heads_act(K, heads, flow, nk, repeat, mag):
+    return DcnHeadsActFn.apply(K, nk, repeat, mag, heads, flow)
+
+
 # ----------------------------------------------------------------------------------------------- flow_warp
 class FlowWarpFn(torch.autograd.Function):
     """flow_warp(x, flow) (model/CRFP.py:90-130), x (n,h,w,c) with c % 4 == 0, flow (n,h,w,2) = (dx, dy)."""

@@ -450,6 +450,62 @@ static int launch_bwd_weight(long long rows, int h, int w, int cin, int cout, in
   return check_launch();
 }
 
+// ------------------------------------------------------------------------------------------------ DCN heads activation
+// The pointwise tail of DCN_module.forward between the fused offset / mask conv and DCNv2 (model/CRFP.py:337-347):
+//   offset[.., 2k+e] = mag * tanh(heads[.., 2k'+e]) + flow[.., 1-e]     (flow is (dx, dy); offsets are (dy, dx) pairs)
+//   mask[.., k]      = sigmoid(heads[.., noff + k'])
+// nk (offset pair, mask) outputs per pixel; repeat: the heads hold ONE pair and ONE mask per pixel (k' = 0, noff = 2) that
+// the nine taps share (the HR module, dg = 1).  Replaces six ATen kernels (slice copies, tanh, mul, flip, repeat, add,
+// sigmoid) per call and their ten backward kernels.  One thread per (pixel, k): sync-free like the rest of this file.
+__global__ void __launch_bounds__(256) dcn_heads_act_fwd_kernel(long long total, int nk, int repeat, float mag,
+                                                                const float* __restrict__ heads, const float* __restrict__ flow,
+                                                                float* __restrict__ offset, float* __restrict__ mask) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long pix = idx / nk;
+  const int k = (int)(idx - pix * nk);
+  const int kin = repeat ? 0 : k, noff = repeat ? 2 : 2 * nk, ch = repeat ? 3 : 3 * nk;
+  const float* hp = heads + pix * ch;
+  const float fx = flow[pix * 2], fy = flow[pix * 2 + 1];
+  offset[pix * 2 * nk + 2 * k] = mag * tanhf(hp[2 * kin]) + fy;
+  offset[pix * 2 * nk + 2 * k + 1] = mag * tanhf(hp[2 * kin + 1]) + fx;
+  mask[pix * nk + k] = 1.f / (1.f + expf(-hp[noff + kin]));
+}
+
+// dheads (overwritten) and dflow (overwritten): one thread per (pixel, INPUT head index k' ); the thread with k' == 0 also
+// reduces the pixel's flow gradient
+__global__ void __launch_bounds__(256) dcn_heads_act_bwd_kernel(long long total, int nk, int repeat, float mag,
+                                                                const float* __restrict__ heads, const float* __restrict__ doffset,
+                                                                const float* __restrict__ dmask, float* __restrict__ dheads,
+                                                                float* __restrict__ dflow) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int nin = repeat ? 1 : nk;
+  const long long pix = idx / nin;
+  const int kin = (int)(idx - pix * nin);
+  const int noff = 2 * nin, ch = 3 * nin;
+  const float* hp = heads + pix * ch;
+  const float* dop = doffset + pix * 2 * nk;
+  const float* dmp = dmask + pix * nk;
+  float gy = 0.f, gx = 0.f, gm = 0.f;
+  if (repeat) {
+    for (int k = 0; k < nk; ++k) { gy += dop[2 * k]; gx += dop[2 * k + 1]; gm += dmp[k]; }
+  } else {
+    gy = dop[2 * kin]; gx = dop[2 * kin + 1]; gm = dmp[kin];
+  }
+  const float ty = tanhf(hp[2 * kin]), tx = tanhf(hp[2 * kin + 1]);
+  const float sg = 1.f / (1.f + expf(-hp[noff + kin]));
+  dheads[pix * ch + 2 * kin] = gy * mag * (1.f - ty * ty);
+  dheads[pix * ch + 2 * kin + 1] = gx * mag * (1.f - tx * tx);
+  dheads[pix * ch + noff + kin] = gm * sg * (1.f - sg);
+  if (kin == 0) {
+    float fy = 0.f, fx = 0.f;
+    for (int k = 0; k < nk; ++k) { fy += dop[2 * k]; fx += dop[2 * k + 1]; }
+    dflow[pix * 2] = fx;
+    dflow[pix * 2 + 1] = fy;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ DCNv2
 // One thread per (pixel, deformable group, tap).  For its C/dg channels it rebuilds the 4 bilinear corners, forms
 // gcol[c] = sum_co W[k][co] * dout[pix][co] and emits
@@ -813,6 +869,28 @@ extern "C" size_t crfp_conv3x3_bwd_weight_workspace(int n, int h, int w, int cin
   long long prows = chunks * lanes;
   if (chunks_s * lanes_s > prows) prows = chunks_s * lanes_s;
   return (size_t)(prows * (9LL * cin * cout + cout));
+}
+
+extern "C" int crfp_dcn_heads_act_fwd(long long npix, int nk, int repeat, float mag, const float* heads, const float* flow,
+                                      float* offset, float* mask, crfp_stream stream) {
+  if (npix < 0 || nk <= 0) return CRFP_ERR_BAD_SHAPE;
+  if (npix == 0) return CRFP_OK;
+  if (!heads || !flow || !offset || !mask) return CRFP_ERR_NULL;
+  const long long total = npix * nk;
+  CRFP_LAUNCH(dcn_heads_act_fwd_kernel, dim3(blocks_for(total, 256)), dim3(256), (cudaStream_t)stream, total, nk, repeat ? 1 : 0, mag,
+              heads, flow, offset, mask);
+  return check_launch();
+}
+
+extern "C" int crfp_dcn_heads_act_bwd(long long npix, int nk, int repeat, float mag, const float* heads, const float* doffset,
+                                      const float* dmask, float* dheads, float* dflow, crfp_stream stream) {
+  if (npix < 0 || nk <= 0) return CRFP_ERR_BAD_SHAPE;
+  if (npix == 0) return CRFP_OK;
+  if (!heads || !doffset || !dmask || !dheads || !dflow) return CRFP_ERR_NULL;
+  const long long total = npix * (repeat ? 1 : nk);
+  CRFP_LAUNCH(dcn_heads_act_bwd_kernel, dim3(blocks_for(total, 256)), dim3(256), (cudaStream_t)stream, total, nk, repeat ? 1 : 0, mag,
+              heads, doffset, dmask, dheads, dflow);
+  return check_launch();
 }
 
 extern "C" int crfp_dcn_v2_bwd(const crfp_dcn_bwd_desc* d, crfp_stream stream) {

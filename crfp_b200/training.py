@@ -101,15 +101,8 @@ class _Net:
                 pre_offset = pixel_shuffle_nhwc(self.conv(name + ".upsample.upsample_conv", [pre_offset]), 4) * 2.0
             z = self.conv(name + ".conv_fuse", [z, pre_offset], A.ACT_LRELU)
         heads = self.conv_cat([name + ".dcn_offset", name + ".dcn_mask"], [z])     # offset ++ mask, one launch
-        n_off = self.p[name + ".dcn_offset.weight"].shape[0]
-        offset = self.max_mag * torch.tanh(heads[..., :n_off])
-        mask = torch.sigmoid(heads[..., n_off:])
-        fyx = flow.flip(-1)                                                        # (x, y) -> (dy, dx)
-        if repeat:      # one (dy, dx) + one mask per pixel shared by the 9 taps (CRFP.py:341-347; dg == 1)
-            offset = (offset + fyx).repeat(1, 1, 1, 9)
-            mask = mask.repeat(1, 1, 1, 9)
-        else:
-            offset = offset + fyx.repeat(1, 1, 1, offset.shape[-1] // 2)
+        # 10 * tanh + flow / sigmoid (+ the 9-fold repeat of the HR module's single pair): one kernel forward, one backward
+        offset, mask = A.dcn_heads_act(self.K, heads, flow, 9 * dg, repeat, self.max_mag)
         out = A.dcn_v2(self.K, pre_x, offset, mask, self.p[name + ".dcn.weight"], self.p[name + ".dcn.bias"], dg,
                        self._cache.setdefault((name + ".dcn", dg), {}))
         return out, z

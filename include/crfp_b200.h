@@ -563,6 +563,17 @@ int crfp_conv3x3_bwd_weight_batched(int count, const float* const* xs, const flo
  *   col      workspace [n*h*w][K] floats: the modulated columns, rebuilt here and contracted with dout
  *   weight_t optional [cout][K] transpose of `weight`: enables the vector kernel when c == 4*dg and cout % 4 == 0
  */
+/*
+ * The pointwise tail of DCN_module.forward between the fused offset / mask conv and DCNv2 (model/CRFP.py:337-347), forward
+ * and backward, one kernel each (NHWC fp32, npix = n*h*w):
+ *   offset[.., 2k+e] = mag * tanh(heads[.., 2k'+e]) + flow[.., 1-e],  mask[.., k] = sigmoid(heads[.., noff + k'])
+ * nk pairs / masks per pixel out; repeat == 0: heads has 3*nk channels (2*nk offsets then nk masks), k' = k; repeat != 0: heads
+ * has 3 channels (one pair, one mask) shared by the nk taps (the HR module).  bwd overwrites dheads and dflow.
+ */
+int crfp_dcn_heads_act_fwd(long long npix, int nk, int repeat, float mag, const float* heads, const float* flow, float* offset,
+                           float* mask, crfp_stream stream);
+int crfp_dcn_heads_act_bwd(long long npix, int nk, int repeat, float mag, const float* heads, const float* doffset,
+                           const float* dmask, float* dheads, float* dflow, crfp_stream stream);
 typedef struct {
   int32_t n, h, w;
   int32_t c, cout, dg;

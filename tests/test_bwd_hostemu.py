@@ -33,7 +33,7 @@ def test_emulation_exports_every_training_symbol():
     h = hostemu.lib()
     for name in L.TRAIN_SYMBOLS:
         assert hasattr(h, name)
-    assert len(L.TRAIN_SYMBOLS) == 13
+    assert len(L.TRAIN_SYMBOLS) == 15
     # argument validation returns a status, never crashes
     assert h.crfp_conv3x3_bwd_data(1, 0, 4, 4, 4, 4, 0, None, None, None, None) == -1
     assert h.crfp_conv3x3_bwd_data(1, 4, 4, 4, 4, 6, 4, None, None, None, None) == -1      # slice outside cin_total
@@ -242,3 +242,32 @@ def test_opt_in_wgrad_variants_in_a_fresh_process():
                           "-p", "no:cacheprovider"], env=env, capture_output=True, text=True,
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.parametrize("nk,repeat", [(72, False), (9, True)])
+def test_dcn_heads_activation_matches_the_torch_formulation(nk, repeat):
+    """crfp_dcn_heads_act_fwd / _bwd == max_mag * tanh(offset heads) + flow.flip(-1) (repeated), sigmoid(mask heads) and
+    their autograd (model/CRFP.py:337-347)."""
+    from crfp_b200 import autograd as A
+    K = hostemu.HostEmuKernelSet()
+    g = _g(41)
+    n, h, w = 2, 5, 7
+    ch = 3 if repeat else 3 * nk
+    heads = torch.randn(n, h, w, ch, generator=g).requires_grad_()
+    flow = (torch.randn(n, h, w, 2, generator=g) * 3).requires_grad_()
+    noff = 2 if repeat else 2 * nk
+    off_ref = 10.0 * torch.tanh(heads[..., :noff])
+    msk_ref = torch.sigmoid(heads[..., noff:])
+    fyx = flow.flip(-1)
+    if repeat:
+        off_ref = (off_ref + fyx).repeat(1, 1, 1, nk)
+        msk_ref = msk_ref.repeat(1, 1, 1, nk)
+    else:
+        off_ref = off_ref + fyx.repeat(1, 1, 1, nk)
+    do, dm = torch.randn(off_ref.shape, generator=g), torch.randn(msk_ref.shape, generator=g)
+    rg = torch.autograd.grad([off_ref, msk_ref], [heads, flow], [do, dm])
+    h2, f2 = heads.detach().clone().requires_grad_(), flow.detach().clone().requires_grad_()
+    off, msk = A.dcn_heads_act(K, h2, f2, nk, repeat, 10.0)
+    assert (off - off_ref).abs().max().item() < 1e-5 and (msk - msk_ref).abs().max().item() < 1e-6
+    got = torch.autograd.grad([off, msk], [h2, f2], [do, dm])
+    assert (got[0] - rg[0]).abs().max().item() < 2e-5 and (got[1] - rg[1]).abs().max().item() < 1e-4
