@@ -249,28 +249,43 @@ __global__ void __launch_bounds__(128) conv_wgrad_thin_kernel(const WgThin A) {
   float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);
   const bool do_bias = ky == 1 && A.db != nullptr;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (px < A.w) {
-    for (long long rr = r0; rr < r1; ++rr) {
-      const int ent = (int)(rr / A.rows);
-      const long long r = rr - (long long)ent * A.rows;
+  if (px < A.w && r0 < r1) {
+    // one row of operands is fetched while the previous one is consumed (the loop is latency bound otherwise: four dependent
+    // loads, then 48 FMAs); loads outside the image are predicated to zero instead of skipping the row
+    const bool vecx = A.vecx != 0, vecg = A.vecg != 0;
+    struct RowOps { float4 g, xm, xc, xp; };
+    auto load_row = [&](int ent, int r, int y) {
+      RowOps o;
       const float* __restrict__ xe = A.x[ent];
-      const float4 gv = wg_ld4(A.g[ent] + (r * A.w + px) * A.cout, A.cout, A.vecg != 0);
-      if (do_bias) { gsum.x += gv.x; gsum.y += gv.y; gsum.z += gv.z; gsum.w += gv.w; }
-      float4 xm, xc, xp;
+      o.g = wg_ld4(A.g[ent] + ((long long)r * A.w + px) * A.cout, A.cout, vecg);
       if (A.flat) {
-        const float* xb = xe + (r * A.w + px) * A.cin + ky * 12;
-        xm = wg_ld4(xb, 4, A.vecx != 0);
-        xc = wg_ld4(xb + 4, 4, A.vecx != 0);
-        xp = wg_ld4(xb + 8, 4, A.vecx != 0);
+        const float* xb = xe + ((long long)r * A.w + px) * A.cin + ky * 12;
+        o.xm = wg_ld4(xb, 4, vecx);
+        o.xc = wg_ld4(xb + 4, 4, vecx);
+        o.xp = wg_ld4(xb + 8, 4, vecx);
       } else {
-        const int yi = (int)(r % A.h) + ky - 1;
-        if (yi < 0 || yi >= A.h) continue;
-        const float* xr = xe + ((r + ky - 1) * A.w + px) * A.cin + A.cq;
-        xm = px > 0 ? wg_ld4(xr - A.cin, A.nci, A.vecx != 0) : zero;
-        xc = wg_ld4(xr, A.nci, A.vecx != 0);
-        xp = px + 1 < A.w ? wg_ld4(xr + A.cin, A.nci, A.vecx != 0) : zero;
+        const int yi = y + ky - 1;
+        const bool ok = yi >= 0 && yi < A.h;
+        const float* xr = xe + ((long long)(r + ky - 1) * A.w + px) * A.cin + A.cq;
+        o.xm = (ok && px > 0) ? wg_ld4(xr - A.cin, A.nci, vecx) : zero;
+        o.xc = ok ? wg_ld4(xr, A.nci, vecx) : zero;
+        o.xp = (ok && px + 1 < A.w) ? wg_ld4(xr + A.cin, A.nci, vecx) : zero;
       }
-      wg_fma48(acc, xm, xc, xp, gv);
+      return o;
+    };
+    int ent = (int)(r0 / A.rows);
+    int r = (int)(r0 - (long long)ent * A.rows);
+    int y = r % A.h;
+    RowOps cur = load_row(ent, r, y);
+    for (long long rr = r0; rr < r1; ++rr) {
+      int en = ent, rn = r + 1, yn = y + 1;
+      if (yn == A.h) yn = 0;
+      if (rn == A.rows) { rn = 0; ++en; }
+      RowOps nxt = cur;
+      if (rr + 1 < r1) nxt = load_row(en, rn, yn);
+      if (do_bias) { gsum.x += cur.g.x; gsum.y += cur.g.y; gsum.z += cur.g.z; gsum.w += cur.g.w; }
+      wg_fma48(acc, cur.xm, cur.xc, cur.xp, cur.g);
+      cur = nxt; ent = en; r = rn; y = yn;
     }
   }
   // CTA reduction: butterfly inside the warp, 4 warps through shared memory, 52 atomics per CTA
