@@ -8,7 +8,9 @@ A "step" is one forward of this rank's synthetic clip(s) through the drop-in mod
   workload "V7"     : LR 64x112, t=7 (configs[0], the reference's CPU-runnable case)
 `value`    = frames/s with the clip already resident in HBM (CUDA events, max over ranks).
 `e2e`      = frames/s through the public API from HOST buffers: pinned lrs + fovea patches + coords H2D, forward,
-             output frames D2H, all inside the timed region; event-timed AND wall-clock-timed.
+             every output frame D2H into pinned memory as 8-bit RGB (quantised on the device with the reference's own
+             (sr*255).clip(0,255).round()), all inside the timed region; event-timed AND wall-clock-timed.
+`e2e_f32`  = the same with fp32 frames (4x the D2H bytes; on an 8-GPU box bound by the host side of the D2H stream).
 `roofline` = the dominant kernel (conv_tc3_ws, per-frame launch mix) and the align kernel (DCNv2 @L1, the kernel
              BASELINE.json's metric names), each timed alone through the C ABI with CUDA events; `traffic` is read from the
              committed ncu DRAM-byte capture under profiles/ (null when there is none for the workload).
