@@ -103,8 +103,9 @@ class _Net:
         heads = self.conv_cat([name + ".dcn_offset", name + ".dcn_mask"], [z])     # offset ++ mask, one launch
         # 10 * tanh + flow / sigmoid (+ the 9-fold repeat of the HR module's single pair): one kernel forward, one backward
         offset, mask = A.dcn_heads_act(self.K, heads, flow, 9 * dg, repeat, self.max_mag)
-        out = A.dcn_v2(self.K, pre_x, offset, mask, self.p[name + ".dcn.weight"], self.p[name + ".dcn.bias"], dg,
-                       self._cache.setdefault((name + ".dcn", dg), {}))
+        dcache = self._cache.setdefault((name + ".dcn", dg), {})
+        dcache["hint"] = flow          # sampling-window hint of the tensor-core align op (values do not depend on it)
+        out = A.dcn_v2(self.K, pre_x, offset, mask, self.p[name + ".dcn.weight"], self.p[name + ".dcn.bias"], dg, dcache)
         return out, z
 
     # ---- FNet.forward (model/CRFP.py:797-814) on pairs (x1, x2) NHWC 3-channel

@@ -472,3 +472,21 @@ def test_deferred_weight_gradients_equal_the_per_frame_ones(A):
     assert tr.defer_wgrad
     ls = [tr.step(*args).item() for _ in range(5)]
     assert tr.use_graphs and len(tr._graphs) == 1 and ls[-1] < ls[0]
+
+
+def test_training_dcn_forward_on_the_tensor_core_align_kernel(A):
+    """KernelSet.dcn_v2 (L1 shape) through crfp_dcn_v2_tc3_fwd == the fp32 SIMT op, with and without the flow hint."""
+    g = _g(51)
+    K, K2 = A.KernelSet(), A.KernelSet()
+    K2.train_tc = False
+    n, h, w = 2, 21, 37
+    x = torch.randn(n, h, w, 32, generator=g).cuda()
+    flow = (torch.randn(n, h, w, 2, generator=g) * 3).cuda()
+    off = (torch.randn(n, h, w, 144, generator=g) * 4).cuda() + flow.flip(-1).repeat(1, 1, 1, 72)
+    msk = torch.rand(n, h, w, 72, generator=g).cuda()
+    wt = (torch.randn(32, 32, 3, 3, generator=g) * 0.05).cuda()
+    b = (torch.randn(32, generator=g) * 0.05).cuda()
+    ref = K2.dcn_v2(x, off, msk, wt, b, 8, {})
+    for hint in (None, flow):
+        out = K.dcn_v2(x, off, msk, wt, b, 8, {"hint": hint} if hint is not None else {})
+        assert (out - ref).abs().max().item() < 1e-4
