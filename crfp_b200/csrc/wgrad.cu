@@ -61,7 +61,7 @@ struct WgTile {
 };
 
 template <bool FLAT>
-__global__ void __launch_bounds__(192, 2) conv_wgrad_tile_kernel(const WgTile A) {
+__global__ void __launch_bounds__(192, FLAT ? 2 : 3) conv_wgrad_tile_kernel(const WgTile A) {
   constexpr int SEG = FLAT ? 32 : 64;
   constexpr int XPX = FLAT ? SEG : SEG + 2;   // pixels per x tile row
   constexpr int XCH = FLAT ? 96 : 32;         // channels per pixel in the x tile
@@ -348,7 +348,8 @@ static int wg_tile_workers(long long rows, int w, int cin, int cout, int taps) {
   const int seg = taps == 9 ? 64 : 32;
   const long long nchunks = rows * ((w + seg - 1) / seg);
   const int gx = (taps == 9 ? (cin + 31) / 32 : 1) * ((cout + 31) / 32);
-  long long workers = (2LL * sm_count() + gx - 1) / gx;
+  static const int per_sm = getenv("CRFP_WGRAD_CTAS") ? atoi(getenv("CRFP_WGRAD_CTAS")) : 3;   // CTAs per SM of the tile kernel (measured: 3 -> 31.7 ms, 2 -> 32.3 ms per V7 step)
+  long long workers = ((long long)(taps == 9 ? per_sm : 2) * sm_count() + gx - 1) / gx;
   if (workers > nchunks) workers = nchunks;
   if (workers < 1) workers = 1;
   return (int)workers;
