@@ -221,6 +221,8 @@ SYMBOLS = {
     "crfp_conv3x3_bwd_weight_batched": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)] + [C.c_int] * 7 +
                                         [C.c_void_p] * 3 + [C.c_size_t, C.c_void_p]),
     "crfp_dcn_v2_bwd_workspace": (C.c_size_t, [C.c_int] * 5),
+    "crfp_fovea_blend_fwd": (C.c_int, [C.c_longlong, C.c_int] + [C.c_void_p] * 5),
+    "crfp_fovea_blend_bwd": (C.c_int, [C.c_longlong, C.c_int] + [C.c_void_p] * 6),
     "crfp_dcn_heads_act_fwd": (C.c_int, [C.c_longlong, C.c_int, C.c_int, C.c_float] + [C.c_void_p] * 5),
     "crfp_dcn_heads_act_bwd": (C.c_int, [C.c_longlong, C.c_int, C.c_int, C.c_float] + [C.c_void_p] * 6),
     "crfp_dcn_v2_bwd": (C.c_int, [C.POINTER(DcnBwdDesc), C.c_void_p]),
@@ -238,7 +240,7 @@ SYMBOLS = {
 }
 
 # the training entry points alone: also exported by the host-emulation build the CPU tests use (tests/tools/hostemu)
-TRAIN_SYMBOLS = [k for k in SYMBOLS if "_bwd" in k or k in ("crfp_adam_step", "crfp_dcn_heads_act_fwd")]
+TRAIN_SYMBOLS = [k for k in SYMBOLS if "_bwd" in k or k in ("crfp_adam_step", "crfp_dcn_heads_act_fwd", "crfp_fovea_blend_fwd")]
 SPYNET_SYMBOLS = ["crfp_conv_kxk_fwd", "crfp_resize_bilinear_ac", "crfp_channel_affine"]
 
 _lib = None

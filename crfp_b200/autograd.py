@@ -445,6 +445,39 @@ def dcn_heads_act(K, heads, flow, nk, repeat, mag):
     return DcnHeadsActFn.apply(K, nk, repeat, mag, heads, flow)
 
 
+# ----------------------------------------------------------------------------------------------- fovea blend
+class FoveaBlendFn(torch.autograd.Function):
+    """lrelu(mask * f + (1 - mask) * s, 0.1) (model/CRFP.py:1672-1675); mask (n,H,W,1) carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, K, f, s, mask):
+        f, s, mask = K.req(f.detach(), "f"), K.req(s.detach(), "s"), K.req(mask.detach(), "mask")
+        n, h, w, c = f.shape
+        if tuple(s.shape) != (n, h, w, c) or mask.numel() != n * h * w or c % 4:
+            raise L.CrfpError("fovea_blend: shapes do not match")
+        out = torch.empty_like(f)
+        _chk(K, K.lib().crfp_fovea_blend_fwd(n * h * w, c, f.data_ptr(), s.data_ptr(), mask.data_ptr(), out.data_ptr(), K.stream()),
+             "fovea_blend_fwd")
+        ctx.K = K
+        ctx.save_for_backward(out, mask)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        K = ctx.K
+        out, mask = ctx.saved_tensors
+        dout = K.req(dout, "grad_output")
+        n, h, w, c = out.shape
+        df, ds = torch.empty_like(out), torch.empty_like(out)
+        _chk(K, K.lib().crfp_fovea_blend_bwd(n * h * w, c, dout.data_ptr(), out.data_ptr(), mask.data_ptr(), df.data_ptr(),
+                                             ds.data_ptr(), K.stream()), "fovea_blend_bwd")
+        return None, df, ds, None
+
+
+def fovea_blend(K, f, s, mask):
+    return FoveaBlendFn.apply(K, f, s, mask)
+
+
 # ----------------------------------------------------------------------------------------------- flow_warp
 class FlowWarpFn(torch.autograd.Function):
     """flow_warp(x, flow) (model/CRFP.py:90-130), x (n,h,w,c) with c % 4 == 0, flow (n,h,w,2) = (dx, dy)."""

@@ -450,6 +450,37 @@ static int launch_bwd_weight(long long rows, int h, int w, int cin, int cout, in
   return check_launch();
 }
 
+// ------------------------------------------------------------------------------------------------ fovea blend
+// S' = lrelu(m * F + (1 - m) * S, 0.1) (model/CRFP.py:1672-1675; m = the (n,H,W,1) fovea mask) and its backward: one kernel each
+// instead of five / six pointwise ATen kernels over HR planes.  One thread per (pixel, channel quad); C % 4 == 0.
+__global__ void __launch_bounds__(256) fovea_blend_fwd_kernel(long long total4, int cq, const float* __restrict__ f,
+                                                              const float* __restrict__ s, const float* __restrict__ m,
+                                                              float* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total4) return;
+  const float mk = m[idx / cq], mi = 1.f - mk;
+  const float4 fv = *reinterpret_cast<const float4*>(f + idx * 4), sv = *reinterpret_cast<const float4*>(s + idx * 4);
+  float4 o;
+  o.x = mk * fv.x + mi * sv.x; o.y = mk * fv.y + mi * sv.y; o.z = mk * fv.z + mi * sv.z; o.w = mk * fv.w + mi * sv.w;
+  o.x = o.x > 0.f ? o.x : 0.1f * o.x; o.y = o.y > 0.f ? o.y : 0.1f * o.y;
+  o.z = o.z > 0.f ? o.z : 0.1f * o.z; o.w = o.w > 0.f ? o.w : 0.1f * o.w;
+  *reinterpret_cast<float4*>(out + idx * 4) = o;
+}
+
+__global__ void __launch_bounds__(256) fovea_blend_bwd_kernel(long long total4, int cq, const float* __restrict__ dout,
+                                                              const float* __restrict__ out, const float* __restrict__ m,
+                                                              float* __restrict__ df, float* __restrict__ ds) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total4) return;
+  const float mk = m[idx / cq], mi = 1.f - mk;
+  const float4 dv = *reinterpret_cast<const float4*>(dout + idx * 4), ov = *reinterpret_cast<const float4*>(out + idx * 4);
+  float4 g;
+  g.x = ov.x > 0.f ? dv.x : 0.1f * dv.x; g.y = ov.y > 0.f ? dv.y : 0.1f * dv.y;
+  g.z = ov.z > 0.f ? dv.z : 0.1f * dv.z; g.w = ov.w > 0.f ? dv.w : 0.1f * dv.w;
+  *reinterpret_cast<float4*>(df + idx * 4) = make_float4(g.x * mk, g.y * mk, g.z * mk, g.w * mk);
+  *reinterpret_cast<float4*>(ds + idx * 4) = make_float4(g.x * mi, g.y * mi, g.z * mi, g.w * mi);
+}
+
 // ------------------------------------------------------------------------------------------------ DCN heads activation
 // The pointwise tail of DCN_module.forward between the fused offset / mask conv and DCNv2 (model/CRFP.py:337-347):
 //   offset[.., 2k+e] = mag * tanh(heads[.., 2k'+e]) + flow[.., 1-e]     (flow is (dx, dy); offsets are (dy, dx) pairs)
@@ -869,6 +900,29 @@ extern "C" size_t crfp_conv3x3_bwd_weight_workspace(int n, int h, int w, int cin
   long long prows = chunks * lanes;
   if (chunks_s * lanes_s > prows) prows = chunks_s * lanes_s;
   return (size_t)(prows * (9LL * cin * cout + cout));
+}
+
+extern "C" int crfp_fovea_blend_fwd(long long npix, int c, const float* f, const float* s, const float* mask, float* out,
+                                    crfp_stream stream) {
+  if (npix < 0 || c <= 0 || c % 4) return CRFP_ERR_BAD_SHAPE;
+  if (npix == 0) return CRFP_OK;
+  if (!f || !s || !mask || !out) return CRFP_ERR_NULL;
+  if (!aligned16(f) || !aligned16(s) || !aligned16(out)) return CRFP_ERR_BAD_SHAPE;
+  const long long total4 = npix * (c / 4);
+  CRFP_LAUNCH(fovea_blend_fwd_kernel, dim3(blocks_for(total4, 256)), dim3(256), (cudaStream_t)stream, total4, c / 4, f, s, mask, out);
+  return check_launch();
+}
+
+extern "C" int crfp_fovea_blend_bwd(long long npix, int c, const float* dout, const float* out, const float* mask, float* df,
+                                    float* ds, crfp_stream stream) {
+  if (npix < 0 || c <= 0 || c % 4) return CRFP_ERR_BAD_SHAPE;
+  if (npix == 0) return CRFP_OK;
+  if (!dout || !out || !mask || !df || !ds) return CRFP_ERR_NULL;
+  if (!aligned16(dout) || !aligned16(out) || !aligned16(df) || !aligned16(ds)) return CRFP_ERR_BAD_SHAPE;
+  const long long total4 = npix * (c / 4);
+  CRFP_LAUNCH(fovea_blend_bwd_kernel, dim3(blocks_for(total4, 256)), dim3(256), (cudaStream_t)stream, total4, c / 4, dout, out, mask,
+              df, ds);
+  return check_launch();
 }
 
 extern "C" int crfp_dcn_heads_act_fwd(long long npix, int nk, int repeat, float mag, const float* heads, const float* flow,

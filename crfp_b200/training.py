@@ -12,7 +12,6 @@ targets; the reference's named training bottlenecks (conv, DCN, flow_warp forwar
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 
 from . import autograd as A
 
@@ -161,7 +160,7 @@ class _Net:
             q = pixel_shuffle_nhwc(self.conv("upsample_post.upsample_conv", [prop], A.ACT_LRELU), 4)
             S = self.res_blocks("forward_resblocks_3", [q, z_hr])
         Fz = self.conv("conv_tttf", [S, x_hr_cur])
-        S = F.leaky_relu(mkf * Fz + (1.0 - mkf) * S, 0.1)
+        S = A.fovea_blend(self.K, Fz, S, mkf)          # lrelu(m * Fz + (1 - m) * S, 0.1), one kernel each way
         out = self.conv("conv_last", [S]) + lr_up8
         return out, (S, torch.cat(feats, dim=-1))
 

@@ -570,6 +570,11 @@ int crfp_conv3x3_bwd_weight_batched(int count, const float* const* xs, const flo
  * nk pairs / masks per pixel out; repeat == 0: heads has 3*nk channels (2*nk offsets then nk masks), k' = k; repeat != 0: heads
  * has 3 channels (one pair, one mask) shared by the nk taps (the HR module).  bwd overwrites dheads and dflow.
  */
+/* Fovea blend of the training forward: out = lrelu(mask * f + (1 - mask) * s, 0.1), mask (npix) one value per pixel, f / s / out
+ * (npix, c) NHWC fp32 with c % 4 == 0 (model/CRFP.py:1672-1675); bwd: df = g * mask, ds = g * (1 - mask), g = dout * lrelu'(out). */
+int crfp_fovea_blend_fwd(long long npix, int c, const float* f, const float* s, const float* mask, float* out, crfp_stream stream);
+int crfp_fovea_blend_bwd(long long npix, int c, const float* dout, const float* out, const float* mask, float* df, float* ds,
+                         crfp_stream stream);
 int crfp_dcn_heads_act_fwd(long long npix, int nk, int repeat, float mag, const float* heads, const float* flow, float* offset,
                            float* mask, crfp_stream stream);
 int crfp_dcn_heads_act_bwd(long long npix, int nk, int repeat, float mag, const float* heads, const float* doffset,

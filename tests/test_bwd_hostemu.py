@@ -33,7 +33,7 @@ def test_emulation_exports_every_training_symbol():
     h = hostemu.lib()
     for name in L.TRAIN_SYMBOLS:
         assert hasattr(h, name)
-    assert len(L.TRAIN_SYMBOLS) == 15
+    assert len(L.TRAIN_SYMBOLS) == 17
     # argument validation returns a status, never crashes
     assert h.crfp_conv3x3_bwd_data(1, 0, 4, 4, 4, 4, 0, None, None, None, None) == -1
     assert h.crfp_conv3x3_bwd_data(1, 4, 4, 4, 4, 6, 4, None, None, None, None) == -1      # slice outside cin_total
@@ -271,3 +271,22 @@ def test_dcn_heads_activation_matches_the_torch_formulation(nk, repeat):
     assert (off - off_ref).abs().max().item() < 1e-5 and (msk - msk_ref).abs().max().item() < 1e-6
     got = torch.autograd.grad([off, msk], [h2, f2], [do, dm])
     assert (got[0] - rg[0]).abs().max().item() < 2e-5 and (got[1] - rg[1]).abs().max().item() < 1e-4
+
+
+def test_fovea_blend_matches_the_torch_formulation():
+    """crfp_fovea_blend_fwd / _bwd == F.leaky_relu(m * f + (1 - m) * s, 0.1) and its autograd (model/CRFP.py:1672-1675)."""
+    from crfp_b200 import autograd as A
+    K = hostemu.HostEmuKernelSet()
+    g = _g(43)
+    n, h, w, c = 2, 9, 11, 4
+    f = torch.randn(n, h, w, c, generator=g).requires_grad_()
+    s = torch.randn(n, h, w, c, generator=g).requires_grad_()
+    m = (torch.rand(n, h, w, 1, generator=g) > 0.6).float()
+    ref = F.leaky_relu(m * f + (1.0 - m) * s, 0.1)
+    dy = torch.randn(ref.shape, generator=g)
+    rg = torch.autograd.grad(ref, [f, s], dy)
+    f2, s2 = f.detach().clone().requires_grad_(), s.detach().clone().requires_grad_()
+    out = A.fovea_blend(K, f2, s2, m)
+    assert (out - ref).abs().max().item() < 1e-6
+    got = torch.autograd.grad(out, [f2, s2], dy)
+    assert (got[0] - rg[0]).abs().max().item() < 1e-6 and (got[1] - rg[1]).abs().max().item() < 1e-6
