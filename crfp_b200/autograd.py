@@ -224,14 +224,25 @@ class WgradDeferral:
         K = self.K
         lib, st = K.lib(), K.stream()
         layers, self.layers, self.armed = self.layers, [], False
-        for cache, c_list, need_w, need_b in layers:
+        if not layers:
+            return
+        # ONE zero fill for every layer's dw / db accumulator (views of a flat buffer) instead of two fills per layer
+        sizes = []
+        for cache, c_list, _, _ in layers:
+            cout = cache["wg_pending"][0][1].shape[-1]
+            sizes.append((9 * sum(c_list) * cout, cout))
+        dev0 = layers[0][0]["wg_pending"][0][1].device
+        flat = torch.zeros(sum(a + b + (-(a + b)) % 4 for a, b in sizes), device=dev0, dtype=torch.float32)
+        pos = 0
+        for (cache, c_list, need_w, need_b), (nw, nb) in zip(layers, sizes):
             pend = cache.pop("wg_pending")
             g0 = pend[0][1]
             n, h, w, cout = g0.shape
             cin = sum(c_list)
             dev = g0.device
-            dw = torch.zeros(9, cin, cout, device=dev, dtype=torch.float32)
-            dbt = torch.zeros(cout, device=dev, dtype=torch.float32)
+            dw = flat[pos:pos + nw].view(9, cin, cout)
+            dbt = flat[pos + nw:pos + nw + nb]
+            pos += nw + nb + (-(nw + nb)) % 4            # keep every accumulator 16-byte aligned
             cnt = len(pend)
             gs = (C.c_void_p * cnt)(*[g.data_ptr() for _, g in pend])
             off = 0
